@@ -1,0 +1,1175 @@
+// ORACLE (test infrastructure, not product code).
+//
+// CPU restatement of MoRiBS-PIMC's sampling hot path: per-bead potential
+// sums, tabulated/analytic pair potentials, rotational density look-ups,
+// translational and rotational Metropolis moves and the per-slice estimator
+// sums.  Every function cites the reference file:line it follows.  The
+// Fortran leaves are reached through the gfortran-ABI symbols of
+// oracle/fortran_shim.cpp.  Pinned against the reference's own C++ objects
+// (oracle/_ref/libpimcref.so) by tests/test_oracle_vs_ref.py; the Fortran
+// leaves themselves are "parity unpinned" (see fortran_shim.cpp).
+//
+// Build: g++ -O2 -ffp-contract=off (oracle/Makefile).
+#include "pimc_oracle.h"
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <array>
+
+extern "C" {
+void rotden_(double *, double *, double *, double *, double *, double *, double *, double *, double *, int *);
+void vcord_(double *, double *, double *, double *, int *, int *, int *, double *, double *, double *,
+            double *, double *, double *, double *, double *, double *, double *, int *);
+void caleng_(double *, double *, double *, double *, double *);
+void vspher_(double *, double *);
+void rsrot_(double *, double *, double *, double *, double *, double *, int *, double *, double *, double *);
+void rsline_(double *, double *, double *, double *, double *);
+void oracle_set_vspher_table(const double *);
+extern int oracle_last_rotden_index, oracle_last_vcord_index;
+}
+
+namespace {
+
+// mc_const.h:12-15, mc_confg.h:60
+const double HBAR = 1.05457266, AMU = 1.6605402, K_B = 1.380658, WNO2K = 0.6950356;
+const double RZERO = 1.0e-10;
+const int PHI = 0, CTH = 1, CHI = 2;
+const int MCMOLEC = 0, MCMULTI = 1, MCROTAT = 2;
+// mc_estim.cc:25-30
+const int MC_BINSR = 300, MC_BINST = 50, MC_BINSC = 100;
+const double MAX_RADIUS = 15.0, MIN_RADIUS = 0.0;
+
+// ---- cubic spline, mc_utils.cc:112-154 ------------------------------------
+void spline(const double *x, const double *y, int n, double yp1, double ypn, double *y2)
+{
+   std::vector<double> u(n);
+   double p, qn, sig, un;
+   if (yp1 > 0.99e30) y2[0] = u[0] = 0.0;
+   else {
+      y2[0] = -0.5;
+      u[0] = (3. / (x[1] - x[0])) * ((y[1] - y[0]) / (x[1] - x[0]) - yp1);
+   }
+   for (int i = 1; i < (n - 1); i++) {
+      sig = (x[i] - x[i - 1]) / (x[i + 1] - x[i - 1]);
+      p = sig * y2[i - 1] + 2.;
+      y2[i] = (sig - 1.) / p;
+      u[i] = (y[i + 1] - y[i]) / (x[i + 1] - x[i]) - (y[i] - y[i - 1]) / (x[i] - x[i - 1]);
+      u[i] = (6. * u[i] / (x[i + 1] - x[i - 1]) - sig * u[i - 1]) / p;
+   }
+   if (ypn > 0.99e30) qn = un = 0.;
+   else {
+      qn = .5;
+      un = (3. / (x[n - 1] - x[n - 2])) * (ypn - (y[n - 1] - y[n - 2]) / (x[n - 1] - x[n - 2]));
+   }
+   y2[n - 1] = (un - qn * u[n - 2]) / (qn * y2[n - 2] + 1.);
+   for (int k = n - 2; k >= 0; k--) y2[k] = y2[k] * y2[k + 1] + u[k];
+}
+// mc_utils.cc:188-201
+void init_spline(const double *grid, const double *data, double *sdata, int n)
+{
+   double drl = grid[1] - grid[0];
+   double dpl = (data[1] - data[0]) / drl;
+   double drr = grid[n - 1] - grid[n - 2];
+   double dpr = (data[n - 1] - data[n - 2]) / drr;
+   spline(grid, data, n, dpl, dpr, sdata);
+}
+// mc_utils.cc:156-186
+double splint(const double *xa, const double *ya, const double *y2a, int n, double x, int *klo_out)
+{
+   int klo = 0, khi = n - 1;
+   while (khi - klo > 1) {
+      int k = (khi + klo) >> 1;
+      if (xa[k] > x) khi = k; else klo = k;
+   }
+   double h = xa[khi] - xa[klo];
+   if (klo_out) *klo_out = klo;
+   double a = (xa[khi] - x) / h;
+   double b = (x - xa[klo]) / h;
+   return a * ya[klo] + b * ya[khi] + ((a * a * a - a) * y2a[klo] + (b * b * b - b) * y2a[khi]) * (h * h) / 6.;
+}
+
+// ---- MRG32k3a in the reference's double arithmetic, rngstream.cc:21-126,242-265
+const double m1 = 4294967087.0, m2 = 4294944443.0, norm = 1.0 / (m1 + 1.0);
+const double a12 = 1403580.0, a13n = 810728.0, a21 = 527612.0, a23n = 1370589.0;
+const double two17 = 131072.0, two53 = 9007199254740992.0;
+const double A1p127[3][3] = {{2427906178.0, 3580155704.0, 949770784.0},
+                             {226153695.0, 1230515664.0, 3580155704.0},
+                             {1988835001.0, 986791581.0, 1230515664.0}};
+const double A2p127[3][3] = {{1464411153.0, 277697599.0, 1610723613.0},
+                             {32183930.0, 1464411153.0, 1022607788.0},
+                             {2824425944.0, 32183930.0, 2093834863.0}};
+double MultModM(double a, double s, double c, double m)
+{
+   double v = a * s + c;
+   long a1;
+   if (v >= two53 || v <= -two53) {
+      a1 = (long)(a / two17); a -= a1 * two17;
+      v = a1 * s;
+      a1 = (long)(v / m); v -= a1 * m;
+      v = v * two17 + a * s + c;
+   }
+   a1 = (long)(v / m);
+   if ((v -= a1 * m) < 0.0) return v += m; else return v;
+}
+void MatVecModM(const double A[3][3], const double s[3], double v[3], double m)
+{
+   double x[3];
+   for (int i = 0; i < 3; ++i) {
+      x[i] = MultModM(A[i][0], s[0], 0.0, m);
+      x[i] = MultModM(A[i][1], s[1], x[i], m);
+      x[i] = MultModM(A[i][2], s[2], x[i], m);
+   }
+   for (int i = 0; i < 3; ++i) v[i] = x[i];
+}
+void MatMatModM(const double A[3][3], const double B[3][3], double C[3][3], double m)
+{
+   double V[3], W[3][3];
+   for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) V[j] = B[j][i];
+      MatVecModM(A, V, V, m);
+      for (int j = 0; j < 3; ++j) W[j][i] = V[j];
+   }
+   for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) C[i][j] = W[i][j];
+}
+// state of the s-th stream = (A^(2^127))^s * seed, by binary powering of the jump matrix
+void mrg_stream_state(const unsigned long *seed6, long s, double *st)
+{
+   double B1[3][3], B2[3][3], W1[3][3], W2[3][3];
+   for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+      W1[i][j] = A1p127[i][j]; W2[i][j] = A2p127[i][j];
+      B1[i][j] = B2[i][j] = (i == j) ? 1.0 : 0.0;
+   }
+   long n = s;
+   while (n > 0) {
+      if (n % 2) { MatMatModM(W1, B1, B1, m1); MatMatModM(W2, B2, B2, m2); }
+      MatMatModM(W1, W1, W1, m1); MatMatModM(W2, W2, W2, m2);
+      n /= 2;
+   }
+   double s1[3] = {(double)seed6[0], (double)seed6[1], (double)seed6[2]};
+   double s2[3] = {(double)seed6[3], (double)seed6[4], (double)seed6[5]};
+   MatVecModM(B1, s1, st, m1);
+   MatVecModM(B2, s2, st + 3, m2);
+}
+// rngstream.cc:242-265 (anti == false)
+double mrg_u01(double *Cg)
+{
+   long k;
+   double p1, p2;
+   p1 = a12 * Cg[1] - a13n * Cg[0];
+   k = (long)(p1 / m1); p1 -= k * m1; if (p1 < 0.0) p1 += m1;
+   Cg[0] = Cg[1]; Cg[1] = Cg[2]; Cg[2] = p1;
+   p2 = a21 * Cg[5] - a23n * Cg[3];
+   k = (long)(p2 / m2); p2 -= k * m2; if (p2 < 0.0) p2 += m2;
+   Cg[3] = Cg[4]; Cg[4] = Cg[5]; Cg[5] = p2;
+   return (p1 > p2) ? (p1 - p2) * norm : (p1 - p2 + m1) * norm;
+}
+// mc_randg.cc:138-150 with explicit uniforms
+inline double gauss_u(double alpha, double r1, double r2)
+{
+   double x1 = sqrt(-log(r1)) * cos(2.0 * M_PI * r2);
+   return x1 / sqrt(alpha);
+}
+
+} // namespace
+
+struct orc {
+   orc_system_t sys;
+   int N, P, Q, R;
+   int offset_atom[3];                // first global atom of each type
+   double lambda[2], beta, tau, rottau;
+   int imtype, bstype;
+   std::vector<int> mctype;           // MCType
+   // tables
+   int n1d = 0; std::vector<double> g1d, v1d, y2_1d; double alpha = 0, unode = 0, c6 = 0;
+   int rs2d = 0, cs2d = 0; double dr2d = 0, dc2d = 0; std::vector<double> rg2d, cg2d, v2d;
+   int rg3 = 0, thg3 = 0, chg3 = 0; double rvmin = 0, rvmax = 0, rvstep = 0; const double *v3d = nullptr;
+   int nrot = 0; std::vector<double> rgrid, rdens, rderv, resqr, rdens2, rderv2, resqr2;
+   const double *rho3 = nullptr, *erot3 = nullptr, *esq3 = nullptr;
+   // state, reference layout [dim][atom*P+it]
+   std::vector<double> coords[3], angles[3], cosine[3], newc[3];
+   std::vector<int> pindex, rindex;
+   double mctotal[2][3], mcaccep[2][3];
+   // histograms
+   std::vector<double> gr1d, gr2d, gr3d[2], relthe, relphi, relchi;
+   double delta_radius, delta_theta, delta_chi;
+   // schedule streams: P translational, Q rotational, 8 misc
+   std::vector<std::array<double, 6>> streams;
+   double ErotSQ = 0, Erot_termSQ = 0;
+
+   int type_offset(int t) const { return offset_atom[t] * P; }
+};
+
+// ----------------------------------------------------------------------------
+// leaf potentials
+// ----------------------------------------------------------------------------
+static double SPot1D(orc_t *o, double r, int *klo)      // mc_poten.cc:624-639
+{
+   int n = o->n1d;
+   if (klo) *klo = -1;
+   if (r >= o->g1d[n - 1]) return -o->c6 / pow(r, 6.0);
+   if (r <= o->g1d[0]) return o->unode * exp(-o->alpha * r);
+   return splint(o->g1d.data(), o->v1d.data(), o->y2_1d.data(), n, r, klo);
+}
+static double LPot2D(orc_t *o, double r, double cost, int *pir, int *pic)   // mc_poten.cc:688-729
+{
+   double rmin = o->rg2d[0], cmin = o->cg2d[0];
+   int rsize = o->rs2d, csize = o->cs2d;
+   int ir = (int)floor((r - rmin) / o->dr2d);
+   int ic = (int)floor((cost - cmin) / o->dc2d);
+   if (ir < 0) ir = 0; else if (ir >= (rsize - 1)) ir = rsize - 2;
+   if (ic < 0) ic = 0; else if (ic >= (csize - 1)) ic = csize - 2;
+   if (pir) *pir = ir;
+   if (pic) *pic = ic;
+   const double *pot = o->v2d.data();
+   double y1 = pot[ir * csize + ic], y2 = pot[(ir + 1) * csize + ic];
+   double y3 = pot[(ir + 1) * csize + ic + 1], y4 = pot[ir * csize + ic + 1];
+   double r1 = o->rg2d[ir], r2 = o->rg2d[ir + 1], c1 = o->cg2d[ic], c2 = o->cg2d[ic + 1];
+   double dr = (r - r1) / (r2 - r1), dc = (cost - c1) / (c2 - c1);
+   return (1.0 - dr) * (1.0 - dc) * y1 + dr * (1.0 - dc) * y2 + dr * dc * y3 + (1.0 - dr) * dc * y4;
+}
+// mc_poten.cc:548-622; which = 0 SRotDens, 1 SRotDensDeriv, 2 SRotDensEsqrt
+static double SRot(orc_t *o, double gamma, int which)
+{
+   int size = o->nrot;
+   const double *g = o->rgrid.data();
+   const double *y = which == 0 ? o->rdens.data() : which == 1 ? o->rderv.data() : o->resqr.data();
+   const double *y2 = which == 0 ? o->rdens2.data() : which == 1 ? o->rderv2.data() : o->resqr2.data();
+   if (gamma > g[size - 1]) return which == 0 ? y[size - 1] : 0.0;
+   if (gamma < g[0]) {
+      double rl = g[0], rr = g[1];
+      double salpha = (y[1] - y[0]) / (rr - rl);
+      double sbeta = (y[0] * rr - y[1] * rl) / (rr - rl);
+      return salpha * gamma + sbeta;
+   }
+   return splint(g, y, y2, size, gamma, nullptr);
+}
+
+static double vcord_call(orc_t *o, const double *eul, const double *rcom, const double *rpt, double *rtc)
+{
+   double E[3] = {eul[0], eul[1], eul[2]}, C[3] = {rcom[0], rcom[1], rcom[2]}, Pt[3] = {rpt[0], rpt[1], rpt[2]};
+   double v, rad, the, chi, hx[3], hy[3], hz[3];
+   int iv = 0;
+   // argument order &Rvmax,&Rvmin as at mc_piqmc.cc:1316
+   vcord_(E, C, Pt, const_cast<double *>(o->v3d), &o->rg3, &o->thg3, &o->chg3, &o->rvmax, &o->rvmin, &o->rvstep,
+          &v, &rad, &the, &chi, hx, hy, hz, &iv);
+   if (rtc) { rtc[0] = rad; rtc[1] = the; rtc[2] = chi; }
+   return v;
+}
+
+// One pair term of PotEnergy: atom0 (bead pos0, orientation row tm0) with atom1
+// at slice `it`.  eul0/cos0 override atom0's stored orientation when non-NULL
+// (PotRotE3D / PotRotEnergy).  mc_piqmc.cc:1822-1959.
+static double pair_energy(orc_t *o, int atom0, const double *pos0, int atom1, int it, const double *eul0,
+                          const double *cos0, int hist, double *hist_out)
+{
+   int P = o->P;
+   int type0 = o->mctype[atom0], type1 = o->mctype[atom1];
+   int offset0 = P * atom0, offset1 = P * atom1;
+   int t1 = offset1 + it;
+   const orc_type_t &T0 = o->sys.type[type0], &T1 = o->sys.type[type1];
+   double dr[3], dr2 = 0.0;
+   for (int id = 0; id < 3; id++) {
+      dr[id] = pos0[id] - o->coords[id][t1];
+      if (o->sys.minimage) dr[id] -= o->sys.box[id] * rint(dr[id] / o->sys.box[id]);
+      dr2 += dr[id] * dr[id];
+   }
+   double r = sqrt(dr2);
+   (void)hist; (void)hist_out;
+   if (T0.molecule == 1 || T1.molecule == 1) {
+      int sgn = 1;
+      int tm = offset1 + it / o->R;
+      const double *cs = nullptr;
+      if (T0.molecule == 1) { sgn = -1; tm = offset0 + it / o->R; cs = cos0; }
+      double cost = 0.0;
+      for (int id = 0; id < 3; id++) cost += (cs ? cs[id] : o->cosine[id][tm]) * dr[id];
+      cost /= r;
+      cost *= sgn;
+      return LPot2D(o, r, cost, nullptr, nullptr);
+   } else if ((T0.molecule == 2 || T1.molecule == 2) && o->sys.ispher == 0 && T0.molecule != T1.molecule) {
+      double RCOM[3], Rpt[3], Eul[3];
+      int tm;
+      if (T0.molecule == 2) {
+         tm = offset0 + it / o->R;
+         for (int id = 0; id < 3; id++) { RCOM[id] = pos0[id]; Rpt[id] = o->coords[id][t1]; }
+         if (eul0) { Eul[0] = eul0[0]; Eul[1] = eul0[1]; Eul[2] = eul0[2]; }
+         else { Eul[PHI] = o->angles[PHI][tm]; Eul[CTH] = acos(o->angles[CTH][tm]); Eul[CHI] = o->angles[CHI][tm]; }
+      } else {
+         tm = offset1 + it / o->R;
+         for (int id = 0; id < 3; id++) { Rpt[id] = pos0[id]; RCOM[id] = o->coords[id][t1]; }
+         Eul[PHI] = o->angles[PHI][tm]; Eul[CTH] = acos(o->angles[CTH][tm]); Eul[CHI] = o->angles[CHI][tm];
+      }
+      return vcord_call(o, Eul, RCOM, Rpt, nullptr);
+   } else if ((T0.molecule == 2 || T1.molecule == 2) && o->sys.ispher == 1 && T0.molecule != T1.molecule) {
+      double radret = r, v;
+      vspher_(&radret, &v);
+      return v;
+   } else if (T0.molecule == 2 && T1.molecule == 2 && o->sys.type[o->imtype].numb > 1) {
+      double c1[3], c2[3], e1[3], e2[3], E;
+      for (int id = 0; id < 3; id++) { c1[id] = pos0[id]; c2[id] = o->coords[id][t1]; }
+      int tm0 = offset0 + it / o->R, tm1 = offset1 + it / o->R;
+      if (eul0) { e1[0] = eul0[0]; e1[1] = eul0[1]; e1[2] = eul0[2]; }
+      else { e1[PHI] = o->angles[PHI][tm0]; e1[CTH] = acos(o->angles[CTH][tm0]); e1[CHI] = o->angles[CHI][tm0]; }
+      e2[PHI] = o->angles[PHI][tm1]; e2[CTH] = acos(o->angles[CTH][tm1]); e2[CHI] = o->angles[CHI][tm1];
+      caleng_(c1, c2, &E, e1, e2);
+      return E;
+   }
+   return SPot1D(o, r, nullptr);
+}
+
+// PotEnergy(atom0,pos,it), mc_piqmc.cc:1796-1965
+static double PotEnergy_it(orc_t *o, int atom0, const double *pos0, int it)
+{
+   double spot = 0.0;
+   for (int atom1 = 0; atom1 < o->N; atom1++)
+      if (atom1 != atom0) spot += pair_energy(o, atom0, pos0, atom1, it, nullptr, nullptr, 0, nullptr);
+   return spot;
+}
+// PotEnergy(atom0,pos), mc_piqmc.cc:1201-1383: per partner, sum over slices, then add
+static double PotEnergy_path(orc_t *o, int atom0, const double *shift)
+{
+   double spot = 0.0;
+   int P = o->P;
+   for (int atom1 = 0; atom1 < o->N; atom1++)
+      if (atom1 != atom0) {
+         double spot_pair = 0.0;
+         for (int it = 0; it < P; it++) {
+            double pos0[3];
+            for (int id = 0; id < 3; id++) {
+               pos0[id] = o->coords[id][P * atom0 + it];
+               if (shift) pos0[id] += shift[id];
+            }
+            spot_pair += pair_energy(o, atom0, pos0, atom1, it, nullptr, nullptr, 0, nullptr);
+         }
+         spot += spot_pair;
+      }
+   return spot;
+}
+// PotRotEnergy, mc_piqmc.cc:1967-2044 (linear rotor; `cosine` row passed explicitly)
+static double PotRotEnergy(orc_t *o, int atom0, const double *cos3, int it)
+{
+   double spot = 0.0;
+   int P = o->P;
+   double pos0[3];
+   for (int id = 0; id < 3; id++) pos0[id] = o->coords[id][P * atom0 + it];
+   for (int atom1 = 0; atom1 < o->N; atom1++)
+      if (atom1 != atom0) spot += pair_energy(o, atom0, pos0, atom1, it, nullptr, cos3, 0, nullptr);
+   return spot;
+}
+// PotRotE3D, mc_piqmc.cc:2046-2151
+static double PotRotE3D(orc_t *o, int atom0, const double *eul, int it)
+{
+   double spot = 0.0;
+   int P = o->P;
+   double pos0[3];
+   for (int id = 0; id < 3; id++) pos0[id] = o->coords[id][P * atom0 + it];
+   for (int atom1 = 0; atom1 < o->N; atom1++)
+      if (atom1 != atom0) spot += pair_energy(o, atom0, pos0, atom1, it, eul, nullptr, 0, nullptr);
+   return spot;
+}
+
+static void rotden_call(orc_t *o, const double *e1, const double *e2, double *rel, double *rho, double *erot,
+                        double *esq, int *istop)
+{
+   double a[3] = {e1[0], e1[1], e1[2]}, b[3] = {e2[0], e2[1], e2[2]};
+   *istop = 0;
+   rotden_(a, b, rel, rho, erot, esq, const_cast<double *>(o->rho3), const_cast<double *>(o->erot3),
+           const_cast<double *>(o->esq3), istop);
+}
+
+// ----------------------------------------------------------------------------
+// moves with explicit uniforms
+// ----------------------------------------------------------------------------
+// MCBisectionMove / MCBisectionMoveExchange for ONE atom, mc_piqmc.cc:194-419.
+// u_gauss: pairs (r1,r2) per midpoint per dimension in sampling order; u_acc:
+// consumed sequentially, only when deltav >= 0 (rnd3 short-circuit, :270-271).
+static int bisection_move(orc_t *o, int type, int atom, int time0, const double *ug, const double *ua, int exch, int *consumed)
+{
+   int P = o->P;
+   const orc_type_t &T = o->sys.type[type];
+   double mclambda = o->lambda[type];
+   int mclevels = T.levels, seg_size = 1 << mclevels;
+   int offset0 = o->type_offset(type) + P * atom, offset1 = offset0;
+   int time1 = time0 + seg_size, timep = time1 % P;
+   if (exch && timep != time1) offset1 = o->type_offset(type) + P * o->pindex[atom];
+   for (int id = 0; id < 3; id++) {
+      o->newc[id][offset0 + time0] = o->coords[id][offset0 + time0];
+      o->newc[id][offset1 + timep] = o->coords[id][offset1 + timep];
+   }
+   double bnorm = 1.0 / (mclambda * o->tau);
+   bool Accepted = false;
+   double pot0 = 0.0, pot1 = 0.0;
+   int ig = 0, ia = 0;
+   for (int level = 0; level < mclevels; level++) {
+      int lss = (int)pow(2.0, (mclevels - level));
+      double bkin_norm = bnorm / (double)lss;
+      double bpot_norm = o->tau * (double)(lss / 2);
+      pot1 = pot0; pot0 = 0.0;
+      int t0, t1, t2 = 0;
+      do {
+         t0 = t2; t2 = t0 + lss; t1 = (t0 + t2) / 2;
+         int pt0 = (time0 + t0) % P, pt1 = (time0 + t1) % P, pt2 = (time0 + t2) % P;
+         int off0 = offset0, off1 = offset0, off2 = offset0;
+         if (exch) {
+            if (pt0 != (time0 + t0)) off0 = offset1;
+            if (pt1 != (time0 + t1)) off1 = offset1;
+            if (pt2 != (time0 + t2)) off2 = offset1;
+         }
+         for (int id = 0; id < 3; id++) {
+            o->newc[id][off1 + pt1] = 0.5 * (o->newc[id][off0 + pt0] + o->newc[id][off2 + pt2]);
+            o->newc[id][off1 + pt1] += gauss_u(bkin_norm, ug[ig], ug[ig + 1]);
+            ig += 2;
+         }
+         // the reference evaluates with gatom0 = off0/P even when pt1 wrapped (:373-379)
+         int gatom0 = off0 / P;
+         double pn[3], po[3];
+         for (int id = 0; id < 3; id++) { pn[id] = o->newc[id][P * gatom0 + pt1]; po[id] = o->coords[id][P * gatom0 + pt1]; }
+         pot0 += PotEnergy_it(o, gatom0, pn, pt1) - PotEnergy_it(o, gatom0, po, pt1);
+         if (t0 != 0) {
+            for (int id = 0; id < 3; id++) { pn[id] = o->newc[id][P * gatom0 + pt0]; po[id] = o->coords[id][P * gatom0 + pt0]; }
+            pot0 += PotEnergy_it(o, gatom0, pn, pt0) - PotEnergy_it(o, gatom0, po, pt0);
+         }
+      } while (t2 < seg_size);
+      double deltav = (pot0 - 2.0 * pot1);
+      deltav *= bpot_norm;
+      Accepted = false;
+      if (deltav < 0.0) Accepted = true;
+      else if (exp(-deltav) > ua[ia++]) Accepted = true;
+      if (!Accepted) break;
+   }
+   if (consumed) { consumed[0] = ig; consumed[1] = ia; }
+   o->mctotal[type][MCMULTI] += 1.0;
+   if (Accepted) {
+      o->mcaccep[type][MCMULTI] += 1.0;
+      for (int id = 0; id < 3; id++)
+         for (int it = time0; it <= time1; it++) {
+            int pit = it % P;
+            int offset = offset0;
+            if (exch && pit != it) offset = offset1;
+            o->coords[id][offset + pit] = o->newc[id][offset + pit];
+         }
+   }
+   return Accepted ? 1 : 0;
+}
+
+// MCMolecularMove for ONE atom, mc_piqmc.cc:54-102
+static int molecular_move(orc_t *o, int type, int atom, const double *u3, double uacc)
+{
+   int P = o->P;
+   int offset = o->type_offset(type) + P * atom;
+   int gatom = offset / P;
+   double disp[3];
+   for (int id = 0; id < 3; id++) disp[id] = o->sys.type[type].mcstep * (u3[id] - 0.5);
+   double deltav = 0.0;
+   deltav += (PotEnergy_path(o, gatom, disp) - PotEnergy_path(o, gatom, nullptr));
+   bool Accepted = false;
+   if (deltav < 0.0) Accepted = true;
+   else if (exp(-deltav * o->tau) > uacc) Accepted = true;
+   o->mctotal[type][MCMOLEC] += 1.0;
+   if (Accepted) {
+      o->mcaccep[type][MCMOLEC] += 1.0;
+      for (int id = 0; id < 3; id++)
+         for (int it = 0; it < P; it++) {
+            // the reference forms newcoords = MCCoords; newcoords += disp (:73-74)
+            double v = o->coords[id][offset + it];
+            v += disp[id];
+            o->coords[id][offset + it] = v;
+         }
+   }
+   return Accepted ? 1 : 0;
+}
+
+// MCRot3Dstep, mc_piqmc.cc:938-1199 (RotDenType 0 and 1)
+static int rot3d_step(orc_t *o, int it1, int atom0, int type, double rand1, double rand2, double rand3, double rand4)
+{
+   int P = o->P, Q = o->Q;
+   int offset = o->type_offset(type) + P * atom0;
+   int gatom = offset / P;
+   double step = o->sys.type[type].rtstep;
+   int it0 = it1 - 1, it2 = it1 + 1;
+   if (it0 < 0) it0 += Q;
+   if (it2 >= Q) it2 -= Q;
+   int t0 = offset + it0, t1 = offset + it1, t2 = offset + it2;
+   double cost = o->angles[CTH][t1], phi = o->angles[PHI][t1], chi = o->angles[CHI][t1];
+   cost += (step * (rand1 - 0.5));
+   phi += 2.0 * M_PI * (step * (rand2 - 0.5));
+   chi += 2.0 * M_PI * (step * (rand3 - 0.5));
+   if (phi < 0.0) phi = 2.0 * M_PI + phi;
+   if (chi < 0.0) chi = 2.0 * M_PI + chi;
+   phi = fmod(phi, 2.0 * M_PI);
+   chi = fmod(chi, 2.0 * M_PI);
+   if (cost > 1.0) cost = 2.0 - cost;
+   if (cost < -1.0) cost = -2.0 - cost;
+
+   double rho, erot, esq, Eul1[3], Eul2[3], Eulrel[3];
+   int istop = 0;
+   auto dens = [&](const double *a, const double *b) -> double {
+      if (o->sys.rotden_type == 0) {
+         rotden_call(o, a, b, Eulrel, &rho, &erot, &esq, &istop);
+         if (istop == 1) { fprintf(stderr, "large matrix test error\n"); exit(0); }
+      } else {
+         double A[3] = {a[0], a[1], a[2]}, B[3] = {b[0], b[1], b[2]};
+         rsrot_(A, B, &o->sys.x_rot, &o->sys.y_rot, &o->sys.z_rot, &o->rottau, &o->sys.rot_odevn, &o->sys.rot_eoff, &rho, &erot);
+      }
+      return rho;
+   };
+   auto eul_old = [&](int t, double *e) { e[0] = o->angles[PHI][t]; e[1] = acos(o->angles[CTH][t]); e[2] = o->angles[CHI][t]; };
+   double Enew[3] = {phi, acos(cost), chi};
+
+   eul_old(t0, Eul1); eul_old(t1, Eul2);
+   double r = dens(Eul1, Eul2);
+   double dens_old = r, rhoold = r;
+   eul_old(t1, Eul1); eul_old(t2, Eul2);
+   r = dens(Eul1, Eul2);
+   dens_old = dens_old * r; rhoold = rhoold + r;
+   if (fabs(dens_old) < RZERO) dens_old = 0.0;
+   if (dens_old < 0.0) dens_old = fabs(dens_old);
+
+   double pot_old = 0.0;
+   int itr0 = it1 * o->R, itr1 = itr0 + o->R;
+   for (int it = itr0; it < itr1; it++) pot_old += PotRotE3D(o, gatom, Eul1, it);
+
+   eul_old(t0, Eul1);
+   r = dens(Eul1, Enew);
+   double dens_new = r, rhonew = r;
+   eul_old(t2, Eul2);
+   r = dens(Enew, Eul2);
+   dens_new = dens_new * r; rhonew = rhonew + r;
+   if (fabs(dens_new) < RZERO) dens_new = 0.0;
+   if (dens_new < 0.0) dens_new = fabs(dens_new);
+
+   double pot_new = 0.0;
+   for (int it = itr0; it < itr1; it++) pot_new += PotRotE3D(o, gatom, Enew, it);
+
+   double rd;
+   bool Accepted = false;
+   if (o->sys.rotden_type == 0) {
+      if (dens_old > RZERO) rd = dens_new / dens_old; else rd = 1.0;
+      rd *= exp(-o->tau * (pot_new - pot_old));
+      if (rd > 1.0) Accepted = true; else if (rd > rand4) Accepted = true;
+   } else {
+      rd = (rhonew - rhoold) / (4.0 * (o->rottau / WNO2K));
+      rd -= o->tau * (pot_new - pot_old);
+      if (rd > 0.0) Accepted = true; else if (rd > log(rand4)) Accepted = true;
+   }
+   o->mctotal[type][MCROTAT] += 1.0;
+   if (Accepted) {
+      o->mcaccep[type][MCROTAT] += 1.0;
+      o->angles[CTH][t1] = cost; o->angles[PHI][t1] = phi; o->angles[CHI][t1] = chi;
+      double sint = sqrt(1.0 - cost * cost);
+      o->cosine[0][t1] = sint * cos(phi);
+      o->cosine[1][t1] = sint * sin(phi);
+      o->cosine[2][t1] = cost;
+   }
+   return Accepted ? 1 : 0;
+}
+
+// MCRotLinStep, mc_piqmc.cc:781-936
+static int rotlin_step(orc_t *o, int it1, int type, double rand1, double rand2, double rand3)
+{
+   int P = o->P, Q = o->Q;
+   int offset = o->type_offset(type);
+   int gatom = offset / P;
+   double step = o->sys.type[type].rtstep;
+   int it0 = it1 - 1, it2 = it1 + 1;
+   if (it0 < 0) it0 += Q;
+   if (it2 >= Q) it2 -= Q;
+   int t0 = offset + it0, t1 = offset + it1, t2 = offset + it2;
+   double cost = o->angles[CTH][t1], phi = o->angles[PHI][t1];
+   cost += (step * (rand1 - 0.5));
+   phi += (step * (rand2 - 0.5));
+   if (cost > 1.0) cost = 2.0 - cost;
+   if (cost < -1.0) cost = -2.0 - cost;
+   double sint = sqrt(1.0 - cost * cost);
+   double nn[3] = {sint * cos(phi), sint * sin(phi), cost};
+
+   double p0 = 0.0, p1 = 0.0;
+   for (int id = 0; id < 3; id++) { p0 += o->cosine[id][t0] * o->cosine[id][t1]; p1 += o->cosine[id][t1] * o->cosine[id][t2]; }
+   double dens_old, rho1, rho2, erot;
+   if (o->sys.rotden_type == 0) dens_old = SRot(o, p0, 0) * SRot(o, p1, 0);
+   else {
+      rsline_(&o->sys.x_rot, &p0, &o->rottau, &rho1, &erot);
+      rsline_(&o->sys.x_rot, &p1, &o->rottau, &rho2, &erot);
+      dens_old = rho1 + rho2;
+   }
+   if (fabs(dens_old) < RZERO) dens_old = 0.0;
+   if (dens_old < 0.0 && o->sys.rotden_type == 0) { printf("Rotational Moves: Negative rot density\n"); exit(1); }
+
+   double pot_old = 0.0;
+   int itr0 = it1 * o->R, itr1 = itr0 + o->R;
+   double cold[3] = {o->cosine[0][t1], o->cosine[1][t1], o->cosine[2][t1]};
+   for (int it = itr0; it < itr1; it++) pot_old += PotRotEnergy(o, gatom, cold, it);
+
+   p0 = 0.0; p1 = 0.0;
+   for (int id = 0; id < 3; id++) { p0 += o->cosine[id][t0] * nn[id]; p1 += nn[id] * o->cosine[id][t2]; }
+   double dens_new;
+   if (o->sys.rotden_type == 0) dens_new = SRot(o, p0, 0) * SRot(o, p1, 0);
+   else {
+      rsline_(&o->sys.x_rot, &p0, &o->rottau, &rho1, &erot);
+      rsline_(&o->sys.x_rot, &p1, &o->rottau, &rho2, &erot);
+      dens_new = rho1 + rho2;
+   }
+   if (fabs(dens_new) < RZERO) dens_new = 0.0;
+   if (dens_new < 0.0 && o->sys.rotden_type == 0) { printf("Rotational Moves: Negative rot density\n"); exit(1); }
+
+   double pot_new = 0.0;
+   for (int it = itr0; it < itr1; it++) pot_new += PotRotEnergy(o, gatom, nn, it);
+
+   double rd;
+   bool Accepted = false;
+   if (o->sys.rotden_type == 0) {
+      if (dens_old > RZERO) rd = dens_new / dens_old; else rd = 1.0;
+      rd *= exp(-o->tau * (pot_new - pot_old));
+      if (rd > 1.0) Accepted = true; else if (rd > rand3) Accepted = true;
+   } else {
+      rd = dens_new - dens_old - o->tau * (pot_new - pot_old);
+      if (rd > 0.0) Accepted = true; else if (rd > log(rand3)) Accepted = true;
+   }
+   o->mctotal[type][MCROTAT] += 1.0;
+   if (Accepted) {
+      o->mcaccep[type][MCROTAT] += 1.0;
+      o->angles[CTH][t1] = cost; o->angles[PHI][t1] = phi;
+      for (int id = 0; id < 3; id++) o->cosine[id][t1] = nn[id];
+   }
+   return Accepted ? 1 : 0;
+}
+
+// ----------------------------------------------------------------------------
+// estimators
+// ----------------------------------------------------------------------------
+static void bin_1D(orc_t *o, double r)                         // mc_estim.cc:1275-1286
+{
+   int bin_r = (int)floor((r - MIN_RADIUS) / o->delta_radius);
+   if (bin_r < MC_BINSR && bin_r >= 0) o->gr1d[bin_r] += 1.0;
+}
+static void bin_2D(orc_t *o, double r, double cost)            // mc_estim.cc:1233-1250
+{
+   int bin_r = (int)floor((r - MIN_RADIUS) / o->delta_radius);
+   if (bin_r < MC_BINSR && bin_r >= 0) {
+      double theta = acos(cost);
+      int bin_t = (int)floor(theta / o->delta_theta);
+      if (bin_t < MC_BINST && bin_t >= 0) o->gr2d[bin_r * MC_BINST + bin_t] += 1.0;
+   }
+}
+static void bin_3D(orc_t *o, double r, double theta, double chi, int dtype)   // mc_estim.cc:1252-1273
+{
+   int bin_r = (int)floor((r - MIN_RADIUS) / o->delta_radius);
+   if (bin_r < MC_BINSR && bin_r >= 0) {
+      int bin_t = (int)floor(theta / o->delta_theta);
+      if (bin_t < MC_BINST && bin_t >= 0) {
+         int bin_c = (int)floor(chi / o->delta_chi);
+         if (bin_c < MC_BINSC && bin_c >= 0) o->gr3d[dtype][((size_t)bin_r * MC_BINST + bin_t) * MC_BINSC + bin_c] += 1.0;
+      }
+   }
+}
+
+// GetPotEnergy_Densities / GetPotEnergy, mc_estim.cc:500-874
+static double GetPot(orc_t *o, int dens)
+{
+   int P = o->P, N = o->N, R = o->R;
+   double spot = 0.0;
+   for (int atom0 = 0; atom0 < N - 1; atom0++)
+      for (int atom1 = atom0 + 1; atom1 < N; atom1++) {
+         int type0 = o->mctype[atom0], type1 = o->mctype[atom1];
+         const orc_type_t &T0 = o->sys.type[type0], &T1 = o->sys.type[type1];
+         int offset0 = P * atom0, offset1 = P * atom1;
+         double spot_pair = 0.0;
+         for (int it = 0; it < P; it++) {
+            int t0 = offset0 + it, t1 = offset1 + it;
+            double dr[3], dr2 = 0.0;
+            for (int id = 0; id < 3; id++) {
+               dr[id] = o->coords[id][t0] - o->coords[id][t1];
+               if (o->sys.minimage) dr[id] -= o->sys.box[id] * rint(dr[id] / o->sys.box[id]);
+               dr2 += dr[id] * dr[id];
+            }
+            double r = sqrt(dr2);
+            if (T0.molecule == 1 || T1.molecule == 1) {
+               int sgn = 1, tm = offset1 + it / R;
+               if (T0.molecule == 1) { sgn = -1; tm = offset0 + it / R; }
+               double cost = 0.0;
+               for (int id = 0; id < 3; id++) cost += o->cosine[id][tm] * dr[id];
+               cost /= r; cost *= sgn;
+               if (dens) bin_2D(o, r, cost);
+               spot_pair += LPot2D(o, r, cost, nullptr, nullptr);
+            } else if ((T0.molecule == 2 || T1.molecule == 2) && T0.molecule != T1.molecule) {
+               int tm, typed;
+               double RCOM[3], Rpt[3], Eul[3], v, rtc[3];
+               if (T0.molecule == 2) {
+                  typed = type1; tm = offset0 + it / R;
+                  for (int id = 0; id < 3; id++) { RCOM[id] = o->coords[id][t0]; Rpt[id] = o->coords[id][t1]; }
+               } else {
+                  typed = type0; tm = offset1 + it / R;
+                  for (int id = 0; id < 3; id++) { Rpt[id] = o->coords[id][t0]; RCOM[id] = o->coords[id][t1]; }
+               }
+               Eul[PHI] = o->angles[PHI][tm]; Eul[CTH] = acos(o->angles[CTH][tm]); Eul[CHI] = o->angles[CHI][tm];
+               if (o->sys.ispher == 0) v = vcord_call(o, Eul, RCOM, Rpt, rtc);
+               else { rtc[0] = r; vspher_(&rtc[0], &v); rtc[1] = 0.0; rtc[2] = 0.0; }
+               if (dens) bin_3D(o, rtc[0], rtc[1], rtc[2], typed);
+               spot_pair += v;
+            } else if (T0.molecule == 2 && T1.molecule == 2 && o->sys.type[o->imtype].numb > 1) {
+               double c1[3], c2[3], e1[3], e2[3], E;
+               for (int id = 0; id < 3; id++) { c1[id] = o->coords[id][t0]; c2[id] = o->coords[id][t1]; }
+               int tm0 = offset0 + it / R, tm1 = offset1 + it / R;
+               e1[PHI] = o->angles[PHI][tm0]; e1[CTH] = acos(o->angles[CTH][tm0]); e1[CHI] = o->angles[CHI][tm0];
+               e2[PHI] = o->angles[PHI][tm1]; e2[CTH] = acos(o->angles[CTH][tm1]); e2[CHI] = o->angles[CHI][tm1];
+               caleng_(c1, c2, &E, e1, e2);
+               spot_pair += E;
+            } else if (type0 == type1 && T0.molecule == 0) {
+               if (dens) bin_1D(o, r);
+               spot_pair += SPot1D(o, r, nullptr);
+            }
+         }
+         spot += spot_pair;
+      }
+   return spot / (double)P;
+}
+
+// GetKinEnergy, mc_estim.cc:876-937
+static double GetKin(orc_t *o)
+{
+   int P = o->P, N = o->N;
+   int numb = 0;
+   double r2avr = 0.0;
+   for (int atom = 0; atom < N; atom++) {
+      numb++;
+      int type = o->mctype[atom];
+      int offset0 = P * atom;
+      int gatom = o->offset_atom[type];
+      double sum = 0.0;
+      for (int it = 0; it < P; it++) {
+         int t0 = offset0 + it;
+         int offset1 = offset0;
+         if (o->sys.type[type].stat == 1 && (it + 1) == P) offset1 = P * (gatom + o->pindex[atom - gatom]);
+         int t1 = offset1 + (it + 1) % P;
+         for (int dim = 0; dim < 3; dim++) {
+            double dr = o->coords[dim][t0] - o->coords[dim][t1];
+            if (o->sys.minimage) dr -= o->sys.box[dim] * rint(dr / o->sys.box[dim]);
+            sum += dr * dr;
+         }
+      }
+      r2avr += sum / (4.0 * o->beta * o->lambda[type]);
+   }
+   return (double)P * o->sys.temperature * (0.5 * (double)(3 * numb) - r2avr);
+}
+
+// GetRotEnergy, mc_estim.cc:939-987
+static double GetRotEnergy(orc_t *o)
+{
+   int type = o->imtype, Q = o->Q;
+   int offset = o->type_offset(type);
+   double srot = 0.0;
+   o->ErotSQ = 0.0; o->Erot_termSQ = 0.0;
+   for (int it0 = 0; it0 < Q; it0++) {
+      int t0 = offset + it0, t1 = offset + (it0 + 1) % Q;
+      double p0 = 0.0;
+      for (int id = 0; id < 3; id++) p0 += o->cosine[id][t0] * o->cosine[id][t1];
+      if (o->sys.rotden_type == 0) {
+         double rdens = SRot(o, p0, 0);
+         if (fabs(rdens) > RZERO) srot += SRot(o, p0, 1) / rdens;
+         o->Erot_termSQ += (SRot(o, p0, 1) / rdens) * (SRot(o, p0, 1) / rdens);
+         o->ErotSQ += SRot(o, p0, 2) / rdens;
+      } else {
+         double rho, erot;
+         rsline_(&o->sys.x_rot, &p0, &o->rottau, &rho, &erot);
+         srot += rho;
+      }
+   }
+   if (o->sys.rotden_type == 1) {
+      srot = srot / (double)Q;
+      srot = srot / o->rottau + 1.0 / o->rottau;
+   }
+   return srot;
+}
+
+// GetRotE3D, mc_estim.cc:989-1096 (including the accumulating `offset +=` at :1002)
+static double GetRotE3D(orc_t *o)
+{
+   int type = o->imtype, P = o->P, Q = o->Q;
+   int offset = o->type_offset(type);
+   double ERot3D = 0.0;
+   o->ErotSQ = 0.0; o->Erot_termSQ = 0.0;
+   for (int atom = 0; atom < o->sys.type[type].numb; atom++) {
+      offset += P * atom;
+      double srot = 0.0, sesq = 0.0, se_termsq = 0.0;
+      int RNskip = (o->sys.rotden_type == 0) ? 1 : o->sys.rnratio;
+      for (int it0 = 0; it0 < Q; it0 = it0 + RNskip) {
+         int t0 = offset + it0, t1 = offset + (it0 + RNskip) % Q;
+         double rho, erot, esq, Eul1[3], Eul2[3], Eulrel[3];
+         int istop = 0;
+         Eul1[0] = o->angles[PHI][t0]; Eul1[1] = acos(o->angles[CTH][t0]); Eul1[2] = o->angles[CHI][t0];
+         Eul2[0] = o->angles[PHI][t1]; Eul2[1] = acos(o->angles[CTH][t1]); Eul2[2] = o->angles[CHI][t1];
+         rotden_call(o, Eul1, Eul2, Eulrel, &rho, &erot, &esq, &istop);
+         double phirel = Eulrel[0], therel = Eulrel[1], chirel = Eulrel[2];
+         int bin_t = (int)floor(therel / o->delta_theta);
+         if (bin_t < MC_BINST && bin_t >= 0) o->relthe[bin_t] += (double)RNskip;
+         int bin_p = (int)floor(phirel / o->delta_chi);
+         if (bin_p < MC_BINSC && bin_p >= 0) o->relphi[bin_p] += (double)RNskip;
+         int bin_c = (int)floor(chirel / o->delta_chi);
+         if (bin_c < MC_BINSC && bin_c >= 0) o->relchi[bin_c] += (double)RNskip;
+         if (o->sys.rotden_type == 1 && o->sys.rnratio == 1) {
+            rsrot_(Eul1, Eul2, &o->sys.x_rot, &o->sys.y_rot, &o->sys.z_rot, &o->rottau, &o->sys.rot_odevn, &o->sys.rot_eoff, &rho, &erot);
+            srot += rho;
+         } else srot += erot;
+         sesq += esq;
+         se_termsq += erot * erot;
+      }
+      double nq = (double)(Q / RNskip);
+      srot = srot / nq;
+      sesq = sesq / (nq * nq);
+      se_termsq = se_termsq / (nq * nq);
+      ERot3D += srot; o->ErotSQ += sesq; o->Erot_termSQ += se_termsq;
+      if (o->sys.rotden_type == 1 && o->sys.rnratio == 1) {
+         double tc = o->rottau / WNO2K;
+         ERot3D = ERot3D / (4.0 * tc * tc);
+         ERot3D += 0.25 * (o->sys.x_rot + o->sys.y_rot + o->sys.z_rot) + 1.5 / tc;
+         ERot3D = ERot3D / WNO2K;
+      }
+   }
+   return ERot3D;
+}
+
+// GetRCF row 0, mc_estim.cc:1099-1139
+static void GetRCF(orc_t *o, double *rcf0)
+{
+   int Q = o->Q, offset = o->type_offset(o->imtype);
+   for (int it0 = 0; it0 < Q; it0++) {
+      int t0 = offset + it0;
+      for (int itc = 0; itc < Q; itc++) {
+         int tc = offset + (it0 + itc) % Q;
+         double p0 = 0.0;
+         for (int id = 0; id < 3; id++) p0 += o->cosine[id][t0] * o->cosine[id][tc];
+         rcf0[itc] += p0;
+      }
+   }
+}
+
+// ----------------------------------------------------------------------------
+// device-schedule replay (DESIGN.md "Schedule"); the per-move mathematics is
+// the reference's, the ORDER of moves and the stream addressing are the CUDA
+// path's.
+// ----------------------------------------------------------------------------
+namespace {
+inline double draw(orc_t *o, int s) { return mrg_u01(o->streams[s].data()); }
+
+// rigid shift of a whole permutation cycle (identity permutation: one atom)
+void sched_molecular(orc_t *o, int type)
+{
+   int P = o->P, numb = o->sys.type[type].numb, base = o->offset_atom[type];
+   int MS = P + o->Q;
+   std::vector<int> flag(numb, 0);
+   for (int atom = 0; atom < numb; atom++) {
+      if (flag[atom]) continue;
+      std::vector<int> cyc;
+      int a = atom;
+      do { cyc.push_back(a); flag[a] = 1; a = (o->sys.type[type].stat == 1) ? o->pindex[a] : a; } while (a != atom);
+      double u[4];
+      for (int k = 0; k < 4; k++) u[k] = draw(o, MS);
+      double disp[3];
+      for (int id = 0; id < 3; id++) disp[id] = o->sys.type[type].mcstep * (u[id] - 0.5);
+      // dV of the rigid shift: members against non-members only
+      double deltav = 0.0;
+      for (int a0 : cyc) {
+         int g0 = base + a0;
+         for (int atom1 = 0; atom1 < o->N; atom1++) {
+            bool member = false;
+            for (int a1 : cyc) if (base + a1 == atom1) member = true;
+            if (member) continue;
+            for (int it = 0; it < P; it++) {
+               double pn[3], po[3];
+               for (int id = 0; id < 3; id++) { po[id] = o->coords[id][P * g0 + it]; pn[id] = po[id] + disp[id]; }
+               deltav += pair_energy(o, g0, pn, atom1, it, nullptr, nullptr, 0, nullptr) -
+                         pair_energy(o, g0, po, atom1, it, nullptr, nullptr, 0, nullptr);
+            }
+         }
+      }
+      bool acc = (deltav < 0.0) || (exp(-deltav * o->tau) > u[3]);
+      o->mctotal[type][MCMOLEC] += 1.0;
+      if (acc) {
+         o->mcaccep[type][MCMOLEC] += 1.0;
+         for (int a0 : cyc)
+            for (int id = 0; id < 3; id++)
+               for (int it = 0; it < P; it++) o->coords[id][P * (base + a0) + it] += disp[id];
+      }
+   }
+}
+
+// one segment [s0, s0+seg] of world line `atom` (continuing on pindex[atom] past beta for BOSE)
+void sched_bisect(orc_t *o, int type, int atom, int s0)
+{
+   int P = o->P;
+   const orc_type_t &T = o->sys.type[type];
+   int L = T.levels, seg = 1 << L, base = o->offset_atom[type];
+   int gA = base + atom;
+   int gB = (T.stat == 1) ? base + o->pindex[atom] : gA;
+   std::vector<double> nx((seg + 1) * 3);
+   auto gat = [&](int t) { return (s0 + t >= P) ? gB : gA; };
+   auto sl = [&](int t) { return (s0 + t) % P; };
+   for (int id = 0; id < 3; id++) {
+      nx[0 * 3 + id] = o->coords[id][P * gat(0) + sl(0)];
+      nx[seg * 3 + id] = o->coords[id][P * gat(seg) + sl(seg)];
+   }
+   double bnorm = 1.0 / (o->lambda[type] * o->tau);
+   double S = 0.0;
+   bool acc = true;
+   for (int level = 0; level < L; level++) {
+      int lss = seg >> level, half = lss / 2;
+      double bkin = bnorm / (double)lss;
+      double D = 0.0;
+      for (int t1 = half; t1 < seg; t1 += lss) {
+         int p = sl(t1), g = gat(t1);
+         double po[3];
+         for (int id = 0; id < 3; id++) {
+            double r1 = draw(o, p), r2 = draw(o, p);
+            nx[t1 * 3 + id] = 0.5 * (nx[(t1 - half) * 3 + id] + nx[(t1 + half) * 3 + id]) + gauss_u(bkin, r1, r2);
+            po[id] = o->coords[id][P * g + p];
+         }
+         D += PotEnergy_it(o, g, &nx[t1 * 3], p) - PotEnergy_it(o, g, po, p);
+      }
+      double deltav = (D - S) * (o->tau * (double)half);
+      S += D;
+      acc = false;
+      if (deltav < 0.0) acc = true;
+      else if (exp(-deltav) > draw(o, sl(0))) acc = true;
+      if (!acc) break;
+   }
+   o->mctotal[type][MCMULTI] += 1.0;
+   if (acc) {
+      o->mcaccep[type][MCMULTI] += 1.0;
+      for (int t = 1; t < seg; t++)
+         for (int id = 0; id < 3; id++) o->coords[id][P * gat(t) + sl(t)] = nx[t * 3 + id];
+   }
+}
+
+void sched_rot_slice(orc_t *o, int type, int q)
+{
+   int RS = o->P + q;
+   for (int a = 0; a < o->sys.type[type].numb; a++) {
+      if (o->sys.type[type].molecule == 2) {
+         double r1 = draw(o, RS), r2 = draw(o, RS), r3 = draw(o, RS), r4 = draw(o, RS);
+         rot3d_step(o, q, a, type, r1, r2, r3, r4);
+      } else {
+         double r1 = draw(o, RS), r2 = draw(o, RS), r3 = draw(o, RS);
+         rotlin_step(o, q, type, r1, r2, r3);
+      }
+   }
+}
+} // namespace
+
+// ----------------------------------------------------------------------------
+// C interface
+// ----------------------------------------------------------------------------
+extern "C" {
+
+orc_t *orc_create(const orc_system_t *sys)
+{
+   orc_t *o = new orc();
+   o->sys = *sys;
+   o->P = sys->P; o->Q = sys->Q;
+   o->N = 0;
+   o->imtype = -1; o->bstype = -1;
+   for (int t = 0; t < sys->ntypes; t++) {
+      o->offset_atom[t] = o->N;
+      o->N += sys->type[t].numb;
+      for (int a = 0; a < sys->type[t].numb; a++) o->mctype.push_back(t);
+      // mc_setup.cc:206-215
+      double lam = 100.0 * (HBAR * HBAR) / (AMU * K_B);
+      o->lambda[t] = 0.5 * lam / sys->type[t].mass;
+      if (sys->type[t].stat == 1) o->bstype = t;
+      if (sys->type[t].molecule) o->imtype = t;
+   }
+   o->offset_atom[sys->ntypes] = o->N;
+   // mc_setup.cc:366-383
+   o->beta = 1.0 / sys->temperature;
+   o->tau = o->beta / (double)o->P;
+   o->R = 1;
+   o->rottau = 0.0;
+   if (o->Q > 0) { o->rottau = o->beta / (double)o->Q; o->R = o->P / o->Q; }
+   size_t n = (size_t)o->N * o->P;
+   for (int d = 0; d < 3; d++) { o->coords[d].assign(n, 0.0); o->angles[d].assign(n, 0.0); o->cosine[d].assign(n, 0.0); o->newc[d].assign(n, 0.0); }
+   o->pindex.resize(o->N); o->rindex.resize(o->N);
+   for (int a = 0; a < o->N; a++) { o->pindex[a] = a; o->rindex[a] = a; }
+   memset(o->mctotal, 0, sizeof(o->mctotal)); memset(o->mcaccep, 0, sizeof(o->mcaccep));
+   // mc_estim.cc:254-261
+   o->delta_radius = (MAX_RADIUS - MIN_RADIUS) / (double)MC_BINSR;
+   o->delta_theta = M_PI / (double)(MC_BINST - 1);
+   o->delta_chi = 2.0 * M_PI / (double)(MC_BINSC - 1);
+   orc_reset_hist(o);
+   return o;
+}
+void orc_destroy(orc_t *o) { delete o; }
+
+void orc_set_pot1d(orc_t *o, int n, const double *grid, const double *v)   // mc_poten.cc:379-438
+{
+   o->n1d = n; o->g1d.assign(grid, grid + n); o->v1d.assign(v, v + n); o->y2_1d.assign(n, 0.0);
+   init_spline(o->g1d.data(), o->v1d.data(), o->y2_1d.data(), n);
+   double fr = o->v1d[0] / o->v1d[1];
+   double dr = o->g1d[1] - o->g1d[0];
+   o->alpha = log(fr) / dr;
+   o->unode = o->v1d[0] * exp(o->alpha * o->g1d[0]);
+   double r0 = pow(o->g1d[n - 2], 6.0), r1 = pow(o->g1d[n - 1], 6.0);
+   fr = o->v1d[n - 1] - o->v1d[n - 2];
+   o->c6 = fr / (1.0 / r0 - 1.0 / r1);
+}
+void orc_get_pot1d_setup(orc_t *o, double *y2, double *auc)
+{
+   memcpy(y2, o->y2_1d.data(), sizeof(double) * o->n1d);
+   auc[0] = o->alpha; auc[1] = o->unode; auc[2] = o->c6;
+}
+void orc_set_pot2d(orc_t *o, int rs, int cs, double dr, double dc, const double *rg, const double *cg, const double *v)
+{
+   o->rs2d = rs; o->cs2d = cs; o->dr2d = dr; o->dc2d = dc;
+   o->rg2d.assign(rg, rg + rs); o->cg2d.assign(cg, cg + cs); o->v2d.assign(v, v + (size_t)rs * cs);
+}
+void orc_set_pot3d(orc_t *o, int rg, int thg, int chg, double rvmin, double rvmax, const double *v)
+{
+   o->rg3 = rg; o->thg3 = thg; o->chg3 = chg; o->rvmin = rvmin; o->rvmax = rvmax;
+   o->rvstep = (rvmax - rvmin) / (double)(rg - 1);       // mc_poten.cc:288
+   o->v3d = v;
+}
+void orc_set_rotlin(orc_t *o, int n, const double *grid, const double *dens, const double *derv, const double *esqr)
+{
+   o->nrot = n;
+   o->rgrid.assign(grid, grid + n); o->rdens.assign(dens, dens + n); o->rderv.assign(derv, derv + n); o->resqr.assign(esqr, esqr + n);
+   o->rdens2.assign(n, 0.0); o->rderv2.assign(n, 0.0); o->resqr2.assign(n, 0.0);
+   init_spline(o->rgrid.data(), o->rdens.data(), o->rdens2.data(), n);     // mc_poten.cc:543-545
+   init_spline(o->rgrid.data(), o->rderv.data(), o->rderv2.data(), n);
+   init_spline(o->rgrid.data(), o->resqr.data(), o->resqr2.data(), n);
+}
+void orc_set_rot3d(orc_t *o, const double *rho, const double *erot, const double *esq) { o->rho3 = rho; o->erot3 = erot; o->esq3 = esq; }
+void orc_set_vspher(orc_t *, const double *t501) { oracle_set_vspher_table(t501); }
+
+void orc_set_state(orc_t *o, const double *coords, const double *angles, const int *pindex)
+{
+   size_t n = (size_t)o->N * o->P;
+   for (int d = 0; d < 3; d++)
+      for (size_t i = 0; i < n; i++) { o->coords[d][i] = coords[d * n + i]; o->angles[d][i] = angles[d * n + i]; }
+   for (size_t i = 0; i < n; i++) {                     // mc_main.cc:192-199
+      double phi = o->angles[PHI][i], cost = o->angles[CTH][i];
+      double sint = sqrt(1.0 - cost * cost);
+      o->cosine[0][i] = sint * cos(phi); o->cosine[1][i] = sint * sin(phi); o->cosine[2][i] = cost;
+   }
+   if (pindex && o->bstype >= 0)
+      for (int a = 0; a < o->sys.type[o->bstype].numb; a++) { o->pindex[a] = pindex[a]; o->rindex[pindex[a]] = a; }
+}
+void orc_get_state(orc_t *o, double *coords, double *angles, double *cosine)
+{
+   size_t n = (size_t)o->N * o->P;
+   for (int d = 0; d < 3; d++)
+      for (size_t i = 0; i < n; i++) {
+         coords[d * n + i] = o->coords[d][i]; angles[d * n + i] = o->angles[d][i];
+         if (cosine) cosine[d * n + i] = o->cosine[d][i];
+      }
+}
+
+double orc_spot1d(orc_t *o, double r, int *klo) { return SPot1D(o, r, klo); }
+double orc_lpot2d(orc_t *o, double r, double c, int *ir, int *ic) { return LPot2D(o, r, c, ir, ic); }
+double orc_srotdens(orc_t *o, double g, int which) { return SRot(o, g, which); }
+void orc_rotden(orc_t *o, const double *e1, const double *e2, double *rel, double *rho, double *erot, double *esq, int *index, int *istop)
+{
+   rotden_call(o, e1, e2, rel, rho, erot, esq, istop);
+   if (index) *index = oracle_last_rotden_index;
+}
+double orc_vcord(orc_t *o, const double *eul, const double *rcom, const double *rpt, double *rtc, int *index)
+{
+   double v = vcord_call(o, eul, rcom, rpt, rtc);
+   if (index) *index = oracle_last_vcord_index;
+   return v;
+}
+double orc_caleng(const double *c1, const double *c2, const double *e1, const double *e2)
+{
+   double a[3] = {c1[0], c1[1], c1[2]}, b[3] = {c2[0], c2[1], c2[2]}, x[3] = {e1[0], e1[1], e1[2]}, y[3] = {e2[0], e2[1], e2[2]}, E;
+   caleng_(a, b, &E, x, y);
+   return E;
+}
+
+double orc_pot_energy_it(orc_t *o, int atom, const double *pos3, int it)
+{
+   double p[3];
+   for (int id = 0; id < 3; id++) p[id] = pos3 ? pos3[id] : o->coords[id][o->P * atom + it];
+   return PotEnergy_it(o, atom, p, it);
+}
+double orc_pot_energy_path(orc_t *o, int atom, const double *shift3) { return PotEnergy_path(o, atom, shift3); }
+double orc_pot_rot_energy(orc_t *o, int atom, const double *c3, int it) { return PotRotEnergy(o, atom, c3, it); }
+double orc_pot_rot_e3d(orc_t *o, int atom, const double *e3, int it) { return PotRotE3D(o, atom, e3, it); }
+
+int orc_bisection_move(orc_t *o, int type, int atom, int time, const double *ug, const double *ua, int exch, int *consumed) { return bisection_move(o, type, atom, time, ug, ua, exch, consumed); }
+int orc_molecular_move(orc_t *o, int type, int atom, const double *u3, double ua) { return molecular_move(o, type, atom, u3, ua); }
+int orc_rot3d_step(orc_t *o, int it1, int atom0, int type, double r1, double r2, double r3, double r4) { return rot3d_step(o, it1, atom0, type, r1, r2, r3, r4); }
+int orc_rotlin_step(orc_t *o, int it1, int type, double r1, double r2, double r3) { return rotlin_step(o, it1, type, r1, r2, r3); }
+
+double orc_get_kin(orc_t *o) { return GetKin(o); }
+double orc_get_pot(orc_t *o, int dens) { return GetPot(o, dens); }
+double orc_get_rot_energy(orc_t *o, double *esq, double *eterm) { double s = GetRotEnergy(o); *esq = o->ErotSQ; *eterm = o->Erot_termSQ; return s; }
+double orc_get_rot_e3d(orc_t *o, double *esq, double *eterm) { double s = GetRotE3D(o); *esq = o->ErotSQ; *eterm = o->Erot_termSQ; return s; }
+void orc_get_rcf(orc_t *o, double *rcf0) { for (int i = 0; i < o->Q; i++) rcf0[i] = 0.0; GetRCF(o, rcf0); }
+void orc_reset_hist(orc_t *o)
+{
+   o->gr1d.assign(MC_BINSR, 0.0); o->gr2d.assign(MC_BINSR * MC_BINST, 0.0);
+   for (int d = 0; d < 2; d++) o->gr3d[d].assign((size_t)MC_BINSR * MC_BINST * MC_BINSC, 0.0);
+   o->relthe.assign(MC_BINST, 0.0); o->relphi.assign(MC_BINSC, 0.0); o->relchi.assign(MC_BINSC, 0.0);
+}
+void orc_get_hist(orc_t *o, double *g1, double *g2, double *g3a, double *g3m, double *rt, double *rp, double *rc)
+{
+   if (g1) memcpy(g1, o->gr1d.data(), sizeof(double) * o->gr1d.size());
+   if (g2) memcpy(g2, o->gr2d.data(), sizeof(double) * o->gr2d.size());
+   if (g3a) memcpy(g3a, o->gr3d[0].data(), sizeof(double) * o->gr3d[0].size());
+   if (g3m) memcpy(g3m, o->gr3d[1].data(), sizeof(double) * o->gr3d[1].size());
+   if (rt) memcpy(rt, o->relthe.data(), sizeof(double) * MC_BINST);
+   if (rp) memcpy(rp, o->relphi.data(), sizeof(double) * MC_BINSC);
+   if (rc) memcpy(rc, o->relchi.data(), sizeof(double) * MC_BINSC);
+}
+
+void orc_mrg_stream_state(const unsigned long *seed6, long stream, double *st) { mrg_stream_state(seed6, stream, st); }
+void orc_mrg_draws(const unsigned long *seed6, long first, int nstream, int ndraw, double *out)
+{
+   for (int s = 0; s < nstream; s++) {
+      double st[6];
+      mrg_stream_state(seed6, first + s, st);
+      for (int k = 0; k < ndraw; k++) out[(size_t)s * ndraw + k] = mrg_u01(st);
+   }
+}
+
+void orc_sched_seed(orc_t *o, const unsigned long *seed6, long chain_global)
+{
+   int S = o->P + o->Q + 8;
+   o->streams.resize(S);
+   double st[6];
+   mrg_stream_state(seed6, chain_global * S, st);
+   double s1[3] = {st[0], st[1], st[2]}, s2[3] = {st[3], st[4], st[5]};
+   for (int s = 0; s < S; s++) {
+      for (int k = 0; k < 3; k++) { o->streams[s][k] = s1[k]; o->streams[s][3 + k] = s2[k]; }
+      MatVecModM(A1p127, s1, s1, m1);                  // rngstream.cc:319-320
+      MatVecModM(A2p127, s2, s2, m2);
+   }
+}
+
+void orc_sched_run(orc_t *o, long t0, long nsteps)
+{
+   int P = o->P, Q = o->Q;
+   for (long t = t0; t < t0 + nsteps; t++) {
+      int time = (int)(t % P);
+      for (int type = 0; type < o->sys.ntypes; type++) {
+         const orc_type_t &T = o->sys.type[type];
+         if (time == 0) sched_molecular(o, type);
+         int seg = 1 << T.levels, nseg = P / seg;
+         if (time % nseg == 0) {
+            int off = (time / nseg) % P;
+            for (int atom = 0; atom < T.numb; atom++)
+               for (int k = 0; k < nseg; k++) sched_bisect(o, type, atom, (off + k * seg) % P);
+         }
+         if (type == o->imtype && Q > 0) {
+            int qe = (Q % 2 == 1 && Q > 1) ? Q - 1 : Q;      // odd Q: the last slice gets its own phase
+            for (int q = 0; q < qe; q += 2) sched_rot_slice(o, type, q);
+            for (int q = 1; q < qe; q += 2) sched_rot_slice(o, type, q);
+            if (qe != Q) sched_rot_slice(o, type, Q - 1);
+         }
+      }
+   }
+}
+void orc_sched_counters(orc_t *o, double *tot, double *acc)
+{
+   for (int t = 0; t < 2; t++) for (int m = 0; m < 3; m++) { tot[t * 3 + m] = o->mctotal[t][m]; acc[t * 3 + m] = o->mcaccep[t][m]; }
+}
+
+} // extern "C"
