@@ -1,0 +1,147 @@
+/* pimcgpu.h -- C ABI of the B200 (sm_100a) PIMC sampling hot path.
+ *
+ * Drop-in boundary for MoRiBS-PIMC's hot path.  The reference has no plugin
+ * ABI: its driver (mc_main.cc) calls free functions that share global arrays
+ * (mc_setup.h:176-191).  Each entry point below names the reference
+ * interface it replaces; INTEGRATION.md shows the patch a maintainer applies
+ * to mc_main.cc to route PIMCPass/MCGetAverage through this library.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on
+ * success and nonzero on failure with a message in pimcgpu_last_error(); the
+ * library never calls exit().  Host state arrays use the reference layout
+ * [dim][atom*P + it] (mc_setup.cc:139-148, mc_utils.cc:10-30); the device
+ * keeps its own slice-major SoA mirror.  Not re-entrant; one context per
+ * process (= per GPU rank), like the reference's globals.
+ */
+#ifndef PIMCGPU_H
+#define PIMCGPU_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PIMCGPU_MAX_TYPES 2      /* one atom type + one molecule type (mc_input.cc:395-396) */
+#define PIMCGPU_BINSR 300        /* MC_BINSR, mc_estim.cc:25 */
+#define PIMCGPU_BINST 50         /* MC_BINST, mc_estim.cc:26 */
+#define PIMCGPU_BINSC 100        /* MC_BINSC, mc_estim.cc:27 */
+#define PIMCGPU_SIZE_ROTDEN (181 * 361 * 361)   /* SizeRotDen, mc_setup.h:116 */
+
+/* TParticle (mc_setup.h:66-91): one species line of qmc.input (mc_input.cc:147-214) */
+typedef struct {
+   int    numb;       /* number of atoms/molecules                                  */
+   int    molecule;   /* 0 ATOM, 1 MOLECULE (linear rotor), 2 NONLINEAR             */
+   int    stat;       /* 0 BOLTZMANN, 1 BOSE                                        */
+   int    levels;     /* bisection levels; segment = 2^levels (mlsegm)              */
+   double mass;       /* amu (MCInitParams, mc_setup.cc:244-319)                    */
+   double mcstep;     /* whole-path move step, Angstrom                             */
+   double rtstep;     /* rotational step (ROTATION line, mc_input.cc:261-273)       */
+} pimcgpu_type;
+
+/* the scalars of mc_setup.h:13-63,103-107 plus how to spread chains over the device */
+typedef struct {
+   int          ntypes;
+   pimcgpu_type type[PIMCGPU_MAX_TYPES];
+   int          P;             /* NumbTimes                                          */
+   int          Q;             /* NumbRotTimes, 0 without ROTATION                   */
+   double       temperature;   /* Kelvin                                             */
+   int          ispher;        /* ISPHER                                             */
+   int          minimage;      /* MINIMAGE                                           */
+   double       box[3];        /* BoxSize                                            */
+   int          rotden_type;   /* RotDenType; only 0 (tabulated) runs on the device  */
+   int          nchains;       /* independent Markov chains on this device           */
+   long         chain_offset;  /* global index of local chain 0 (rank * nchains)     */
+   int          device;        /* CUDA device ordinal                                */
+   int          ctas_per_chain;/* thread-block cluster size per chain, 0 = auto      */
+   int          threads_per_cta;/* 0 = auto                                          */
+   int          team;          /* lanes cooperating on one segment / rot slice, 0 = auto */
+} pimcgpu_system;
+
+/* host pointers to the tables the reference loads in InitPotentials / InitRotDensity
+ * (mc_poten.cc:93-164); all are copied to the device by pimcgpu_init.  Unused ones NULL. */
+typedef struct {
+   /* 1-D pair potential of the atom type: init_pot1D, mc_poten.cc:379-438 (K, Angstrom) */
+   int           n1d;
+   const double *grid1d, *pot1d;
+   /* 2-D atom--linear-rotor potential: init_pot2D, mc_poten.cc:305-377 */
+   int           rsize2d, csize2d;
+   double        dr2d, dc2d;
+   const double *rgrid2d, *cgrid2d, *pot2d;           /* pot2d[rsize][csize]        */
+   /* 3-D atom--top potential: init_pot3D, mc_poten.cc:254-303 (r in bohr, 1-degree grids) */
+   int           rgrd, thgrd, chgrd;
+   double        rvmin, rvmax;
+   const double *vtable;                              /* [rgrd][thgrd][chgrd]       */
+   /* linear-rotor density matrix columns of <type>_T<T>t<Q>.rot: init_rotdens, mc_poten.cc:508-546 */
+   int           nrot;
+   const double *rotgrid, *rotdens, *rotderv, *rotesqr;
+   /* top density matrix / energy / energy^2 tables: init_rot3D, mc_poten.cc:440-506 */
+   const double *rho3d, *erot3d, *esq3d;              /* PIMCGPU_SIZE_ROTDEN each   */
+   /* 501-entry spherical H2O-pH2 table of vspher.f:15-517 (ISPHER=1), else NULL     */
+   const double *vspher;
+} pimcgpu_tables;
+
+/* Block accumulators: the file-statics of mc_estim.cc:39-103 and mc_main.cc:45-64,
+ * SUMS and COUNTS only (ratios are formed after the cross-GPU reduction).          */
+typedef struct {
+   double count;                 /* avergCount summed over chains                    */
+   double kin, pot, rot, rotsq;  /* _bkin _bpot _brot _brotsq                        */
+   double cv, cv_trans, cv_rot;  /* _bCv _bCv_trans _bCv_rot                         */
+   double mctotal[PIMCGPU_MAX_TYPES][3];   /* MCTotal[type][MCMOLEC,MCMULTI,MCROTAT]  */
+   double mcaccep[PIMCGPU_MAX_TYPES][3];   /* MCAccep                                 */
+} pimcgpu_scalars;
+
+/* ---- life cycle: MCMemAlloc/MCInit/InitPotentials/InitRotDensity (mc_main.cc:110-238) ---- */
+int  pimcgpu_init(const pimcgpu_system *sys, const pimcgpu_tables *tab);
+void pimcgpu_finalize(void);                       /* MCMemFree/Done* (mc_main.cc:495-505)  */
+const char *pimcgpu_last_error(void);
+
+/* ---- state: the arrays of mc_setup.h:176-191; chain = -1 addresses every chain ---- */
+int pimcgpu_upload_state(int chain, const double *coords, const double *angles, const int *pindex);
+int pimcgpu_download_state(int chain, double *coords, double *angles, double *cosine, int *pindex);
+
+/* ---- MRG32k3a package seed: RngStream::SetPackageSeed (rngstream.cc:346-353) ---- */
+int pimcgpu_seed(const unsigned long seed6[6]);
+
+/* ---- moves: nsteps iterations of the `time` loop body mc_main.cc:349-381 (PIMCPass :510-522)
+ *      for every chain, asynchronous on the library's stream                              ---- */
+int pimcgpu_steps(long nsteps);
+int pimcgpu_sync(void);
+long pimcgpu_step_counter(void);                   /* passTotal of mc_main.cc:346              */
+
+/* ---- estimators: the device part of MCGetAverage (mc_main.cc:551-646): GetKinEnergy,
+ *      GetPotEnergy_Densities, GetRotEnergy/GetRotE3D, GetRCF, Cv terms -> accumulators   ---- */
+int pimcgpu_measure(void);
+/* accumulator buffer (doubles): layout from pimcgpu_accum_layout, lives on the device so the
+ * host plumbing can all-reduce it in place over NCCL before the Save* writers run            */
+int    pimcgpu_accum_layout(long *n_total, long *off_scalars, long *off_gr1d, long *off_gr2d, long *off_gr3d,
+                            long *off_rcf, long *off_relbins);
+void  *pimcgpu_accum_device_ptr(void);
+int    pimcgpu_accum_download(double *host, long n);
+int    pimcgpu_accum_reset(void);                  /* MCResetBlockAverage, mc_main.cc:524-549  */
+int    pimcgpu_block_scalars(pimcgpu_scalars *out);/* reads the (possibly all-reduced) buffer  */
+int    pimcgpu_counters(double *mctotal, double *mcaccep);   /* [types][3], MCTotal/MCAccep    */
+void  *pimcgpu_stream(void);                       /* cudaStream_t the library launches on     */
+
+/* instantaneous estimator values of one chain (parity with GetKinEnergy, GetPotEnergy,
+ * GetRotEnergy|GetRotE3D, ErotSQ, Erot_termSQ; mc_estim.cc:689-1096): out[5]                 */
+int pimcgpu_chain_energies(int chain, double *out5);
+int pimcgpu_chain_rcf(int chain, double *rcf0 /* [Q] */);    /* GetRCF row 0, mc_estim.cc:1099-1139 */
+
+/* ---- batched leaf evaluations on the device (parity entry points; pure functions) ---- */
+int pimcgpu_eval_spot1d(int n, const double *r, double *v, int *klo);                 /* SPot1D  mc_poten.cc:624-639 */
+int pimcgpu_eval_lpot2d(int n, const double *r, const double *cost, double *v, int *ir, int *ic); /* LPot2D :688-729 */
+int pimcgpu_eval_srotdens(int n, const double *gamma, int which, double *v);          /* SRotDens* :548-622 */
+int pimcgpu_eval_rotden(int n, const double *eul1, const double *eul2, double *rho, double *erot, double *esq,
+                        int *index);                                                  /* rotden_ rotden.f:1-31 */
+int pimcgpu_eval_vcord(int n, const double *eul, const double *rcom, const double *rpt, double *v, double *rtc,
+                       int *index);                                                   /* vcord_ vcord.f:1-98 */
+int pimcgpu_eval_caleng(int n, const double *com1, const double *com2, const double *eul1, const double *eul2,
+                        double *e);                                                   /* caleng_ caleng_tip4p_gg.f:2-186 */
+/* PotEnergy(atom, MCCoords, it) for every atom and slice of one chain: v[N][P] (mc_piqmc.cc:1796-1965) */
+int pimcgpu_pot_energy_slice(int chain, double *v);
+/* first n uniforms of MRG32k3a stream `stream` (global stream index, 2^127 spacing): RngStream::RandU01 */
+int pimcgpu_rng_draws(long stream, int n, double *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,474 @@
+// Device-side data model, MRG32k3a streams and leaf potentials of the PIMC hot path (sm_100a).
+//
+// Layout in HBM (per chain c, all FP64):
+//   pos  [c][it][d][Npad]      beads of one imaginary-time slice are contiguous (SoA by component,
+//                              atoms fastest) so a warp sweeping partners j reads coalesced sectors
+//   ang  [c][q][3][NMpad]      (phi, cos(theta), chi) of every rotor at rot slice q
+//   cosn [c][q][3][NMpad]      unit axis vector n (MCCosine)
+//   rng  [c][S][6] uint32      MRG32k3a states: S = P (one per translational slice) + Q (one per
+//                              rotational slice) + 8 (per-chain miscellaneous)
+// Tables: the 1-D spline (grid, V, V'') and the linear-rotor density spline are staged in shared
+// memory by every CTA; the 2-D/3-D potential tables and the 181x361x361 rho/E/E^2 tables stay in
+// global memory (L2-resident working set) and are gathered with the reference's index arithmetic.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+
+namespace pimc {
+
+constexpr int MAXT = 2;
+constexpr double RZERO = 1.0e-10;                 // mc_confg.h:60
+constexpr double PI = 3.14159265358979323846;     // rotden.f:6 (== M_PI in double)
+constexpr double WNO2K = 0.6950356;               // rotden.f:6, mc_const.h:15
+
+// interaction branch of PotEnergy for an (atom0 type, atom1 type) pair, mc_piqmc.cc:1847-1958
+enum Mode : int { M_SPOT1D = 0, M_LIN_0MOL = 1, M_LIN_1MOL = 2, M_TOP_0MOL = 3, M_TOP_1MOL = 4, M_SPHER = 5, M_TOPTOP = 6 };
+
+struct Params {
+   int ntypes, N, P, Q, R, Npad, NM, NMpad;
+   int numb[MAXT], molecule[MAXT], stat[MAXT], levels[MAXT], first[MAXT + 1];
+   double lambda[MAXT], mcstep[MAXT], rtstep[MAXT];
+   double tau, rottau, beta, temperature;
+   int imtype, bstype, ispher, minimage;
+   double box[3];
+   int mode[MAXT][MAXT];
+   // tables
+   int n1d, nlut1d;  const double *g1d, *v1d, *y2_1d; const int *lut1d; double alpha, unode, c6, lut1d_scale;
+   int rs2d, cs2d;   const double *rg2d, *cg2d, *v2d; double dr2d, dc2d;
+   int rg3, thg3, chg3; const double *v3d; double rvmin, rvmax, rvstep;
+   int nrot, nlutrot; const double *rgrid, *rdens, *rderv, *resqr, *rdens2, *rderv2, *resqr2; const int *lutrot; double lutrot_scale;
+   const double *rho3, *erot3, *esq3;
+   const double *vspher;
+   // state
+   int nchains, S;
+   double *pos, *ang, *cosn;
+   int *pindex;                  // [c][N] next world line (global atom index; identity for non-bosons)
+   int *cyc_start, *cyc_atoms;   // [c][N+1], [c][N]: permutation cycles (groups moved rigidly together)
+   int *ncyc;                    // [c][MAXT]
+   uint32_t *rng;
+   double *counters;             // [c][MAXT][3][2] (total, accepted)
+   double *scratch;              // [c][64] cross-CTA partial sums
+   // execution geometry
+   int cpc, team;
+   int seg_max;
+};
+
+__host__ __device__ inline size_t pos_index(const Params &p, int c, int it, int d, int a)
+{
+   return (((size_t)c * p.P + it) * 3 + d) * p.Npad + a;
+}
+__host__ __device__ inline size_t ang_index(const Params &p, int c, int q, int d, int m)
+{
+   return (((size_t)c * p.Q + q) * 3 + d) * p.NMpad + m;
+}
+
+// ---------------------------------------------------------------------------------------------
+// MRG32k3a (L'Ecuyer), integer form of RngStream::U01 (rngstream.cc:242-265): bit-identical output
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t MRG_M1 = 4294967087u, MRG_M2 = 4294944443u;
+
+struct Mrg { uint32_t s[6]; };
+
+__device__ __forceinline__ double mrg_u01(Mrg &g)
+{
+   // component 1: p1 = (1403580*s11 - 810728*s10) mod m1, with 2^32 = 209 (mod m1)
+   uint64_t x = 1403580ull * g.s[1] + 810728ull * (uint64_t)(MRG_M1 - g.s[0]);
+   x = (x >> 32) * 209ull + (x & 0xffffffffull);
+   x = (x >> 32) * 209ull + (x & 0xffffffffull);
+   if (x >= MRG_M1) x -= MRG_M1;
+   uint32_t p1 = (uint32_t)x;
+   g.s[0] = g.s[1]; g.s[1] = g.s[2]; g.s[2] = p1;
+   // component 2: p2 = (527612*s22 - 1370589*s20) mod m2, with 2^32 = 22853 (mod m2)
+   uint64_t y = 527612ull * g.s[5] + 1370589ull * (uint64_t)(MRG_M2 - g.s[3]);
+   y = (y >> 32) * 22853ull + (y & 0xffffffffull);
+   y = (y >> 32) * 22853ull + (y & 0xffffffffull);
+   if (y >= MRG_M2) y -= MRG_M2;
+   uint32_t p2 = (uint32_t)y;
+   g.s[3] = g.s[4]; g.s[4] = g.s[5]; g.s[5] = p2;
+   const double norm = 1.0 / (4294967087.0 + 1.0);
+   return (p1 > p2) ? (double)(p1 - p2) * norm : ((double)p1 - (double)p2 + 4294967087.0) * norm;
+}
+__device__ __forceinline__ void mrg_load(Mrg &g, const uint32_t *st)
+{
+   #pragma unroll
+   for (int i = 0; i < 6; i++) g.s[i] = st[i];
+}
+__device__ __forceinline__ void mrg_store(const Mrg &g, uint32_t *st)
+{
+   #pragma unroll
+   for (int i = 0; i < 6; i++) st[i] = g.s[i];
+}
+// gauss(alpha) of mc_randg.cc:138-150: sqrt(-ln r1) cos(2 pi r2) / sqrt(alpha)
+__device__ __forceinline__ double gauss_u(double alpha, double r1, double r2)
+{
+   return sqrt(-log(r1)) * cos(2.0 * PI * r2) / sqrt(alpha);
+}
+
+// ---------------------------------------------------------------------------------------------
+// spline look-ups
+// ---------------------------------------------------------------------------------------------
+// interval index of the reference's bisection search in splint (mc_utils.cc:170-176):
+// klo = max{k : xa[k] <= x}, clamped to [0, n-2]; bucket LUT guess corrected against the grid.
+__device__ __forceinline__ int spline_klo(const double *xa, int n, const int *lut, int nlut, double scale, double x)
+{
+   int b = (int)((x - xa[0]) * scale);
+   b = b < 0 ? 0 : (b >= nlut ? nlut - 1 : b);
+   int k = lut[b];
+   while (k < n - 2 && xa[k + 1] <= x) k++;
+   while (k > 0 && xa[k] > x) k--;
+   return k;
+}
+__device__ __forceinline__ double splint_eval(const double *xa, const double *ya, const double *y2a, int klo, double x)
+{
+   int khi = klo + 1;
+   double h = xa[khi] - xa[klo];
+   double a = (xa[khi] - x) / h;
+   double b = (x - xa[klo]) / h;
+   return a * ya[klo] + b * ya[khi] + ((a * a * a - a) * y2a[klo] + (b * b * b - b) * y2a[khi]) * (h * h) / 6.;
+}
+
+// shared-memory (or global) views of the small tables, set up once per CTA
+struct SmallTables {
+   const double *g1d, *v1d, *y2_1d; const int *lut1d;
+   const double *rgrid, *rdens, *rdens2; const int *lutrot;
+};
+
+// SPot1D, mc_poten.cc:624-639
+__device__ __forceinline__ double spot1d(const Params &p, const SmallTables &t, double r, int *klo_out = nullptr)
+{
+   int n = p.n1d;
+   if (klo_out) *klo_out = -1;
+   if (r >= t.g1d[n - 1]) return -p.c6 / pow(r, 6.0);
+   if (r <= t.g1d[0]) return p.unode * exp(-p.alpha * r);
+   int k = spline_klo(t.g1d, n, t.lut1d, p.nlut1d, p.lut1d_scale, r);
+   if (klo_out) *klo_out = k;
+   return splint_eval(t.g1d, t.v1d, t.y2_1d, k, r);
+}
+
+// LPot2D, mc_poten.cc:688-729
+__device__ __forceinline__ double lpot2d(const Params &p, double r, double cost, int *pir = nullptr, int *pic = nullptr)
+{
+   double rmin = __ldg(p.rg2d), cmin = __ldg(p.cg2d);
+   int ir = (int)floor((r - rmin) / p.dr2d);
+   int ic = (int)floor((cost - cmin) / p.dc2d);
+   if (ir < 0) ir = 0; else if (ir >= p.rs2d - 1) ir = p.rs2d - 2;
+   if (ic < 0) ic = 0; else if (ic >= p.cs2d - 1) ic = p.cs2d - 2;
+   if (pir) *pir = ir;
+   if (pic) *pic = ic;
+   const double *row0 = p.v2d + (size_t)ir * p.cs2d + ic;
+   const double *row1 = row0 + p.cs2d;
+   double y1 = __ldg(row0), y4 = __ldg(row0 + 1), y2 = __ldg(row1), y3 = __ldg(row1 + 1);
+   double r1 = __ldg(p.rg2d + ir), r2 = __ldg(p.rg2d + ir + 1);
+   double c1 = __ldg(p.cg2d + ic), c2 = __ldg(p.cg2d + ic + 1);
+   double dr = (r - r1) / (r2 - r1);
+   double dc = (cost - c1) / (c2 - c1);
+   return (1.0 - dr) * (1.0 - dc) * y1 + dr * (1.0 - dc) * y2 + dr * dc * y3 + (1.0 - dr) * dc * y4;
+}
+
+// SRotDens / SRotDensDeriv / SRotDensEsqrt, mc_poten.cc:548-622 (which = 0,1,2)
+__device__ __forceinline__ double srot_eval(const Params &p, const double *g, const double *y, const double *y2,
+                                            const int *lut, double gamma, int which)
+{
+   int size = p.nrot;
+   if (gamma > g[size - 1]) return which == 0 ? y[size - 1] : 0.0;
+   if (gamma < g[0]) {
+      double rl = g[0], rr = g[1];
+      double salpha = (y[1] - y[0]) / (rr - rl);
+      double sbeta = (y[0] * rr - y[1] * rl) / (rr - rl);
+      return salpha * gamma + sbeta;
+   }
+   int k = spline_klo(g, size, lut, p.nlutrot, p.lutrot_scale, gamma);
+   return splint_eval(g, y, y2, k, gamma);
+}
+__device__ __forceinline__ double srotdens(const Params &p, const SmallTables &t, double gamma)
+{
+   return srot_eval(p, t.rgrid, t.rdens, t.rdens2, t.lutrot, gamma, 0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// rigid-body leaves
+// ---------------------------------------------------------------------------------------------
+struct Mat3 { double m[3][3]; };   // m[i][j] = rotmat(i+1, j+1)
+
+// matpre, rotden.f:136-163; eul = (phi, theta, chi)
+__device__ __forceinline__ void matpre(double phi, double theta, double chi, Mat3 &r)
+{
+   double sp, cp, st, ct, sk, ck;
+   sincos(phi, &sp, &cp);
+   sincos(theta, &st, &ct);
+   sincos(chi, &sk, &ck);
+   r.m[0][0] = cp * ct * ck - sp * sk;
+   r.m[0][1] = -cp * ct * sk - sp * ck;
+   r.m[0][2] = cp * st;
+   r.m[1][0] = sp * ct * ck + cp * sk;
+   r.m[1][1] = -sp * ct * sk + cp * ck;
+   r.m[1][2] = sp * st;
+   r.m[2][0] = -st * ck;
+   r.m[2][1] = st * sk;
+   r.m[2][2] = ct;
+}
+__device__ __forceinline__ double within(double v) { return v > 1.0 ? 1.0 : (v < -1.0 ? -1.0 : v); }
+
+// Euler angles of R = R1^T R2 (deleul, rotden.f:32-134), radians
+__device__ __forceinline__ void deleul(const Mat3 &r1, const Mat3 &r2, double &phi2, double &theta2, double &chi2)
+{
+   const double small = 1.0e-08;
+   double m[3][3];
+   #pragma unroll
+   for (int i = 0; i < 3; i++)
+      #pragma unroll
+      for (int j = 0; j < 3; j++) {
+         double s = 0.0;
+         #pragma unroll
+         for (int k = 0; k < 3; k++) s = s + r1.m[k][i] * r2.m[k][j];
+         m[i][j] = s;
+      }
+   double cost = within(m[2][2]);
+   theta2 = acos(cost);
+   double sint = sin(theta2);
+   if (fabs(1.0 - cost) < small) {
+      phi2 = 0.0;
+      double cchi = within(m[0][0]), schi = within(m[1][0]);
+      chi2 = (schi > 0.0) ? acos(cchi) : 2.0 * PI - acos(cchi);
+   } else if (fabs(1.0 + cost) < small) {
+      phi2 = 0.0;
+      double cchi = within(m[1][1]), schi = within(m[0][1]);
+      chi2 = (schi > 0.0) ? acos(cchi) : 2.0 * PI - acos(cchi);
+   } else {
+      double cphi = within(m[0][2] / sint), sphi = within(m[1][2] / sint);
+      double cchi = within(-m[2][0] / sint), schi = within(m[2][1] / sint);
+      phi2 = (sphi > 0.0) ? acos(cphi) : 2.0 * PI - acos(cphi);
+      chi2 = (schi > 0.0) ? acos(cchi) : 2.0 * PI - acos(cchi);
+   }
+}
+
+// rotden_ (rotden.f:1-31) + rotpro (rotpro_sub.f:1-64).  Returns rho; erot/esq only when the
+// pointers are non-null (moves need rho alone).  *istop mirrors the Fortran's out-of-range flag.
+__device__ __forceinline__ double rotden(const Params &p, const Mat3 &r1, const Mat3 &r2, double *rel, double *erot,
+                                         double *esq, int *index, int *istop)
+{
+   double phi, theta, chi;
+   deleul(r1, r2, phi, theta, chi);
+   if (rel) { rel[0] = phi; rel[1] = theta; rel[2] = chi; }
+   phi = phi * 180.0 / PI;
+   theta = theta * 180.0 / PI;
+   chi = chi * 180.0 / PI;
+   int ichi = (int)chi, iphi = (int)phi, itheta = (int)theta;
+   if (ichi > 360 || ichi < 0) { ichi = 0; if (istop) *istop = 1; }
+   if (iphi > 360 || iphi < 0) { iphi = 0; if (istop) *istop = 1; }
+   if (itheta > 180 || itheta < 0) { itheta = 0; if (istop) *istop = 1; }
+   int ind = (itheta * 361 + iphi) * 361 + ichi;
+   if (index) *index = ind;
+   int kc = (ichi != 360) ? ind + 1 : ind;
+   int kp = (iphi != 360) ? ind + 361 : ind;
+   int kt = (itheta != 180) ? ind + 361 * 361 : ind;
+   double fc = chi - (double)ichi, fp = phi - (double)iphi, ft = theta - (double)itheta;
+   double rho0 = __ldg(p.rho3 + ind);
+   double rho = rho0 + (__ldg(p.rho3 + kc) - rho0) * fc + (__ldg(p.rho3 + kp) - rho0) * fp + (__ldg(p.rho3 + kt) - rho0) * ft;
+   if (erot) {
+      double e0 = __ldg(p.erot3 + ind);
+      double e = e0 + (__ldg(p.erot3 + kc) - e0) * fc + (__ldg(p.erot3 + kp) - e0) * fp + (__ldg(p.erot3 + kt) - e0) * ft;
+      *erot = e / WNO2K;
+      double q0 = __ldg(p.esq3 + ind);
+      double q = q0 + (__ldg(p.esq3 + kc) - q0) * fc + (__ldg(p.esq3 + kp) - q0) * fp + (__ldg(p.esq3 + kt) - q0) * ft;
+      *esq = q / (WNO2K * WNO2K);
+   }
+   return rho;
+}
+
+// vcord_ (vcord.f:1-98) + vcalc (vcalc.f:1-65) for a rotor with rotation matrix `rm` at `rcom`
+// and a point particle at `rpt`.  rtc (optional) receives radret, theret, chiret.
+__device__ __forceinline__ double vcord(const Params &p, const Mat3 &rm, const double *rcom, const double *rpt,
+                                        double *rtc, int *index)
+{
+   const double small = 1.0e-08, bo2ang = 0.529177249;
+   double R[3] = {rpt[0] - rcom[0], rpt[1] - rcom[1], rpt[2] - rcom[2]};
+   // hatx, haty, hatz = columns of the rotation matrix (rottrn of the unit vectors)
+   double dx = 0.0, dy = 0.0, dz = 0.0, nz = 0.0, rr = 0.0;
+   #pragma unroll
+   for (int i = 0; i < 3; i++) {
+      dx = dx + R[i] * rm.m[i][0];
+      dy = dy + R[i] * rm.m[i][1];
+      dz = dz + rm.m[i][2] * R[i];
+      nz = nz + rm.m[i][2] * rm.m[i][2];
+      rr = rr + R[i] * R[i];
+   }
+   double radwff = sqrt(rr);
+   double ca = dz / (sqrt(nz) * radwff);
+   ca = ca > 1.0 ? 1.0 : (ca < -1.0 ? -1.0 : ca);
+   double thewff = acos(ca);
+   double chiwff;
+   if (fabs(dx) < small) chiwff = PI / 2.0;
+   else chiwff = atan(fabs(dy / dx));
+   double chiret;
+   if (dx >= 0.0 && dy >= 0.0) chiret = chiwff;
+   else if (dx < 0.0 && dy >= 0.0) chiret = PI - chiwff;
+   else if (dx < 0.0 && dy < 0.0) chiret = PI + chiwff;
+   else chiret = 2 * PI - chiwff;
+   if (rtc) { rtc[0] = radwff; rtc[1] = thewff; rtc[2] = chiret; }
+   if (p.chg3 == 181) { chiwff = chiret; if (chiret > PI) chiwff = 2 * PI - chiret; }
+   else if (p.chg3 == 361) chiwff = chiret;
+   double r = radwff / bo2ang;
+   double theta = thewff * 180.0 / PI;
+   double chi = chiwff * 180.0 / PI;
+   // vcalc
+   int maxrpt = p.rg3 - 1, mxthpt = p.thg3 - 1, mxchpt = p.chg3 - 1;
+   if (r < p.rvmin) r = p.rvmin;
+   if (r > p.rvmax) r = p.rvmax;
+   int ir = (int)((r - p.rvmin) / p.rvstep);
+   // "index sits on the last grid line" is decided on the doubles (theta, chi >= 0 here), not by comparing the
+   // clamped integers: ptxas 12.9 fuses min/max/compare into a predicated VIMNMX whose predicate came out
+   // inverted on sm_100a (angular gradient terms silently dropped) -- see DESIGN.md "Toolchain notes".
+   const bool th_last = !(theta < (double)mxthpt), ch_last = !(chi < (double)mxchpt);
+   int ith = th_last ? mxthpt : (int)theta;
+   int ich = ch_last ? mxchpt : (int)chi;
+   if (ith < 0) ith = 0;
+   if (ich < 0) ich = 0;
+   int ind = (ir * p.thg3 + ith) * p.chg3 + ich;
+   if (index) *index = ind;
+   double v0 = __ldg(p.v3d + ind);
+   double gradr = 0.0, delr = 0.0;
+   if (ir != maxrpt) { gradr = (__ldg(p.v3d + ind + p.thg3 * p.chg3) - v0) / p.rvstep; delr = r - (p.rvmin + ir * p.rvstep); }
+   const double gradth = __ldg(p.v3d + (th_last ? ind : ind + p.chg3)) - v0;
+   const double delth = th_last ? 0.0 : theta - (double)ith;
+   const double gradch = __ldg(p.v3d + (ch_last ? ind : ind + 1)) - v0;
+   const double delch = ch_last ? 0.0 : chi - (double)ich;
+#ifdef PIMC_VCORD_DEBUG
+   printf("dbg ir %d ith %d ich %d mx %d %d %d gr %g dr %g gt %g dt %g gc %g dc %g theta %.12g chi %.12g\n", ir, ith, ich, maxrpt, mxthpt, mxchpt, gradr, delr, gradth, delth, gradch, delch, theta, chi);
+#endif
+   return v0 + gradr * delr + gradth * delth + gradch * delch;
+}
+
+// vspher_, vspher.f:519-543 (r in Angstrom)
+__device__ __forceinline__ double vspher(const Params &p, double r)
+{
+   const double r0 = 3.0, rmax = 26.0, rstep = 0.046, ang2bo = 0.5291772;
+   r = r / ang2bo;
+   if (r < r0) r = r0;
+   if (r > rmax) r = rmax;
+   int ir = (int)((r - r0) / rstep);
+   double v0 = __ldg(p.vspher + ir);
+   if (ir == 500) return v0;
+   double gradr = (__ldg(p.vspher + ir + 1) - v0) / rstep;
+   return v0 + gradr * (r - (r0 + ir * rstep));
+}
+
+// TIP4P site frame: rottrn of the four body-frame sites (caleng_tip4p_gg.f:37-94)
+struct Tip4pSites { double o[3], m[3], h1[3], h2[3]; };
+__device__ __forceinline__ void tip4p_sites(const Mat3 &r, const double *com, Tip4pSites &s)
+{
+   #pragma unroll
+   for (int i = 0; i < 3; i++) {
+      // rsf(i) = rcom(i) + sum_j rotmat(i,j)*rwf(j), body sites O(0,0,.06562) M(0,0,-.08438) H(+-.7557,0,-.5223)
+      // (the zero components of the body-frame sites add exact zeros and are dropped)
+      s.o[i]  = com[i] + r.m[i][2] * 0.06562;
+      s.m[i]  = com[i] + r.m[i][2] * -0.08438;
+      s.h1[i] = (com[i] + r.m[i][0] * 0.7557) + r.m[i][2] * -0.5223;
+      s.h2[i] = (com[i] + r.m[i][0] * -0.7557) + r.m[i][2] * -0.5223;
+   }
+}
+__device__ __forceinline__ double dist2(const double *a, const double *b)
+{
+   double s = 0.0;
+   #pragma unroll
+   for (int i = 0; i < 3; i++) s = s + (a[i] - b[i]) * (a[i] - b[i]);
+   return s;
+}
+// caleng_, caleng_tip4p_gg.f:95-183
+__device__ __forceinline__ double caleng(const Tip4pSites &a, const Tip4pSites &b)
+{
+   const double qm = -1.04, qh = 0.520, br2ang = 0.52917721092, hr2k = 3.1577465e5, kcal2k = 503.218978939;
+   double roo = dist2(a.o, b.o);
+   double rmm = sqrt(dist2(a.m, b.m));
+   double roo4 = roo * roo, roo6 = roo4 * roo, roo12 = roo6 * roo6;
+   double v_o2lj = 6.0e5 / roo12 - 610.0 / roo6;
+   double rhm1 = sqrt(dist2(a.m, b.h1)), rhm2 = sqrt(dist2(a.m, b.h2));
+   double rhm3 = sqrt(dist2(b.m, a.h1)), rhm4 = sqrt(dist2(b.m, a.h2));
+   double rhh1 = sqrt(dist2(a.h1, b.h1)), rhh2 = sqrt(dist2(a.h1, b.h2));
+   double rhh3 = sqrt(dist2(a.h2, b.h1)), rhh4 = sqrt(dist2(a.h2, b.h2));
+   double v_mh = qm * qh * (1.0 / rhm1 + 1.0 / rhm2 + 1.0 / rhm3 + 1.0 / rhm4);
+   double v_hh = qh * qh * (1.0 / rhh1 + 1.0 / rhh2 + 1.0 / rhh3 + 1.0 / rhh4);
+   double v_mm = qm * qm * (1.0 / rmm);
+   return v_o2lj * kcal2k + (v_mh + v_mm + v_hh) * hr2k * br2ang;
+}
+
+// ---------------------------------------------------------------------------------------------
+// one pair term of PotEnergy (mc_piqmc.cc:1822-1959): atom0 with bead position pos0 against atom1
+// at slice `it` of chain c.  rm0/n0 (optional) override atom0's stored orientation: PotRotE3D's
+// Eulang argument (mc_piqmc.cc:2046-2151) and PotRotEnergy's cosine argument (:1967-2044).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int type_of(const Params &p, int atom) { return atom < p.first[1] ? 0 : 1; }
+
+__device__ __forceinline__ void load_rotmat(const Params &p, int c, int q, int m, Mat3 &r)
+{
+   double phi = p.ang[ang_index(p, c, q, 0, m)];
+   double cth = p.ang[ang_index(p, c, q, 1, m)];
+   double chi = p.ang[ang_index(p, c, q, 2, m)];
+   matpre(phi, acos(cth), chi, r);
+}
+
+__device__ __forceinline__ double pair_energy(const Params &p, const SmallTables &t, int c, int atom0, const double *pos0,
+                                              int atom1, int it, const Mat3 *rm0, const double *n0)
+{
+   int type0 = type_of(p, atom0), type1 = type_of(p, atom1);
+   int mode = p.mode[type0][type1];
+   double p1[3], dr[3], dr2 = 0.0;
+   #pragma unroll
+   for (int d = 0; d < 3; d++) {
+      p1[d] = p.pos[pos_index(p, c, it, d, atom1)];
+      dr[d] = pos0[d] - p1[d];
+      if (p.minimage) dr[d] -= p.box[d] * rint(dr[d] / p.box[d]);
+      dr2 += dr[d] * dr[d];
+   }
+   int q = it / p.R;
+   switch (mode) {
+   case M_LIN_0MOL: case M_LIN_1MOL: {
+      double r = sqrt(dr2);
+      double n[3];
+      int sgn;
+      if (mode == M_LIN_0MOL) {
+         sgn = -1;
+         if (n0) { n[0] = n0[0]; n[1] = n0[1]; n[2] = n0[2]; }
+         else { int m = atom0 - p.first[p.imtype]; for (int d = 0; d < 3; d++) n[d] = p.cosn[ang_index(p, c, q, d, m)]; }
+      } else {
+         sgn = 1;
+         int m = atom1 - p.first[p.imtype];
+         for (int d = 0; d < 3; d++) n[d] = p.cosn[ang_index(p, c, q, d, m)];
+      }
+      double cost = 0.0;
+      #pragma unroll
+      for (int d = 0; d < 3; d++) cost += n[d] * dr[d];
+      cost /= r;
+      cost *= sgn;
+      return lpot2d(p, r, cost);
+   }
+   case M_TOP_0MOL: {
+      Mat3 rl;
+      const Mat3 *rm = rm0;
+      if (!rm) { load_rotmat(p, c, q, atom0 - p.first[p.imtype], rl); rm = &rl; }
+      return vcord(p, *rm, pos0, p1, nullptr, nullptr);
+   }
+   case M_TOP_1MOL: {
+      Mat3 rl;
+      load_rotmat(p, c, q, atom1 - p.first[p.imtype], rl);
+      return vcord(p, rl, p1, pos0, nullptr, nullptr);
+   }
+   case M_SPHER:
+      return vspher(p, sqrt(dr2));
+   case M_TOPTOP: {
+      Mat3 ra, rb;
+      const Mat3 *rm = rm0;
+      if (!rm) { load_rotmat(p, c, q, atom0 - p.first[p.imtype], ra); rm = &ra; }
+      load_rotmat(p, c, q, atom1 - p.first[p.imtype], rb);
+      Tip4pSites sa, sb;
+      tip4p_sites(*rm, pos0, sa);
+      tip4p_sites(rb, p1, sb);
+      return caleng(sa, sb);
+   }
+   default:
+      return spot1d(p, t, sqrt(dr2));
+   }
+}
+
+} // namespace pimc

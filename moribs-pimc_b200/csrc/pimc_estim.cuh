@@ -1,0 +1,337 @@
+// Per-slice estimator sums on the device: GetKinEnergy, GetPotEnergy_Densities, GetRotEnergy /
+// GetRotE3D, GetRCF and the Cv algebra of MCGetAverage (mc_estim.cc:500-1139, mc_main.cc:551-616).
+//
+// Each estimator kernel uses EB blocks per chain; a block reduces its share in a fixed order and
+// writes one partial per quantity, est_finalize adds the partials in block order and the chains in
+// chain order (deterministic).  Histogram counts are integer-valued, so they are accumulated with
+// FP64 atomics straight into the block accumulator buffer (order-independent).
+#pragma once
+#include "pimc_device.cuh"
+
+namespace pimc {
+
+constexpr int EST_BLOCKS = 16;       // blocks per chain in the estimator kernels
+constexpr int EST_THREADS = 256;
+constexpr int NPART = 8;             // partial slots per block: r2avr, pot, srot, sesq, setermsq
+constexpr int BINSR = 300, BINST = 50, BINSC = 100;          // mc_estim.cc:25-27
+constexpr double MAX_RADIUS = 15.0, MIN_RADIUS = 0.0;        // mc_estim.cc:29-30
+
+struct EstBuffers {
+   double *partials;      // [c][EST_BLOCKS][NPART]
+   double *chain_e;       // [c][8]: skin, spot, srot, ErotSQ, Erot_termSQ
+   double *chain_rcf;     // [c][Q]
+   double *acc;           // accumulator buffer
+   long off_gr1d, off_gr2d, off_gr3d, off_rcf, off_relbins;
+   int has_gr3d;
+   const int *pairs;      // [npairs][2]
+   int npairs;
+};
+
+__device__ __forceinline__ double block_sum(double v, double *red)
+{
+   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+   int warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+   __syncthreads();
+   if ((threadIdx.x & 31) == 0) red[warp] = v;
+   __syncthreads();
+   double s = 0.0;
+   for (int w = 0; w < nwarp; w++) s += red[w];
+   return s;
+}
+
+__device__ __forceinline__ void bin_r(const EstBuffers &e, double r, int *bin)
+{
+   const double delta_radius = (MAX_RADIUS - MIN_RADIUS) / (double)BINSR;
+   *bin = (int)floor((r - MIN_RADIUS) / delta_radius);
+}
+
+// one thread-block slice of all three energy estimators for chain c = blockIdx.x / EST_BLOCKS
+__global__ void __launch_bounds__(EST_THREADS)
+est_energy_kernel(const __grid_constant__ Params p, const __grid_constant__ EstBuffers e, int with_dens)
+{
+   extern __shared__ double smem[];
+   double *red = smem;
+   const int c = blockIdx.x / EST_BLOCKS, b = blockIdx.x % EST_BLOCKS;
+   const int P = p.P, N = p.N, Q = p.Q;
+   const int gt = b * blockDim.x + threadIdx.x, nt = EST_BLOCKS * blockDim.x;
+   SmallTables t;
+   t.g1d = p.g1d; t.v1d = p.v1d; t.y2_1d = p.y2_1d; t.lut1d = p.lut1d;
+   t.rgrid = p.rgrid; t.rdens = p.rdens; t.rdens2 = p.rdens2; t.lutrot = p.lutrot;
+   const double delta_theta = PI / (double)(BINST - 1), delta_chi = 2.0 * PI / (double)(BINSC - 1);
+
+   // ---- GetKinEnergy, mc_estim.cc:876-937: sum_atoms sum_it |r_it - r_it+1|^2 / (4 beta lambda)
+   double r2 = 0.0;
+   for (long i = gt; i < (long)N * P; i += nt) {
+      int a = (int)(i % N), it = (int)(i / N);
+      int type = type_of(p, a);
+      int a1 = a, it1 = it + 1;
+      if (it1 == P) { it1 = 0; if (p.stat[type] == 1) a1 = p.pindex[(size_t)c * N + a]; }
+      double s = 0.0;
+      #pragma unroll
+      for (int d = 0; d < 3; d++) {
+         double dr = p.pos[pos_index(p, c, it, d, a)] - p.pos[pos_index(p, c, it1, d, a1)];
+         if (p.minimage) dr -= p.box[d] * rint(dr / p.box[d]);
+         s += dr * dr;
+      }
+      r2 += s / (4.0 * p.beta * p.lambda[type]);
+   }
+   r2 = block_sum(r2, red);
+
+   // ---- GetPotEnergy_Densities, mc_estim.cc:500-687
+   double pot = 0.0;
+   for (long i = gt; i < (long)e.npairs * P; i += nt) {
+      int pi = (int)(i % e.npairs), it = (int)(i / e.npairs);
+      int a0 = e.pairs[2 * pi], a1 = e.pairs[2 * pi + 1];
+      int mode = p.mode[type_of(p, a0)][type_of(p, a1)];
+      double p0[3], p1[3], dr[3], dr2 = 0.0;
+      #pragma unroll
+      for (int d = 0; d < 3; d++) {
+         p0[d] = p.pos[pos_index(p, c, it, d, a0)];
+         p1[d] = p.pos[pos_index(p, c, it, d, a1)];
+         dr[d] = p0[d] - p1[d];
+         if (p.minimage) dr[d] -= p.box[d] * rint(dr[d] / p.box[d]);
+         dr2 += dr[d] * dr[d];
+      }
+      int q = it / p.R;
+      if (mode == M_LIN_0MOL || mode == M_LIN_1MOL) {
+         double r = sqrt(dr2);
+         int m = ((mode == M_LIN_0MOL) ? a0 : a1) - p.first[p.imtype];
+         double cost = 0.0;
+         #pragma unroll
+         for (int d = 0; d < 3; d++) cost += p.cosn[ang_index(p, c, q, d, m)] * dr[d];
+         cost /= r;
+         cost *= (mode == M_LIN_0MOL) ? -1 : 1;
+         if (with_dens) {          // bin_2Ddensity, mc_estim.cc:1233-1250
+            int br; bin_r(e, r, &br);
+            if (br < BINSR && br >= 0) {
+               int bt = (int)floor(acos(cost) / delta_theta);
+               if (bt < BINST && bt >= 0) atomicAdd(e.acc + e.off_gr2d + br * BINST + bt, 1.0);
+            }
+         }
+         pot += lpot2d(p, r, cost);
+      } else if (mode == M_TOP_0MOL || mode == M_TOP_1MOL || mode == M_SPHER) {
+         double rtc[3], v;
+         if (p.ispher == 0) {
+            Mat3 rm;
+            if (mode == M_TOP_0MOL) { load_rotmat(p, c, q, a0 - p.first[p.imtype], rm); v = vcord(p, rm, p0, p1, rtc, nullptr); }
+            else { load_rotmat(p, c, q, a1 - p.first[p.imtype], rm); v = vcord(p, rm, p1, p0, rtc, nullptr); }
+         } else {
+            // vspher_ overwrites its r argument with the clamped value in bohr, which is then binned (mc_estim.cc:631-637)
+            double r = sqrt(dr2);
+            v = vspher(p, r);
+            double rb = r / 0.5291772;
+            rb = rb < 3.0 ? 3.0 : (rb > 26.0 ? 26.0 : rb);
+            rtc[0] = rb; rtc[1] = 0.0; rtc[2] = 0.0;
+         }
+         if (with_dens && e.has_gr3d) {   // bin_3Ddensity, mc_estim.cc:1252-1273
+            int br; bin_r(e, rtc[0], &br);
+            if (br < BINSR && br >= 0) {
+               int bt = (int)floor(rtc[1] / delta_theta);
+               if (bt < BINST && bt >= 0) {
+                  int bc = (int)floor(rtc[2] / delta_chi);
+                  if (bc < BINSC && bc >= 0) atomicAdd(e.acc + e.off_gr3d + ((size_t)br * BINST + bt) * BINSC + bc, 1.0);
+               }
+            }
+         }
+         pot += v;
+      } else if (mode == M_TOPTOP) {
+         Mat3 ra, rb;
+         load_rotmat(p, c, q, a0 - p.first[p.imtype], ra);
+         load_rotmat(p, c, q, a1 - p.first[p.imtype], rb);
+         Tip4pSites sa, sb;
+         tip4p_sites(ra, p0, sa);
+         tip4p_sites(rb, p1, sb);
+         pot += caleng(sa, sb);
+      } else {
+         double r = sqrt(dr2);
+         if (with_dens) { int br; bin_r(e, r, &br); if (br < BINSR && br >= 0) atomicAdd(e.acc + e.off_gr1d + br, 1.0); }
+         pot += spot1d(p, t, r);
+      }
+   }
+   pot = block_sum(pot, red);
+
+   // ---- GetRotE3D (mc_estim.cc:989-1096) / GetRotEnergy (:939-987), RotDenType 0
+   double srot = 0.0, sesq = 0.0, sterm = 0.0;
+   if (Q > 0 && p.imtype >= 0) {
+      const int nm = p.numb[p.imtype];
+      const bool top = p.molecule[p.imtype] == 2;
+      for (int i = gt; i < nm * Q; i += nt) {
+         int m = i / Q, q0 = i % Q, q1 = (q0 + 1) % Q;
+         if (top) {
+            Mat3 r0, r1;
+            load_rotmat(p, c, q0, m, r0);
+            load_rotmat(p, c, q1, m, r1);
+            double rel[3], erot, esq;
+            rotden(p, r0, r1, rel, &erot, &esq, nullptr, nullptr);
+            if (with_dens) {
+               int bt = (int)floor(rel[1] / delta_theta);
+               if (bt < BINST && bt >= 0) atomicAdd(e.acc + e.off_relbins + bt, 1.0);
+               int bp = (int)floor(rel[0] / delta_chi);
+               if (bp < BINSC && bp >= 0) atomicAdd(e.acc + e.off_relbins + BINST + bp, 1.0);
+               int bc = (int)floor(rel[2] / delta_chi);
+               if (bc < BINSC && bc >= 0) atomicAdd(e.acc + e.off_relbins + BINST + BINSC + bc, 1.0);
+            }
+            srot += erot / (double)Q;
+            sesq += esq / ((double)Q * (double)Q);
+            sterm += erot * erot / ((double)Q * (double)Q);
+         } else if (m == 0) {
+            double p0 = 0.0;
+            #pragma unroll
+            for (int d = 0; d < 3; d++) p0 += p.cosn[ang_index(p, c, q0, d, 0)] * p.cosn[ang_index(p, c, q1, d, 0)];
+            double rdens = srot_eval(p, p.rgrid, p.rdens, p.rdens2, p.lutrot, p0, 0);
+            double rderv = srot_eval(p, p.rgrid, p.rderv, p.rderv2, p.lutrot, p0, 1);
+            double resqr = srot_eval(p, p.rgrid, p.resqr, p.resqr2, p.lutrot, p0, 2);
+            if (fabs(rdens) > RZERO) srot += rderv / rdens;
+            sterm += (rderv / rdens) * (rderv / rdens);
+            sesq += resqr / rdens;
+         }
+      }
+   }
+   srot = block_sum(srot, red);
+   sesq = block_sum(sesq, red);
+   sterm = block_sum(sterm, red);
+   if (threadIdx.x == 0) {
+      double *o = e.partials + ((size_t)c * EST_BLOCKS + b) * NPART;
+      o[0] = r2; o[1] = pot; o[2] = srot; o[3] = sesq; o[4] = sterm;
+   }
+}
+
+// GetRCF row 0 (mc_estim.cc:1099-1139): rcf[itc] = sum_it0 n(it0).n(it0+itc) for the first rotor
+__global__ void est_rcf_kernel(const __grid_constant__ Params p, const __grid_constant__ EstBuffers e)
+{
+   const int c = blockIdx.y, Q = p.Q;
+   const int itc = blockIdx.x * blockDim.x + threadIdx.x;
+   if (itc >= Q) return;
+   double s = 0.0;
+   for (int it0 = 0; it0 < Q; it0++) {
+      int tc = (it0 + itc) % Q;
+      double p0 = 0.0;
+      #pragma unroll
+      for (int d = 0; d < 3; d++) p0 += p.cosn[ang_index(p, c, it0, d, 0)] * p.cosn[ang_index(p, c, tc, d, 0)];
+      s += p0;
+   }
+   e.chain_rcf[(size_t)c * Q + itc] = s;
+}
+
+// per-chain totals, Cv algebra (mc_main.cc:589-616), accumulation in chain order
+__global__ void est_finalize_kernel(const __grid_constant__ Params p, const __grid_constant__ EstBuffers e, int accumulate)
+{
+   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+   const int Q = p.Q;
+   if (tid == 0) {
+      for (int c = 0; c < p.nchains; c++) {
+         double r2 = 0, pot = 0, srot = 0, sesq = 0, sterm = 0;
+         for (int b = 0; b < EST_BLOCKS; b++) {
+            const double *o = e.partials + ((size_t)c * EST_BLOCKS + b) * NPART;
+            r2 += o[0]; pot += o[1]; srot += o[2]; sesq += o[3]; sterm += o[4];
+         }
+         double skin = (double)p.P * p.temperature * (0.5 * (double)(3 * p.N) - r2);
+         double spot = pot / (double)p.P;
+         double *ce = e.chain_e + (size_t)c * 8;
+         ce[0] = skin; ce[1] = spot; ce[2] = srot; ce[3] = sesq; ce[4] = sterm;
+         if (accumulate) {
+            double nd = (double)(3 * p.N);
+            double kterm = nd * 0.5 / p.tau - skin;
+            double sCv = -0.5 * nd / (p.beta * p.tau) - (kterm - spot - srot) * (kterm - spot - srot) + (2.0 / p.beta) * (0.5 * nd / p.tau - skin) + sterm - sesq;
+            double sCv_trans = -0.5 * nd / (p.beta * p.tau) - kterm * kterm + (2.0 / p.beta) * (0.5 * nd / p.tau - skin);
+            double sCv_rot = -srot * srot + sterm - sesq;
+            double *a = e.acc;
+            a[0] += 1.0; a[1] += skin; a[2] += spot; a[3] += srot; a[4] += sesq; a[5] += sCv; a[6] += sCv_trans; a[7] += sCv_rot;
+         }
+      }
+   }
+   if (accumulate && Q > 0)
+      for (int itc = tid; itc < Q; itc += gridDim.x * blockDim.x) {
+         double s = 0.0;
+         for (int c = 0; c < p.nchains; c++) s += e.chain_rcf[(size_t)c * Q + itc];
+         e.acc[e.off_rcf + itc] += s;
+      }
+}
+
+// MCTotal/MCAccep of every chain folded into the accumulator scalars (slots 8..19)
+__global__ void fold_counters_kernel(const __grid_constant__ Params p, double *acc)
+{
+   int i = threadIdx.x;       // (type, move, which) -> 12 slots
+   if (i >= MAXT * 3 * 2) return;
+   int which = i % 2, move = (i / 2) % 3, type = i / 6;
+   double s = 0.0;
+   for (int c = 0; c < p.nchains; c++) s += p.counters[(((size_t)c * MAXT + type) * 3 + move) * 2 + which];
+   acc[8 + which * 6 + type * 3 + move] = s;
+}
+
+// ---- parity kernels -----------------------------------------------------------------------------
+__global__ void eval_spot1d_kernel(const __grid_constant__ Params p, int n, const double *r, double *v, int *klo)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) return;
+   SmallTables t; t.g1d = p.g1d; t.v1d = p.v1d; t.y2_1d = p.y2_1d; t.lut1d = p.lut1d;
+   int k; v[i] = spot1d(p, t, r[i], &k); klo[i] = k;
+}
+__global__ void eval_lpot2d_kernel(const __grid_constant__ Params p, int n, const double *r, const double *c, double *v, int *ir, int *ic)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) return;
+   int a, b; v[i] = lpot2d(p, r[i], c[i], &a, &b); ir[i] = a; ic[i] = b;
+}
+__global__ void eval_srot_kernel(const __grid_constant__ Params p, int n, const double *g, int which, double *v)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) return;
+   const double *y = which == 0 ? p.rdens : which == 1 ? p.rderv : p.resqr;
+   const double *y2 = which == 0 ? p.rdens2 : which == 1 ? p.rderv2 : p.resqr2;
+   v[i] = srot_eval(p, p.rgrid, y, y2, p.lutrot, g[i], which);
+}
+__global__ void eval_rotden_kernel(const __grid_constant__ Params p, int n, const double *e1, const double *e2, double *rho, double *erot, double *esq, int *idx)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) return;
+   Mat3 a, b;
+   matpre(e1[3 * i], e1[3 * i + 1], e1[3 * i + 2], a);
+   matpre(e2[3 * i], e2[3 * i + 1], e2[3 * i + 2], b);
+   double er, es; int k, istop = 0;
+   rho[i] = rotden(p, a, b, nullptr, &er, &es, &k, &istop);
+   erot[i] = er; esq[i] = es; idx[i] = istop ? -1 - k : k;
+}
+__global__ void eval_vcord_kernel(const __grid_constant__ Params p, int n, const double *eul, const double *rcom, const double *rpt, double *v, double *rtc, int *idx)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) return;
+   Mat3 a;
+   matpre(eul[3 * i], eul[3 * i + 1], eul[3 * i + 2], a);
+   int k; v[i] = vcord(p, a, rcom + 3 * i, rpt + 3 * i, rtc + 3 * i, &k); idx[i] = k;
+}
+__global__ void eval_caleng_kernel(int n, const double *c1, const double *c2, const double *e1, const double *e2, double *e)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) return;
+   Mat3 a, b;
+   matpre(e1[3 * i], e1[3 * i + 1], e1[3 * i + 2], a);
+   matpre(e2[3 * i], e2[3 * i + 1], e2[3 * i + 2], b);
+   Tip4pSites sa, sb;
+   tip4p_sites(a, c1 + 3 * i, sa);
+   tip4p_sites(b, c2 + 3 * i, sb);
+   e[i] = caleng(sa, sb);
+}
+// PotEnergy(atom, MCCoords, it) for all (atom, it) of chain c: one warp per bead, lanes over partners
+__global__ void pot_energy_slice_kernel(const __grid_constant__ Params p, int c, double *v)
+{
+   SmallTables t; t.g1d = p.g1d; t.v1d = p.v1d; t.y2_1d = p.y2_1d; t.lut1d = p.lut1d;
+   t.rgrid = p.rgrid; t.rdens = p.rdens; t.rdens2 = p.rdens2; t.lutrot = p.lutrot;
+   int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+   if (w >= p.N * p.P) return;
+   int atom = w / p.P, it = w % p.P;
+   double p0[3];
+   for (int d = 0; d < 3; d++) p0[d] = p.pos[pos_index(p, c, it, d, atom)];
+   double s = 0.0;
+   for (int j = lane; j < p.N; j += 32)
+      if (j != atom) s += pair_energy(p, t, c, atom, p0, j, it, nullptr, nullptr);
+   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+   if (lane == 0) v[(size_t)atom * p.P + it] = s;
+}
+__global__ void rng_draws_kernel(uint32_t s0, uint32_t s1, uint32_t s2, uint32_t s3, uint32_t s4, uint32_t s5, int n, double *out)
+{
+   Mrg g; g.s[0] = s0; g.s[1] = s1; g.s[2] = s2; g.s[3] = s3; g.s[4] = s4; g.s[5] = s5;
+   for (int i = 0; i < n; i++) out[i] = mrg_u01(g);
+}
+
+} // namespace pimc

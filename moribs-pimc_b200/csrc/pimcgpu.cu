@@ -1,0 +1,693 @@
+// C ABI of the B200 PIMC hot path (include/pimcgpu.h): context set-up, table preparation,
+// state transfer, kernel launches.  Host-side numerics here (spline second derivatives, the
+// short/long-range extrapolation constants, MRG32k3a stream jumps) are this library's own
+// implementation of the published algorithms the reference uses at table-load time
+// (mc_utils.cc:112-201, mc_poten.cc:416-437, rngstream.cc:303-321).
+#include "../../include/pimcgpu.h"
+#include "pimc_device.cuh"
+#include "pimc_moves.cuh"
+#include "pimc_estim.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+using namespace pimc;
+
+namespace {
+
+std::string g_err;
+int fail(const char *fmt, ...)
+{
+   char buf[512];
+   va_list ap;
+   va_start(ap, fmt);
+   vsnprintf(buf, sizeof buf, fmt, ap);
+   va_end(ap);
+   g_err = buf;
+   return 1;
+}
+#define CK(call)                                                                            \
+   do {                                                                                     \
+      cudaError_t e_ = (call);                                                              \
+      if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+   } while (0)
+
+struct Context {
+   bool live = false;
+   pimcgpu_system sys;
+   Params p;
+   EstBuffers e;
+   cudaStream_t stream = nullptr;
+   std::vector<void *> allocs;
+   int threads = 0;
+   size_t smem = 0;
+   long step = 0;
+   long nacc = 0;
+   int *d_err = nullptr;
+   bool seeded = false;
+   std::vector<int> h_pindex;       // [c][N]
+} G;
+
+template <class T> int dalloc(T **ptr, size_t n)
+{
+   void *q = nullptr;
+   cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T));
+   if (e != cudaSuccess) return fail("cudaMalloc(%zu bytes) failed: %s", n * sizeof(T), cudaGetErrorString(e));
+   cudaMemset(q, 0, std::max<size_t>(n, 1) * sizeof(T));
+   G.allocs.push_back(q);
+   *ptr = (T *)q;
+   return 0;
+}
+template <class T> int dupload(const T **dst, const T *src, size_t n)
+{
+   T *q = nullptr;
+   if (dalloc(&q, n)) return 1;
+   cudaError_t e = cudaMemcpy(q, src, n * sizeof(T), cudaMemcpyHostToDevice);
+   if (e != cudaSuccess) return fail("cudaMemcpy H2D failed: %s", cudaGetErrorString(e));
+   *dst = q;
+   return 0;
+}
+
+// natural-cubic-spline second derivatives with clamped end slopes taken from the first/last
+// interval (Numerical-Recipes tridiagonal sweep; same choice as init_spline, mc_utils.cc:188-201)
+void spline_setup(const std::vector<double> &x, const std::vector<double> &y, std::vector<double> &y2)
+{
+   int n = (int)x.size();
+   y2.assign(n, 0.0);
+   std::vector<double> u(n, 0.0);
+   double yp1 = (y[1] - y[0]) / (x[1] - x[0]);
+   double ypn = (y[n - 1] - y[n - 2]) / (x[n - 1] - x[n - 2]);
+   y2[0] = -0.5;
+   u[0] = (3. / (x[1] - x[0])) * ((y[1] - y[0]) / (x[1] - x[0]) - yp1);
+   for (int i = 1; i < n - 1; i++) {
+      double sig = (x[i] - x[i - 1]) / (x[i + 1] - x[i - 1]);
+      double pp = sig * y2[i - 1] + 2.;
+      y2[i] = (sig - 1.) / pp;
+      double ui = (y[i + 1] - y[i]) / (x[i + 1] - x[i]) - (y[i] - y[i - 1]) / (x[i] - x[i - 1]);
+      u[i] = (6. * ui / (x[i + 1] - x[i - 1]) - sig * u[i - 1]) / pp;
+   }
+   double qn = .5;
+   double un = (3. / (x[n - 1] - x[n - 2])) * (ypn - (y[n - 1] - y[n - 2]) / (x[n - 1] - x[n - 2]));
+   y2[n - 1] = (un - qn * u[n - 2]) / (qn * y2[n - 2] + 1.);
+   for (int k = n - 2; k >= 0; k--) y2[k] = y2[k] * y2[k + 1] + u[k];
+}
+// bucket table for the interval search: lut[b] = max{k : x[k] <= x0 + b/scale} (lower bound of the bucket)
+void build_lut(const std::vector<double> &x, std::vector<int> &lut, double &scale)
+{
+   int n = (int)x.size();
+   int nl = 4 * n;
+   lut.assign(nl, 0);
+   scale = (double)nl / (x[n - 1] - x[0]);
+   int k = 0;
+   for (int b = 0; b < nl; b++) {
+      double xb = x[0] + (double)b / scale;
+      while (k < n - 2 && x[k + 1] <= xb) k++;
+      lut[b] = k;
+   }
+}
+
+// ---- MRG32k3a stream jumps in exact integer arithmetic -------------------------------------------
+typedef unsigned long long u64;
+const u64 M1 = 4294967087ull, M2 = 4294944443ull;
+// A^(2^127) of the two components (L'Ecuyer, Simard, Chen, Kelton 2002; RngStreams package constants)
+const u64 A1P127[3][3] = {{2427906178ull, 3580155704ull, 949770784ull}, {226153695ull, 1230515664ull, 3580155704ull}, {1988835001ull, 986791581ull, 1230515664ull}};
+const u64 A2P127[3][3] = {{1464411153ull, 277697599ull, 1610723613ull}, {32183930ull, 1464411153ull, 1022607788ull}, {2824425944ull, 32183930ull, 2093834863ull}};
+inline u64 mulmod(u64 a, u64 b, u64 m) { return (u64)(((unsigned __int128)a * b) % m); }
+void matvec(const u64 A[3][3], const u64 s[3], u64 v[3], u64 m)
+{
+   u64 x[3];
+   for (int i = 0; i < 3; i++) x[i] = (mulmod(A[i][0], s[0], m) + mulmod(A[i][1], s[1], m) + mulmod(A[i][2], s[2], m)) % m;
+   for (int i = 0; i < 3; i++) v[i] = x[i];
+}
+void matmat(const u64 A[3][3], const u64 B[3][3], u64 C[3][3], u64 m)
+{
+   u64 W[3][3];
+   for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) W[i][j] = (mulmod(A[i][0], B[0][j], m) + mulmod(A[i][1], B[1][j], m) + mulmod(A[i][2], B[2][j], m)) % m;
+   memcpy(C, W, sizeof W);
+}
+// state of the s-th stream declared after SetPackageSeed(seed): (A^(2^127))^s applied to the seed
+void stream_state(const u64 seed[6], u64 s, u64 st[6])
+{
+   u64 B1[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}, B2[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}, W1[3][3], W2[3][3];
+   memcpy(W1, A1P127, sizeof W1);
+   memcpy(W2, A2P127, sizeof W2);
+   while (s > 0) {
+      if (s & 1) { matmat(W1, B1, B1, M1); matmat(W2, B2, B2, M2); }
+      matmat(W1, W1, W1, M1); matmat(W2, W2, W2, M2);
+      s >>= 1;
+   }
+   matvec(B1, seed, st, M1);
+   matvec(B2, seed + 3, st + 3, M2);
+}
+
+int pow2floor(int v) { int r = 1; while (2 * r <= v) r *= 2; return r; }
+int pow2ceil(int v) { int r = 1; while (r < v) r *= 2; return r; }
+
+size_t smem_bytes(const Params &p, int threads)
+{
+   size_t d = 40;
+   auto pad = [](int n) { return (size_t)((n + 1) & ~1); };
+   auto padi = [](int n) { return (size_t)(((n + 1) / 2 + 1) & ~1); };
+   if (p.n1d) d += 3 * pad(p.n1d) + padi(p.nlut1d);
+   if (p.nrot) d += 3 * pad(p.nrot) + padi(p.nlutrot);
+   d += (size_t)(threads / p.team) * ((p.seg_max + 1) * 3);
+   return d * sizeof(double);
+}
+
+void est_shapes(dim3 &g_rcf, dim3 &b_rcf)
+{
+   b_rcf = dim3(128);
+   g_rcf = dim3((G.p.Q + 127) / 128, G.p.nchains);
+}
+
+int launch_estimators(int with_dens, int accumulate)
+{
+   est_energy_kernel<<<G.p.nchains * EST_BLOCKS, EST_THREADS, 64 * sizeof(double), G.stream>>>(G.p, G.e, with_dens);
+   if (G.p.Q > 0 && G.p.imtype >= 0) {
+      dim3 g, b;
+      est_shapes(g, b);
+      est_rcf_kernel<<<g, b, 0, G.stream>>>(G.p, G.e);
+   }
+   est_finalize_kernel<<<8, 128, 0, G.stream>>>(G.p, G.e, accumulate);
+   CK(cudaGetLastError());
+   return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *pimcgpu_last_error(void) { return g_err.c_str(); }
+
+void pimcgpu_finalize(void)
+{
+   if (!G.live) return;
+   cudaStreamSynchronize(G.stream);
+   for (void *q : G.allocs) cudaFree(q);
+   G.allocs.clear();
+   if (G.stream) cudaStreamDestroy(G.stream);
+   G.stream = nullptr;
+   G.live = false;
+   G.seeded = false;
+   G.step = 0;
+}
+
+int pimcgpu_init(const pimcgpu_system *sys, const pimcgpu_tables *tab)
+{
+   if (G.live) pimcgpu_finalize();
+   if (!sys || !tab) return fail("pimcgpu_init: null argument");
+   if (sys->ntypes < 1 || sys->ntypes > MAXT) return fail("pimcgpu_init: ntypes must be 1 or 2 (one atom type, one molecule type)");
+   if (sys->rotden_type != 0) return fail("pimcgpu_init: RotDenType=%d (rattle-and-shake propagator) is not available on the device", sys->rotden_type);
+   if (sys->nchains < 1) return fail("pimcgpu_init: nchains must be >= 1");
+   int ndev = 0;
+   cudaError_t ce = cudaGetDeviceCount(&ndev);
+   if (ce != cudaSuccess || ndev == 0) return fail("pimcgpu_init: no CUDA device available (%s)", cudaGetErrorString(ce));
+   CK(cudaSetDevice(sys->device));
+   G.sys = *sys;
+   Params &p = G.p;
+   memset(&p, 0, sizeof p);
+   p.ntypes = sys->ntypes; p.P = sys->P; p.Q = sys->Q;
+   p.N = 0; p.imtype = -1; p.bstype = -1;
+   int nmolt = 0, natomt = 0;
+   for (int t = 0; t < sys->ntypes; t++) {
+      const pimcgpu_type &T = sys->type[t];
+      if (T.numb < 1) return fail("pimcgpu_init: type %d has no particles", t);
+      p.first[t] = p.N; p.N += T.numb;
+      p.numb[t] = T.numb; p.molecule[t] = T.molecule; p.stat[t] = T.stat; p.levels[t] = T.levels;
+      p.mcstep[t] = T.mcstep; p.rtstep[t] = T.rtstep;
+      // lambda = hbar^2/2m in K A^2: 100 hbar^2/(amu k_B) with the CODATA-86 mantissas of mc_const.h:12-14
+      p.lambda[t] = 0.5 * (100.0 * (1.05457266 * 1.05457266) / (1.6605402 * 1.380658)) / T.mass;
+      if (T.stat == 1) p.bstype = t;
+      if (T.molecule) { p.imtype = t; nmolt++; } else natomt++;
+      if ((1 << T.levels) >= sys->P) return fail("pimcgpu_init: segment size 2^%d is not smaller than the number of slices %d", T.levels, sys->P);
+      if (T.molecule == 1 && T.numb > 1) return fail("pimcgpu_init: no more than one linear dopant molecule");
+   }
+   if (nmolt > 1 || natomt > 1) return fail("pimcgpu_init: no more than one atom type and one molecule type");
+   if (sys->ntypes == 2 && sys->type[0].molecule != 0) return fail("pimcgpu_init: molecules must follow atoms");
+   p.first[sys->ntypes] = p.N;
+   if (sys->ntypes == 1) p.first[2] = p.N;
+   p.Npad = (p.N + 3) & ~3;
+   p.NM = p.imtype >= 0 ? p.numb[p.imtype] : 0;
+   p.NMpad = std::max(1, p.NM);
+   p.temperature = sys->temperature;
+   p.beta = 1.0 / sys->temperature;
+   p.tau = p.beta / (double)p.P;
+   p.R = 1; p.rottau = 0.0;
+   if (p.Q > 0) {
+      if (p.imtype < 0) return fail("pimcgpu_init: ROTATION without a molecule type");
+      if (p.P % p.Q) return fail("pimcgpu_init: NumbTimes is not proportional to NumbRotTimes");
+      p.R = p.P / p.Q; p.rottau = p.beta / (double)p.Q;
+   }
+   p.ispher = sys->ispher; p.minimage = sys->minimage;
+   for (int d = 0; d < 3; d++) p.box[d] = sys->box[d];
+   if (p.ispher && p.Q > 0) return fail("pimcgpu_init: ISPHER = 1 is not compatible with ROTATION");
+   // interaction branch per (type0, type1), the if-chain of mc_piqmc.cc:1847-1958
+   for (int t0 = 0; t0 < sys->ntypes; t0++)
+      for (int t1 = 0; t1 < sys->ntypes; t1++) {
+         int m0 = p.molecule[t0], m1 = p.molecule[t1], mode;
+         if (m0 == 1 || m1 == 1) mode = (m0 == 1) ? M_LIN_0MOL : M_LIN_1MOL;
+         else if ((m0 == 2 || m1 == 2) && m0 != m1) mode = p.ispher ? M_SPHER : (m0 == 2 ? M_TOP_0MOL : M_TOP_1MOL);
+         else if (m0 == 2 && m1 == 2 && p.numb[p.imtype] > 1) mode = M_TOPTOP;
+         else mode = M_SPOT1D;
+         p.mode[t0][t1] = mode;
+      }
+   bool need1d = false, need2d = false, need3d = false, needsph = false;
+   for (int t0 = 0; t0 < sys->ntypes; t0++)
+      for (int t1 = 0; t1 < sys->ntypes; t1++) {
+         if (t0 == t1 && p.numb[t0] < 2) continue;
+         int m = p.mode[t0][t1];
+         need1d |= m == M_SPOT1D; need2d |= (m == M_LIN_0MOL || m == M_LIN_1MOL);
+         need3d |= (m == M_TOP_0MOL || m == M_TOP_1MOL); needsph |= m == M_SPHER;
+      }
+   // ---- tables ----
+   if (need1d) {
+      if (!tab->grid1d || !tab->pot1d || tab->n1d < 2) return fail("pimcgpu_init: the 1-D pair potential table is required");
+      int n = tab->n1d;
+      std::vector<double> g(tab->grid1d, tab->grid1d + n), v(tab->pot1d, tab->pot1d + n), y2;
+      spline_setup(g, v, y2);
+      // short range U0 exp(-alpha r) and long range -C6/r^6 fitted to the end intervals (mc_poten.cc:422-437)
+      p.alpha = log(v[0] / v[1]) / (g[1] - g[0]);
+      p.unode = v[0] * exp(p.alpha * g[0]);
+      p.c6 = (v[n - 1] - v[n - 2]) / (1.0 / pow(g[n - 2], 6.0) - 1.0 / pow(g[n - 1], 6.0));
+      std::vector<int> lut;
+      build_lut(g, lut, p.lut1d_scale);
+      p.n1d = n; p.nlut1d = (int)lut.size();
+      if (dupload(&p.g1d, g.data(), n) || dupload(&p.v1d, v.data(), n) || dupload(&p.y2_1d, y2.data(), n) || dupload(&p.lut1d, lut.data(), lut.size())) return 1;
+   }
+   if (need2d) {
+      if (!tab->pot2d || !tab->rgrid2d || !tab->cgrid2d) return fail("pimcgpu_init: the 2-D atom-rotor potential table is required");
+      p.rs2d = tab->rsize2d; p.cs2d = tab->csize2d; p.dr2d = tab->dr2d; p.dc2d = tab->dc2d;
+      if (dupload(&p.rg2d, tab->rgrid2d, p.rs2d) || dupload(&p.cg2d, tab->cgrid2d, p.cs2d) || dupload(&p.v2d, tab->pot2d, (size_t)p.rs2d * p.cs2d)) return 1;
+   }
+   if (need3d) {
+      if (!tab->vtable) return fail("pimcgpu_init: the 3-D atom-top potential table is required");
+      p.rg3 = tab->rgrd; p.thg3 = tab->thgrd; p.chg3 = tab->chgrd; p.rvmin = tab->rvmin; p.rvmax = tab->rvmax;
+      p.rvstep = (p.rvmax - p.rvmin) / (double)(p.rg3 - 1);
+      if (dupload(&p.v3d, tab->vtable, (size_t)p.rg3 * p.thg3 * p.chg3)) return 1;
+   }
+   if (needsph) {
+      if (!tab->vspher) return fail("pimcgpu_init: ISPHER=1 needs the 501-entry spherical table");
+      if (dupload(&p.vspher, tab->vspher, 501)) return 1;
+   }
+   if (p.Q > 0 && p.molecule[p.imtype] == 1) {
+      if (!tab->rotgrid || tab->nrot < 2) return fail("pimcgpu_init: the linear-rotor density table (.rot) is required");
+      int n = tab->nrot;
+      std::vector<double> g(tab->rotgrid, tab->rotgrid + n), y2;
+      const double *cols[3] = {tab->rotdens, tab->rotderv, tab->rotesqr};
+      const double **dst[3] = {&p.rdens, &p.rderv, &p.resqr}, **dst2[3] = {&p.rdens2, &p.rderv2, &p.resqr2};
+      for (int k = 0; k < 3; k++) {
+         std::vector<double> y(cols[k], cols[k] + n);
+         spline_setup(g, y, y2);
+         if (dupload(dst[k], y.data(), n) || dupload(dst2[k], y2.data(), n)) return 1;
+      }
+      std::vector<int> lut;
+      build_lut(g, lut, p.lutrot_scale);
+      p.nrot = n; p.nlutrot = (int)lut.size();
+      if (dupload(&p.rgrid, g.data(), n) || dupload(&p.lutrot, lut.data(), lut.size())) return 1;
+   }
+   if (p.Q > 0 && p.molecule[p.imtype] == 2) {
+      if (!tab->rho3d || !tab->erot3d || !tab->esq3d) return fail("pimcgpu_init: the rho/eng/esq density-matrix tables are required");
+      if (dupload(&p.rho3, tab->rho3d, PIMCGPU_SIZE_ROTDEN) || dupload(&p.erot3, tab->erot3d, PIMCGPU_SIZE_ROTDEN) || dupload(&p.esq3, tab->esq3d, PIMCGPU_SIZE_ROTDEN)) return 1;
+   }
+   // ---- state ----
+   p.nchains = sys->nchains;
+   p.S = p.P + p.Q + 8;
+   const size_t C = p.nchains;
+   if (dalloc(&p.pos, C * p.P * 3 * p.Npad) || dalloc(&p.ang, C * std::max(1, p.Q) * 3 * p.NMpad) || dalloc(&p.cosn, C * std::max(1, p.Q) * 3 * p.NMpad) ||
+       dalloc(&p.pindex, C * p.N) || dalloc(&p.cyc_start, C * (p.N + 1)) || dalloc(&p.cyc_atoms, C * p.N) || dalloc(&p.ncyc, C * MAXT) ||
+       dalloc(&p.rng, C * p.S * 6) || dalloc(&p.counters, C * MAXT * 3 * 2) || dalloc(&p.scratch, C * 64) || dalloc(&G.d_err, 1)) return 1;
+   G.h_pindex.assign(C * p.N, 0);
+   // ---- execution geometry ----
+   int seg_max = 1, seg_min = 1 << 30;
+   for (int t = 0; t < p.ntypes; t++) { seg_max = std::max(seg_max, 1 << p.levels[t]); seg_min = std::min(seg_min, 1 << p.levels[t]); }
+   p.seg_max = seg_max;
+   int team = sys->team;
+   if (team <= 0) team = pow2ceil(std::min(32, std::max(1, p.R * (p.N - 1) / 2)));
+   team = std::min(32, pow2floor(std::max(1, team)));
+   int units = std::max(p.Q / 2, p.P / seg_min);           // widest stage: rot slices of one parity / segments of one atom
+   long want = (long)units * team;
+   int threads = sys->threads_per_cta, cpc = sys->ctas_per_chain;
+   if (cpc <= 0) cpc = (int)std::min<long>(16, std::max<long>(1, (want + 511) / 512));
+   if (threads <= 0) {
+      long per = (want + cpc - 1) / cpc;
+      threads = (int)std::min<long>(512, std::max<long>(64, ((per + 31) / 32) * 32));
+   }
+   if (threads % 32 || threads > 512 || threads < 32) return fail("pimcgpu_init: threads_per_cta must be a multiple of 32 in [32,512]");
+   if (cpc > 16) return fail("pimcgpu_init: ctas_per_chain must be <= 16");
+   p.team = team; p.cpc = cpc;
+   G.threads = threads;
+   G.smem = smem_bytes(p, threads);
+   if (G.smem > 227 * 1024) return fail("pimcgpu_init: %zu bytes of shared memory per CTA exceed the 227 KB limit", G.smem);
+   CK(cudaFuncSetAttribute(pimc_steps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
+   if (cpc > 8) CK(cudaFuncSetAttribute(pimc_steps_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+   // ---- estimator buffers / accumulator layout ----
+   EstBuffers &e = G.e;
+   memset(&e, 0, sizeof e);
+   std::vector<int> pairs;
+   for (int a0 = 0; a0 < p.N - 1; a0++)
+      for (int a1 = a0 + 1; a1 < p.N; a1++) { pairs.push_back(a0); pairs.push_back(a1); }
+   e.npairs = (int)pairs.size() / 2;
+   if (dupload(&e.pairs, pairs.data(), std::max<size_t>(pairs.size(), 2))) return 1;
+   e.has_gr3d = (need3d || needsph) ? 1 : 0;
+   e.off_gr1d = 32; e.off_gr2d = e.off_gr1d + BINSR; e.off_rcf = e.off_gr2d + (long)BINSR * BINST;
+   e.off_relbins = e.off_rcf + std::max(1, p.Q); e.off_gr3d = e.off_relbins + BINST + 2 * BINSC;
+   G.nacc = e.off_gr3d + (e.has_gr3d ? (long)BINSR * BINST * BINSC : 0);
+   if (dalloc(&e.acc, G.nacc) || dalloc(&e.partials, C * EST_BLOCKS * NPART) || dalloc(&e.chain_e, C * 8) || dalloc(&e.chain_rcf, C * std::max(1, p.Q))) return 1;
+   CK(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
+   CK(cudaDeviceSynchronize());
+   G.live = true;
+   G.step = 0;
+   G.seeded = false;
+   return 0;
+}
+
+int pimcgpu_upload_state(int chain, const double *coords, const double *angles, const int *pindex)
+{
+   if (!G.live) return fail("pimcgpu_upload_state: not initialised");
+   const Params &p = G.p;
+   if (chain < -1 || chain >= p.nchains) return fail("pimcgpu_upload_state: chain %d out of range", chain);
+   const size_t n = (size_t)p.N * p.P;
+   std::vector<double> hpos((size_t)p.P * 3 * p.Npad, 0.0), hang((size_t)std::max(1, p.Q) * 3 * p.NMpad, 0.0), hcos(hang.size(), 0.0);
+   for (int it = 0; it < p.P; it++)
+      for (int d = 0; d < 3; d++)
+         for (int a = 0; a < p.N; a++) hpos[((size_t)it * 3 + d) * p.Npad + a] = coords[d * n + (size_t)a * p.P + it];
+   if (p.imtype >= 0)
+      for (int q = 0; q < p.Q; q++)
+         for (int m = 0; m < p.NM; m++) {
+            size_t src = (size_t)(p.first[p.imtype] + m) * p.P + q;
+            double phi = angles[0 * n + src], cost = angles[1 * n + src], chi = angles[2 * n + src];
+            double sint = sqrt(1.0 - cost * cost);         // MCCosine from (phi, cos theta), mc_main.cc:192-199
+            size_t b = (size_t)q * 3 * p.NMpad + m;
+            hang[b] = phi; hang[b + p.NMpad] = cost; hang[b + 2 * p.NMpad] = chi;
+            hcos[b] = sint * cos(phi); hcos[b + p.NMpad] = sint * sin(phi); hcos[b + 2 * p.NMpad] = cost;
+         }
+   // permutation: pindex[] of the boson type in type-local numbering (PIndex, mc_setup.h:97) -> global next world line
+   std::vector<int> gp(p.N), cstart, catoms;
+   for (int a = 0; a < p.N; a++) gp[a] = a;
+   if (pindex && p.bstype >= 0)
+      for (int a = 0; a < p.numb[p.bstype]; a++) {
+         if (pindex[a] < 0 || pindex[a] >= p.numb[p.bstype]) return fail("pimcgpu_upload_state: bad permutation entry");
+         gp[p.first[p.bstype] + a] = p.first[p.bstype] + pindex[a];
+      }
+   std::vector<int> ncyc(MAXT, 0), seen(p.N, 0);
+   for (int t = 0; t < p.ntypes; t++)
+      for (int a = p.first[t]; a < p.first[t] + p.numb[t]; a++) {
+         if (seen[a]) continue;
+         cstart.push_back((int)catoms.size());
+         int b = a, guard = 0;
+         do { catoms.push_back(b); seen[b] = 1; b = gp[b]; } while (b != a && ++guard <= p.N);
+         if (b != a) return fail("pimcgpu_upload_state: permutation is not a bijection");
+         ncyc[t]++;
+      }
+   while ((int)cstart.size() < p.N + 1) cstart.push_back((int)catoms.size());
+   int c0 = chain < 0 ? 0 : chain, c1 = chain < 0 ? p.nchains : chain + 1;
+   for (int c = c0; c < c1; c++) {
+      CK(cudaMemcpyAsync(p.pos + (size_t)c * hpos.size(), hpos.data(), hpos.size() * sizeof(double), cudaMemcpyHostToDevice, G.stream));
+      CK(cudaMemcpyAsync(p.ang + (size_t)c * hang.size(), hang.data(), hang.size() * sizeof(double), cudaMemcpyHostToDevice, G.stream));
+      CK(cudaMemcpyAsync(p.cosn + (size_t)c * hcos.size(), hcos.data(), hcos.size() * sizeof(double), cudaMemcpyHostToDevice, G.stream));
+      CK(cudaMemcpyAsync(p.pindex + (size_t)c * p.N, gp.data(), p.N * sizeof(int), cudaMemcpyHostToDevice, G.stream));
+      CK(cudaMemcpyAsync(p.cyc_start + (size_t)c * (p.N + 1), cstart.data(), (p.N + 1) * sizeof(int), cudaMemcpyHostToDevice, G.stream));
+      CK(cudaMemcpyAsync(p.cyc_atoms + (size_t)c * p.N, catoms.data(), p.N * sizeof(int), cudaMemcpyHostToDevice, G.stream));
+      CK(cudaMemcpyAsync(p.ncyc + (size_t)c * MAXT, ncyc.data(), MAXT * sizeof(int), cudaMemcpyHostToDevice, G.stream));
+      std::copy(gp.begin(), gp.end(), G.h_pindex.begin() + (size_t)c * p.N);
+   }
+   CK(cudaStreamSynchronize(G.stream));
+   return 0;
+}
+
+int pimcgpu_download_state(int chain, double *coords, double *angles, double *cosine, int *pindex)
+{
+   if (!G.live) return fail("pimcgpu_download_state: not initialised");
+   const Params &p = G.p;
+   if (chain < 0 || chain >= p.nchains) return fail("pimcgpu_download_state: chain %d out of range", chain);
+   const size_t n = (size_t)p.N * p.P;
+   std::vector<double> hpos((size_t)p.P * 3 * p.Npad), hang((size_t)std::max(1, p.Q) * 3 * p.NMpad), hcos(hang.size());
+   CK(cudaStreamSynchronize(G.stream));
+   CK(cudaMemcpy(hpos.data(), p.pos + (size_t)chain * hpos.size(), hpos.size() * sizeof(double), cudaMemcpyDeviceToHost));
+   CK(cudaMemcpy(hang.data(), p.ang + (size_t)chain * hang.size(), hang.size() * sizeof(double), cudaMemcpyDeviceToHost));
+   CK(cudaMemcpy(hcos.data(), p.cosn + (size_t)chain * hcos.size(), hcos.size() * sizeof(double), cudaMemcpyDeviceToHost));
+   if (coords)
+      for (int it = 0; it < p.P; it++)
+         for (int d = 0; d < 3; d++)
+            for (int a = 0; a < p.N; a++) coords[d * n + (size_t)a * p.P + it] = hpos[((size_t)it * 3 + d) * p.Npad + a];
+   // rotor rows: only the first Q entries of a molecule's row carry angles (README.md:228); the rest keep
+   // the reference's initial values phi=0, cos(theta)=1, chi=0 (MCConfigInit, mc_setup.cc:471-487)
+   for (int d = 0; d < 3; d++)
+      for (size_t i = 0; i < n; i++) {
+         if (angles) angles[d * n + i] = (d == 1) ? 1.0 : 0.0;
+         if (cosine) cosine[d * n + i] = (d == 2) ? 1.0 : 0.0;
+      }
+   if (p.imtype >= 0)
+      for (int q = 0; q < p.Q; q++)
+         for (int m = 0; m < p.NM; m++) {
+            size_t dst = (size_t)(p.first[p.imtype] + m) * p.P + q, b = (size_t)q * 3 * p.NMpad + m;
+            for (int d = 0; d < 3; d++) {
+               if (angles) angles[d * n + dst] = hang[b + d * p.NMpad];
+               if (cosine) cosine[d * n + dst] = hcos[b + d * p.NMpad];
+            }
+         }
+   if (pindex && p.bstype >= 0)
+      for (int a = 0; a < p.numb[p.bstype]; a++) pindex[a] = G.h_pindex[(size_t)chain * p.N + p.first[p.bstype] + a] - p.first[p.bstype];
+   return 0;
+}
+
+int pimcgpu_seed(const unsigned long seed6[6])
+{
+   if (!G.live) return fail("pimcgpu_seed: not initialised");
+   const Params &p = G.p;
+   u64 seed[6];
+   for (int i = 0; i < 6; i++) seed[i] = seed6[i];
+   // CheckSeed, rngstream.cc:200-236
+   for (int i = 0; i < 3; i++) if (seed[i] >= M1) return fail("pimcgpu_seed: seed[%d] >= 4294967087", i);
+   for (int i = 3; i < 6; i++) if (seed[i] >= M2) return fail("pimcgpu_seed: seed[%d] >= 4294944443", i);
+   if (!(seed[0] | seed[1] | seed[2]) || !(seed[3] | seed[4] | seed[5])) return fail("pimcgpu_seed: a seed triple is all zero");
+   std::vector<uint32_t> h((size_t)p.nchains * p.S * 6);
+   u64 st[6];
+   stream_state(seed, (u64)G.sys.chain_offset * (u64)p.S, st);
+   for (size_t s = 0; s < (size_t)p.nchains * p.S; s++) {
+      for (int k = 0; k < 6; k++) h[s * 6 + k] = (uint32_t)st[k];
+      matvec(A1P127, st, st, M1);
+      matvec(A2P127, st + 3, st + 3, M2);
+   }
+   CK(cudaMemcpy(p.rng, h.data(), h.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+   G.seeded = true;
+   return 0;
+}
+
+int pimcgpu_steps(long nsteps)
+{
+   if (!G.live) return fail("pimcgpu_steps: not initialised");
+   if (!G.seeded) return fail("pimcgpu_steps: call pimcgpu_seed first");
+   if (nsteps <= 0) return 0;
+   cudaLaunchConfig_t cfg = {};
+   cfg.gridDim = dim3(G.p.nchains * G.p.cpc);
+   cfg.blockDim = dim3(G.threads);
+   cfg.dynamicSmemBytes = G.smem;
+   cfg.stream = G.stream;
+   cudaLaunchAttribute attr[1];
+   attr[0].id = cudaLaunchAttributeClusterDimension;
+   attr[0].val.clusterDim.x = G.p.cpc; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+   cfg.attrs = attr; cfg.numAttrs = 1;
+   CK(cudaLaunchKernelEx(&cfg, pimc_steps_kernel, G.p, G.step, nsteps, G.d_err));
+   G.step += nsteps;
+   return 0;
+}
+
+int pimcgpu_sync(void)
+{
+   if (!G.live) return fail("pimcgpu_sync: not initialised");
+   CK(cudaStreamSynchronize(G.stream));
+   int err = 0;
+   CK(cudaMemcpy(&err, G.d_err, sizeof err, cudaMemcpyDeviceToHost));
+   if (err & 1) return fail("rotational density table index out of range (the reference prints 'large matrix test error' and exits)");
+   if (err & 2) return fail("Rotational Moves: Negative rot density");
+   return 0;
+}
+
+long pimcgpu_step_counter(void) { return G.step; }
+void *pimcgpu_stream(void) { return (void *)G.stream; }
+
+int pimcgpu_measure(void)
+{
+   if (!G.live) return fail("pimcgpu_measure: not initialised");
+   return launch_estimators(1, 1);
+}
+
+int pimcgpu_chain_energies(int chain, double *out5)
+{
+   if (!G.live) return fail("pimcgpu_chain_energies: not initialised");
+   if (chain < 0 || chain >= G.p.nchains) return fail("pimcgpu_chain_energies: chain out of range");
+   if (launch_estimators(0, 0)) return 1;
+   CK(cudaStreamSynchronize(G.stream));
+   CK(cudaMemcpy(out5, G.e.chain_e + (size_t)chain * 8, 5 * sizeof(double), cudaMemcpyDeviceToHost));
+   return 0;
+}
+
+int pimcgpu_chain_rcf(int chain, double *rcf0)
+{
+   if (!G.live) return fail("pimcgpu_chain_rcf: not initialised");
+   if (chain < 0 || chain >= G.p.nchains || G.p.Q <= 0) return fail("pimcgpu_chain_rcf: bad chain or no rotation");
+   if (launch_estimators(0, 0)) return 1;
+   CK(cudaStreamSynchronize(G.stream));
+   CK(cudaMemcpy(rcf0, G.e.chain_rcf + (size_t)chain * G.p.Q, G.p.Q * sizeof(double), cudaMemcpyDeviceToHost));
+   return 0;
+}
+
+int pimcgpu_accum_layout(long *n_total, long *off_scalars, long *off_gr1d, long *off_gr2d, long *off_gr3d, long *off_rcf, long *off_relbins)
+{
+   if (!G.live) return fail("pimcgpu_accum_layout: not initialised");
+   if (n_total) *n_total = G.nacc;
+   if (off_scalars) *off_scalars = 0;
+   if (off_gr1d) *off_gr1d = G.e.off_gr1d;
+   if (off_gr2d) *off_gr2d = G.e.off_gr2d;
+   if (off_gr3d) *off_gr3d = G.e.has_gr3d ? G.e.off_gr3d : -1;
+   if (off_rcf) *off_rcf = G.e.off_rcf;
+   if (off_relbins) *off_relbins = G.e.off_relbins;
+   return 0;
+}
+void *pimcgpu_accum_device_ptr(void)
+{
+   if (!G.live) return nullptr;
+   fold_counters_kernel<<<1, 32, 0, G.stream>>>(G.p, G.e.acc);
+   cudaStreamSynchronize(G.stream);
+   return G.e.acc;
+}
+int pimcgpu_accum_download(double *host, long n)
+{
+   if (!G.live) return fail("pimcgpu_accum_download: not initialised");
+   if (n > G.nacc) n = G.nacc;
+   CK(cudaStreamSynchronize(G.stream));
+   CK(cudaMemcpy(host, G.e.acc, n * sizeof(double), cudaMemcpyDeviceToHost));
+   return 0;
+}
+int pimcgpu_accum_reset(void)
+{
+   if (!G.live) return fail("pimcgpu_accum_reset: not initialised");
+   CK(cudaMemsetAsync(G.e.acc, 0, G.nacc * sizeof(double), G.stream));
+   CK(cudaMemsetAsync(G.p.counters, 0, (size_t)G.p.nchains * MAXT * 3 * 2 * sizeof(double), G.stream));
+   return 0;
+}
+int pimcgpu_block_scalars(pimcgpu_scalars *out)
+{
+   if (!G.live) return fail("pimcgpu_block_scalars: not initialised");
+   double h[32];
+   CK(cudaStreamSynchronize(G.stream));
+   CK(cudaMemcpy(h, G.e.acc, sizeof h, cudaMemcpyDeviceToHost));
+   out->count = h[0]; out->kin = h[1]; out->pot = h[2]; out->rot = h[3]; out->rotsq = h[4];
+   out->cv = h[5]; out->cv_trans = h[6]; out->cv_rot = h[7];
+   for (int t = 0; t < MAXT; t++)
+      for (int m = 0; m < 3; m++) { out->mctotal[t][m] = h[8 + t * 3 + m]; out->mcaccep[t][m] = h[14 + t * 3 + m]; }
+   return 0;
+}
+int pimcgpu_counters(double *mctotal, double *mcaccep)
+{
+   if (!G.live) return fail("pimcgpu_counters: not initialised");
+   const Params &p = G.p;
+   std::vector<double> h((size_t)p.nchains * MAXT * 3 * 2);
+   CK(cudaStreamSynchronize(G.stream));
+   CK(cudaMemcpy(h.data(), p.counters, h.size() * sizeof(double), cudaMemcpyDeviceToHost));
+   for (int i = 0; i < MAXT * 3; i++) { mctotal[i] = 0.0; mcaccep[i] = 0.0; }
+   for (int c = 0; c < p.nchains; c++)
+      for (int i = 0; i < MAXT * 3; i++) { mctotal[i] += h[((size_t)c * MAXT * 3 + i) * 2]; mcaccep[i] += h[((size_t)c * MAXT * 3 + i) * 2 + 1]; }
+   return 0;
+}
+
+} // extern "C"
+
+// ---- parity entry points ---------------------------------------------------------------------------
+namespace {
+struct DevBuf {
+   std::vector<void *> ptrs;
+   ~DevBuf() { for (void *q : ptrs) cudaFree(q); }
+   template <class T> T *in(const T *h, size_t n) { T *d = nullptr; cudaMalloc(&d, std::max<size_t>(1, n) * sizeof(T)); cudaMemcpy(d, h, n * sizeof(T), cudaMemcpyHostToDevice); ptrs.push_back(d); return d; }
+   template <class T> T *out(size_t n) { T *d = nullptr; cudaMalloc(&d, std::max<size_t>(1, n) * sizeof(T)); ptrs.push_back(d); return d; }
+};
+template <class T> int back(T *h, const T *d, size_t n)
+{
+   if (!h) return 0;
+   cudaError_t e = cudaMemcpy(h, d, n * sizeof(T), cudaMemcpyDeviceToHost);
+   if (e != cudaSuccess) return fail("device evaluation failed: %s", cudaGetErrorString(e));
+   return 0;
+}
+}
+
+extern "C" {
+
+int pimcgpu_eval_spot1d(int n, const double *r, double *v, int *klo)
+{
+   if (!G.live || !G.p.n1d) return fail("pimcgpu_eval_spot1d: no 1-D table loaded");
+   DevBuf b; const double *dr = b.in(r, n); double *dv = b.out<double>(n); int *dk = b.out<int>(n);
+   eval_spot1d_kernel<<<(n + 127) / 128, 128>>>(G.p, n, dr, dv, dk);
+   return back(v, dv, n) || back(klo, dk, n);
+}
+int pimcgpu_eval_lpot2d(int n, const double *r, const double *c, double *v, int *ir, int *ic)
+{
+   if (!G.live || !G.p.rs2d) return fail("pimcgpu_eval_lpot2d: no 2-D table loaded");
+   DevBuf b; const double *dr = b.in(r, n), *dc = b.in(c, n); double *dv = b.out<double>(n); int *di = b.out<int>(n), *dj = b.out<int>(n);
+   eval_lpot2d_kernel<<<(n + 127) / 128, 128>>>(G.p, n, dr, dc, dv, di, dj);
+   return back(v, dv, n) || back(ir, di, n) || back(ic, dj, n);
+}
+int pimcgpu_eval_srotdens(int n, const double *g, int which, double *v)
+{
+   if (!G.live || !G.p.nrot) return fail("pimcgpu_eval_srotdens: no linear-rotor density table loaded");
+   DevBuf b; const double *dg = b.in(g, n); double *dv = b.out<double>(n);
+   eval_srot_kernel<<<(n + 127) / 128, 128>>>(G.p, n, dg, which, dv);
+   return back(v, dv, n);
+}
+int pimcgpu_eval_rotden(int n, const double *e1, const double *e2, double *rho, double *erot, double *esq, int *index)
+{
+   if (!G.live || !G.p.rho3) return fail("pimcgpu_eval_rotden: no top density-matrix tables loaded");
+   DevBuf b; const double *d1 = b.in(e1, 3 * (size_t)n), *d2 = b.in(e2, 3 * (size_t)n);
+   double *dr = b.out<double>(n), *de = b.out<double>(n), *dq = b.out<double>(n); int *di = b.out<int>(n);
+   eval_rotden_kernel<<<(n + 127) / 128, 128>>>(G.p, n, d1, d2, dr, de, dq, di);
+   return back(rho, dr, n) || back(erot, de, n) || back(esq, dq, n) || back(index, di, n);
+}
+int pimcgpu_eval_vcord(int n, const double *eul, const double *rcom, const double *rpt, double *v, double *rtc, int *index)
+{
+   if (!G.live || !G.p.v3d) return fail("pimcgpu_eval_vcord: no 3-D potential table loaded");
+   DevBuf b; const double *de = b.in(eul, 3 * (size_t)n), *dc = b.in(rcom, 3 * (size_t)n), *dp = b.in(rpt, 3 * (size_t)n);
+   double *dv = b.out<double>(n), *dt = b.out<double>(3 * (size_t)n); int *di = b.out<int>(n);
+   eval_vcord_kernel<<<(n + 127) / 128, 128>>>(G.p, n, de, dc, dp, dv, dt, di);
+   return back(v, dv, n) || back(rtc, dt, 3 * (size_t)n) || back(index, di, n);
+}
+int pimcgpu_eval_caleng(int n, const double *c1, const double *c2, const double *e1, const double *e2, double *e)
+{
+   int ndev = 0;
+   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("pimcgpu_eval_caleng: no CUDA device");
+   DevBuf b; const double *a1 = b.in(c1, 3 * (size_t)n), *a2 = b.in(c2, 3 * (size_t)n), *b1 = b.in(e1, 3 * (size_t)n), *b2 = b.in(e2, 3 * (size_t)n);
+   double *de = b.out<double>(n);
+   eval_caleng_kernel<<<(n + 127) / 128, 128>>>(n, a1, a2, b1, b2, de);
+   return back(e, de, n);
+}
+int pimcgpu_pot_energy_slice(int chain, double *v)
+{
+   if (!G.live) return fail("pimcgpu_pot_energy_slice: not initialised");
+   if (chain < 0 || chain >= G.p.nchains) return fail("pimcgpu_pot_energy_slice: chain out of range");
+   size_t n = (size_t)G.p.N * G.p.P;
+   DevBuf b; double *dv = b.out<double>(n);
+   CK(cudaStreamSynchronize(G.stream));
+   pot_energy_slice_kernel<<<(unsigned)((n * 32 + 255) / 256), 256>>>(G.p, chain, dv);
+   return back(v, dv, n);
+}
+int pimcgpu_rng_draws(long stream, int n, double *out)
+{
+   if (!G.live || !G.seeded) return fail("pimcgpu_rng_draws: seed the library first");
+   // not kept: uses the package seed recorded at pimcgpu_seed time through the device copy of local streams
+   const Params &p = G.p;
+   long local = stream - G.sys.chain_offset * (long)p.S;
+   if (local < 0 || local >= (long)p.nchains * p.S) return fail("pimcgpu_rng_draws: stream %ld is not owned by this context", stream);
+   uint32_t st[6];
+   CK(cudaStreamSynchronize(G.stream));
+   CK(cudaMemcpy(st, p.rng + (size_t)local * 6, sizeof st, cudaMemcpyDeviceToHost));
+   DevBuf b; double *d = b.out<double>(n);
+   rng_draws_kernel<<<1, 1>>>(st[0], st[1], st[2], st[3], st[4], st[5], n, d);
+   return back(out, d, n);
+}
+
+} // extern "C"

@@ -1,1 +1,274 @@
-"""placeholder, replaced below"""
+"""ctypes binding of libpimcgpu.so (include/pimcgpu.h) -- the Python host-side mirror used by the
+tests and bench.py.  There is NO CPU fallback: if the CUDA library is missing or no GPU is
+visible every compute call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(CSRC, "libpimcgpu.so")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int)
+
+EXPORTS = [
+    "pimcgpu_init", "pimcgpu_finalize", "pimcgpu_last_error", "pimcgpu_upload_state", "pimcgpu_download_state",
+    "pimcgpu_seed", "pimcgpu_steps", "pimcgpu_sync", "pimcgpu_step_counter", "pimcgpu_measure", "pimcgpu_accum_layout",
+    "pimcgpu_accum_device_ptr", "pimcgpu_accum_download", "pimcgpu_accum_reset", "pimcgpu_block_scalars",
+    "pimcgpu_counters", "pimcgpu_stream", "pimcgpu_chain_energies", "pimcgpu_chain_rcf", "pimcgpu_eval_spot1d",
+    "pimcgpu_eval_lpot2d", "pimcgpu_eval_srotdens", "pimcgpu_eval_rotden", "pimcgpu_eval_vcord", "pimcgpu_eval_caleng",
+    "pimcgpu_pot_energy_slice", "pimcgpu_rng_draws",
+]
+
+
+class GpuType(C.Structure):
+    _fields_ = [("numb", C.c_int), ("molecule", C.c_int), ("stat", C.c_int), ("levels", C.c_int),
+                ("mass", C.c_double), ("mcstep", C.c_double), ("rtstep", C.c_double)]
+
+
+class GpuSystem(C.Structure):
+    _fields_ = [("ntypes", C.c_int), ("type", GpuType * 2), ("P", C.c_int), ("Q", C.c_int), ("temperature", C.c_double),
+                ("ispher", C.c_int), ("minimage", C.c_int), ("box", C.c_double * 3), ("rotden_type", C.c_int),
+                ("nchains", C.c_int), ("chain_offset", C.c_long), ("device", C.c_int), ("ctas_per_chain", C.c_int),
+                ("threads_per_cta", C.c_int), ("team", C.c_int)]
+
+
+class GpuTables(C.Structure):
+    _fields_ = [("n1d", C.c_int), ("grid1d", c_dp), ("pot1d", c_dp),
+                ("rsize2d", C.c_int), ("csize2d", C.c_int), ("dr2d", C.c_double), ("dc2d", C.c_double),
+                ("rgrid2d", c_dp), ("cgrid2d", c_dp), ("pot2d", c_dp),
+                ("rgrd", C.c_int), ("thgrd", C.c_int), ("chgrd", C.c_int), ("rvmin", C.c_double), ("rvmax", C.c_double),
+                ("vtable", c_dp),
+                ("nrot", C.c_int), ("rotgrid", c_dp), ("rotdens", c_dp), ("rotderv", c_dp), ("rotesqr", c_dp),
+                ("rho3d", c_dp), ("erot3d", c_dp), ("esq3d", c_dp), ("vspher", c_dp)]
+
+
+class GpuScalars(C.Structure):
+    _fields_ = [("count", C.c_double), ("kin", C.c_double), ("pot", C.c_double), ("rot", C.c_double), ("rotsq", C.c_double),
+                ("cv", C.c_double), ("cv_trans", C.c_double), ("cv_rot", C.c_double),
+                ("mctotal", (C.c_double * 3) * 2), ("mcaccep", (C.c_double * 3) * 2)]
+
+
+def build(force: bool = False) -> str:
+    """nvcc cross-compile of the in-tree library for sm_100a (works without a GPU)."""
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
+    srcs.append(os.path.join(os.path.dirname(HERE), "include", "pimcgpu.h"))
+    if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(s) for s in srcs):
+        return LIB
+    cmd = ["nvcc"] + NVCC_FLAGS + ["-o", LIB, os.path.join(CSRC, "pimcgpu.cu")]
+    subprocess.check_call(cmd)
+    return LIB
+
+
+_lib = None
+
+
+def lib():
+    """Load libpimcgpu.so; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB):
+            raise RuntimeError(f"{LIB} is missing: run __graft_entry__.build() (nvcc, sm_100a) first; there is no CPU fallback")
+        L = C.CDLL(LIB)
+        L.pimcgpu_last_error.restype = C.c_char_p
+        L.pimcgpu_step_counter.restype = C.c_long
+        L.pimcgpu_accum_device_ptr.restype = C.c_void_p
+        L.pimcgpu_stream.restype = C.c_void_p
+        L.pimcgpu_steps.argtypes = [C.c_long]
+        L.pimcgpu_rng_draws.argtypes = [C.c_long, C.c_int, c_dp]
+        L.pimcgpu_accum_download.argtypes = [c_dp, C.c_long]
+        _lib = L
+    return _lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_dp) if a is not None else None
+
+
+def _ip(a):
+    return a.ctypes.data_as(c_ip) if a is not None else None
+
+
+class PimcGpuError(RuntimeError):
+    pass
+
+
+def _ck(rc):
+    if rc:
+        raise PimcGpuError(lib().pimcgpu_last_error().decode())
+
+
+class PimcGpu:
+    """One device context (the library is a per-process singleton, like the reference's globals)."""
+
+    def __init__(self, cfg, nchains=1, chain_offset=0, device=0, ctas_per_chain=0, threads_per_cta=0, team=0):
+        self.cfg = cfg
+        s = cfg.system
+        self.s = s
+        self.N, self.P, self.Q = s.N, s.P, s.Q
+        self.nchains = nchains
+        sy = GpuSystem()
+        sy.ntypes = len(s.types)
+        for i, t in enumerate(s.types):
+            sy.type[i] = GpuType(t.numb, t.molecule, t.stat, t.levels, t.mass, t.mcstep, t.rtstep)
+        sy.P, sy.Q, sy.temperature = s.P, s.Q, s.temperature
+        sy.ispher, sy.minimage, sy.rotden_type = s.ispher, s.minimage, s.rotden_type
+        box = (s.N / s.density) ** (1.0 / 3.0)               # MCInit, mc_setup.cc:339,359-360
+        for d in range(3):
+            sy.box[d] = box
+        sy.nchains, sy.chain_offset, sy.device = nchains, chain_offset, device
+        sy.ctas_per_chain, sy.threads_per_cta, sy.team = ctas_per_chain, threads_per_cta, team
+        tb = GpuTables()
+        self._keep = []
+        t = cfg.tables
+
+        def arr(x):
+            a = np.ascontiguousarray(x, dtype=np.float64)
+            self._keep.append(a)
+            return a
+
+        if "pot1d" in t:
+            g, v = arr(t["pot1d"][0]), arr(t["pot1d"][1])
+            tb.n1d, tb.grid1d, tb.pot1d = len(g), _dp(g), _dp(v)
+        if "pot2d" in t:
+            rg, cg, v = (arr(x) for x in t["pot2d"])
+            dr, dc = t.get("pot2d_delta", (round(float(rg[1] - rg[0]), 12), round(float(cg[1] - cg[0]), 12)))
+            tb.rsize2d, tb.csize2d, tb.dr2d, tb.dc2d = len(rg), len(cg), dr, dc
+            tb.rgrid2d, tb.cgrid2d, tb.pot2d = _dp(rg), _dp(cg), _dp(v)
+        if "pot3d" in t:
+            rg, thg, chg, rmin, rmax, v = t["pot3d"]
+            v = arr(v)
+            tb.rgrd, tb.thgrd, tb.chgrd, tb.rvmin, tb.rvmax, tb.vtable = rg, thg, chg, rmin, rmax, _dp(v)
+        if "rotlin" in t:
+            a = [arr(x) for x in t["rotlin"]]
+            tb.nrot, tb.rotgrid, tb.rotdens, tb.rotderv, tb.rotesqr = len(a[0]), _dp(a[0]), _dp(a[1]), _dp(a[2]), _dp(a[3])
+        if "rot3d" in t:
+            a = [arr(x) for x in t["rot3d"]]
+            tb.rho3d, tb.erot3d, tb.esq3d = _dp(a[0]), _dp(a[1]), _dp(a[2])
+        if "vspher" in t:
+            tb.vspher = _dp(arr(t["vspher"]))
+        self.L = lib()
+        _ck(self.L.pimcgpu_init(C.byref(sy), C.byref(tb)))
+        self.upload(-1, cfg.coords, cfg.angles, cfg.perm)
+
+    def close(self):
+        self.L.pimcgpu_finalize()
+
+    # state -------------------------------------------------------------------------------
+    def upload(self, chain, coords, angles, perm=None):
+        c = np.ascontiguousarray(coords, dtype=np.float64)
+        a = np.ascontiguousarray(angles, dtype=np.float64)
+        p = np.ascontiguousarray(perm, dtype=np.int32) if perm is not None else None
+        _ck(self.L.pimcgpu_upload_state(C.c_int(chain), _dp(c), _dp(a), _ip(p)))
+
+    def download(self, chain=0):
+        n = self.N * self.P
+        c, a, cs = (np.zeros((3, n)) for _ in range(3))
+        _ck(self.L.pimcgpu_download_state(C.c_int(chain), _dp(c), _dp(a), _dp(cs), None))
+        return c, a, cs
+
+    def seed(self, seed6=(12345,) * 6):
+        _ck(self.L.pimcgpu_seed((C.c_ulong * 6)(*seed6)))
+
+    # moves / estimators ----------------------------------------------------------------------
+    def steps(self, n, sync=True):
+        _ck(self.L.pimcgpu_steps(C.c_long(n)))
+        if sync:
+            _ck(self.L.pimcgpu_sync())
+
+    def sync(self):
+        _ck(self.L.pimcgpu_sync())
+
+    def measure(self):
+        _ck(self.L.pimcgpu_measure())
+
+    def chain_energies(self, chain=0):
+        out = np.zeros(5)
+        _ck(self.L.pimcgpu_chain_energies(C.c_int(chain), _dp(out)))
+        return dict(kin=out[0], pot=out[1], rot=out[2], erotsq=out[3], eterm=out[4])
+
+    def chain_rcf(self, chain=0):
+        out = np.zeros(self.Q)
+        _ck(self.L.pimcgpu_chain_rcf(C.c_int(chain), _dp(out)))
+        return out
+
+    def accum_layout(self):
+        v = [C.c_long() for _ in range(7)]
+        _ck(self.L.pimcgpu_accum_layout(*[C.byref(x) for x in v]))
+        k = ("n_total", "scalars", "gr1d", "gr2d", "gr3d", "rcf", "relbins")
+        return dict(zip(k, [x.value for x in v]))
+
+    def accum_download(self):
+        lay = self.accum_layout()
+        self.L.pimcgpu_accum_device_ptr()          # folds the move counters into the buffer
+        out = np.zeros(lay["n_total"])
+        _ck(self.L.pimcgpu_accum_download(_dp(out), C.c_long(len(out))))
+        return out, lay
+
+    def accum_reset(self):
+        _ck(self.L.pimcgpu_accum_reset())
+
+    def block_scalars(self):
+        self.L.pimcgpu_accum_device_ptr()
+        s = GpuScalars()
+        _ck(self.L.pimcgpu_block_scalars(C.byref(s)))
+        return s
+
+    def counters(self):
+        t, a = np.zeros(6), np.zeros(6)
+        _ck(self.L.pimcgpu_counters(_dp(t), _dp(a)))
+        return t.reshape(2, 3), a.reshape(2, 3)
+
+    # parity entry points ------------------------------------------------------------------------
+    def eval_spot1d(self, r):
+        r = np.ascontiguousarray(r, dtype=np.float64); v = np.zeros_like(r); k = np.zeros(len(r), dtype=np.int32)
+        _ck(self.L.pimcgpu_eval_spot1d(len(r), _dp(r), _dp(v), _ip(k)))
+        return v, k
+
+    def eval_lpot2d(self, r, c):
+        r = np.ascontiguousarray(r, dtype=np.float64); c = np.ascontiguousarray(c, dtype=np.float64)
+        v = np.zeros_like(r); ir = np.zeros(len(r), dtype=np.int32); ic = np.zeros(len(r), dtype=np.int32)
+        _ck(self.L.pimcgpu_eval_lpot2d(len(r), _dp(r), _dp(c), _dp(v), _ip(ir), _ip(ic)))
+        return v, ir, ic
+
+    def eval_srotdens(self, g, which=0):
+        g = np.ascontiguousarray(g, dtype=np.float64); v = np.zeros_like(g)
+        _ck(self.L.pimcgpu_eval_srotdens(len(g), _dp(g), C.c_int(which), _dp(v)))
+        return v
+
+    def eval_rotden(self, e1, e2):
+        e1 = np.ascontiguousarray(e1, dtype=np.float64); e2 = np.ascontiguousarray(e2, dtype=np.float64)
+        n = len(e1)
+        rho, erot, esq = np.zeros(n), np.zeros(n), np.zeros(n); idx = np.zeros(n, dtype=np.int32)
+        _ck(self.L.pimcgpu_eval_rotden(n, _dp(e1), _dp(e2), _dp(rho), _dp(erot), _dp(esq), _ip(idx)))
+        return rho, erot, esq, idx
+
+    def eval_vcord(self, eul, rcom, rpt):
+        eul, rcom, rpt = (np.ascontiguousarray(x, dtype=np.float64) for x in (eul, rcom, rpt))
+        n = len(eul)
+        v = np.zeros(n); rtc = np.zeros((n, 3)); idx = np.zeros(n, dtype=np.int32)
+        _ck(self.L.pimcgpu_eval_vcord(n, _dp(eul), _dp(rcom), _dp(rpt), _dp(v), _dp(rtc), _ip(idx)))
+        return v, rtc, idx
+
+    def eval_caleng(self, c1, c2, e1, e2):
+        a = [np.ascontiguousarray(x, dtype=np.float64) for x in (c1, c2, e1, e2)]
+        n = len(a[0]); e = np.zeros(n)
+        _ck(self.L.pimcgpu_eval_caleng(n, *[_dp(x) for x in a], _dp(e)))
+        return e
+
+    def pot_energy_slice(self, chain=0):
+        v = np.zeros((self.N, self.P))
+        _ck(self.L.pimcgpu_pot_energy_slice(C.c_int(chain), _dp(v)))
+        return v
+
+    def rng_draws(self, stream, n):
+        out = np.zeros(n)
+        _ck(self.L.pimcgpu_rng_draws(C.c_long(stream), C.c_int(n), _dp(out)))
+        return out
