@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py -- PIMC bead-updates/s (translational + rotational) of the B200 hot path.
+
+  python bench.py --gpus N --steps K --warmup W [--workload C5] [--chains 8]
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...     (N > 1)
+  python bench.py --impl reference ...    the reference's own CPU hot path (oracle/_ref) on the host cores
+
+One "step" = one Monte-Carlo PASS (P iterations of the reference's `time` loop, mc_main.cc:348-381)
+of every chain resident on the GPU.  Bead-updates are counted with the formula of SURVEY.md 8(d):
+bisection 2^L-1 per atom per reference call, whole-path move P per atom, rotational step 1.
+Default workload: C5, synthetic N2O in (pH2)_100 at 0.5 K, P=1024, Q=128, 8 chains per GPU (BASELINE.json
+configs[4], 64 chains over 8 GPUs); weak scaling, chains are independent, the only collective is the
+NCCL all-reduce of the estimator accumulators at the end of the block.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+
+# algorithmic flops / operand bytes of the leaves (reference algorithm, every operand once)
+LEAF_FLOPS = dict(spot1d=45, lpot2d=58, srot=33, gauss3=170, rotden=470, vcord=335, caleng=685)
+LEAF_BYTES = dict(spot1d=72, lpot2d=88, vcord=56, caleng=48)
+
+
+def algorithmic_work(s):
+    """(flops, bytes) per PASS per chain of the reference algorithm, and the bead-updates per pass."""
+    N, P, Q, R = s.N, s.P, s.Q, s.R
+    mol = [t for t in s.types if t.molecule]
+    atoms = [t for t in s.types if not t.molecule]
+    na = atoms[0].numb if atoms else 0
+    nm = mol[0].numb if mol else 0
+    kind = mol[0].molecule if mol else 0
+    cross = "lpot2d" if kind == 1 else "vcord"
+
+    def partners(t):          # (flops, bytes) of the sum over partners of one bead of type t
+        if t.molecule:
+            f = na * LEAF_FLOPS[cross] + (nm - 1) * LEAF_FLOPS["caleng"]
+            b = na * LEAF_BYTES[cross] + (nm - 1) * LEAF_BYTES["caleng"]
+        else:
+            f = (na - 1) * LEAF_FLOPS["spot1d"] + nm * LEAF_FLOPS[cross]
+            b = (na - 1) * LEAF_BYTES["spot1d"] + nm * LEAF_BYTES[cross]
+        return f, b
+
+    flops = bytes_ = 0.0
+    for t in s.types:
+        L = t.levels
+        pf, pb = partners(t)
+        red = (2 ** (L + 1) - 2 - L) / (2 ** L - 1)                    # the reference's redundant level schedule
+        nb = P * t.numb * (2 ** L - 1)
+        flops += nb * (2 * pf * red + LEAF_FLOPS["gauss3"])
+        bytes_ += nb * (72 + 2 * pb) * red
+        flops += P * t.numb * 2 * pf                                    # whole-path move
+        bytes_ += P * t.numb * (24 + 2 * pb)
+        if t.molecule and Q:
+            nrot = P * Q * t.numb
+            dens = 4 * (LEAF_FLOPS["srot"] if kind == 1 else LEAF_FLOPS["rotden"])
+            dens_b = 4 * (56 if kind == 1 else 32)
+            flops += nrot * (dens + 2 * R * pf + 130)
+            bytes_ += nrot * (72 + dens_b + 2 * R * pb + 24 * R + 48)
+    return flops, bytes_, s.bead_updates_per_pass()
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi-equivalent clock / throttle-reason samples during the timed region (NVML)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.stop_flag = [], set(), False
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.nv:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+def sample_size(s):
+    """time steps per CPU-baseline sample: a whole pass would take minutes on one core for C5"""
+    return max(1, min(s.P, 64))
+
+
+def reference_arm(args):
+    """The reference's own CPU implementation of the path (oracle/_ref, its unmodified C++ objects + the C++
+    restatement of its Fortran leaves), all host threads, on a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle_py as op
+    pkg = ge.load_package()
+    cfg = pkg.configs.make_config(args.workload)
+    s = cfg.system
+    cores = os.cpu_count() or 1
+    fast = op.ref_available(fast=True)
+    if not (fast or op.ref_available()):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref was not built (needs /root/reference at build time)"}))
+        return
+    sys.stdout.flush()
+    saved = os.dup(1)                                              # the reference chats on stdout (cout); keep ours to one JSON line
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    os.dup2(devnull, 1)
+    try:
+        R = op.Ref(cfg, nthreads=cores, fast=fast)
+    finally:
+        os.dup2(saved, 1)
+    R.lib.ref_run_steps.restype = __import__("ctypes").c_double
+    nsamp = sample_size(s)
+    bu = s.bead_updates_per_pass()
+    per_step = (bu["bisection"] + bu["rotation"]) / s.P          # bead-updates per `time` iteration (one chain)
+
+    def one(t0):
+        return R.lib.ref_run_steps(t0, nsamp), per_step * nsamp
+    t0 = 1                                                         # samples start after time 0: the whole-path sweep is
+    for _ in range(args.warmup):                                   # timed once, separately, and added pro rata below
+        one(t0); t0 += nsamp
+    t_mol = R.lib.ref_run_steps(0, 1)                              # one step at time == 0: molecular + 1 ordinary step
+    tt = nn = 0.0
+    for _ in range(args.steps):
+        dt, n = one(t0); t0 += nsamp
+        tt += dt; nn += n
+    t_step = tt / (args.steps * nsamp)
+    t_pass = t_step * s.P + max(0.0, t_mol - t_step)               # a full pass = P ordinary steps + the time-0 extras
+    value = bu["total"] / t_pass
+    line = {"metric": "pimc_bead_updates_per_sec", "value": value, "unit": "bead-updates/s", "impl": "reference", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.workload, s, 1), "chains": 1, "sample_time_steps": nsamp},
+            "cpu_baseline": {"value": value, "unit": "bead-updates/s", "cores": cores, "kind": "reference",
+                             "sample": f"{args.steps} x {nsamp} iterations of the time loop (mc_main.cc:349-381) of one chain + one time-0 step, scaled to a pass; "
+                                       f"{'-Ofast' if fast else '-O2'} build of the reference objects, OMP threads={cores}"},
+            "e2e": {"value": value, "unit": "bead-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_name(w, s, chains):
+    names = {"C1": "examples/MF_1He_0.37K_512_128", "C2": "examples/MF_8He_0.37K_512_128 (worm off)",
+             "C3": "examples/SO2_4pH2_0.37K_1024_256 (worm off)", "C4": "examples/H2Odimer_0.74K_4096_2048",
+             "C5": "synthetic N2O in (pH2)_100 at 0.5 K"}
+    return f"{w}: {names[w]}, N={s.N}, P={s.P}, Q={s.Q}, {chains} chains/GPU"
+
+
+def cpu_baseline(pkg, args, cfg):
+    """Bounded CPU sample in a subprocess (the reference keeps global state and must not share our CUDA process)."""
+    import subprocess
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", args.workload, "--steps", "3", "--warmup", "1"]
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env={**os.environ, "RANK": "0", "WORLD_SIZE": "1"})
+        for ln in reversed(out.stdout.splitlines()):
+            if ln.startswith("{"):
+                d = json.loads(ln)
+                return d.get("cpu_baseline", {"unavailable": d.get("unavailable")})
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": repr(e)}
+    return {"unavailable": "no output"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default="C5")
+    ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: 8 for C5, 148 otherwise)")
+    ap.add_argument("--cpc", type=int, default=0)
+    ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--team", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup) if args.impl != "reference" else args.warmup
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pkg = ge.load_package()
+    cfg = pkg.configs.make_config(args.workload)
+    s = cfg.system
+    chains = args.chains or (8 if args.workload == "C5" else 148)
+    G = pkg.gpu.PimcGpu(cfg, nchains=chains, chain_offset=rank * chains, device=local, ctas_per_chain=args.cpc,
+                        threads_per_cta=args.threads, team=args.team)
+    G.seed((12345,) * 6)
+    stream = torch.cuda.ExternalStream(G.L.pimcgpu_stream(), device=local)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")          # 256 MB > 126 MB L2
+
+    class Acc:          # zero-copy torch view of the library's accumulator buffer for the NCCL all-reduce
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+    lay = G.accum_layout()
+    acc_t = torch.as_tensor(Acc(G.L.pimcgpu_accum_device_ptr(), lay["n_total"]), device="cuda")
+
+    P = s.P
+    flops_pass, bytes_pass, bu = algorithmic_work(s)
+    per_step_units = bu["total"] * chains                     # bead-updates per step on this GPU
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: K passes, CUDA events on the library's stream, L2 flushed between passes ----
+    for _ in range(args.warmup):
+        G.steps(P)
+    sampler = ClockSampler(local); sampler.start()
+    barrier()
+    t_kernel = 0.0
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        G.steps(P, sync=False)
+        e1.record(stream)
+        e1.synchronize()
+        G.sync()
+        t_kernel += e0.elapsed_time(e1) * 1e-3
+    barrier()
+    if dist:
+        t = torch.tensor([t_kernel], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_kernel = float(t.item())
+    value = per_step_units * world * args.steps / t_kernel
+
+    # ---- end to end through the C ABI with host buffers: upload -> pass -> estimators -> (all-reduce) -> download ----
+    host = [G.download(c)[:2] for c in range(chains)]
+    h2d = chains * ((P * 3 * ((s.N + 3) // 4 * 4) + 2 * max(1, s.Q) * 3 * max(1, sum(t.numb for t in s.types if t.molecule))) * 8 + (3 * s.N + 3) * 4)
+    d2h = h2d - chains * (3 * s.N + 3) * 4 + lay["n_total"] * 8
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        for c in range(chains):
+            G.upload(c, host[c][0], host[c][1], cfg.perm)
+        G.accum_reset()
+        G.steps(P, sync=False)
+        G.measure()
+        G.L.pimcgpu_accum_device_ptr()
+        if dist:
+            torch.cuda.current_stream().wait_stream(stream)
+            dist.all_reduce(acc_t)
+            torch.cuda.current_stream().synchronize()
+        G.sync()
+        accum, _ = G.accum_download()
+        host = [G.download(c)[:2] for c in range(chains)]
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - w0
+    if dist:
+        t = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e = float(t.item())
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    e2e_value = per_step_units * world * args.steps / t_e2e
+
+    if rank == 0:
+        peaks, how = measured_peaks()
+        fp64_peak = pkg.gpu.fp64_peak_tflops()
+        ach_tf = flops_pass * chains * args.steps / t_kernel / 1e12          # per GPU (dominant kernel = the whole step)
+        ach_gb = bytes_pass * chains * args.steps / t_kernel / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(args.workload)
+        line = {
+            "metric": "pimc_bead_updates_per_sec", "value": value, "unit": "bead-updates/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_kernel / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.workload, s, chains), "chains_per_gpu": chains, "step": "one MC pass = P iterations of the time loop",
+                       "l2": "flushed (256 MB write) between timed passes; the state is L2/SMEM-resident by design inside a pass",
+                       "parallelism": f"independent chains x{world} GPUs, NCCL all-reduce of accumulators per block"},
+            "e2e": {"value": e2e_value, "unit": "bead-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": args.steps,
+            "clocks": sampler.summary(),
+            "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
+                         "traffic": traffic, "kernel": "pimc_steps_kernel (one launch = one pass of all chains)",
+                         "peak_source": "pimcgpu_fp64_peak DFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
+                         "hbm": {"achieved": ach_gb, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach_gb / peaks["hbm_gbs"], "of": how}},
+        }
+        if not args.no_cpu and world == 1:
+            line["cpu_baseline"] = cpu_baseline(pkg, args, cfg)
+        print(json.dumps(line))
+    G.close()
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

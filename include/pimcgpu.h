@@ -141,6 +141,9 @@ int pimcgpu_pot_energy_slice(int chain, double *v);
 /* first n uniforms of MRG32k3a stream `stream` (global stream index, 2^127 spacing): RngStream::RandU01 */
 int pimcgpu_rng_draws(long stream, int n, double *out);
 
+/* measured FP64 FMA throughput of the current device in TFLOP/s (roofline denominator; not part of the path) */
+int pimcgpu_fp64_peak(double *tflops);
+
 #ifdef __cplusplus
 }
 #endif

@@ -334,4 +334,16 @@ __global__ void rng_draws_kernel(uint32_t s0, uint32_t s1, uint32_t s2, uint32_t
    for (int i = 0; i < n; i++) out[i] = mrg_u01(g);
 }
 
+// FP64 FMA throughput microbenchmark (the denominator of the FP64 roofline)
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, double a, double b)
+{
+   double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+   for (int i = 0; i < iters; i++) {
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+   }
+   double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+   if (s == 12345.678) out[0] = s;
+}
+
 } // namespace pimc

@@ -51,6 +51,8 @@ struct Context {
    int *d_err = nullptr;
    bool seeded = false;
    std::vector<int> h_pindex;       // [c][N]
+   double *stage = nullptr;         // pinned host staging: [c][pos | ang | cosn] in the device layout
+   size_t stage_chain = 0;          // doubles per chain in `stage`
 } G;
 
 template <class T> int dalloc(T **ptr, size_t n)
@@ -193,6 +195,8 @@ void pimcgpu_finalize(void)
    G.allocs.clear();
    if (G.stream) cudaStreamDestroy(G.stream);
    G.stream = nullptr;
+   if (G.stage) cudaFreeHost(G.stage);
+   G.stage = nullptr;
    G.live = false;
    G.seeded = false;
    G.step = 0;
@@ -323,6 +327,9 @@ int pimcgpu_init(const pimcgpu_system *sys, const pimcgpu_tables *tab)
        dalloc(&p.pindex, C * p.N) || dalloc(&p.cyc_start, C * (p.N + 1)) || dalloc(&p.cyc_atoms, C * p.N) || dalloc(&p.ncyc, C * MAXT) ||
        dalloc(&p.rng, C * p.S * 6) || dalloc(&p.counters, C * MAXT * 3 * 2) || dalloc(&p.scratch, C * 64) || dalloc(&G.d_err, 1)) return 1;
    G.h_pindex.assign(C * p.N, 0);
+   G.stage_chain = (size_t)p.P * 3 * p.Npad + 2 * (size_t)std::max(1, p.Q) * 3 * p.NMpad;
+   CK(cudaHostAlloc((void **)&G.stage, C * G.stage_chain * sizeof(double), cudaHostAllocDefault));
+   memset(G.stage, 0, C * G.stage_chain * sizeof(double));
    // ---- execution geometry ----
    int seg_max = 1, seg_min = 1 << 30;
    for (int t = 0; t < p.ntypes; t++) { seg_max = std::max(seg_max, 1 << p.levels[t]); seg_min = std::min(seg_min, 1 << p.levels[t]); }
@@ -373,10 +380,16 @@ int pimcgpu_upload_state(int chain, const double *coords, const double *angles, 
    const Params &p = G.p;
    if (chain < -1 || chain >= p.nchains) return fail("pimcgpu_upload_state: chain %d out of range", chain);
    const size_t n = (size_t)p.N * p.P;
-   std::vector<double> hpos((size_t)p.P * 3 * p.Npad, 0.0), hang((size_t)std::max(1, p.Q) * 3 * p.NMpad, 0.0), hcos(hang.size(), 0.0);
+   const size_t npos = (size_t)p.P * 3 * p.Npad, nang = (size_t)std::max(1, p.Q) * 3 * p.NMpad;
+   const int cfirst = chain < 0 ? 0 : chain;
+   double *hpos = G.stage + (size_t)cfirst * G.stage_chain, *hang = hpos + npos, *hcos = hang + nang;
+   CK(cudaStreamSynchronize(G.stream));          // the staging area may still be in flight
    for (int it = 0; it < p.P; it++)
-      for (int d = 0; d < 3; d++)
-         for (int a = 0; a < p.N; a++) hpos[((size_t)it * 3 + d) * p.Npad + a] = coords[d * n + (size_t)a * p.P + it];
+      for (int d = 0; d < 3; d++) {
+         double *row = hpos + ((size_t)it * 3 + d) * p.Npad;
+         const double *src = coords + d * n + it;
+         for (int a = 0; a < p.N; a++) row[a] = src[(size_t)a * p.P];
+      }
    if (p.imtype >= 0)
       for (int q = 0; q < p.Q; q++)
          for (int m = 0; m < p.NM; m++) {
@@ -408,9 +421,9 @@ int pimcgpu_upload_state(int chain, const double *coords, const double *angles, 
    while ((int)cstart.size() < p.N + 1) cstart.push_back((int)catoms.size());
    int c0 = chain < 0 ? 0 : chain, c1 = chain < 0 ? p.nchains : chain + 1;
    for (int c = c0; c < c1; c++) {
-      CK(cudaMemcpyAsync(p.pos + (size_t)c * hpos.size(), hpos.data(), hpos.size() * sizeof(double), cudaMemcpyHostToDevice, G.stream));
-      CK(cudaMemcpyAsync(p.ang + (size_t)c * hang.size(), hang.data(), hang.size() * sizeof(double), cudaMemcpyHostToDevice, G.stream));
-      CK(cudaMemcpyAsync(p.cosn + (size_t)c * hcos.size(), hcos.data(), hcos.size() * sizeof(double), cudaMemcpyHostToDevice, G.stream));
+      CK(cudaMemcpyAsync(p.pos + (size_t)c * npos, hpos, npos * sizeof(double), cudaMemcpyHostToDevice, G.stream));
+      CK(cudaMemcpyAsync(p.ang + (size_t)c * nang, hang, nang * sizeof(double), cudaMemcpyHostToDevice, G.stream));
+      CK(cudaMemcpyAsync(p.cosn + (size_t)c * nang, hcos, nang * sizeof(double), cudaMemcpyHostToDevice, G.stream));
       CK(cudaMemcpyAsync(p.pindex + (size_t)c * p.N, gp.data(), p.N * sizeof(int), cudaMemcpyHostToDevice, G.stream));
       CK(cudaMemcpyAsync(p.cyc_start + (size_t)c * (p.N + 1), cstart.data(), (p.N + 1) * sizeof(int), cudaMemcpyHostToDevice, G.stream));
       CK(cudaMemcpyAsync(p.cyc_atoms + (size_t)c * p.N, catoms.data(), p.N * sizeof(int), cudaMemcpyHostToDevice, G.stream));
@@ -427,11 +440,12 @@ int pimcgpu_download_state(int chain, double *coords, double *angles, double *co
    const Params &p = G.p;
    if (chain < 0 || chain >= p.nchains) return fail("pimcgpu_download_state: chain %d out of range", chain);
    const size_t n = (size_t)p.N * p.P;
-   std::vector<double> hpos((size_t)p.P * 3 * p.Npad), hang((size_t)std::max(1, p.Q) * 3 * p.NMpad), hcos(hang.size());
+   const size_t npos = (size_t)p.P * 3 * p.Npad, nang = (size_t)std::max(1, p.Q) * 3 * p.NMpad;
+   double *hpos = G.stage + (size_t)chain * G.stage_chain, *hang = hpos + npos, *hcos = hang + nang;
+   CK(cudaMemcpyAsync(hpos, p.pos + (size_t)chain * npos, npos * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
+   CK(cudaMemcpyAsync(hang, p.ang + (size_t)chain * nang, nang * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
+   CK(cudaMemcpyAsync(hcos, p.cosn + (size_t)chain * nang, nang * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
    CK(cudaStreamSynchronize(G.stream));
-   CK(cudaMemcpy(hpos.data(), p.pos + (size_t)chain * hpos.size(), hpos.size() * sizeof(double), cudaMemcpyDeviceToHost));
-   CK(cudaMemcpy(hang.data(), p.ang + (size_t)chain * hang.size(), hang.size() * sizeof(double), cudaMemcpyDeviceToHost));
-   CK(cudaMemcpy(hcos.data(), p.cosn + (size_t)chain * hcos.size(), hcos.size() * sizeof(double), cudaMemcpyDeviceToHost));
    if (coords)
       for (int it = 0; it < p.P; it++)
          for (int d = 0; d < 3; d++)
@@ -674,6 +688,35 @@ int pimcgpu_pot_energy_slice(int chain, double *v)
    CK(cudaStreamSynchronize(G.stream));
    pot_energy_slice_kernel<<<(unsigned)((n * 32 + 255) / 256), 256>>>(G.p, chain, dv);
    return back(v, dv, n);
+}
+int pimcgpu_fp64_peak(double *tflops)
+{
+   int ndev = 0;
+   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("pimcgpu_fp64_peak: no CUDA device");
+   cudaDeviceProp prop;
+   int dev = 0;
+   CK(cudaGetDevice(&dev));
+   CK(cudaGetDeviceProperties(&prop, dev));
+   double *d = nullptr;
+   CK(cudaMalloc(&d, 8));
+   const int iters = 1 << 16, blocks = prop.multiProcessorCount * 8, threads = 256;
+   cudaEvent_t e0, e1;
+   cudaEventCreate(&e0); cudaEventCreate(&e1);
+   double best = 0.0;
+   for (int rep = 0; rep < 5; rep++) {
+      cudaEventRecord(e0);
+      fp64_peak_kernel<<<blocks, threads>>>(d, iters, 0.999999, 1e-9);
+      cudaEventRecord(e1);
+      CK(cudaEventSynchronize(e1));
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      double fl = 2.0 * 8.0 * (double)iters * blocks * threads;
+      best = std::max(best, fl / (ms * 1e-3) / 1e12);
+   }
+   cudaEventDestroy(e0); cudaEventDestroy(e1);
+   cudaFree(d);
+   *tflops = best;
+   return 0;
 }
 int pimcgpu_rng_draws(long stream, int n, double *out)
 {

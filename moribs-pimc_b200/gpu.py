@@ -24,7 +24,7 @@ EXPORTS = [
     "pimcgpu_accum_device_ptr", "pimcgpu_accum_download", "pimcgpu_accum_reset", "pimcgpu_block_scalars",
     "pimcgpu_counters", "pimcgpu_stream", "pimcgpu_chain_energies", "pimcgpu_chain_rcf", "pimcgpu_eval_spot1d",
     "pimcgpu_eval_lpot2d", "pimcgpu_eval_srotdens", "pimcgpu_eval_rotden", "pimcgpu_eval_vcord", "pimcgpu_eval_caleng",
-    "pimcgpu_pot_energy_slice", "pimcgpu_rng_draws",
+    "pimcgpu_pot_energy_slice", "pimcgpu_rng_draws", "pimcgpu_fp64_peak",
 ]
 
 
@@ -94,6 +94,12 @@ def _dp(a):
 
 def _ip(a):
     return a.ctypes.data_as(c_ip) if a is not None else None
+
+
+def fp64_peak_tflops() -> float:
+    v = C.c_double()
+    _ck(lib().pimcgpu_fp64_peak(C.byref(v)))
+    return v.value
 
 
 class PimcGpuError(RuntimeError):
