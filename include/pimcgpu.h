@@ -141,6 +141,13 @@ int pimcgpu_pot_energy_slice(int chain, double *v);
 /* first n uniforms of MRG32k3a stream `stream` (global stream index, 2^127 spacing): RngStream::RandU01 */
 int pimcgpu_rng_draws(long stream, int n, double *out);
 
+/* ---- host-side table preparation (no device needed): what pimcgpu_init does with the raw tables ----
+ * spline second derivatives + short/long-range constants: init_spline/init_pot1D (mc_utils.cc:188-201,
+ * mc_poten.cc:416-437); MRG32k3a state of the s-th stream (rngstream.cc:303-321); interval-search bucket table */
+int pimcgpu_host_spline(int n, const double *x, const double *y, double *y2, double *alpha_unode_c6);
+int pimcgpu_host_stream_state(const unsigned long seed6[6], long stream, unsigned long state6[6]);
+int pimcgpu_host_lut(int n, const double *x, int *lut /* [4n] */, double *scale);   /* returns the table length */
+
 /* measured FP64 FMA throughput of the current device in TFLOP/s (roofline denominator; not part of the path) */
 int pimcgpu_fp64_peak(double *tflops);
 

@@ -689,6 +689,38 @@ int pimcgpu_pot_energy_slice(int chain, double *v)
    pot_energy_slice_kernel<<<(unsigned)((n * 32 + 255) / 256), 256>>>(G.p, chain, dv);
    return back(v, dv, n);
 }
+// ---- host-side table preparation, exposed for the CPU-only tests (no device needed) ----
+int pimcgpu_host_spline(int n, const double *x, const double *y, double *y2, double *alpha_unode_c6)
+{
+   if (n < 2) return fail("pimcgpu_host_spline: need at least two points");
+   std::vector<double> g(x, x + n), v(y, y + n), d2;
+   spline_setup(g, v, d2);
+   memcpy(y2, d2.data(), n * sizeof(double));
+   if (alpha_unode_c6) {
+      double alpha = log(v[0] / v[1]) / (g[1] - g[0]);
+      alpha_unode_c6[0] = alpha;
+      alpha_unode_c6[1] = v[0] * exp(alpha * g[0]);
+      alpha_unode_c6[2] = (v[n - 1] - v[n - 2]) / (1.0 / pow(g[n - 2], 6.0) - 1.0 / pow(g[n - 1], 6.0));
+   }
+   return 0;
+}
+int pimcgpu_host_stream_state(const unsigned long seed6[6], long stream, unsigned long state6[6])
+{
+   u64 seed[6], st[6];
+   for (int i = 0; i < 6; i++) seed[i] = seed6[i];
+   stream_state(seed, (u64)stream, st);
+   for (int i = 0; i < 6; i++) state6[i] = st[i];
+   return 0;
+}
+int pimcgpu_host_lut(int n, const double *x, int *lut, double *scale)
+{
+   std::vector<double> g(x, x + n);
+   std::vector<int> l;
+   build_lut(g, l, *scale);
+   memcpy(lut, l.data(), l.size() * sizeof(int));
+   return (int)l.size();
+}
+
 int pimcgpu_fp64_peak(double *tflops)
 {
    int ndev = 0;

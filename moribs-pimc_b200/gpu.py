@@ -24,7 +24,8 @@ EXPORTS = [
     "pimcgpu_accum_device_ptr", "pimcgpu_accum_download", "pimcgpu_accum_reset", "pimcgpu_block_scalars",
     "pimcgpu_counters", "pimcgpu_stream", "pimcgpu_chain_energies", "pimcgpu_chain_rcf", "pimcgpu_eval_spot1d",
     "pimcgpu_eval_lpot2d", "pimcgpu_eval_srotdens", "pimcgpu_eval_rotden", "pimcgpu_eval_vcord", "pimcgpu_eval_caleng",
-    "pimcgpu_pot_energy_slice", "pimcgpu_rng_draws", "pimcgpu_fp64_peak",
+    "pimcgpu_pot_energy_slice", "pimcgpu_rng_draws", "pimcgpu_fp64_peak", "pimcgpu_host_spline",
+    "pimcgpu_host_stream_state", "pimcgpu_host_lut",
 ]
 
 

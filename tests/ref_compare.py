@@ -23,14 +23,25 @@ def rel(a, b):
     return abs(a - b) / max(1e-300, abs(b))
 
 
-def main():
-    name = sys.argv[1]
-    golden = sys.argv[3] if len(sys.argv) > 3 and sys.argv[2] == "--golden" else None
+class _NoRef:
+    """Stand-in when the reference objects are not available: every reference call returns None."""
+    class _L:
+        def __getattr__(self, k):
+            return lambda *a, **kw: 0
+    lib = _L()
+    def rot_energy(self): return (0.0, 0.0, 0.0)
+    def get_state(self): return None
+    def push(self, *a): pass
+    def queue_mode(self, *a): pass
+
+
+def run(name, with_ref=True):
+    """Returns (res, gold): comparisons against the reference (when with_ref) and the oracle's own outputs."""
     cfgs = op._configs()
     cfg = cfgs.make_config(name, **SMALL[name])
     s = cfg.system
     O = op.Oracle(cfg)
-    R = op.Ref(cfg)
+    R = op.Ref(cfg) if with_ref else _NoRef()
     rng = np.random.default_rng(12345)
     N, P, Q = s.N, s.P, s.Q
     res = {}
@@ -85,10 +96,10 @@ def main():
         g1 = np.zeros(300); R.lib.ref_get_gr1D(op._dp(g1)); res["gr1D"] = float(np.abs(g1 - h["gr1d"]).max())
     if mol.molecule == 1:
         g2 = np.zeros(300 * 50); R.lib.ref_get_gr2D(op._dp(g2)); res["gr2D"] = float(np.abs(g2 - h["gr2d"]).max())
-        assert g2.sum() > 0
+        assert (not with_ref) or g2.sum() > 0
     if mol.molecule == 2 and len(s.types) > 1:
         g3 = np.zeros(300 * 50 * 100); R.lib.ref_get_gr3D(0, op._dp(g3)); res["gr3D"] = float(np.abs(g3 - h["gr3d_atoms"]).max())
-        assert g3.sum() > 0
+        assert (not with_ref) or g3.sum() > 0
     if Q:
         if mol.molecule == 2:
             R.lib.ref_zero_relbins()
@@ -143,7 +154,8 @@ def main():
             nacc += O.molecular_move(typ, a_, u[3 * a_:3 * a_ + 3], ua[0])
         R.lib.ref_MCMolecularMove(typ)
     res["molecular_accepted"] = nacc
-    co, ao, cso = O.get_state(); cr, ar, csr = R.get_state()
+    co, ao, cso = O.get_state()
+    cr, ar, csr = R.get_state() if with_ref else (co, ao, cso)
     res["state_coords_maxdiff"] = float(np.abs(co - cr).max())
     res["state_angles_maxdiff"] = float(np.abs(ao - ar).max())
     tot, acc = O.counters()
@@ -154,9 +166,17 @@ def main():
                                         np.abs(acc[:nt, :2] - ra_.reshape(2, 3)[:nt, :2]).max()))
     res["final_kin"] = rel(O.get_kin(), R.lib.ref_GetKinEnergy())
     res["final_pot"] = rel(O.get_pot(0), R.lib.ref_GetPotEnergy())
+    gold["final_coords"] = co; gold["final_angles"] = ao
+    gold["final_kin"] = O.get_kin(); gold["final_pot"] = O.get_pot(0)
+    return res, gold
+
+
+def main():
+    name = sys.argv[1]
+    golden = sys.argv[3] if len(sys.argv) > 3 and sys.argv[2] == "--golden" else None
+    res, gold = run(name, with_ref=True)
     print("RESULT " + json.dumps(res))
     if golden:
-        gold["final_coords"] = co; gold["final_angles"] = ao
         np.savez_compressed(golden, **gold)
 
 
