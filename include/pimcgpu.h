@@ -106,6 +106,9 @@ int pimcgpu_seed(const unsigned long seed6[6]);
 int pimcgpu_steps(long nsteps);
 int pimcgpu_sync(void);
 long pimcgpu_step_counter(void);                   /* passTotal of mc_main.cc:346              */
+/* launch geometry chosen by pimcgpu_init: out8 = {ctas_per_chain, threads_per_cta, team, rot_group, smem bytes,
+ * rotor kind, clusters the device can keep resident at once, nchains}                                         */
+int pimcgpu_geometry(int *out8);
 
 /* ---- estimators: the device part of MCGetAverage (mc_main.cc:551-646): GetKinEnergy,
  *      GetPotEnergy_Densities, GetRotEnergy/GetRotE3D, GetRCF, Cv terms -> accumulators   ---- */

@@ -25,6 +25,9 @@ constexpr double WNO2K = 0.6950356;               // rotden.f:6, mc_const.h:15
 // interaction branch of PotEnergy for an (atom0 type, atom1 type) pair, mc_piqmc.cc:1847-1958
 enum Mode : int { M_SPOT1D = 0, M_LIN_0MOL = 1, M_LIN_1MOL = 2, M_TOP_0MOL = 3, M_TOP_1MOL = 4, M_SPHER = 5, M_TOPTOP = 6 };
 
+// one spline interval [xlo, xhi]: everything splint (mc_utils.cc:156-186) needs, with 1/h and y''h^2/6 folded in
+struct SplineRec { double xlo, xhi, inv_h, ylo, yhi, clo, chi; };
+
 struct Params {
    int ntypes, N, P, Q, R, Npad, NM, NMpad;
    int numb[MAXT], molecule[MAXT], stat[MAXT], levels[MAXT], first[MAXT + 1];
@@ -35,9 +38,15 @@ struct Params {
    int mode[MAXT][MAXT];
    // tables
    int n1d, nlut1d;  const double *g1d, *v1d, *y2_1d; const int *lut1d; double alpha, unode, c6, lut1d_scale;
+   const SplineRec *rec1d;       // packed per-interval records of the 1-D potential spline
    int rs2d, cs2d;   const double *rg2d, *cg2d, *v2d; double dr2d, dc2d;
+   const double *irg2d, *icg2d;  // 1/(grid[i+1]-grid[i]) of the 2-D potential axes
+   double inv_dr2d, inv_dc2d;
+   const double *cell2d;         // [(rs-1)*(cs-1)][4]: the four corner values y1,y2,y3,y4 of every bilinear cell in one 32-byte sector
+   const double2 *rgi2d, *cgi2d; // {grid[i], 1/(grid[i+1]-grid[i])} of the two axes
    int rg3, thg3, chg3; const double *v3d; double rvmin, rvmax, rvstep;
    int nrot, nlutrot; const double *rgrid, *rdens, *rderv, *resqr, *rdens2, *rderv2, *resqr2; const int *lutrot; double lutrot_scale;
+   const SplineRec *recrot;      // packed records of the linear-rotor density spline (rho column)
    const double *rho3, *erot3, *esq3;
    const double *vspher;
    // state
@@ -49,9 +58,15 @@ struct Params {
    uint32_t *rng;
    double *counters;             // [c][MAXT][3][2] (total, accepted)
    double *scratch;              // [c][64] cross-CTA partial sums
+   double *vold;                 // [c][Q][NMpad] cached sum of the rotor's potential over the R slices of rot slice q
+   int *vepoch;                  // [c][Q][NMpad] value of pos_epoch the cache entry was computed at (-1: invalid)
+   int *pos_epoch;               // [c] bumped by every translational sweep
    // execution geometry
    int cpc, team;
+   int rot_group;                // threads cooperating on one rotational slice (power of two, may span warps)
    int seg_max;
+   double *segbuf;               // [c][nseg_max][(seg_max+1)*6] per-segment scratch in global memory, used when the
+   int segbuf_global, nseg_max;  // per-team shared-memory buffers would not fit (many narrow teams, long segments)
 };
 
 __host__ __device__ inline size_t pos_index(const Params &p, int c, int it, int d, int a)
@@ -132,38 +147,104 @@ __device__ __forceinline__ double splint_eval(const double *xa, const double *ya
 struct SmallTables {
    const double *g1d, *v1d, *y2_1d; const int *lut1d;
    const double *rgrid, *rdens, *rdens2; const int *lutrot;
+   const SplineRec *rec1d, *recrot;
+   const double2 *rgi2d, *cgi2d;   // axis tables of the 2-D potential (shared memory in the move kernel)
 };
+
+// interval search + cubic evaluation on the packed records: same interval as the reference's bisection search
+// (klo = max{k : x_k <= x}); a, b use the stored 1/h, the curvature terms the stored y'' h^2/6
+__device__ __forceinline__ double spline_rec_eval(const SplineRec *rec, int n, const int *lut, int nlut, double scale, double x0, double x, int *klo_out)
+{
+   int b = (int)((x - x0) * scale);
+   b = b < 0 ? 0 : (b >= nlut ? nlut - 1 : b);
+   int k = lut[b];
+   while (k < n - 2 && rec[k].xhi <= x) k++;
+   while (k > 0 && rec[k].xlo > x) k--;
+   if (klo_out) *klo_out = k;
+   const SplineRec r = rec[k];
+   double a = (r.xhi - x) * r.inv_h;
+   double bb = (x - r.xlo) * r.inv_h;
+   return a * r.ylo + bb * r.yhi + ((a * a * a - a) * r.clo + (bb * bb * bb - bb) * r.chi);
+}
 
 // SPot1D, mc_poten.cc:624-639
 __device__ __forceinline__ double spot1d(const Params &p, const SmallTables &t, double r, int *klo_out = nullptr)
 {
    int n = p.n1d;
    if (klo_out) *klo_out = -1;
-   if (r >= t.g1d[n - 1]) return -p.c6 / pow(r, 6.0);
-   if (r <= t.g1d[0]) return p.unode * exp(-p.alpha * r);
-   int k = spline_klo(t.g1d, n, t.lut1d, p.nlut1d, p.lut1d_scale, r);
-   if (klo_out) *klo_out = k;
-   return splint_eval(t.g1d, t.v1d, t.y2_1d, k, r);
+   const double x0 = t.rec1d[0].xlo, xn = t.rec1d[n - 2].xhi;
+   if (r >= xn) return -p.c6 / pow(r, 6.0);
+   if (r <= x0) return p.unode * exp(-p.alpha * r);
+   return spline_rec_eval(t.rec1d, n, t.lut1d, p.nlut1d, p.lut1d_scale, x0, r, klo_out);
 }
 
-// LPot2D, mc_poten.cc:688-729
-__device__ __forceinline__ double lpot2d(const Params &p, double r, double cost, int *pir = nullptr, int *pic = nullptr)
+// floor(x/delta) by true division: the rare exact path of lpot2d's index selection, kept out of line so ptxas does
+// not if-convert the FP64 division into the common path
+__device__ __noinline__ double exact_floor_div(double x, double delta) { return floor(x / delta); }
+
+// one 256-bit gather of the four corner values of a bilinear cell (one L1TEX wavefront per lane instead of eight)
+__device__ __forceinline__ void load_cell(const double *cell, double &y1, double &y2, double &y3, double &y4)
 {
-   double rmin = __ldg(p.rg2d), cmin = __ldg(p.cg2d);
-   int ir = (int)floor((r - rmin) / p.dr2d);
-   int ic = (int)floor((cost - cmin) / p.dc2d);
-   if (ir < 0) ir = 0; else if (ir >= p.rs2d - 1) ir = p.rs2d - 2;
-   if (ic < 0) ic = 0; else if (ic >= p.cs2d - 1) ic = p.cs2d - 2;
+   asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(y1), "=d"(y2), "=d"(y3), "=d"(y4) : "l"(cell));
+}
+// index selection of LPot2D, mc_poten.cc:696-704: floor((x - xmin)/delta) exactly as the reference -- the product with
+// the stored reciprocal decides unless it lands within 1e-7 of an integer, where the true quotient is taken
+// (|x*inv - x/delta| < 1e-11 here) -- then the clamp to [0, size-2]
+__device__ __forceinline__ int lpot_index(double x, double inv_delta, double delta, int size)
+{
+   // nearest integer of x*inv_delta by the 2^52+2^51 trick (no FP64<->int conversion instructions), then floor
+   const double MAGIC = 6755399441055744.0;
+   const double xq = x * inv_delta;
+   const double tq = xq + MAGIC;
+   int i = __double2loint(tq);
+   const double d = xq - (tq - MAGIC);
+   if (__builtin_expect(fabs(d) < 1e-7, 0)) i = (int)exact_floor_div(x, delta);
+   else if (d < 0.0) i -= 1;
+   return max(0, min(i, size - 2));
+}
+// r and 1/r from r^2 with one reciprocal-square-root (<= 1 ulp each); used inside the move kernel where the IEEE
+// sqrt + divide of the reference would cost ~40 more instructions per pair (the batched parity entry points keep
+// the exact forms)
+__device__ __forceinline__ void fast_r_invr(double r2, double &r, double &invr)
+{
+   invr = rsqrt(r2);
+   r = r2 * invr;
+}
+// LPot2D, mc_poten.cc:688-729
+__device__ __forceinline__ double lpot2d(const Params &p, const SmallTables &t, double r, double cost, int *pir = nullptr, int *pic = nullptr)
+{
+   const double rmin = t.rgi2d[0].x, cmin = t.cgi2d[0].x;
+   const int ir = lpot_index(r - rmin, p.inv_dr2d, p.dr2d, p.rs2d);
+   const int ic = lpot_index(cost - cmin, p.inv_dc2d, p.dc2d, p.cs2d);
    if (pir) *pir = ir;
    if (pic) *pic = ic;
-   const double *row0 = p.v2d + (size_t)ir * p.cs2d + ic;
-   const double *row1 = row0 + p.cs2d;
-   double y1 = __ldg(row0), y4 = __ldg(row0 + 1), y2 = __ldg(row1), y3 = __ldg(row1 + 1);
-   double r1 = __ldg(p.rg2d + ir), r2 = __ldg(p.rg2d + ir + 1);
-   double c1 = __ldg(p.cg2d + ic), c2 = __ldg(p.cg2d + ic + 1);
-   double dr = (r - r1) / (r2 - r1);
-   double dc = (cost - c1) / (c2 - c1);
+   double y1, y2, y3, y4;
+   load_cell(p.cell2d + ((size_t)ir * (p.cs2d - 1) + ic) * 4, y1, y2, y3, y4);
+   const double2 gr = t.rgi2d[ir], gc = t.cgi2d[ic];
+   double dr = (r - gr.x) * gr.y;
+   double dc = (cost - gc.x) * gc.y;
    return (1.0 - dr) * (1.0 - dc) * y1 + dr * (1.0 - dc) * y2 + dr * dc * y3 + (1.0 - dr) * dc * y4;
+}
+// four independent LPot2D evaluations: index arithmetic first, the four cell gathers next, the bilinear forms last
+__device__ __forceinline__ void lpot2d_x4(const Params &p, const SmallTables &t, const double *r, const double *cost, double *out)
+{
+   const double rmin = t.rgi2d[0].x, cmin = t.cgi2d[0].x;
+   int ir[4], ic[4];
+   #pragma unroll
+   for (int u = 0; u < 4; u++) {
+      ir[u] = lpot_index(r[u] - rmin, p.inv_dr2d, p.dr2d, p.rs2d);
+      ic[u] = lpot_index(cost[u] - cmin, p.inv_dc2d, p.dc2d, p.cs2d);
+   }
+   double y1[4], y2[4], y3[4], y4[4];
+   #pragma unroll
+   for (int u = 0; u < 4; u++) load_cell(p.cell2d + ((size_t)ir[u] * (p.cs2d - 1) + ic[u]) * 4, y1[u], y2[u], y3[u], y4[u]);
+   #pragma unroll
+   for (int u = 0; u < 4; u++) {
+      const double2 gr = t.rgi2d[ir[u]], gc = t.cgi2d[ic[u]];
+      double dr = (r[u] - gr.x) * gr.y;
+      double dc = (cost[u] - gc.x) * gc.y;
+      out[u] = (1.0 - dr) * (1.0 - dc) * y1[u] + dr * (1.0 - dc) * y2[u] + dr * dc * y3[u] + (1.0 - dr) * dc * y4[u];
+   }
 }
 
 // SRotDens / SRotDensDeriv / SRotDensEsqrt, mc_poten.cc:548-622 (which = 0,1,2)
@@ -183,7 +264,16 @@ __device__ __forceinline__ double srot_eval(const Params &p, const double *g, co
 }
 __device__ __forceinline__ double srotdens(const Params &p, const SmallTables &t, double gamma)
 {
-   return srot_eval(p, t.rgrid, t.rdens, t.rdens2, t.lutrot, gamma, 0);
+   const int n = p.nrot;
+   const SplineRec *rec = t.recrot;
+   if (gamma > rec[n - 2].xhi) return rec[n - 2].yhi;
+   if (gamma < rec[0].xlo) {
+      double rl = rec[0].xlo, rr = rec[0].xhi, y0 = rec[0].ylo, y1 = rec[0].yhi;
+      double salpha = (y1 - y0) / (rr - rl);
+      double sbeta = (y0 * rr - y1 * rl) / (rr - rl);
+      return salpha * gamma + sbeta;
+   }
+   return spline_rec_eval(rec, n, t.lutrot, p.nlutrot, p.lutrot_scale, rec[0].xlo, gamma, nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -408,11 +498,16 @@ __device__ __forceinline__ void load_rotmat(const Params &p, int c, int q, int m
    matpre(phi, acos(cth), chi, r);
 }
 
+// KIND prunes the branches at compile time: -1 all, 0 atoms only, 1 linear-rotor system, 2 top system.
+template <int KIND = -1>
 __device__ __forceinline__ double pair_energy(const Params &p, const SmallTables &t, int c, int atom0, const double *pos0,
                                               int atom1, int it, const Mat3 *rm0, const double *n0)
 {
    int type0 = type_of(p, atom0), type1 = type_of(p, atom1);
    int mode = p.mode[type0][type1];
+   if (KIND == 0) mode = M_SPOT1D;
+   if (KIND == 1 && mode != M_LIN_0MOL && mode != M_LIN_1MOL) mode = M_SPOT1D;
+   if (KIND == 2 && (mode == M_LIN_0MOL || mode == M_LIN_1MOL)) mode = M_SPOT1D;
    double p1[3], dr[3], dr2 = 0.0;
    #pragma unroll
    for (int d = 0; d < 3; d++) {
@@ -422,8 +517,7 @@ __device__ __forceinline__ double pair_energy(const Params &p, const SmallTables
       dr2 += dr[d] * dr[d];
    }
    int q = it / p.R;
-   switch (mode) {
-   case M_LIN_0MOL: case M_LIN_1MOL: {
+   if ((KIND == -1 || KIND == 1) && (mode == M_LIN_0MOL || mode == M_LIN_1MOL)) {
       double r = sqrt(dr2);
       double n[3];
       int sgn;
@@ -441,34 +535,33 @@ __device__ __forceinline__ double pair_energy(const Params &p, const SmallTables
       for (int d = 0; d < 3; d++) cost += n[d] * dr[d];
       cost /= r;
       cost *= sgn;
-      return lpot2d(p, r, cost);
+      return lpot2d(p, t, r, cost);
    }
-   case M_TOP_0MOL: {
-      Mat3 rl;
-      const Mat3 *rm = rm0;
-      if (!rm) { load_rotmat(p, c, q, atom0 - p.first[p.imtype], rl); rm = &rl; }
-      return vcord(p, *rm, pos0, p1, nullptr, nullptr);
+   if (KIND == -1 || KIND == 2) {
+      if (mode == M_TOP_0MOL) {
+         Mat3 rl;
+         const Mat3 *rm = rm0;
+         if (!rm) { load_rotmat(p, c, q, atom0 - p.first[p.imtype], rl); rm = &rl; }
+         return vcord(p, *rm, pos0, p1, nullptr, nullptr);
+      }
+      if (mode == M_TOP_1MOL) {
+         Mat3 rl;
+         load_rotmat(p, c, q, atom1 - p.first[p.imtype], rl);
+         return vcord(p, rl, p1, pos0, nullptr, nullptr);
+      }
+      if (mode == M_SPHER) return vspher(p, sqrt(dr2));
+      if (mode == M_TOPTOP) {
+         Mat3 ra, rb;
+         const Mat3 *rm = rm0;
+         if (!rm) { load_rotmat(p, c, q, atom0 - p.first[p.imtype], ra); rm = &ra; }
+         load_rotmat(p, c, q, atom1 - p.first[p.imtype], rb);
+         Tip4pSites sa, sb;
+         tip4p_sites(*rm, pos0, sa);
+         tip4p_sites(rb, p1, sb);
+         return caleng(sa, sb);
+      }
    }
-   case M_TOP_1MOL: {
-      Mat3 rl;
-      load_rotmat(p, c, q, atom1 - p.first[p.imtype], rl);
-      return vcord(p, rl, p1, pos0, nullptr, nullptr);
-   }
-   case M_SPHER:
-      return vspher(p, sqrt(dr2));
-   case M_TOPTOP: {
-      Mat3 ra, rb;
-      const Mat3 *rm = rm0;
-      if (!rm) { load_rotmat(p, c, q, atom0 - p.first[p.imtype], ra); rm = &ra; }
-      load_rotmat(p, c, q, atom1 - p.first[p.imtype], rb);
-      Tip4pSites sa, sb;
-      tip4p_sites(*rm, pos0, sa);
-      tip4p_sites(rb, p1, sb);
-      return caleng(sa, sb);
-   }
-   default:
-      return spot1d(p, t, sqrt(dr2));
-   }
+   return spot1d(p, t, sqrt(dr2));
 }
 
 } // namespace pimc

@@ -57,6 +57,7 @@ est_energy_kernel(const __grid_constant__ Params p, const __grid_constant__ EstB
    SmallTables t;
    t.g1d = p.g1d; t.v1d = p.v1d; t.y2_1d = p.y2_1d; t.lut1d = p.lut1d;
    t.rgrid = p.rgrid; t.rdens = p.rdens; t.rdens2 = p.rdens2; t.lutrot = p.lutrot;
+   t.rec1d = p.rec1d; t.recrot = p.recrot; t.rgi2d = p.rgi2d; t.cgi2d = p.cgi2d;
    const double delta_theta = PI / (double)(BINST - 1), delta_chi = 2.0 * PI / (double)(BINSC - 1);
 
    // ---- GetKinEnergy, mc_estim.cc:876-937: sum_atoms sum_it |r_it - r_it+1|^2 / (4 beta lambda)
@@ -108,7 +109,7 @@ est_energy_kernel(const __grid_constant__ Params p, const __grid_constant__ EstB
                if (bt < BINST && bt >= 0) atomicAdd(e.acc + e.off_gr2d + br * BINST + bt, 1.0);
             }
          }
-         pot += lpot2d(p, r, cost);
+         pot += lpot2d(p, t, r, cost);
       } else if (mode == M_TOP_0MOL || mode == M_TOP_1MOL || mode == M_SPHER) {
          double rtc[3], v;
          if (p.ispher == 0) {
@@ -264,14 +265,15 @@ __global__ void eval_spot1d_kernel(const __grid_constant__ Params p, int n, cons
 {
    int i = blockIdx.x * blockDim.x + threadIdx.x;
    if (i >= n) return;
-   SmallTables t; t.g1d = p.g1d; t.v1d = p.v1d; t.y2_1d = p.y2_1d; t.lut1d = p.lut1d;
+   SmallTables t; t.g1d = p.g1d; t.v1d = p.v1d; t.y2_1d = p.y2_1d; t.lut1d = p.lut1d; t.rec1d = p.rec1d; t.recrot = p.recrot; t.rgi2d = p.rgi2d; t.cgi2d = p.cgi2d;
    int k; v[i] = spot1d(p, t, r[i], &k); klo[i] = k;
 }
 __global__ void eval_lpot2d_kernel(const __grid_constant__ Params p, int n, const double *r, const double *c, double *v, int *ir, int *ic)
 {
    int i = blockIdx.x * blockDim.x + threadIdx.x;
    if (i >= n) return;
-   int a, b; v[i] = lpot2d(p, r[i], c[i], &a, &b); ir[i] = a; ic[i] = b;
+   SmallTables t; t.rgi2d = p.rgi2d; t.cgi2d = p.cgi2d;
+   int a, b; v[i] = lpot2d(p, t, r[i], c[i], &a, &b); ir[i] = a; ic[i] = b;
 }
 __global__ void eval_srot_kernel(const __grid_constant__ Params p, int n, const double *g, int which, double *v)
 {
@@ -316,7 +318,7 @@ __global__ void eval_caleng_kernel(int n, const double *c1, const double *c2, co
 __global__ void pot_energy_slice_kernel(const __grid_constant__ Params p, int c, double *v)
 {
    SmallTables t; t.g1d = p.g1d; t.v1d = p.v1d; t.y2_1d = p.y2_1d; t.lut1d = p.lut1d;
-   t.rgrid = p.rgrid; t.rdens = p.rdens; t.rdens2 = p.rdens2; t.lutrot = p.lutrot;
+   t.rgrid = p.rgrid; t.rdens = p.rdens; t.rdens2 = p.rdens2; t.lutrot = p.lutrot; t.rec1d = p.rec1d; t.recrot = p.recrot; t.rgi2d = p.rgi2d; t.cgi2d = p.cgi2d;
    int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
    if (w >= p.N * p.P) return;
    int atom = w / p.P, it = w % p.P;

@@ -5,9 +5,14 @@
 // resident for `nsteps` iterations of the reference's `time` loop (mc_main.cc:349-381) and walks
 // the stages of one step in order; dependent stages are separated by a chain-wide barrier
 // (__syncthreads for a 1-CTA chain, barrier.cluster otherwise).  Inside a stage the independent
-// units (bisection segments, rotational slices of one parity) are dealt to TEAMS of `team` lanes
-// (power of two, <= 32); the lanes of a team split the partner loop of the pair-action sum and
-// combine with a fixed-order warp-shuffle butterfly, so results are bit-reproducible.
+// units are dealt to groups of threads:
+//   * bisection segments -> TEAMS of `team` lanes (power of two <= 32): the lanes split the
+//     partner loop of the pair-action sum and combine with a fixed-order shuffle butterfly;
+//   * rotational slices of one parity -> ROT GROUPS of `rot_group` threads (power of two, may span
+//     several warps of one CTA): warp butterfly + fixed-order shared-memory combine.
+// Every reduction has a fixed order, so a trajectory is bit-reproducible for a given geometry.
+// The kernel is specialised at compile time on the rotor kind (KIND 0 atoms only, 1 linear rotor,
+// 2 non-linear top) so each variant carries only its own interaction branches.
 //
 // Schedule (DESIGN.md "Schedule"; the CPU replay is oracle/pimc_oracle.cpp:orc_sched_run):
 //   step t, time = t mod P, for each type:
@@ -22,13 +27,33 @@
 namespace pimc {
 namespace cg = cooperative_groups;
 
+#ifdef PIMC_TIMELINE
+__device__ long long g_marks[4096];
+__device__ int g_nmarks;
+#define MARK(x, id) do { if ((x).gthread == 0 && (x).c == 0 && g_nmarks < 4000) { g_marks[g_nmarks++] = ((long long)(id) << 48) | (clock64() & 0xffffffffffffLL); } } while (0)
+#else
+#define MARK(x, id) do { } while (0)
+#endif
+
+// per rot group scratch in shared memory
+struct RotSlot {
+   double u4;                 // uniform of the accept test
+   double cost, phi, chi;     // proposal
+   double a[9], b[9];         // KIND 2: rotation matrices of the new (a) and current (b) orientation; KIND 1: a[0..2] = n_new, b[0..2] = n_cur
+   double rho[4];             // the four density-matrix factors
+   int need_old, bad;
+};
+
 struct Ctx {
    int c, crank;
    int tid, gthread, nthreads_chain;
    int T, lane_t, team_lane0, team_id, nteams_chain;
+   int G, gl, grp, ngrp;      // rot group size, index inside the group, group index in the CTA, groups per CTA
    SmallTables t;
-   double *team_buf;   // shared: (seg_max+1)*3 doubles per team
+   double *team_buf;   // shared: (seg_max+1)*6 doubles per team (segment positions + unit normals)
    double *red;        // shared: 40 doubles
+   RotSlot *slot;      // shared: this thread's rot group slot (thread-private storage when the group is one thread)
+   double *part;       // shared: per-warp partial sums (new, old) of this thread's rot group, used when it spans warps
 };
 
 __device__ __forceinline__ void chain_sync(const Params &p)
@@ -39,16 +64,6 @@ __device__ __forceinline__ void chain_sync(const Params &p)
 __device__ __forceinline__ double team_sum(double v, int T)
 {
    for (int o = T >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-   return v;
-}
-__device__ __forceinline__ double team_prod(double v, int T)
-{
-   for (int o = T >> 1; o > 0; o >>= 1) v *= __shfl_xor_sync(0xffffffffu, v, o);
-   return v;
-}
-__device__ __forceinline__ int team_or(int v, int T)
-{
-   for (int o = T >> 1; o > 0; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
    return v;
 }
 __device__ __forceinline__ uint32_t *stream_ptr(const Params &p, int c, int s)
@@ -78,10 +93,80 @@ __device__ double chain_reduce(const Params &p, Ctx &x, double v)
    return tot;
 }
 
+// V(bead at pn) - V(bead at po) of atom g against partner j at slice it; for atom-atom pairs of a spline system the
+// partner position is loaded once
+template <int KIND>
+__device__ __forceinline__ double pair_diff(const Params &p, const SmallTables &t, int c, int g, const double *pn, const double *po, int j, int it)
+{
+   if (KIND != 2 && p.mode[type_of(p, g)][type_of(p, j)] == M_SPOT1D && !p.minimage) {
+      double d2n = 0.0, d2o = 0.0;
+      #pragma unroll
+      for (int d = 0; d < 3; d++) {
+         double pj = p.pos[pos_index(p, c, it, d, j)];
+         d2n += (pn[d] - pj) * (pn[d] - pj);
+         d2o += (po[d] - pj) * (po[d] - pj);
+      }
+      return spot1d(p, t, sqrt(d2n)) - spot1d(p, t, sqrt(d2o));
+   }
+   return pair_energy<KIND>(p, t, c, g, pn, j, it, nullptr, nullptr) - pair_energy<KIND>(p, t, c, g, po, j, it, nullptr, nullptr);
+}
+
+// sum over the partners j = lane, lane+stride, ... of V(g at pn) - V(g at po) at slice it.  Atom-atom spline pairs are
+// processed four partners at a time per lane (their position loads are issued together); rotor partners and
+// everything else go through pair_diff.
+template <int KIND>
+__device__ __forceinline__ double partner_sum_diff(const Params &p, const SmallTables &t, int c, int g, const double *pn, const double *po,
+                                                   int it, int lane, int stride)
+{
+   double D = 0.0;
+   const int N = p.N;
+   const int tg = type_of(p, g);
+   const bool fast = (KIND != 2) && p.molecule[tg] == 0 && !p.minimage && p.n1d > 0;      // moved bead is an atom of a spline system
+   if (fast) {
+      const int ja = p.first[tg], jb = ja + p.numb[tg];          // atom partners [ja, jb)
+      const double *px = p.pos + pos_index(p, c, it, 0, 0), *py = px + p.Npad, *pz = py + p.Npad;
+      for (int j0 = ja + lane; j0 < jb; j0 += 4 * stride) {
+         double rn[4], ro[4];
+         bool ok[4];
+         #pragma unroll
+         for (int u = 0; u < 4; u++) {
+            const int j = j0 + u * stride;
+            ok[u] = j < jb && j != g;
+            const int jj = ok[u] ? j : ja;
+            const double qx = px[jj], qy = py[jj], qz = pz[jj];
+            double inv_;
+            fast_r_invr((pn[0] - qx) * (pn[0] - qx) + (pn[1] - qy) * (pn[1] - qy) + (pn[2] - qz) * (pn[2] - qz), rn[u], inv_);
+            fast_r_invr((po[0] - qx) * (po[0] - qx) + (po[1] - qy) * (po[1] - qy) + (po[2] - qz) * (po[2] - qz), ro[u], inv_);
+         }
+         #pragma unroll
+         for (int u = 0; u < 4; u++) {
+            double e = spot1d(p, t, rn[u]) - spot1d(p, t, ro[u]);
+            D += ok[u] ? e : 0.0;
+         }
+      }
+      for (int j = lane; j < N; j += stride) {                    // the remaining partners (the rotor)
+         if (j >= ja && j < jb) continue;
+         D += pair_diff<KIND>(p, t, c, g, pn, po, j, it);
+      }
+      return D;
+   }
+   for (int j = lane; j < N; j += stride) {
+      if (j == g) continue;
+      D += pair_diff<KIND>(p, t, c, g, pn, po, j, it);
+   }
+   return D;
+}
+
+__device__ __forceinline__ void bump_pos_epoch(const Params &p, Ctx &x)
+{
+   if (x.gthread == 0) p.pos_epoch[x.c] += 1;      // read by the rot leaders after the next chain barrier
+}
+
 // ---------------------------------------------------------------------------------------------
 // whole-path move of every permutation cycle of `type` (MCMolecularMove / MCMolecularMoveExchange,
 // mc_piqmc.cc:54-192).  dV of the rigid shift: cycle members against non-members, all P slices.
 // ---------------------------------------------------------------------------------------------
+template <int KIND>
 __device__ void molecular_sweep(const Params &p, Ctx &x, int type)
 {
    const int c = x.c, P = p.P, N = p.N;
@@ -91,6 +176,7 @@ __device__ void molecular_sweep(const Params &p, Ctx &x, int type)
    for (int t = 0; t < type; t++) g0 += p.ncyc[c * MAXT + t];
    int g1 = g0 + p.ncyc[c * MAXT + type];
    uint32_t *ms = stream_ptr(p, c, P + p.Q);
+   bump_pos_epoch(p, x);
    for (int g = g0; g < g1; g++) {
       Mrg rs;
       mrg_load(rs, ms);
@@ -110,7 +196,7 @@ __device__ void molecular_sweep(const Params &p, Ctx &x, int type)
          double po[3], pn[3];
          #pragma unroll
          for (int d = 0; d < 3; d++) { po[d] = p.pos[pos_index(p, c, it, d, a0)]; pn[d] = po[d] + disp[d]; }
-         part += pair_energy(p, x.t, c, a0, pn, j, it, nullptr, nullptr) - pair_energy(p, x.t, c, a0, po, j, it, nullptr, nullptr);
+         part += pair_diff<KIND>(p, x.t, c, a0, pn, po, j, it);
       }
       double deltav = chain_reduce(p, x, part);
       bool acc = (deltav < 0.0) || (exp(-deltav * p.tau) > u3);
@@ -141,14 +227,15 @@ __device__ void molecular_sweep(const Params &p, Ctx &x, int type)
 // the dV of the midpoints sampled at level l, so delta = (D - S)*tau*seg_l/2 equals the
 // reference's (pot0 - 2 pot1)*tau*(seg_l/2) without re-evaluating earlier levels (:263 "inefficient").
 // ---------------------------------------------------------------------------------------------
+template <int KIND>
 __device__ void bisection_sweep(const Params &p, Ctx &x, int type, int off)
 {
    const int c = x.c, P = p.P, N = p.N, T = x.T;
    const int L = p.levels[type], seg = 1 << L, nseg = P / seg;
    const int base = p.first[type];
    const double bnorm = 1.0 / (p.lambda[type] * p.tau);
-   double *nx = x.team_buf;
    const int nrounds = (nseg + x.nteams_chain - 1) / x.nteams_chain;
+   bump_pos_epoch(p, x);
    for (int a = 0; a < p.numb[type]; a++) {
       const int gA = base + a;
       const int gB = (p.stat[type] == 1) ? p.pindex[(size_t)c * N + gA] : gA;
@@ -156,47 +243,56 @@ __device__ void bisection_sweep(const Params &p, Ctx &x, int type, int off)
          const int k = rd * x.nteams_chain + x.team_id;
          const bool active = k < nseg;
          const int s0 = active ? (off + k * seg) % P : 0;
+         double *nx = p.segbuf_global ? p.segbuf + ((size_t)c * p.nseg_max + (active ? k : 0)) * ((p.seg_max + 1) * 6) : x.team_buf;
          if (active)
             for (int i = x.lane_t; i < 6; i += T) {
                int e = i / 3, d = i - 3 * e, t = e * seg;
                int g = (s0 + t >= P) ? gB : gA;
                nx[t * 3 + d] = p.pos[pos_index(p, c, (s0 + t) % P, d, g)];
             }
-         __syncwarp();
+         // unit normals for all interior slices of the segment, drawn up front from the slices' own streams
+         // (6 uniforms per slice: gauss() of mc_randg.cc:138-150 per dimension), stored behind the positions
+         double *xi = nx + (seg + 1) * 3;
+         for (int i0 = 0; i0 < (seg - 1) * 3; i0 += T) {
+            const int i = i0 + x.lane_t;
+            const bool valid = active && i < (seg - 1) * 3;
+            const int t = 1 + i / 3, d = i - 3 * (t - 1);
+            uint32_t *sp = stream_ptr(p, c, (s0 + (valid ? t : 0)) % P);
+            Mrg rs;
+            if (valid) {
+               mrg_load(rs, sp);
+               double r1 = 0, r2 = 0;
+               for (int k = 0; k <= d; k++) { r1 = mrg_u01(rs); r2 = mrg_u01(rs); }
+               for (int k = d + 1; k < 3; k++) { mrg_u01(rs); mrg_u01(rs); }
+               xi[t * 3 + d] = sqrt(-log(r1)) * cos(2.0 * PI * r2);
+            }
+            __syncwarp();                               // every lane of a slice has read the state before it advances
+            if (valid && d == 2) mrg_store(rs, sp);
+            __syncwarp();
+         }
          double S = 0.0;
          bool alive = active;
          for (int level = 0; level < L; level++) {
             const int lss = seg >> level, half = lss >> 1, nmid = 1 << level;
             if (alive) {
-               const double bkin = bnorm / (double)lss;
-               for (int m = x.lane_t; m < nmid; m += T) {
+               const double sq = sqrt(bnorm / (double)lss);
+               for (int i = x.lane_t; i < nmid * 3; i += T) {
+                  int m = i / 3, d = i - 3 * m;
                   int t1 = half + m * lss;
-                  int sl = (s0 + t1) % P;
-                  uint32_t *sp = stream_ptr(p, c, sl);
-                  Mrg rs;
-                  mrg_load(rs, sp);
-                  #pragma unroll
-                  for (int d = 0; d < 3; d++) {
-                     double r1 = mrg_u01(rs), r2 = mrg_u01(rs);
-                     nx[t1 * 3 + d] = 0.5 * (nx[(t1 - half) * 3 + d] + nx[(t1 + half) * 3 + d]) + gauss_u(bkin, r1, r2);
-                  }
-                  mrg_store(rs, sp);
+                  nx[t1 * 3 + d] = 0.5 * (nx[(t1 - half) * 3 + d] + nx[(t1 + half) * 3 + d]) + xi[t1 * 3 + d] / sq;
                }
             }
             __syncwarp();
             double D = 0.0;
             if (alive) {
-               const int nitems = nmid * N;
-               for (int i = x.lane_t; i < nitems; i += T) {
-                  int m = i / N, j = i - m * N;
-                  int t1 = half + m * lss;
-                  int sl = (s0 + t1) % P;
-                  int g = (s0 + t1 >= P) ? gB : gA;
-                  if (j == g) continue;
+               for (int m = 0; m < nmid; m++) {
+                  const int t1 = half + m * lss;
+                  const int sl = (s0 + t1) % P;
+                  const int g = (s0 + t1 >= P) ? gB : gA;
                   double po[3], pn[3];
                   #pragma unroll
                   for (int d = 0; d < 3; d++) { po[d] = p.pos[pos_index(p, c, sl, d, g)]; pn[d] = nx[t1 * 3 + d]; }
-                  D += pair_energy(p, x.t, c, g, pn, j, sl, nullptr, nullptr) - pair_energy(p, x.t, c, g, po, j, sl, nullptr, nullptr);
+                  D += partner_sum_diff<KIND>(p, x.t, c, g, pn, po, sl, x.lane_t, T);
                }
             }
             D = team_sum(D, T);
@@ -234,43 +330,124 @@ __device__ void bisection_sweep(const Params &p, Ctx &x, int type, int off)
 }
 
 // ---------------------------------------------------------------------------------------------
-// one rotational Metropolis step at rot slice q for rotor m of `type`
-// (MCRot3Dstep mc_piqmc.cc:938-1199, MCRotLinStep :781-936; RotDenType 0)
+// rotational Metropolis step at rot slice q for rotor m (MCRot3Dstep mc_piqmc.cc:938-1199,
+// MCRotLinStep :781-936; RotDenType 0), executed by one rot group:
+//   leader: uniforms, proposal, orientation matrices          -> shared slot          | group sync
+//   all   : the four density factors (first four threads) and the partner/slice sum of the
+//           potential for the proposed orientation; the sum for the current orientation is taken
+//           from the per-slice cache unless a translational sweep or a partner rotor invalidated it
+//           (mathematically the reference's pot_old, :1069-1075)                      | group sync
+//   leader: acceptance, state and cache update
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void group_sync(const Ctx &x)
+{
+   if (x.G > 32) __syncthreads(); else __syncwarp();
+}
+
+// sum over the R translational slices of rot slice q and all partners of the rotor's potential
+// for the orientation in `o` (KIND 2: rotation matrix; KIND 1: unit vector); strided over the group
+template <int KIND>
+__device__ __forceinline__ double rot_potential(const Params &p, Ctx &x, int g, int q, const double *o)
+{
+   const int c = x.c, N = p.N, R = p.R, it0 = q * R;
+   double v = 0.0;
+   if (KIND == 2) {
+      Mat3 ro;
+      #pragma unroll
+      for (int i = 0; i < 9; i++) ro.m[i / 3][i % 3] = o[i];
+      for (int j = x.gl; j < N; j += x.G) {
+         if (j == g) continue;
+         if (type_of(p, j) == p.imtype) {           // rotor partner: its orientation is the same for all R slices
+            Mat3 rb;
+            load_rotmat(p, c, q, j - p.first[p.imtype], rb);
+            for (int r = 0; r < R; r++) {
+               double pg[3], pj[3];
+               #pragma unroll
+               for (int d = 0; d < 3; d++) { pg[d] = p.pos[pos_index(p, c, it0 + r, d, g)]; pj[d] = p.pos[pos_index(p, c, it0 + r, d, j)]; }
+               Tip4pSites sa, sb;
+               tip4p_sites(ro, pg, sa);
+               tip4p_sites(rb, pj, sb);
+               v += caleng(sa, sb);
+            }
+         } else {
+            for (int r = 0; r < R; r++) {
+               double pg[3], pj[3];
+               #pragma unroll
+               for (int d = 0; d < 3; d++) { pg[d] = p.pos[pos_index(p, c, it0 + r, d, g)]; pj[d] = p.pos[pos_index(p, c, it0 + r, d, j)]; }
+               v += p.ispher ? vspher(p, sqrt(dist2(pg, pj))) : vcord(p, ro, pg, pj, nullptr, nullptr);
+            }
+         }
+      }
+   } else {
+      // items (slice r, partner j) without integer division: the warps of the group stride over the R slices,
+      // their lanes over the partners (coalesced over j); a group narrower than a warp walks the slices in turn
+      const int lanes = (x.G < 32) ? x.G : 32, lane = x.gl & (lanes - 1);
+      const int gw = x.gl / lanes, ngw = x.G / lanes;
+      for (int r = gw; r < R; r += ngw) {
+         const int it = it0 + r;
+         const double gx = p.pos[pos_index(p, c, it, 0, g)], gy = p.pos[pos_index(p, c, it, 1, g)], gz = p.pos[pos_index(p, c, it, 2, g)];
+         const double *px = p.pos + pos_index(p, c, it, 0, 0), *py = px + p.Npad, *pz = py + p.Npad;
+         // four partners per lane in flight: position loads, then all table gathers, then the bilinear forms, so
+         // the L2 latencies of independent evaluations overlap (the loop body alone exposes ~2 k cycles per partner)
+         for (int j0 = lane; j0 < N; j0 += 4 * lanes) {
+            double rr[4], cs[4];
+            bool ok[4];
+            #pragma unroll
+            for (int u = 0; u < 4; u++) {
+               const int j = j0 + u * lanes;
+               ok[u] = j < N && j != g;
+               const int jj = ok[u] ? j : (g == 0 ? 1 : 0);        // a valid, distinct partner for masked slots
+               double dx = gx - px[jj], dy = gy - py[jj], dz = gz - pz[jj];
+               double dr2 = dx * dx + dy * dy + dz * dz;
+               double dot = o[0] * dx + o[1] * dy + o[2] * dz;
+               double invr;
+               fast_r_invr(dr2, rr[u], invr);
+               cs[u] = -dot * invr;
+            }
+            double e[4];
+            lpot2d_x4(p, x.t, rr, cs, e);
+            #pragma unroll
+            for (int u = 0; u < 4; u++) v += ok[u] ? e[u] : 0.0;
+         }
+      }
+   }
+   return v;
+}
+
+template <int KIND>
 __device__ void rot_step(const Params &p, Ctx &x, int type, int q, int m, bool active, int *err)
 {
-   const int c = x.c, N = p.N, Q = p.Q, R = p.R, T = x.T;
+   const int c = x.c, Q = p.Q, G = x.G;
    const int g = p.first[type] + m;
-   const bool top = p.molecule[type] == 2;
-   double r1 = 0, r2 = 0, r3 = 0, r4 = 0;
-   if (active && x.lane_t == 0) {
-      uint32_t *sp = stream_ptr(p, c, p.P + q);
-      Mrg rs;
-      mrg_load(rs, sp);
-      r1 = mrg_u01(rs); r2 = mrg_u01(rs); r3 = mrg_u01(rs);
-      if (top) r4 = mrg_u01(rs);
-      mrg_store(rs, sp);
-   }
-   r1 = __shfl_sync(0xffffffffu, r1, x.team_lane0);
-   r2 = __shfl_sync(0xffffffffu, r2, x.team_lane0);
-   r3 = __shfl_sync(0xffffffffu, r3, x.team_lane0);
-   r4 = __shfl_sync(0xffffffffu, r4, x.team_lane0);
-   if (!top) r4 = r3;            // the linear step uses its third uniform for the accept test
-
+   RotSlot own;
+   RotSlot *sl = (G == 1) ? &own : x.slot;
    int q0 = q - 1, q2 = q + 1;
    if (q0 < 0) q0 += Q;
    if (q2 >= Q) q2 -= Q;
-   const double step = p.rtstep[type];
-   double dens_old = 1.0, dens_new = 1.0, dV = 0.0;
-   double cost = 0, phi = 0, chi = 0, nn[3] = {0, 0, 1};
-   int bad = 0;
-   if (active) {
-      cost = p.ang[ang_index(p, c, q, 1, m)];
-      phi = p.ang[ang_index(p, c, q, 0, m)];
-      chi = p.ang[ang_index(p, c, q, 2, m)];
-      const double cost_old = cost, phi_old = phi, chi_old = chi;
+   double *vcache = p.vold + ((size_t)c * Q + q) * p.NMpad + m;
+   int *vep = p.vepoch + ((size_t)c * Q + q) * p.NMpad + m;
+
+   MARK(x, 1);
+   if (active && x.gl == 0) {
+      uint32_t *sp = stream_ptr(p, c, p.P + q);
+      Mrg rs;
+      mrg_load(rs, sp);
+      double r1 = mrg_u01(rs), r2 = mrg_u01(rs), r3 = mrg_u01(rs), r4 = r3;
+      if (KIND == 2) r4 = mrg_u01(rs);
+      mrg_store(rs, sp);
+      const double step = p.rtstep[type];
+      double cost = p.ang[ang_index(p, c, q, 1, m)], phi = p.ang[ang_index(p, c, q, 0, m)], chi = p.ang[ang_index(p, c, q, 2, m)];
+      if (KIND == 2) {
+         Mat3 R1;
+         matpre(phi, acos(cost), chi, R1);
+         #pragma unroll
+         for (int i = 0; i < 9; i++) sl->b[i] = R1.m[i / 3][i % 3];
+      } else {
+         #pragma unroll
+         for (int d = 0; d < 3; d++) sl->b[d] = p.cosn[ang_index(p, c, q, d, m)];
+      }
       cost += step * (r1 - 0.5);
-      if (top) {
+      if (KIND == 2) {
          phi += 2.0 * PI * (step * (r2 - 0.5));
          chi += 2.0 * PI * (step * (r3 - 0.5));
          if (phi < 0.0) phi = 2.0 * PI + phi;
@@ -282,102 +459,118 @@ __device__ void rot_step(const Params &p, Ctx &x, int type, int q, int m, bool a
       }
       if (cost > 1.0) cost = 2.0 - cost;
       if (cost < -1.0) cost = -2.0 - cost;
-      const int it0 = q * R;
-      const int nitems = R * N;
-      if (top) {
-         Mat3 R0, R1, R2, Rn;
-         load_rotmat(p, c, q0, m, R0);
-         matpre(phi_old, acos(cost_old), chi_old, R1);
-         load_rotmat(p, c, q2, m, R2);
+      if (KIND == 2) {
+         Mat3 Rn;
          matpre(phi, acos(cost), chi, Rn);
-         double po = 1.0, pn = 1.0;
-         for (int i = x.lane_t; i < 4; i += T) {
-            int istop = 0;
-            if (i == 0) po *= rotden(p, R0, R1, nullptr, nullptr, nullptr, nullptr, &istop);
-            else if (i == 1) po *= rotden(p, R1, R2, nullptr, nullptr, nullptr, nullptr, &istop);
-            else if (i == 2) pn *= rotden(p, R0, Rn, nullptr, nullptr, nullptr, nullptr, &istop);
-            else pn *= rotden(p, Rn, R2, nullptr, nullptr, nullptr, nullptr, &istop);
-            bad |= istop;
-         }
-         dens_old = po; dens_new = pn;
-         for (int i = x.lane_t; i < nitems; i += T) {
-            int r = i / N, j = i - r * N;
-            if (j == g) continue;
-            int it = it0 + r;
-            double pg[3];
-            #pragma unroll
-            for (int d = 0; d < 3; d++) pg[d] = p.pos[pos_index(p, c, it, d, g)];
-            dV += pair_energy(p, x.t, c, g, pg, j, it, &Rn, nullptr) - pair_energy(p, x.t, c, g, pg, j, it, &R1, nullptr);
-         }
+         #pragma unroll
+         for (int i = 0; i < 9; i++) sl->a[i] = Rn.m[i / 3][i % 3];
       } else {
          const double sint = sqrt(1.0 - cost * cost);
          double sp_, cp_;
          sincos(phi, &sp_, &cp_);
-         nn[0] = sint * cp_; nn[1] = sint * sp_; nn[2] = cost;
-         double n0[3], n1[3], n2[3];
-         #pragma unroll
-         for (int d = 0; d < 3; d++) {
-            n0[d] = p.cosn[ang_index(p, c, q0, d, m)];
-            n1[d] = p.cosn[ang_index(p, c, q, d, m)];
-            n2[d] = p.cosn[ang_index(p, c, q2, d, m)];
-         }
-         double po = 1.0, pn = 1.0;
-         for (int i = x.lane_t; i < 4; i += T) {
-            const double *a = (i == 0 || i == 2) ? n0 : (i == 1 ? n1 : nn);
-            const double *b = (i == 0) ? n1 : (i == 2 ? nn : n2);
+         sl->a[0] = sint * cp_; sl->a[1] = sint * sp_; sl->a[2] = cost;
+      }
+      sl->u4 = r4; sl->cost = cost; sl->phi = phi; sl->chi = chi;
+      sl->need_old = (*vep != p.pos_epoch[c]) ? 1 : 0;
+      sl->bad = 0;
+   }
+   MARK(x, 2);
+   group_sync(x);
+   MARK(x, 3);
+
+   double vnew = 0.0, vold = 0.0;
+   if (active) {
+      // density factors: i = 0 rho(q0 -> cur), 1 rho(cur -> q2), 2 rho(q0 -> new), 3 rho(new -> q2)
+      for (int i = x.gl; i < 4; i += G) {
+         if (KIND == 2) {
+            Mat3 A, B;
+            const double *mid = (i < 2) ? sl->b : sl->a;
+            if (i == 0 || i == 2) {
+               load_rotmat(p, c, q0, m, A);
+               #pragma unroll
+               for (int k = 0; k < 9; k++) B.m[k / 3][k % 3] = mid[k];
+            } else {
+               #pragma unroll
+               for (int k = 0; k < 9; k++) A.m[k / 3][k % 3] = mid[k];
+               load_rotmat(p, c, q2, m, B);
+            }
+            int istop = 0;
+            sl->rho[i] = rotden(p, A, B, nullptr, nullptr, nullptr, nullptr, &istop);
+            if (istop) { if (G == 1) sl->bad |= 1; else atomicOr(&sl->bad, 1); }
+         } else {
+            const double *mid = (i < 2) ? sl->b : sl->a;
+            const int qq = (i == 0 || i == 2) ? q0 : q2;
             double dot = 0.0;
             #pragma unroll
-            for (int d = 0; d < 3; d++) dot += a[d] * b[d];
-            double rho = srotdens(p, x.t, dot);
-            if (i < 2) po *= rho; else pn *= rho;
-         }
-         dens_old = po; dens_new = pn;
-         for (int i = x.lane_t; i < nitems; i += T) {
-            int r = i / N, j = i - r * N;
-            if (j == g) continue;
-            int it = it0 + r;
-            double pg[3];
-            #pragma unroll
-            for (int d = 0; d < 3; d++) pg[d] = p.pos[pos_index(p, c, it, d, g)];
-            dV += pair_energy(p, x.t, c, g, pg, j, it, nullptr, nn) - pair_energy(p, x.t, c, g, pg, j, it, nullptr, n1);
+            for (int d = 0; d < 3; d++) {
+               double nb = p.cosn[ang_index(p, c, qq, d, m)];
+               dot += (i == 0 || i == 2) ? nb * mid[d] : mid[d] * nb;
+            }
+            sl->rho[i] = srotdens(p, x.t, dot);
          }
       }
+      MARK(x, 4);
+      vnew = rot_potential<KIND>(p, x, g, q, sl->a);
+      if (sl->need_old) vold = rot_potential<KIND>(p, x, g, q, sl->b);
    }
-   dens_old = team_prod(dens_old, T);
-   dens_new = team_prod(dens_new, T);
-   dV = team_sum(dV, T);
-   bad = team_or(bad, T);
-   if (active && x.lane_t == 0) {
+   MARK(x, 5);
+   // group reduction in a fixed order
+   const int gw = (G < 32) ? G : 32;
+   vnew = team_sum(vnew, gw);
+   vold = team_sum(vold, gw);
+   if (G > 32 && (x.tid & 31) == 0) { x.part[2 * (x.gl >> 5)] = vnew; x.part[2 * (x.gl >> 5) + 1] = vold; }
+   group_sync(x);
+   MARK(x, 6);
+
+   if (active && x.gl == 0) {
+      if (G > 32) {
+         vnew = 0.0; vold = 0.0;
+         for (int w = 0; w < (G >> 5); w++) { vnew += x.part[2 * w]; vold += x.part[2 * w + 1]; }
+      }
+      if (!sl->need_old) vold = *vcache;
+      double dens_old = sl->rho[0] * sl->rho[1], dens_new = sl->rho[2] * sl->rho[3];
+      int bad = sl->bad;
       if (fabs(dens_old) < RZERO) dens_old = 0.0;
       if (fabs(dens_new) < RZERO) dens_new = 0.0;
-      if (top) { dens_old = fabs(dens_old); dens_new = fabs(dens_new); }
+      if (KIND == 2) { dens_old = fabs(dens_old); dens_new = fabs(dens_new); }
       else if (dens_old < 0.0 || dens_new < 0.0) bad = 2;     // "Negative rot density" is fatal in the reference
       double rd = (dens_old > RZERO) ? dens_new / dens_old : 1.0;
-      rd *= exp(-p.tau * dV);
-      bool acc = (rd > 1.0) || (rd > r4);
+      rd *= exp(-p.tau * (vnew - vold));
+      bool acc = (rd > 1.0) || (rd > sl->u4);
       if (bad) { acc = false; atomicOr(err, bad); }
       double *cn = counter_ptr(p, c, type, 2);
       atomicAdd(cn, 1.0);
+      *vcache = acc ? vnew : vold;
+      *vep = p.pos_epoch[c];
       if (acc) {
          atomicAdd(cn + 1, 1.0);
-         p.ang[ang_index(p, c, q, 1, m)] = cost;
-         p.ang[ang_index(p, c, q, 0, m)] = phi;
-         if (top) {
-            p.ang[ang_index(p, c, q, 2, m)] = chi;
-            const double sint = sqrt(1.0 - cost * cost);
+         p.ang[ang_index(p, c, q, 1, m)] = sl->cost;
+         p.ang[ang_index(p, c, q, 0, m)] = sl->phi;
+         double nn[3];
+         if (KIND == 2) {
+            p.ang[ang_index(p, c, q, 2, m)] = sl->chi;
+            const double sint = sqrt(1.0 - sl->cost * sl->cost);
             double sp_, cp_;
-            sincos(phi, &sp_, &cp_);
-            nn[0] = sint * cp_; nn[1] = sint * sp_; nn[2] = cost;
+            sincos(sl->phi, &sp_, &cp_);
+            nn[0] = sint * cp_; nn[1] = sint * sp_; nn[2] = sl->cost;
+            for (int mm = 0; mm < p.NM; mm++)            // partner rotors at this slice see a new neighbour
+               if (mm != m) p.vepoch[((size_t)c * Q + q) * p.NMpad + mm] = -1;
+         } else {
+            nn[0] = sl->a[0]; nn[1] = sl->a[1]; nn[2] = sl->a[2];
          }
          #pragma unroll
          for (int d = 0; d < 3; d++) p.cosn[ang_index(p, c, q, d, m)] = nn[d];
       }
    }
-   __syncwarp();
+   MARK(x, 7);
+   group_sync(x);
+   MARK(x, 8);
 }
 
 // even slices, then odd slices (MCRotations3D mc_piqmc.cc:737-771, MCRotationsMove :490-512);
-// an odd slice count gets a third phase for the last slice.
+// an odd slice count gets a third phase for the last slice.  CTA `crank` of the chain owns the
+// slices idx = s*cpc + crank of a phase; its rot groups take them ngrp at a time.
+template <int KIND>
 __device__ void rot_sweep(const Params &p, Ctx &x, int type, int *err)
 {
    const int Q = p.Q;
@@ -385,15 +578,19 @@ __device__ void rot_sweep(const Params &p, Ctx &x, int type, int *err)
    for (int phase = 0; phase < 3; phase++) {
       int count = (phase == 0) ? (qe + 1) / 2 : (phase == 1 ? qe / 2 : (qe != Q ? 1 : 0));
       if (count == 0) continue;
-      int nrounds = (count + x.nteams_chain - 1) / x.nteams_chain;
+      int S = (count + p.cpc - 1) / p.cpc;
+      int nrounds = (S + x.ngrp - 1) / x.ngrp;
       for (int rd = 0; rd < nrounds; rd++) {
-         int idx = rd * x.nteams_chain + x.team_id;
-         bool active = idx < count;
+         int s = rd * x.ngrp + x.grp;
+         int idx = s * p.cpc + x.crank;
+         bool active = s < S && idx < count;
          int q = (phase == 0) ? 2 * idx : (phase == 1 ? 2 * idx + 1 : Q - 1);
          if (!active) q = 0;
-         for (int m = 0; m < p.numb[type]; m++) rot_step(p, x, type, q, m, active, err);
+         for (int m = 0; m < p.numb[type]; m++) rot_step<KIND>(p, x, type, q, m, active, err);
       }
+      MARK(x, 9);
       chain_sync(p);
+      MARK(x, 10);
    }
 }
 
@@ -402,27 +599,37 @@ __device__ void rot_sweep(const Params &p, Ctx &x, int type, int *err)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void stage_tables(const Params &p, SmallTables &t, double *&cursor)
 {
-   // copies the small spline tables into shared memory; `cursor` walks the dynamic smem block
-   auto put = [&](const double *src, int n) -> const double * {
-      double *dst = cursor;
-      for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
-      cursor += (n + 1) & ~1;
-      return dst;
-   };
-   auto puti = [&](const int *src, int n) -> const int * {
-      int *dst = reinterpret_cast<int *>(cursor);
-      for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
-      cursor += ((n + 1) / 2 + 1) & ~1;
-      return dst;
-   };
-   t.g1d = t.v1d = t.y2_1d = nullptr; t.lut1d = nullptr;
-   t.rgrid = t.rdens = t.rdens2 = nullptr; t.lutrot = nullptr;
-   if (p.n1d) { t.g1d = put(p.g1d, p.n1d); t.v1d = put(p.v1d, p.n1d); t.y2_1d = put(p.y2_1d, p.n1d); t.lut1d = puti(p.lut1d, p.nlut1d); }
-   if (p.nrot) { t.rgrid = put(p.rgrid, p.nrot); t.rdens = put(p.rdens, p.nrot); t.rdens2 = put(p.rdens2, p.nrot); t.lutrot = puti(p.lutrot, p.nlutrot); }
+   // copies the packed 1-D spline records and their bucket table into shared memory; `cursor` walks the dynamic
+   // smem block.  The linear-rotor density spline is touched four times per rot step and stays in global/L1.
+   t.g1d = p.g1d; t.v1d = p.v1d; t.y2_1d = p.y2_1d; t.lut1d = p.lut1d; t.rec1d = p.rec1d;
+   t.rgrid = p.rgrid; t.rdens = p.rdens; t.rdens2 = p.rdens2; t.lutrot = p.lutrot; t.recrot = p.recrot;
+   t.rgi2d = p.rgi2d; t.cgi2d = p.cgi2d;
+   if (p.rs2d) {
+      double2 *d2 = reinterpret_cast<double2 *>(cursor);
+      for (int i = threadIdx.x; i < p.rs2d; i += blockDim.x) d2[i] = p.rgi2d[i];
+      for (int i = threadIdx.x; i < p.cs2d; i += blockDim.x) d2[p.rs2d + i] = p.cgi2d[i];
+      t.rgi2d = d2; t.cgi2d = d2 + p.rs2d;
+      cursor += 2 * (size_t)(p.rs2d + p.cs2d);
+   }
+   if (p.n1d) {
+      const int nd = (p.n1d - 1) * (int)(sizeof(SplineRec) / sizeof(double));
+      const double *src = reinterpret_cast<const double *>(p.rec1d);
+      for (int i = threadIdx.x; i < nd; i += blockDim.x) cursor[i] = src[i];
+      t.rec1d = reinterpret_cast<const SplineRec *>(cursor);
+      cursor += (nd + 1) & ~1;
+      int *li = reinterpret_cast<int *>(cursor);
+      for (int i = threadIdx.x; i < p.nlut1d; i += blockDim.x) li[i] = p.lut1d[i];
+      t.lut1d = li;
+      cursor += ((p.nlut1d + 1) / 2 + 1) & ~1;
+   }
    __syncthreads();
 }
 
-__global__ void __launch_bounds__(512, 1)
+#ifndef PIMC_MAX_THREADS
+#define PIMC_MAX_THREADS 512
+#endif
+template <int KIND>
+__global__ void __launch_bounds__(PIMC_MAX_THREADS, 1)
 pimc_steps_kernel(const __grid_constant__ Params p, long t0, long nsteps, int *err)
 {
    extern __shared__ double smem[];
@@ -437,19 +644,27 @@ pimc_steps_kernel(const __grid_constant__ Params p, long t0, long nsteps, int *e
    x.team_lane0 = (x.tid & 31) & ~(x.T - 1);
    x.team_id = x.gthread / x.T;
    x.nteams_chain = x.nthreads_chain / x.T;
+   x.G = p.rot_group;
+   x.gl = x.tid & (x.G - 1);
+   x.grp = x.tid / x.G;
+   x.ngrp = blockDim.x / x.G;
    double *cursor = smem;
    x.red = cursor; cursor += 40;
    stage_tables(p, x.t, cursor);
-   x.team_buf = cursor + (size_t)(x.tid / x.T) * ((p.seg_max + 1) * 3);
+   x.team_buf = cursor + (size_t)(x.tid / x.T) * ((p.seg_max + 1) * 6);
+   if (!p.segbuf_global) cursor += (size_t)(blockDim.x / x.T) * ((p.seg_max + 1) * 6);
+   x.part = cursor + 2 * (size_t)((x.tid >> 5) - (x.gl >> 5));      // first warp of this thread's rot group
+   cursor += 2 * (size_t)(blockDim.x >> 5);
+   x.slot = reinterpret_cast<RotSlot *>(cursor) + x.grp;
 
    for (long s = 0; s < nsteps; s++) {
       const long t = t0 + s;
       const int time = (int)(t % p.P);
       for (int type = 0; type < p.ntypes; type++) {
-         if (time == 0) molecular_sweep(p, x, type);
+         if (time == 0) molecular_sweep<KIND>(p, x, type);
          const int seg = 1 << p.levels[type], nseg = p.P / seg;
-         if (time % nseg == 0) bisection_sweep(p, x, type, (time / nseg) % p.P);
-         if (type == p.imtype && p.Q > 0) rot_sweep(p, x, type, err);
+         if (time % nseg == 0) bisection_sweep<KIND>(p, x, type, (time / nseg) % p.P);
+         if (KIND != 0 && type == p.imtype && p.Q > 0) rot_sweep<KIND>(p, x, type, err);
       }
    }
 }

@@ -50,6 +50,7 @@ struct Context {
    long nacc = 0;
    int *d_err = nullptr;
    bool seeded = false;
+   int kind = 0;                    // rotor kind the move kernel is specialised on
    std::vector<int> h_pindex;       // [c][N]
    double *stage = nullptr;         // pinned host staging: [c][pos | ang | cosn] in the device layout
    size_t stage_chain = 0;          // doubles per chain in `stage`
@@ -102,7 +103,10 @@ void spline_setup(const std::vector<double> &x, const std::vector<double> &y, st
 void build_lut(const std::vector<double> &x, std::vector<int> &lut, double &scale)
 {
    int n = (int)x.size();
-   int nl = 4 * n;
+#ifndef PIMC_LUT_FACTOR
+#define PIMC_LUT_FACTOR 4
+#endif
+   int nl = PIMC_LUT_FACTOR * n;
    lut.assign(nl, 0);
    scale = (double)nl / (x[n - 1] - x[0]);
    int k = 0;
@@ -148,6 +152,20 @@ void stream_state(const u64 seed[6], u64 s, u64 st[6])
    matvec(B2, seed + 3, st + 3, M2);
 }
 
+// packed per-interval records: 1/h and y'' h^2/6 folded in (the device evaluates a*ylo + b*yhi + (a^3-a)clo + (b^3-b)chi)
+std::vector<SplineRec> make_records(const std::vector<double> &x, const std::vector<double> &y, const std::vector<double> &y2)
+{
+   int n = (int)x.size();
+   std::vector<SplineRec> r(n - 1);
+   for (int k = 0; k < n - 1; k++) {
+      double h = x[k + 1] - x[k];
+      r[k].xlo = x[k]; r[k].xhi = x[k + 1]; r[k].inv_h = 1.0 / h;
+      r[k].ylo = y[k]; r[k].yhi = y[k + 1];
+      r[k].clo = y2[k] * (h * h) / 6.; r[k].chi = y2[k + 1] * (h * h) / 6.;
+   }
+   return r;
+}
+
 int pow2floor(int v) { int r = 1; while (2 * r <= v) r *= 2; return r; }
 int pow2ceil(int v) { int r = 1; while (r < v) r *= 2; return r; }
 
@@ -156,10 +174,13 @@ size_t smem_bytes(const Params &p, int threads)
    size_t d = 40;
    auto pad = [](int n) { return (size_t)((n + 1) & ~1); };
    auto padi = [](int n) { return (size_t)(((n + 1) / 2 + 1) & ~1); };
-   if (p.n1d) d += 3 * pad(p.n1d) + padi(p.nlut1d);
-   if (p.nrot) d += 3 * pad(p.nrot) + padi(p.nlutrot);
-   d += (size_t)(threads / p.team) * ((p.seg_max + 1) * 3);
-   return d * sizeof(double);
+   if (p.n1d) d += pad((p.n1d - 1) * (int)(sizeof(SplineRec) / sizeof(double))) + padi(p.nlut1d);
+   if (p.rs2d) d += 2 * (size_t)(p.rs2d + p.cs2d);
+   if (!p.segbuf_global) d += (size_t)(threads / p.team) * ((p.seg_max + 1) * 6);
+   d += 2 * (size_t)(threads / 32);
+   size_t bytes = d * sizeof(double);
+   if (p.rot_group > 1) bytes += (size_t)(threads / p.rot_group) * sizeof(RotSlot);
+   return bytes;
 }
 
 void est_shapes(dim3 &g_rcf, dim3 &b_rcf)
@@ -282,12 +303,34 @@ int pimcgpu_init(const pimcgpu_system *sys, const pimcgpu_tables *tab)
       std::vector<int> lut;
       build_lut(g, lut, p.lut1d_scale);
       p.n1d = n; p.nlut1d = (int)lut.size();
-      if (dupload(&p.g1d, g.data(), n) || dupload(&p.v1d, v.data(), n) || dupload(&p.y2_1d, y2.data(), n) || dupload(&p.lut1d, lut.data(), lut.size())) return 1;
+      std::vector<SplineRec> rec = make_records(g, v, y2);
+      if (dupload(&p.g1d, g.data(), n) || dupload(&p.v1d, v.data(), n) || dupload(&p.y2_1d, y2.data(), n) || dupload(&p.lut1d, lut.data(), lut.size()) ||
+          dupload(&p.rec1d, rec.data(), rec.size())) return 1;
    }
    if (need2d) {
       if (!tab->pot2d || !tab->rgrid2d || !tab->cgrid2d) return fail("pimcgpu_init: the 2-D atom-rotor potential table is required");
       p.rs2d = tab->rsize2d; p.cs2d = tab->csize2d; p.dr2d = tab->dr2d; p.dc2d = tab->dc2d;
-      if (dupload(&p.rg2d, tab->rgrid2d, p.rs2d) || dupload(&p.cg2d, tab->cgrid2d, p.cs2d) || dupload(&p.v2d, tab->pot2d, (size_t)p.rs2d * p.cs2d)) return 1;
+      p.inv_dr2d = 1.0 / p.dr2d; p.inv_dc2d = 1.0 / p.dc2d;
+      std::vector<double> ir(p.rs2d, 0.0), ic(p.cs2d, 0.0);
+      for (int i = 0; i + 1 < p.rs2d; i++) ir[i] = 1.0 / (tab->rgrid2d[i + 1] - tab->rgrid2d[i]);
+      for (int i = 0; i + 1 < p.cs2d; i++) ic[i] = 1.0 / (tab->cgrid2d[i + 1] - tab->cgrid2d[i]);
+      if (dupload(&p.rg2d, tab->rgrid2d, p.rs2d) || dupload(&p.cg2d, tab->cgrid2d, p.cs2d) || dupload(&p.v2d, tab->pot2d, (size_t)p.rs2d * p.cs2d) ||
+          dupload(&p.irg2d, ir.data(), ir.size()) || dupload(&p.icg2d, ic.data(), ic.size())) return 1;
+      // cell-packed copy: the four corners of every bilinear cell contiguous (32-byte aligned) for one 256-bit gather
+      {
+         const int rs = p.rs2d, cs = p.cs2d;
+         std::vector<double> cell((size_t)(rs - 1) * (cs - 1) * 4);
+         for (int i = 0; i < rs - 1; i++)
+            for (int j = 0; j < cs - 1; j++) {
+               double *q = &cell[((size_t)i * (cs - 1) + j) * 4];
+               q[0] = tab->pot2d[(size_t)i * cs + j]; q[1] = tab->pot2d[(size_t)(i + 1) * cs + j];
+               q[2] = tab->pot2d[(size_t)(i + 1) * cs + j + 1]; q[3] = tab->pot2d[(size_t)i * cs + j + 1];
+            }
+         std::vector<double2> rgi(rs), cgi(cs);
+         for (int i = 0; i < rs; i++) rgi[i] = make_double2(tab->rgrid2d[i], ir[i]);
+         for (int i = 0; i < cs; i++) cgi[i] = make_double2(tab->cgrid2d[i], ic[i]);
+         if (dupload(&p.cell2d, cell.data(), cell.size()) || dupload(&p.rgi2d, rgi.data(), rgi.size()) || dupload(&p.cgi2d, cgi.data(), cgi.size())) return 1;
+      }
    }
    if (need3d) {
       if (!tab->vtable) return fail("pimcgpu_init: the 3-D atom-top potential table is required");
@@ -309,6 +352,10 @@ int pimcgpu_init(const pimcgpu_system *sys, const pimcgpu_tables *tab)
          std::vector<double> y(cols[k], cols[k] + n);
          spline_setup(g, y, y2);
          if (dupload(dst[k], y.data(), n) || dupload(dst2[k], y2.data(), n)) return 1;
+         if (k == 0) {
+            std::vector<SplineRec> rec = make_records(g, y, y2);
+            if (dupload(&p.recrot, rec.data(), rec.size())) return 1;
+         }
       }
       std::vector<int> lut;
       build_lut(g, lut, p.lutrot_scale);
@@ -325,6 +372,7 @@ int pimcgpu_init(const pimcgpu_system *sys, const pimcgpu_tables *tab)
    const size_t C = p.nchains;
    if (dalloc(&p.pos, C * p.P * 3 * p.Npad) || dalloc(&p.ang, C * std::max(1, p.Q) * 3 * p.NMpad) || dalloc(&p.cosn, C * std::max(1, p.Q) * 3 * p.NMpad) ||
        dalloc(&p.pindex, C * p.N) || dalloc(&p.cyc_start, C * (p.N + 1)) || dalloc(&p.cyc_atoms, C * p.N) || dalloc(&p.ncyc, C * MAXT) ||
+       dalloc(&p.vold, C * std::max(1, p.Q) * p.NMpad) || dalloc(&p.vepoch, C * std::max(1, p.Q) * p.NMpad) || dalloc(&p.pos_epoch, C) ||
        dalloc(&p.rng, C * p.S * 6) || dalloc(&p.counters, C * MAXT * 3 * 2) || dalloc(&p.scratch, C * 64) || dalloc(&G.d_err, 1)) return 1;
    G.h_pindex.assign(C * p.N, 0);
    G.stage_chain = (size_t)p.P * 3 * p.Npad + 2 * (size_t)std::max(1, p.Q) * 3 * p.NMpad;
@@ -340,19 +388,43 @@ int pimcgpu_init(const pimcgpu_system *sys, const pimcgpu_tables *tab)
    int units = std::max(p.Q / 2, p.P / seg_min);           // widest stage: rot slices of one parity / segments of one atom
    long want = (long)units * team;
    int threads = sys->threads_per_cta, cpc = sys->ctas_per_chain;
-   if (cpc <= 0) cpc = (int)std::min<long>(16, std::max<long>(1, (want + 511) / 512));
+   if (cpc <= 0) {
+      // enough CTAs for one thread per partner term of the widest rotational phase (or per segment lane), but never
+      // more clusters x CTAs than the 148 SMs can hold at once, and at most 16 CTAs per cluster
+      long rot_work = (long)(p.Q / 2) * p.R * std::max(1, p.N - 1);
+      long useful = (std::max(want, rot_work) + 511) / 512;
+      long fit = std::max(1, 148 / std::max(1, p.nchains));
+      // clusters of 16 are allowed by the hardware but only ~7 of them fit on a B200 at once (measured with
+      // cudaOccupancyMaxActiveClusters), so the automatic choice stops at the portable size 8
+      cpc = (int)std::max<long>(1, std::min<long>(8, std::min(useful, fit)));
+      while (cpc & (cpc - 1)) cpc &= cpc - 1;                 // power of two
+   }
    if (threads <= 0) {
       long per = (want + cpc - 1) / cpc;
       threads = (int)std::min<long>(512, std::max<long>(64, ((per + 31) / 32) * 32));
    }
-   if (threads % 32 || threads > 512 || threads < 32) return fail("pimcgpu_init: threads_per_cta must be a multiple of 32 in [32,512]");
+   if (threads % 32 || threads > PIMC_MAX_THREADS || threads < 32) return fail("pimcgpu_init: threads_per_cta must be a multiple of 32 in [32,%d]", PIMC_MAX_THREADS);
    if (cpc > 16) return fail("pimcgpu_init: ctas_per_chain must be <= 16");
    p.team = team; p.cpc = cpc;
+   // rot group: the threads of a CTA are split evenly over the slices it owns in one parity phase
+   {
+      int count = std::max(1, (p.Q + 1) / 2);
+      int per_cta = (count + cpc - 1) / cpc;
+      int rg = pow2floor(std::max(1, threads / std::max(1, std::min(per_cta, threads))));
+      long work = (long)p.R * std::max(1, p.N - 1);           // partner terms of one rot step
+      while (rg > 1 && rg > 2 * work) rg >>= 1;               // no point in more threads than terms
+      p.rot_group = std::min(rg, threads);
+   }
    G.threads = threads;
+   p.nseg_max = p.P / seg_min;
+   p.segbuf_global = ((size_t)(threads / team) * ((seg_max + 1) * 6) * sizeof(double) > 64 * 1024) ? 1 : 0;
+   if (p.segbuf_global && dalloc(&p.segbuf, C * p.nseg_max * ((seg_max + 1) * 6))) return 1;
    G.smem = smem_bytes(p, threads);
    if (G.smem > 227 * 1024) return fail("pimcgpu_init: %zu bytes of shared memory per CTA exceed the 227 KB limit", G.smem);
-   CK(cudaFuncSetAttribute(pimc_steps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
-   if (cpc > 8) CK(cudaFuncSetAttribute(pimc_steps_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+   G.kind = p.imtype >= 0 && p.Q > 0 ? p.molecule[p.imtype] : (p.imtype >= 0 ? p.molecule[p.imtype] : 0);
+   const void *kfun = G.kind == 2 ? (const void *)pimc_steps_kernel<2> : G.kind == 1 ? (const void *)pimc_steps_kernel<1> : (const void *)pimc_steps_kernel<0>;
+   CK(cudaFuncSetAttribute(kfun, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
+   if (cpc > 8) CK(cudaFuncSetAttribute(kfun, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
    // ---- estimator buffers / accumulator layout ----
    EstBuffers &e = G.e;
    memset(&e, 0, sizeof e);
@@ -429,6 +501,7 @@ int pimcgpu_upload_state(int chain, const double *coords, const double *angles, 
       CK(cudaMemcpyAsync(p.cyc_atoms + (size_t)c * p.N, catoms.data(), p.N * sizeof(int), cudaMemcpyHostToDevice, G.stream));
       CK(cudaMemcpyAsync(p.ncyc + (size_t)c * MAXT, ncyc.data(), MAXT * sizeof(int), cudaMemcpyHostToDevice, G.stream));
       std::copy(gp.begin(), gp.end(), G.h_pindex.begin() + (size_t)c * p.N);
+      CK(cudaMemsetAsync(p.vepoch + (size_t)c * std::max(1, p.Q) * p.NMpad, 0xff, (size_t)std::max(1, p.Q) * p.NMpad * sizeof(int), G.stream));
    }
    CK(cudaStreamSynchronize(G.stream));
    return 0;
@@ -508,7 +581,9 @@ int pimcgpu_steps(long nsteps)
    attr[0].id = cudaLaunchAttributeClusterDimension;
    attr[0].val.clusterDim.x = G.p.cpc; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
    cfg.attrs = attr; cfg.numAttrs = 1;
-   CK(cudaLaunchKernelEx(&cfg, pimc_steps_kernel, G.p, G.step, nsteps, G.d_err));
+   if (G.kind == 2) CK(cudaLaunchKernelEx(&cfg, pimc_steps_kernel<2>, G.p, G.step, nsteps, G.d_err));
+   else if (G.kind == 1) CK(cudaLaunchKernelEx(&cfg, pimc_steps_kernel<1>, G.p, G.step, nsteps, G.d_err));
+   else CK(cudaLaunchKernelEx(&cfg, pimc_steps_kernel<0>, G.p, G.step, nsteps, G.d_err));
    G.step += nsteps;
    return 0;
 }
@@ -525,6 +600,23 @@ int pimcgpu_sync(void)
 }
 
 long pimcgpu_step_counter(void) { return G.step; }
+
+int pimcgpu_geometry(int *out8)
+{
+   if (!G.live) return fail("pimcgpu_geometry: not initialised");
+   out8[0] = G.p.cpc; out8[1] = G.threads; out8[2] = G.p.team; out8[3] = G.p.rot_group; out8[4] = (int)G.smem; out8[5] = G.kind;
+   cudaLaunchConfig_t cfg = {};
+   cfg.gridDim = dim3(G.p.nchains * G.p.cpc); cfg.blockDim = dim3(G.threads); cfg.dynamicSmemBytes = G.smem;
+   cudaLaunchAttribute attr[1];
+   attr[0].id = cudaLaunchAttributeClusterDimension;
+   attr[0].val.clusterDim.x = G.p.cpc; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+   cfg.attrs = attr; cfg.numAttrs = 1;
+   int nclusters = -1;
+   const void *kfun = G.kind == 2 ? (const void *)pimc_steps_kernel<2> : G.kind == 1 ? (const void *)pimc_steps_kernel<1> : (const void *)pimc_steps_kernel<0>;
+   if (cudaOccupancyMaxActiveClusters(&nclusters, kfun, &cfg) != cudaSuccess) { nclusters = -1; cudaGetLastError(); }
+   out8[6] = nclusters; out8[7] = G.p.nchains;
+   return 0;
+}
 void *pimcgpu_stream(void) { return (void *)G.stream; }
 
 int pimcgpu_measure(void)
@@ -712,7 +804,7 @@ int pimcgpu_host_stream_state(const unsigned long seed6[6], long stream, unsigne
    for (int i = 0; i < 6; i++) state6[i] = st[i];
    return 0;
 }
-int pimcgpu_host_lut(int n, const double *x, int *lut, double *scale)
+int pimcgpu_host_lut(int n, const double *x, int *lut /* [4n] */, double *scale)
 {
    std::vector<double> g(x, x + n);
    std::vector<int> l;
@@ -720,6 +812,20 @@ int pimcgpu_host_lut(int n, const double *x, int *lut, double *scale)
    memcpy(lut, l.data(), l.size() * sizeof(int));
    return (int)l.size();
 }
+
+#ifdef PIMC_TIMELINE
+int pimcgpu_timeline(long long *out, int n)
+{
+   int nm = 0;
+   cudaDeviceSynchronize();
+   cudaMemcpyFromSymbol(&nm, g_nmarks, sizeof nm);
+   if (nm > n) nm = n;
+   cudaMemcpyFromSymbol(out, g_marks, nm * sizeof(long long));
+   int zero = 0;
+   cudaMemcpyToSymbol(g_nmarks, &zero, sizeof zero);
+   return nm;
+}
+#endif
 
 int pimcgpu_fp64_peak(double *tflops)
 {

@@ -12,7 +12,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(CSRC, "libpimcgpu.so")
+LIB = os.environ.get("PIMCGPU_LIB", os.path.join(CSRC, "libpimcgpu.so"))   # override only for kernel-variant experiments
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
 
 c_dp = C.POINTER(C.c_double)
@@ -20,7 +20,7 @@ c_ip = C.POINTER(C.c_int)
 
 EXPORTS = [
     "pimcgpu_init", "pimcgpu_finalize", "pimcgpu_last_error", "pimcgpu_upload_state", "pimcgpu_download_state",
-    "pimcgpu_seed", "pimcgpu_steps", "pimcgpu_sync", "pimcgpu_step_counter", "pimcgpu_measure", "pimcgpu_accum_layout",
+    "pimcgpu_seed", "pimcgpu_steps", "pimcgpu_sync", "pimcgpu_step_counter", "pimcgpu_geometry", "pimcgpu_measure", "pimcgpu_accum_layout",
     "pimcgpu_accum_device_ptr", "pimcgpu_accum_download", "pimcgpu_accum_reset", "pimcgpu_block_scalars",
     "pimcgpu_counters", "pimcgpu_stream", "pimcgpu_chain_energies", "pimcgpu_chain_rcf", "pimcgpu_eval_spot1d",
     "pimcgpu_eval_lpot2d", "pimcgpu_eval_srotdens", "pimcgpu_eval_rotden", "pimcgpu_eval_vcord", "pimcgpu_eval_caleng",
@@ -192,6 +192,12 @@ class PimcGpu:
 
     def sync(self):
         _ck(self.L.pimcgpu_sync())
+
+    def geometry(self):
+        g = (C.c_int * 8)()
+        _ck(self.L.pimcgpu_geometry(g))
+        k = ("ctas_per_chain", "threads_per_cta", "team", "rot_group", "smem_bytes", "kind", "max_active_clusters", "nchains")
+        return dict(zip(k, list(g)))
 
     def measure(self):
         _ck(self.L.pimcgpu_measure())

@@ -910,6 +910,13 @@ void sched_bisect(orc_t *o, int type, int atom, int s0)
       nx[seg * 3 + id] = o->coords[id][P * gat(seg) + sl(seg)];
    }
    double bnorm = 1.0 / (o->lambda[type] * o->tau);
+   // unit normals of all interior slices up front, six uniforms per slice from the slice's own stream
+   std::vector<double> xi((seg + 1) * 3, 0.0);
+   for (int t = 1; t < seg; t++)
+      for (int id = 0; id < 3; id++) {
+         double r1 = draw(o, sl(t)), r2 = draw(o, sl(t));
+         xi[t * 3 + id] = sqrt(-log(r1)) * cos(2.0 * M_PI * r2);
+      }
    double S = 0.0;
    bool acc = true;
    for (int level = 0; level < L; level++) {
@@ -920,8 +927,7 @@ void sched_bisect(orc_t *o, int type, int atom, int s0)
          int p = sl(t1), g = gat(t1);
          double po[3];
          for (int id = 0; id < 3; id++) {
-            double r1 = draw(o, p), r2 = draw(o, p);
-            nx[t1 * 3 + id] = 0.5 * (nx[(t1 - half) * 3 + id] + nx[(t1 + half) * 3 + id]) + gauss_u(bkin, r1, r2);
+            nx[t1 * 3 + id] = 0.5 * (nx[(t1 - half) * 3 + id] + nx[(t1 + half) * 3 + id]) + xi[t1 * 3 + id] / sqrt(bkin);
             po[id] = o->coords[id][P * g + p];
          }
          D += PotEnergy_it(o, g, &nx[t1 * 3], p) - PotEnergy_it(o, g, po, p);

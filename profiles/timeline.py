@@ -1,0 +1,25 @@
+"""clock64 timeline of the rot phases of chain 0 / CTA 0 / thread 0 (library built with -DPIMC_TIMELINE)."""
+import sys, os, ctypes as C
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge
+import numpy as np
+pkg = ge.load_package()
+geo = [int(x) for x in sys.argv[1:4]] + [0] * 3
+cfg = pkg.configs.make_config("C5")
+G = pkg.gpu.PimcGpu(cfg, nchains=8, ctas_per_chain=geo[0], threads_per_cta=geo[1], team=geo[2])
+G.seed((12345,) * 6)
+G.steps(1024 + 5)
+buf = (C.c_longlong * 4096)()
+G.L.pimcgpu_timeline(buf, 4096)
+G.steps(6)
+n = G.L.pimcgpu_timeline(buf, 4096)
+m = np.array(buf[:n], dtype=np.int64)
+ids, t = m >> 48, m & 0xffffffffffff
+names = {1: "step start", 2: "leader proposal done", 3: "after sync#1", 4: "densities done (thread 0)", 5: "items done", 6: "after reduce sync#2",
+         7: "leader decision done", 8: "after sync#3", 9: "phase end", 10: "after chain barrier"}
+prev = t[0]
+for i in range(min(n, 60)):
+    print(f"{int(ids[i]):3d} {names.get(int(ids[i]), ''):28s} +{int(t[i]-prev):7d} cycles")
+    prev = t[i]
+G.close()
