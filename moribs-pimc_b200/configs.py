@@ -309,7 +309,7 @@ def _deck(name: str) -> str:
 
 
 def make_config(name: str, P: Optional[int] = None, Q: Optional[int] = None, nsolv: Optional[int] = None,
-                seed: int = 1, big_tables: bool = True) -> Config:
+                seed: int = 1, big_tables: bool = True, temperature: Optional[float] = None) -> Config:
     """Build C1..C5.  P/Q/nsolv override the deck for reduced-size parity cases."""
     tables: Dict[str, object] = {}
     perm = None
@@ -374,6 +374,16 @@ def make_config(name: str, P: Optional[int] = None, Q: Optional[int] = None, nso
         if big_tables:
             tables["rot3d"] = synth_rot3d(s.temperature, s.Q, *ROT_CONSTANTS["H2O"])
         coords, angles = cluster_config(s, seed)
+    elif name == "CO2":
+        # examples/CO2_100K_4_4: one free linear rotor (zero potential), the only deck of the reference whose files are all in the tree
+        d = _deck("CO2_100K_4_4")
+        s = parse_qmc_input(os.path.join(d, "qmc.input"))
+        s.rotden_type = 0
+        rot = load_columns(os.path.join(d, "CO2_T100t4.rot"), 4)
+        tables["rotlin"] = tuple(np.ascontiguousarray(rot[i]) for i in range(4))
+        coords, angles = cluster_config(s, seed)
     else:
         raise ValueError(name)
+    if temperature is not None:
+        s.temperature = temperature
     return Config(name, s, tables, coords, angles, perm, d)

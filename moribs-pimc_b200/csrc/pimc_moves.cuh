@@ -404,6 +404,7 @@ __device__ __forceinline__ double rot_potential(const Params &p, Ctx &x, int g, 
                fast_r_invr(dr2, rr[u], invr);
                cs[u] = -dot * invr;
             }
+            if (!(ok[0] | ok[1] | ok[2] | ok[3])) continue;       // nothing to evaluate (e.g. a lone rotor: no table loaded)
             double e[4];
             lpot2d_x4(p, x.t, rr, cs, e);
             #pragma unroll

@@ -432,7 +432,8 @@ int pimcgpu_init(const pimcgpu_system *sys, const pimcgpu_tables *tab)
    for (int a0 = 0; a0 < p.N - 1; a0++)
       for (int a1 = a0 + 1; a1 < p.N; a1++) { pairs.push_back(a0); pairs.push_back(a1); }
    e.npairs = (int)pairs.size() / 2;
-   if (dupload(&e.pairs, pairs.data(), std::max<size_t>(pairs.size(), 2))) return 1;
+   if (pairs.empty()) { pairs.push_back(0); pairs.push_back(0); }          // a lone particle has no pairs
+   if (dupload(&e.pairs, pairs.data(), pairs.size())) return 1;
    e.has_gr3d = (need3d || needsph) ? 1 : 0;
    e.off_gr1d = 32; e.off_gr2d = e.off_gr1d + BINSR; e.off_rcf = e.off_gr2d + (long)BINSR * BINST;
    e.off_relbins = e.off_rcf + std::max(1, p.Q); e.off_gr3d = e.off_relbins + BINST + 2 * BINSC;

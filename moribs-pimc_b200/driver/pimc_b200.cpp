@@ -1,0 +1,457 @@
+// pimc_b200 -- C++ host driver of the B200 PIMC hot path: a drop-in for the reference's `pimc` binary on the
+// sampling path.  It reads the same `qmc.input` from the current directory (keywords and semantics of
+// mc_input.cc:18-57,115-343), the same table files (1-D/2-D/3-D potentials, <type>_T<T>t<Q>.rot or
+// .rho/.eng/.esq; formats of mc_poten.cc:254-546 and README.md:78-149), `xyz.init` (initconf.f) when
+// READMCCOORDS is set, runs the block loop of mc_main.cc:340-484 with the moves and estimator sums on the GPU
+// through include/pimcgpu.h, and writes <prefix>.eng, <prefix>_sum.eng, <prefix>NNN.rcf, <prefix>_sum.rcf,
+// <prefix>_sum.gra, <prefix>.xyz and the yw001.stat/.conf/.tabl checkpoints in the reference's formats
+// (mc_main.cc:764-836, mc_estim.cc:1141-1191,1288-1326, mc_input.cc:517-794).
+//
+// Independent Markov chains: `--chains C` chains per GPU (default 1); with `--ranks N --rank r` (or the
+// RANK/WORLD_SIZE environment of a launcher) every rank drives one GPU, the block accumulators are all-reduced
+// with NCCL over NVLink before rank 0 writes the block files.
+//
+// Not done on the device (and rejected loudly): WORM moves, RotDenType=1.  yw001.rand (SPRNG state) has no
+// counterpart: the MRG32k3a package seed and step counter are written to yw001.mrg instead.
+#include "../../include/pimcgpu.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <sstream>
+#include <string>
+#include <vector>
+#include <chrono>
+#include <thread>
+#include <algorithm>
+#include <array>
+#include <sys/stat.h>
+
+#ifdef PIMC_WITH_NCCL
+#include <nccl.h>
+#include <cuda_runtime.h>
+#endif
+
+using namespace std;
+
+static const int IO_WIDTH = 14, IO_WIDTH_BLOCK = 4, IO_PRECISION = 6;
+static const char BLANK[] = "   ";
+
+[[noreturn]] static void die(const string &proc, const string &msg)
+{
+   // nrerror, mc_utils.cc:99-108: message on stdout, exit status 1
+   cout << endl << "run-time error..." << endl << proc << ":  " << msg << endl << "...now exiting to system..." << endl << endl;
+   exit(1);
+}
+static void ck(int rc, const char *what)
+{
+   if (rc) die(what, pimcgpu_last_error());
+}
+
+struct Species { string name, fpot; int numb, molecule, stat, levels; double mcstep, rtstep, mass; };
+
+struct Deck {
+   vector<Species> types;
+   string outdir = "./", prefix = "pimc";
+   int P = 0, Q = 0, ispher = 0, minimage = 0, rotden_type = 0, read_coords = 0, worm = 0;
+   double temperature = 0, density = 0.02;
+   long passes = 1, blocks = 1, eq_blocks = 0;
+   int skip_ratio = 100000, skip_total = 10000, skip_averg = 1;
+   int N() const { int n = 0; for (auto &t : types) n += t.numb; return n; }
+};
+
+static double species_mass(const string &s)
+{
+   // MCInitParams, mc_setup.cc:244-319 with the masses of mc_const.h:50-56
+   const double H1 = 1.0078, H2 = 2.015650642, HE4 = 4.0026032497, C12 = 12.0, N14 = 14.003, O16 = 15.994915, S32 = 31.972;
+   if (s == "He4") return HE4;
+   if (s == "H2") return H2;
+   if (s == "OCS") return O16 + C12 + S32;
+   if (s == "N2O") return 2.0 * N14 + O16;
+   if (s == "CO2") return C12 + 2.0 * O16;
+   if (s == "CO") return C12 + O16;
+   if (s == "HCN") return H1 + C12 + N14;
+   if (s == "HCCCN") return H1 + 3.0 * C12 + N14;
+   if (s == "H2O") return 2.0 * H1 + O16;
+   if (s == "SO2") return 2.0 * O16 + S32;
+   if (s == "HCOOCH3") return 4.0 * H1 + 2.0 * O16 + 2.0 * C12;
+   die("MCInitParams", "Unknown atom/molecule type");
+}
+
+static Deck read_deck(const char *path)
+{
+   ifstream inf(path);
+   if (!inf.good()) die("IOReadParams", string("Can't open input file  [") + path + "]");
+   Deck d;
+   string key, rot_type;
+   double rot_step = 0;
+   bool impurity = false;
+   while (inf >> key) {
+      if (key == "OUTPUTDIR") inf >> d.outdir;
+      else if (key == "FILENAMEPREFIX") inf >> d.prefix;
+      else if (key == "TEMPERATURE") inf >> d.temperature;
+      else if (key == "DENSITY") inf >> d.density;
+      else if (key == "ATOM" || key == "MOLECULE" || key == "NONLINEAR") {
+         Species s;
+         string sstat, smod;
+         inf >> s.name >> s.numb >> sstat >> s.mcstep >> s.levels >> s.fpot >> smod;
+         if (s.numb < 0) { d.ispher = 1; s.numb = -s.numb; }
+         if (sstat == "BOSE") s.stat = 1; else if (sstat == "BOLTZMANN") s.stat = 0; else die("IOReadParams", "Unknown statistics");
+         if (smod != "PRIMITIVE" && smod != "EFFECTIVE") die("IOReadParams", "Unknown model of interaction");
+         if (smod == "EFFECTIVE") s.fpot += ".eff"; else s.fpot += ".pot";
+         s.molecule = key == "ATOM" ? 0 : (key == "MOLECULE" ? 1 : 2);
+         if (s.molecule == 0 && impurity) die("IOReadParams", "Molecules should follow atoms in input file");
+         if (s.molecule) impurity = true;
+         s.rtstep = 0;
+         if (s.numb > 0) { s.mass = species_mass(s.name); d.types.push_back(s); }
+      }
+      else if (key == "NUMBEROFSLICES") inf >> d.P;
+      else if (key == "NUMBEROFPASSES") inf >> d.passes;
+      else if (key == "NUMBEROFBLOCKS") inf >> d.blocks >> d.eq_blocks;
+      else if (key == "ROTATION") inf >> rot_type >> rot_step >> d.Q;
+      else if (key == "ROTDENSI") inf >> d.rotden_type;
+      else if (key == "WORM") d.worm = 1;
+      else if (key == "MINIMAGE") d.minimage = 1;
+      else if (key == "READMCCOORDS") d.read_coords = 1;
+      else if (key == "MCSKIP_RATIO") inf >> d.skip_ratio;
+      else if (key == "MCSKIP_TOTAL") inf >> d.skip_total;
+      else if (key == "MCSKIP_AVERG") inf >> d.skip_averg;
+      string rest;
+      getline(inf, rest);                 // the rest of the line is a comment
+   }
+   if (d.Q) {
+      bool found = false;
+      for (auto &t : d.types) if (t.name == rot_type) { if (!t.molecule) die("IOReadParams", "Rotational degrees of freedom for molecules only"); t.rtstep = rot_step; found = true; }
+      if (!found) die("IOReadParams", "Can't find a particle type to sample rotational degrees of freedom");
+   }
+   if (d.types.empty() || d.types.size() > 2) die("IOReadParams", "No more then one atom/molecule type: densities and potential energy");
+   return d;
+}
+
+// read_datafile, mc_poten.cc:757-865: whitespace-separated columns, lines starting with '#' skipped
+static vector<vector<double>> read_columns(const string &path, int ncol)
+{
+   ifstream f(path);
+   if (!f.good()) die("read_datafile", "Can't open input file  [" + path + "]");
+   vector<vector<double>> c(ncol);
+   string line;
+   while (getline(f, line)) {
+      istringstream is(line);
+      string tok;
+      if (!(is >> tok) || tok == "#") continue;
+      c[0].push_back(strtod(tok.c_str(), nullptr));
+      for (int k = 1; k < ncol; k++) { is >> tok; c[k].push_back(strtod(tok.c_str(), nullptr)); }
+   }
+   return c;
+}
+// one number per token, fast path for the 23.6 M-line density-matrix files (init_rot3D, mc_poten.cc:462-499)
+static vector<double> read_numbers(const string &path, size_t n)
+{
+   FILE *f = fopen(path.c_str(), "rb");
+   if (!f) die("init_rot3D", "Can't open input file  [" + path + "]");
+   fseek(f, 0, SEEK_END);
+   long sz = ftell(f);
+   fseek(f, 0, SEEK_SET);
+   string buf(sz, '\0');
+   if (fread(&buf[0], 1, sz, f) != (size_t)sz) die("init_rot3D", "short read of " + path);
+   fclose(f);
+   vector<double> v;
+   v.reserve(n);
+   const char *p = buf.c_str(), *end = p + sz;
+   while (p < end && v.size() < n) {
+      char *q;
+      double x = strtod(p, &q);
+      if (q == p) { p++; continue; }
+      v.push_back(x);
+      p = q;
+   }
+   if (v.size() != n) die("init_rot3D", "wrong number of entries in " + path);
+   return v;
+}
+
+static string cxx_double(double x) { ostringstream o; o << x; return o.str(); }     // how init_rot3D spells the temperature
+
+struct Writer {
+   static void setout(ostream &o) { o << setprecision(IO_PRECISION) << setiosflags(ios::scientific); }
+};
+
+int main(int argc, char **argv)
+{
+   int chains = 1, rank = 0, ranks = 1;
+   unsigned long seed[6] = {12345, 12345, 12345, 12345, 12345, 12345};          // fixedseed(), omprng.cc:14-18
+   if (getenv("RANK")) rank = atoi(getenv("RANK"));
+   if (getenv("WORLD_SIZE")) ranks = atoi(getenv("WORLD_SIZE"));
+   for (int i = 1; i < argc; i++) {
+      string a = argv[i];
+      if (a == "--chains" && i + 1 < argc) chains = atoi(argv[++i]);
+      else if (a == "--rank" && i + 1 < argc) rank = atoi(argv[++i]);
+      else if (a == "--ranks" && i + 1 < argc) ranks = atoi(argv[++i]);
+      else if (a == "--seed" && i + 1 < argc) { unsigned long s = strtoul(argv[++i], nullptr, 10); for (int k = 0; k < 6; k++) seed[k] = s + k; }
+      else die("main", "usage: pimc_b200 [--chains C] [--ranks N --rank r] [--seed s]   (reads ./qmc.input)");
+   }
+   Deck d = read_deck("qmc.input");
+   if (d.worm) die("main", "WORM moves are not available on the device path yet (remove the WORM line to sample a fixed permutation)");
+   if (d.rotden_type != 0) die("main", "RotDenType=1 (rattle-and-shake propagator) is not available on the device path");
+   const int N = d.N(), P = d.P, Q = d.Q;
+   const size_t n = (size_t)N * P;
+
+   pimcgpu_system sys;
+   memset(&sys, 0, sizeof sys);
+   sys.ntypes = (int)d.types.size();
+   int imtype = -1, bstype = -1, first[3] = {0, 0, 0};
+   for (int t = 0; t < sys.ntypes; t++) {
+      const Species &s = d.types[t];
+      sys.type[t].numb = s.numb; sys.type[t].molecule = s.molecule; sys.type[t].stat = s.stat; sys.type[t].levels = s.levels;
+      sys.type[t].mass = s.mass; sys.type[t].mcstep = s.mcstep; sys.type[t].rtstep = s.rtstep;
+      first[t + 1] = first[t] + s.numb;
+      if (s.molecule) imtype = t;
+      if (s.stat == 1) bstype = t;
+   }
+   sys.P = P; sys.Q = Q; sys.temperature = d.temperature; sys.ispher = d.ispher; sys.minimage = d.minimage;
+   for (int k = 0; k < 3; k++) sys.box[k] = pow((double)N / d.density, 1.0 / 3.0);        // MCInit, mc_setup.cc:339,359-360
+   sys.nchains = chains; sys.chain_offset = (long)rank * chains; sys.device = rank;
+#ifdef PIMC_WITH_NCCL
+   { int nd = 1; cudaGetDeviceCount(&nd); sys.device = rank % std::max(1, nd); }
+#else
+   sys.device = 0;
+#endif
+
+   // ---- tables: InitPotentials / InitRotDensity, mc_poten.cc:93-164 ----
+   pimcgpu_tables tab;
+   memset(&tab, 0, sizeof tab);
+   vector<vector<double>> t1d, trot;
+   vector<double> rg2, cg2, v2, v3, rho, erot, esq;
+   for (int t = 0; t < sys.ntypes; t++) {
+      const Species &s = d.types[t];
+      if (s.molecule == 0) {
+         t1d = read_columns(s.fpot, 2);
+         tab.n1d = (int)t1d[0].size(); tab.grid1d = t1d[0].data(); tab.pot1d = t1d[1].data();
+      } else if (s.molecule == 1) {
+         ifstream f(s.fpot);
+         if (!f.good()) die("init_pot2D", "Can't open input file  [" + s.fpot + "]");
+         f >> tab.rsize2d >> tab.csize2d >> tab.dr2d >> tab.dc2d;
+         rg2.resize(tab.rsize2d); cg2.resize(tab.csize2d); v2.resize((size_t)tab.rsize2d * tab.csize2d);
+         for (auto &x : rg2) f >> x;
+         for (auto &x : cg2) f >> x;
+         for (auto &x : v2) f >> x;
+         tab.rgrid2d = rg2.data(); tab.cgrid2d = cg2.data(); tab.pot2d = v2.data();
+      } else if (sys.ntypes > 1) {
+         ifstream f(s.fpot);
+         if (!f.good()) die("init_pot3D", "Can't open input file  [" + s.fpot + "]");
+         f >> tab.rgrd >> tab.thgrd >> tab.chgrd >> tab.rvmin >> tab.rvmax;
+         v3.resize((size_t)tab.rgrd * tab.thgrd * tab.chgrd);
+         for (auto &x : v3) f >> x;
+         tab.vtable = v3.data();
+         cout << "Rgrd=" << tab.rgrd << " THgrd=" << tab.thgrd << " CHgrd=" << tab.chgrd << " Rvmin=" << tab.rvmin << " Rvmax=" << tab.rvmax << endl;
+      }
+   }
+   if (Q > 0 && imtype >= 0) {
+      const Species &s = d.types[imtype];
+      string base = s.name + "_T" + cxx_double(d.temperature) + "t" + to_string(Q);          // mc_poten.cc:443-458,518-524
+      if (s.molecule == 1) {
+         trot = read_columns(base + ".rot", 4);
+         tab.nrot = (int)trot[0].size(); tab.rotgrid = trot[0].data(); tab.rotdens = trot[1].data(); tab.rotderv = trot[2].data(); tab.rotesqr = trot[3].data();
+      } else {
+         cout << base << ".rho " << base << ".eng " << base << ".esq" << endl;
+         rho = read_numbers(base + ".rho", PIMCGPU_SIZE_ROTDEN);
+         erot = read_numbers(base + ".eng", PIMCGPU_SIZE_ROTDEN);
+         esq = read_numbers(base + ".esq", PIMCGPU_SIZE_ROTDEN);
+         tab.rho3d = rho.data(); tab.erot3d = erot.data(); tab.esq3d = esq.data();
+      }
+   }
+   ck(pimcgpu_init(&sys, &tab), "pimcgpu_init");
+
+   // ---- initial configuration ----
+   vector<double> coords(3 * n, 0.0), angles(3 * n, 0.0), cosine(3 * n, 0.0);
+   vector<int> pindex(N), rindex(N);
+   for (int a = 0; a < N; a++) pindex[a] = rindex[a] = a;
+   for (size_t i = 0; i < n; i++) angles[n + i] = 1.0;                                       // MCConfigInit, mc_setup.cc:471-487
+   if (d.read_coords) {
+      // initconf.f:1-27 + mc_main.cc:184-201
+      ifstream f("xyz.init");
+      if (!f.good()) die("initconf", "Can't open input file  [xyz.init]");
+      long ntot; f >> ntot;
+      int nb = bstype >= 0 ? d.types[bstype].numb : 0;
+      for (int i = 0; i < nb; i++) { f >> pindex[i]; rindex[pindex[i]] = i; }
+      string line; getline(f, line); getline(f, line);
+      for (size_t i = 0; i < n; i++) {
+         string label; f >> label;
+         for (int k = 0; k < 3; k++) f >> coords[k * n + i] >> angles[k * n + i];
+      }
+      if (!f) die("initconf", "short xyz.init");
+   } else {
+      // classical start: molecules in a row through the origin, atoms on the nearest sites of a simple cubic lattice
+      // (the reference's initLattice_config draws a different lattice; only the equilibrated ensemble matters)
+      vector<array<double, 4>> sites;
+      const double a0 = 3.8;
+      for (int i = -8; i <= 8; i++) for (int j = -8; j <= 8; j++) for (int k = -8; k <= 8; k++) {
+         double x = i * a0, y = j * a0, z = k * a0, r = sqrt(x * x + y * y + z * z);
+         if (r > 3.3) sites.push_back({r, x, y, z});
+      }
+      sort(sites.begin(), sites.end());
+      int isite = 0, atom = 0;
+      for (int t = 0; t < sys.ntypes; t++)
+         for (int k = 0; k < d.types[t].numb; k++, atom++) {
+            double c[3] = {0, 0, 0};
+            if (d.types[t].molecule == 0) { c[0] = sites[isite][1]; c[1] = sites[isite][2]; c[2] = sites[isite][3]; isite++; }
+            else c[0] = 2.9 * (k - 0.5 * (d.types[t].numb - 1));
+            for (int it = 0; it < P; it++) for (int dd = 0; dd < 3; dd++) coords[dd * n + (size_t)atom * P + it] = c[dd];
+         }
+   }
+   ck(pimcgpu_upload_state(-1, coords.data(), angles.data(), bstype >= 0 ? pindex.data() : nullptr), "pimcgpu_upload_state");
+   ck(pimcgpu_seed(seed), "pimcgpu_seed");
+
+#ifdef PIMC_WITH_NCCL
+   ncclComm_t comm = nullptr;
+   if (ranks > 1) {
+      ncclUniqueId id;
+      string idf = d.outdir + ".pimc_nccl_id";
+      if (rank == 0) { ncclGetUniqueId(&id); FILE *f = fopen((idf + ".tmp").c_str(), "wb"); fwrite(&id, sizeof id, 1, f); fclose(f); rename((idf + ".tmp").c_str(), idf.c_str()); }
+      else { FILE *f; while (!(f = fopen(idf.c_str(), "rb"))) this_thread::sleep_for(chrono::milliseconds(50)); if (fread(&id, sizeof id, 1, f) != 1) die("nccl", "bad id file"); fclose(f); }
+      if (ncclCommInitRank(&comm, ranks, id, rank) != ncclSuccess) die("nccl", "ncclCommInitRank failed");
+   }
+#else
+   if (ranks > 1) die("main", "built without NCCL: multi-rank runs need -DPIMC_WITH_NCCL");
+#endif
+
+   long n_acc = 0, off_gr1d = 0, off_gr2d = 0, off_gr3d = 0, off_rcf = 0, off_rel = 0;
+   ck(pimcgpu_accum_layout(&n_acc, nullptr, &off_gr1d, &off_gr2d, &off_gr3d, &off_rcf, &off_rel), "pimcgpu_accum_layout");
+   vector<double> acc(n_acc), gr1d_sum(PIMCGPU_BINSR, 0.0), rcf_sum(max(1, Q), 0.0);
+   const string fname = d.outdir + d.prefix;
+   const double beta = 1.0 / d.temperature, rottau = Q ? beta / Q : 0.0;
+   double kin_tot = 0, pot_tot = 0, rot_tot = 0, rotsq_tot = 0, cv_tot = 0, cvt_tot = 0, cvr_tot = 0, total_count = 0, sums = 0;
+   ofstream fsum;
+   if (rank == 0) { fsum.open(fname + "_sum.eng"); Writer::setout(fsum); }
+   auto t_start = chrono::steady_clock::now();
+   double bead_updates = 0;
+
+   for (long block = 1; block <= d.blocks; block++) {
+      ck(pimcgpu_accum_reset(), "pimcgpu_accum_reset");
+      const long steps_block = d.passes * P;
+      long done = 0;
+      while (done < steps_block) {
+         long chunk = min<long>(d.skip_averg, steps_block - done);
+         if (block <= d.eq_blocks) chunk = min<long>(steps_block - done, 4L * P);            // no estimators while equilibrating
+         ck(pimcgpu_steps(chunk), "pimcgpu_steps");
+         done += chunk;
+         if (block > d.eq_blocks && done % d.skip_averg == 0) ck(pimcgpu_measure(), "pimcgpu_measure");
+      }
+      ck(pimcgpu_sync(), "pimcgpu_sync");
+      double *dacc = (double *)pimcgpu_accum_device_ptr();                                   // move counters folded in
+#ifdef PIMC_WITH_NCCL
+      if (comm) {
+         cudaStream_t st = (cudaStream_t)pimcgpu_stream();
+         if (ncclAllReduce(dacc, dacc, n_acc, ncclDouble, ncclSum, comm, st) != ncclSuccess) die("nccl", "ncclAllReduce failed");
+         cudaStreamSynchronize(st);
+      }
+#else
+      (void)dacc;
+#endif
+      ck(pimcgpu_accum_download(acc.data(), n_acc), "pimcgpu_accum_download");
+      pimcgpu_scalars sc;
+      ck(pimcgpu_block_scalars(&sc), "pimcgpu_block_scalars");
+      for (int t = 0; t < sys.ntypes; t++)
+         bead_updates += sc.mctotal[t][0] * P + sc.mctotal[t][1] * ((1 << d.types[t].levels) - 1) + sc.mctotal[t][2];
+      if (rank != 0) continue;
+      // MCSaveAcceptRatio, mc_main.cc:879-943
+      cout << "BLOCK:" << setw(8) << block << BLANK << "PASS:" << setw(8) << d.passes << BLANK << "STEP:" << setw(8) << steps_block << BLANK;
+      for (int t = 0; t < sys.ntypes; t++)
+         cout << setw(8) << d.types[t].name << BLANK << setw(8) << sc.mcaccep[t][0] / sc.mctotal[t][0] << BLANK << setw(8) << sc.mcaccep[t][1] / sc.mctotal[t][1] << BLANK;
+      if (Q) cout << BLANK << "Rot: " << setw(8) << sc.mcaccep[imtype][2] / sc.mctotal[imtype][2] << BLANK;
+      cout << endl;
+      if (block > d.eq_blocks && sc.count > 0) {
+         const double ac = sc.count;
+         // SaveEnergy, mc_main.cc:764-795
+         ofstream fe(fname + ".eng", ios::app);
+         Writer::setout(fe);
+         fe << setw(IO_WIDTH_BLOCK) << block << BLANK << setw(IO_WIDTH) << sc.kin / ac << BLANK << setw(IO_WIDTH) << sc.pot / ac << BLANK
+            << setw(IO_WIDTH) << (sc.kin + sc.pot) / ac << BLANK << setw(IO_WIDTH) << sc.rot / ac << BLANK << setw(IO_WIDTH) << sc.rotsq / ac << BLANK
+            << setw(IO_WIDTH) << (sc.kin + sc.pot + sc.rot) / ac << BLANK << setw(IO_WIDTH) << sc.cv / ac << BLANK << setw(IO_WIDTH) << sc.cv_trans / ac << BLANK
+            << setw(IO_WIDTH) << sc.cv_rot / ac << BLANK << endl;
+         // SaveSumEnergy, mc_main.cc:797-836 (written once per block here)
+         kin_tot += sc.kin; pot_tot += sc.pot; rot_tot += sc.rot; rotsq_tot += sc.rotsq; cv_tot += sc.cv; cvt_tot += sc.cv_trans; cvr_tot += sc.cv_rot;
+         total_count += ac; sums += 1.0;
+         const double tc = total_count, T = d.temperature;
+         double Cv = 0.5 * (double)(3 * N * P * T) - (kin_tot + pot_tot + rot_tot) / tc;
+         Cv = -(Cv * Cv + cv_tot / tc) * beta / T;
+         double Cvt = 0.5 * (double)(3 * N * P * T) - kin_tot / tc;
+         Cvt = -(Cvt * Cvt + cvt_tot / tc) * beta / T;
+         double Cvr = -rot_tot / tc;
+         Cvr = -(Cvr * Cvr + cvr_tot / tc) * beta / T;
+         fsum << setw(IO_WIDTH_BLOCK) << sums << BLANK << setw(IO_WIDTH) << kin_tot / tc << BLANK << setw(IO_WIDTH) << pot_tot / tc << BLANK
+              << setw(IO_WIDTH) << (kin_tot + pot_tot) / tc << BLANK << setw(IO_WIDTH) << rot_tot / tc << BLANK << setw(IO_WIDTH) << rotsq_tot / tc << BLANK
+              << setw(IO_WIDTH) << (kin_tot + pot_tot + rot_tot) / tc << BLANK << setw(IO_WIDTH) << Cv << BLANK << setw(IO_WIDTH) << Cvt << BLANK
+              << setw(IO_WIDTH) << Cvr << BLANK << endl;
+         // SaveRCF (block and accumulated), mc_estim.cc:1141-1191
+         if (Q) {
+            for (int it = 0; it < Q; it++) rcf_sum[it] += acc[off_rcf + it];
+            for (int mode = 0; mode < 2; mode++) {
+               ostringstream bc; bc << setw(3) << setfill('0') << block;
+               ofstream fr(mode == 0 ? fname + bc.str() + ".rcf" : fname + "_sum.rcf");
+               Writer::setout(fr);
+               const double norm = (mode == 0 ? ac : tc) * (double)Q;
+               for (int it = 0; it <= Q; it++)
+                  fr << setw(IO_WIDTH) << (double)it * rottau << BLANK << setw(IO_WIDTH) << (mode == 0 ? acc[off_rcf + it % Q] : rcf_sum[it % Q]) / norm << BLANK << endl;
+            }
+         }
+         // SaveGraSum, mc_estim.cc:1288-1326
+         int na = 0;
+         for (auto &t : d.types) if (!t.molecule) na = t.numb;
+         if (na > 1) {
+            for (int ir = 0; ir < PIMCGPU_BINSR; ir++) gr1d_sum[ir] += acc[off_gr1d + ir];
+            ofstream fg(fname + "_sum.gra");
+            Writer::setout(fg);
+            const double dr = 15.0 / PIMCGPU_BINSR, norma = dr * tc * (double)P;
+            for (int ir = 0; ir < PIMCGPU_BINSR; ir++)
+               fg << setw(IO_WIDTH) << (ir + 0.5) * dr << BLANK << setw(IO_WIDTH) << gr1d_sum[ir] / (norma * (na * (na - 1)) / 2.0) << BLANK << endl;
+         }
+      }
+      // checkpoint, mc_main.cc:471-483: yw001.stat / .conf / .tabl in the reference's byte layout, chain 0
+      ck(pimcgpu_download_state(0, coords.data(), angles.data(), cosine.data(), bstype >= 0 ? pindex.data() : nullptr), "pimcgpu_download_state");
+      { ofstream f("yw001.stat"); f << "STARTBLOCK " << 0 << endl; }
+      {
+         ofstream f("yw001.conf", ios::binary);
+         streamsize size = sizeof(double) * n;
+         f.write((char *)&size, sizeof(streamsize));
+         f.write((char *)coords.data(), size);         // MCCoords[0]: the x row only, as the reference does (mc_input.cc:587-590)
+         f.write((char *)cosine.data(), size);         // MCCosine[0]
+      }
+      {
+         ofstream f("yw001.tabl", ios::binary);
+         for (int a = 0; a < N; a++) rindex[pindex[a]] = a;
+         streamsize size = sizeof(int) * N;
+         f.write((char *)&size, sizeof(streamsize));
+         f.write((char *)pindex.data(), size);
+         f.write((char *)rindex.data(), size);
+      }
+      { ofstream f("yw001.mrg"); f << "SEED"; for (int k = 0; k < 6; k++) f << " " << seed[k]; f << "\nSTEP " << pimcgpu_step_counter() << "\nCHAINS " << chains << " RANKS " << ranks << endl; }
+      {
+         // IOxyz, mc_input.cc:690-794
+         ofstream f(fname + ".xyz");
+         Writer::setout(f);
+         f << n << endl << "#" << BLANK << "xyz format:  [atom type]  x y z (Angstrom) " << endl;
+         int atom = 0;
+         for (int t = 0; t < sys.ntypes; t++)
+            for (int k = 0; k < d.types[t].numb; k++, atom++)
+               for (int it = 0; it < P; it++) {
+                  ostringstream lab; lab << d.types[t].name << (k + 1);
+                  f << setw(5) << lab.str() << BLANK;
+                  for (int dd = 0; dd < 3; dd++)
+                     f << setw(IO_WIDTH) << coords[dd * n + (size_t)atom * P + it] << BLANK << setw(IO_WIDTH) << cosine[dd * n + (size_t)atom * P + it] << BLANK;
+                  f << endl;
+               }
+      }
+   }
+   double secs = chrono::duration<double>(chrono::steady_clock::now() - t_start).count();
+   if (rank == 0)
+      cout << "pimc_b200: " << d.blocks << " blocks, " << chains * ranks << " chains, " << secs << " s, " << bead_updates / secs << " bead-updates/s" << endl;
+#ifdef PIMC_WITH_NCCL
+   if (comm) ncclCommDestroy(comm);
+#endif
+   pimcgpu_finalize();
+   return 0;
+}

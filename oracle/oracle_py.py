@@ -267,9 +267,12 @@ class Ref:
                 g, v = t["pot1d"]
                 np.savetxt(os.path.join(self.work, ty.fpot + ".pot"), np.c_[g, v], fmt="%.17g")
             elif ty.molecule == 1:
-                rg, cg, v = t["pot2d"]
-                dr, dc = t.get("pot2d_delta", (round(float(rg[1] - rg[0]), 12), round(float(cg[1] - cg[0]), 12)))
-                cfgmod.write_pot2d(os.path.join(self.work, ty.fpot + ".pot"), rg, cg, v, dr, dc)
+                if "pot2d" in t:
+                    rg, cg, v = t["pot2d"]
+                    dr, dc = t.get("pot2d_delta", (round(float(rg[1] - rg[0]), 12), round(float(cg[1] - cg[0]), 12)))
+                    cfgmod.write_pot2d(os.path.join(self.work, ty.fpot + ".pot"), rg, cg, v, dr, dc)
+                else:       # a lone rotor: the reference's CO2_fake.pot
+                    open(os.path.join(self.work, ty.fpot + ".pot"), "w").write("0 0\n0 0\n")
                 if s.Q and s.rotden_type == 0:
                     # init_rotdens file name: type + "_T" + temperature + "t" + Q (mc_poten.cc:518-524)
                     fn = f"{ty.name}_T{_cxx_double(s.temperature)}t{s.Q}.rot"
