@@ -313,7 +313,8 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args.workload, s, chains), "chains_per_gpu": chains, "step": "one MC pass = P iterations of the time loop",
                        "l2": "flushed (256 MB write) between timed passes; the state is L2/SMEM-resident by design inside a pass",
-                       "parallelism": f"independent chains x{world} GPUs, NCCL all-reduce of accumulators per block"},
+                       "parallelism": f"independent chains x{world} GPUs, NCCL all-reduce of accumulators per block",
+                       "geometry": G.geometry()},
             "e2e": {"value": e2e_value, "unit": "bead-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": args.steps,
             "clocks": sampler.summary(),

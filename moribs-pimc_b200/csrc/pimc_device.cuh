@@ -66,7 +66,8 @@ struct Params {
    int rot_group;                // threads cooperating on one rotational slice (power of two, may span warps)
    int seg_max;
    double *segbuf;               // [c][nseg_max][(seg_max+1)*6] per-segment scratch in global memory, used when the
-   int segbuf_global, nseg_max;  // per-team shared-memory buffers would not fit (many narrow teams, long segments)
+   int segbuf_global, nseg_max;
+   int rot_in_smem;              // the linear-rotor density spline is staged in shared memory  // per-team shared-memory buffers would not fit (many narrow teams, long segments)
 };
 
 __host__ __device__ inline size_t pos_index(const Params &p, int c, int it, int d, int a)
@@ -207,8 +208,15 @@ __device__ __forceinline__ int lpot_index(double x, double inv_delta, double del
 // the exact forms)
 __device__ __forceinline__ void fast_r_invr(double r2, double &r, double &invr)
 {
-   invr = rsqrt(r2);
-   r = r2 * invr;
+   // MUFU.RSQ64H seed (about 20 bits) + two Newton steps y <- y(1.5 - 0.5 r2 y^2); r2 is a squared distance between
+   // distinct beads (positive, normal), so the special-case handling of the library rsqrt() is not needed
+   double y;
+   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(r2));
+   const double h = 0.5 * r2;
+   y = y * fma(-h * y, y, 1.5);
+   y = y * fma(-h * y, y, 1.5);
+   invr = y;
+   r = r2 * y;
 }
 // LPot2D, mc_poten.cc:688-729
 __device__ __forceinline__ double lpot2d(const Params &p, const SmallTables &t, double r, double cost, int *pir = nullptr, int *pic = nullptr)
@@ -225,21 +233,22 @@ __device__ __forceinline__ double lpot2d(const Params &p, const SmallTables &t, 
    double dc = (cost - gc.x) * gc.y;
    return (1.0 - dr) * (1.0 - dc) * y1 + dr * (1.0 - dc) * y2 + dr * dc * y3 + (1.0 - dr) * dc * y4;
 }
-// four independent LPot2D evaluations: index arithmetic first, the four cell gathers next, the bilinear forms last
-__device__ __forceinline__ void lpot2d_x4(const Params &p, const SmallTables &t, const double *r, const double *cost, double *out)
+// NB independent LPot2D evaluations: index arithmetic first, the NB cell gathers next, the bilinear forms last
+template <int NB>
+__device__ __forceinline__ void lpot2d_xn(const Params &p, const SmallTables &t, const double *r, const double *cost, double *out)
 {
    const double rmin = t.rgi2d[0].x, cmin = t.cgi2d[0].x;
-   int ir[4], ic[4];
+   int ir[NB], ic[NB];
    #pragma unroll
-   for (int u = 0; u < 4; u++) {
+   for (int u = 0; u < NB; u++) {
       ir[u] = lpot_index(r[u] - rmin, p.inv_dr2d, p.dr2d, p.rs2d);
       ic[u] = lpot_index(cost[u] - cmin, p.inv_dc2d, p.dc2d, p.cs2d);
    }
-   double y1[4], y2[4], y3[4], y4[4];
+   double y1[NB], y2[NB], y3[NB], y4[NB];
    #pragma unroll
-   for (int u = 0; u < 4; u++) load_cell(p.cell2d + ((size_t)ir[u] * (p.cs2d - 1) + ic[u]) * 4, y1[u], y2[u], y3[u], y4[u]);
+   for (int u = 0; u < NB; u++) load_cell(p.cell2d + ((size_t)ir[u] * (p.cs2d - 1) + ic[u]) * 4, y1[u], y2[u], y3[u], y4[u]);
    #pragma unroll
-   for (int u = 0; u < 4; u++) {
+   for (int u = 0; u < NB; u++) {
       const double2 gr = t.rgi2d[ir[u]], gc = t.cgi2d[ic[u]];
       double dr = (r[u] - gr.x) * gr.y;
       double dc = (cost[u] - gc.x) * gc.y;

@@ -108,12 +108,33 @@ __device__ __forceinline__ double pair_diff(const Params &p, const SmallTables &
       }
       return spot1d(p, t, sqrt(d2n)) - spot1d(p, t, sqrt(d2o));
    }
+   if (KIND == 1 && p.mode[type_of(p, g)][type_of(p, j)] == M_LIN_1MOL && !p.minimage) {
+      // atom bead (new and old position) against the linear rotor: shared partner loads, both bilinear forms in flight
+      const int q = it / p.R, m = j - p.first[p.imtype];
+      double rr[2], cs[2], e[2], d2n = 0.0, d2o = 0.0, dn = 0.0, dold = 0.0;
+      #pragma unroll
+      for (int d = 0; d < 3; d++) {
+         const double pj = p.pos[pos_index(p, c, it, d, j)], n = p.cosn[ang_index(p, c, q, d, m)];
+         d2n += (pn[d] - pj) * (pn[d] - pj); dn += n * (pn[d] - pj);
+         d2o += (po[d] - pj) * (po[d] - pj); dold += n * (po[d] - pj);
+      }
+      double inv;
+      fast_r_invr(d2n, rr[0], inv); cs[0] = dn * inv;
+      fast_r_invr(d2o, rr[1], inv); cs[1] = dold * inv;
+      lpot2d_xn<2>(p, t, rr, cs, e);
+      return e[0] - e[1];
+   }
    return pair_energy<KIND>(p, t, c, g, pn, j, it, nullptr, nullptr) - pair_energy<KIND>(p, t, c, g, po, j, it, nullptr, nullptr);
 }
 
-// sum over the partners j = lane, lane+stride, ... of V(g at pn) - V(g at po) at slice it.  Atom-atom spline pairs are
-// processed four partners at a time per lane (their position loads are issued together); rotor partners and
-// everything else go through pair_diff.
+// sum over the partners j = lane, lane+stride, ... of V(g at pn) - V(g at po) at slice it.  When the moved bead is an atom of
+// a spline system (`fast_atoms`) only its atom partners are summed here, four per lane at a time with their position loads
+// issued together; the caller deals the few remaining (rotor) partners of all midpoints of a level to separate lanes.
+template <int KIND>
+__device__ __forceinline__ bool fast_atoms(const Params &p, int tg)
+{
+   return (KIND != 2) && p.molecule[tg] == 0 && !p.minimage && p.n1d > 0;      // moved bead is an atom of a spline system
+}
 template <int KIND>
 __device__ __forceinline__ double partner_sum_diff(const Params &p, const SmallTables &t, int c, int g, const double *pn, const double *po,
                                                    int it, int lane, int stride)
@@ -121,7 +142,7 @@ __device__ __forceinline__ double partner_sum_diff(const Params &p, const SmallT
    double D = 0.0;
    const int N = p.N;
    const int tg = type_of(p, g);
-   const bool fast = (KIND != 2) && p.molecule[tg] == 0 && !p.minimage && p.n1d > 0;      // moved bead is an atom of a spline system
+   const bool fast = fast_atoms<KIND>(p, tg);
    if (fast) {
       const int ja = p.first[tg], jb = ja + p.numb[tg];          // atom partners [ja, jb)
       const double *px = p.pos + pos_index(p, c, it, 0, 0), *py = px + p.Npad, *pz = py + p.Npad;
@@ -143,10 +164,6 @@ __device__ __forceinline__ double partner_sum_diff(const Params &p, const SmallT
             double e = spot1d(p, t, rn[u]) - spot1d(p, t, ro[u]);
             D += ok[u] ? e : 0.0;
          }
-      }
-      for (int j = lane; j < N; j += stride) {                    // the remaining partners (the rotor)
-         if (j >= ja && j < jb) continue;
-         D += pair_diff<KIND>(p, t, c, g, pn, po, j, it);
       }
       return D;
    }
@@ -236,13 +253,16 @@ __device__ void bisection_sweep(const Params &p, Ctx &x, int type, int off)
    const double bnorm = 1.0 / (p.lambda[type] * p.tau);
    const int nrounds = (nseg + x.nteams_chain - 1) / x.nteams_chain;
    bump_pos_epoch(p, x);
-   for (int a = 0; a < p.numb[type]; a++) {
-      const int gA = base + a;
-      const int gB = (p.stat[type] == 1) ? p.pindex[(size_t)c * N + gA] : gA;
-      for (int rd = 0; rd < nrounds; rd++) {
-         const int k = rd * x.nteams_chain + x.team_id;
-         const bool active = k < nseg;
-         const int s0 = active ? (off + k * seg) % P : 0;
+   // The pair action is diagonal in imaginary time and the segment end points are fixed during a sweep, so
+   // segment k of every atom only ever reads slices of segment k: a team keeps its segment index and walks
+   // through the atoms in sequence with no chain-wide barrier; the sweep ends with one barrier.
+   for (int rd = 0; rd < nrounds; rd++) {
+      const int k = rd * x.nteams_chain + x.team_id;
+      const bool active = k < nseg;
+      const int s0 = active ? (off + k * seg) % P : 0;
+      for (int a = 0; a < p.numb[type]; a++) {
+         const int gA = base + a;
+         const int gB = (p.stat[type] == 1) ? p.pindex[(size_t)c * N + gA] : gA;
          double *nx = p.segbuf_global ? p.segbuf + ((size_t)c * p.nseg_max + (active ? k : 0)) * ((p.seg_max + 1) * 6) : x.team_buf;
          if (active)
             for (int i = x.lane_t; i < 6; i += T) {
@@ -252,6 +272,7 @@ __device__ void bisection_sweep(const Params &p, Ctx &x, int type, int off)
             }
          // unit normals for all interior slices of the segment, drawn up front from the slices' own streams
          // (6 uniforms per slice: gauss() of mc_randg.cc:138-150 per dimension), stored behind the positions
+         MARK(x, 20);
          double *xi = nx + (seg + 1) * 3;
          for (int i0 = 0; i0 < (seg - 1) * 3; i0 += T) {
             const int i = i0 + x.lane_t;
@@ -270,6 +291,7 @@ __device__ void bisection_sweep(const Params &p, Ctx &x, int type, int off)
             if (valid && d == 2) mrg_store(rs, sp);
             __syncwarp();
          }
+         MARK(x, 21);
          double S = 0.0;
          bool alive = active;
          for (int level = 0; level < L; level++) {
@@ -284,6 +306,21 @@ __device__ void bisection_sweep(const Params &p, Ctx &x, int type, int off)
             }
             __syncwarp();
             double D = 0.0;
+            if (alive && fast_atoms<KIND>(p, type)) {
+               // the partners that are not atoms of this type (the rotor): one lane per (midpoint, partner)
+               const int nother = N - p.numb[type];
+               for (int i = x.lane_t; i < nmid * nother; i += T) {
+                  const int m = i / nother, jo = i - m * nother;
+                  const int j = (jo < base) ? jo : jo + p.numb[type];
+                  const int t1 = half + m * lss;
+                  const int sl = (s0 + t1) % P;
+                  const int g = (s0 + t1 >= P) ? gB : gA;
+                  double po[3], pn[3];
+                  #pragma unroll
+                  for (int d = 0; d < 3; d++) { po[d] = p.pos[pos_index(p, c, sl, d, g)]; pn[d] = nx[t1 * 3 + d]; }
+                  D += pair_diff<KIND>(p, x.t, c, g, pn, po, j, sl);
+               }
+            }
             if (alive) {
                for (int m = 0; m < nmid; m++) {
                   const int t1 = half + m * lss;
@@ -295,6 +332,7 @@ __device__ void bisection_sweep(const Params &p, Ctx &x, int type, int off)
                   D += partner_sum_diff<KIND>(p, x.t, c, g, pn, po, sl, x.lane_t, T);
                }
             }
+            MARK(x, 22);
             D = team_sum(D, T);
             const double deltav = (D - S) * (p.tau * (double)half);
             S += D;
@@ -311,6 +349,7 @@ __device__ void bisection_sweep(const Params &p, Ctx &x, int type, int off)
             }
             acc = __shfl_sync(0xffffffffu, acc, x.team_lane0);
             if (!acc) alive = false;
+            MARK(x, 23);
          }
          if (active && x.lane_t == 0) {
             double *cn = counter_ptr(p, c, type, 1);
@@ -324,9 +363,11 @@ __device__ void bisection_sweep(const Params &p, Ctx &x, int type, int off)
                p.pos[pos_index(p, c, (s0 + t) % P, d, g)] = nx[t * 3 + d];
             }
          __syncwarp();
+         MARK(x, 24);
       }
-      chain_sync(p);
    }
+   chain_sync(p);
+   MARK(x, 25);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -341,7 +382,9 @@ __device__ void bisection_sweep(const Params &p, Ctx &x, int type, int off)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void group_sync(const Ctx &x)
 {
-   if (x.G > 32) __syncthreads(); else __syncwarp();
+   if (x.G <= 32) __syncwarp();
+   else if (x.ngrp <= 15) asm volatile("bar.sync %0, %1;" ::"r"(x.grp + 1), "r"(x.G) : "memory");   // one named barrier per rot group
+   else __syncthreads();
 }
 
 // sum over the R translational slices of rot slice q and all partners of the rotor's potential
@@ -406,7 +449,7 @@ __device__ __forceinline__ double rot_potential(const Params &p, Ctx &x, int g, 
             }
             if (!(ok[0] | ok[1] | ok[2] | ok[3])) continue;       // nothing to evaluate (e.g. a lone rotor: no table loaded)
             double e[4];
-            lpot2d_x4(p, x.t, rr, cs, e);
+            lpot2d_xn<4>(p, x.t, rr, cs, e);
             #pragma unroll
             for (int u = 0; u < 4; u++) v += ok[u] ? e[u] : 0.0;
          }
@@ -611,6 +654,17 @@ __device__ __forceinline__ void stage_tables(const Params &p, SmallTables &t, do
       for (int i = threadIdx.x; i < p.cs2d; i += blockDim.x) d2[p.rs2d + i] = p.cgi2d[i];
       t.rgi2d = d2; t.cgi2d = d2 + p.rs2d;
       cursor += 2 * (size_t)(p.rs2d + p.cs2d);
+   }
+   if (p.nrot && p.rot_in_smem) {
+      const int nd = (p.nrot - 1) * (int)(sizeof(SplineRec) / sizeof(double));
+      const double *src = reinterpret_cast<const double *>(p.recrot);
+      for (int i = threadIdx.x; i < nd; i += blockDim.x) cursor[i] = src[i];
+      t.recrot = reinterpret_cast<const SplineRec *>(cursor);
+      cursor += (nd + 1) & ~1;
+      int *li = reinterpret_cast<int *>(cursor);
+      for (int i = threadIdx.x; i < p.nlutrot; i += blockDim.x) li[i] = p.lutrot[i];
+      t.lutrot = li;
+      cursor += ((p.nlutrot + 1) / 2 + 1) & ~1;
    }
    if (p.n1d) {
       const int nd = (p.n1d - 1) * (int)(sizeof(SplineRec) / sizeof(double));

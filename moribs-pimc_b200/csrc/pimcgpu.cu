@@ -176,6 +176,7 @@ size_t smem_bytes(const Params &p, int threads)
    auto padi = [](int n) { return (size_t)(((n + 1) / 2 + 1) & ~1); };
    if (p.n1d) d += pad((p.n1d - 1) * (int)(sizeof(SplineRec) / sizeof(double))) + padi(p.nlut1d);
    if (p.rs2d) d += 2 * (size_t)(p.rs2d + p.cs2d);
+   if (p.nrot && p.rot_in_smem) d += pad((p.nrot - 1) * (int)(sizeof(SplineRec) / sizeof(double))) + padi(p.nlutrot);
    if (!p.segbuf_global) d += (size_t)(threads / p.team) * ((p.seg_max + 1) * 6);
    d += 2 * (size_t)(threads / 32);
    size_t bytes = d * sizeof(double);
@@ -419,6 +420,8 @@ int pimcgpu_init(const pimcgpu_system *sys, const pimcgpu_tables *tab)
    p.nseg_max = p.P / seg_min;
    p.segbuf_global = ((size_t)(threads / team) * ((seg_max + 1) * 6) * sizeof(double) > 64 * 1024) ? 1 : 0;
    if (p.segbuf_global && dalloc(&p.segbuf, C * p.nseg_max * ((seg_max + 1) * 6))) return 1;
+   p.rot_in_smem = 1;
+   if (smem_bytes(p, threads) > 200 * 1024) p.rot_in_smem = 0;
    G.smem = smem_bytes(p, threads);
    if (G.smem > 227 * 1024) return fail("pimcgpu_init: %zu bytes of shared memory per CTA exceed the 227 KB limit", G.smem);
    G.kind = p.imtype >= 0 && p.Q > 0 ? p.molecule[p.imtype] : (p.imtype >= 0 ? p.molecule[p.imtype] : 0);

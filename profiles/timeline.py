@@ -9,17 +9,19 @@ geo = [int(x) for x in sys.argv[1:4]] + [0] * 3
 cfg = pkg.configs.make_config("C5")
 G = pkg.gpu.PimcGpu(cfg, nchains=8, ctas_per_chain=geo[0], threads_per_cta=geo[1], team=geo[2])
 G.seed((12345,) * 6)
-G.steps(1024 + 5)
+warm = int(sys.argv[4]) if len(sys.argv) > 4 else 1024 + 5
+G.steps(warm)
 buf = (C.c_longlong * 4096)()
 G.L.pimcgpu_timeline(buf, 4096)
-G.steps(6)
+G.steps(int(sys.argv[5]) if len(sys.argv) > 5 else 6)
 n = G.L.pimcgpu_timeline(buf, 4096)
 m = np.array(buf[:n], dtype=np.int64)
 ids, t = m >> 48, m & 0xffffffffffff
 names = {1: "step start", 2: "leader proposal done", 3: "after sync#1", 4: "densities done (thread 0)", 5: "items done", 6: "after reduce sync#2",
-         7: "leader decision done", 8: "after sync#3", 9: "phase end", 10: "after chain barrier"}
+         7: "leader decision done", 8: "after sync#3", 9: "phase end", 10: "after chain barrier",
+         20: "bisect: segment start", 21: "normals drawn", 22: "level pair sums done", 23: "level accept done", 24: "segment end", 25: "after chain barrier"}
 prev = t[0]
-for i in range(min(n, 60)):
+for i in range(min(n, int(sys.argv[6]) if len(sys.argv) > 6 else 60)):
     print(f"{int(ids[i]):3d} {names.get(int(ids[i]), ''):28s} +{int(t[i]-prev):7d} cycles")
     prev = t[i]
 G.close()
