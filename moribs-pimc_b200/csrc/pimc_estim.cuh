@@ -10,7 +10,7 @@
 
 namespace pimc {
 
-constexpr int EST_BLOCKS = 16;       // blocks per chain in the estimator kernels
+constexpr int EST_BLOCKS = 64;       // blocks per chain in the estimator kernels
 constexpr int EST_THREADS = 256;
 constexpr int NPART = 8;             // partial slots per block: r2avr, pot, srot, sesq, setermsq
 constexpr int BINSR = 300, BINST = 50, BINSC = 100;          // mc_estim.cc:25-27

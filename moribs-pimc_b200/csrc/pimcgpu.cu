@@ -460,12 +460,16 @@ int pimcgpu_upload_state(int chain, const double *coords, const double *angles, 
    const int cfirst = chain < 0 ? 0 : chain;
    double *hpos = G.stage + (size_t)cfirst * G.stage_chain, *hang = hpos + npos, *hcos = hang + nang;
    CK(cudaStreamSynchronize(G.stream));          // the staging area may still be in flight
-   for (int it = 0; it < p.P; it++)
-      for (int d = 0; d < 3; d++) {
-         double *row = hpos + ((size_t)it * 3 + d) * p.Npad;
-         const double *src = coords + d * n + it;
-         for (int a = 0; a < p.N; a++) row[a] = src[(size_t)a * p.P];
-      }
+   // [dim][atom][it] -> [it][dim][atom], tiled so both sides stay within a few cache lines
+   for (int d = 0; d < 3; d++)
+      for (int a0 = 0; a0 < p.N; a0 += 8)
+         for (int it0 = 0; it0 < p.P; it0 += 64) {
+            const int a1 = std::min(p.N, a0 + 8), it1 = std::min(p.P, it0 + 64);
+            for (int a = a0; a < a1; a++) {
+               const double *src = coords + d * n + (size_t)a * p.P;
+               for (int it = it0; it < it1; it++) hpos[((size_t)it * 3 + d) * p.Npad + a] = src[it];
+            }
+         }
    if (p.imtype >= 0)
       for (int q = 0; q < p.Q; q++)
          for (int m = 0; m < p.NM; m++) {
@@ -524,9 +528,15 @@ int pimcgpu_download_state(int chain, double *coords, double *angles, double *co
    CK(cudaMemcpyAsync(hcos, p.cosn + (size_t)chain * nang, nang * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
    CK(cudaStreamSynchronize(G.stream));
    if (coords)
-      for (int it = 0; it < p.P; it++)
-         for (int d = 0; d < 3; d++)
-            for (int a = 0; a < p.N; a++) coords[d * n + (size_t)a * p.P + it] = hpos[((size_t)it * 3 + d) * p.Npad + a];
+      for (int d = 0; d < 3; d++)
+         for (int a0 = 0; a0 < p.N; a0 += 8)
+            for (int it0 = 0; it0 < p.P; it0 += 64) {
+               const int a1 = std::min(p.N, a0 + 8), it1 = std::min(p.P, it0 + 64);
+               for (int a = a0; a < a1; a++) {
+                  double *dst = coords + d * n + (size_t)a * p.P;
+                  for (int it = it0; it < it1; it++) dst[it] = hpos[((size_t)it * 3 + d) * p.Npad + a];
+               }
+            }
    // rotor rows: only the first Q entries of a molecule's row carry angles (README.md:228); the rest keep
    // the reference's initial values phi=0, cos(theta)=1, chi=0 (MCConfigInit, mc_setup.cc:471-487)
    for (int d = 0; d < 3; d++)
