@@ -264,3 +264,78 @@ def test_geometry_independence(pkg):
             ref = (c, a)
         else:
             assert np.abs(c - ref[0]).max() < 1e-9 and np.abs(a - ref[1]).max() < 1e-9
+
+
+def test_permuted_world_lines_exchange_paths(pkg):
+    """BOSE species with a non-identity permutation: bisection segments that cross beta continue on PIndex[atom],
+    whole-path moves shift complete cycles, the kinetic estimator closes each path on its successor (a3, a4, a14)."""
+    import copy
+    op = _oracle()
+    cfg = copy.copy(make(pkg, "C2"))
+    cfg.perm = np.array([1, 2, 0], dtype=np.int32)            # one 3-cycle
+    s = cfg.system
+    G = pkg.gpu.PimcGpu(cfg, nchains=2)
+    O = op.Oracle(cfg)
+    e = G.chain_energies(0)
+    assert abs(e["kin"] - O.get_kin()) <= RTOL * abs(O.get_kin())
+    seed = (777, 778, 779, 780, 781, 782)
+    G.seed(seed); O.sched_seed(seed, 1)
+    n = 2 * s.P + 1
+    G.steps(n); O.sched_run(0, n)
+    cg, ag, _ = G.download(1)
+    co, ao, _ = O.get_state()
+    assert np.abs(cg - co).max() < 1e-9
+    ot, oa = O.counters()
+    gt, ga = G.counters()
+    assert np.array_equal(gt, 2 * ot) and oa[0, 1] > 0 and oa[0, 0] >= 0
+    assert ot[0, 0] == 3                                      # three passes started (t = 0, P, 2P); one 3-cycle -> ONE whole-path move each
+    e = G.chain_energies(1)
+    assert abs(e["kin"] - O.get_kin()) <= 1e-9 * abs(O.get_kin())
+    G.close()
+
+
+def test_odd_rot_slices_and_ragged_segments(pkg):
+    """Q odd (third rotational phase for the last slice) and P not a multiple of the segment length."""
+    op = _oracle()
+    cfg = pkg.configs.make_config("C5", P=36, Q=9, nsolv=5)
+    s = cfg.system
+    G = pkg.gpu.PimcGpu(cfg, nchains=1)
+    O = op.Oracle(cfg)
+    seed = (31, 32, 33, 34, 35, 36)
+    G.seed(seed); O.sched_seed(seed, 0)
+    n = 3 * s.P
+    G.steps(n); O.sched_run(0, n)
+    cg, ag, _ = G.download(0)
+    co, ao, _ = O.get_state()
+    rows = np.zeros(s.N * s.P, dtype=bool); rows[(s.N - 1) * s.P:(s.N - 1) * s.P + s.Q] = True
+    assert np.abs(cg - co).max() < 1e-9 and np.abs(ag[:, rows] - ao[:, rows]).max() < 1e-9
+    gt, _ = G.counters(); ot, _ = O.counters()
+    assert np.array_equal(gt, ot)
+    G.close()
+
+
+def test_minimum_image_and_error_paths(pkg):
+    """MINIMAGE pair distances; init-time errors are reported, not fatal."""
+    op = _oracle()
+    cfg = pkg.configs.make_config("C2", P=32, Q=8, nsolv=4, big_tables=True)
+    cfg.system.minimage = 1
+    cfg.system.density = 0.004
+    G = pkg.gpu.PimcGpu(cfg, nchains=1)
+    O = op.Oracle(cfg)
+    pe = G.pot_energy_slice(0)
+    po = np.array([[O.pot_energy_it(a, it) for it in range(cfg.system.P)] for a in range(cfg.system.N)])
+    assert np.max(np.abs(pe - po) / np.maximum(np.abs(po), 1e-3)) < 1e-9
+    G.close()
+    bad = pkg.configs.make_config("C5", P=8, Q=4, nsolv=2)          # segment 2^3 is not smaller than P
+    with pytest.raises(pkg.gpu.PimcGpuError, match="segment size"):
+        pkg.gpu.PimcGpu(bad)
+    rs = pkg.configs.make_config("C4", P=64, Q=32)
+    rs.system.rotden_type = 1
+    with pytest.raises(pkg.gpu.PimcGpuError, match="RotDenType"):
+        pkg.gpu.PimcGpu(rs)
+    G = pkg.gpu.PimcGpu(make(pkg, "C5"))
+    with pytest.raises(pkg.gpu.PimcGpuError, match="seed"):
+        G.steps(1)                                                   # stepping before pimcgpu_seed
+    with pytest.raises(pkg.gpu.PimcGpuError):
+        G.seed((0, 0, 0, 1, 2, 3))                                   # CheckSeed: first triple all zero
+    G.close()
