@@ -42,7 +42,8 @@ struct Params {
    int rs2d, cs2d;   const double *rg2d, *cg2d, *v2d; double dr2d, dc2d;
    const double *irg2d, *icg2d;  // 1/(grid[i+1]-grid[i]) of the 2-D potential axes
    double inv_dr2d, inv_dc2d;
-   const double *cell2d;         // [(rs-1)*(cs-1)][4]: the four corner values y1,y2,y3,y4 of every bilinear cell in one 32-byte sector
+   const double2 *cell2d;        // [(rs-1)][cs] row pairs {V[ir][ic], V[ir+1][ic]}: a bilinear cell is two adjacent 16-byte
+                                 // entries (32 contiguous bytes, 2x the table instead of 4x so the hot region stays in L2)
    const double2 *rgi2d, *cgi2d; // {grid[i], 1/(grid[i+1]-grid[i])} of the two axes
    int rg3, thg3, chg3; const double *v3d; double rvmin, rvmax, rvstep;
    int nrot, nlutrot; const double *rgrid, *rdens, *rderv, *resqr, *rdens2, *rderv2, *resqr2; const int *lutrot; double lutrot_scale;
@@ -183,10 +184,12 @@ __device__ __forceinline__ double spot1d(const Params &p, const SmallTables &t, 
 // not if-convert the FP64 division into the common path
 __device__ __noinline__ double exact_floor_div(double x, double delta) { return floor(x / delta); }
 
-// one 256-bit gather of the four corner values of a bilinear cell (one L1TEX wavefront per lane instead of eight)
-__device__ __forceinline__ void load_cell(const double *cell, double &y1, double &y2, double &y3, double &y4)
+// the four corner values of a bilinear cell from the row-pair table: two adjacent 128-bit gathers (usually one
+// sector) instead of eight scalar ones
+__device__ __forceinline__ void load_cell(const double2 *cell, double &y1, double &y2, double &y3, double &y4)
 {
-   asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(y1), "=d"(y2), "=d"(y3), "=d"(y4) : "l"(cell));
+   const double2 a = __ldg(cell), b = __ldg(cell + 1);
+   y1 = a.x; y2 = a.y; y4 = b.x; y3 = b.y;
 }
 // index selection of LPot2D, mc_poten.cc:696-704: floor((x - xmin)/delta) exactly as the reference -- the product with
 // the stored reciprocal decides unless it lands within 1e-7 of an integer, where the true quotient is taken
@@ -227,7 +230,7 @@ __device__ __forceinline__ double lpot2d(const Params &p, const SmallTables &t, 
    if (pir) *pir = ir;
    if (pic) *pic = ic;
    double y1, y2, y3, y4;
-   load_cell(p.cell2d + ((size_t)ir * (p.cs2d - 1) + ic) * 4, y1, y2, y3, y4);
+   load_cell(p.cell2d + (size_t)ir * p.cs2d + ic, y1, y2, y3, y4);
    const double2 gr = t.rgi2d[ir], gc = t.cgi2d[ic];
    double dr = (r - gr.x) * gr.y;
    double dc = (cost - gc.x) * gc.y;
@@ -246,7 +249,7 @@ __device__ __forceinline__ void lpot2d_xn(const Params &p, const SmallTables &t,
    }
    double y1[NB], y2[NB], y3[NB], y4[NB];
    #pragma unroll
-   for (int u = 0; u < NB; u++) load_cell(p.cell2d + ((size_t)ir[u] * (p.cs2d - 1) + ic[u]) * 4, y1[u], y2[u], y3[u], y4[u]);
+   for (int u = 0; u < NB; u++) load_cell(p.cell2d + (size_t)ir[u] * p.cs2d + ic[u], y1[u], y2[u], y3[u], y4[u]);
    #pragma unroll
    for (int u = 0; u < NB; u++) {
       const double2 gr = t.rgi2d[ir[u]], gc = t.cgi2d[ic[u]];

@@ -317,16 +317,12 @@ int pimcgpu_init(const pimcgpu_system *sys, const pimcgpu_tables *tab)
       for (int i = 0; i + 1 < p.cs2d; i++) ic[i] = 1.0 / (tab->cgrid2d[i + 1] - tab->cgrid2d[i]);
       if (dupload(&p.rg2d, tab->rgrid2d, p.rs2d) || dupload(&p.cg2d, tab->cgrid2d, p.cs2d) || dupload(&p.v2d, tab->pot2d, (size_t)p.rs2d * p.cs2d) ||
           dupload(&p.irg2d, ir.data(), ir.size()) || dupload(&p.icg2d, ic.data(), ic.size())) return 1;
-      // cell-packed copy: the four corners of every bilinear cell contiguous (32-byte aligned) for one 256-bit gather
+      // row-pair copy: {V[ir][ic], V[ir+1][ic]} so the four corners of a bilinear cell are 32 contiguous bytes
       {
          const int rs = p.rs2d, cs = p.cs2d;
-         std::vector<double> cell((size_t)(rs - 1) * (cs - 1) * 4);
+         std::vector<double2> cell((size_t)(rs - 1) * cs);
          for (int i = 0; i < rs - 1; i++)
-            for (int j = 0; j < cs - 1; j++) {
-               double *q = &cell[((size_t)i * (cs - 1) + j) * 4];
-               q[0] = tab->pot2d[(size_t)i * cs + j]; q[1] = tab->pot2d[(size_t)(i + 1) * cs + j];
-               q[2] = tab->pot2d[(size_t)(i + 1) * cs + j + 1]; q[3] = tab->pot2d[(size_t)i * cs + j + 1];
-            }
+            for (int j = 0; j < cs; j++) cell[(size_t)i * cs + j] = make_double2(tab->pot2d[(size_t)i * cs + j], tab->pot2d[(size_t)(i + 1) * cs + j]);
          std::vector<double2> rgi(rs), cgi(cs);
          for (int i = 0; i < rs; i++) rgi[i] = make_double2(tab->rgrid2d[i], ir[i]);
          for (int i = 0; i < cs; i++) cgi[i] = make_double2(tab->cgrid2d[i], ic[i]);
