@@ -215,6 +215,32 @@ class Oracle:
         self.lib.orc_get_hist(self.h, _dp(g1), _dp(g2), _dp(g3a), _dp(g3m), _dp(rt), _dp(rp), _dp(rc))
         return dict(gr1d=g1, gr2d=g2, gr3d_atoms=g3a, gr3d_mols=g3m, relthe=rt, relphi=rp, relchi=rc)
 
+    # area / exchange estimators and symmetry operations ---------------------------------
+    def exchange_length(self):
+        nb = max(t.numb for t in self.cfg.system.types if t.stat == 1)
+        out = np.zeros(nb)
+        self.lib.orc_exchange_length(self.h, _dp(out))
+        return out
+
+    def area_estimators(self):
+        out = np.zeros(4)
+        self.lib.orc_area_estimators(self.h, _dp(out))
+        return out
+
+    def area_estim3d(self, iframe):
+        a, i = np.zeros(3), np.zeros(9)
+        self.lib.orc_area_estim3d(self.h, C.c_int(iframe), _dp(a), _dp(i))
+        return a, i
+
+    def reflect(self, plane):
+        self.lib.orc_reflect(self.h, C.c_int(plane))
+
+    def rotsym(self, u, nfold):
+        self.lib.orc_rotsym(self.h, C.c_double(u), C.c_int(nfold))
+
+    def sched_symmetry(self, refl_x, refl_y, refl_z, rotsym, nfold):
+        self.lib.orc_sched_symmetry(self.h, *[C.c_int(v) for v in (refl_x, refl_y, refl_z, rotsym, nfold)])
+
     # schedule replay -----------------------------------------------------------------
     def sched_seed(self, seed6, chain_global=0):
         sd = (C.c_ulong * 6)(*seed6)

@@ -26,6 +26,9 @@ void caleng_(double *, double *, double *, double *, double *);
 void vspher_(double *, double *);
 void rsrot_(double *, double *, double *, double *, double *, double *, int *, double *, double *, double *);
 void rsline_(double *, double *, double *, double *, double *);
+void rflmfx_(double *, double *, double *, double *, double *);
+void rflmfy_(double *, double *, double *, double *, double *);
+void rflmfz_(double *, double *, double *, double *, double *);
 void oracle_set_vspher_table(const double *);
 extern int oracle_last_rotden_index, oracle_last_vcord_index;
 }
@@ -845,6 +848,189 @@ static void GetRCF(orc_t *o, double *rcf0)
 }
 
 // ----------------------------------------------------------------------------
+// area / exchange estimators (a18) and symmetry operations (a19)
+// ----------------------------------------------------------------------------
+// body axes of a top from its Euler angles: vcord_ with ivcord = 1 (vcord.f:36-44)
+static void body_axes(orc_t *o, const double *eul, const double *rcom, double *hx, double *hy, double *hz)
+{
+   double E[3] = {eul[0], eul[1], eul[2]}, C[3] = {rcom[0], rcom[1], rcom[2]}, Pt[3] = {0, 0, 0};
+   double v, rad, the, chi;
+   int iv = 1;
+   vcord_(E, C, Pt, const_cast<double *>(o->v3d), &o->rg3, &o->thg3, &o->chg3, &o->rvmax, &o->rvmin, &o->rvstep,
+          &v, &rad, &the, &chi, hx, hy, hz, &iv);
+}
+
+// GetExchangeLength, mc_estim.cc:1997-2019: ploops[cycle length - 1] += 1 for every permutation cycle
+static void GetExchangeLength(orc_t *o, double *ploops)
+{
+   int nb = o->sys.type[o->bstype].numb;
+   std::vector<int> flag(nb, 0);
+   for (int atom = 0; atom < nb; atom++)
+      if (flag[atom] == 0) {
+         int clen = 0, patom = o->pindex[atom];
+         while (patom != atom) { flag[patom] = 1; patom = o->pindex[patom]; clen++; }
+         ploops[clen] += 1.0;
+      }
+}
+
+// GetAreaEstimators, mc_estim.cc:2087-2250 (reference point: the dopant's centre of mass, option (ii)).
+// out[0..3] = area_perp, area_parl, inert_perp, inert_parl (the inertias before the division by NumbTimes)
+static void GetAreaEstimators(orc_t *o, double *out4)
+{
+   int P = o->P;
+   int moff = o->type_offset(o->imtype), boff = o->type_offset(o->bstype);
+   double area_perp = 0.0, area_parl = 0.0, inert_perp = 0.0, inert_parl = 0.0;
+   for (int atom = 0; atom < o->sys.type[o->bstype].numb; atom++)
+      for (int it0 = 0; it0 < P; it0++) {
+         int it1 = (it0 + 1) % P;
+         int pt0 = boff + P * atom, pt1 = pt0;
+         if (it1 != (it0 + 1)) pt1 = boff + P * o->pindex[atom];
+         pt0 += it0; pt1 += it1;
+         double dr0[3], dr1[3], n_parl[3], n_perp[3], area[3], rn0[3], rn1[3];
+         for (int d = 0; d < 3; d++) {
+            dr0[d] = o->coords[d][pt0] - o->coords[d][moff + it0];
+            dr1[d] = o->coords[d][pt1] - o->coords[d][moff + it1];
+         }
+         int it_rot = it0 / o->R;
+         for (int d = 0; d < 3; d++) n_parl[d] = o->cosine[d][moff + it_rot];
+         const double zero = 10e-4;
+         double tg = 0.0, st = 1.0;
+         if (fabs(n_parl[0]) > zero) { tg = n_parl[1] / n_parl[0]; st = sqrt(1.0 + tg * tg); }
+         n_perp[0] = tg / st; n_perp[1] = -1.0 / st; n_perp[2] = 0.0;
+         area[0] = 0.5 * (dr0[1] * dr1[2] - dr0[2] * dr1[1]);
+         area[1] = 0.5 * (dr0[2] * dr1[0] - dr0[0] * dr1[2]);
+         area[2] = 0.5 * (dr0[0] * dr1[1] - dr0[1] * dr1[0]);
+         for (int d = 0; d < 3; d++) { area_perp += (n_perp[d] * area[d]); area_parl += (n_parl[d] * area[d]); }
+         for (int k = 0; k < 2; k++) {
+            const double *n = k == 0 ? n_perp : n_parl;
+            rn0[0] = n[1] * dr0[2] - n[2] * dr0[1]; rn0[1] = n[2] * dr0[0] - n[0] * dr0[2]; rn0[2] = n[0] * dr0[1] - n[1] * dr0[0];
+            rn1[0] = n[1] * dr1[2] - n[2] * dr1[1]; rn1[1] = n[2] * dr1[0] - n[0] * dr1[2]; rn1[2] = n[0] * dr1[1] - n[1] * dr1[0];
+            for (int d = 0; d < 3; d++) { if (k == 0) inert_perp += (rn0[d] * rn1[d]); else inert_parl += (rn0[d] * rn1[d]); }
+         }
+      }
+   out4[0] = area_perp; out4[1] = area_parl; out4[2] = inert_perp; out4[3] = inert_parl;
+}
+
+// GetAreaEstim3D(iframe), mc_estim.cc:2252-2594: iframe 0 = space-fixed frame about the total centre of mass,
+// 1 = dopant-fixed frame about the dopant.  area_proj[3], inert[9] (before the division by NumbTimes)
+static void GetAreaEstim3D(orc_t *o, int iframe, double *area_proj, double *inert)
+{
+   int P = o->P, N = o->N;
+   std::vector<double> com[3];
+   for (int d = 0; d < 3; d++) {
+      com[d].assign(P, 0.0);
+      for (int it = 0; it < P; it++) {
+         if (iframe == 0) {
+            double tmass = 0.0, c = 0.0;
+            for (int atom = 0; atom < N; atom++) {
+               double mass = o->sys.type[o->mctype[atom]].mass;
+               c += (mass * o->coords[d][atom * P + it]);
+               tmass += mass;
+            }
+            com[d][it] = c / tmass;
+         } else com[d][it] = o->coords[d][o->type_offset(o->imtype) + it];
+      }
+   }
+   int boff = o->type_offset(o->bstype);
+   double bmass = o->sys.type[o->bstype].mass;
+   double ap[3] = {0, 0, 0}, ic[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+   for (int it0 = 0; it0 < P; it0++) {
+      double hat[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+      if (iframe == 1) {
+         int it_rot = it0 / o->R + o->type_offset(o->imtype);
+         double E[3] = {o->angles[PHI][it_rot], acos(o->angles[CTH][it_rot]), o->angles[CHI][it_rot]}, C0[3] = {0, 0, 0};
+         body_axes(o, E, C0, hat[0], hat[1], hat[2]);
+      }
+      for (int atom = 0; atom < o->sys.type[o->bstype].numb; atom++) {
+         int it1 = (it0 + 1) % P;
+         int pt0 = boff + P * atom, pt1 = pt0;
+         if (it1 != (it0 + 1)) pt1 = boff + P * o->pindex[atom];
+         pt0 += it0; pt1 += it1;
+         double dr0[3], dr1[3], area[3], rn0[3], rn1[3];
+         for (int d = 0; d < 3; d++) { dr0[d] = o->coords[d][pt0] - com[d][it0]; dr1[d] = o->coords[d][pt1] - com[d][it1]; }
+         area[0] = 0.5 * (dr0[1] * dr1[2] - dr0[2] * dr1[1]);
+         area[1] = 0.5 * (dr0[2] * dr1[0] - dr0[0] * dr1[2]);
+         area[2] = 0.5 * (dr0[0] * dr1[1] - dr0[1] * dr1[0]);
+         for (int id = 0; id < 3; id++) { ap[0] += area[id] * hat[0][id]; ap[1] += area[id] * hat[1][id]; ap[2] += area[id] * hat[2][id]; }
+         for (int id = 0; id < 3; id++) {
+            const double *h = hat[id];
+            rn0[0] = dr0[1] * h[2] - dr0[2] * h[1]; rn0[1] = dr0[2] * h[0] - dr0[0] * h[2]; rn0[2] = dr0[0] * h[1] - dr0[1] * h[0];
+            rn1[0] = dr1[1] * h[2] - dr1[2] * h[1]; rn1[1] = dr1[2] * h[0] - dr1[0] * h[2]; rn1[2] = dr1[0] * h[1] - dr1[1] * h[0];
+            double sum = 0.0;
+            for (int d = 0; d < 3; d++) sum += rn0[d] * rn1[d] * bmass;
+            ic[id * 3 + id] += sum;
+            double dr0_id = 0.0;
+            for (int d = 0; d < 3; d++) dr0_id += h[d] * dr0[d];
+            for (int jd = 0; jd < 3; jd++)
+               if (jd != id) {
+                  double dr1_jd = 0.0;
+                  for (int d = 0; d < 3; d++) dr1_jd += hat[jd][d] * dr1[d];
+                  ic[id * 3 + jd] += -bmass * dr0_id * dr1_jd;
+               }
+         }
+      }
+   }
+   for (int i = 0; i < 3; i++) area_proj[i] = ap[i];
+   for (int i = 0; i < 9; i++) inert[i] = ic[i];
+}
+
+// Reflect_MF_XZ / _YZ / _XY, mc_piqmc.cc:1385-1708: plane 0 = XZ (REFLECTY, rflmfy), 1 = YZ (REFLECTX, rflmfx),
+// 2 = XY (REFLECTZ, rflmfz).  Euler angles of every rotor slice are re-extracted from the flipped body axes, the
+// y coordinate of every bead is negated; MCCosine is NOT refreshed (as in the reference).
+static void Reflect_MF(orc_t *o, int plane)
+{
+   int P = o->P, type = o->imtype;
+   for (int molec = 0; molec < o->sys.type[type].numb; molec++) {
+      int offset = o->type_offset(type) + molec * P;
+      for (int it_rot = 0; it_rot < P / o->R; it_rot++) {
+         int pMF = it_rot + offset;
+         double RCOM[3] = {o->coords[0][pMF], o->coords[1][pMF], o->coords[2][pMF]};
+         double E[3] = {o->angles[PHI][pMF], acos(o->angles[CTH][pMF]), o->angles[CHI][pMF]};
+         double hx[3], hy[3], hz[3];
+         body_axes(o, E, RCOM, hx, hy, hz);
+         if (plane == 0) rflmfy_(RCOM, hx, hy, hz, E);
+         else if (plane == 1) rflmfx_(RCOM, hx, hy, hz, E);
+         else rflmfz_(RCOM, hx, hy, hz, E);
+         o->angles[PHI][pMF] = E[0];
+         o->angles[CTH][pMF] = cos(E[1]);
+         o->angles[CHI][pMF] = E[2];
+      }
+   }
+   for (size_t i = 0; i < o->coords[1].size(); i++) o->coords[1][i] *= -1.0;
+}
+
+// RotSymConfig, mc_piqmc.cc:1710-1794: one rotor, picked by `rand`, is turned by its symmetry operation
+// (top: chi += 2 pi / nfold; linear: n -> -n)
+static void RotSymConfig(orc_t *o, double rand, int nfold)
+{
+   int P = o->P, type = o->imtype, numb = o->sys.type[type].numb;
+   for (int molec = 0; molec < numb; molec++)
+      if (rand > (double)molec / (double)numb && rand <= (double)(molec + 1) / (double)numb) {
+         int offset = o->type_offset(type) + molec * P;
+         for (int it_rot = 0; it_rot < P / o->R; it_rot++) {
+            int pMF = it_rot + offset;
+            if (o->sys.type[type].molecule == 2) {
+               double chi = o->angles[CHI][pMF] + 2.0 * M_PI / (double)nfold;
+               chi = fmod(chi, 2.0 * M_PI);
+               if (chi < 0.0) chi = 2.0 * M_PI + chi;
+               o->angles[CHI][pMF] = chi;
+            } else if (o->sys.type[type].molecule == 1) {
+               double phi = o->angles[PHI][pMF] + M_PI;
+               o->angles[CTH][pMF] *= -1.0;
+               phi = fmod(phi, 2.0 * M_PI);
+               if (phi < 0.0) phi = 2.0 * M_PI + phi;
+               o->angles[PHI][pMF] = phi;
+               double cost = o->angles[CTH][pMF];
+               double sint = sqrt(1.0 - cost * cost);
+               o->cosine[0][pMF] = sint * cos(phi);
+               o->cosine[1][pMF] = sint * sin(phi);
+               o->cosine[2][pMF] = cost;
+            }
+         }
+      }
+}
+
+// ----------------------------------------------------------------------------
 // device-schedule replay (DESIGN.md "Schedule"); the per-move mathematics is
 // the reference's, the ORDER of moves and the stream addressing are the CUDA
 // path's.
@@ -1124,6 +1310,22 @@ void orc_get_hist(orc_t *o, double *g1, double *g2, double *g3a, double *g3m, do
    if (rt) memcpy(rt, o->relthe.data(), sizeof(double) * MC_BINST);
    if (rp) memcpy(rp, o->relphi.data(), sizeof(double) * MC_BINSC);
    if (rc) memcpy(rc, o->relchi.data(), sizeof(double) * MC_BINSC);
+}
+
+void orc_exchange_length(orc_t *o, double *ploops) { GetExchangeLength(o, ploops); }
+void orc_area_estimators(orc_t *o, double *out4) { GetAreaEstimators(o, out4); }
+void orc_area_estim3d(orc_t *o, int iframe, double *area_proj3, double *inert9) { GetAreaEstim3D(o, iframe, area_proj3, inert9); }
+void orc_reflect(orc_t *o, int plane) { Reflect_MF(o, plane); }
+void orc_rotsym(orc_t *o, double u, int nfold) { RotSymConfig(o, u, nfold); }
+// the tail of MCGetAverage (mc_main.cc:647-692) with the uniforms taken from the chain's miscellaneous stream
+// in the device's order: REFLECTY, REFLECTX, REFLECTZ, ROTSYM (+ the rotor pick)
+void orc_sched_symmetry(orc_t *o, int refl_x, int refl_y, int refl_z, int rotsym, int nfold)
+{
+   int MS = o->P + o->Q;
+   if (refl_y && draw(o, MS) < 0.5) Reflect_MF(o, 0);
+   if (refl_x && draw(o, MS) < 0.5) Reflect_MF(o, 1);
+   if (refl_z && draw(o, MS) < 0.5) Reflect_MF(o, 2);
+   if (rotsym && draw(o, MS) < 0.5) RotSymConfig(o, draw(o, MS), nfold);
 }
 
 void orc_mrg_stream_state(const unsigned long *seed6, long stream, double *st) { mrg_stream_state(seed6, stream, st); }

@@ -91,6 +91,15 @@ void   orc_reset_hist(orc_t *);
 void   orc_get_hist(orc_t *, double *gr1d, double *gr2d, double *gr3d_atoms, double *gr3d_mols,
                     double *relthe, double *relphi, double *relchi);
 
+/* area / exchange estimators (a18): instantaneous values on the current state */
+void orc_exchange_length(orc_t *, double *ploops /* [numb bosons], += */);            /* GetExchangeLength mc_estim.cc:1997-2019 */
+void orc_area_estimators(orc_t *, double *out4 /* area_perp, area_parl, inert_perp, inert_parl */); /* :2087-2250 */
+void orc_area_estim3d(orc_t *, int iframe, double *area_proj3, double *inert9);       /* GetAreaEstim3D :2252-2594 */
+/* symmetry operations (a19) */
+void orc_reflect(orc_t *, int plane /* 0 XZ (REFLECTY), 1 YZ (REFLECTX), 2 XY (REFLECTZ) */); /* mc_piqmc.cc:1385-1708 */
+void orc_rotsym(orc_t *, double u, int nfold);                                        /* RotSymConfig mc_piqmc.cc:1710-1794 */
+void orc_sched_symmetry(orc_t *, int refl_x, int refl_y, int refl_z, int rotsym, int nfold);
+
 /* MRG32k3a (a13): state of the s-th RngStream after SetPackageSeed(seed), and draws */
 void orc_mrg_stream_state(const unsigned long *seed6, long stream, double *state6);
 void orc_mrg_draws(const unsigned long *seed6, long first_stream, int nstream, int ndraw, double *out);

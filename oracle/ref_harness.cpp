@@ -272,6 +272,35 @@ void ref_GetAreaEstim3D(int iframe, double *areas6, double *inert9)
    for (int i = 0; i < 6; i++) areas6[i] = iframe ? _areas3DMFF[i] : _areas3DSFF[i];
    for (int i = 0; i < 9; i++) inert9[i] = iframe ? _inert3DMFF[i] : _inert3DSFF[i];
 }
+// instantaneous values: the block accumulators are zeroed first (mc_estim.cc:2232-2249, 2565-2590)
+void ref_area_estimators(double *out4)
+{
+   for (int i = 0; i < 2; i++) { _areas[i] = 0; _area2[i] = 0; _inert[i] = 0; }
+   GetAreaEstimators();
+   out4[0] = _areas[0]; out4[1] = _areas[1]; out4[2] = _inert[0] * (double)NumbTimes; out4[3] = _inert[1] * (double)NumbTimes;
+}
+void ref_area_estim3d(int iframe, double *areas6, double *inert9)
+{
+   for (int i = 0; i < 6; i++) { _areas3DMFF[i] = 0; _areas3DSFF[i] = 0; }
+   for (int i = 0; i < 9; i++) { _inert3DMFF[i] = 0; _inert3DSFF[i] = 0; }
+   GetAreaEstim3D(iframe);
+   for (int i = 0; i < 6; i++) areas6[i] = iframe ? _areas3DMFF[i] : _areas3DSFF[i];
+   for (int i = 0; i < 9; i++) inert9[i] = (iframe ? _inert3DMFF[i] : _inert3DSFF[i]) * (double)NumbTimes;
+}
+void ref_exchange_length(double *ploops)
+{
+   int nb = MCAtom[BSTYPE].numb;
+   for (int i = 0; i < nb; i++) _ploops[i] = 0;
+   GetExchangeLength();
+   for (int i = 0; i < nb; i++) ploops[i] = _ploops[i];
+}
+void ref_reflect(int plane)
+{
+   PrintYrfl = 0; PrintXrfl = 0; PrintZrfl = 0;
+   if (plane == 0) Reflect_MF_XZ(); else if (plane == 1) Reflect_MF_YZ(); else Reflect_MF_XY();
+}
+void ref_rotsym(void) { RotSymConfig(); }       // rotor pick from rnd1 (queue 1)
+void ref_set_nfold(int n) { NFOLD_ROT = n; }
 void ref_MCGetAverage(double *out7)
 {
    MCGetAverage();

@@ -115,6 +115,39 @@ def run(name, with_ref=True):
             R.lib.ref_get_relbins(op._dp(rt), op._dp(rp), op._dp(rch))
             res["relbins"] = float(max(np.abs(rt - h["relthe"]).max(), np.abs(rp - h["relphi"]).max(), np.abs(rch - h["relchi"]).max()))
 
+    # --- area / exchange estimators (a18) on a permuted configuration -----------------------------
+    bos = [t for t in s.types if t.stat == 1]
+    if bos and mol.molecule:
+        nb = bos[0].numb
+        perm = np.roll(np.arange(nb, dtype=np.int32), 1) if nb > 1 else np.zeros(1, dtype=np.int32)
+        if nb > 3:
+            perm = np.arange(nb, dtype=np.int32); perm[[0, 1, 2]] = [1, 2, 0]       # one 3-cycle, the rest identity
+        c0, a0, _ = O.get_state()
+        O.set_state(c0, a0, perm)
+        if with_ref:
+            R.set_state(c0, a0, perm)
+        pl = O.exchange_length(); gold["ploops"] = pl
+        a3, i3 = O.area_estim3d(0); gold["area_sff"] = np.r_[a3, i3]
+        if with_ref:
+            rp = np.zeros(nb); R.lib.ref_exchange_length(op._dp(rp)); res["ploops"] = float(np.abs(rp - pl).max())
+            ra, ri = np.zeros(6), np.zeros(9); R.lib.ref_area_estim3d(0, op._dp(ra), op._dp(ri))
+            tri = np.array([a3[i] * a3[j] for i in range(3) for j in range(i + 1)])
+            res["area_sff"] = float(max(np.abs(ra - tri).max() / max(1e-300, np.abs(tri).max()), np.abs(ri - i3).max() / np.abs(i3).max()))
+        if mol.molecule == 2:
+            a3, i3 = O.area_estim3d(1); gold["area_mff"] = np.r_[a3, i3]
+            if with_ref:
+                ra, ri = np.zeros(6), np.zeros(9); R.lib.ref_area_estim3d(1, op._dp(ra), op._dp(ri))
+                tri = np.array([a3[i] * a3[j] for i in range(3) for j in range(i + 1)])
+                res["area_mff"] = float(max(np.abs(ra - tri).max() / max(1e-300, np.abs(tri).max()), np.abs(ri - i3).max() / np.abs(i3).max()))
+        else:
+            a4 = O.area_estimators(); gold["area_lin"] = a4
+            if with_ref:
+                r4 = np.zeros(4); R.lib.ref_area_estimators(op._dp(r4))
+                res["area_lin"] = float(np.max(np.abs(r4 - a4) / np.maximum(1e-300, np.abs(a4))))
+        O.set_state(c0, a0, np.arange(nb, dtype=np.int32))
+        if with_ref:
+            R.set_state(c0, a0, np.arange(nb, dtype=np.int32))
+
     # --- moves with shared explicit uniforms -----------------------------------------------------
     R.queue_mode(True)
     nacc = mism = 0
@@ -154,8 +187,19 @@ def run(name, with_ref=True):
             nacc += O.molecular_move(typ, a_, u[3 * a_:3 * a_ + 3], ua[0])
         R.lib.ref_MCMolecularMove(typ)
     res["molecular_accepted"] = nacc
+    # --- symmetry operations (a19) on the moved state ------------------------------------------------
+    if Q and mol.molecule:
+        if mol.molecule == 2:
+            for plane in (0, 1, 2):
+                O.reflect(plane); R.lib.ref_reflect(plane)
+        nfold = 2 if mol.molecule == 2 else 1
+        R.lib.ref_set_nfold(nfold)
+        for u in (0.3, 0.95):
+            O.rotsym(u, nfold)
+            R.lib.ref_rng_clear(); R.push(1, [u]); R.lib.ref_rotsym()
     co, ao, cso = O.get_state()
     cr, ar, csr = R.get_state() if with_ref else (co, ao, cso)
+    res["state_cosine_maxdiff"] = float(np.abs(cso - csr).max())
     res["state_coords_maxdiff"] = float(np.abs(co - cr).max())
     res["state_angles_maxdiff"] = float(np.abs(ao - ar).max())
     tot, acc = O.counters()
