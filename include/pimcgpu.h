@@ -54,6 +54,17 @@ typedef struct {
    int          ctas_per_chain;/* thread-block cluster size per chain, 0 = auto      */
    int          threads_per_cta;/* 0 = auto                                          */
    int          team;          /* lanes cooperating on one segment / rot slice, 0 = auto */
+   /* ROTDENSI line (mc_input.cc:274-284): with rotden_type = 1 the rattle-and-shake propagator of
+    * rsrot_/rsline_ (rotden.f:218-286,356-375) replaces the tables in moves and estimators     */
+   int          rot_odevn;     /* RotOdEvn (only the -1 branch of rsrot_ is live)               */
+   double       rot_eoff;      /* RotEoff, cm^-1 (unused by the live branch)                    */
+   double       x_rot, y_rot, z_rot;  /* X_Rot Y_Rot Z_Rot, cm^-1                                */
+   int          rnratio;       /* RNratio: RS slices per Noya slice in GetRotE3D (0 -> 1)       */
+   /* symmetry operations applied with probability 1/2 at the end of every measurement
+    * (MCGetAverage, mc_main.cc:647-692): REFLECTX/Y/Z and ROTSYM (mc_input.cc:296-330)         */
+   int          reflect[3];    /* IREFLX, IREFLY, IREFLZ                                        */
+   int          rotsym;        /* IROTSYM                                                       */
+   int          nfold_rot;     /* NFOLD_ROT                                                     */
 } pimcgpu_system;
 
 /* host pointers to the tables the reference loads in InitPotentials / InitRotDensity
@@ -123,6 +134,25 @@ int    pimcgpu_accum_reset(void);                  /* MCResetBlockAverage, mc_ma
 int    pimcgpu_block_scalars(pimcgpu_scalars *out);/* reads the (possibly all-reduced) buffer  */
 int    pimcgpu_counters(double *mctotal, double *mcaccep);   /* [types][3], MCTotal/MCAccep    */
 void  *pimcgpu_stream(void);                       /* cudaStream_t the library launches on     */
+
+/* offset (in doubles) of a named region of the accumulator buffer, -1 if unknown:
+ *   "scalars" "gr1d" "gr2d" "gr3d" "rcf" "relbins"  as in pimcgpu_accum_layout
+ *   "area"   40 doubles: _areas[PERP,PARL] _area2[2] _inert[2] (GetAreaEstimators, mc_estim.cc:2087-2250), then
+ *            _areas3DSFF[6] _inert3DSFF[9] _areas3DMFF[6] _inert3DMFF[9] (GetAreaEstim3D, :2252-2594)
+ *   "ploops" one double per boson: _ploops (GetExchangeLength, :1997-2019)                       */
+long   pimcgpu_accum_offset(const char *name);
+
+/* ---- symmetry operations of MCGetAverage (mc_main.cc:647-692): Reflect_MF_XZ/YZ/XY (mc_piqmc.cc:1385-1708) and
+ *      RotSymConfig (:1710-1794) on the device.  pimcgpu_measure applies them after the estimators when the system
+ *      enables them; pimcgpu_symmetry_moves does the same on its own.  pimcgpu_symmetry_ops applies explicit
+ *      operations: ops[chain][4] = {XZ, YZ, XY reflection flags, rotor index for the symmetry rotation or -1}  ---- */
+int pimcgpu_symmetry_moves(void);
+int pimcgpu_symmetry_ops(const int *ops);
+
+/* instantaneous area estimators of one chain, out[28]: area_perp, area_parl, inert_perp, inert_parl of
+ * GetAreaEstimators (linear dopant; inertia sums before the division by NumbTimes), then area_proj[3] and
+ * inert3D[9] of GetAreaEstim3D in the space-fixed frame, then the same in the dopant-fixed frame             */
+int pimcgpu_chain_areas(int chain, double *out28);
 
 /* instantaneous estimator values of one chain (parity with GetKinEnergy, GetPotEnergy,
  * GetRotEnergy|GetRotE3D, ErotSQ, Erot_termSQ; mc_estim.cc:689-1096): out[5]                 */

@@ -31,9 +31,12 @@ struct SplineRec { double xlo, xhi, inv_h, ylo, yhi, clo, chi; };
 struct Params {
    int ntypes, N, P, Q, R, Npad, NM, NMpad;
    int numb[MAXT], molecule[MAXT], stat[MAXT], levels[MAXT], first[MAXT + 1];
-   double lambda[MAXT], mcstep[MAXT], rtstep[MAXT];
+   double lambda[MAXT], mcstep[MAXT], rtstep[MAXT], mass[MAXT];
    double tau, rottau, beta, temperature;
    int imtype, bstype, ispher, minimage;
+   int rotden_type, rnratio;     // ROTDENSI: 0 tabulated densities, 1 rattle-and-shake propagator (rsrot/rsline); RS/Noya ratio
+   double xrot, yrot, zrot;      // rotational constants of the ROTDENSI line, cm^-1
+   int refl[3], rotsym, nfold;   // REFLECTX/Y/Z, ROTSYM (IREFLX.., IROTSYM, NFOLD_ROT; mc_setup.h:24-30)
    double box[3];
    int mode[MAXT][MAXT];
    // tables
@@ -312,20 +315,10 @@ __device__ __forceinline__ void matpre(double phi, double theta, double chi, Mat
 }
 __device__ __forceinline__ double within(double v) { return v > 1.0 ? 1.0 : (v < -1.0 ? -1.0 : v); }
 
-// Euler angles of R = R1^T R2 (deleul, rotden.f:32-134), radians
-__device__ __forceinline__ void deleul(const Mat3 &r1, const Mat3 &r2, double &phi2, double &theta2, double &chi2)
+// (phi, theta, chi) of a rotation matrix: the extraction shared by deleul (rotden.f:62-119) and rflmfx/y/z (vcord.f:293-343)
+__device__ __forceinline__ void euler_from_matrix(const double (&m)[3][3], double &phi2, double &theta2, double &chi2)
 {
    const double small = 1.0e-08;
-   double m[3][3];
-   #pragma unroll
-   for (int i = 0; i < 3; i++)
-      #pragma unroll
-      for (int j = 0; j < 3; j++) {
-         double s = 0.0;
-         #pragma unroll
-         for (int k = 0; k < 3; k++) s = s + r1.m[k][i] * r2.m[k][j];
-         m[i][j] = s;
-      }
    double cost = within(m[2][2]);
    theta2 = acos(cost);
    double sint = sin(theta2);
@@ -343,6 +336,51 @@ __device__ __forceinline__ void deleul(const Mat3 &r1, const Mat3 &r2, double &p
       phi2 = (sphi > 0.0) ? acos(cphi) : 2.0 * PI - acos(cphi);
       chi2 = (schi > 0.0) ? acos(cchi) : 2.0 * PI - acos(cchi);
    }
+}
+// Euler angles of R = R1^T R2 (deleul, rotden.f:32-134), radians
+__device__ __forceinline__ void deleul(const Mat3 &r1, const Mat3 &r2, double &phi2, double &theta2, double &chi2)
+{
+   double m[3][3];
+   #pragma unroll
+   for (int i = 0; i < 3; i++)
+      #pragma unroll
+      for (int j = 0; j < 3; j++) {
+         double s = 0.0;
+         #pragma unroll
+         for (int k = 0; k < 3; k++) s = s + r1.m[k][i] * r2.m[k][j];
+         m[i][j] = s;
+      }
+   euler_from_matrix(m, phi2, theta2, chi2);
+}
+// rsrot_ (rotden.f:218-286, the live branch iodevn = -1): rattle-and-shake propagator exponent numerator `rho`
+// and energy estimator `erot` (K) for a top with rotational constants x, y, z (cm^-1); tauC = MCRotTau (1/K)
+__device__ __forceinline__ double rsrot(const Params &p, const Mat3 &r1, const Mat3 &r2, double *erot)
+{
+   const double tau = p.rottau / WNO2K;
+   const double b0 = 1.0 / p.xrot, b1 = 1.0 / p.yrot, b2 = 1.0 / p.zrot;
+   double dg[3];
+   #pragma unroll
+   for (int i = 0; i < 3; i++) {
+      double s = 0.0;
+      #pragma unroll
+      for (int j = 0; j < 3; j++) s = s + r1.m[j][i] * r2.m[j][i];
+      dg[i] = s;
+   }
+   const double sumaxs = (b0 - b1 - b2) * (1.0 - dg[0]) + (b1 - b2 - b0) * (1.0 - dg[1]) + (b2 - b0 - b1) * (1.0 - dg[2]);
+   if (erot) {
+      double e = sumaxs / (4.0 * tau * tau);
+      e = e + 1.5 / tau + 0.25 * (p.xrot + p.yrot + p.zrot);
+      *erot = e / WNO2K;
+   }
+   return sumaxs;
+}
+// rsline_ (rotden.f:356-375): -(1 - gamma)/(2 B tau) for a linear rotor with constant B = X_Rot
+__device__ __forceinline__ double rsline(const Params &p, double dprd, double *erot)
+{
+   const double tau = p.rottau / WNO2K;
+   const double r = (1.0 - dprd) / (2.0 * p.xrot * tau);
+   if (erot) *erot = ((1.0 - r) / tau) / WNO2K;
+   return -r;
 }
 
 // rotden_ (rotden.f:1-31) + rotpro (rotpro_sub.f:1-64).  Returns rho; erot/esq only when the

@@ -13,6 +13,8 @@ namespace pimc {
 constexpr int EST_BLOCKS = 64;       // blocks per chain in the estimator kernels
 constexpr int EST_THREADS = 256;
 constexpr int NPART = 8;             // partial slots per block: r2avr, pot, srot, sesq, setermsq
+constexpr int NAREA = 28;            // area sums per chain: lin (area_perp, area_parl, inert_perp, inert_parl), SFF (area[3], inert[9]), MFF (same)
+constexpr int NAREA_ACC = 40;        // accumulator slots: _areas[2] _area2[2] _inert[2] _areas3DSFF[6] _inert3DSFF[9] _areas3DMFF[6] _inert3DMFF[9]
 constexpr int BINSR = 300, BINST = 50, BINSC = 100;          // mc_estim.cc:25-27
 constexpr double MAX_RADIUS = 15.0, MIN_RADIUS = 0.0;        // mc_estim.cc:29-30
 
@@ -21,7 +23,10 @@ struct EstBuffers {
    double *chain_e;       // [c][8]: skin, spot, srot, ErotSQ, Erot_termSQ
    double *chain_rcf;     // [c][Q]
    double *acc;           // accumulator buffer
-   long off_gr1d, off_gr2d, off_gr3d, off_rcf, off_relbins;
+   double *com;           // [c][P][3] total centre of mass per slice (space-fixed-frame area estimator)
+   double *area_partials; // [c][EST_BLOCKS][NAREA]
+   double *chain_area;    // [c][NAREA]
+   long off_gr1d, off_gr2d, off_gr3d, off_rcf, off_relbins, off_area, off_ploops;
    int has_gr3d;
    const int *pairs;      // [npairs][2]
    int npairs;
@@ -153,7 +158,62 @@ est_energy_kernel(const __grid_constant__ Params p, const __grid_constant__ EstB
 
    // ---- GetRotE3D (mc_estim.cc:989-1096) / GetRotEnergy (:939-987), RotDenType 0
    double srot = 0.0, sesq = 0.0, sterm = 0.0;
-   if (Q > 0 && p.imtype >= 0) {
+   if (Q > 0 && p.imtype >= 0 && p.rotden_type == 1) {
+      // rattle-and-shake estimators (GetRotE3D with RotDenType 1, mc_estim.cc:1003-1092; GetRotEnergy :970-984).  The
+      // reference folds the analytic offset into the running sum once per molecule, so the molecules are taken in
+      // sequence by block 0 of the chain.
+      if (b == 0) {
+         const int nm = p.numb[p.imtype];
+         if (p.molecule[p.imtype] == 2) {
+            const int skip = p.rnratio;
+            const double nq = (double)(Q / skip), tc = p.rottau / WNO2K;
+            double E = 0.0, ESQ = 0.0, ETERM = 0.0;
+            for (int m = 0; m < nm; m++) {
+               double s = 0.0, q2 = 0.0, t2 = 0.0;
+               for (int q0 = threadIdx.x * skip; q0 < Q; q0 += blockDim.x * skip) {
+                  const int q1 = (q0 + skip) % Q;
+                  Mat3 r0, r1;
+                  load_rotmat(p, c, q0, m, r0);
+                  load_rotmat(p, c, q1, m, r1);
+                  double rel[3], erot = 0.0, esq = 0.0, rho = 0.0;
+                  if (p.rho3) rho = rotden(p, r0, r1, rel, &erot, &esq, nullptr, nullptr);      // Noya tables for the coarse slices
+                  else deleul(r0, r1, rel[0], rel[1], rel[2]);
+                  if (with_dens) {
+                     int bt = (int)floor(rel[1] / delta_theta);
+                     if (bt < BINST && bt >= 0) atomicAdd(e.acc + e.off_relbins + bt, (double)skip);
+                     int bp = (int)floor(rel[0] / delta_chi);
+                     if (bp < BINSC && bp >= 0) atomicAdd(e.acc + e.off_relbins + BINST + bp, (double)skip);
+                     int bc = (int)floor(rel[2] / delta_chi);
+                     if (bc < BINSC && bc >= 0) atomicAdd(e.acc + e.off_relbins + BINST + BINSC + bc, (double)skip);
+                  }
+                  if (skip == 1) { rho = rsrot(p, r0, r1, &erot); s += rho; }
+                  else s += erot;
+                  q2 += esq;
+                  t2 += erot * erot;
+               }
+               s = block_sum(s, red); q2 = block_sum(q2, red); t2 = block_sum(t2, red);
+               E += s / nq; ESQ += q2 / (nq * nq); ETERM += t2 / (nq * nq);
+               if (skip == 1) {
+                  E = E / (4.0 * tc * tc);
+                  E += 0.25 * (p.xrot + p.yrot + p.zrot) + 1.5 / tc;
+                  E = E / WNO2K;
+               }
+            }
+            if (threadIdx.x == 0) { srot = E; sesq = ESQ; sterm = ETERM; }
+         } else {
+            double s = 0.0;
+            for (int q0 = threadIdx.x; q0 < Q; q0 += blockDim.x) {
+               const int q1 = (q0 + 1) % Q;
+               double p0 = 0.0;
+               #pragma unroll
+               for (int d = 0; d < 3; d++) p0 += p.cosn[ang_index(p, c, q0, d, 0)] * p.cosn[ang_index(p, c, q1, d, 0)];
+               s += rsline(p, p0, nullptr);
+            }
+            s = block_sum(s, red);
+            if (threadIdx.x == 0) { s = s / (double)Q; srot = s / p.rottau + 1.0 / p.rottau; }
+         }
+      }
+   } else if (Q > 0 && p.imtype >= 0) {
       const int nm = p.numb[p.imtype];
       const bool top = p.molecule[p.imtype] == 2;
       for (int i = gt; i < nm * Q; i += nt) {
@@ -194,6 +254,131 @@ est_energy_kernel(const __grid_constant__ Params p, const __grid_constant__ EstB
    if (threadIdx.x == 0) {
       double *o = e.partials + ((size_t)c * EST_BLOCKS + b) * NPART;
       o[0] = r2; o[1] = pot; o[2] = srot; o[3] = sesq; o[4] = sterm;
+   }
+}
+
+// total centre of mass of every slice (GetAreaEstim3D iframe 0, mc_estim.cc:2283-2302): atoms in sequence, one thread
+// per (chain, slice, dimension)
+__global__ void est_com_kernel(const __grid_constant__ Params p, const __grid_constant__ EstBuffers e)
+{
+   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= (long)p.nchains * p.P * 3) return;
+   const int d = (int)(i % 3), it = (int)((i / 3) % p.P), c = (int)(i / (3L * p.P));
+   double tmass = 0.0, s = 0.0;
+   for (int a = 0; a < p.N; a++) {
+      const double mass = p.mass[type_of(p, a)];
+      s += (mass * p.pos[pos_index(p, c, it, d, a)]);
+      tmass += mass;
+   }
+   e.com[i] = s / tmass;
+}
+
+// dr0 x n, dr1 x n products of the classical-inertia terms
+__device__ __forceinline__ void cross3(const double *a, const double *b, double *o)
+{
+   o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+}
+// area vector + inertia tensor of one link (dr0 -> dr1) on the axes hat[3][3]: GetAreaEstim3D, mc_estim.cc:2418-2538
+__device__ __forceinline__ void area3d_link(const double *dr0, const double *dr1, const double (&hat)[3][3], double bmass, double *out12)
+{
+   double area[3];
+   cross3(dr0, dr1, area);
+   #pragma unroll
+   for (int k = 0; k < 3; k++) area[k] *= 0.5;
+   #pragma unroll
+   for (int id = 0; id < 3; id++) {
+      #pragma unroll
+      for (int k = 0; k < 3; k++) out12[k] += area[id] * hat[k][id];
+   }
+   #pragma unroll
+   for (int id = 0; id < 3; id++) {
+      double rn0[3], rn1[3];
+      cross3(dr0, hat[id], rn0);
+      cross3(dr1, hat[id], rn1);
+      double sum = 0.0;
+      #pragma unroll
+      for (int d = 0; d < 3; d++) sum += rn0[d] * rn1[d] * bmass;
+      out12[3 + id * 3 + id] += sum;
+      double dr0_id = 0.0;
+      #pragma unroll
+      for (int d = 0; d < 3; d++) dr0_id += hat[id][d] * dr0[d];
+      #pragma unroll
+      for (int jd = 0; jd < 3; jd++)
+         if (jd != id) {
+            double dr1_jd = 0.0;
+            #pragma unroll
+            for (int d = 0; d < 3; d++) dr1_jd += hat[jd][d] * dr1[d];
+            out12[3 + id * 3 + jd] += -bmass * dr0_id * dr1_jd;
+         }
+   }
+}
+
+// GetAreaEstimators (mc_estim.cc:2087-2250) and GetAreaEstim3D for both frames (:2252-2594): one item per
+// (slice, boson); links close onto world line PIndex[atom] at it0 = P-1
+__global__ void __launch_bounds__(EST_THREADS)
+est_area_kernel(const __grid_constant__ Params p, const __grid_constant__ EstBuffers e)
+{
+   __shared__ double red[32];
+   const int c = blockIdx.x / EST_BLOCKS, b = blockIdx.x % EST_BLOCKS;
+   const int P = p.P, N = p.N, bt = p.bstype;
+   const int nb = p.numb[bt], b0 = p.first[bt];
+   const int gt = b * blockDim.x + threadIdx.x, nt = EST_BLOCKS * blockDim.x;
+   const bool lin = p.imtype >= 0 && p.molecule[p.imtype] == 1, mff = p.imtype >= 0 && p.molecule[p.imtype] == 2 && p.ispher == 0;
+   const int gm = p.imtype >= 0 ? p.first[p.imtype] : 0;        // the (first) dopant molecule
+   const double bmass = p.mass[bt];
+   double acc[NAREA];
+   #pragma unroll
+   for (int k = 0; k < NAREA; k++) acc[k] = 0.0;
+   const double ident[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+   for (long i = gt; i < (long)P * nb; i += nt) {
+      const int a = b0 + (int)(i % nb), it0 = (int)(i / nb);
+      int it1 = it0 + 1, a1 = a;
+      if (it1 == P) { it1 = 0; a1 = p.pindex[(size_t)c * N + a]; }
+      double r0[3], r1[3], dr0[3], dr1[3];
+      #pragma unroll
+      for (int d = 0; d < 3; d++) { r0[d] = p.pos[pos_index(p, c, it0, d, a)]; r1[d] = p.pos[pos_index(p, c, it1, d, a1)]; }
+      // space-fixed frame about the total centre of mass
+      #pragma unroll
+      for (int d = 0; d < 3; d++) { dr0[d] = r0[d] - e.com[((size_t)c * P + it0) * 3 + d]; dr1[d] = r1[d] - e.com[((size_t)c * P + it1) * 3 + d]; }
+      area3d_link(dr0, dr1, ident, bmass, acc + 4);
+      if (lin || mff) {
+         #pragma unroll
+         for (int d = 0; d < 3; d++) { dr0[d] = r0[d] - p.pos[pos_index(p, c, it0, d, gm)]; dr1[d] = r1[d] - p.pos[pos_index(p, c, it1, d, gm)]; }
+      }
+      const int q = it0 / p.R;
+      if (mff) {
+         Mat3 rm;
+         load_rotmat(p, c, q, 0, rm);
+         double hat[3][3];                         // hatx, haty, hatz = columns of the rotation matrix (vcord_ ivcord = 1)
+         #pragma unroll
+         for (int k = 0; k < 3; k++)
+            #pragma unroll
+            for (int d = 0; d < 3; d++) hat[k][d] = rm.m[d][k];
+         area3d_link(dr0, dr1, hat, bmass, acc + 16);
+      }
+      if (lin) {
+         double n_parl[3], n_perp[3], area[3], rn0[3], rn1[3];
+         #pragma unroll
+         for (int d = 0; d < 3; d++) n_parl[d] = p.cosn[ang_index(p, c, q, d, 0)];
+         const double zero = 10e-4;
+         double tg = 0.0, st = 1.0;
+         if (fabs(n_parl[0]) > zero) { tg = n_parl[1] / n_parl[0]; st = sqrt(1.0 + tg * tg); }
+         n_perp[0] = tg / st; n_perp[1] = -1.0 / st; n_perp[2] = 0.0;
+         cross3(dr0, dr1, area);
+         #pragma unroll
+         for (int d = 0; d < 3; d++) { acc[0] += (n_perp[d] * (0.5 * area[d])); acc[1] += (n_parl[d] * (0.5 * area[d])); }
+         cross3(n_perp, dr0, rn0); cross3(n_perp, dr1, rn1);
+         #pragma unroll
+         for (int d = 0; d < 3; d++) acc[2] += (rn0[d] * rn1[d]);
+         cross3(n_parl, dr0, rn0); cross3(n_parl, dr1, rn1);
+         #pragma unroll
+         for (int d = 0; d < 3; d++) acc[3] += (rn0[d] * rn1[d]);
+      }
+   }
+   double *o = e.area_partials + ((size_t)c * EST_BLOCKS + b) * NAREA;
+   for (int k = 0; k < NAREA; k++) {
+      double v = block_sum(acc[k], red);
+      if (threadIdx.x == 0) o[k] = v;
    }
 }
 
@@ -241,6 +426,41 @@ __global__ void est_finalize_kernel(const __grid_constant__ Params p, const __gr
          }
       }
    }
+   if (tid == 32 && p.bstype >= 0) {
+      const int nb = p.numb[p.bstype], b0 = p.first[p.bstype];
+      const bool lin = p.imtype >= 0 && p.molecule[p.imtype] == 1, mff = p.imtype >= 0 && p.molecule[p.imtype] == 2 && p.ispher == 0;
+      for (int c = 0; c < p.nchains; c++) {
+         double *ca = e.chain_area + (size_t)c * NAREA;
+         for (int k = 0; k < NAREA; k++) {
+            double s = 0.0;
+            for (int b = 0; b < EST_BLOCKS; b++) s += e.area_partials[((size_t)c * EST_BLOCKS + b) * NAREA + k];
+            ca[k] = s;
+         }
+         if (!accumulate) continue;
+         double *a = e.acc + e.off_area;
+         if (lin) {            // mc_estim.cc:2242-2249
+            a[0] += ca[0]; a[1] += ca[1]; a[2] += ca[0] * ca[0]; a[3] += ca[1] * ca[1];
+            a[4] += ca[2] / (double)p.P; a[5] += ca[3] / (double)p.P;
+         }
+         for (int f = 0; f < 2; f++) {     // space-fixed, then dopant-fixed frame (mc_estim.cc:2565-2590)
+            if (f == 1 && !mff) break;
+            const double *ap = ca + 4 + 12 * f, *ic = ap + 3;
+            double *aa = a + 6 + 15 * f, *ai = aa + 6;
+            int ind = 0;
+            for (int id = 0; id < 3; id++)
+               for (int jd = 0; jd <= id; jd++) aa[ind++] += ap[id] * ap[jd];
+            for (int k = 0; k < 9; k++) ai[k] += ic[k] / (double)p.P;
+         }
+         // GetExchangeLength, mc_estim.cc:1997-2019: one count per permutation cycle, binned by length - 1
+         const int *pi = p.pindex + (size_t)c * p.N;
+         for (int at = 0; at < nb; at++) {
+            int len = 0, pa = pi[b0 + at] - b0;
+            bool first = true;                    // `at` is the smallest member of its cycle
+            while (pa != at) { if (pa < at) first = false; pa = pi[b0 + pa] - b0; len++; }
+            if (first) e.acc[e.off_ploops + len] += 1.0;
+         }
+      }
+   }
    if (accumulate && Q > 0)
       for (int itc = tid; itc < Q; itc += gridDim.x * blockDim.x) {
          double s = 0.0;
@@ -258,6 +478,82 @@ __global__ void fold_counters_kernel(const __grid_constant__ Params p, double *a
    double s = 0.0;
    for (int c = 0; c < p.nchains; c++) s += p.counters[(((size_t)c * MAXT + type) * 3 + move) * 2 + which];
    acc[8 + which * 6 + type * 3 + move] = s;
+}
+
+// Symmetry operations at the end of MCGetAverage (mc_main.cc:647-692): Reflect_MF_XZ / _YZ / _XY (mc_piqmc.cc:1385-1708
+// with rflmfy/x/z, vcord.f:257-546) and RotSymConfig (mc_piqmc.cc:1710-1794).  One block per chain.  ops == nullptr:
+// each enabled operation is applied with probability 1/2, uniforms from the chain's miscellaneous stream in the order
+// REFLECTY, REFLECTX, REFLECTZ, ROTSYM (+ one more for the rotor pick); otherwise ops[c][4] = {XZ, YZ, XY flags, rotor
+// index or -1}.  As in the reference, the reflections leave MCCosine untouched and flip the y coordinate of every bead.
+__global__ void symmetry_kernel(const __grid_constant__ Params p, const int *ops)
+{
+   __shared__ int op[4];
+   const int c = blockIdx.x, Q = p.Q, nm = p.NM;
+   if (threadIdx.x == 0) {
+      op[0] = op[1] = op[2] = 0; op[3] = -1;
+      if (ops) { for (int k = 0; k < 4; k++) op[k] = ops[c * 4 + k]; }
+      else {
+         uint32_t *sp = p.rng + ((size_t)c * p.S + p.P + p.Q) * 6;
+         Mrg rs;
+         mrg_load(rs, sp);
+         if (p.refl[1] && mrg_u01(rs) < 0.5) op[0] = 1;
+         if (p.refl[0] && mrg_u01(rs) < 0.5) op[1] = 1;
+         if (p.refl[2] && mrg_u01(rs) < 0.5) op[2] = 1;
+         if (p.rotsym && mrg_u01(rs) < 0.5) {
+            const double u = mrg_u01(rs);
+            for (int m = 0; m < nm; m++)
+               if (u > (double)m / (double)nm && u <= (double)(m + 1) / (double)nm) op[3] = m;
+         }
+         mrg_store(rs, sp);
+      }
+      if (op[0] | op[1] | op[2] | (op[3] >= 0)) p.pos_epoch[c] += 1;        // cached rotor potentials are stale
+   }
+   __syncthreads();
+   if (!(op[0] | op[1] | op[2]) && op[3] < 0) return;
+   const bool top = p.imtype >= 0 && p.molecule[p.imtype] == 2;
+   for (int i = threadIdx.x; i < nm * Q; i += blockDim.x) {
+      const int m = i / Q, q = i % Q;
+      double phi = p.ang[ang_index(p, c, q, 0, m)], cth = p.ang[ang_index(p, c, q, 1, m)], chi = p.ang[ang_index(p, c, q, 2, m)];
+      if (top)
+         for (int k = 0; k < 3; k++) {
+            if (!op[k]) continue;
+            Mat3 r;
+            matpre(phi, acos(cth), chi, r);
+            double hx[3], hy[3], hz[3];
+            #pragma unroll
+            for (int d = 0; d < 3; d++) { hx[d] = r.m[d][0]; hy[d] = r.m[d][1]; hz[d] = r.m[d][2]; }
+            if (k == 0) { hx[1] = -hx[1]; hz[1] = -hz[1]; cross3(hz, hx, hy); }          // rflmfy: y-hat = z x x
+            else if (k == 1) { hy[1] = -hy[1]; hz[1] = -hz[1]; cross3(hy, hz, hx); }     // rflmfx: x-hat = y x z
+            else { hx[1] = -hx[1]; hy[1] = -hy[1]; cross3(hx, hy, hz); }                 // rflmfz: z-hat = x x y
+            double mm[3][3], theta;
+            #pragma unroll
+            for (int d = 0; d < 3; d++) { mm[d][0] = hx[d]; mm[d][1] = hy[d]; mm[d][2] = hz[d]; }
+            euler_from_matrix(mm, phi, theta, chi);
+            cth = cos(theta);
+         }
+      if (op[3] == m) {
+         if (top) {
+            chi = chi + 2.0 * PI / (double)p.nfold;
+            chi = fmod(chi, 2.0 * PI);
+            if (chi < 0.0) chi = 2.0 * PI + chi;
+         } else {
+            phi = phi + PI;
+            cth *= -1.0;
+            phi = fmod(phi, 2.0 * PI);
+            if (phi < 0.0) phi = 2.0 * PI + phi;
+            const double sint = sqrt(1.0 - cth * cth);
+            p.cosn[ang_index(p, c, q, 0, m)] = sint * cos(phi);
+            p.cosn[ang_index(p, c, q, 1, m)] = sint * sin(phi);
+            p.cosn[ang_index(p, c, q, 2, m)] = cth;
+         }
+      }
+      p.ang[ang_index(p, c, q, 0, m)] = phi; p.ang[ang_index(p, c, q, 1, m)] = cth; p.ang[ang_index(p, c, q, 2, m)] = chi;
+   }
+   if ((op[0] + op[1] + op[2]) & 1)
+      for (long i = threadIdx.x; i < (long)p.P * p.Npad; i += blockDim.x) {
+         const int it = (int)(i / p.Npad), a = (int)(i % p.Npad);
+         p.pos[pos_index(p, c, it, 1, a)] *= -1.0;
+      }
 }
 
 // ---- parity kernels -----------------------------------------------------------------------------

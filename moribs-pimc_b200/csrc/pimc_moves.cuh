@@ -538,9 +538,12 @@ __device__ void rot_step(const Params &p, Ctx &x, int type, int q, int m, bool a
                for (int k = 0; k < 9; k++) A.m[k / 3][k % 3] = mid[k];
                load_rotmat(p, c, q2, m, B);
             }
-            int istop = 0;
-            sl->rho[i] = rotden(p, A, B, nullptr, nullptr, nullptr, nullptr, &istop);
-            if (istop) { if (G == 1) sl->bad |= 1; else atomicOr(&sl->bad, 1); }
+            if (p.rotden_type == 1) sl->rho[i] = rsrot(p, A, B, nullptr);
+            else {
+               int istop = 0;
+               sl->rho[i] = rotden(p, A, B, nullptr, nullptr, nullptr, nullptr, &istop);
+               if (istop) { if (G == 1) sl->bad |= 1; else atomicOr(&sl->bad, 1); }
+            }
          } else {
             const double *mid = (i < 2) ? sl->b : sl->a;
             const int qq = (i == 0 || i == 2) ? q0 : q2;
@@ -550,7 +553,7 @@ __device__ void rot_step(const Params &p, Ctx &x, int type, int q, int m, bool a
                double nb = p.cosn[ang_index(p, c, qq, d, m)];
                dot += (i == 0 || i == 2) ? nb * mid[d] : mid[d] * nb;
             }
-            sl->rho[i] = srotdens(p, x.t, dot);
+            sl->rho[i] = (p.rotden_type == 1) ? rsline(p, dot, nullptr) : srotdens(p, x.t, dot);
          }
       }
       MARK(x, 4);
@@ -572,15 +575,30 @@ __device__ void rot_step(const Params &p, Ctx &x, int type, int q, int m, bool a
          for (int w = 0; w < (G >> 5); w++) { vnew += x.part[2 * w]; vold += x.part[2 * w + 1]; }
       }
       if (!sl->need_old) vold = *vcache;
-      double dens_old = sl->rho[0] * sl->rho[1], dens_new = sl->rho[2] * sl->rho[3];
       int bad = sl->bad;
-      if (fabs(dens_old) < RZERO) dens_old = 0.0;
-      if (fabs(dens_new) < RZERO) dens_new = 0.0;
-      if (KIND == 2) { dens_old = fabs(dens_old); dens_new = fabs(dens_new); }
-      else if (dens_old < 0.0 || dens_new < 0.0) bad = 2;     // "Negative rot density" is fatal in the reference
-      double rd = (dens_old > RZERO) ? dens_new / dens_old : 1.0;
-      rd *= exp(-p.tau * (vnew - vold));
-      bool acc = (rd > 1.0) || (rd > sl->u4);
+      bool acc;
+      if (p.rotden_type == 0) {
+         double dens_old = sl->rho[0] * sl->rho[1], dens_new = sl->rho[2] * sl->rho[3];
+         if (fabs(dens_old) < RZERO) dens_old = 0.0;
+         if (fabs(dens_new) < RZERO) dens_new = 0.0;
+         if (KIND == 2) { dens_old = fabs(dens_old); dens_new = fabs(dens_new); }
+         else if (dens_old < 0.0 || dens_new < 0.0) bad = 2;     // "Negative rot density" is fatal in the reference
+         double rd = (dens_old > RZERO) ? dens_new / dens_old : 1.0;
+         rd *= exp(-p.tau * (vnew - vold));
+         acc = (rd > 1.0) || (rd > sl->u4);
+      } else {
+         // rattle-and-shake propagator: the acceptance works on exponents (mc_piqmc.cc:903-921, 1152-1178)
+         double rd;
+         if (KIND == 2) rd = ((sl->rho[2] + sl->rho[3]) - (sl->rho[0] + sl->rho[1])) / (4.0 * (p.rottau / WNO2K));
+         else {
+            double dens_old = sl->rho[0] + sl->rho[1], dens_new = sl->rho[2] + sl->rho[3];
+            if (fabs(dens_old) < RZERO) dens_old = 0.0;
+            if (fabs(dens_new) < RZERO) dens_new = 0.0;
+            rd = dens_new - dens_old;
+         }
+         rd -= p.tau * (vnew - vold);
+         acc = (rd > 0.0) || (rd > log(sl->u4));
+      }
       if (bad) { acc = false; atomicOr(err, bad); }
       double *cn = counter_ptr(p, c, type, 2);
       atomicAdd(cn, 1.0);

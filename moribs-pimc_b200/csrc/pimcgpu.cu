@@ -49,6 +49,7 @@ struct Context {
    long step = 0;
    long nacc = 0;
    int *d_err = nullptr;
+   int *d_ops = nullptr;            // [c][4] explicit symmetry operations
    bool seeded = false;
    int kind = 0;                    // rotor kind the move kernel is specialised on
    std::vector<int> h_pindex;       // [c][N]
@@ -198,6 +199,11 @@ int launch_estimators(int with_dens, int accumulate)
       est_shapes(g, b);
       est_rcf_kernel<<<g, b, 0, G.stream>>>(G.p, G.e);
    }
+   if (G.p.bstype >= 0) {
+      const long n = (long)G.p.nchains * G.p.P * 3;
+      est_com_kernel<<<(unsigned)((n + 255) / 256), 256, 0, G.stream>>>(G.p, G.e);
+      est_area_kernel<<<G.p.nchains * EST_BLOCKS, EST_THREADS, 0, G.stream>>>(G.p, G.e);
+   }
    est_finalize_kernel<<<8, 128, 0, G.stream>>>(G.p, G.e, accumulate);
    CK(cudaGetLastError());
    return 0;
@@ -229,7 +235,7 @@ int pimcgpu_init(const pimcgpu_system *sys, const pimcgpu_tables *tab)
    if (G.live) pimcgpu_finalize();
    if (!sys || !tab) return fail("pimcgpu_init: null argument");
    if (sys->ntypes < 1 || sys->ntypes > MAXT) return fail("pimcgpu_init: ntypes must be 1 or 2 (one atom type, one molecule type)");
-   if (sys->rotden_type != 0) return fail("pimcgpu_init: RotDenType=%d (rattle-and-shake propagator) is not available on the device", sys->rotden_type);
+   if (sys->rotden_type != 0 && sys->rotden_type != 1) return fail("pimcgpu_init: RotDenType must be 0 (tables) or 1 (rattle-and-shake propagator)");
    if (sys->nchains < 1) return fail("pimcgpu_init: nchains must be >= 1");
    int ndev = 0;
    cudaError_t ce = cudaGetDeviceCount(&ndev);
@@ -246,7 +252,7 @@ int pimcgpu_init(const pimcgpu_system *sys, const pimcgpu_tables *tab)
       if (T.numb < 1) return fail("pimcgpu_init: type %d has no particles", t);
       p.first[t] = p.N; p.N += T.numb;
       p.numb[t] = T.numb; p.molecule[t] = T.molecule; p.stat[t] = T.stat; p.levels[t] = T.levels;
-      p.mcstep[t] = T.mcstep; p.rtstep[t] = T.rtstep;
+      p.mcstep[t] = T.mcstep; p.rtstep[t] = T.rtstep; p.mass[t] = T.mass;
       // lambda = hbar^2/2m in K A^2: 100 hbar^2/(amu k_B) with the CODATA-86 mantissas of mc_const.h:12-14
       p.lambda[t] = 0.5 * (100.0 * (1.05457266 * 1.05457266) / (1.6605402 * 1.380658)) / T.mass;
       if (T.stat == 1) p.bstype = t;
@@ -271,6 +277,20 @@ int pimcgpu_init(const pimcgpu_system *sys, const pimcgpu_tables *tab)
       p.R = p.P / p.Q; p.rottau = p.beta / (double)p.Q;
    }
    p.ispher = sys->ispher; p.minimage = sys->minimage;
+   p.rotden_type = sys->rotden_type; p.rnratio = std::max(1, sys->rnratio);
+   p.xrot = sys->x_rot; p.yrot = sys->y_rot; p.zrot = sys->z_rot;
+   for (int d = 0; d < 3; d++) p.refl[d] = sys->reflect[d] ? 1 : 0;
+   p.rotsym = sys->rotsym ? 1 : 0; p.nfold = std::max(1, sys->nfold_rot);
+   if ((p.refl[0] | p.refl[1] | p.refl[2]) && !(p.imtype >= 0 && p.molecule[p.imtype] == 2 && p.Q > 0))
+      return fail("pimcgpu_init: REFLECTX/Y/Z need a NONLINEAR rotor with ROTATION");
+   if (p.rotsym && !(p.imtype >= 0 && p.Q > 0)) return fail("pimcgpu_init: ROTSYM needs a rotor with ROTATION");
+   if (p.rotden_type == 1) {
+      if (p.Q <= 0) return fail("pimcgpu_init: ROTDENSI 1 without ROTATION");
+      const bool lin = p.molecule[p.imtype] == 1;
+      if (!(p.xrot > 0.0) || (!lin && (!(p.yrot > 0.0) || !(p.zrot > 0.0)))) return fail("pimcgpu_init: ROTDENSI 1 needs positive rotational constants");
+      if (p.Q % p.rnratio) return fail("pimcgpu_init: NumbRotTimes is not a multiple of RNratio");
+      if (!lin && p.rnratio > 1 && !tab->rho3d) return fail("pimcgpu_init: RNratio > 1 needs the density-matrix tables of the coarse slices");
+   }
    for (int d = 0; d < 3; d++) p.box[d] = sys->box[d];
    if (p.ispher && p.Q > 0) return fail("pimcgpu_init: ISPHER = 1 is not compatible with ROTATION");
    // interaction branch per (type0, type1), the if-chain of mc_piqmc.cc:1847-1958
@@ -339,7 +359,7 @@ int pimcgpu_init(const pimcgpu_system *sys, const pimcgpu_tables *tab)
       if (!tab->vspher) return fail("pimcgpu_init: ISPHER=1 needs the 501-entry spherical table");
       if (dupload(&p.vspher, tab->vspher, 501)) return 1;
    }
-   if (p.Q > 0 && p.molecule[p.imtype] == 1) {
+   if (p.Q > 0 && p.molecule[p.imtype] == 1 && p.rotden_type == 0) {
       if (!tab->rotgrid || tab->nrot < 2) return fail("pimcgpu_init: the linear-rotor density table (.rot) is required");
       int n = tab->nrot;
       std::vector<double> g(tab->rotgrid, tab->rotgrid + n), y2;
@@ -359,7 +379,7 @@ int pimcgpu_init(const pimcgpu_system *sys, const pimcgpu_tables *tab)
       p.nrot = n; p.nlutrot = (int)lut.size();
       if (dupload(&p.rgrid, g.data(), n) || dupload(&p.lutrot, lut.data(), lut.size())) return 1;
    }
-   if (p.Q > 0 && p.molecule[p.imtype] == 2) {
+   if (p.Q > 0 && p.molecule[p.imtype] == 2 && (p.rotden_type == 0 || tab->rho3d)) {
       if (!tab->rho3d || !tab->erot3d || !tab->esq3d) return fail("pimcgpu_init: the rho/eng/esq density-matrix tables are required");
       if (dupload(&p.rho3, tab->rho3d, PIMCGPU_SIZE_ROTDEN) || dupload(&p.erot3, tab->erot3d, PIMCGPU_SIZE_ROTDEN) || dupload(&p.esq3, tab->esq3d, PIMCGPU_SIZE_ROTDEN)) return 1;
    }
@@ -435,8 +455,10 @@ int pimcgpu_init(const pimcgpu_system *sys, const pimcgpu_tables *tab)
    if (dupload(&e.pairs, pairs.data(), pairs.size())) return 1;
    e.has_gr3d = (need3d || needsph) ? 1 : 0;
    e.off_gr1d = 32; e.off_gr2d = e.off_gr1d + BINSR; e.off_rcf = e.off_gr2d + (long)BINSR * BINST;
-   e.off_relbins = e.off_rcf + std::max(1, p.Q); e.off_gr3d = e.off_relbins + BINST + 2 * BINSC;
+   e.off_relbins = e.off_rcf + std::max(1, p.Q); e.off_area = e.off_relbins + BINST + 2 * BINSC;
+   e.off_ploops = e.off_area + NAREA_ACC; e.off_gr3d = e.off_ploops + std::max(1, p.bstype >= 0 ? p.numb[p.bstype] : 1);
    G.nacc = e.off_gr3d + (e.has_gr3d ? (long)BINSR * BINST * BINSC : 0);
+   if (dalloc(&e.com, C * p.P * 3) || dalloc(&e.area_partials, C * EST_BLOCKS * NAREA) || dalloc(&e.chain_area, C * NAREA) || dalloc(&G.d_ops, C * 4)) return 1;
    if (dalloc(&e.acc, G.nacc) || dalloc(&e.partials, C * EST_BLOCKS * NPART) || dalloc(&e.chain_e, C * 8) || dalloc(&e.chain_rcf, C * std::max(1, p.Q))) return 1;
    CK(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
    CK(cudaDeviceSynchronize());
@@ -632,7 +654,61 @@ void *pimcgpu_stream(void) { return (void *)G.stream; }
 int pimcgpu_measure(void)
 {
    if (!G.live) return fail("pimcgpu_measure: not initialised");
-   return launch_estimators(1, 1);
+   if (launch_estimators(1, 1)) return 1;
+   if (G.p.refl[0] | G.p.refl[1] | G.p.refl[2] | G.p.rotsym) return pimcgpu_symmetry_moves();
+   return 0;
+}
+
+int pimcgpu_symmetry_moves(void)
+{
+   if (!G.live) return fail("pimcgpu_symmetry_moves: not initialised");
+   if (!G.seeded) return fail("pimcgpu_symmetry_moves: call pimcgpu_seed first");
+   if (!(G.p.refl[0] | G.p.refl[1] | G.p.refl[2] | G.p.rotsym)) return 0;
+   symmetry_kernel<<<G.p.nchains, 256, 0, G.stream>>>(G.p, nullptr);
+   CK(cudaGetLastError());
+   return 0;
+}
+
+int pimcgpu_symmetry_ops(const int *ops)
+{
+   if (!G.live) return fail("pimcgpu_symmetry_ops: not initialised");
+   if (!ops) return fail("pimcgpu_symmetry_ops: null argument");
+   if (!(G.p.imtype >= 0 && G.p.Q > 0)) return fail("pimcgpu_symmetry_ops: no rotor with ROTATION");
+   for (int c = 0; c < G.p.nchains; c++) {
+      if ((ops[4 * c] | ops[4 * c + 1] | ops[4 * c + 2]) && G.p.molecule[G.p.imtype] != 2) return fail("pimcgpu_symmetry_ops: reflections need a NONLINEAR rotor");
+      if (ops[4 * c + 3] >= G.p.NM) return fail("pimcgpu_symmetry_ops: rotor index out of range");
+   }
+   CK(cudaMemcpyAsync(G.d_ops, ops, (size_t)G.p.nchains * 4 * sizeof(int), cudaMemcpyHostToDevice, G.stream));
+   symmetry_kernel<<<G.p.nchains, 256, 0, G.stream>>>(G.p, G.d_ops);
+   CK(cudaGetLastError());
+   CK(cudaStreamSynchronize(G.stream));          // `ops` is pageable host memory
+   return 0;
+}
+
+int pimcgpu_chain_areas(int chain, double *out28)
+{
+   if (!G.live) return fail("pimcgpu_chain_areas: not initialised");
+   if (chain < 0 || chain >= G.p.nchains) return fail("pimcgpu_chain_areas: chain out of range");
+   if (G.p.bstype < 0) return fail("pimcgpu_chain_areas: no BOSE type in the system");
+   if (launch_estimators(0, 0)) return 1;
+   CK(cudaStreamSynchronize(G.stream));
+   CK(cudaMemcpy(out28, G.e.chain_area + (size_t)chain * NAREA, NAREA * sizeof(double), cudaMemcpyDeviceToHost));
+   return 0;
+}
+
+long pimcgpu_accum_offset(const char *name)
+{
+   if (!G.live || !name) return -1;
+   const std::string n(name);
+   if (n == "scalars") return 0;
+   if (n == "gr1d") return G.e.off_gr1d;
+   if (n == "gr2d") return G.e.off_gr2d;
+   if (n == "gr3d") return G.e.has_gr3d ? G.e.off_gr3d : -1;
+   if (n == "rcf") return G.e.off_rcf;
+   if (n == "relbins") return G.e.off_relbins;
+   if (n == "area") return G.e.off_area;
+   if (n == "ploops") return G.e.off_ploops;
+   return -1;
 }
 
 int pimcgpu_chain_energies(int chain, double *out5)

@@ -4,14 +4,16 @@
 // .rho/.eng/.esq; formats of mc_poten.cc:254-546 and README.md:78-149), `xyz.init` (initconf.f) when
 // READMCCOORDS is set, runs the block loop of mc_main.cc:340-484 with the moves and estimator sums on the GPU
 // through include/pimcgpu.h, and writes <prefix>.eng, <prefix>_sum.eng, <prefix>NNN.rcf, <prefix>_sum.rcf,
-// <prefix>_sum.gra, <prefix>.xyz and the yw001.stat/.conf/.tabl checkpoints in the reference's formats
-// (mc_main.cc:764-836, mc_estim.cc:1141-1191,1288-1326, mc_input.cc:517-794).
+// <prefix>_sum.gra, <prefix>.prl / .sup / .sffs3d / .mffs3d (exchange lengths and superfluid area estimators),
+// <prefix>.xyz and the yw001.stat/.conf/.tabl checkpoints in the reference's formats
+// (mc_main.cc:704-836, mc_estim.cc:1141-1191,1288-1326,2021-2085,2596-2729, mc_input.cc:517-794).
 //
 // Independent Markov chains: `--chains C` chains per GPU (default 1); with `--ranks N --rank r` (or the
 // RANK/WORLD_SIZE environment of a launcher) every rank drives one GPU, the block accumulators are all-reduced
 // with NCCL over NVLink before rank 0 writes the block files.
 //
-// Not done on the device (and rejected loudly): WORM moves, RotDenType=1.  yw001.rand (SPRNG state) has no
+// ROTDENSI 1 (rattle-and-shake propagator), REFLECTX/Y/Z and ROTSYM are honoured on the device.
+// Not done on the device (and rejected loudly): WORM moves.  yw001.rand (SPRNG state) has no
 // counterpart: the MRG32k3a package seed and step counter are written to yw001.mrg instead.
 #include "../../include/pimcgpu.h"
 
@@ -58,6 +60,8 @@ struct Deck {
    vector<Species> types;
    string outdir = "./", prefix = "pimc";
    int P = 0, Q = 0, ispher = 0, minimage = 0, rotden_type = 0, read_coords = 0, worm = 0;
+   int rot_odevn = 0, rnratio = 1, refl[3] = {0, 0, 0}, rotsym = 0, nfold = 1;
+   double rot_eoff = 0, xrot = 0, yrot = 0, zrot = 0;
    double temperature = 0, density = 0.02;
    long passes = 1, blocks = 1, eq_blocks = 0;
    int skip_ratio = 100000, skip_total = 10000, skip_averg = 1;
@@ -113,7 +117,11 @@ static Deck read_deck(const char *path)
       else if (key == "NUMBEROFPASSES") inf >> d.passes;
       else if (key == "NUMBEROFBLOCKS") inf >> d.blocks >> d.eq_blocks;
       else if (key == "ROTATION") inf >> rot_type >> rot_step >> d.Q;
-      else if (key == "ROTDENSI") inf >> d.rotden_type;
+      else if (key == "ROTDENSI") inf >> d.rotden_type >> d.rot_odevn >> d.rot_eoff >> d.xrot >> d.yrot >> d.zrot >> d.rnratio;   // mc_input.cc:274-284
+      else if (key == "REFLECTX") inf >> d.refl[0];                                                                               // mc_input.cc:296-330
+      else if (key == "REFLECTY") inf >> d.refl[1];
+      else if (key == "REFLECTZ") inf >> d.refl[2];
+      else if (key == "ROTSYM") { d.rotsym = 1; inf >> d.nfold; }
       else if (key == "WORM") d.worm = 1;
       else if (key == "MINIMAGE") d.minimage = 1;
       else if (key == "READMCCOORDS") d.read_coords = 1;
@@ -195,7 +203,6 @@ int main(int argc, char **argv)
    }
    Deck d = read_deck("qmc.input");
    if (d.worm) die("main", "WORM moves are not available on the device path yet (remove the WORM line to sample a fixed permutation)");
-   if (d.rotden_type != 0) die("main", "RotDenType=1 (rattle-and-shake propagator) is not available on the device path");
    const int N = d.N(), P = d.P, Q = d.Q;
    const size_t n = (size_t)N * P;
 
@@ -213,6 +220,10 @@ int main(int argc, char **argv)
    }
    sys.P = P; sys.Q = Q; sys.temperature = d.temperature; sys.ispher = d.ispher; sys.minimage = d.minimage;
    for (int k = 0; k < 3; k++) sys.box[k] = pow((double)N / d.density, 1.0 / 3.0);        // MCInit, mc_setup.cc:339,359-360
+   sys.rotden_type = d.rotden_type; sys.rot_odevn = d.rot_odevn; sys.rot_eoff = d.rot_eoff;
+   sys.x_rot = d.xrot; sys.y_rot = d.yrot; sys.z_rot = d.zrot; sys.rnratio = d.rnratio;
+   for (int k = 0; k < 3; k++) sys.reflect[k] = d.refl[k];
+   sys.rotsym = d.rotsym; sys.nfold_rot = d.nfold;
    sys.nchains = chains; sys.chain_offset = (long)rank * chains; sys.device = rank;
 #ifdef PIMC_WITH_NCCL
    { int nd = 1; cudaGetDeviceCount(&nd); sys.device = rank % std::max(1, nd); }
@@ -252,7 +263,9 @@ int main(int argc, char **argv)
    if (Q > 0 && imtype >= 0) {
       const Species &s = d.types[imtype];
       string base = s.name + "_T" + cxx_double(d.temperature) + "t" + to_string(Q);          // mc_poten.cc:443-458,518-524
-      if (s.molecule == 1) {
+      if (d.rotden_type == 1) {
+         // InitRotDensity loads nothing for the rattle-and-shake propagator (mc_poten.cc:148-164)
+      } else if (s.molecule == 1) {
          trot = read_columns(base + ".rot", 4);
          tab.nrot = (int)trot[0].size(); tab.rotgrid = trot[0].data(); tab.rotdens = trot[1].data(); tab.rotderv = trot[2].data(); tab.rotesqr = trot[3].data();
       } else {
@@ -408,6 +421,50 @@ int main(int argc, char **argv)
             const double dr = 15.0 / PIMCGPU_BINSR, norma = dr * tc * (double)P;
             for (int ir = 0; ir < PIMCGPU_BINSR; ir++)
                fg << setw(IO_WIDTH) << (ir + 0.5) * dr << BLANK << setw(IO_WIDTH) << gr1d_sum[ir] / (norma * (na * (na - 1)) / 2.0) << BLANK << endl;
+         }
+      }
+      if (block > d.eq_blocks && sc.count > 0 && bstype >= 0) {
+         const double ac = sc.count, bmass = d.types[bstype].mass;
+         const double lambda = 0.5 * (100.0 * (1.05457266 * 1.05457266) / (1.6605402 * 1.380658)) / bmass;    // mc_setup.cc:206-215
+         const long oa = pimcgpu_accum_offset("area"), op = pimcgpu_accum_offset("ploops");
+         const int nb = d.types[bstype].numb;
+         ck(pimcgpu_download_state(0, nullptr, nullptr, nullptr, pindex.data()), "pimcgpu_download_state");
+         {  // SaveExchangeLength, mc_estim.cc:2021-2085 (GSLOOP_MAX = 7, mc_confg.h:67); the permutation row is chain 0's
+            ofstream f(fname + ".prl", ios::app);
+            Writer::setout(f);
+            f << setw(IO_WIDTH_BLOCK) << block << BLANK;
+            double excited = 0.0, ground = 0.0;
+            for (int cl = 0; cl < nb; cl++) {
+               double norm = (double)(cl + 1) / (ac * (double)nb);
+               if (cl <= 7) excited += acc[op + cl] * norm; else ground += acc[op + cl] * norm;
+            }
+            f << setw(IO_WIDTH) << ground << BLANK << setw(IO_WIDTH) << excited << BLANK << setw(IO_WIDTH) << (ground + excited) << BLANK;
+            for (int cl = 0; cl < nb; cl++) f << setw(IO_WIDTH) << acc[op + cl] * (double)(cl + 1) / (ac * (double)nb) << BLANK;
+            f << endl;
+            for (int a = 0; a < nb; a++) f << setw(IO_WIDTH) << pindex[a] << BLANK;
+            f << 0 << endl;
+         }
+         if (imtype >= 0 && d.types[imtype].molecule == 1) {
+            // SaveAreaEstimators, mc_estim.cc:2596-2640: columns rho_s perp/parl, I_cl perp/parl, normalised areas
+            const double *A = &acc[oa];
+            const double norm = 2.0 / (beta * lambda);
+            ofstream f(fname + ".sup", ios::app);
+            Writer::setout(f);
+            f << setw(IO_WIDTH_BLOCK) << block << BLANK << setw(IO_WIDTH) << A[2] * norm / A[4] << BLANK << setw(IO_WIDTH) << A[3] * norm / A[5] << BLANK
+              << setw(IO_WIDTH) << A[4] * bmass / ac << BLANK << setw(IO_WIDTH) << A[5] * bmass / ac << BLANK
+              << setw(IO_WIDTH) << A[0] * sqrt(norm / A[4]) / ac << BLANK << setw(IO_WIDTH) << A[1] * sqrt(norm / A[5]) / ac << BLANK << endl;
+         }
+         for (int iframe = 0; iframe < 2; iframe++) {
+            // SaveAreaEstim3D, mc_estim.cc:2667-2729: 9 components of the classical inertia, 6 of 4m^2/(hbar^2 beta) <A_i A_j>
+            if (iframe == 1 && !(imtype >= 0 && d.types[imtype].molecule == 2 && d.ispher == 0)) break;
+            const double *A = &acc[oa + 6 + 15 * iframe], *I = A + 6;
+            const double norm = 2.0 * bmass / (beta * lambda);
+            ofstream f(fname + (iframe ? ".mffs3d" : ".sffs3d"), ios::app);
+            Writer::setout(f);
+            f << setw(IO_WIDTH_BLOCK) << block << BLANK;
+            for (int k = 0; k < 9; k++) f << setw(IO_WIDTH) << I[k] / ac << BLANK;
+            for (int k = 0; k < 6; k++) f << setw(IO_WIDTH) << A[k] * norm / ac << BLANK;
+            f << endl;
          }
       }
       // checkpoint, mc_main.cc:471-483: yw001.stat / .conf / .tabl in the reference's byte layout, chain 0

@@ -25,7 +25,8 @@ EXPORTS = [
     "pimcgpu_counters", "pimcgpu_stream", "pimcgpu_chain_energies", "pimcgpu_chain_rcf", "pimcgpu_eval_spot1d",
     "pimcgpu_eval_lpot2d", "pimcgpu_eval_srotdens", "pimcgpu_eval_rotden", "pimcgpu_eval_vcord", "pimcgpu_eval_caleng",
     "pimcgpu_pot_energy_slice", "pimcgpu_rng_draws", "pimcgpu_fp64_peak", "pimcgpu_host_spline",
-    "pimcgpu_host_stream_state", "pimcgpu_host_lut",
+    "pimcgpu_host_stream_state", "pimcgpu_host_lut", "pimcgpu_accum_offset", "pimcgpu_symmetry_moves", "pimcgpu_symmetry_ops",
+    "pimcgpu_chain_areas",
 ]
 
 
@@ -38,7 +39,9 @@ class GpuSystem(C.Structure):
     _fields_ = [("ntypes", C.c_int), ("type", GpuType * 2), ("P", C.c_int), ("Q", C.c_int), ("temperature", C.c_double),
                 ("ispher", C.c_int), ("minimage", C.c_int), ("box", C.c_double * 3), ("rotden_type", C.c_int),
                 ("nchains", C.c_int), ("chain_offset", C.c_long), ("device", C.c_int), ("ctas_per_chain", C.c_int),
-                ("threads_per_cta", C.c_int), ("team", C.c_int)]
+                ("threads_per_cta", C.c_int), ("team", C.c_int),
+                ("rot_odevn", C.c_int), ("rot_eoff", C.c_double), ("x_rot", C.c_double), ("y_rot", C.c_double), ("z_rot", C.c_double),
+                ("rnratio", C.c_int), ("reflect", C.c_int * 3), ("rotsym", C.c_int), ("nfold_rot", C.c_int)]
 
 
 class GpuTables(C.Structure):
@@ -85,6 +88,8 @@ def lib():
         L.pimcgpu_steps.argtypes = [C.c_long]
         L.pimcgpu_rng_draws.argtypes = [C.c_long, C.c_int, c_dp]
         L.pimcgpu_accum_download.argtypes = [c_dp, C.c_long]
+        L.pimcgpu_accum_offset.restype = C.c_long
+        L.pimcgpu_accum_offset.argtypes = [C.c_char_p]
         _lib = L
     return _lib
 
@@ -132,6 +137,11 @@ class PimcGpu:
             sy.box[d] = box
         sy.nchains, sy.chain_offset, sy.device = nchains, chain_offset, device
         sy.ctas_per_chain, sy.threads_per_cta, sy.team = ctas_per_chain, threads_per_cta, team
+        sy.rot_odevn, sy.rot_eoff, sy.rnratio = s.rot_odevn, s.rot_eoff, s.rnratio
+        sy.x_rot, sy.y_rot, sy.z_rot = s.x_rot, s.y_rot, s.z_rot
+        for d in range(3):
+            sy.reflect[d] = s.reflect[d]
+        sy.rotsym, sy.nfold_rot = (1 if s.rotsym else 0), max(1, s.rotsym)      # ROTSYM n: IROTSYM = 1, NFOLD_ROT = n
         tb = GpuTables()
         self._keep = []
         t = cfg.tables
@@ -216,7 +226,24 @@ class PimcGpu:
         v = [C.c_long() for _ in range(7)]
         _ck(self.L.pimcgpu_accum_layout(*[C.byref(x) for x in v]))
         k = ("n_total", "scalars", "gr1d", "gr2d", "gr3d", "rcf", "relbins")
-        return dict(zip(k, [x.value for x in v]))
+        lay = dict(zip(k, [x.value for x in v]))
+        for name in ("area", "ploops"):
+            lay[name] = self.L.pimcgpu_accum_offset(name.encode())
+        return lay
+
+    def chain_areas(self, chain=0):
+        """GetAreaEstimators / GetAreaEstim3D sums of one chain (a18)."""
+        out = np.zeros(28)
+        _ck(self.L.pimcgpu_chain_areas(C.c_int(chain), _dp(out)))
+        return dict(lin=out[0:4], sff_area=out[4:7], sff_inert=out[7:16], mff_area=out[16:19], mff_inert=out[19:28])
+
+    def symmetry_moves(self):
+        _ck(self.L.pimcgpu_symmetry_moves())
+
+    def symmetry_ops(self, ops):
+        """ops[chain][4] = XZ, YZ, XY reflection flags, rotor index of the symmetry rotation or -1."""
+        o = np.ascontiguousarray(ops, dtype=np.int32).reshape(self.nchains, 4)
+        _ck(self.L.pimcgpu_symmetry_ops(_ip(o)))
 
     def accum_download(self):
         lay = self.accum_layout()
