@@ -69,9 +69,13 @@ struct Params {
    int cpc, team;
    int rot_group;                // threads cooperating on one rotational slice (power of two, may span warps)
    int seg_max;
-   double *segbuf;               // [c][nseg_max][(seg_max+1)*6] per-segment scratch in global memory, used when the
-   int segbuf_global, nseg_max;
-   int rot_in_smem;              // the linear-rotor density spline is staged in shared memory  // per-team shared-memory buffers would not fit (many narrow teams, long segments)
+   double *segbuf;               // [c][nseg_max][team_buf_n] per-segment scratch in global memory, used when the per-team
+   int segbuf_global, nseg_max;  // shared-memory buffers would not fit (many narrow teams, long segments)
+   int team_buf_n;               // doubles of scratch per bisection team (team_buf_doubles)
+   int rot_in_smem;              // the linear-rotor density spline is staged in shared memory
+   int swbar;                    // chain barrier in global memory (cooperative grid) instead of the cluster barrier
+   unsigned *barrier;            // [c][32] arrival counters of the software chain barrier (zeroed before every launch)
+   int rot_fused;                // one-rotor system, even Q: potential sums of all Q proposals in one stage, decisions pipelined (rot_sweep_pipe)
 };
 
 __host__ __device__ inline size_t pos_index(const Params &p, int c, int it, int d, int a)

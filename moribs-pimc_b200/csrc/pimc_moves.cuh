@@ -1,15 +1,15 @@
 // Persistent move kernel: translational multilevel bisection, whole-path (molecular) moves and
 // rotational checkerboard sweeps for many independent Markov chains (sm_100a, FP64).
 //
-// Execution model: one thread-block CLUSTER per chain (cluster size 1..16).  The kernel stays
-// resident for `nsteps` iterations of the reference's `time` loop (mc_main.cc:349-381) and walks
-// the stages of one step in order; dependent stages are separated by a chain-wide barrier
-// (__syncthreads for a 1-CTA chain, barrier.cluster otherwise).  Inside a stage the independent
-// units are dealt to groups of threads:
-//   * bisection segments -> TEAMS of `team` lanes (power of two <= 32): the lanes split the
-//     partner loop of the pair-action sum and combine with a fixed-order shuffle butterfly;
-//   * rotational slices of one parity -> ROT GROUPS of `rot_group` threads (power of two, may span
-//     several warps of one CTA): warp butterfly + fixed-order shared-memory combine.
+// Execution model: `cpc` CTAs per chain (1 CTA per SM).  Up to 8 CTAs form one thread-block CLUSTER and use the
+// hardware cluster barrier; 16 CTAs per chain (8 chains x 16 = 128 of the 148 SMs -- only seven 16-CTA clusters fit
+// on a B200 at once, measured) run as a cooperative grid with a per-chain barrier in global memory.  The kernel
+// stays resident for `nsteps` iterations of the reference's `time` loop (mc_main.cc:349-381) and walks the stages of
+// one step in order; dependent stages are separated by the chain barrier.  Inside a stage the independent units are
+// dealt to groups of threads:
+//   * bisection segments -> TEAMS of `team` threads (power of two, 1..128; more than 32 = several warps of one CTA):
+//     the lanes split the (midpoint, partner) terms of the pair-action sum; warp butterfly + fixed-order combine;
+//   * rotational slices -> ROT GROUPS of `rot_group` threads (power of two, may span several warps of one CTA).
 // Every reduction has a fixed order, so a trajectory is bit-reproducible for a given geometry.
 // The kernel is specialised at compile time on the rotor kind (KIND 0 atoms only, 1 linear rotor,
 // 2 non-linear top) so each variant carries only its own interaction branches.
@@ -20,6 +20,10 @@
 //     time mod (P/seg) == 0      -> bisection sweep with offset time/(P/seg): all P/seg disjoint
 //                                   segments of every atom, atoms in sequence       (MCBisectionMove*)
 //     rotor type                 -> even slices, then odd slices                    (MCRotations3D / MCRotationsMove)
+// A system with ONE rotor evaluates the potential part of all Q proposals in a single parallel stage (the pair action
+// is diagonal in imaginary time and the proposal of a slice depends on that slice alone); the even and the odd
+// accept/reject decisions, which couple neighbouring slices only through the density matrix, are pipelined across
+// time steps behind split arrive/wait counters (rot_sweep_pipe).
 #pragma once
 #include "pimc_device.cuh"
 #include <cooperative_groups.h>
@@ -35,31 +39,54 @@ __device__ int g_nmarks;
 #define MARK(x, id) do { } while (0)
 #endif
 
+constexpr int TEAM_EXTRA = 8;     // doubles per team behind the segment buffers: per-warp partial sums + accept flag
+
 // per rot group scratch in shared memory
 struct RotSlot {
    double u4;                 // uniform of the accept test
    double cost, phi, chi;     // proposal
    double a[9], b[9];         // KIND 2: rotation matrices of the new (a) and current (b) orientation; KIND 1: a[0..2] = n_new, b[0..2] = n_cur
    double rho[4];             // the four density-matrix factors
+   double vnew, vold;         // potential sums of the proposed / current orientation (pipelined sweep)
    int need_old, bad;
 };
 
 struct Ctx {
    int c, crank;
    int tid, gthread, nthreads_chain;
-   int T, lane_t, team_lane0, team_id, nteams_chain;
+   int T, lane_t, team_lane0, team_id, nteams_chain, team_cta;
+   int W, tw, wl, wlanes;     // warps per team, this thread's warp inside the team, lane inside that warp, lanes per warp part
    int G, gl, grp, ngrp;      // rot group size, index inside the group, group index in the CTA, groups per CTA
    SmallTables t;
-   double *team_buf;   // shared: (seg_max+1)*6 doubles per team (segment positions + unit normals)
+   double *team_buf;   // shared: this thread's team scratch (segment positions, unit normals, stream cache, partial sums)
    double *red;        // shared: 40 doubles
    RotSlot *slot;      // shared: this thread's rot group slot (thread-private storage when the group is one thread)
    double *part;       // shared: per-warp partial sums (new, old) of this thread's rot group, used when it spans warps
+   uint32_t *rrng;     // shared: MRG32k3a states of the rot slices this CTA owns in the fused rotational sweep
+   unsigned bar_target;
+   int red_par;
+   int rot_iter;       // pipelined rotational sweeps done in this launch
 };
 
-__device__ __forceinline__ void chain_sync(const Params &p)
+// doubles of scratch per bisection team (host and device use the same formula)
+__host__ __device__ inline int team_buf_doubles(int seg_max) { return (seg_max + 1) * 6 + seg_max * 3 + TEAM_EXTRA; }
+
+__device__ __forceinline__ void chain_sync(const Params &p, Ctx &x)
 {
-   if (p.cpc == 1) __syncthreads();
-   else cg::this_cluster().sync();
+   if (p.cpc == 1) { __syncthreads(); return; }
+   if (!p.swbar) { cg::this_cluster().sync(); return; }
+   // cooperative grid: arrive/spin on the chain's counter (the pattern of a grid-wide barrier)
+   __syncthreads();
+   if (x.tid == 0) {
+      x.bar_target += (unsigned)p.cpc;
+      unsigned *b = p.barrier + (size_t)x.c * 32;
+      __threadfence();
+      atomicAdd(b, 1u);
+      unsigned v;
+      do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(b) : "memory"); } while ((int)(v - x.bar_target) < 0);
+      __threadfence();
+   }
+   __syncthreads();
 }
 __device__ __forceinline__ double team_sum(double v, int T)
 {
@@ -75,7 +102,7 @@ __device__ __forceinline__ double *counter_ptr(const Params &p, int c, int type,
    return p.counters + (((size_t)c * MAXT + type) * 3 + move) * 2;
 }
 
-// deterministic chain-wide sum: warp butterfly, per-CTA shared slots, per-chain global slots
+// deterministic chain-wide sum: warp butterfly, per-CTA shared slots, per-chain global slots (two alternating sets)
 __device__ double chain_reduce(const Params &p, Ctx &x, double v)
 {
    v = team_sum(v, 32);
@@ -86,10 +113,12 @@ __device__ double chain_reduce(const Params &p, Ctx &x, double v)
    for (int w = 0; w < nwarp; w++) s += x.red[w];
    __syncthreads();
    if (p.cpc == 1) return s;
-   if (x.tid == 0) p.scratch[(size_t)x.c * 64 + x.crank] = s;
-   cg::this_cluster().sync();
+   x.red_par ^= 1;
+   double *slots = p.scratch + (size_t)x.c * 64 + 32 * x.red_par;
+   if (x.tid == 0) slots[x.crank] = s;
+   chain_sync(p, x);
    double tot = 0.0;
-   for (int r = 0; r < p.cpc; r++) tot += __ldcg(p.scratch + (size_t)x.c * 64 + r);
+   for (int r = 0; r < p.cpc; r++) tot += __ldcg(slots + r);
    return tot;
 }
 
@@ -129,7 +158,7 @@ __device__ __forceinline__ double pair_diff(const Params &p, const SmallTables &
 
 // sum over the partners j = lane, lane+stride, ... of V(g at pn) - V(g at po) at slice it.  When the moved bead is an atom of
 // a spline system (`fast_atoms`) only its atom partners are summed here, four per lane at a time with their position loads
-// issued together; the caller deals the few remaining (rotor) partners of all midpoints of a level to separate lanes.
+// issued together; the caller deals the few remaining (rotor) partners to separate lanes.
 template <int KIND>
 __device__ __forceinline__ bool fast_atoms(const Params &p, int tg)
 {
@@ -182,6 +211,8 @@ __device__ __forceinline__ void bump_pos_epoch(const Params &p, Ctx &x)
 // ---------------------------------------------------------------------------------------------
 // whole-path move of every permutation cycle of `type` (MCMolecularMove / MCMolecularMoveExchange,
 // mc_piqmc.cc:54-192).  dV of the rigid shift: cycle members against non-members, all P slices.
+// A cycle of one world line (the common case) gives every warp of the chain whole slices and its
+// lanes the partners; longer cycles use the flat (member, slice, partner) loop.
 // ---------------------------------------------------------------------------------------------
 template <int KIND>
 __device__ void molecular_sweep(const Params &p, Ctx &x, int type)
@@ -194,26 +225,44 @@ __device__ void molecular_sweep(const Params &p, Ctx &x, int type)
    int g1 = g0 + p.ncyc[c * MAXT + type];
    uint32_t *ms = stream_ptr(p, c, P + p.Q);
    bump_pos_epoch(p, x);
+   const int gwarp = x.gthread >> 5, nwarps = x.nthreads_chain >> 5, lane = x.tid & 31;
    for (int g = g0; g < g1; g++) {
       Mrg rs;
       mrg_load(rs, ms);
       double u0 = mrg_u01(rs), u1 = mrg_u01(rs), u2 = mrg_u01(rs), u3 = mrg_u01(rs);
       double disp[3] = {p.mcstep[type] * (u0 - 0.5), p.mcstep[type] * (u1 - 0.5), p.mcstep[type] * (u2 - 0.5)};
       int b = cyc_start[g], len = cyc_start[g + 1] - b;
-      long nitems = (long)len * P * N;
       double part = 0.0;
-      for (long i = x.gthread; i < nitems; i += x.nthreads_chain) {
-         int j = (int)(i % N);
-         long r = i / N;
-         int it = (int)(r % P);
-         int a0 = cyc_atoms[b + (int)(r / P)];
-         bool member = false;
-         for (int k = 0; k < len; k++) member |= (cyc_atoms[b + k] == j);
-         if (member) continue;
-         double po[3], pn[3];
-         #pragma unroll
-         for (int d = 0; d < 3; d++) { po[d] = p.pos[pos_index(p, c, it, d, a0)]; pn[d] = po[d] + disp[d]; }
-         part += pair_diff<KIND>(p, x.t, c, a0, pn, po, j, it);
+      if (len == 1) {
+         const int a0 = cyc_atoms[b];
+         const bool fast = fast_atoms<KIND>(p, type);
+         const int nother = N - p.numb[type], base = p.first[type];
+         for (int it = gwarp; it < P; it += nwarps) {
+            double po[3], pn[3];
+            #pragma unroll
+            for (int d = 0; d < 3; d++) { po[d] = p.pos[pos_index(p, c, it, d, a0)]; pn[d] = po[d] + disp[d]; }
+            part += partner_sum_diff<KIND>(p, x.t, c, a0, pn, po, it, lane, 32);
+            if (fast)
+               for (int jo = lane; jo < nother; jo += 32) {
+                  const int j = (jo < base) ? jo : jo + p.numb[type];
+                  part += pair_diff<KIND>(p, x.t, c, a0, pn, po, j, it);
+               }
+         }
+      } else {
+         long nitems = (long)len * P * N;
+         for (long i = x.gthread; i < nitems; i += x.nthreads_chain) {
+            int j = (int)(i % N);
+            long r = i / N;
+            int it = (int)(r % P);
+            int a0 = cyc_atoms[b + (int)(r / P)];
+            bool member = false;
+            for (int k = 0; k < len; k++) member |= (cyc_atoms[b + k] == j);
+            if (member) continue;
+            double po[3], pn[3];
+            #pragma unroll
+            for (int d = 0; d < 3; d++) { po[d] = p.pos[pos_index(p, c, it, d, a0)]; pn[d] = po[d] + disp[d]; }
+            part += pair_diff<KIND>(p, x.t, c, a0, pn, po, j, it);
+         }
       }
       double deltav = chain_reduce(p, x, part);
       bool acc = (deltav < 0.0) || (exp(-deltav * p.tau) > u3);
@@ -233,7 +282,7 @@ __device__ void molecular_sweep(const Params &p, Ctx &x, int type)
          cn[0] += 1.0;
          if (acc) cn[1] += 1.0;
       }
-      chain_sync(p);
+      chain_sync(p, x);
    }
 }
 
@@ -244,10 +293,27 @@ __device__ void molecular_sweep(const Params &p, Ctx &x, int type)
 // the dV of the midpoints sampled at level l, so delta = (D - S)*tau*seg_l/2 equals the
 // reference's (pot0 - 2 pot1)*tau*(seg_l/2) without re-evaluating earlier levels (:263 "inefficient").
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void team_sync(const Ctx &x)
+{
+   if (x.T <= 32) __syncwarp();
+   else asm volatile("bar.sync %0, %1;" ::"r"(x.team_cta + 1), "r"(x.T) : "memory");     // one named barrier per team (<= 15 teams per CTA)
+}
+// fixed-order sum over the team; all lanes return the total
+__device__ __forceinline__ double team_reduce(const Ctx &x, double v, double *red)
+{
+   v = team_sum(v, x.wlanes);
+   if (x.W == 1) return v;
+   if (x.wl == 0) red[x.tw] = v;
+   team_sync(x);
+   double s = 0.0;
+   for (int w = 0; w < x.W; w++) s += red[w];
+   return s;
+}
+
 template <int KIND>
 __device__ void bisection_sweep(const Params &p, Ctx &x, int type, int off)
 {
-   const int c = x.c, P = p.P, N = p.N, T = x.T;
+   const int c = x.c, P = p.P, N = p.N, T = x.T, W = x.W;
    const int L = p.levels[type], seg = 1 << L, nseg = P / seg;
    const int base = p.first[type];
    const double bnorm = 1.0 / (p.lambda[type] * p.tau);
@@ -260,10 +326,17 @@ __device__ void bisection_sweep(const Params &p, Ctx &x, int type, int off)
       const int k = rd * x.nteams_chain + x.team_id;
       const bool active = k < nseg;
       const int s0 = active ? (off + k * seg) % P : 0;
+      double *nx = p.segbuf_global ? p.segbuf + ((size_t)c * p.nseg_max + k) * p.team_buf_n : x.team_buf;      // nseg_max is rounded up to whole rounds
+      double *xi = nx + (p.seg_max + 1) * 3;
+      uint32_t *rc = reinterpret_cast<uint32_t *>(nx + (p.seg_max + 1) * 6);       // streams of slices s0 .. s0+seg-1, cached for the sweep
+      double *tred = nx + (p.seg_max + 1) * 6 + p.seg_max * 3;
+      int *tflag = reinterpret_cast<int *>(tred + 4);
+      if (active)
+         for (int i = x.lane_t; i < seg * 6; i += T) rc[i] = stream_ptr(p, c, (s0 + i / 6) % P)[i % 6];
+      team_sync(x);
       for (int a = 0; a < p.numb[type]; a++) {
          const int gA = base + a;
          const int gB = (p.stat[type] == 1) ? p.pindex[(size_t)c * N + gA] : gA;
-         double *nx = p.segbuf_global ? p.segbuf + ((size_t)c * p.nseg_max + (active ? k : 0)) * ((p.seg_max + 1) * 6) : x.team_buf;
          if (active)
             for (int i = x.lane_t; i < 6; i += T) {
                int e = i / 3, d = i - 3 * e, t = e * seg;
@@ -271,25 +344,23 @@ __device__ void bisection_sweep(const Params &p, Ctx &x, int type, int off)
                nx[t * 3 + d] = p.pos[pos_index(p, c, (s0 + t) % P, d, g)];
             }
          // unit normals for all interior slices of the segment, drawn up front from the slices' own streams
-         // (6 uniforms per slice: gauss() of mc_randg.cc:138-150 per dimension), stored behind the positions
+         // (6 uniforms per slice: gauss() of mc_randg.cc:138-150 per dimension)
          MARK(x, 20);
-         double *xi = nx + (seg + 1) * 3;
          for (int i0 = 0; i0 < (seg - 1) * 3; i0 += T) {
             const int i = i0 + x.lane_t;
             const bool valid = active && i < (seg - 1) * 3;
-            const int t = 1 + i / 3, d = i - 3 * (t - 1);
-            uint32_t *sp = stream_ptr(p, c, (s0 + (valid ? t : 0)) % P);
+            const int t = valid ? 1 + i / 3 : 1, d = i - 3 * (t - 1);
             Mrg rs;
             if (valid) {
-               mrg_load(rs, sp);
+               mrg_load(rs, rc + t * 6);
                double r1 = 0, r2 = 0;
-               for (int k = 0; k <= d; k++) { r1 = mrg_u01(rs); r2 = mrg_u01(rs); }
-               for (int k = d + 1; k < 3; k++) { mrg_u01(rs); mrg_u01(rs); }
+               for (int kk = 0; kk <= d; kk++) { r1 = mrg_u01(rs); r2 = mrg_u01(rs); }
+               for (int kk = d + 1; kk < 3; kk++) { mrg_u01(rs); mrg_u01(rs); }
                xi[t * 3 + d] = sqrt(-log(r1)) * cos(2.0 * PI * r2);
             }
-            __syncwarp();                               // every lane of a slice has read the state before it advances
-            if (valid && d == 2) mrg_store(rs, sp);
-            __syncwarp();
+            team_sync(x);                               // every lane of a slice has read the state before it advances
+            if (valid && d == 2) mrg_store(rs, rc + t * 6);
+            team_sync(x);
          }
          MARK(x, 21);
          double S = 0.0;
@@ -304,7 +375,7 @@ __device__ void bisection_sweep(const Params &p, Ctx &x, int type, int off)
                   nx[t1 * 3 + d] = 0.5 * (nx[(t1 - half) * 3 + d] + nx[(t1 + half) * 3 + d]) + xi[t1 * 3 + d] / sq;
                }
             }
-            __syncwarp();
+            team_sync(x);
             double D = 0.0;
             if (alive && fast_atoms<KIND>(p, type)) {
                // the partners that are not atoms of this type (the rotor): one lane per (midpoint, partner)
@@ -322,32 +393,39 @@ __device__ void bisection_sweep(const Params &p, Ctx &x, int type, int off)
                }
             }
             if (alive) {
-               for (int m = 0; m < nmid; m++) {
+               // the warps of the team take the midpoints in turn; with fewer midpoints than warps several warps share one
+               const int wpm = (nmid >= W) ? 1 : W / nmid, mstep = W / wpm;
+               const int li = (x.tw % wpm) * x.wlanes + x.wl, stride = wpm * x.wlanes;
+               for (int m = x.tw / wpm; m < nmid; m += mstep) {
                   const int t1 = half + m * lss;
                   const int sl = (s0 + t1) % P;
                   const int g = (s0 + t1 >= P) ? gB : gA;
                   double po[3], pn[3];
                   #pragma unroll
                   for (int d = 0; d < 3; d++) { po[d] = p.pos[pos_index(p, c, sl, d, g)]; pn[d] = nx[t1 * 3 + d]; }
-                  D += partner_sum_diff<KIND>(p, x.t, c, g, pn, po, sl, x.lane_t, T);
+                  D += partner_sum_diff<KIND>(p, x.t, c, g, pn, po, sl, li, stride);
                }
             }
             MARK(x, 22);
-            D = team_sum(D, T);
+            D = team_reduce(x, D, tred);
             const double deltav = (D - S) * (p.tau * (double)half);
             S += D;
             int acc = 1;
             if (alive && x.lane_t == 0) {
                if (!(deltav < 0.0)) {
-                  uint32_t *sp = stream_ptr(p, c, s0);
                   Mrg rs;
-                  mrg_load(rs, sp);
+                  mrg_load(rs, rc);
                   double u = mrg_u01(rs);
-                  mrg_store(rs, sp);
+                  mrg_store(rs, rc);
                   acc = (exp(-deltav) > u) ? 1 : 0;
                }
             }
-            acc = __shfl_sync(0xffffffffu, acc, x.team_lane0);
+            if (W == 1) acc = __shfl_sync(0xffffffffu, acc, x.team_lane0);
+            else {
+               if (x.lane_t == 0) *tflag = acc;
+               team_sync(x);
+               acc = *tflag;
+            }
             if (!acc) alive = false;
             MARK(x, 23);
          }
@@ -362,17 +440,20 @@ __device__ void bisection_sweep(const Params &p, Ctx &x, int type, int off)
                int g = (s0 + t >= P) ? gB : gA;
                p.pos[pos_index(p, c, (s0 + t) % P, d, g)] = nx[t * 3 + d];
             }
-         __syncwarp();
+         team_sync(x);
          MARK(x, 24);
       }
+      if (active)
+         for (int i = x.lane_t; i < seg * 6; i += T) stream_ptr(p, c, (s0 + i / 6) % P)[i % 6] = rc[i];
+      team_sync(x);
    }
-   chain_sync(p);
+   chain_sync(p, x);
    MARK(x, 25);
 }
 
 // ---------------------------------------------------------------------------------------------
 // rotational Metropolis step at rot slice q for rotor m (MCRot3Dstep mc_piqmc.cc:938-1199,
-// MCRotLinStep :781-936; RotDenType 0), executed by one rot group:
+// MCRotLinStep :781-936), executed by one rot group:
 //   leader: uniforms, proposal, orientation matrices          -> shared slot          | group sync
 //   all   : the four density factors (first four threads) and the partner/slice sum of the
 //           potential for the proposed orientation; the sum for the current orientation is taken
@@ -458,6 +539,114 @@ __device__ __forceinline__ double rot_potential(const Params &p, Ctx &x, int g, 
    return v;
 }
 
+// proposal of a rotational step (mc_piqmc.cc:950-995 top, :796-814 linear): angles in (cost, phi, chi), the
+// orientation (KIND 2: rotation matrix, 9 doubles; KIND 1: unit vector) in `o`
+template <int KIND>
+__device__ __forceinline__ void rot_propose(const Params &p, int type, double r1, double r2, double r3, double &cost, double &phi, double &chi, double *o)
+{
+   const double step = p.rtstep[type];
+   cost += step * (r1 - 0.5);
+   if (KIND == 2) {
+      phi += 2.0 * PI * (step * (r2 - 0.5));
+      chi += 2.0 * PI * (step * (r3 - 0.5));
+      if (phi < 0.0) phi = 2.0 * PI + phi;
+      if (chi < 0.0) chi = 2.0 * PI + chi;
+      phi = fmod(phi, 2.0 * PI);
+      chi = fmod(chi, 2.0 * PI);
+   } else {
+      phi += step * (r2 - 0.5);
+   }
+   if (cost > 1.0) cost = 2.0 - cost;
+   if (cost < -1.0) cost = -2.0 - cost;
+   if (KIND == 2) {
+      Mat3 Rn;
+      matpre(phi, acos(cost), chi, Rn);
+      #pragma unroll
+      for (int i = 0; i < 9; i++) o[i] = Rn.m[i / 3][i % 3];
+   } else {
+      const double sint = sqrt(1.0 - cost * cost);
+      double sp_, cp_;
+      sincos(phi, &sp_, &cp_);
+      o[0] = sint * cp_; o[1] = sint * sp_; o[2] = cost;
+   }
+}
+
+// acceptance of a rotational step from the four density factors rho = {(q0->cur), (cur->q2), (q0->new), (new->q2)} and
+// the potential sums (mc_piqmc.cc:895-921, 1145-1178); *bad collects the reference's fatal conditions
+template <int KIND>
+__device__ __forceinline__ bool rot_accept(const Params &p, const double *rho, double vnew, double vold, double u4, int *bad)
+{
+   if (p.rotden_type == 0) {
+      double dens_old = rho[0] * rho[1], dens_new = rho[2] * rho[3];
+      if (fabs(dens_old) < RZERO) dens_old = 0.0;
+      if (fabs(dens_new) < RZERO) dens_new = 0.0;
+      if (KIND == 2) { dens_old = fabs(dens_old); dens_new = fabs(dens_new); }
+      else if (dens_old < 0.0 || dens_new < 0.0) *bad |= 2;     // "Negative rot density" is fatal in the reference
+      double rd = (dens_old > RZERO) ? dens_new / dens_old : 1.0;
+      rd *= exp(-p.tau * (vnew - vold));
+      return (rd > 1.0) || (rd > u4);
+   }
+   // rattle-and-shake propagator: the acceptance works on exponents (mc_piqmc.cc:903-921, 1152-1178)
+   double rd;
+   if (KIND == 2) rd = ((rho[2] + rho[3]) - (rho[0] + rho[1])) / (4.0 * (p.rottau / WNO2K));
+   else {
+      double dens_old = rho[0] + rho[1], dens_new = rho[2] + rho[3];
+      if (fabs(dens_old) < RZERO) dens_old = 0.0;
+      if (fabs(dens_new) < RZERO) dens_new = 0.0;
+      rd = dens_new - dens_old;
+   }
+   rd -= p.tau * (vnew - vold);
+   return (rd > 0.0) || (rd > log(u4));
+}
+
+// density factor i of a step at slice q: i = 0 rho(q0 -> cur), 1 rho(cur -> q2), 2 rho(q0 -> new), 3 rho(new -> q2);
+// cur / nw are the orientations of the slice (matrix or unit vector)
+template <int KIND>
+__device__ __forceinline__ double rot_density(const Params &p, const SmallTables &t, int c, int q0, int q2, int m, int i, const double *cur, const double *nw, int *bad)
+{
+   const double *mid = (i < 2) ? cur : nw;
+   if (KIND == 2) {
+      Mat3 A, B;
+      if (i == 0 || i == 2) {
+         load_rotmat(p, c, q0, m, A);
+         #pragma unroll
+         for (int k = 0; k < 9; k++) B.m[k / 3][k % 3] = mid[k];
+      } else {
+         #pragma unroll
+         for (int k = 0; k < 9; k++) A.m[k / 3][k % 3] = mid[k];
+         load_rotmat(p, c, q2, m, B);
+      }
+      if (p.rotden_type == 1) return rsrot(p, A, B, nullptr);
+      int istop = 0;
+      const double r = rotden(p, A, B, nullptr, nullptr, nullptr, nullptr, &istop);
+      if (istop) *bad |= 1;
+      return r;
+   }
+   const int qq = (i == 0 || i == 2) ? q0 : q2;
+   double dot = 0.0;
+   #pragma unroll
+   for (int d = 0; d < 3; d++) {
+      double nb = p.cosn[ang_index(p, c, qq, d, m)];
+      dot += (i == 0 || i == 2) ? nb * mid[d] : mid[d] * nb;
+   }
+   return (p.rotden_type == 1) ? rsline(p, dot, nullptr) : srotdens(p, t, dot);
+}
+
+// state update of an accepted step (mc_piqmc.cc:923-935, 1180-1198)
+template <int KIND>
+__device__ __forceinline__ void rot_commit(const Params &p, int c, int q, int m, double cost, double phi, double chi)
+{
+   p.ang[ang_index(p, c, q, 1, m)] = cost;
+   p.ang[ang_index(p, c, q, 0, m)] = phi;
+   if (KIND == 2) p.ang[ang_index(p, c, q, 2, m)] = chi;
+   const double sint = sqrt(1.0 - cost * cost);
+   double sp_, cp_;
+   sincos(phi, &sp_, &cp_);
+   p.cosn[ang_index(p, c, q, 0, m)] = sint * cp_;
+   p.cosn[ang_index(p, c, q, 1, m)] = sint * sp_;
+   p.cosn[ang_index(p, c, q, 2, m)] = cost;
+}
+
 template <int KIND>
 __device__ void rot_step(const Params &p, Ctx &x, int type, int q, int m, bool active, int *err)
 {
@@ -479,7 +668,6 @@ __device__ void rot_step(const Params &p, Ctx &x, int type, int q, int m, bool a
       double r1 = mrg_u01(rs), r2 = mrg_u01(rs), r3 = mrg_u01(rs), r4 = r3;
       if (KIND == 2) r4 = mrg_u01(rs);
       mrg_store(rs, sp);
-      const double step = p.rtstep[type];
       double cost = p.ang[ang_index(p, c, q, 1, m)], phi = p.ang[ang_index(p, c, q, 0, m)], chi = p.ang[ang_index(p, c, q, 2, m)];
       if (KIND == 2) {
          Mat3 R1;
@@ -490,30 +678,7 @@ __device__ void rot_step(const Params &p, Ctx &x, int type, int q, int m, bool a
          #pragma unroll
          for (int d = 0; d < 3; d++) sl->b[d] = p.cosn[ang_index(p, c, q, d, m)];
       }
-      cost += step * (r1 - 0.5);
-      if (KIND == 2) {
-         phi += 2.0 * PI * (step * (r2 - 0.5));
-         chi += 2.0 * PI * (step * (r3 - 0.5));
-         if (phi < 0.0) phi = 2.0 * PI + phi;
-         if (chi < 0.0) chi = 2.0 * PI + chi;
-         phi = fmod(phi, 2.0 * PI);
-         chi = fmod(chi, 2.0 * PI);
-      } else {
-         phi += step * (r2 - 0.5);
-      }
-      if (cost > 1.0) cost = 2.0 - cost;
-      if (cost < -1.0) cost = -2.0 - cost;
-      if (KIND == 2) {
-         Mat3 Rn;
-         matpre(phi, acos(cost), chi, Rn);
-         #pragma unroll
-         for (int i = 0; i < 9; i++) sl->a[i] = Rn.m[i / 3][i % 3];
-      } else {
-         const double sint = sqrt(1.0 - cost * cost);
-         double sp_, cp_;
-         sincos(phi, &sp_, &cp_);
-         sl->a[0] = sint * cp_; sl->a[1] = sint * sp_; sl->a[2] = cost;
-      }
+      rot_propose<KIND>(p, type, r1, r2, r3, cost, phi, chi, sl->a);
       sl->u4 = r4; sl->cost = cost; sl->phi = phi; sl->chi = chi;
       sl->need_old = (*vep != p.pos_epoch[c]) ? 1 : 0;
       sl->bad = 0;
@@ -524,37 +689,10 @@ __device__ void rot_step(const Params &p, Ctx &x, int type, int q, int m, bool a
 
    double vnew = 0.0, vold = 0.0;
    if (active) {
-      // density factors: i = 0 rho(q0 -> cur), 1 rho(cur -> q2), 2 rho(q0 -> new), 3 rho(new -> q2)
       for (int i = x.gl; i < 4; i += G) {
-         if (KIND == 2) {
-            Mat3 A, B;
-            const double *mid = (i < 2) ? sl->b : sl->a;
-            if (i == 0 || i == 2) {
-               load_rotmat(p, c, q0, m, A);
-               #pragma unroll
-               for (int k = 0; k < 9; k++) B.m[k / 3][k % 3] = mid[k];
-            } else {
-               #pragma unroll
-               for (int k = 0; k < 9; k++) A.m[k / 3][k % 3] = mid[k];
-               load_rotmat(p, c, q2, m, B);
-            }
-            if (p.rotden_type == 1) sl->rho[i] = rsrot(p, A, B, nullptr);
-            else {
-               int istop = 0;
-               sl->rho[i] = rotden(p, A, B, nullptr, nullptr, nullptr, nullptr, &istop);
-               if (istop) { if (G == 1) sl->bad |= 1; else atomicOr(&sl->bad, 1); }
-            }
-         } else {
-            const double *mid = (i < 2) ? sl->b : sl->a;
-            const int qq = (i == 0 || i == 2) ? q0 : q2;
-            double dot = 0.0;
-            #pragma unroll
-            for (int d = 0; d < 3; d++) {
-               double nb = p.cosn[ang_index(p, c, qq, d, m)];
-               dot += (i == 0 || i == 2) ? nb * mid[d] : mid[d] * nb;
-            }
-            sl->rho[i] = (p.rotden_type == 1) ? rsline(p, dot, nullptr) : srotdens(p, x.t, dot);
-         }
+         int bad = 0;
+         sl->rho[i] = rot_density<KIND>(p, x.t, c, q0, q2, m, i, sl->b, sl->a, &bad);
+         if (bad) { if (G == 1) sl->bad |= bad; else atomicOr(&sl->bad, bad); }
       }
       MARK(x, 4);
       vnew = rot_potential<KIND>(p, x, g, q, sl->a);
@@ -576,29 +714,7 @@ __device__ void rot_step(const Params &p, Ctx &x, int type, int q, int m, bool a
       }
       if (!sl->need_old) vold = *vcache;
       int bad = sl->bad;
-      bool acc;
-      if (p.rotden_type == 0) {
-         double dens_old = sl->rho[0] * sl->rho[1], dens_new = sl->rho[2] * sl->rho[3];
-         if (fabs(dens_old) < RZERO) dens_old = 0.0;
-         if (fabs(dens_new) < RZERO) dens_new = 0.0;
-         if (KIND == 2) { dens_old = fabs(dens_old); dens_new = fabs(dens_new); }
-         else if (dens_old < 0.0 || dens_new < 0.0) bad = 2;     // "Negative rot density" is fatal in the reference
-         double rd = (dens_old > RZERO) ? dens_new / dens_old : 1.0;
-         rd *= exp(-p.tau * (vnew - vold));
-         acc = (rd > 1.0) || (rd > sl->u4);
-      } else {
-         // rattle-and-shake propagator: the acceptance works on exponents (mc_piqmc.cc:903-921, 1152-1178)
-         double rd;
-         if (KIND == 2) rd = ((sl->rho[2] + sl->rho[3]) - (sl->rho[0] + sl->rho[1])) / (4.0 * (p.rottau / WNO2K));
-         else {
-            double dens_old = sl->rho[0] + sl->rho[1], dens_new = sl->rho[2] + sl->rho[3];
-            if (fabs(dens_old) < RZERO) dens_old = 0.0;
-            if (fabs(dens_new) < RZERO) dens_new = 0.0;
-            rd = dens_new - dens_old;
-         }
-         rd -= p.tau * (vnew - vold);
-         acc = (rd > 0.0) || (rd > log(sl->u4));
-      }
+      bool acc = rot_accept<KIND>(p, sl->rho, vnew, vold, sl->u4, &bad);
       if (bad) { acc = false; atomicOr(err, bad); }
       double *cn = counter_ptr(p, c, type, 2);
       atomicAdd(cn, 1.0);
@@ -606,22 +722,10 @@ __device__ void rot_step(const Params &p, Ctx &x, int type, int q, int m, bool a
       *vep = p.pos_epoch[c];
       if (acc) {
          atomicAdd(cn + 1, 1.0);
-         p.ang[ang_index(p, c, q, 1, m)] = sl->cost;
-         p.ang[ang_index(p, c, q, 0, m)] = sl->phi;
-         double nn[3];
-         if (KIND == 2) {
-            p.ang[ang_index(p, c, q, 2, m)] = sl->chi;
-            const double sint = sqrt(1.0 - sl->cost * sl->cost);
-            double sp_, cp_;
-            sincos(sl->phi, &sp_, &cp_);
-            nn[0] = sint * cp_; nn[1] = sint * sp_; nn[2] = sl->cost;
+         rot_commit<KIND>(p, c, q, m, sl->cost, sl->phi, sl->chi);
+         if (KIND == 2)
             for (int mm = 0; mm < p.NM; mm++)            // partner rotors at this slice see a new neighbour
                if (mm != m) p.vepoch[((size_t)c * Q + q) * p.NMpad + mm] = -1;
-         } else {
-            nn[0] = sl->a[0]; nn[1] = sl->a[1]; nn[2] = sl->a[2];
-         }
-         #pragma unroll
-         for (int d = 0; d < 3; d++) p.cosn[ang_index(p, c, q, d, m)] = nn[d];
       }
    }
    MARK(x, 7);
@@ -651,9 +755,158 @@ __device__ void rot_sweep(const Params &p, Ctx &x, int type, int *err)
          for (int m = 0; m < p.numb[type]; m++) rot_step<KIND>(p, x, type, q, m, active, err);
       }
       MARK(x, 9);
-      chain_sync(p);
+      chain_sync(p, x);
       MARK(x, 10);
    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// rotational sweep of a ONE-rotor system with an even number of rot slices, software-pipelined over the
+// time steps.  The potential part of a proposal depends on its own slice only (the pair action is diagonal
+// in imaginary time), the accept/reject decision couples a slice to its two neighbours through the density
+// matrix.  Per sweep every rot group first evaluates the potential sums of ALL slices its CTA owns, then
+//   CTAs of even slices: wait until the odd decisions of the PREVIOUS sweep are published, decide, publish;
+//   CTAs of odd slices : wait until the even decisions of THIS sweep are published, decide, publish
+// (per-chain arrival counters in global memory, split arrive / wait).  An even-slice CTA therefore starts the
+// sums of the next time step while the odd slices are still being decided: the chain-wide barriers of the
+// two-phase sweep disappear from the critical path.  Draws per slice and step are those of rot_step, the order
+// of decisions (all even, then all odd) is unchanged, so the trajectory is that of the two-phase sweep.
+// A chain that lives in one CTA (cpc = 1) runs sums | even decisions | odd decisions with CTA barriers.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void rot_arrive(const Params &p, Ctx &x, int parity)
+{
+   __syncthreads();
+   if (x.tid == 0) {
+      __threadfence();
+      atomicAdd(p.barrier + (size_t)x.c * 32 + 8 + 8 * parity, 1u);
+   }
+}
+__device__ __forceinline__ void rot_wait(const Params &p, Ctx &x, int parity, unsigned target)
+{
+   if (x.tid == 0) {
+      unsigned *b = p.barrier + (size_t)x.c * 32 + 8 + 8 * parity, v;
+      do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(b) : "memory"); } while ((int)(v - target) < 0);
+      __threadfence();
+   }
+   __syncthreads();
+}
+
+// decisions of the owned slices of parity `par` (par < 0: all owned slices)
+template <int KIND>
+__device__ __forceinline__ void rot_decide_owned(const Params &p, Ctx &x, int type, int par, int *err)
+{
+   const int c = x.c, Q = p.Q, G = x.G, m = 0;
+   const int nown = (Q + p.cpc - 1) / p.cpc;
+   const int nrounds = (nown + x.ngrp - 1) / x.ngrp;
+   for (int rd = 0; rd < nrounds; rd++) {
+      const int ls = rd * x.ngrp + x.grp;
+      const int q = ls * p.cpc + x.crank;
+      const bool active = ls < nown && q < Q && (par < 0 || (q & 1) == par);
+      RotSlot *sl = x.slot + (ls < nown ? ls : 0);
+      int q0 = q - 1, q2 = q + 1;
+      if (q0 < 0) q0 += Q;
+      if (q2 >= Q) q2 -= Q;
+      if (active)
+         for (int i = x.gl; i < 4; i += G) {
+            int bad = 0;
+            sl->rho[i] = rot_density<KIND>(p, x.t, c, q0, q2, m, i, sl->b, sl->a, &bad);
+            if (bad) { if (G == 1) sl->bad |= bad; else atomicOr(&sl->bad, bad); }
+         }
+      group_sync(x);
+      if (active && x.gl == 0) {
+         int bad = sl->bad;
+         const double vnew = sl->vnew, vold = sl->vold;
+         bool acc = rot_accept<KIND>(p, sl->rho, vnew, vold, sl->u4, &bad);
+         if (bad) { acc = false; atomicOr(err, bad); }
+         double *cn = counter_ptr(p, c, type, 2);
+         atomicAdd(cn, 1.0);
+         p.vold[((size_t)c * Q + q) * p.NMpad + m] = acc ? vnew : vold;
+         p.vepoch[((size_t)c * Q + q) * p.NMpad + m] = p.pos_epoch[c];
+         if (acc) {
+            atomicAdd(cn + 1, 1.0);
+            rot_commit<KIND>(p, c, q, m, sl->cost, sl->phi, sl->chi);
+         }
+      }
+      group_sync(x);
+   }
+}
+
+template <int KIND>
+__device__ void rot_sweep_pipe(const Params &p, Ctx &x, int type, int *err)
+{
+   const int c = x.c, Q = p.Q, G = x.G, m = 0;
+   const int g = p.first[type];
+   const int nown = (Q + p.cpc - 1) / p.cpc;
+   const int nrounds = (nown + x.ngrp - 1) / x.ngrp;
+   MARK(x, 1);
+   for (int rd = 0; rd < nrounds; rd++) {
+      const int ls = rd * x.ngrp + x.grp;
+      const int q = ls * p.cpc + x.crank;
+      const bool active = ls < nown && q < Q;
+      RotSlot *sl = x.slot + (ls < nown ? ls : 0);
+      if (active && x.gl == 0) {
+         Mrg rs;
+         mrg_load(rs, x.rrng + ls * 6);
+         double r1 = mrg_u01(rs), r2 = mrg_u01(rs), r3 = mrg_u01(rs), r4 = r3;
+         if (KIND == 2) r4 = mrg_u01(rs);
+         mrg_store(rs, x.rrng + ls * 6);
+         double cost = p.ang[ang_index(p, c, q, 1, m)], phi = p.ang[ang_index(p, c, q, 0, m)], chi = p.ang[ang_index(p, c, q, 2, m)];
+         if (KIND == 2) {
+            Mat3 R1;
+            matpre(phi, acos(cost), chi, R1);
+            #pragma unroll
+            for (int i = 0; i < 9; i++) sl->b[i] = R1.m[i / 3][i % 3];
+         } else {
+            #pragma unroll
+            for (int d = 0; d < 3; d++) sl->b[d] = p.cosn[ang_index(p, c, q, d, m)];
+         }
+         rot_propose<KIND>(p, type, r1, r2, r3, cost, phi, chi, sl->a);
+         sl->u4 = r4; sl->cost = cost; sl->phi = phi; sl->chi = chi;
+         sl->need_old = (p.vepoch[((size_t)c * Q + q) * p.NMpad + m] != p.pos_epoch[c]) ? 1 : 0;
+         sl->bad = 0;
+      }
+      MARK(x, 2);
+      group_sync(x);
+      MARK(x, 3);
+      double vnew = 0.0, vold = 0.0;
+      if (active) {
+         vnew = rot_potential<KIND>(p, x, g, q, sl->a);
+         if (sl->need_old) vold = rot_potential<KIND>(p, x, g, q, sl->b);
+      }
+      MARK(x, 4);
+      const int gw = (G < 32) ? G : 32;
+      vnew = team_sum(vnew, gw);
+      vold = team_sum(vold, gw);
+      if (G > 32 && (x.tid & 31) == 0) { x.part[2 * (x.gl >> 5)] = vnew; x.part[2 * (x.gl >> 5) + 1] = vold; }
+      group_sync(x);
+      if (active && x.gl == 0) {
+         if (G > 32) {
+            vnew = 0.0; vold = 0.0;
+            for (int w = 0; w < (G >> 5); w++) { vnew += x.part[2 * w]; vold += x.part[2 * w + 1]; }
+         }
+         if (!sl->need_old) vold = p.vold[((size_t)c * Q + q) * p.NMpad + m];
+         sl->vnew = vnew; sl->vold = vold;
+      }
+      group_sync(x);
+   }
+   MARK(x, 5);
+   if (p.cpc == 1) {
+      __syncthreads();
+      rot_decide_owned<KIND>(p, x, type, 0, err);
+      __syncthreads();
+      rot_decide_owned<KIND>(p, x, type, 1, err);
+      __syncthreads();
+   } else {
+      const int par = x.crank & 1, half = p.cpc >> 1;
+      if (par == 0) rot_wait(p, x, 1, (unsigned)(x.rot_iter * half));              // odd decisions of the previous sweep
+      else rot_wait(p, x, 0, (unsigned)((x.rot_iter + 1) * half));                 // even decisions of this sweep
+      MARK(x, 6);
+      rot_decide_owned<KIND>(p, x, type, -1, err);
+      MARK(x, 9);
+      rot_arrive(p, x, par);
+   }
+   x.rot_iter++;
+   MARK(x, 10);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -716,19 +969,38 @@ pimc_steps_kernel(const __grid_constant__ Params p, long t0, long nsteps, int *e
    x.lane_t = x.tid & (x.T - 1);
    x.team_lane0 = (x.tid & 31) & ~(x.T - 1);
    x.team_id = x.gthread / x.T;
+   x.team_cta = x.tid / x.T;
    x.nteams_chain = x.nthreads_chain / x.T;
+   x.W = x.T > 32 ? x.T >> 5 : 1;
+   x.tw = x.T > 32 ? x.lane_t >> 5 : 0;
+   x.wl = x.T > 32 ? (x.tid & 31) : x.lane_t;
+   x.wlanes = x.T > 32 ? 32 : x.T;
    x.G = p.rot_group;
    x.gl = x.tid & (x.G - 1);
    x.grp = x.tid / x.G;
    x.ngrp = blockDim.x / x.G;
+   x.bar_target = 0;
+   x.red_par = 0;
    double *cursor = smem;
    x.red = cursor; cursor += 40;
    stage_tables(p, x.t, cursor);
-   x.team_buf = cursor + (size_t)(x.tid / x.T) * ((p.seg_max + 1) * 6);
-   if (!p.segbuf_global) cursor += (size_t)(blockDim.x / x.T) * ((p.seg_max + 1) * 6);
+   x.team_buf = cursor + (size_t)x.team_cta * p.team_buf_n;
+   if (!p.segbuf_global) cursor += (size_t)(blockDim.x / x.T) * p.team_buf_n;
    x.part = cursor + 2 * (size_t)((x.tid >> 5) - (x.gl >> 5));      // first warp of this thread's rot group
    cursor += 2 * (size_t)(blockDim.x >> 5);
-   x.slot = reinterpret_cast<RotSlot *>(cursor) + x.grp;
+   x.rrng = reinterpret_cast<uint32_t *>(cursor);
+   const bool piped = (KIND != 0) && p.rot_fused && p.Q > 0;
+   const int nown = (p.Q + p.cpc - 1) / p.cpc;
+   x.rot_iter = 0;
+   if (piped) {
+      cursor += (size_t)nown * 3;
+      for (int i = x.tid; i < nown * 6; i += blockDim.x) {
+         const int q = (i / 6) * p.cpc + x.crank;
+         if (q < p.Q) x.rrng[i] = stream_ptr(p, x.c, p.P + q)[i % 6];
+      }
+      __syncthreads();
+      x.slot = reinterpret_cast<RotSlot *>(cursor);                  // one slot per owned slice
+   } else x.slot = reinterpret_cast<RotSlot *>(cursor) + x.grp;      // one slot per rot group
 
    for (long s = 0; s < nsteps; s++) {
       const long t = t0 + s;
@@ -737,7 +1009,23 @@ pimc_steps_kernel(const __grid_constant__ Params p, long t0, long nsteps, int *e
          if (time == 0) molecular_sweep<KIND>(p, x, type);
          const int seg = 1 << p.levels[type], nseg = p.P / seg;
          if (time % nseg == 0) bisection_sweep<KIND>(p, x, type, (time / nseg) % p.P);
-         if (KIND != 0 && type == p.imtype && p.Q > 0) rot_sweep<KIND>(p, x, type, err);
+         if (KIND != 0 && type == p.imtype && p.Q > 0) {
+            if (piped) {
+               rot_sweep_pipe<KIND>(p, x, type, err);
+               // a translational sweep (or the end of the launch) needs every decision of this sweep: full barrier
+               bool full = (s == nsteps - 1) || type != p.ntypes - 1;
+               const int tn = (int)((t + 1) % p.P);
+               for (int ty = 0; ty < p.ntypes; ty++) full |= (tn % (p.P >> p.levels[ty]) == 0);
+               if (full && p.cpc > 1) chain_sync(p, x);
+            } else rot_sweep<KIND>(p, x, type, err);
+         }
+      }
+   }
+   if (piped) {
+      __syncthreads();
+      for (int i = x.tid; i < nown * 6; i += blockDim.x) {
+         const int q = (i / 6) * p.cpc + x.crank;
+         if (q < p.Q) stream_ptr(p, x.c, p.P + q)[i % 6] = x.rrng[i];
       }
    }
 }

@@ -178,10 +178,12 @@ size_t smem_bytes(const Params &p, int threads)
    if (p.n1d) d += pad((p.n1d - 1) * (int)(sizeof(SplineRec) / sizeof(double))) + padi(p.nlut1d);
    if (p.rs2d) d += 2 * (size_t)(p.rs2d + p.cs2d);
    if (p.nrot && p.rot_in_smem) d += pad((p.nrot - 1) * (int)(sizeof(SplineRec) / sizeof(double))) + padi(p.nlutrot);
-   if (!p.segbuf_global) d += (size_t)(threads / p.team) * ((p.seg_max + 1) * 6);
+   if (!p.segbuf_global) d += (size_t)(threads / p.team) * p.team_buf_n;
    d += 2 * (size_t)(threads / 32);
+   if (p.rot_fused) d += 3 * (size_t)((p.Q + p.cpc - 1) / p.cpc);
    size_t bytes = d * sizeof(double);
-   if (p.rot_group > 1) bytes += (size_t)(threads / p.rot_group) * sizeof(RotSlot);
+   if (p.rot_fused) bytes += (size_t)((p.Q + p.cpc - 1) / p.cpc) * sizeof(RotSlot);
+   else if (p.rot_group > 1) bytes += (size_t)(threads / p.rot_group) * sizeof(RotSlot);
    return bytes;
 }
 
@@ -399,21 +401,27 @@ int pimcgpu_init(const pimcgpu_system *sys, const pimcgpu_tables *tab)
    int seg_max = 1, seg_min = 1 << 30;
    for (int t = 0; t < p.ntypes; t++) { seg_max = std::max(seg_max, 1 << p.levels[t]); seg_min = std::min(seg_min, 1 << p.levels[t]); }
    p.seg_max = seg_max;
+   p.team_buf_n = team_buf_doubles(seg_max);
+   // one rotor: the potential sums of all Q proposals are one parallel stage (rot_sweep_fused)
+   p.rot_fused = (p.Q > 0 && p.NM == 1 && p.Q % 2 == 0) ? 1 : 0;
+   if (getenv("PIMC_NO_FUSED_ROT")) p.rot_fused = 0;
+   const int rot_units = p.rot_fused ? p.Q : p.Q / 2;          // rot slices that are independent within one stage
    int team = sys->team;
    if (team <= 0) team = pow2ceil(std::min(32, std::max(1, p.R * (p.N - 1) / 2)));
-   team = std::min(32, pow2floor(std::max(1, team)));
-   int units = std::max(p.Q / 2, p.P / seg_min);           // widest stage: rot slices of one parity / segments of one atom
-   long want = (long)units * team;
+   team = std::min(128, pow2floor(std::max(1, team)));
+   const int nseg_widest = p.P / seg_min;
+   int units = std::max(rot_units, nseg_widest);              // widest stage: rot slices / segments of one atom
+   const long rot_work = (long)rot_units * p.R * std::max(1, p.N - 1);                 // pair terms of one rotational stage
+   const long bis_work = (long)nseg_widest * (seg_min - 1) * 2 * std::max(1, p.N - 1); // pair terms of one atom's bisection
+   long want = std::max<long>((long)units * team, std::max(rot_work / 4, bis_work / 8));
    int threads = sys->threads_per_cta, cpc = sys->ctas_per_chain;
    if (cpc <= 0) {
-      // enough CTAs for one thread per partner term of the widest rotational phase (or per segment lane), but never
-      // more clusters x CTAs than the 148 SMs can hold at once, and at most 16 CTAs per cluster
-      long rot_work = (long)(p.Q / 2) * p.R * std::max(1, p.N - 1);
-      long useful = (std::max(want, rot_work) + 511) / 512;
+      // enough CTAs for a few pair terms per thread in the widest stage, but never more CTAs than the 148 SMs can hold
+      // at once.  Up to 8 CTAs per chain form a cluster; 16 CTAs per chain run as a cooperative grid with a software
+      // chain barrier, because only seven 16-CTA clusters fit on a B200 at once (cudaOccupancyMaxActiveClusters)
+      long useful = (want + 511) / 512;
       long fit = std::max(1, 148 / std::max(1, p.nchains));
-      // clusters of 16 are allowed by the hardware but only ~7 of them fit on a B200 at once (measured with
-      // cudaOccupancyMaxActiveClusters), so the automatic choice stops at the portable size 8
-      cpc = (int)std::max<long>(1, std::min<long>(8, std::min(useful, fit)));
+      cpc = (int)std::max<long>(1, std::min<long>(16, std::min(useful, fit)));
       while (cpc & (cpc - 1)) cpc &= cpc - 1;                 // power of two
    }
    if (threads <= 0) {
@@ -421,11 +429,18 @@ int pimcgpu_init(const pimcgpu_system *sys, const pimcgpu_tables *tab)
       threads = (int)std::min<long>(512, std::max<long>(64, ((per + 31) / 32) * 32));
    }
    if (threads % 32 || threads > PIMC_MAX_THREADS || threads < 32) return fail("pimcgpu_init: threads_per_cta must be a multiple of 32 in [32,%d]", PIMC_MAX_THREADS);
-   if (cpc > 16) return fail("pimcgpu_init: ctas_per_chain must be <= 16");
+   if (cpc > 16 || (cpc & (cpc - 1))) return fail("pimcgpu_init: ctas_per_chain must be a power of two <= 16");
+   if (sys->team <= 0) {
+      // more threads than one team per segment can use: widen the teams (several warps per segment)
+      while (team < 128 && (long)cpc * threads / team >= 2L * nseg_widest && std::max(1, p.N - 1) >= 2 * team && 2 * team <= threads) team *= 2;
+   }
+   if (team > threads) team = pow2floor(threads);
+   if (team > 32 && threads / team > 15) return fail("pimcgpu_init: a team wider than a warp needs at most 15 teams per CTA");
    p.team = team; p.cpc = cpc;
-   // rot group: the threads of a CTA are split evenly over the slices it owns in one parity phase
+   p.swbar = (cpc > 8 || getenv("PIMC_SWBAR")) && cpc > 1 ? 1 : 0;
+   // rot group: the threads of a CTA are split evenly over the slices it owns in one stage
    {
-      int count = std::max(1, (p.Q + 1) / 2);
+      int count = std::max(1, p.rot_fused ? p.Q : (p.Q + 1) / 2);
       int per_cta = (count + cpc - 1) / cpc;
       int rg = pow2floor(std::max(1, threads / std::max(1, std::min(per_cta, threads))));
       long work = (long)p.R * std::max(1, p.N - 1);           // partner terms of one rot step
@@ -433,17 +448,30 @@ int pimcgpu_init(const pimcgpu_system *sys, const pimcgpu_tables *tab)
       p.rot_group = std::min(rg, threads);
    }
    G.threads = threads;
-   p.nseg_max = p.P / seg_min;
-   p.segbuf_global = ((size_t)(threads / team) * ((seg_max + 1) * 6) * sizeof(double) > 64 * 1024) ? 1 : 0;
-   if (p.segbuf_global && dalloc(&p.segbuf, C * p.nseg_max * ((seg_max + 1) * 6))) return 1;
+   {
+      const int nteams = cpc * threads / team;
+      p.nseg_max = ((nseg_widest + nteams - 1) / nteams) * nteams;       // whole rounds: every team of a round has its own buffer
+   }
    p.rot_in_smem = 1;
+   p.segbuf_global = 0;
    if (smem_bytes(p, threads) > 200 * 1024) p.rot_in_smem = 0;
+   if (smem_bytes(p, threads) > 200 * 1024) { p.rot_in_smem = 1; p.segbuf_global = 1; }
+   if (smem_bytes(p, threads) > 200 * 1024) p.rot_in_smem = 0;
+   if (p.segbuf_global && dalloc(&p.segbuf, C * p.nseg_max * p.team_buf_n)) return 1;
+   if (dalloc(&p.barrier, C * 32)) return 1;
    G.smem = smem_bytes(p, threads);
    if (G.smem > 227 * 1024) return fail("pimcgpu_init: %zu bytes of shared memory per CTA exceed the 227 KB limit", G.smem);
    G.kind = p.imtype >= 0 && p.Q > 0 ? p.molecule[p.imtype] : (p.imtype >= 0 ? p.molecule[p.imtype] : 0);
    const void *kfun = G.kind == 2 ? (const void *)pimc_steps_kernel<2> : G.kind == 1 ? (const void *)pimc_steps_kernel<1> : (const void *)pimc_steps_kernel<0>;
    CK(cudaFuncSetAttribute(kfun, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
-   if (cpc > 8) CK(cudaFuncSetAttribute(kfun, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+   if (p.swbar) {
+      int per_sm = 0;
+      cudaDeviceProp prop;
+      CK(cudaGetDeviceProperties(&prop, sys->device));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfun, threads, G.smem));
+      if ((long)per_sm * prop.multiProcessorCount < (long)p.nchains * cpc)
+         return fail("pimcgpu_init: %d chains x %d CTAs cannot be co-resident on %d SMs (needed by the software chain barrier)", p.nchains, cpc, prop.multiProcessorCount);
+   }
    // ---- estimator buffers / accumulator layout ----
    EstBuffers &e = G.e;
    memset(&e, 0, sizeof e);
@@ -599,20 +627,32 @@ int pimcgpu_seed(const unsigned long seed6[6])
    return 0;
 }
 
+static void launch_config(cudaLaunchConfig_t &cfg, cudaLaunchAttribute *attr)
+{
+   cfg = cudaLaunchConfig_t{};
+   cfg.gridDim = dim3(G.p.nchains * G.p.cpc);
+   cfg.blockDim = dim3(G.threads);
+   cfg.dynamicSmemBytes = G.smem;
+   cfg.stream = G.stream;
+   if (G.p.swbar) {
+      attr[0].id = cudaLaunchAttributeCooperative;           // all CTAs co-resident: the software chain barrier spins
+      attr[0].val.cooperative = 1;
+   } else {
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = G.p.cpc; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+   }
+   cfg.attrs = attr; cfg.numAttrs = 1;
+}
+
 int pimcgpu_steps(long nsteps)
 {
    if (!G.live) return fail("pimcgpu_steps: not initialised");
    if (!G.seeded) return fail("pimcgpu_steps: call pimcgpu_seed first");
    if (nsteps <= 0) return 0;
-   cudaLaunchConfig_t cfg = {};
-   cfg.gridDim = dim3(G.p.nchains * G.p.cpc);
-   cfg.blockDim = dim3(G.threads);
-   cfg.dynamicSmemBytes = G.smem;
-   cfg.stream = G.stream;
+   cudaLaunchConfig_t cfg;
    cudaLaunchAttribute attr[1];
-   attr[0].id = cudaLaunchAttributeClusterDimension;
-   attr[0].val.clusterDim.x = G.p.cpc; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-   cfg.attrs = attr; cfg.numAttrs = 1;
+   launch_config(cfg, attr);
+   if (G.p.cpc > 1) CK(cudaMemsetAsync(G.p.barrier, 0, (size_t)G.p.nchains * 32 * sizeof(unsigned), G.stream));
    if (G.kind == 2) CK(cudaLaunchKernelEx(&cfg, pimc_steps_kernel<2>, G.p, G.step, nsteps, G.d_err));
    else if (G.kind == 1) CK(cudaLaunchKernelEx(&cfg, pimc_steps_kernel<1>, G.p, G.step, nsteps, G.d_err));
    else CK(cudaLaunchKernelEx(&cfg, pimc_steps_kernel<0>, G.p, G.step, nsteps, G.d_err));
@@ -637,15 +677,18 @@ int pimcgpu_geometry(int *out8)
 {
    if (!G.live) return fail("pimcgpu_geometry: not initialised");
    out8[0] = G.p.cpc; out8[1] = G.threads; out8[2] = G.p.team; out8[3] = G.p.rot_group; out8[4] = (int)G.smem; out8[5] = G.kind;
-   cudaLaunchConfig_t cfg = {};
-   cfg.gridDim = dim3(G.p.nchains * G.p.cpc); cfg.blockDim = dim3(G.threads); cfg.dynamicSmemBytes = G.smem;
+   cudaLaunchConfig_t cfg;
    cudaLaunchAttribute attr[1];
-   attr[0].id = cudaLaunchAttributeClusterDimension;
-   attr[0].val.clusterDim.x = G.p.cpc; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-   cfg.attrs = attr; cfg.numAttrs = 1;
+   launch_config(cfg, attr);
    int nclusters = -1;
    const void *kfun = G.kind == 2 ? (const void *)pimc_steps_kernel<2> : G.kind == 1 ? (const void *)pimc_steps_kernel<1> : (const void *)pimc_steps_kernel<0>;
-   if (cudaOccupancyMaxActiveClusters(&nclusters, kfun, &cfg) != cudaSuccess) { nclusters = -1; cudaGetLastError(); }
+   if (G.p.swbar) {
+      int per_sm = 0, dev = 0;
+      cudaDeviceProp prop;
+      cudaGetDevice(&dev);
+      if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfun, G.threads, G.smem) == cudaSuccess)
+         nclusters = per_sm * prop.multiProcessorCount / G.p.cpc;          // chains that can be co-resident
+   } else if (cudaOccupancyMaxActiveClusters(&nclusters, kfun, &cfg) != cudaSuccess) { nclusters = -1; cudaGetLastError(); }
    out8[6] = nclusters; out8[7] = G.p.nchains;
    return 0;
 }

@@ -256,7 +256,9 @@ def test_geometry_independence(pkg):
     seed = (12345,) * 6
     ref = None
     for kw in (dict(), dict(ctas_per_chain=1, threads_per_cta=64, team=4), dict(ctas_per_chain=2, threads_per_cta=128, team=32),
-               dict(ctas_per_chain=4, threads_per_cta=32, team=8)):
+               dict(ctas_per_chain=4, threads_per_cta=32, team=8),
+               dict(ctas_per_chain=16, threads_per_cta=128, team=64),          # cooperative grid + software chain barrier, two-warp teams
+               dict(ctas_per_chain=2, threads_per_cta=256, team=128)):
         G = pkg.gpu.PimcGpu(cfg, nchains=2, **kw)
         G.seed(seed)
         G.steps(cfg.system.P + 5)
