@@ -26,7 +26,7 @@ constexpr double WNO2K = 0.6950356;               // rotden.f:6, mc_const.h:15
 enum Mode : int { M_SPOT1D = 0, M_LIN_0MOL = 1, M_LIN_1MOL = 2, M_TOP_0MOL = 3, M_TOP_1MOL = 4, M_SPHER = 5, M_TOPTOP = 6 };
 
 // one spline interval [xlo, xhi]: everything splint (mc_utils.cc:156-186) needs, with 1/h and y''h^2/6 folded in
-struct SplineRec { double xlo, xhi, inv_h, ylo, yhi, clo, chi; };
+struct alignas(16) SplineRec { double xlo, xhi, inv_h, ylo, yhi, clo, chi, pad; };      // 64 bytes: four 128-bit shared-memory loads
 
 struct Params {
    int ntypes, N, P, Q, R, Npad, NM, NMpad;
@@ -41,6 +41,7 @@ struct Params {
    int mode[MAXT][MAXT];
    // tables
    int n1d, nlut1d;  const double *g1d, *v1d, *y2_1d; const int *lut1d; double alpha, unode, c6, lut1d_scale;
+   int uniform1d; double x0_1d, xn_1d, invh_1d;      // 1-D grid end points; uniform grid: interval index = (r - x0)/h directly
    const SplineRec *rec1d;       // packed per-interval records of the 1-D potential spline
    int rs2d, cs2d;   const double *rg2d, *cg2d, *v2d; double dr2d, dc2d;
    const double *irg2d, *icg2d;  // 1/(grid[i+1]-grid[i]) of the 2-D potential axes
@@ -185,6 +186,48 @@ __device__ __forceinline__ double spot1d(const Params &p, const SmallTables &t, 
    if (r >= xn) return -p.c6 / pow(r, 6.0);
    if (r <= x0) return p.unode * exp(-p.alpha * r);
    return spline_rec_eval(t.rec1d, n, t.lut1d, p.nlut1d, p.lut1d_scale, x0, r, klo_out);
+}
+
+// SPot1D inside the move kernel.  The two extrapolation branches (beyond either end of the grid, rare) are kept out of
+// line; the interval is guessed from the uniform-grid quotient or the bucket table and checked against the record, so
+// it is always the reference's klo = max{k : x_k <= r}.
+__device__ __noinline__ double spot1d_tail(const Params &p, double r)
+{
+   if (r >= p.xn_1d) return -p.c6 / pow(r, 6.0);
+   return p.unode * exp(-p.alpha * r);
+}
+__device__ __forceinline__ double spot1d_move(const Params &p, const SmallTables &t, double r)
+{
+   const int n = p.n1d;
+   if (__builtin_expect(!(r < p.xn_1d && r > p.x0_1d), 0)) return spot1d_tail(p, r);
+   int k;
+   if (p.uniform1d) k = min((int)((r - p.x0_1d) * p.invh_1d), n - 2);
+   else {
+      int b = (int)((r - p.x0_1d) * p.lut1d_scale);
+      k = t.lut1d[min(b, p.nlut1d - 1)];
+   }
+   const SplineRec *rec = t.rec1d;
+   SplineRec rc = rec[k];
+   if (__builtin_expect(!(rc.xlo <= r && r < rc.xhi), 0)) {
+      while (k < n - 2 && rec[k].xhi <= r) k++;
+      while (k > 0 && rec[k].xlo > r) k--;
+      rc = rec[k];
+   }
+   const double a = (rc.xhi - r) * rc.inv_h, bb = (r - rc.xlo) * rc.inv_h;
+   return a * rc.ylo + bb * rc.yhi + ((a * a * a - a) * rc.clo + (bb * bb * bb - bb) * rc.chi);
+}
+
+// Branch-free form for batches of independent evaluations on a (quasi-)uniform grid: value from the guessed interval,
+// `bad` set when the guess is not the reference's interval or r lies beyond the grid; the caller then redoes the batch
+// with spot1d_move.  No data-dependent branch, so the evaluations of a batch interleave in the pipeline.
+__device__ __forceinline__ double spot1d_try(const Params &p, const SmallTables &t, double r, bool &bad)
+{
+   int k = (int)((r - p.x0_1d) * p.invh_1d);
+   k = max(0, min(k, p.n1d - 2));
+   const SplineRec rc = t.rec1d[k];
+   bad |= !(rc.xlo <= r && r < rc.xhi && r > p.x0_1d);
+   const double a = (rc.xhi - r) * rc.inv_h, bb = (r - rc.xlo) * rc.inv_h;
+   return a * rc.ylo + bb * rc.yhi + ((a * a * a - a) * rc.clo + (bb * bb * bb - bb) * rc.chi);
 }
 
 // floor(x/delta) by true division: the rare exact path of lpot2d's index selection, kept out of line so ptxas does

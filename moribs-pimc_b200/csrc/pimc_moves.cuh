@@ -39,7 +39,8 @@ __device__ int g_nmarks;
 #define MARK(x, id) do { } while (0)
 #endif
 
-constexpr int TEAM_EXTRA = 8;     // doubles per team behind the segment buffers: per-warp partial sums + accept flag
+constexpr int MAXLEV = 8;         // bisection levels supported by the per-team scratch
+constexpr int TEAM_EXTRA = 4 + MAXLEV + 3 * MAXLEV;   // doubles per team behind the segment buffers: per-warp partial sums, candidate accept uniforms and their stream states
 
 // per rot group scratch in shared memory
 struct RotSlot {
@@ -48,6 +49,9 @@ struct RotSlot {
    double a[9], b[9];         // KIND 2: rotation matrices of the new (a) and current (b) orientation; KIND 1: a[0..2] = n_new, b[0..2] = n_cur
    double rho[4];             // the four density-matrix factors
    double vnew, vold;         // potential sums of the proposed / current orientation (pipelined sweep)
+   double cur[3];             // pipelined sweep: current (cost, phi, chi) of the owned slice, kept across time steps
+   double vcache;             // pipelined sweep: cached potential sum of the current orientation ...
+   int vep, epoch;            // ... the position epoch it belongs to, and the epoch seen by the current sweep
    int need_old, bad;
 };
 
@@ -135,7 +139,7 @@ __device__ __forceinline__ double pair_diff(const Params &p, const SmallTables &
          d2n += (pn[d] - pj) * (pn[d] - pj);
          d2o += (po[d] - pj) * (po[d] - pj);
       }
-      return spot1d(p, t, sqrt(d2n)) - spot1d(p, t, sqrt(d2o));
+      return spot1d_move(p, t, sqrt(d2n)) - spot1d_move(p, t, sqrt(d2o));
    }
    if (KIND == 1 && p.mode[type_of(p, g)][type_of(p, j)] == M_LIN_1MOL && !p.minimage) {
       // atom bead (new and old position) against the linear rotor: shared partner loads, both bilinear forms in flight
@@ -182,17 +186,24 @@ __device__ __forceinline__ double partner_sum_diff(const Params &p, const SmallT
          for (int u = 0; u < 4; u++) {
             const int j = j0 + u * stride;
             ok[u] = j < jb && j != g;
-            const int jj = ok[u] ? j : ja;
+            const int jj = ok[u] ? j : (g == ja ? ja + 1 : ja);     // masked slots: any atom other than g (a real distance)
             const double qx = px[jj], qy = py[jj], qz = pz[jj];
             double inv_;
             fast_r_invr((pn[0] - qx) * (pn[0] - qx) + (pn[1] - qy) * (pn[1] - qy) + (pn[2] - qz) * (pn[2] - qz), rn[u], inv_);
             fast_r_invr((po[0] - qx) * (po[0] - qx) + (po[1] - qy) * (po[1] - qy) + (po[2] - qz) * (po[2] - qz), ro[u], inv_);
          }
-         #pragma unroll
-         for (int u = 0; u < 4; u++) {
-            double e = spot1d(p, t, rn[u]) - spot1d(p, t, ro[u]);
-            D += ok[u] ? e : 0.0;
+         double e[4];
+         bool bad = !p.uniform1d;
+         if (p.uniform1d) {
+            #pragma unroll
+            for (int u = 0; u < 4; u++) e[u] = spot1d_try(p, t, rn[u], bad) - spot1d_try(p, t, ro[u], bad);
          }
+         if (__builtin_expect(bad, 0)) {
+            #pragma unroll
+            for (int u = 0; u < 4; u++) e[u] = spot1d_move(p, t, rn[u]) - spot1d_move(p, t, ro[u]);
+         }
+         #pragma unroll
+         for (int u = 0; u < 4; u++) D += ok[u] ? e[u] : 0.0;
       }
       return D;
    }
@@ -330,7 +341,8 @@ __device__ void bisection_sweep(const Params &p, Ctx &x, int type, int off)
       double *xi = nx + (p.seg_max + 1) * 3;
       uint32_t *rc = reinterpret_cast<uint32_t *>(nx + (p.seg_max + 1) * 6);       // streams of slices s0 .. s0+seg-1, cached for the sweep
       double *tred = nx + (p.seg_max + 1) * 6 + p.seg_max * 3;
-      int *tflag = reinterpret_cast<int *>(tred + 4);
+      double *ucand = tred + 4;                                                  // next L uniforms of the segment's accept stream ...
+      uint32_t *cst = reinterpret_cast<uint32_t *>(tred + 4 + MAXLEV);           // ... and the stream state after each of them
       if (active)
          for (int i = x.lane_t; i < seg * 6; i += T) rc[i] = stream_ptr(p, c, (s0 + i / 6) % P)[i % 6];
       team_sync(x);
@@ -343,6 +355,18 @@ __device__ void bisection_sweep(const Params &p, Ctx &x, int type, int off)
                int g = (s0 + t >= P) ? gB : gA;
                nx[t * 3 + d] = p.pos[pos_index(p, c, (s0 + t) % P, d, g)];
             }
+         // candidate uniforms of the level tests (stream of slice s0): drawn ahead by the lanes that idle below, consumed
+         // only where a level needs one (delta >= 0), the stream is advanced by the number actually used
+         if (active)
+            for (int k = T - 1 - x.lane_t; k < L; k += T) {
+               Mrg rs;
+               mrg_load(rs, rc);
+               double u = 0.0;
+               for (int j = 0; j <= k; j++) u = mrg_u01(rs);
+               ucand[k] = u;
+               mrg_store(rs, cst + k * 6);
+            }
+         int used = 0;
          // unit normals for all interior slices of the segment, drawn up front from the slices' own streams
          // (6 uniforms per slice: gauss() of mc_randg.cc:138-150 per dimension)
          MARK(x, 20);
@@ -379,8 +403,10 @@ __device__ void bisection_sweep(const Params &p, Ctx &x, int type, int off)
             double D = 0.0;
             if (alive && fast_atoms<KIND>(p, type)) {
                // the partners that are not atoms of this type (the rotor): one lane per (midpoint, partner)
+               // (dealt from the top lane down, spread over the team: the low lanes carry the most atom partners)
                const int nother = N - p.numb[type];
-               for (int i = x.lane_t; i < nmid * nother; i += T) {
+               const int nt = nmid * nother, sdeal = max(1, T / max(1, nt)), rl = T - 1 - x.lane_t;
+               for (int i = (rl % sdeal == 0) ? rl / sdeal : nt; i < nt; i += (T + sdeal - 1) / sdeal) {
                   const int m = i / nother, jo = i - m * nother;
                   const int j = (jo < base) ? jo : jo + p.numb[type];
                   const int t1 = half + m * lss;
@@ -410,22 +436,9 @@ __device__ void bisection_sweep(const Params &p, Ctx &x, int type, int off)
             D = team_reduce(x, D, tred);
             const double deltav = (D - S) * (p.tau * (double)half);
             S += D;
+            // every lane holds the same D (symmetric butterfly, fixed-order combine), so the test needs no broadcast
             int acc = 1;
-            if (alive && x.lane_t == 0) {
-               if (!(deltav < 0.0)) {
-                  Mrg rs;
-                  mrg_load(rs, rc);
-                  double u = mrg_u01(rs);
-                  mrg_store(rs, rc);
-                  acc = (exp(-deltav) > u) ? 1 : 0;
-               }
-            }
-            if (W == 1) acc = __shfl_sync(0xffffffffu, acc, x.team_lane0);
-            else {
-               if (x.lane_t == 0) *tflag = acc;
-               team_sync(x);
-               acc = *tflag;
-            }
+            if (alive && !(deltav < 0.0)) { acc = (exp(-deltav) > ucand[used]) ? 1 : 0; used++; }
             if (!acc) alive = false;
             MARK(x, 23);
          }
@@ -440,6 +453,8 @@ __device__ void bisection_sweep(const Params &p, Ctx &x, int type, int off)
                int g = (s0 + t >= P) ? gB : gA;
                p.pos[pos_index(p, c, (s0 + t) % P, d, g)] = nx[t * 3 + d];
             }
+         if (active && used > 0)
+            for (int i = x.lane_t; i < 6; i += T) rc[i] = cst[(used - 1) * 6 + i];
          team_sync(x);
          MARK(x, 24);
       }
@@ -820,11 +835,14 @@ __device__ __forceinline__ void rot_decide_owned(const Params &p, Ctx &x, int ty
          if (bad) { acc = false; atomicOr(err, bad); }
          double *cn = counter_ptr(p, c, type, 2);
          atomicAdd(cn, 1.0);
-         p.vold[((size_t)c * Q + q) * p.NMpad + m] = acc ? vnew : vold;
-         p.vepoch[((size_t)c * Q + q) * p.NMpad + m] = p.pos_epoch[c];
+         sl->vcache = acc ? vnew : vold;
+         sl->vep = sl->epoch;
          if (acc) {
             atomicAdd(cn + 1, 1.0);
             rot_commit<KIND>(p, c, q, m, sl->cost, sl->phi, sl->chi);
+            sl->cur[0] = sl->cost; sl->cur[1] = sl->phi; sl->cur[2] = sl->chi;
+            #pragma unroll
+            for (int i = 0; i < (KIND == 2 ? 9 : 3); i++) sl->b[i] = sl->a[i];
          }
       }
       group_sync(x);
@@ -850,19 +868,12 @@ __device__ void rot_sweep_pipe(const Params &p, Ctx &x, int type, int *err)
          double r1 = mrg_u01(rs), r2 = mrg_u01(rs), r3 = mrg_u01(rs), r4 = r3;
          if (KIND == 2) r4 = mrg_u01(rs);
          mrg_store(rs, x.rrng + ls * 6);
-         double cost = p.ang[ang_index(p, c, q, 1, m)], phi = p.ang[ang_index(p, c, q, 0, m)], chi = p.ang[ang_index(p, c, q, 2, m)];
-         if (KIND == 2) {
-            Mat3 R1;
-            matpre(phi, acos(cost), chi, R1);
-            #pragma unroll
-            for (int i = 0; i < 9; i++) sl->b[i] = R1.m[i / 3][i % 3];
-         } else {
-            #pragma unroll
-            for (int d = 0; d < 3; d++) sl->b[d] = p.cosn[ang_index(p, c, q, d, m)];
-         }
+         const int epoch = p.pos_epoch[c];
+         double cost = sl->cur[0], phi = sl->cur[1], chi = sl->cur[2];     // current state and orientation live in the slot
          rot_propose<KIND>(p, type, r1, r2, r3, cost, phi, chi, sl->a);
          sl->u4 = r4; sl->cost = cost; sl->phi = phi; sl->chi = chi;
-         sl->need_old = (p.vepoch[((size_t)c * Q + q) * p.NMpad + m] != p.pos_epoch[c]) ? 1 : 0;
+         sl->epoch = epoch;
+         sl->need_old = (sl->vep != epoch) ? 1 : 0;
          sl->bad = 0;
       }
       MARK(x, 2);
@@ -884,7 +895,7 @@ __device__ void rot_sweep_pipe(const Params &p, Ctx &x, int type, int *err)
             vnew = 0.0; vold = 0.0;
             for (int w = 0; w < (G >> 5); w++) { vnew += x.part[2 * w]; vold += x.part[2 * w + 1]; }
          }
-         if (!sl->need_old) vold = p.vold[((size_t)c * Q + q) * p.NMpad + m];
+         if (!sl->need_old) vold = sl->vcache;
          sl->vnew = vnew; sl->vold = vold;
       }
       group_sync(x);
@@ -943,10 +954,12 @@ __device__ __forceinline__ void stage_tables(const Params &p, SmallTables &t, do
       for (int i = threadIdx.x; i < nd; i += blockDim.x) cursor[i] = src[i];
       t.rec1d = reinterpret_cast<const SplineRec *>(cursor);
       cursor += (nd + 1) & ~1;
-      int *li = reinterpret_cast<int *>(cursor);
-      for (int i = threadIdx.x; i < p.nlut1d; i += blockDim.x) li[i] = p.lut1d[i];
-      t.lut1d = li;
-      cursor += ((p.nlut1d + 1) / 2 + 1) & ~1;
+      if (!p.uniform1d) {
+         int *li = reinterpret_cast<int *>(cursor);
+         for (int i = threadIdx.x; i < p.nlut1d; i += blockDim.x) li[i] = p.lut1d[i];
+         t.lut1d = li;
+         cursor += ((p.nlut1d + 1) / 2 + 1) & ~1;
+      }
    }
    __syncthreads();
 }
@@ -998,27 +1011,52 @@ pimc_steps_kernel(const __grid_constant__ Params p, long t0, long nsteps, int *e
          const int q = (i / 6) * p.cpc + x.crank;
          if (q < p.Q) x.rrng[i] = stream_ptr(p, x.c, p.P + q)[i % 6];
       }
-      __syncthreads();
       x.slot = reinterpret_cast<RotSlot *>(cursor);                  // one slot per owned slice
+      for (int ls = x.tid; ls < nown; ls += blockDim.x) {
+         const int q = ls * p.cpc + x.crank;
+         if (q >= p.Q) continue;
+         RotSlot *sl = x.slot + ls;
+         const double phi = p.ang[ang_index(p, x.c, q, 0, 0)], cost = p.ang[ang_index(p, x.c, q, 1, 0)], chi = p.ang[ang_index(p, x.c, q, 2, 0)];
+         sl->cur[0] = cost; sl->cur[1] = phi; sl->cur[2] = chi;
+         if (KIND == 2) {
+            Mat3 R1;
+            matpre(phi, acos(cost), chi, R1);
+            for (int i = 0; i < 9; i++) sl->b[i] = R1.m[i / 3][i % 3];
+         } else {
+            for (int d = 0; d < 3; d++) sl->b[d] = p.cosn[ang_index(p, x.c, q, d, 0)];
+         }
+         sl->vcache = p.vold[((size_t)x.c * p.Q + q) * p.NMpad];
+         sl->vep = p.vepoch[((size_t)x.c * p.Q + q) * p.NMpad];
+      }
+      __syncthreads();
    } else x.slot = reinterpret_cast<RotSlot *>(cursor) + x.grp;      // one slot per rot group
 
+   // time = t mod P and, per type, time mod (P/seg) and time / (P/seg), advanced incrementally (no divisions in the loop)
+   int time = (int)(t0 % p.P), tmod[MAXT], toff[MAXT], tnseg[MAXT];
+   for (int type = 0; type < p.ntypes; type++) {
+      tnseg[type] = p.P / (1 << p.levels[type]);
+      tmod[type] = time % tnseg[type];
+      toff[type] = time / tnseg[type];
+   }
    for (long s = 0; s < nsteps; s++) {
-      const long t = t0 + s;
-      const int time = (int)(t % p.P);
+      // does the NEXT step start with a translational sweep?  (decided before this step's rotational sweep runs ahead)
+      bool next_trans = false;
+      for (int type = 0; type < p.ntypes; type++) next_trans |= (tmod[type] + 1 == tnseg[type]) || (time + 1 == p.P);
       for (int type = 0; type < p.ntypes; type++) {
          if (time == 0) molecular_sweep<KIND>(p, x, type);
-         const int seg = 1 << p.levels[type], nseg = p.P / seg;
-         if (time % nseg == 0) bisection_sweep<KIND>(p, x, type, (time / nseg) % p.P);
+         if (tmod[type] == 0) bisection_sweep<KIND>(p, x, type, toff[type]);
          if (KIND != 0 && type == p.imtype && p.Q > 0) {
             if (piped) {
                rot_sweep_pipe<KIND>(p, x, type, err);
                // a translational sweep (or the end of the launch) needs every decision of this sweep: full barrier
-               bool full = (s == nsteps - 1) || type != p.ntypes - 1;
-               const int tn = (int)((t + 1) % p.P);
-               for (int ty = 0; ty < p.ntypes; ty++) full |= (tn % (p.P >> p.levels[ty]) == 0);
-               if (full && p.cpc > 1) chain_sync(p, x);
+               if ((s == nsteps - 1 || type != p.ntypes - 1 || next_trans) && p.cpc > 1) chain_sync(p, x);
             } else rot_sweep<KIND>(p, x, type, err);
          }
+      }
+      if (++time == p.P) time = 0;
+      for (int type = 0; type < p.ntypes; type++) {
+         if (time == 0) { tmod[type] = 0; toff[type] = 0; }
+         else if (++tmod[type] == tnseg[type]) { tmod[type] = 0; toff[type]++; }
       }
    }
    if (piped) {
@@ -1026,6 +1064,12 @@ pimc_steps_kernel(const __grid_constant__ Params p, long t0, long nsteps, int *e
       for (int i = x.tid; i < nown * 6; i += blockDim.x) {
          const int q = (i / 6) * p.cpc + x.crank;
          if (q < p.Q) stream_ptr(p, x.c, p.P + q)[i % 6] = x.rrng[i];
+      }
+      for (int ls = x.tid; ls < nown; ls += blockDim.x) {
+         const int q = ls * p.cpc + x.crank;
+         if (q >= p.Q) continue;
+         p.vold[((size_t)x.c * p.Q + q) * p.NMpad] = x.slot[ls].vcache;
+         p.vepoch[((size_t)x.c * p.Q + q) * p.NMpad] = x.slot[ls].vep;
       }
    }
 }

@@ -101,13 +101,10 @@ void spline_setup(const std::vector<double> &x, const std::vector<double> &y, st
    for (int k = n - 2; k >= 0; k--) y2[k] = y2[k] * y2[k + 1] + u[k];
 }
 // bucket table for the interval search: lut[b] = max{k : x[k] <= x0 + b/scale} (lower bound of the bucket)
-void build_lut(const std::vector<double> &x, std::vector<int> &lut, double &scale)
+void build_lut(const std::vector<double> &x, std::vector<int> &lut, double &scale, int factor = 4)
 {
    int n = (int)x.size();
-#ifndef PIMC_LUT_FACTOR
-#define PIMC_LUT_FACTOR 4
-#endif
-   int nl = PIMC_LUT_FACTOR * n;
+   int nl = factor * n;
    lut.assign(nl, 0);
    scale = (double)nl / (x[n - 1] - x[0]);
    int k = 0;
@@ -162,7 +159,7 @@ std::vector<SplineRec> make_records(const std::vector<double> &x, const std::vec
       double h = x[k + 1] - x[k];
       r[k].xlo = x[k]; r[k].xhi = x[k + 1]; r[k].inv_h = 1.0 / h;
       r[k].ylo = y[k]; r[k].yhi = y[k + 1];
-      r[k].clo = y2[k] * (h * h) / 6.; r[k].chi = y2[k + 1] * (h * h) / 6.;
+      r[k].clo = y2[k] * (h * h) / 6.; r[k].chi = y2[k + 1] * (h * h) / 6.; r[k].pad = 0.0;
    }
    return r;
 }
@@ -175,7 +172,7 @@ size_t smem_bytes(const Params &p, int threads)
    size_t d = 40;
    auto pad = [](int n) { return (size_t)((n + 1) & ~1); };
    auto padi = [](int n) { return (size_t)(((n + 1) / 2 + 1) & ~1); };
-   if (p.n1d) d += pad((p.n1d - 1) * (int)(sizeof(SplineRec) / sizeof(double))) + padi(p.nlut1d);
+   if (p.n1d) d += pad((p.n1d - 1) * (int)(sizeof(SplineRec) / sizeof(double))) + (p.uniform1d ? 0 : padi(p.nlut1d));
    if (p.rs2d) d += 2 * (size_t)(p.rs2d + p.cs2d);
    if (p.nrot && p.rot_in_smem) d += pad((p.nrot - 1) * (int)(sizeof(SplineRec) / sizeof(double))) + padi(p.nlutrot);
    if (!p.segbuf_global) d += (size_t)(threads / p.team) * p.team_buf_n;
@@ -259,6 +256,7 @@ int pimcgpu_init(const pimcgpu_system *sys, const pimcgpu_tables *tab)
       p.lambda[t] = 0.5 * (100.0 * (1.05457266 * 1.05457266) / (1.6605402 * 1.380658)) / T.mass;
       if (T.stat == 1) p.bstype = t;
       if (T.molecule) { p.imtype = t; nmolt++; } else natomt++;
+      if (T.levels < 1 || T.levels > MAXLEV) return fail("pimcgpu_init: bisection levels must be in [1,%d]", MAXLEV);
       if ((1 << T.levels) >= sys->P) return fail("pimcgpu_init: segment size 2^%d is not smaller than the number of slices %d", T.levels, sys->P);
       if (T.molecule == 1 && T.numb > 1) return fail("pimcgpu_init: no more than one linear dopant molecule");
    }
@@ -323,8 +321,15 @@ int pimcgpu_init(const pimcgpu_system *sys, const pimcgpu_tables *tab)
       p.alpha = log(v[0] / v[1]) / (g[1] - g[0]);
       p.unode = v[0] * exp(p.alpha * g[0]);
       p.c6 = (v[n - 1] - v[n - 2]) / (1.0 / pow(g[n - 2], 6.0) - 1.0 / pow(g[n - 1], 6.0));
+      // uniform grid: the interval index is the quotient (r - x0)/h, checked against the record; otherwise a bucket table
+      // fine enough that a bucket rarely holds a grid point
+      const double havg = (g[n - 1] - g[0]) / (double)(n - 1);
+      double dev = 0.0;
+      for (int i = 0; i < n; i++) dev = std::max(dev, fabs(g[i] - (g[0] + i * havg)));
+      p.uniform1d = (dev <= 0.02 * havg) ? 1 : 0;             // also grids printed with a few digits (helium.pot)
+      p.x0_1d = g[0]; p.xn_1d = g[n - 1]; p.invh_1d = 1.0 / havg;
       std::vector<int> lut;
-      build_lut(g, lut, p.lut1d_scale);
+      build_lut(g, lut, p.lut1d_scale, p.uniform1d ? 4 : 16);
       p.n1d = n; p.nlut1d = (int)lut.size();
       std::vector<SplineRec> rec = make_records(g, v, y2);
       if (dupload(&p.g1d, g.data(), n) || dupload(&p.v1d, v.data(), n) || dupload(&p.y2_1d, y2.data(), n) || dupload(&p.lut1d, lut.data(), lut.size()) ||
@@ -402,31 +407,41 @@ int pimcgpu_init(const pimcgpu_system *sys, const pimcgpu_tables *tab)
    for (int t = 0; t < p.ntypes; t++) { seg_max = std::max(seg_max, 1 << p.levels[t]); seg_min = std::min(seg_min, 1 << p.levels[t]); }
    p.seg_max = seg_max;
    p.team_buf_n = team_buf_doubles(seg_max);
-   // one rotor: the potential sums of all Q proposals are one parallel stage (rot_sweep_fused)
+   // one rotor, even Q: the potential sums of all Q proposals are one parallel stage and the decisions are pipelined
+   // (rot_sweep_pipe).  A chain that lives in one CTA keeps the two-phase sweep when a top's four density look-ups
+   // would have to share fewer than four threads per slice (measured on C3: 676 vs 847 M bead-updates/s).
    p.rot_fused = (p.Q > 0 && p.NM == 1 && p.Q % 2 == 0) ? 1 : 0;
    if (getenv("PIMC_NO_FUSED_ROT")) p.rot_fused = 0;
-   const int rot_units = p.rot_fused ? p.Q : p.Q / 2;          // rot slices that are independent within one stage
-   int team = sys->team;
-   if (team <= 0) team = pow2ceil(std::min(32, std::max(1, p.R * (p.N - 1) / 2)));
-   team = std::min(128, pow2floor(std::max(1, team)));
+   const bool top = p.imtype >= 0 && p.molecule[p.imtype] == 2;
+   int team = 1, threads = 0, cpc = 0, rot_units = 0, units = 0;
    const int nseg_widest = p.P / seg_min;
-   int units = std::max(rot_units, nseg_widest);              // widest stage: rot slices / segments of one atom
-   const long rot_work = (long)rot_units * p.R * std::max(1, p.N - 1);                 // pair terms of one rotational stage
-   const long bis_work = (long)nseg_widest * (seg_min - 1) * 2 * std::max(1, p.N - 1); // pair terms of one atom's bisection
-   long want = std::max<long>((long)units * team, std::max(rot_work / 4, bis_work / 8));
-   int threads = sys->threads_per_cta, cpc = sys->ctas_per_chain;
-   if (cpc <= 0) {
-      // enough CTAs for a few pair terms per thread in the widest stage, but never more CTAs than the 148 SMs can hold
-      // at once.  Up to 8 CTAs per chain form a cluster; 16 CTAs per chain run as a cooperative grid with a software
-      // chain barrier, because only seven 16-CTA clusters fit on a B200 at once (cudaOccupancyMaxActiveClusters)
-      long useful = (want + 511) / 512;
-      long fit = std::max(1, 148 / std::max(1, p.nchains));
-      cpc = (int)std::max<long>(1, std::min<long>(16, std::min(useful, fit)));
-      while (cpc & (cpc - 1)) cpc &= cpc - 1;                 // power of two
-   }
-   if (threads <= 0) {
-      long per = (want + cpc - 1) / cpc;
-      threads = (int)std::min<long>(512, std::max<long>(64, ((per + 31) / 32) * 32));
+   for (int attempt = 0; attempt < 2; attempt++) {
+      rot_units = p.rot_fused ? p.Q : p.Q / 2;                // rot slices that are independent within one stage
+      team = sys->team;
+      if (team <= 0) team = pow2ceil(std::min(32, std::max(1, p.R * (p.N - 1) / 2)));
+      team = std::min(128, pow2floor(std::max(1, team)));
+      units = std::max(rot_units, nseg_widest);               // widest stage: rot slices / segments of one atom
+      const long rot_work = (long)rot_units * p.R * std::max(1, p.N - 1);                 // pair terms of one rotational stage
+      const long bis_work = (long)nseg_widest * (seg_min - 1) * 2 * std::max(1, p.N - 1); // pair terms of one atom's bisection
+      long want = std::max<long>((long)units * team, std::max(rot_work / 4, bis_work / 8));
+      if (top && p.rot_fused) want = std::max<long>(want, 4L * rot_units);               // four density look-ups per slice
+      threads = sys->threads_per_cta; cpc = sys->ctas_per_chain;
+      if (cpc <= 0) {
+         // enough CTAs for a few pair terms per thread in the widest stage, but never more CTAs than the 148 SMs can hold
+         // at once.  Up to 8 CTAs per chain form a cluster; 16 CTAs per chain run as a cooperative grid with a software
+         // chain barrier, because only seven 16-CTA clusters fit on a B200 at once (cudaOccupancyMaxActiveClusters)
+         long useful = (want + 511) / 512;
+         long fit = std::max(1, 148 / std::max(1, p.nchains));
+         cpc = (int)std::max<long>(1, std::min<long>(16, std::min(useful, fit)));
+         while (cpc & (cpc - 1)) cpc &= cpc - 1;                 // power of two
+      }
+      if (threads <= 0) {
+         long per = (want + cpc - 1) / cpc;
+         threads = (int)std::min<long>(512, std::max<long>(64, ((per + 31) / 32) * 32));
+      }
+      const int per_cta = (p.Q + cpc - 1) / std::max(1, cpc);
+      if (p.rot_fused && cpc == 1 && top && threads / std::max(1, per_cta) < 4 && !getenv("PIMC_FORCE_FUSED_ROT")) { p.rot_fused = 0; continue; }
+      break;
    }
    if (threads % 32 || threads > PIMC_MAX_THREADS || threads < 32) return fail("pimcgpu_init: threads_per_cta must be a multiple of 32 in [32,%d]", PIMC_MAX_THREADS);
    if (cpc > 16 || (cpc & (cpc - 1))) return fail("pimcgpu_init: ctas_per_chain must be a power of two <= 16");

@@ -1,10 +1,14 @@
-"""Throughput of every BASELINE configuration on one GPU: python profiles/all_workloads.py"""
+"""Throughput of every BASELINE configuration on one GPU: python profiles/all_workloads.py [C1 C3 ...]"""
 import sys, os, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as ge
 pkg = ge.load_package()
-for w, chains, nsteps in (("C1", 148, 512), ("C2", 148, 512), ("C3", 148, 256), ("C4", 148, 64), ("C5", 8, 1024), ("C5", 15, 1024)):
+ALL = (("C1", 148, 512), ("C2", 148, 512), ("C3", 148, 256), ("C4", 148, 64), ("C5", 8, 1024), ("C5", 15, 1024))
+sel = set(sys.argv[1:])
+for w, chains, nsteps in ALL:
+    if sel and w not in sel:
+        continue
     cfg = pkg.configs.make_config(w)
     s = cfg.system
     G = pkg.gpu.PimcGpu(cfg, nchains=chains)
