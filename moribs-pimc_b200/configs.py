@@ -156,6 +156,8 @@ def write_qmc_input(s: System, path: str, outdir: str = "./out/") -> None:
             lines.append(f"ROTATION {t.name} {t.rtstep!r} {s.Q}")
     if s.rotden_type or s.x_rot:
         lines.append(f"ROTDENSI {s.rotden_type} {s.rot_odevn} {s.rot_eoff!r} {s.x_rot!r} {s.y_rot!r} {s.z_rot!r} {s.rnratio}")
+    if s.worm:
+        lines.append(f"WORM {s.worm[0]} {s.worm[1]!r} {s.worm[2]}")
     if s.minimage:
         lines.append("MINIMAGE")
     lines += [f"NUMBEROFSLICES {s.P}", f"NUMBEROFPASSES {s.passes}", f"NUMBEROFBLOCKS {s.blocks} {s.eq_blocks}",

@@ -241,6 +241,44 @@ class Oracle:
     def sched_symmetry(self, refl_x, refl_y, refl_z, rotsym, nfold):
         self.lib.orc_sched_symmetry(self.h, *[C.c_int(v) for v in (refl_x, refl_y, refl_z, rotsym, nfold)])
 
+    # worm ------------------------------------------------------------------------------
+    def worm_init(self, type_, c_input, m):
+        self.lib.orc_worm_init(self.h, C.c_int(type_), C.c_double(c_input), C.c_int(m))
+
+    def worm_set(self, st5):
+        self.lib.orc_worm_set(self.h, (C.c_int * 5)(*[int(v) for v in st5]))
+
+    def worm_get(self):
+        st = (C.c_int * 5)()
+        self.lib.orc_worm_get(self.h, st)
+        return list(st)
+
+    def worm_push(self, stream, u):
+        u = np.ascontiguousarray(np.atleast_1d(u), dtype=np.float64)
+        self.lib.orc_worm_push(self.h, C.c_int(stream), _dp(u), C.c_int(len(u)))
+
+    def worm_clear(self):
+        self.lib.orc_worm_clear(self.h)
+
+    def worm_pending(self, stream):
+        return self.lib.orc_worm_pending(self.h, C.c_int(stream))
+
+    def worm_op(self, which, sched_stream=False):
+        self.lib.orc_worm_op(self.h, C.c_int(which), C.c_int(1 if sched_stream else 0))
+
+    def worm_counters(self):
+        t, a, cq = np.zeros(7), np.zeros(7), C.c_double()
+        self.lib.orc_worm_counters(self.h, _dp(t), _dp(a), C.byref(cq))
+        return t, a, cq.value
+
+    def get_perm(self, n):
+        p, r = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+        self.lib.orc_get_perm(self.h, _ip(p), _ip(r), C.c_int(n))
+        return p, r
+
+    def world_line(self, atom, pt):
+        return bool(self.lib.orc_world_line(self.h, C.c_int(atom), C.c_int(pt)))
+
     # schedule replay -----------------------------------------------------------------
     def sched_seed(self, seed6, chain_global=0):
         sd = (C.c_ulong * 6)(*seed6)

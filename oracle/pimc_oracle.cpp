@@ -17,6 +17,7 @@
 #include <cstring>
 #include <vector>
 #include <array>
+#include <deque>
 
 extern "C" {
 void rotden_(double *, double *, double *, double *, double *, double *, double *, double *, double *, int *);
@@ -200,9 +201,39 @@ struct orc {
    // schedule streams: P translational, Q rotational, 8 misc
    std::vector<std::array<double, 6>> streams;
    double ErotSQ = 0, Erot_termSQ = 0;
+   // worm (mc_qworm.h:32-47 TPathWorm, mc_qworm.cc:15-46): atoms are numbered inside the worm type
+   struct { int on = 0, type = 0, exists = 0, ira = 0, masha = 0, atom_i = 0, atom_m = 0, m = 1;
+            double c = 0, qw_norm = 0, cutoff2 = 0, twave2 = 0; } worm;
+   double qwtotal[7] = {0, 0, 0, 0, 0, 0, 0}, qwaccep[7] = {0, 0, 0, 0, 0, 0, 0}, countqw = 1.0;
+   std::deque<double> wq[15];          // explicit uniforms per SPRNG stream (mc_randg.cc:90-174), test mode
+   int wmode = 0;                      // 0: queues, 1: the chain's worm stream of the device schedule
+   std::vector<double> dr2_list, ptable; std::vector<int> atm_list;
 
    int type_offset(int t) const { return offset_atom[t] * P; }
 };
+
+// WorldLine(atom, pt), mc_qworm.cc:553-575: false when bead pt of world line `atom` lies in the ira-masha gap
+static bool WorldLine(const orc_t *o, int atom, int pt)
+{
+   const auto &W = o->worm;
+   bool wline = true;
+   if ((atom == W.atom_m) || (atom == W.atom_i)) {
+      if ((W.atom_i != W.atom_m) || (W.ira > W.masha)) {
+         if (((atom == W.atom_m) && (pt < W.masha)) || ((atom == W.atom_i) && (pt > W.ira))) wline = false;
+      } else {
+         if ((pt > W.ira) && (pt < W.masha)) wline = false;
+      }
+   }
+   return wline;
+}
+// the mask every PotEnergy variant applies to its partner loop (mc_piqmc.cc:1226-1227,1816-1817,2000-2001,2082-2083)
+static inline bool partner_on_line(const orc_t *o, int atom1, int it)
+{
+   if (!(o->worm.on && o->worm.exists)) return true;
+   int type1 = o->mctype[atom1];
+   if (o->worm.type != type1) return true;
+   return WorldLine(o, atom1 - o->offset_atom[type1], it);
+}
 
 // ----------------------------------------------------------------------------
 // leaf potentials
@@ -326,7 +357,7 @@ static double PotEnergy_it(orc_t *o, int atom0, const double *pos0, int it)
 {
    double spot = 0.0;
    for (int atom1 = 0; atom1 < o->N; atom1++)
-      if (atom1 != atom0) spot += pair_energy(o, atom0, pos0, atom1, it, nullptr, nullptr, 0, nullptr);
+      if (atom1 != atom0 && partner_on_line(o, atom1, it)) spot += pair_energy(o, atom0, pos0, atom1, it, nullptr, nullptr, 0, nullptr);
    return spot;
 }
 // PotEnergy(atom0,pos), mc_piqmc.cc:1201-1383: per partner, sum over slices, then add
@@ -338,6 +369,7 @@ static double PotEnergy_path(orc_t *o, int atom0, const double *shift)
       if (atom1 != atom0) {
          double spot_pair = 0.0;
          for (int it = 0; it < P; it++) {
+            if (!partner_on_line(o, atom1, it)) continue;
             double pos0[3];
             for (int id = 0; id < 3; id++) {
                pos0[id] = o->coords[id][P * atom0 + it];
@@ -357,7 +389,7 @@ static double PotRotEnergy(orc_t *o, int atom0, const double *cos3, int it)
    double pos0[3];
    for (int id = 0; id < 3; id++) pos0[id] = o->coords[id][P * atom0 + it];
    for (int atom1 = 0; atom1 < o->N; atom1++)
-      if (atom1 != atom0) spot += pair_energy(o, atom0, pos0, atom1, it, nullptr, cos3, 0, nullptr);
+      if (atom1 != atom0 && partner_on_line(o, atom1, it)) spot += pair_energy(o, atom0, pos0, atom1, it, nullptr, cos3, 0, nullptr);
    return spot;
 }
 // PotRotE3D, mc_piqmc.cc:2046-2151
@@ -368,7 +400,7 @@ static double PotRotE3D(orc_t *o, int atom0, const double *eul, int it)
    double pos0[3];
    for (int id = 0; id < 3; id++) pos0[id] = o->coords[id][P * atom0 + it];
    for (int atom1 = 0; atom1 < o->N; atom1++)
-      if (atom1 != atom0) spot += pair_energy(o, atom0, pos0, atom1, it, eul, nullptr, 0, nullptr);
+      if (atom1 != atom0 && partner_on_line(o, atom1, it)) spot += pair_energy(o, atom0, pos0, atom1, it, eul, nullptr, 0, nullptr);
    return spot;
 }
 
@@ -846,6 +878,288 @@ static void GetRCF(orc_t *o, double *rcf0)
       }
    }
 }
+
+
+// ----------------------------------------------------------------------------
+// worm moves (N1), mc_qworm.cc:93-667.  Uniforms come from per-stream queues in
+// test mode (same stream numbers as mc_randg.cc:90-174) or, in schedule mode,
+// all from the chain's worm stream in program order (what the device does).
+// ----------------------------------------------------------------------------
+namespace {
+inline double draw(orc_t *o, int s);
+double wr(orc_t *o, int stream)
+{
+   if (o->wmode == 1) return draw(o, o->P + o->Q + 1);
+   if (o->wq[stream].empty()) { fprintf(stderr, "oracle: worm RNG queue %d empty\n", stream); exit(2); }
+   double v = o->wq[stream].front(); o->wq[stream].pop_front(); return v;
+}
+inline double w_gauss(orc_t *o, double alpha)        // mc_randg.cc:138-150
+{
+   double r1 = wr(o, 8), r2 = wr(o, 9);
+   double x1 = sqrt(-log(r1)) * cos(2.0 * M_PI * r2);
+   return (x1 / sqrt(alpha));
+}
+inline int w_nrnd(orc_t *o, int k, int n) { return (int)floor(n * wr(o, 9 + k)); }   // nrnd1..3 -> streams 10..12
+
+// get_potential, mc_qworm.cc:400-422: sum of PotEnergy over the open interval (it0, it1); the moving atom's beads are
+// read from `pos` (MCCoords or the swap path)
+typedef std::vector<double> *coord3;
+double get_potential(orc_t *o, int it0, int it1, int atom0, int atom1, std::vector<double> *coords)
+{
+   int P = o->P, aoff = o->offset_atom[o->worm.type];
+   int pit0 = it0 % P;
+   double pot = 0.0;
+   int atom = atom0;
+   for (int it = (it0 + 1); it < it1; it++) {
+      int pit = it % P;
+      if ((pit != it) && (pit0 == it0)) atom = atom1;
+      double pos0[3];
+      for (int id = 0; id < 3; id++) pos0[id] = coords[id][P * (aoff + atom) + pit];
+      pot += PotEnergy_it(o, aoff + atom, pos0, pit);
+   }
+   return pot;
+}
+// sample_middle, mc_qworm.cc:240-287
+void sample_middle(orc_t *o, int it0, int it2, int atom0, int atom2, std::vector<double> *coords)
+{
+   if ((it2 - it0) < 2) return;
+   int P = o->P;
+   int it1 = (int)rint(0.5 * (double)(it0 + it2));
+   int pt0 = it0 % P, pt1 = it1 % P, pt2 = it2 % P;
+   int atom1 = atom0;
+   if ((pt1 != it1) && (pt0 == it0)) atom1 = atom2;
+   int offset = o->type_offset(o->worm.type);
+   pt0 += (offset + atom0 * P); pt1 += (offset + atom1 * P); pt2 += (offset + atom2 * P);
+   double s0 = (double)(it1 - it0), s2 = (double)(it2 - it1);
+   double gkin = (s0 + s2) / (o->worm.twave2 * s0 * s2);
+   for (int id = 0; id < 3; id++) {
+      coords[id][pt1] = (s2 * coords[id][pt0] + s0 * coords[id][pt2]) / (s0 + s2);
+      coords[id][pt1] += w_gauss(o, gkin);
+   }
+   sample_middle(o, it0, it1, atom0, atom1, coords);
+   sample_middle(o, it1, it2, atom1, atom2, coords);
+}
+// qw_open_prob, mc_qworm.cc:127-153
+double qw_open_prob(orc_t *o, int segm)
+{
+   auto &W = o->worm;
+   int P = o->P, offset = o->type_offset(W.type);
+   double kin = 0.0;
+   int pt0 = offset + W.atom_i * P + W.ira, pt1 = offset + W.atom_m * P + W.masha;
+   for (int id = 0; id < 3; id++) {
+      double dr = o->coords[id][pt0] - o->coords[id][pt1];
+      if (o->sys.minimage) dr -= (o->sys.box[id] * rint(dr / o->sys.box[id]));
+      kin += (dr * dr);
+   }
+   kin /= (W.twave2 * (double)segm);
+   double pot = get_potential(o, W.ira, W.ira + segm, W.atom_i, W.atom_m, o->coords);
+   pot *= o->tau;
+   return (W.qw_norm * pow((double)segm, 0.5 * 3.0) * exp(kin + pot));
+}
+void qworm_open(orc_t *o)            // mc_qworm.cc:155-182
+{
+   auto &W = o->worm;
+   int P = o->P;
+   o->qwtotal[0] += 1.0;
+   W.atom_i = w_nrnd(o, 1, o->sys.type[W.type].numb);
+   W.ira = w_nrnd(o, 2, P);
+   int segm = w_nrnd(o, 3, W.m) + 1;
+   W.masha = (W.ira + segm) % P;
+   W.atom_m = W.atom_i;
+   if (W.masha != (W.ira + segm)) W.atom_m = o->pindex[W.atom_i];
+   double prob = qw_open_prob(o, segm);
+   bool Accepted = false;
+   if (prob >= 1.0) Accepted = true;
+   else if (prob > wr(o, 1)) Accepted = true;
+   if (Accepted) { W.exists = 1; o->qwaccep[0] += 1.0; }
+}
+void qworm_close(orc_t *o)           // mc_qworm.cc:184-238
+{
+   auto &W = o->worm;
+   int P = o->P;
+   o->qwtotal[1] += 1.0;
+   int segm = W.masha - W.ira;
+   if (segm < 0) segm += P;
+   if (segm > W.m) return;
+   int it0 = W.ira, it2 = W.ira + segm;
+   sample_middle(o, it0, it2, W.atom_i, W.atom_m, o->coords);
+   double prob = 1.0 / qw_open_prob(o, segm);
+   bool Accepted = false;
+   if (prob >= 1.0) Accepted = true;
+   else if (prob > wr(o, 1)) Accepted = true;
+   if (Accepted) { W.exists = 0; o->qwaccep[1] += 1.0; }
+}
+void qworm_advance(orc_t *o)         // mc_qworm.cc:299-357
+{
+   auto &W = o->worm;
+   int P = o->P;
+   o->qwtotal[4] += 1.0;
+   int segm = W.masha - W.ira;
+   if (segm < 0) segm += P;
+   int advance = w_nrnd(o, 3, W.m) + 1;
+   if (segm - advance <= 0) return;
+   int type = W.type, offset = o->type_offset(type);
+   int it0 = W.ira, it2 = W.ira + advance;
+   int ira_new = it2 % P, atom_i_new = W.atom_i;
+   if (ira_new != it2) atom_i_new = W.atom_m;
+   double gvar = 1.0 / ((double)advance * W.twave2);
+   int pt0 = offset + W.atom_i * P + it0 % P, pt2 = offset + atom_i_new * P + it2 % P;
+   for (int id = 0; id < 3; id++) o->coords[id][pt2] = o->coords[id][pt0] + w_gauss(o, gvar);
+   sample_middle(o, it0, it2, W.atom_i, atom_i_new, o->coords);
+   double pot = get_potential(o, it0, it2 + 1, W.atom_i, atom_i_new, o->coords);
+   bool Accepted = false;
+   if (pot < 0.0) Accepted = true;
+   else if (exp(-pot * o->tau) > wr(o, 2)) Accepted = true;
+   if (Accepted) { o->qwaccep[4] += 1.0; W.ira = ira_new; W.atom_i = atom_i_new; }
+}
+void qworm_recede(orc_t *o)          // mc_qworm.cc:359-398
+{
+   auto &W = o->worm;
+   int P = o->P;
+   o->qwtotal[5] += 1.0;
+   int segm = W.ira - W.masha;
+   if (segm < 0) segm += P;
+   int recede = w_nrnd(o, 3, W.m) + 1;
+   if ((segm - recede) < 1) return;
+   int it0 = (W.ira - recede), it1 = W.ira;
+   int atom0 = W.atom_i, atom1 = W.atom_i;
+   if (it0 < 0) { it0 += P; it1 += P; atom0 = o->rindex[atom1]; }
+   double pot = get_potential(o, it0, it1 + 1, atom0, atom1, o->coords);
+   bool Accepted = false;
+   if (pot > 0.0) Accepted = true;
+   else if (exp(pot * o->tau) > wr(o, 2)) Accepted = true;
+   if (Accepted) { W.ira = it0 % P; W.atom_i = atom0; o->qwaccep[5] += 1.0; }
+}
+// get_ptable, mc_qworm.cc:577-643 (entries 1..count)
+int get_ptable(orc_t *o, int atomw, int pt0, int pt1, int segm, int t1)
+{
+   auto &W = o->worm;
+   int P = o->P, type = W.type, offset = o->type_offset(type);
+   int itw = offset + atomw * P + pt0;
+   int count = 0;
+   for (int atom1 = 0; atom1 < o->sys.type[type].numb; atom1++)
+      if (WorldLine(o, atom1, pt1)) {
+         int atom0 = atom1;
+         if (t1 != pt1) atom0 = o->rindex[atom1];
+         if (atom0 != W.atom_i) {
+            int it1 = offset + atom1 * P + pt1;
+            double dr2 = 0.0;
+            for (int id = 0; id < 3; id++) {
+               double dx = o->coords[id][itw] - o->coords[id][it1];
+               if (o->sys.minimage) dx -= (o->sys.box[id] * rint(dx / o->sys.box[id]));
+               dr2 += (dx * dx);
+            }
+            if (dr2 < W.cutoff2) { count++; o->dr2_list[count] = dr2; o->atm_list[count] = atom1; }
+         }
+      }
+   for (int j = 2; j <= count; j++) {          // mmsort, mc_utils.cc:206-231
+      double dtmp = o->dr2_list[j]; int itmp = o->atm_list[j];
+      int i = j - 1;
+      while ((i > 0) && (o->dr2_list[i] > dtmp)) { o->dr2_list[i + 1] = o->dr2_list[i]; o->atm_list[i + 1] = o->atm_list[i]; i--; }
+      o->dr2_list[i + 1] = dtmp; o->atm_list[i + 1] = itmp;
+   }
+   if (count > 100) count = 100;               // MAXNEIGHBORS
+   double norm = 1.0 / ((double)segm * W.twave2);
+   for (int ic = 1; ic <= count; ic++) o->ptable[ic] = exp(-norm * o->dr2_list[ic]);
+   return count;
+}
+int atom2swap(orc_t *o, int count, double &pnorm)    // mc_qworm.cc:645-667
+{
+   pnorm = 0.0;
+   for (int ic = 1; ic <= count; ic++) pnorm += o->ptable[ic];
+   double prand = pnorm * wr(o, 3);
+   double sum = 0.0;
+   int ic = 1;
+   while ((ic <= count) && (sum < prand)) { sum += o->ptable[ic]; ic++; }
+   ic--;
+   return (o->atm_list[ic]);
+}
+void qworm_swap(orc_t *o)            // mc_qworm.cc:424-551
+{
+   auto &W = o->worm;
+   int P = o->P;
+   o->qwtotal[6] += 1.0;
+   int segm = W.m;
+   int it0 = W.ira, it1 = it0 + segm;
+   int pit0 = it0, pit1 = it1 % P;
+   int atomw = W.atom_i;
+   int count = get_ptable(o, atomw, pit0, pit1, segm, it1);
+   if (count <= 0) return;
+   double pnorm_old, pnorm_new;
+   int atom1 = atom2swap(o, count, pnorm_old);
+   if (atom1 < 0) return;
+   int atom0 = atom1;
+   if (pit1 != it1) atom0 = o->rindex[atom1];
+   int type = W.type;
+   int offset0 = o->type_offset(type) + atom0 * P, offset1 = o->type_offset(type) + atom1 * P, offsetw = o->type_offset(type) + atomw * P;
+   for (int id = 0; id < 3; id++) {
+      o->newc[id][offset0 + pit0] = o->coords[id][offsetw + pit0];
+      o->newc[id][offset1 + pit1] = o->coords[id][offset1 + pit1];
+   }
+   sample_middle(o, it0, it1, atom0, atom1, o->newc);
+   int gatom0 = offset0 / P, gatom1 = offset1 / P;
+   double pot = 0.0;
+   int gatom = gatom0;
+   for (int it = (it0 + 1); it < it1; it++) {
+      int pit = it % P;
+      if (pit != it) gatom = gatom1;
+      double pn[3], po[3];
+      for (int id = 0; id < 3; id++) { pn[id] = o->newc[id][P * gatom + pit]; po[id] = o->coords[id][P * gatom + pit]; }
+      pot += PotEnergy_it(o, gatom, pn, pit);
+      pot -= PotEnergy_it(o, gatom, po, pit);
+   }
+   double prob = exp(-pot * o->tau);
+   count = get_ptable(o, atom0, pit0, pit1, segm, it1);
+   pnorm_new = 0.0;
+   for (int ic = 1; ic <= count; ic++) pnorm_new += o->ptable[ic];
+   prob *= (pnorm_old / pnorm_new);
+   bool Accepted = false;
+   if (prob >= 1.0) Accepted = true;
+   else if (prob > wr(o, 4)) Accepted = true;
+   if (Accepted) {
+      o->qwaccep[6] += 1.0;
+      for (int id = 0; id < 3; id++) {
+         int offset = offset0;
+         for (int it = (it0 + 1); it < it1; it++) {
+            int pit = it % P;
+            if (pit != it) offset = offset1;
+            o->coords[id][offset + pit] = o->newc[id][offset + pit];
+         }
+      }
+      for (int id = 0; id < 3; id++)
+         for (int it = 0; it <= it0; it++) {
+            o->newc[id][offset0 + it] = o->coords[id][offset0 + it];
+            o->coords[id][offset0 + it] = o->coords[id][offsetw + it];
+            o->coords[id][offsetw + it] = o->newc[id][offset0 + it];
+         }
+      int ratomw = o->rindex[atomw], ratom0 = o->rindex[atom0];
+      o->pindex[ratomw] = atom0; o->rindex[atom0] = ratomw;
+      o->pindex[ratom0] = atomw; o->rindex[atomw] = ratom0;
+      if (W.ira > W.masha) {
+         if (atom0 == W.atom_m) W.atom_m = W.atom_i;
+         else if (W.atom_i == W.atom_m) W.atom_m = atom0;
+      }
+   }
+}
+// MCWormMove, mc_qworm.cc:93-125
+void worm_move(orc_t *o)
+{
+   auto &W = o->worm;
+   for (int atom = 0; atom < o->sys.type[W.type].numb; atom++) {
+      o->countqw += 1.0;
+      if (W.exists) qworm_close(o); else qworm_open(o);
+      if (W.exists) {
+         o->countqw += 1.0;
+         double r = wr(o, 5);
+         if (r > 0.5) qworm_advance(o); else qworm_recede(o);
+      }
+      if (o->bstype >= 0 && W.type == o->bstype) {
+         o->countqw += 1.0;
+         if (W.exists) qworm_swap(o);
+      }
+   }
+}
+} // namespace
 
 // ----------------------------------------------------------------------------
 // area / exchange estimators (a18) and symmetry operations (a19)
@@ -1328,6 +1642,47 @@ void orc_sched_symmetry(orc_t *o, int refl_x, int refl_y, int refl_z, int rotsym
    if (rotsym && draw(o, MS) < 0.5) RotSymConfig(o, draw(o, MS), nfold);
 }
 
+// ---- worm (N1) ----
+void orc_worm_init(orc_t *o, int type, double c_input, int m)      // MCWormInit, mc_qworm.cc:48-82
+{
+   auto &W = o->worm;
+   W.on = 1; W.type = type; W.exists = 0; W.m = m;
+   int numb = o->sys.type[type].numb;
+   double density = (double)o->N / (o->sys.box[0] * o->sys.box[1] * o->sys.box[2]);
+   W.c = c_input * (density / (numb * o->P * m));
+   W.qw_norm = W.c * numb * o->P * m;
+   W.twave2 = 4.0 * o->lambda[type] * o->tau;                      // mc_setup.cc:394
+   W.cutoff2 = 100.0 * 100.0 * ((double)m * 4.0 * o->lambda[type] * o->tau);
+   o->dr2_list.assign(numb + 2, 0.0); o->atm_list.assign(numb + 2, 0); o->ptable.assign(numb + 2, 0.0);
+   o->countqw = 1.0;
+   for (int i = 0; i < 7; i++) { o->qwtotal[i] = 0; o->qwaccep[i] = 0; }
+}
+void orc_worm_set(orc_t *o, const int *st5) { auto &W = o->worm; W.exists = st5[0]; W.ira = st5[1]; W.masha = st5[2]; W.atom_i = st5[3]; W.atom_m = st5[4]; }
+void orc_worm_get(orc_t *o, int *st5) { auto &W = o->worm; st5[0] = W.exists; st5[1] = W.ira; st5[2] = W.masha; st5[3] = W.atom_i; st5[4] = W.atom_m; }
+void orc_worm_push(orc_t *o, int stream, const double *u, int n) { for (int i = 0; i < n; i++) o->wq[stream].push_back(u[i]); }
+void orc_worm_clear(orc_t *o) { for (auto &q : o->wq) q.clear(); }
+int  orc_worm_pending(orc_t *o, int stream) { return (int)o->wq[stream].size(); }
+/* which: 0 open, 1 close, 4 advance, 5 recede, 6 swap (the QW_* codes), 7 the whole MCWormMove */
+void orc_worm_op(orc_t *o, int which, int sched_stream)
+{
+   o->wmode = sched_stream ? 1 : 0;
+   switch (which) {
+      case 0: qworm_open(o); break;
+      case 1: qworm_close(o); break;
+      case 4: qworm_advance(o); break;
+      case 5: qworm_recede(o); break;
+      case 6: qworm_swap(o); break;
+      default: worm_move(o);
+   }
+}
+void orc_worm_counters(orc_t *o, double *total7, double *accep7, double *countqw)
+{
+   for (int i = 0; i < 7; i++) { total7[i] = o->qwtotal[i]; accep7[i] = o->qwaccep[i]; }
+   *countqw = o->countqw;
+}
+void orc_get_perm(orc_t *o, int *pindex, int *rindex, int n) { for (int i = 0; i < n; i++) { pindex[i] = o->pindex[i]; rindex[i] = o->rindex[i]; } }
+int  orc_world_line(orc_t *o, int atom, int pt) { return WorldLine(o, atom, pt) ? 1 : 0; }
+
 void orc_mrg_stream_state(const unsigned long *seed6, long stream, double *st) { mrg_stream_state(seed6, stream, st); }
 void orc_mrg_draws(const unsigned long *seed6, long first, int nstream, int ndraw, double *out)
 {
@@ -1359,9 +1714,15 @@ void orc_sched_run(orc_t *o, long t0, long nsteps)
       int time = (int)(t % P);
       for (int type = 0; type < o->sys.ntypes; type++) {
          const orc_type_t &T = o->sys.type[type];
-         if (time == 0) sched_molecular(o, type);
+         bool closed = true;
+         if (o->worm.on && type == o->worm.type) {        // mc_main.cc:355-379: worm moves, then the path moves in the Z sector only
+            o->wmode = 1;
+            worm_move(o);
+            closed = !o->worm.exists;
+         }
+         if (time == 0 && closed) sched_molecular(o, type);
          int seg = 1 << T.levels, nseg = P / seg;
-         if (time % nseg == 0) {
+         if (time % nseg == 0 && closed) {
             int off = (time / nseg) % P;
             for (int atom = 0; atom < T.numb; atom++)
                for (int k = 0; k < nseg; k++) sched_bisect(o, type, atom, (off + k * seg) % P);

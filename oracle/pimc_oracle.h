@@ -100,6 +100,18 @@ void orc_reflect(orc_t *, int plane /* 0 XZ (REFLECTY), 1 YZ (REFLECTX), 2 XY (R
 void orc_rotsym(orc_t *, double u, int nfold);                                        /* RotSymConfig mc_piqmc.cc:1710-1794 */
 void orc_sched_symmetry(orc_t *, int refl_x, int refl_y, int refl_z, int rotsym, int nfold);
 
+/* worm moves (N1, mc_qworm.cc:93-667) and the world-line mask (a22); worm atoms are numbered inside their type */
+void orc_worm_init(orc_t *, int type, double c_input, int m);                 /* WORM line of qmc.input + MCWormInit */
+void orc_worm_set(orc_t *, const int *st5 /* exists, ira, masha, atom_i, atom_m */);
+void orc_worm_get(orc_t *, int *st5);
+void orc_worm_push(orc_t *, int stream, const double *u, int n);              /* explicit uniforms per SPRNG stream number */
+void orc_worm_clear(orc_t *);
+int  orc_worm_pending(orc_t *, int stream);
+void orc_worm_op(orc_t *, int which /* 0 open 1 close 4 advance 5 recede 6 swap, else MCWormMove */, int sched_stream);
+void orc_worm_counters(orc_t *, double *total7, double *accep7, double *countqw);
+void orc_get_perm(orc_t *, int *pindex, int *rindex, int n);
+int  orc_world_line(orc_t *, int atom, int pt);                               /* WorldLine, mc_qworm.cc:553-575 */
+
 /* MRG32k3a (a13): state of the s-th RngStream after SetPackageSeed(seed), and draws */
 void orc_mrg_stream_state(const unsigned long *seed6, long stream, double *state6);
 void orc_mrg_draws(const unsigned long *seed6, long first_stream, int nstream, int ndraw, double *out);

@@ -55,6 +55,7 @@ extern double **_gr3D;
 extern double *_relthe_sum, *_relphi_sum, *_relchi_sum;
 extern double *_ploops;
 extern double _areas[2], _area2[2], _inert[2];
+void qworm_open(void); void qworm_close(void); void qworm_advance(void); void qworm_recede(void); void qworm_swap(void);
 
 static int g_queue_mode = 0;
 static std::deque<double> g_q[15];
@@ -301,6 +302,28 @@ void ref_reflect(int plane)
 }
 void ref_rotsym(void) { RotSymConfig(); }       // rotor pick from rnd1 (queue 1)
 void ref_set_nfold(int n) { NFOLD_ROT = n; }
+// worm moves (mc_qworm.cc; the move functions have external linkage but no header declaration)
+void ref_worm_set(const int *st5) { Worm.exists = st5[0]; Worm.ira = st5[1]; Worm.masha = st5[2]; Worm.atom_i = st5[3]; Worm.atom_m = st5[4]; }
+void ref_worm_get(int *st5) { st5[0] = Worm.exists; st5[1] = Worm.ira; st5[2] = Worm.masha; st5[3] = Worm.atom_i; st5[4] = Worm.atom_m; }
+void ref_worm_op(int which)
+{
+   switch (which) {
+      case 0: qworm_open(); break;
+      case 1: qworm_close(); break;
+      case 4: qworm_advance(); break;
+      case 5: qworm_recede(); break;
+      case 6: qworm_swap(); break;
+      default: MCWormMove();
+   }
+}
+void ref_worm_counters(double *t7, double *a7, double *cq)
+{
+   for (int i = 0; i < QWMAXMOVES; i++) { t7[i] = QWTotal[0][i]; a7[i] = QWAccep[0][i]; }
+   *cq = countQW;
+}
+void ref_get_perm(int *pi, int *ri, int n) { for (int i = 0; i < n; i++) { pi[i] = PIndex[i]; ri[i] = RIndex[i]; } }
+int ref_world_line(int atom, int pt) { return WorldLine(atom, pt) ? 1 : 0; }
+int ref_worm_enabled(void) { return WORM ? 1 : 0; }
 void ref_MCGetAverage(double *out7)
 {
    MCGetAverage();
