@@ -65,6 +65,11 @@ typedef struct {
    int          reflect[3];    /* IREFLX, IREFLY, IREFLZ                                        */
    int          rotsym;        /* IROTSYM                                                       */
    int          nfold_rot;     /* NFOLD_ROT                                                     */
+   /* WORM line (mc_input.cc:286-293) + MCWormInit (mc_qworm.cc:48-82): worm moves on the device */
+   int          worm;          /* 1: sample exchange with the worm algorithm                    */
+   int          worm_type;     /* Worm.type: index of the species the worm lives in             */
+   double       worm_c;        /* Worm.c as in qmc.input (normalised with the density at init)  */
+   int          worm_m;        /* Worm.m (m-tilde), < P                                         */
 } pimcgpu_system;
 
 /* host pointers to the tables the reference loads in InitPotentials / InitRotDensity
@@ -148,6 +153,14 @@ long   pimcgpu_accum_offset(const char *name);
  *      operations: ops[chain][4] = {XZ, YZ, XY reflection flags, rotor index for the symmetry rotation or -1}  ---- */
 int pimcgpu_symmetry_moves(void);
 int pimcgpu_symmetry_ops(const int *ops);
+
+/* ---- worm moves (mc_qworm.cc:93-667).  With sys.worm set, pimcgpu_steps runs MCWormMove for the worm's species in
+ *      every step and its path moves only while the worm is closed (mc_main.cc:355-379); pimcgpu_measure skips chains
+ *      whose worm is open.  Worm atoms are numbered inside their species, as Worm.atom_i / atom_m.            ---- */
+int pimcgpu_worm_moves(void);                               /* one MCWormMove per chain (parity entry point)        */
+int pimcgpu_worm_state(int chain, int *st5);                /* Worm.exists, ira, masha, atom_i, atom_m              */
+int pimcgpu_worm_set(int chain, const int *st5);
+int pimcgpu_worm_counters(double *total7, double *accep7, double *countqw);   /* QWTotal, QWAccep, countQW over all chains */
 
 /* instantaneous area estimators of one chain, out[28]: area_perp, area_parl, inert_perp, inert_parl of
  * GetAreaEstimators (linear dopant; inertia sums before the division by NumbTimes), then area_proj[3] and

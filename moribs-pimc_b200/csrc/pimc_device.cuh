@@ -37,6 +37,12 @@ struct Params {
    int rotden_type, rnratio;     // ROTDENSI: 0 tabulated densities, 1 rattle-and-shake propagator (rsrot/rsline); RS/Noya ratio
    double xrot, yrot, zrot;      // rotational constants of the ROTDENSI line, cm^-1
    int refl[3], rotsym, nfold;   // REFLECTX/Y/Z, ROTSYM (IREFLX.., IROTSYM, NFOLD_ROT; mc_setup.h:24-30)
+   // worm (WORM line, MCWormInit mc_qworm.cc:48-82): type, m-tilde, C * density, 4 lambda tau, neighbour cutoff^2
+   int worm_on, worm_type, worm_m;
+   double worm_norm, worm_twave2, worm_cutoff2;
+   int *wstate;                  // [c][8]: Worm.exists, ira, masha, atom_i, atom_m (atoms numbered inside the worm type)
+   int *rindex;                  // [c][N] previous world line (RIndex), global atom index like pindex
+   double *qwc;                  // [c][16]: QWTotal[7], QWAccep[7], countQW
    double box[3];
    int mode[MAXT][MAXT];
    // tables

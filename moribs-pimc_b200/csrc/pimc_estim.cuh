@@ -7,6 +7,7 @@
 // FP64 atomics straight into the block accumulator buffer (order-independent).
 #pragma once
 #include "pimc_device.cuh"
+#include "pimc_worm.cuh"
 
 namespace pimc {
 
@@ -59,6 +60,7 @@ est_energy_kernel(const __grid_constant__ Params p, const __grid_constant__ EstB
    const int c = blockIdx.x / EST_BLOCKS, b = blockIdx.x % EST_BLOCKS;
    const int P = p.P, N = p.N, Q = p.Q;
    const int gt = b * blockDim.x + threadIdx.x, nt = EST_BLOCKS * blockDim.x;
+   if (p.worm_on && p.wstate[(size_t)c * 8]) return;      // G sector: no estimators (mc_main.cc:389-391, mc_estim.cc:506-507)
    SmallTables t;
    t.g1d = p.g1d; t.v1d = p.v1d; t.y2_1d = p.y2_1d; t.lut1d = p.lut1d;
    t.rgrid = p.rgrid; t.rdens = p.rdens; t.rdens2 = p.rdens2; t.lutrot = p.lutrot;
@@ -320,6 +322,7 @@ est_area_kernel(const __grid_constant__ Params p, const __grid_constant__ EstBuf
 {
    __shared__ double red[32];
    const int c = blockIdx.x / EST_BLOCKS, b = blockIdx.x % EST_BLOCKS;
+   if (p.worm_on && p.wstate[(size_t)c * 8]) return;
    const int P = p.P, N = p.N, bt = p.bstype;
    const int nb = p.numb[bt], b0 = p.first[bt];
    const int gt = b * blockDim.x + threadIdx.x, nt = EST_BLOCKS * blockDim.x;
@@ -406,6 +409,7 @@ __global__ void est_finalize_kernel(const __grid_constant__ Params p, const __gr
    const int Q = p.Q;
    if (tid == 0) {
       for (int c = 0; c < p.nchains; c++) {
+         if (p.worm_on && p.wstate[(size_t)c * 8]) continue;      // a chain in the G sector contributes no sample
          double r2 = 0, pot = 0, srot = 0, sesq = 0, sterm = 0;
          for (int b = 0; b < EST_BLOCKS; b++) {
             const double *o = e.partials + ((size_t)c * EST_BLOCKS + b) * NPART;
@@ -430,6 +434,7 @@ __global__ void est_finalize_kernel(const __grid_constant__ Params p, const __gr
       const int nb = p.numb[p.bstype], b0 = p.first[p.bstype];
       const bool lin = p.imtype >= 0 && p.molecule[p.imtype] == 1, mff = p.imtype >= 0 && p.molecule[p.imtype] == 2 && p.ispher == 0;
       for (int c = 0; c < p.nchains; c++) {
+         if (p.worm_on && p.wstate[(size_t)c * 8]) continue;
          double *ca = e.chain_area + (size_t)c * NAREA;
          for (int k = 0; k < NAREA; k++) {
             double s = 0.0;
@@ -464,7 +469,8 @@ __global__ void est_finalize_kernel(const __grid_constant__ Params p, const __gr
    if (accumulate && Q > 0)
       for (int itc = tid; itc < Q; itc += gridDim.x * blockDim.x) {
          double s = 0.0;
-         for (int c = 0; c < p.nchains; c++) s += e.chain_rcf[(size_t)c * Q + itc];
+         for (int c = 0; c < p.nchains; c++)
+            if (!(p.worm_on && p.wstate[(size_t)c * 8])) s += e.chain_rcf[(size_t)c * Q + itc];
          e.acc[e.off_rcf + itc] += s;
       }
 }
@@ -489,6 +495,7 @@ __global__ void symmetry_kernel(const __grid_constant__ Params p, const int *ops
 {
    __shared__ int op[4];
    const int c = blockIdx.x, Q = p.Q, nm = p.NM;
+   if (p.worm_on && p.wstate[(size_t)c * 8]) return;      // applied inside MCGetAverage: Z sector only
    if (threadIdx.x == 0) {
       op[0] = op[1] = op[2] = 0; op[3] = -1;
       if (ops) { for (int k = 0; k < 4; k++) op[k] = ops[c * 4 + k]; }
@@ -554,6 +561,17 @@ __global__ void symmetry_kernel(const __grid_constant__ Params p, const int *ops
          const int it = (int)(i / p.Npad), a = (int)(i % p.Npad);
          p.pos[pos_index(p, c, it, 1, a)] *= -1.0;
       }
+}
+
+// one MCWormMove per chain outside the step kernel (parity entry point; one CTA per chain)
+template <int KIND>
+__global__ void __launch_bounds__(256) worm_move_kernel(const __grid_constant__ Params p)
+{
+   extern __shared__ double wsm[];
+   SmallTables t;
+   t.g1d = p.g1d; t.v1d = p.v1d; t.y2_1d = p.y2_1d; t.lut1d = p.lut1d; t.rgrid = p.rgrid; t.rdens = p.rdens; t.rdens2 = p.rdens2;
+   t.lutrot = p.lutrot; t.rec1d = p.rec1d; t.recrot = p.recrot; t.rgi2d = p.rgi2d; t.cgi2d = p.cgi2d;
+   worm_sweep_cta<KIND>(p, t, blockIdx.x, wsm, reinterpret_cast<unsigned char *>(wsm + 64));
 }
 
 // ---- parity kernels -----------------------------------------------------------------------------
@@ -622,7 +640,7 @@ __global__ void pot_energy_slice_kernel(const __grid_constant__ Params p, int c,
    for (int d = 0; d < 3; d++) p0[d] = p.pos[pos_index(p, c, it, d, atom)];
    double s = 0.0;
    for (int j = lane; j < p.N; j += 32)
-      if (j != atom) s += pair_energy(p, t, c, atom, p0, j, it, nullptr, nullptr);
+      if (j != atom && partner_on_line(p, c, j, it)) s += pair_energy(p, t, c, atom, p0, j, it, nullptr, nullptr);
    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
    if (lane == 0) v[(size_t)atom * p.P + it] = s;
 }

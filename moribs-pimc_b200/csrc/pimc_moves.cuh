@@ -11,8 +11,9 @@
 //     the lanes split the (midpoint, partner) terms of the pair-action sum; warp butterfly + fixed-order combine;
 //   * rotational slices -> ROT GROUPS of `rot_group` threads (power of two, may span several warps of one CTA).
 // Every reduction has a fixed order, so a trajectory is bit-reproducible for a given geometry.
-// The kernel is specialised at compile time on the rotor kind (KIND 0 atoms only, 1 linear rotor,
-// 2 non-linear top) so each variant carries only its own interaction branches.
+// The kernel is specialised at compile time on the rotor kind (KIND & 3: 0 atoms only, 1 linear rotor,
+// 2 non-linear top) so each variant carries only its own interaction branches, and on the worm (KIND & 4):
+// the worm moves and the world-line masks of the pair loops exist only in the variants that need them.
 //
 // Schedule (DESIGN.md "Schedule"; the CPU replay is oracle/pimc_oracle.cpp:orc_sched_run):
 //   step t, time = t mod P, for each type:
@@ -26,6 +27,7 @@
 // time steps behind split arrive/wait counters (rot_sweep_pipe).
 #pragma once
 #include "pimc_device.cuh"
+#include "pimc_worm.cuh"
 #include <cooperative_groups.h>
 
 namespace pimc {
@@ -131,7 +133,7 @@ __device__ double chain_reduce(const Params &p, Ctx &x, double v)
 template <int KIND>
 __device__ __forceinline__ double pair_diff(const Params &p, const SmallTables &t, int c, int g, const double *pn, const double *po, int j, int it)
 {
-   if (KIND != 2 && p.mode[type_of(p, g)][type_of(p, j)] == M_SPOT1D && !p.minimage) {
+   if ((KIND & 3) != 2 && p.mode[type_of(p, g)][type_of(p, j)] == M_SPOT1D && !p.minimage) {
       double d2n = 0.0, d2o = 0.0;
       #pragma unroll
       for (int d = 0; d < 3; d++) {
@@ -141,7 +143,7 @@ __device__ __forceinline__ double pair_diff(const Params &p, const SmallTables &
       }
       return spot1d_move(p, t, sqrt(d2n)) - spot1d_move(p, t, sqrt(d2o));
    }
-   if (KIND == 1 && p.mode[type_of(p, g)][type_of(p, j)] == M_LIN_1MOL && !p.minimage) {
+   if ((KIND & 3) == 1 && p.mode[type_of(p, g)][type_of(p, j)] == M_LIN_1MOL && !p.minimage) {
       // atom bead (new and old position) against the linear rotor: shared partner loads, both bilinear forms in flight
       const int q = it / p.R, m = j - p.first[p.imtype];
       double rr[2], cs[2], e[2], d2n = 0.0, d2o = 0.0, dn = 0.0, dold = 0.0;
@@ -157,7 +159,7 @@ __device__ __forceinline__ double pair_diff(const Params &p, const SmallTables &
       lpot2d_xn<2>(p, t, rr, cs, e);
       return e[0] - e[1];
    }
-   return pair_energy<KIND>(p, t, c, g, pn, j, it, nullptr, nullptr) - pair_energy<KIND>(p, t, c, g, po, j, it, nullptr, nullptr);
+   return pair_energy<(KIND & 3)>(p, t, c, g, pn, j, it, nullptr, nullptr) - pair_energy<(KIND & 3)>(p, t, c, g, po, j, it, nullptr, nullptr);
 }
 
 // sum over the partners j = lane, lane+stride, ... of V(g at pn) - V(g at po) at slice it.  When the moved bead is an atom of
@@ -166,7 +168,7 @@ __device__ __forceinline__ double pair_diff(const Params &p, const SmallTables &
 template <int KIND>
 __device__ __forceinline__ bool fast_atoms(const Params &p, int tg)
 {
-   return (KIND != 2) && p.molecule[tg] == 0 && !p.minimage && p.n1d > 0;      // moved bead is an atom of a spline system
+   return ((KIND & 3) != 2) && p.molecule[tg] == 0 && !p.minimage && p.n1d > 0;      // moved bead is an atom of a spline system
 }
 template <int KIND>
 __device__ __forceinline__ double partner_sum_diff(const Params &p, const SmallTables &t, int c, int g, const double *pn, const double *po,
@@ -208,7 +210,7 @@ __device__ __forceinline__ double partner_sum_diff(const Params &p, const SmallT
       return D;
    }
    for (int j = lane; j < N; j += stride) {
-      if (j == g) continue;
+      if (j == g || !partner_on_line<KIND>(p, c, j, it)) continue;         // world-line mask of an open worm (a22)
       D += pair_diff<KIND>(p, t, c, g, pn, po, j, it);
    }
    return D;
@@ -268,7 +270,7 @@ __device__ void molecular_sweep(const Params &p, Ctx &x, int type)
             int a0 = cyc_atoms[b + (int)(r / P)];
             bool member = false;
             for (int k = 0; k < len; k++) member |= (cyc_atoms[b + k] == j);
-            if (member) continue;
+            if (member || !partner_on_line<KIND>(p, c, j, it)) continue;
             double po[3], pn[3];
             #pragma unroll
             for (int d = 0; d < 3; d++) { po[d] = p.pos[pos_index(p, c, it, d, a0)]; pn[d] = po[d] + disp[d]; }
@@ -490,7 +492,7 @@ __device__ __forceinline__ double rot_potential(const Params &p, Ctx &x, int g, 
 {
    const int c = x.c, N = p.N, R = p.R, it0 = q * R;
    double v = 0.0;
-   if (KIND == 2) {
+   if ((KIND & 3) == 2) {
       Mat3 ro;
       #pragma unroll
       for (int i = 0; i < 9; i++) ro.m[i / 3][i % 3] = o[i];
@@ -510,6 +512,7 @@ __device__ __forceinline__ double rot_potential(const Params &p, Ctx &x, int g, 
             }
          } else {
             for (int r = 0; r < R; r++) {
+               if (!partner_on_line<KIND>(p, c, j, it0 + r)) continue;
                double pg[3], pj[3];
                #pragma unroll
                for (int d = 0; d < 3; d++) { pg[d] = p.pos[pos_index(p, c, it0 + r, d, g)]; pj[d] = p.pos[pos_index(p, c, it0 + r, d, j)]; }
@@ -534,7 +537,7 @@ __device__ __forceinline__ double rot_potential(const Params &p, Ctx &x, int g, 
             #pragma unroll
             for (int u = 0; u < 4; u++) {
                const int j = j0 + u * lanes;
-               ok[u] = j < N && j != g;
+               ok[u] = j < N && j != g && partner_on_line<KIND>(p, c, min(j, N - 1), it);
                const int jj = ok[u] ? j : (g == 0 ? 1 : 0);        // a valid, distinct partner for masked slots
                double dx = gx - px[jj], dy = gy - py[jj], dz = gz - pz[jj];
                double dr2 = dx * dx + dy * dy + dz * dz;
@@ -561,7 +564,7 @@ __device__ __forceinline__ void rot_propose(const Params &p, int type, double r1
 {
    const double step = p.rtstep[type];
    cost += step * (r1 - 0.5);
-   if (KIND == 2) {
+   if ((KIND & 3) == 2) {
       phi += 2.0 * PI * (step * (r2 - 0.5));
       chi += 2.0 * PI * (step * (r3 - 0.5));
       if (phi < 0.0) phi = 2.0 * PI + phi;
@@ -573,7 +576,7 @@ __device__ __forceinline__ void rot_propose(const Params &p, int type, double r1
    }
    if (cost > 1.0) cost = 2.0 - cost;
    if (cost < -1.0) cost = -2.0 - cost;
-   if (KIND == 2) {
+   if ((KIND & 3) == 2) {
       Mat3 Rn;
       matpre(phi, acos(cost), chi, Rn);
       #pragma unroll
@@ -595,7 +598,7 @@ __device__ __forceinline__ bool rot_accept(const Params &p, const double *rho, d
       double dens_old = rho[0] * rho[1], dens_new = rho[2] * rho[3];
       if (fabs(dens_old) < RZERO) dens_old = 0.0;
       if (fabs(dens_new) < RZERO) dens_new = 0.0;
-      if (KIND == 2) { dens_old = fabs(dens_old); dens_new = fabs(dens_new); }
+      if ((KIND & 3) == 2) { dens_old = fabs(dens_old); dens_new = fabs(dens_new); }
       else if (dens_old < 0.0 || dens_new < 0.0) *bad |= 2;     // "Negative rot density" is fatal in the reference
       double rd = (dens_old > RZERO) ? dens_new / dens_old : 1.0;
       rd *= exp(-p.tau * (vnew - vold));
@@ -603,7 +606,7 @@ __device__ __forceinline__ bool rot_accept(const Params &p, const double *rho, d
    }
    // rattle-and-shake propagator: the acceptance works on exponents (mc_piqmc.cc:903-921, 1152-1178)
    double rd;
-   if (KIND == 2) rd = ((rho[2] + rho[3]) - (rho[0] + rho[1])) / (4.0 * (p.rottau / WNO2K));
+   if ((KIND & 3) == 2) rd = ((rho[2] + rho[3]) - (rho[0] + rho[1])) / (4.0 * (p.rottau / WNO2K));
    else {
       double dens_old = rho[0] + rho[1], dens_new = rho[2] + rho[3];
       if (fabs(dens_old) < RZERO) dens_old = 0.0;
@@ -620,7 +623,7 @@ template <int KIND>
 __device__ __forceinline__ double rot_density(const Params &p, const SmallTables &t, int c, int q0, int q2, int m, int i, const double *cur, const double *nw, int *bad)
 {
    const double *mid = (i < 2) ? cur : nw;
-   if (KIND == 2) {
+   if ((KIND & 3) == 2) {
       Mat3 A, B;
       if (i == 0 || i == 2) {
          load_rotmat(p, c, q0, m, A);
@@ -653,7 +656,7 @@ __device__ __forceinline__ void rot_commit(const Params &p, int c, int q, int m,
 {
    p.ang[ang_index(p, c, q, 1, m)] = cost;
    p.ang[ang_index(p, c, q, 0, m)] = phi;
-   if (KIND == 2) p.ang[ang_index(p, c, q, 2, m)] = chi;
+   if ((KIND & 3) == 2) p.ang[ang_index(p, c, q, 2, m)] = chi;
    const double sint = sqrt(1.0 - cost * cost);
    double sp_, cp_;
    sincos(phi, &sp_, &cp_);
@@ -681,10 +684,10 @@ __device__ void rot_step(const Params &p, Ctx &x, int type, int q, int m, bool a
       Mrg rs;
       mrg_load(rs, sp);
       double r1 = mrg_u01(rs), r2 = mrg_u01(rs), r3 = mrg_u01(rs), r4 = r3;
-      if (KIND == 2) r4 = mrg_u01(rs);
+      if ((KIND & 3) == 2) r4 = mrg_u01(rs);
       mrg_store(rs, sp);
       double cost = p.ang[ang_index(p, c, q, 1, m)], phi = p.ang[ang_index(p, c, q, 0, m)], chi = p.ang[ang_index(p, c, q, 2, m)];
-      if (KIND == 2) {
+      if ((KIND & 3) == 2) {
          Mat3 R1;
          matpre(phi, acos(cost), chi, R1);
          #pragma unroll
@@ -738,7 +741,7 @@ __device__ void rot_step(const Params &p, Ctx &x, int type, int q, int m, bool a
       if (acc) {
          atomicAdd(cn + 1, 1.0);
          rot_commit<KIND>(p, c, q, m, sl->cost, sl->phi, sl->chi);
-         if (KIND == 2)
+         if ((KIND & 3) == 2)
             for (int mm = 0; mm < p.NM; mm++)            // partner rotors at this slice see a new neighbour
                if (mm != m) p.vepoch[((size_t)c * Q + q) * p.NMpad + mm] = -1;
       }
@@ -842,7 +845,7 @@ __device__ __forceinline__ void rot_decide_owned(const Params &p, Ctx &x, int ty
             rot_commit<KIND>(p, c, q, m, sl->cost, sl->phi, sl->chi);
             sl->cur[0] = sl->cost; sl->cur[1] = sl->phi; sl->cur[2] = sl->chi;
             #pragma unroll
-            for (int i = 0; i < (KIND == 2 ? 9 : 3); i++) sl->b[i] = sl->a[i];
+            for (int i = 0; i < ((KIND & 3) == 2 ? 9 : 3); i++) sl->b[i] = sl->a[i];
          }
       }
       group_sync(x);
@@ -866,7 +869,7 @@ __device__ void rot_sweep_pipe(const Params &p, Ctx &x, int type, int *err)
          Mrg rs;
          mrg_load(rs, x.rrng + ls * 6);
          double r1 = mrg_u01(rs), r2 = mrg_u01(rs), r3 = mrg_u01(rs), r4 = r3;
-         if (KIND == 2) r4 = mrg_u01(rs);
+         if ((KIND & 3) == 2) r4 = mrg_u01(rs);
          mrg_store(rs, x.rrng + ls * 6);
          const int epoch = p.pos_epoch[c];
          double cost = sl->cur[0], phi = sl->cur[1], chi = sl->cur[2];     // current state and orientation live in the slot
@@ -1002,7 +1005,7 @@ pimc_steps_kernel(const __grid_constant__ Params p, long t0, long nsteps, int *e
    x.part = cursor + 2 * (size_t)((x.tid >> 5) - (x.gl >> 5));      // first warp of this thread's rot group
    cursor += 2 * (size_t)(blockDim.x >> 5);
    x.rrng = reinterpret_cast<uint32_t *>(cursor);
-   const bool piped = (KIND != 0) && p.rot_fused && p.Q > 0;
+   const bool piped = ((KIND & 3) != 0) && p.rot_fused && p.Q > 0;
    const int nown = (p.Q + p.cpc - 1) / p.cpc;
    x.rot_iter = 0;
    if (piped) {
@@ -1018,7 +1021,7 @@ pimc_steps_kernel(const __grid_constant__ Params p, long t0, long nsteps, int *e
          RotSlot *sl = x.slot + ls;
          const double phi = p.ang[ang_index(p, x.c, q, 0, 0)], cost = p.ang[ang_index(p, x.c, q, 1, 0)], chi = p.ang[ang_index(p, x.c, q, 2, 0)];
          sl->cur[0] = cost; sl->cur[1] = phi; sl->cur[2] = chi;
-         if (KIND == 2) {
+         if ((KIND & 3) == 2) {
             Mat3 R1;
             matpre(phi, acos(cost), chi, R1);
             for (int i = 0; i < 9; i++) sl->b[i] = R1.m[i / 3][i % 3];
@@ -1031,6 +1034,12 @@ pimc_steps_kernel(const __grid_constant__ Params p, long t0, long nsteps, int *e
       __syncthreads();
    } else x.slot = reinterpret_cast<RotSlot *>(cursor) + x.grp;      // one slot per rot group
 
+   // worm scratch (WormShared + neighbour lists) behind the rot slots
+   unsigned char *worm_scr = nullptr;
+   if ((KIND & 4) && p.worm_on) {
+      size_t off = (size_t)(piped ? nown : (x.G > 1 ? (int)(blockDim.x / x.G) : 0)) * sizeof(RotSlot);
+      worm_scr = reinterpret_cast<unsigned char *>(cursor) + ((off + 15) & ~(size_t)15);
+   }
    // time = t mod P and, per type, time mod (P/seg) and time / (P/seg), advanced incrementally (no divisions in the loop)
    int time = (int)(t0 % p.P), tmod[MAXT], toff[MAXT], tnseg[MAXT];
    for (int type = 0; type < p.ntypes; type++) {
@@ -1041,11 +1050,18 @@ pimc_steps_kernel(const __grid_constant__ Params p, long t0, long nsteps, int *e
    for (long s = 0; s < nsteps; s++) {
       // does the NEXT step start with a translational sweep?  (decided before this step's rotational sweep runs ahead)
       bool next_trans = false;
-      for (int type = 0; type < p.ntypes; type++) next_trans |= (tmod[type] + 1 == tnseg[type]) || (time + 1 == p.P);
+      for (int type = 0; type < p.ntypes; type++) next_trans |= (tmod[type] + 1 == tnseg[type]) || (time + 1 == p.P) || p.worm_on;
       for (int type = 0; type < p.ntypes; type++) {
-         if (time == 0) molecular_sweep<KIND>(p, x, type);
-         if (tmod[type] == 0) bisection_sweep<KIND>(p, x, type, toff[type]);
-         if (KIND != 0 && type == p.imtype && p.Q > 0) {
+         bool closed = true;
+         if ((KIND & 4) && p.worm_on && type == p.worm_type) {
+            // mc_main.cc:355-379: MCWormMove, then the path moves of this type in the Z sector only
+            if (x.crank == 0) worm_sweep_cta<KIND>(p, x.t, x.c, x.red, worm_scr);
+            chain_sync(p, x);
+            closed = p.wstate[(size_t)x.c * 8] == 0;
+         }
+         if (time == 0 && closed) molecular_sweep<KIND>(p, x, type);
+         if (tmod[type] == 0 && closed) bisection_sweep<KIND>(p, x, type, toff[type]);
+         if ((KIND & 3) != 0 && type == p.imtype && p.Q > 0) {
             if (piped) {
                rot_sweep_pipe<KIND>(p, x, type, err);
                // a translational sweep (or the end of the launch) needs every decision of this sweep: full barrier

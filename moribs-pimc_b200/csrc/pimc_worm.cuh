@@ -1,0 +1,417 @@
+// Worm moves on the device: open, close, advance, recede and swap of
+// mc_qworm.cc:93-667 for one chain, executed by CTA 0 of the chain.  The moves of one MCWormMove call are inherently
+// sequential (each starts from the worm the previous one left), so thread 0 carries the control flow -- uniforms,
+// Levy-bridge sampling of the <= m new beads, the permutation table of the swap -- while every potential sum over
+// (slices of the segment) x (partners) is dealt to all threads of the CTA and reduced in a fixed order.
+//
+// All uniforms come from ONE MRG32k3a stream of the chain (index P + Q + 1) in program order; the CPU replay is
+// oracle/pimc_oracle.cpp:worm_move in schedule mode.  Worm atoms are numbered inside the worm's type, as in the
+// reference (Worm.atom_i, Worm.atom_m, PIndex, RIndex); the device arrays pindex/rindex hold global atom indices.
+#pragma once
+#include "pimc_device.cuh"
+
+namespace pimc {
+
+constexpr int QW_OPEN = 0, QW_CLOSE = 1, QW_ADVANCE = 4, QW_RECEDE = 5, QW_SWAP = 6;     // mc_qworm.h:58-64
+constexpr int WORM_MAXM = 64;          // largest Worm.m the per-CTA scratch holds
+constexpr int WORM_MAXNEIGHBORS = 100; // mc_qworm.cc:12
+
+// WorldLine(atom, pt), mc_qworm.cc:553-575; st = {exists, ira, masha, atom_i, atom_m}
+__device__ __forceinline__ bool worm_world_line(const int *st, int atom, int pt)
+{
+   const int ira = st[1], masha = st[2], atom_i = st[3], atom_m = st[4];
+   bool wline = true;
+   if ((atom == atom_m) || (atom == atom_i)) {
+      if ((atom_i != atom_m) || (ira > masha)) {
+         if (((atom == atom_m) && (pt < masha)) || ((atom == atom_i) && (pt > ira))) wline = false;
+      } else {
+         if ((pt > ira) && (pt < masha)) wline = false;
+      }
+   }
+   return wline;
+}
+// the mask of the PotEnergy partner loops (mc_piqmc.cc:1226-1227,1816-1817,2000-2001,2082-2083): false when partner j
+// must be skipped at slice it
+template <int KIND = 4>
+__device__ __forceinline__ bool partner_on_line(const Params &p, int c, int j, int it)
+{
+   if (!(KIND & 4)) return true;          // kernel variant without a worm: no mask code at all
+   if (!p.worm_on) return true;
+   const int *st = p.wstate + (size_t)c * 8;
+   if (!st[0] || type_of(p, j) != p.worm_type) return true;
+   return worm_world_line(st, j - p.first[p.worm_type], it);
+}
+
+struct WormShared {
+   int st[5];                 // exists, ira, masha, atom_i, atom_m
+   int it0, it1, atom0, atom1, use_path, diff, go, changed, perm_changed;
+   double path[(WORM_MAXM + 2) * 3];     // swap: the proposed path, point k = it - it0
+   double result;
+};
+
+// sum over the open interval (it0, it1) of PotEnergy(atom(it), pos, it mod P) -- get_potential, mc_qworm.cc:400-422 -- with
+// the moving atom's beads from the state (use_path = 0) or from the proposed path; diff = 1 subtracts the same sum for the
+// beads of the state (qworm_swap, mc_qworm.cc:479-489).  All threads of the CTA; returns the total to every thread.
+template <int KIND>
+__device__ double worm_pot_sum(const Params &p, const SmallTables &t, int c, const WormShared &w, double *red)
+{
+   const int P = p.P, N = p.N, base = p.first[p.worm_type];
+   const int it0 = w.it0, it1 = w.it1, nint = it1 - it0 - 1;
+   const int pit0 = it0 % P;
+   double s = 0.0;
+   for (int i = threadIdx.x; i < nint * N; i += blockDim.x) {
+      const int k = i / N, j = i - k * N;
+      const int it = it0 + 1 + k, pit = it % P;
+      int atom = w.atom0;
+      if (w.diff) { if (pit != it) atom = w.atom1; }                       // qworm_swap switches on the wrap alone
+      else if ((pit != it) && (pit0 == it0)) atom = w.atom1;
+      const int g = base + atom;
+      if (j == g) continue;
+      // the mask uses the worm as it stands in shared memory (the open move evaluates with exists = 0)
+      if (w.st[0] && type_of(p, j) == p.worm_type && !worm_world_line(w.st, j - base, pit)) continue;
+      double pn[3], po[3];
+      #pragma unroll
+      for (int d = 0; d < 3; d++) {
+         po[d] = p.pos[pos_index(p, c, pit, d, g)];
+         pn[d] = w.use_path ? w.path[(it - it0) * 3 + d] : po[d];
+      }
+      s += pair_energy<(KIND & 3)>(p, t, c, g, pn, j, pit, nullptr, nullptr);
+      if (w.diff) s -= pair_energy<(KIND & 3)>(p, t, c, g, po, j, pit, nullptr, nullptr);
+   }
+   // fixed-order block reduction
+   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+   const int warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+   __syncthreads();
+   if ((threadIdx.x & 31) == 0) red[warp] = s;
+   __syncthreads();
+   double tot = 0.0;
+   for (int k = 0; k < nwarp; k++) tot += red[k];
+   __syncthreads();
+   return tot;
+}
+
+struct WormRng { Mrg g; };
+__device__ __forceinline__ double w_gauss(Mrg &g, double alpha)          // mc_randg.cc:138-150
+{
+   const double r1 = mrg_u01(g), r2 = mrg_u01(g);
+   const double x1 = sqrt(-log(r1)) * cos(2.0 * PI * r2);
+   return (x1 / sqrt(alpha));
+}
+__device__ __forceinline__ int w_nrnd(Mrg &g, int n) { return (int)floor(n * mrg_u01(g)); }
+
+// sample_middle, mc_qworm.cc:240-287, in the recursion's own (pre-)order; thread 0 only.  Points live in the state
+// (path == nullptr; atom0 before the wrap, atom2 after it) or in the proposed path of the swap.
+__device__ void worm_sample_middle(const Params &p, int c, Mrg &g, int it0r, int it2r, int atom0r, int atom2r, double *path)
+{
+   const int P = p.P, base = p.first[p.worm_type];
+   int stk[16][4], sp = 0;
+   stk[sp][0] = it0r; stk[sp][1] = it2r; stk[sp][2] = atom0r; stk[sp][3] = atom2r; sp++;
+   while (sp > 0) {
+      sp--;
+      const int it0 = stk[sp][0], it2 = stk[sp][1], atom0 = stk[sp][2], atom2 = stk[sp][3];
+      if ((it2 - it0) < 2) continue;
+      const int it1 = (int)rint(0.5 * (double)(it0 + it2));
+      const int pt0 = it0 % P, pt1 = it1 % P, pt2 = it2 % P;
+      int atom1 = atom0;
+      if ((pt1 != it1) && (pt0 == it0)) atom1 = atom2;
+      const double s0 = (double)(it1 - it0), s2 = (double)(it2 - it1);
+      const double gkin = (s0 + s2) / (p.worm_twave2 * s0 * s2);
+      #pragma unroll
+      for (int d = 0; d < 3; d++) {
+         double x0, x2;
+         if (path) { x0 = path[(it0 - it0r) * 3 + d]; x2 = path[(it2 - it0r) * 3 + d]; }
+         else { x0 = p.pos[pos_index(p, c, pt0, d, base + atom0)]; x2 = p.pos[pos_index(p, c, pt2, d, base + atom2)]; }
+         double x1 = (s2 * x0 + s0 * x2) / (s0 + s2);
+         x1 += w_gauss(g, gkin);
+         if (path) path[(it1 - it0r) * 3 + d] = x1;
+         else p.pos[pos_index(p, c, pt1, d, base + atom1)] = x1;
+      }
+      // left half first, then the right half: push right, then left
+      stk[sp][0] = it1; stk[sp][1] = it2; stk[sp][2] = atom1; stk[sp][3] = atom2; sp++;
+      stk[sp][0] = it0; stk[sp][1] = it1; stk[sp][2] = atom0; stk[sp][3] = atom1; sp++;
+   }
+}
+
+// get_ptable, mc_qworm.cc:577-643: neighbours of world line atomw at slice pt0 among the beads at slice pt1, sorted by
+// distance (mmsort, mc_utils.cc:206-231), weights exp(-dr^2 / (segm * 4 lambda tau)); entries 1..count.  Thread 0 only.
+__device__ int worm_get_ptable(const Params &p, int c, const int *st, int atomw, int pt0, int pt1, int segm, int t1,
+                               double *dr2_list, int *atm_list, double *ptable)
+{
+   const int base = p.first[p.worm_type], numb = p.numb[p.worm_type];
+   const int *rindex = p.rindex + (size_t)c * p.N;
+   int count = 0;
+   for (int atom1 = 0; atom1 < numb; atom1++)
+      if (worm_world_line(st, atom1, pt1)) {
+         int atom0 = atom1;
+         if (t1 != pt1) atom0 = rindex[base + atom1] - base;
+         if (atom0 != st[3]) {
+            double dr2 = 0.0;
+            #pragma unroll
+            for (int d = 0; d < 3; d++) {
+               double dx = p.pos[pos_index(p, c, pt0, d, base + atomw)] - p.pos[pos_index(p, c, pt1, d, base + atom1)];
+               if (p.minimage) dx -= (p.box[d] * rint(dx / p.box[d]));
+               dr2 += (dx * dx);
+            }
+            if (dr2 < p.worm_cutoff2) { count++; dr2_list[count] = dr2; atm_list[count] = atom1; }
+         }
+      }
+   for (int j = 2; j <= count; j++) {
+      const double dtmp = dr2_list[j];
+      const int itmp = atm_list[j];
+      int i = j - 1;
+      while ((i > 0) && (dr2_list[i] > dtmp)) { dr2_list[i + 1] = dr2_list[i]; atm_list[i + 1] = atm_list[i]; i--; }
+      dr2_list[i + 1] = dtmp; atm_list[i + 1] = itmp;
+   }
+   if (count > WORM_MAXNEIGHBORS) count = WORM_MAXNEIGHBORS;
+   const double norm = 1.0 / ((double)segm * p.worm_twave2);
+   for (int ic = 1; ic <= count; ic++) ptable[ic] = exp(-norm * dr2_list[ic]);
+   return count;
+}
+
+// permutation cycles of every type from pindex (what pimcgpu_upload_state prepares on the host); thread 0 only
+__device__ void worm_rebuild_cycles(const Params &p, int c, int *seen /* [N] scratch */)
+{
+   const int N = p.N;
+   const int *pindex = p.pindex + (size_t)c * N;
+   int *cstart = p.cyc_start + (size_t)c * (N + 1), *catoms = p.cyc_atoms + (size_t)c * N, *ncyc = p.ncyc + (size_t)c * MAXT;
+   for (int a = 0; a < N; a++) seen[a] = 0;
+   int ns = 0, na = 0;
+   for (int t = 0; t < p.ntypes; t++) {
+      ncyc[t] = 0;
+      for (int a = p.first[t]; a < p.first[t] + p.numb[t]; a++) {
+         if (seen[a]) continue;
+         cstart[ns++] = na;
+         int b = a;
+         do { catoms[na++] = b; seen[b] = 1; b = pindex[b]; } while (b != a && na <= N);
+         ncyc[t]++;
+      }
+   }
+   while (ns < N + 1) cstart[ns++] = na;
+}
+
+// MCWormMove, mc_qworm.cc:93-125, for chain c by the calling CTA.  `scratch` holds WormShared and the neighbour lists.
+template <int KIND>
+__device__ void worm_sweep_cta(const Params &p, const SmallTables &t, int c, double *red, unsigned char *scratch)
+{
+   WormShared &w = *reinterpret_cast<WormShared *>(scratch);
+   double *dr2_list = reinterpret_cast<double *>(scratch + ((sizeof(WormShared) + 15) & ~15));
+   double *ptable = dr2_list + (p.N + 2);
+   int *atm_list = reinterpret_cast<int *>(ptable + (p.N + 2));
+   int *seen = atm_list + (p.N + 2);
+   const int P = p.P, base = p.first[p.worm_type], numb = p.numb[p.worm_type], tid = threadIdx.x;
+   int *gst = p.wstate + (size_t)c * 8;
+   int *pindex = p.pindex + (size_t)c * p.N, *rindex = p.rindex + (size_t)c * p.N;
+   double *qw = p.qwc + (size_t)c * 16;
+   uint32_t *sp = p.rng + ((size_t)c * p.S + p.P + p.Q + 1) * 6;
+   Mrg g;
+   if (tid == 0) {
+      mrg_load(g, sp);
+      for (int i = 0; i < 5; i++) w.st[i] = gst[i];
+      w.changed = 0; w.perm_changed = 0;
+   }
+   __syncthreads();
+   const bool bose_worm = p.bstype >= 0 && p.worm_type == p.bstype;
+   for (int atom = 0; atom < numb; atom++) {
+      // ---------------- open / close ----------------
+      int segm = 0;
+      if (tid == 0) {
+         qw[14] += 1.0;
+         w.go = 0;
+         if (w.st[0]) {                                     // qworm_close, mc_qworm.cc:184-238
+            qw[QW_CLOSE] += 1.0;
+            segm = w.st[2] - w.st[1];
+            if (segm < 0) segm += P;
+            if (segm <= p.worm_m) {
+               worm_sample_middle(p, c, g, w.st[1], w.st[1] + segm, w.st[3], w.st[4], nullptr);
+               w.go = 1;
+            }
+         } else {                                           // qworm_open, mc_qworm.cc:155-182
+            qw[QW_OPEN] += 1.0;
+            w.st[3] = w_nrnd(g, numb);
+            w.st[1] = w_nrnd(g, P);
+            segm = w_nrnd(g, p.worm_m) + 1;
+            w.st[2] = (w.st[1] + segm) % P;
+            w.st[4] = w.st[3];
+            if (w.st[2] != (w.st[1] + segm)) w.st[4] = pindex[base + w.st[3]] - base;
+            w.go = 1;
+         }
+         w.it0 = w.st[1]; w.it1 = w.st[1] + segm; w.atom0 = w.st[3]; w.atom1 = w.st[4]; w.use_path = 0; w.diff = 0;
+      }
+      __syncthreads();
+      if (w.go) {
+         // qw_open_prob, mc_qworm.cc:127-153
+         const double pot = worm_pot_sum<KIND>(p, t, c, w, red);
+         if (tid == 0) {
+            double kin = 0.0;
+            #pragma unroll
+            for (int d = 0; d < 3; d++) {
+               double dr = p.pos[pos_index(p, c, w.st[1], d, base + w.st[3])] - p.pos[pos_index(p, c, w.st[2], d, base + w.st[4])];
+               if (p.minimage) dr -= (p.box[d] * rint(dr / p.box[d]));
+               kin += (dr * dr);
+            }
+            kin /= (p.worm_twave2 * (double)segm);
+            const double popen = p.worm_norm * pow((double)segm, 0.5 * 3.0) * exp(kin + pot * p.tau);
+            const double prob = w.st[0] ? 1.0 / popen : popen;
+            bool acc = false;
+            if (prob >= 1.0) acc = true;
+            else if (prob > mrg_u01(g)) acc = true;
+            if (acc) {
+               if (w.st[0]) { w.st[0] = 0; qw[7 + QW_CLOSE] += 1.0; }
+               else { w.st[0] = 1; qw[7 + QW_OPEN] += 1.0; }
+               w.changed = 1;
+            }
+         }
+      }
+      __syncthreads();
+      // ---------------- advance / recede ----------------
+      if (w.st[0]) {
+         if (tid == 0) {
+            qw[14] += 1.0;
+            w.go = 0;
+            const double r = mrg_u01(g);
+            if (r > 0.5) {                                  // qworm_advance, mc_qworm.cc:299-357
+               qw[QW_ADVANCE] += 1.0;
+               int sg = w.st[2] - w.st[1];
+               if (sg < 0) sg += P;
+               const int advance = w_nrnd(g, p.worm_m) + 1;
+               if (sg - advance > 0) {
+                  const int it0 = w.st[1], it2 = w.st[1] + advance;
+                  const int ira_new = it2 % P;
+                  int atom_i_new = w.st[3];
+                  if (ira_new != it2) atom_i_new = w.st[4];
+                  const double gvar = 1.0 / ((double)advance * p.worm_twave2);
+                  #pragma unroll
+                  for (int d = 0; d < 3; d++)
+                     p.pos[pos_index(p, c, it2 % P, d, base + atom_i_new)] = p.pos[pos_index(p, c, it0 % P, d, base + w.st[3])] + w_gauss(g, gvar);
+                  worm_sample_middle(p, c, g, it0, it2, w.st[3], atom_i_new, nullptr);
+                  w.it0 = it0; w.it1 = it2 + 1; w.atom0 = w.st[3]; w.atom1 = atom_i_new; w.use_path = 0; w.diff = 0;
+                  w.go = 1;
+               }
+            } else {                                        // qworm_recede, mc_qworm.cc:359-398
+               qw[QW_RECEDE] += 1.0;
+               int sg = w.st[1] - w.st[2];
+               if (sg < 0) sg += P;
+               const int recede = w_nrnd(g, p.worm_m) + 1;
+               if ((sg - recede) >= 1) {
+                  int it0 = w.st[1] - recede, it1 = w.st[1];
+                  int atom0 = w.st[3];
+                  const int atom1 = w.st[3];
+                  if (it0 < 0) { it0 += P; it1 += P; atom0 = rindex[base + atom1] - base; }
+                  w.it0 = it0; w.it1 = it1 + 1; w.atom0 = atom0; w.atom1 = atom1; w.use_path = 0; w.diff = 0;
+                  w.go = 2;
+               }
+            }
+         }
+         __syncthreads();
+         if (w.go) {
+            const double pot = worm_pot_sum<KIND>(p, t, c, w, red);
+            if (tid == 0) {
+               bool acc = false;
+               if (w.go == 1) {
+                  if (pot < 0.0) acc = true;
+                  else if (exp(-pot * p.tau) > mrg_u01(g)) acc = true;
+                  if (acc) { qw[7 + QW_ADVANCE] += 1.0; w.st[1] = (w.it1 - 1) % P; w.st[3] = w.atom1; w.changed = 1; }
+               } else {
+                  if (pot > 0.0) acc = true;
+                  else if (exp(pot * p.tau) > mrg_u01(g)) acc = true;
+                  if (acc) { w.st[1] = w.it0 % P; w.st[3] = w.atom0; qw[7 + QW_RECEDE] += 1.0; w.changed = 1; }
+               }
+            }
+         }
+         __syncthreads();
+      }
+      // ---------------- swap (qworm_swap, mc_qworm.cc:424-551) ----------------
+      if (bose_worm) {
+         if (tid == 0) qw[14] += 1.0;
+         if (w.st[0]) {
+            double pnorm_old = 0.0;
+            if (tid == 0) {
+               qw[QW_SWAP] += 1.0;
+               w.go = 0;
+               const int sg = p.worm_m, it0 = w.st[1], it1 = it0 + sg, pit0 = it0, pit1 = it1 % P, atomw = w.st[3];
+               int count = worm_get_ptable(p, c, w.st, atomw, pit0, pit1, sg, it1, dr2_list, atm_list, ptable);
+               if (count > 0) {
+                  // atom2swap, mc_qworm.cc:645-667
+                  for (int ic = 1; ic <= count; ic++) pnorm_old += ptable[ic];
+                  const double prand = pnorm_old * mrg_u01(g);
+                  double sum = 0.0;
+                  int ic = 1;
+                  while ((ic <= count) && (sum < prand)) { sum += ptable[ic]; ic++; }
+                  ic--;
+                  const int atom1 = atm_list[ic];
+                  if (atom1 >= 0) {
+                     int atom0 = atom1;
+                     if (pit1 != it1) atom0 = rindex[base + atom1] - base;
+                     #pragma unroll
+                     for (int d = 0; d < 3; d++) {
+                        w.path[0 * 3 + d] = p.pos[pos_index(p, c, pit0, d, base + atomw)];
+                        w.path[sg * 3 + d] = p.pos[pos_index(p, c, pit1, d, base + atom1)];
+                     }
+                     worm_sample_middle(p, c, g, it0, it1, atom0, atom1, w.path);
+                     w.it0 = it0; w.it1 = it1; w.atom0 = atom0; w.atom1 = atom1; w.use_path = 1; w.diff = 1;
+                     w.go = 1;
+                  }
+               }
+            }
+            __syncthreads();
+            if (w.go) {
+               const double pot = worm_pot_sum<KIND>(p, t, c, w, red);
+               if (tid == 0) {
+                  const int sg = p.worm_m, it0 = w.it0, it1 = w.it1, pit0 = it0, pit1 = it1 % P;
+                  double prob = exp(-pot * p.tau);
+                  const int count = worm_get_ptable(p, c, w.st, w.atom0, pit0, pit1, sg, it1, dr2_list, atm_list, ptable);
+                  double pnorm_new = 0.0;
+                  for (int ic = 1; ic <= count; ic++) pnorm_new += ptable[ic];
+                  prob *= (pnorm_old / pnorm_new);
+                  bool acc = false;
+                  if (prob >= 1.0) acc = true;
+                  else if (prob > mrg_u01(g)) acc = true;
+                  w.go = acc ? 1 : 0;
+               }
+               __syncthreads();
+               if (w.go) {
+                  const int it0 = w.it0, it1 = w.it1, atom0 = w.atom0, atom1 = w.atom1, atomw = w.st[3];
+                  // the proposed beads replace the state's between it0 and it1 ...
+                  for (int i = tid; i < (it1 - it0 - 1) * 3; i += blockDim.x) {
+                     const int it = it0 + 1 + i / 3, d = i % 3, pit = it % P;
+                     p.pos[pos_index(p, c, pit, d, base + (pit != it ? atom1 : atom0))] = w.path[(it - it0) * 3 + d];
+                  }
+                  // ... and the world lines of atom0 and atomw trade their beads 0..it0
+                  for (int i = tid; i < (it0 + 1) * 3; i += blockDim.x) {
+                     const int it = i / 3, d = i % 3;
+                     const size_t a = pos_index(p, c, it, d, base + atom0), b = pos_index(p, c, it, d, base + atomw);
+                     const double va = p.pos[a], vb = p.pos[b];
+                     p.pos[a] = vb; p.pos[b] = va;
+                  }
+                  if (tid == 0) {
+                     qw[7 + QW_SWAP] += 1.0;
+                     const int ratomw = rindex[base + atomw] - base, ratom0 = rindex[base + atom0] - base;
+                     pindex[base + ratomw] = base + atom0; rindex[base + atom0] = base + ratomw;
+                     pindex[base + ratom0] = base + atomw; rindex[base + atomw] = base + ratom0;
+                     if (w.st[1] > w.st[2]) {
+                        if (atom0 == w.st[4]) w.st[4] = w.st[3];
+                        else if (w.st[3] == w.st[4]) w.st[4] = atom0;
+                     }
+                     w.changed = 1; w.perm_changed = 1;
+                  }
+               }
+            }
+            __syncthreads();
+         }
+      }
+   }
+   if (tid == 0) {
+      mrg_store(g, sp);
+      for (int i = 0; i < 5; i++) gst[i] = w.st[i];
+      if (w.changed) p.pos_epoch[c] += 1;                   // cached rotor potentials are stale (beads moved or masks changed)
+      if (w.perm_changed) worm_rebuild_cycles(p, c, seen);
+   }
+   __syncthreads();
+}
+
+__host__ __device__ inline size_t worm_scratch_bytes(int N)
+{
+   return ((sizeof(WormShared) + 15) & ~(size_t)15) + 2 * (size_t)(N + 2) * sizeof(double) + 2 * (size_t)(N + 2) * sizeof(int) + 16;
+}
+
+} // namespace pimc

@@ -181,6 +181,7 @@ size_t smem_bytes(const Params &p, int threads)
    size_t bytes = d * sizeof(double);
    if (p.rot_fused) bytes += (size_t)((p.Q + p.cpc - 1) / p.cpc) * sizeof(RotSlot);
    else if (p.rot_group > 1) bytes += (size_t)(threads / p.rot_group) * sizeof(RotSlot);
+   if (p.worm_on) bytes += 16 + worm_scratch_bytes(p.N);
    return bytes;
 }
 
@@ -188,6 +189,19 @@ void est_shapes(dim3 &g_rcf, dim3 &b_rcf)
 {
    b_rcf = dim3(128);
    g_rcf = dim3((G.p.Q + 127) / 128, G.p.nchains);
+}
+
+// the step kernel variant: rotor kind in bits 0-1, worm in bit 2
+const void *steps_kernel(int kind, int worm)
+{
+   switch (kind + 4 * (worm ? 1 : 0)) {
+      case 0: return (const void *)pimc_steps_kernel<0>;
+      case 1: return (const void *)pimc_steps_kernel<1>;
+      case 2: return (const void *)pimc_steps_kernel<2>;
+      case 4: return (const void *)pimc_steps_kernel<4>;
+      case 5: return (const void *)pimc_steps_kernel<5>;
+      default: return (const void *)pimc_steps_kernel<6>;
+   }
 }
 
 int launch_estimators(int with_dens, int accumulate)
@@ -284,6 +298,16 @@ int pimcgpu_init(const pimcgpu_system *sys, const pimcgpu_tables *tab)
    if ((p.refl[0] | p.refl[1] | p.refl[2]) && !(p.imtype >= 0 && p.molecule[p.imtype] == 2 && p.Q > 0))
       return fail("pimcgpu_init: REFLECTX/Y/Z need a NONLINEAR rotor with ROTATION");
    if (p.rotsym && !(p.imtype >= 0 && p.Q > 0)) return fail("pimcgpu_init: ROTSYM needs a rotor with ROTATION");
+   if (sys->worm) {
+      if (sys->worm_type < 0 || sys->worm_type >= sys->ntypes) return fail("pimcgpu_init: Can't find a particle type for the worm algorithm");
+      if (sys->worm_m < 1 || sys->worm_m >= sys->P) return fail("pimcgpu_init: Worm algorithm: m should be smaller then M");
+      if (sys->worm_m > WORM_MAXM) return fail("pimcgpu_init: Worm.m above %d is not supported on the device", WORM_MAXM);
+      p.worm_on = 1; p.worm_type = sys->worm_type; p.worm_m = sys->worm_m;
+      const double density = (double)p.N / (sys->box[0] * sys->box[1] * sys->box[2]);
+      p.worm_norm = sys->worm_c * density;                     // Worm.c * numb * NumbTimes * Worm.m after MCWormInit's rescaling
+      p.worm_twave2 = 4.0 * p.lambda[p.worm_type] * p.tau;     // twave2, mc_setup.cc:394
+      p.worm_cutoff2 = 100.0 * 100.0 * ((double)p.worm_m * p.worm_twave2);
+   }
    if (p.rotden_type == 1) {
       if (p.Q <= 0) return fail("pimcgpu_init: ROTDENSI 1 without ROTATION");
       const bool lin = p.molecule[p.imtype] == 1;
@@ -397,8 +421,14 @@ int pimcgpu_init(const pimcgpu_system *sys, const pimcgpu_tables *tab)
    if (dalloc(&p.pos, C * p.P * 3 * p.Npad) || dalloc(&p.ang, C * std::max(1, p.Q) * 3 * p.NMpad) || dalloc(&p.cosn, C * std::max(1, p.Q) * 3 * p.NMpad) ||
        dalloc(&p.pindex, C * p.N) || dalloc(&p.cyc_start, C * (p.N + 1)) || dalloc(&p.cyc_atoms, C * p.N) || dalloc(&p.ncyc, C * MAXT) ||
        dalloc(&p.vold, C * std::max(1, p.Q) * p.NMpad) || dalloc(&p.vepoch, C * std::max(1, p.Q) * p.NMpad) || dalloc(&p.pos_epoch, C) ||
+       dalloc(&p.wstate, C * 8) || dalloc(&p.rindex, C * p.N) || dalloc(&p.qwc, C * 16) ||
        dalloc(&p.rng, C * p.S * 6) || dalloc(&p.counters, C * MAXT * 3 * 2) || dalloc(&p.scratch, C * 64) || dalloc(&G.d_err, 1)) return 1;
    G.h_pindex.assign(C * p.N, 0);
+   {
+      std::vector<double> q0(C * 16, 0.0);
+      for (size_t c = 0; c < C; c++) q0[c * 16 + 14] = 1.0;      // countQW starts at 1 (ResetQWCounts, mc_qworm.cc:669-678)
+      CK(cudaMemcpy(p.qwc, q0.data(), q0.size() * sizeof(double), cudaMemcpyHostToDevice));
+   }
    G.stage_chain = (size_t)p.P * 3 * p.Npad + 2 * (size_t)std::max(1, p.Q) * 3 * p.NMpad;
    CK(cudaHostAlloc((void **)&G.stage, C * G.stage_chain * sizeof(double), cudaHostAllocDefault));
    memset(G.stage, 0, C * G.stage_chain * sizeof(double));
@@ -477,7 +507,7 @@ int pimcgpu_init(const pimcgpu_system *sys, const pimcgpu_tables *tab)
    G.smem = smem_bytes(p, threads);
    if (G.smem > 227 * 1024) return fail("pimcgpu_init: %zu bytes of shared memory per CTA exceed the 227 KB limit", G.smem);
    G.kind = p.imtype >= 0 && p.Q > 0 ? p.molecule[p.imtype] : (p.imtype >= 0 ? p.molecule[p.imtype] : 0);
-   const void *kfun = G.kind == 2 ? (const void *)pimc_steps_kernel<2> : G.kind == 1 ? (const void *)pimc_steps_kernel<1> : (const void *)pimc_steps_kernel<0>;
+   const void *kfun = steps_kernel(G.kind, p.worm_on);
    CK(cudaFuncSetAttribute(kfun, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
    if (p.swbar) {
       int per_sm = 0;
@@ -549,6 +579,8 @@ int pimcgpu_upload_state(int chain, const double *coords, const double *angles, 
          if (pindex[a] < 0 || pindex[a] >= p.numb[p.bstype]) return fail("pimcgpu_upload_state: bad permutation entry");
          gp[p.first[p.bstype] + a] = p.first[p.bstype] + pindex[a];
       }
+   std::vector<int> gr(p.N);
+   for (int a = 0; a < p.N; a++) gr[gp[a]] = a;
    std::vector<int> ncyc(MAXT, 0), seen(p.N, 0);
    for (int t = 0; t < p.ntypes; t++)
       for (int a = p.first[t]; a < p.first[t] + p.numb[t]; a++) {
@@ -566,6 +598,8 @@ int pimcgpu_upload_state(int chain, const double *coords, const double *angles, 
       CK(cudaMemcpyAsync(p.ang + (size_t)c * nang, hang, nang * sizeof(double), cudaMemcpyHostToDevice, G.stream));
       CK(cudaMemcpyAsync(p.cosn + (size_t)c * nang, hcos, nang * sizeof(double), cudaMemcpyHostToDevice, G.stream));
       CK(cudaMemcpyAsync(p.pindex + (size_t)c * p.N, gp.data(), p.N * sizeof(int), cudaMemcpyHostToDevice, G.stream));
+      CK(cudaMemcpyAsync(p.rindex + (size_t)c * p.N, gr.data(), p.N * sizeof(int), cudaMemcpyHostToDevice, G.stream));
+      CK(cudaMemsetAsync(p.wstate + (size_t)c * 8, 0, 8 * sizeof(int), G.stream));              // uploaded paths are closed (Z sector)
       CK(cudaMemcpyAsync(p.cyc_start + (size_t)c * (p.N + 1), cstart.data(), (p.N + 1) * sizeof(int), cudaMemcpyHostToDevice, G.stream));
       CK(cudaMemcpyAsync(p.cyc_atoms + (size_t)c * p.N, catoms.data(), p.N * sizeof(int), cudaMemcpyHostToDevice, G.stream));
       CK(cudaMemcpyAsync(p.ncyc + (size_t)c * MAXT, ncyc.data(), MAXT * sizeof(int), cudaMemcpyHostToDevice, G.stream));
@@ -614,8 +648,10 @@ int pimcgpu_download_state(int chain, double *coords, double *angles, double *co
                if (cosine) cosine[d * n + dst] = hcos[b + d * p.NMpad];
             }
          }
-   if (pindex && p.bstype >= 0)
+   if (pindex && p.bstype >= 0) {
+      CK(cudaMemcpy(G.h_pindex.data() + (size_t)chain * p.N, p.pindex + (size_t)chain * p.N, p.N * sizeof(int), cudaMemcpyDeviceToHost));   // the worm's swaps change it
       for (int a = 0; a < p.numb[p.bstype]; a++) pindex[a] = G.h_pindex[(size_t)chain * p.N + p.first[p.bstype] + a] - p.first[p.bstype];
+   }
    return 0;
 }
 
@@ -668,9 +704,8 @@ int pimcgpu_steps(long nsteps)
    cudaLaunchAttribute attr[1];
    launch_config(cfg, attr);
    if (G.p.cpc > 1) CK(cudaMemsetAsync(G.p.barrier, 0, (size_t)G.p.nchains * 32 * sizeof(unsigned), G.stream));
-   if (G.kind == 2) CK(cudaLaunchKernelEx(&cfg, pimc_steps_kernel<2>, G.p, G.step, nsteps, G.d_err));
-   else if (G.kind == 1) CK(cudaLaunchKernelEx(&cfg, pimc_steps_kernel<1>, G.p, G.step, nsteps, G.d_err));
-   else CK(cudaLaunchKernelEx(&cfg, pimc_steps_kernel<0>, G.p, G.step, nsteps, G.d_err));
+   void *args[4] = {(void *)&G.p, (void *)&G.step, (void *)&nsteps, (void *)&G.d_err};
+   CK(cudaLaunchKernelExC(&cfg, steps_kernel(G.kind, G.p.worm_on), args));
    G.step += nsteps;
    return 0;
 }
@@ -696,7 +731,7 @@ int pimcgpu_geometry(int *out8)
    cudaLaunchAttribute attr[1];
    launch_config(cfg, attr);
    int nclusters = -1;
-   const void *kfun = G.kind == 2 ? (const void *)pimc_steps_kernel<2> : G.kind == 1 ? (const void *)pimc_steps_kernel<1> : (const void *)pimc_steps_kernel<0>;
+   const void *kfun = steps_kernel(G.kind, G.p.worm_on);
    if (G.p.swbar) {
       int per_sm = 0, dev = 0;
       cudaDeviceProp prop;
@@ -740,6 +775,54 @@ int pimcgpu_symmetry_ops(const int *ops)
    symmetry_kernel<<<G.p.nchains, 256, 0, G.stream>>>(G.p, G.d_ops);
    CK(cudaGetLastError());
    CK(cudaStreamSynchronize(G.stream));          // `ops` is pageable host memory
+   return 0;
+}
+
+int pimcgpu_worm_moves(void)
+{
+   if (!G.live) return fail("pimcgpu_worm_moves: not initialised");
+   if (!G.p.worm_on) return fail("pimcgpu_worm_moves: the system has no WORM");
+   if (!G.seeded) return fail("pimcgpu_worm_moves: call pimcgpu_seed first");
+   const size_t smem = 64 * sizeof(double) + worm_scratch_bytes(G.p.N);
+   if (G.kind == 2) worm_move_kernel<6><<<G.p.nchains, 256, smem, G.stream>>>(G.p);
+   else if (G.kind == 1) worm_move_kernel<5><<<G.p.nchains, 256, smem, G.stream>>>(G.p);
+   else worm_move_kernel<4><<<G.p.nchains, 256, smem, G.stream>>>(G.p);
+   CK(cudaGetLastError());
+   return 0;
+}
+int pimcgpu_worm_state(int chain, int *st5)
+{
+   if (!G.live) return fail("pimcgpu_worm_state: not initialised");
+   if (chain < 0 || chain >= G.p.nchains) return fail("pimcgpu_worm_state: chain out of range");
+   CK(cudaStreamSynchronize(G.stream));
+   CK(cudaMemcpy(st5, G.p.wstate + (size_t)chain * 8, 5 * sizeof(int), cudaMemcpyDeviceToHost));
+   return 0;
+}
+int pimcgpu_worm_set(int chain, const int *st5)
+{
+   if (!G.live) return fail("pimcgpu_worm_set: not initialised");
+   if (!G.p.worm_on) return fail("pimcgpu_worm_set: the system has no WORM");
+   if (chain < 0 || chain >= G.p.nchains) return fail("pimcgpu_worm_set: chain out of range");
+   const int nb = G.p.numb[G.p.worm_type];
+   if (st5[1] < 0 || st5[1] >= G.p.P || st5[2] < 0 || st5[2] >= G.p.P || st5[3] < 0 || st5[3] >= nb || st5[4] < 0 || st5[4] >= nb)
+      return fail("pimcgpu_worm_set: worm end points out of range");
+   CK(cudaStreamSynchronize(G.stream));
+   CK(cudaMemcpy(G.p.wstate + (size_t)chain * 8, st5, 5 * sizeof(int), cudaMemcpyHostToDevice));
+   CK(cudaMemset(G.p.vepoch + (size_t)chain * std::max(1, G.p.Q) * G.p.NMpad, 0xff, (size_t)std::max(1, G.p.Q) * G.p.NMpad * sizeof(int)));
+   return 0;
+}
+int pimcgpu_worm_counters(double *total7, double *accep7, double *countqw)
+{
+   if (!G.live) return fail("pimcgpu_worm_counters: not initialised");
+   std::vector<double> h((size_t)G.p.nchains * 16);
+   CK(cudaStreamSynchronize(G.stream));
+   CK(cudaMemcpy(h.data(), G.p.qwc, h.size() * sizeof(double), cudaMemcpyDeviceToHost));
+   for (int i = 0; i < 7; i++) { total7[i] = 0.0; accep7[i] = 0.0; }
+   *countqw = 0.0;
+   for (int c = 0; c < G.p.nchains; c++) {
+      for (int i = 0; i < 7; i++) { total7[i] += h[(size_t)c * 16 + i]; accep7[i] += h[(size_t)c * 16 + 7 + i]; }
+      *countqw += h[(size_t)c * 16 + 14];
+   }
    return 0;
 }
 
@@ -821,6 +904,12 @@ int pimcgpu_accum_reset(void)
    if (!G.live) return fail("pimcgpu_accum_reset: not initialised");
    CK(cudaMemsetAsync(G.e.acc, 0, G.nacc * sizeof(double), G.stream));
    CK(cudaMemsetAsync(G.p.counters, 0, (size_t)G.p.nchains * MAXT * 3 * 2 * sizeof(double), G.stream));
+   if (G.p.worm_on) {                     // ResetQWCounts, mc_main.cc:531
+      std::vector<double> q0((size_t)G.p.nchains * 16, 0.0);
+      for (int c = 0; c < G.p.nchains; c++) q0[(size_t)c * 16 + 14] = 1.0;
+      CK(cudaStreamSynchronize(G.stream));
+      CK(cudaMemcpy(G.p.qwc, q0.data(), q0.size() * sizeof(double), cudaMemcpyHostToDevice));
+   }
    return 0;
 }
 int pimcgpu_block_scalars(pimcgpu_scalars *out)

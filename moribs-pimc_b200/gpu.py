@@ -26,7 +26,7 @@ EXPORTS = [
     "pimcgpu_eval_lpot2d", "pimcgpu_eval_srotdens", "pimcgpu_eval_rotden", "pimcgpu_eval_vcord", "pimcgpu_eval_caleng",
     "pimcgpu_pot_energy_slice", "pimcgpu_rng_draws", "pimcgpu_fp64_peak", "pimcgpu_host_spline",
     "pimcgpu_host_stream_state", "pimcgpu_host_lut", "pimcgpu_accum_offset", "pimcgpu_symmetry_moves", "pimcgpu_symmetry_ops",
-    "pimcgpu_chain_areas",
+    "pimcgpu_chain_areas", "pimcgpu_worm_moves", "pimcgpu_worm_state", "pimcgpu_worm_set", "pimcgpu_worm_counters",
 ]
 
 
@@ -41,7 +41,8 @@ class GpuSystem(C.Structure):
                 ("nchains", C.c_int), ("chain_offset", C.c_long), ("device", C.c_int), ("ctas_per_chain", C.c_int),
                 ("threads_per_cta", C.c_int), ("team", C.c_int),
                 ("rot_odevn", C.c_int), ("rot_eoff", C.c_double), ("x_rot", C.c_double), ("y_rot", C.c_double), ("z_rot", C.c_double),
-                ("rnratio", C.c_int), ("reflect", C.c_int * 3), ("rotsym", C.c_int), ("nfold_rot", C.c_int)]
+                ("rnratio", C.c_int), ("reflect", C.c_int * 3), ("rotsym", C.c_int), ("nfold_rot", C.c_int),
+                ("worm", C.c_int), ("worm_type", C.c_int), ("worm_c", C.c_double), ("worm_m", C.c_int)]
 
 
 class GpuTables(C.Structure):
@@ -142,6 +143,9 @@ class PimcGpu:
         for d in range(3):
             sy.reflect[d] = s.reflect[d]
         sy.rotsym, sy.nfold_rot = (1 if s.rotsym else 0), max(1, s.rotsym)      # ROTSYM n: IROTSYM = 1, NFOLD_ROT = n
+        if s.worm:
+            names = [t.name for t in s.types]
+            sy.worm, sy.worm_type, sy.worm_c, sy.worm_m = 1, names.index(s.worm[0]), float(s.worm[1]), int(s.worm[2])
         tb = GpuTables()
         self._keep = []
         t = cfg.tables
@@ -236,6 +240,33 @@ class PimcGpu:
         out = np.zeros(28)
         _ck(self.L.pimcgpu_chain_areas(C.c_int(chain), _dp(out)))
         return dict(lin=out[0:4], sff_area=out[4:7], sff_inert=out[7:16], mff_area=out[16:19], mff_inert=out[19:28])
+
+    # worm --------------------------------------------------------------------------------------
+    def worm_moves(self, sync=True):
+        _ck(self.L.pimcgpu_worm_moves())
+        if sync:
+            _ck(self.L.pimcgpu_sync())
+
+    def worm_state(self, chain=0):
+        st = (C.c_int * 5)()
+        _ck(self.L.pimcgpu_worm_state(C.c_int(chain), st))
+        return list(st)
+
+    def worm_set(self, chain, st5):
+        _ck(self.L.pimcgpu_worm_set(C.c_int(chain), (C.c_int * 5)(*[int(v) for v in st5])))
+
+    def worm_counters(self):
+        t, a, cq = np.zeros(7), np.zeros(7), C.c_double()
+        _ck(self.L.pimcgpu_worm_counters(_dp(t), _dp(a), C.byref(cq)))
+        return t, a, cq.value
+
+    def download_perm(self, chain=0):
+        nb = max((t.numb for t in self.s.types if t.stat == 1), default=0)
+        p = np.zeros(max(1, nb), dtype=np.int32)
+        n = self.N * self.P
+        c = np.zeros((3, n))
+        _ck(self.L.pimcgpu_download_state(C.c_int(chain), _dp(c), None, None, _ip(p)))
+        return p[:nb]
 
     def symmetry_moves(self):
         _ck(self.L.pimcgpu_symmetry_moves())

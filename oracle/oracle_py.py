@@ -102,6 +102,8 @@ class Oracle:
             L.orc_set_rot3d(self.h, *[_dp(x) for x in t["rot3d"]])
         self.N, self.P, self.Q = s.N, s.P, s.Q
         self.set_state(cfg.coords, cfg.angles, cfg.perm)
+        if getattr(s, "worm", None):
+            self.worm_init([t.name for t in s.types].index(s.worm[0]), s.worm[1], s.worm[2])
 
     def __del__(self):
         try:

@@ -1376,6 +1376,7 @@ void sched_molecular(orc_t *o, int type)
             for (int a1 : cyc) if (base + a1 == atom1) member = true;
             if (member) continue;
             for (int it = 0; it < P; it++) {
+               if (!partner_on_line(o, atom1, it)) continue;         // world-line mask of PotEnergy(atom,pos), mc_piqmc.cc:1226-1227
                double pn[3], po[3];
                for (int id = 0; id < 3; id++) { po[id] = o->coords[id][P * g0 + it]; pn[id] = po[id] + disp[id]; }
                deltav += pair_energy(o, g0, pn, atom1, it, nullptr, nullptr, 0, nullptr) -
