@@ -12,8 +12,8 @@
 // RANK/WORLD_SIZE environment of a launcher) every rank drives one GPU, the block accumulators are all-reduced
 // with NCCL over NVLink before rank 0 writes the block files.
 //
-// ROTDENSI 1 (rattle-and-shake propagator), REFLECTX/Y/Z and ROTSYM are honoured on the device.
-// Not done on the device (and rejected loudly): WORM moves.  yw001.rand (SPRNG state) has no
+// ROTDENSI 1 (rattle-and-shake propagator), REFLECTX/Y/Z, ROTSYM and WORM (exchange sampling with the worm algorithm,
+// mc_qworm.cc) are honoured on the device; yw001.worm is written in the reference's layout for chain 0.  yw001.rand (SPRNG state) has no
 // counterpart: the MRG32k3a package seed and step counter are written to yw001.mrg instead.
 #include "../../include/pimcgpu.h"
 
@@ -60,7 +60,9 @@ struct Deck {
    vector<Species> types;
    string outdir = "./", prefix = "pimc";
    int P = 0, Q = 0, ispher = 0, minimage = 0, rotden_type = 0, read_coords = 0, worm = 0;
-   int rot_odevn = 0, rnratio = 1, refl[3] = {0, 0, 0}, rotsym = 0, nfold = 1;
+   int rot_odevn = 0, rnratio = 1, refl[3] = {0, 0, 0}, rotsym = 0, nfold = 1, worm_m = 0;
+   string worm_type;
+   double worm_c = 0;
    double rot_eoff = 0, xrot = 0, yrot = 0, zrot = 0;
    double temperature = 0, density = 0.02;
    long passes = 1, blocks = 1, eq_blocks = 0;
@@ -122,7 +124,7 @@ static Deck read_deck(const char *path)
       else if (key == "REFLECTY") inf >> d.refl[1];
       else if (key == "REFLECTZ") inf >> d.refl[2];
       else if (key == "ROTSYM") { d.rotsym = 1; inf >> d.nfold; }
-      else if (key == "WORM") d.worm = 1;
+      else if (key == "WORM") { d.worm = 1; inf >> d.worm_type >> d.worm_c >> d.worm_m; }       // mc_input.cc:286-293
       else if (key == "MINIMAGE") d.minimage = 1;
       else if (key == "READMCCOORDS") d.read_coords = 1;
       else if (key == "MCSKIP_RATIO") inf >> d.skip_ratio;
@@ -202,7 +204,6 @@ int main(int argc, char **argv)
       else die("main", "usage: pimc_b200 [--chains C] [--ranks N --rank r] [--seed s]   (reads ./qmc.input)");
    }
    Deck d = read_deck("qmc.input");
-   if (d.worm) die("main", "WORM moves are not available on the device path yet (remove the WORM line to sample a fixed permutation)");
    const int N = d.N(), P = d.P, Q = d.Q;
    const size_t n = (size_t)N * P;
 
@@ -224,6 +225,12 @@ int main(int argc, char **argv)
    sys.x_rot = d.xrot; sys.y_rot = d.yrot; sys.z_rot = d.zrot; sys.rnratio = d.rnratio;
    for (int k = 0; k < 3; k++) sys.reflect[k] = d.refl[k];
    sys.rotsym = d.rotsym; sys.nfold_rot = d.nfold;
+   if (d.worm) {
+      sys.worm = 1; sys.worm_type = -1; sys.worm_c = d.worm_c; sys.worm_m = d.worm_m;
+      for (int t = 0; t < sys.ntypes; t++) if (d.types[t].name == d.worm_type) sys.worm_type = t;
+      if (sys.worm_type < 0) die("MCWormInit", "Can't find a particle type for the worm algorithm");
+      if (d.worm_m >= P) die("IOReadParams", "Worm algorithm: m should be smaller then M");
+   }
    sys.nchains = chains; sys.chain_offset = (long)rank * chains; sys.device = rank;
 #ifdef PIMC_WITH_NCCL
    { int nd = 1; cudaGetDeviceCount(&nd); sys.device = rank % std::max(1, nd); }
@@ -376,6 +383,14 @@ int main(int argc, char **argv)
          cout << setw(8) << d.types[t].name << BLANK << setw(8) << sc.mcaccep[t][0] / sc.mctotal[t][0] << BLANK << setw(8) << sc.mcaccep[t][1] / sc.mctotal[t][1] << BLANK;
       if (Q) cout << BLANK << "Rot: " << setw(8) << sc.mcaccep[imtype][2] / sc.mctotal[imtype][2] << BLANK;
       cout << endl;
+      if (d.worm) {
+         // worm part of MCSaveAcceptRatio, mc_main.cc:886-921 (this rank's chains)
+         double qt[7], qa[7], cq = 0;
+         ck(pimcgpu_worm_counters(qt, qa, &cq), "pimcgpu_worm_counters");
+         cout << "WORM: open/close " << qa[0] / qt[0] << BLANK << qa[1] / qt[1] << BLANK << qt[0] / cq << "-" << qt[1] / cq << BLANK
+              << "advance/recede " << qa[4] / qt[4] << BLANK << qa[5] / qt[5] << BLANK << qt[4] / cq << "-" << qt[5] / cq << BLANK
+              << "swap " << qa[6] / qt[6] << BLANK << qt[6] / cq << endl;
+      }
       if (block > d.eq_blocks && sc.count > 0) {
          const double ac = sc.count;
          // SaveEnergy, mc_main.cc:764-795
@@ -484,6 +499,18 @@ int main(int argc, char **argv)
          f.write((char *)&size, sizeof(streamsize));
          f.write((char *)pindex.data(), size);
          f.write((char *)rindex.data(), size);
+      }
+      if (d.worm) {
+         // QWormsIO, mc_input.cc:653-688: the TPathWorm record of mc_qworm.h:32-47 (chain 0)
+         struct { char stype[80]; int type, exists, ira, masha, atom_i, atom_m; double c; int m; } rec;
+         memset(&rec, 0, sizeof rec);
+         int st[5];
+         ck(pimcgpu_worm_state(0, st), "pimcgpu_worm_state");
+         strncpy(rec.stype, d.worm_type.c_str(), sizeof rec.stype - 1);
+         rec.type = sys.worm_type; rec.exists = st[0]; rec.ira = st[1]; rec.masha = st[2]; rec.atom_i = st[3]; rec.atom_m = st[4];
+         rec.c = d.worm_c * d.density / ((double)d.types[sys.worm_type].numb * P * d.worm_m); rec.m = d.worm_m;
+         ofstream f("yw001.worm", ios::binary);
+         f.write((char *)&rec, sizeof rec);
       }
       { ofstream f("yw001.mrg"); f << "SEED"; for (int k = 0; k < 6; k++) f << " " << seed[k]; f << "\nSTEP " << pimcgpu_step_counter() << "\nCHAINS " << chains << " RANKS " << ranks << endl; }
       {

@@ -354,4 +354,42 @@ double ref_run_steps(int time0, int nsteps)
    return omp_get_wtime() - t0;
 }
 
+// The hot loop of mc_main.cc:348-381 including the worm branch (:355-379): MCWormMove, then -- in the Z sector only --
+// one bisection move at a random slice and the whole-path move at time 0.
+double ref_run_steps_worm(int time0, int nsteps)
+{
+   double t0 = omp_get_wtime();
+   for (int s = 0; s < nsteps; s++) {
+      int time = (time0 + s) % NumbTimes;
+      for (int type = 0; type < NumbTypes; type++)
+         if (WORM && (type == Worm.type)) {
+            MCWormMove();
+            if (!Worm.exists) {
+               int rt = nrnd2(NumbTimes);
+               if ((type == BSTYPE) || (type == FERMTYPE)) MCBisectionMoveExchange(type, rt);
+               else MCBisectionMove(type, rt);
+               if (time == 0) {
+                  if ((type == BSTYPE) || (type == FERMTYPE)) MCMolecularMoveExchange(type);
+                  else MCMolecularMove(type);
+               }
+            }
+         } else PIMCPass(type, time);
+   }
+   return omp_get_wtime() - t0;
+}
+int ref_worm_exists(void) { return Worm.exists; }
+// block accumulators of the exchange / area estimators as MCGetAverage left them
+void ref_get_exchange_acc(double *ploops, double *sff_area6, double *sff_inert9)
+{
+   for (int i = 0; i < MCAtom[BSTYPE].numb; i++) ploops[i] = _ploops[i];
+   for (int i = 0; i < 6; i++) sff_area6[i] = _areas3DSFF[i];
+   for (int i = 0; i < 9; i++) sff_inert9[i] = _inert3DSFF[i];
+}
+void ref_reset_exchange_acc(void)
+{
+   for (int i = 0; i < MCAtom[BSTYPE].numb; i++) _ploops[i] = 0.0;
+   for (int i = 0; i < 6; i++) { _areas3DSFF[i] = 0.0; _areas3DMFF[i] = 0.0; }
+   for (int i = 0; i < 9; i++) { _inert3DSFF[i] = 0.0; _inert3DMFF[i] = 0.0; }
+}
+
 } // extern "C"

@@ -92,6 +92,84 @@ def test_rotor_in_solvent_cluster_matches_reference(pkg):
     compare(g, r, [(0, "K"), (1, "V"), (2, "E_rot")])
 
 
+WORM_REF_SCRIPT = r'''
+import sys, json, numpy as np
+sys.path.insert(0, %(root)r)
+from oracle import oracle_py as op
+cfgs = op._configs()
+cfg = cfgs.make_config(%(name)r, **%(kw)r)
+cfg.system.worm = %(worm)r
+R = op.Ref(cfg)
+s = cfg.system
+nb = s.types[0].numb
+nblocks, per_block, skip = %(nblocks)d, %(per_block)d, %(skip)d
+R.lib.ref_run_steps_worm(0, 200 * s.P)                # equilibrate
+out7 = np.zeros(7); pl = np.zeros(nb); a6 = np.zeros(6); i9 = np.zeros(9)
+rows = []
+t = 200 * s.P
+for b in range(nblocks):
+    R.lib.ref_reset_block(); R.lib.ref_reset_exchange_acc()
+    n = 0
+    for k in range(per_block // skip):
+        R.lib.ref_run_steps_worm(t, skip); t += skip
+        if not R.lib.ref_worm_exists():
+            R.lib.ref_MCGetAverage(op._dp(out7)); n += 1
+    R.lib.ref_get_exchange_acc(op._dp(pl), op._dp(a6), op._dp(i9))
+    exch = float(sum((l + 1) * pl[l] for l in range(1, nb)) / (n * nb))
+    rows.append([out7[0] / n, out7[1] / n, exch, (a6[0] + a6[2] + a6[5]) / n, n])
+print("ROWS " + json.dumps(rows))
+'''
+
+
+def test_exchange_sampling_matches_reference(pkg):
+    """Worm algorithm (N1): a cold He4 cluster around the top (5 He, P=64, 1 K) where permutations are frequent.  <K>, <V>,
+    the fraction of atoms on exchange cycles (GetExchangeLength) and the space-fixed area estimator <A.A> (GetAreaEstim3D,
+    the superfluid-response numerator) sampled on the GPU agree with the reference's own worm sampling within 2 sigma."""
+    import json
+    kw = dict(P=64, Q=16, nsolv=5, temperature=1.0)
+    worm = ("He4", 0.13, 8)
+    nblocks, per_block, skip = 24, 12800, 16
+    # 64 blocks of the reference's own worm sampling (its unmodified objects, run in the build container by
+    # profiles/worm_stats_ref.py = WORM_REF_SCRIPT above, about 6 minutes of CPU) are committed as a fixture
+    fixture = os.path.join(ROOT, "tests", "golden", "stats", "worm_C2_P64_Q16_5He_1K_ref.json")
+    if os.path.exists(fixture):
+        r = np.array(json.load(open(fixture)))
+    else:
+        if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libpimcref.so")):
+            pytest.skip("neither the fixture nor oracle/_ref is available")
+        code = WORM_REF_SCRIPT % dict(root=ROOT, name="C2", kw=kw, worm=worm, nblocks=nblocks, per_block=per_block, skip=skip)
+        out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=1500)
+        line = [l for l in out.stdout.splitlines() if l.startswith("ROWS ")]
+        assert line, out.stdout[-1500:] + out.stderr[-1500:]
+        r = np.array(json.loads(line[-1][5:]))
+    cfg = pkg.configs.make_config("C2", **kw)
+    cfg.system.worm = worm
+    cfg.system.reflect, cfg.system.rotsym = (0, 0, 0), 0
+    nb = cfg.system.types[0].numb
+    G = pkg.gpu.PimcGpu(cfg, nchains=32)
+    G.seed((12345,) * 6)
+    G.steps(200 * cfg.system.P)
+    rows = []
+    for b in range(nblocks):
+        G.accum_reset()
+        for k in range(3200 // skip):
+            G.steps(skip, sync=False)
+            G.measure()
+        G.sync()
+        acc, lay = G.accum_download()
+        n = acc[0]
+        pl = acc[lay["ploops"]:lay["ploops"] + nb]
+        a6 = acc[lay["area"] + 6:lay["area"] + 12]
+        rows.append([acc[1] / n, acc[2] / n, float(sum((l + 1) * pl[l] for l in range(1, nb)) / (n * nb)), (a6[0] + a6[2] + a6[5]) / n, n])
+    g = np.array(rows)
+    wt, wa, _ = G.worm_counters()
+    G.close()
+    print("closed-sector fraction: gpu", g[:, 4].mean() / (32 * 3200 / skip), "reference", r[:, 4].mean() / (per_block / skip), "swap acceptance (gpu)", wa[6] / max(wt[6], 1))
+    assert abs(g[:, 4].mean() / (32 * 3200 / skip) - r[:, 4].mean() / (per_block / skip)) < 0.03
+    assert g[:, 2].mean() > 0.01 and r[:, 2].mean() > 0.01, "no exchange sampled"
+    compare(g, r, [(0, "K"), (1, "V"), (2, "exchange fraction"), (3, "<A.A> space-fixed")])
+
+
 def test_cxx_driver_writes_reference_formats(pkg, tmp_path):
     """pimc_b200 on the reference's CO2 deck: .eng rows in the reference's column layout (mc_main.cc:780-792)."""
     drv = os.path.join(ROOT, "moribs-pimc_b200", "driver", "pimc_b200")
