@@ -171,8 +171,9 @@ def reference_arm(args):
 
 
 def workload_name(w, s, chains):
-    names = {"C1": "examples/MF_1He_0.37K_512_128", "C2": "examples/MF_8He_0.37K_512_128 (worm off)",
-             "C3": "examples/SO2_4pH2_0.37K_1024_256 (worm off)", "C4": "examples/H2Odimer_0.74K_4096_2048",
+    wm = f" (WORM {s.worm[0]} {s.worm[1]} {s.worm[2]})" if getattr(s, "worm", None) else " (worm off)"
+    names = {"C1": "examples/MF_1He_0.37K_512_128", "C2": "examples/MF_8He_0.37K_512_128" + wm,
+             "C3": "examples/SO2_4pH2_0.37K_1024_256" + wm, "C4": "examples/H2Odimer_0.74K_4096_2048",
              "C5": "synthetic N2O in (pH2)_100 at 0.5 K"}
     return f"{w}: {names[w]}, N={s.N}, P={s.P}, Q={s.Q}, {chains} chains/GPU"
 
@@ -204,6 +205,7 @@ def main():
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--team", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--worm", action="store_true", help="keep the deck's WORM line (C2, C3): exchange sampled with the worm algorithm")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
@@ -220,7 +222,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pkg = ge.load_package()
-    cfg = pkg.configs.make_config(args.workload)
+    cfg = pkg.configs.make_config(args.workload, worm=args.worm)
     s = cfg.system
     chains = args.chains or (8 if args.workload == "C5" else 148)
     G = pkg.gpu.PimcGpu(cfg, nchains=chains, chain_offset=rank * chains, device=local, ctas_per_chain=args.cpc,

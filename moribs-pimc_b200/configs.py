@@ -295,6 +295,9 @@ ROT_CONSTANTS = {            # A, B, C in cm^-1 used for the synthetic density-m
 }
 
 
+_deck_worm = {"C2": ("He4", 0.13, 16), "C3": ("H2", 0.35, 16)}      # WORM lines of the example decks
+
+
 @dataclasses.dataclass
 class Config:
     name: str
@@ -311,10 +314,12 @@ def _deck(name: str) -> str:
 
 
 def make_config(name: str, P: Optional[int] = None, Q: Optional[int] = None, nsolv: Optional[int] = None,
-                seed: int = 1, big_tables: bool = True, temperature: Optional[float] = None) -> Config:
-    """Build C1..C5.  P/Q/nsolv override the deck for reduced-size parity cases."""
+                seed: int = 1, big_tables: bool = True, temperature: Optional[float] = None, worm: bool = False) -> Config:
+    """Build C1..C5.  P/Q/nsolv override the deck for reduced-size parity cases; worm=True keeps
+    the deck's WORM line (C2: He4 0.13 16, C3: H2 0.35 16) so exchange is sampled with the worm algorithm."""
     tables: Dict[str, object] = {}
     perm = None
+    keep_worm = worm
     if name == "C5":
         d = _deck("N2O_5pH2_0.5K_512_128")
         s = parse_qmc_input(os.path.join(d, "qmc.input"))
@@ -388,4 +393,6 @@ def make_config(name: str, P: Optional[int] = None, Q: Optional[int] = None, nso
         raise ValueError(name)
     if temperature is not None:
         s.temperature = temperature
+    if keep_worm and _deck_worm.get(name):
+        s.worm = _deck_worm[name]
     return Config(name, s, tables, coords, angles, perm, d)
