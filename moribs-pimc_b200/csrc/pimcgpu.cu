@@ -551,7 +551,8 @@ int pimcgpu_upload_state(int chain, const double *coords, const double *angles, 
    const int cfirst = chain < 0 ? 0 : chain;
    double *hpos = G.stage + (size_t)cfirst * G.stage_chain, *hang = hpos + npos, *hcos = hang + nang;
    CK(cudaStreamSynchronize(G.stream));          // the staging area may still be in flight
-   // [dim][atom][it] -> [it][dim][atom], tiled so both sides stay within a few cache lines
+   // [dim][atom][it] -> [it][dim][atom], tiled so both sides stay within a few cache lines; host threads over the tiles
+   #pragma omp parallel for collapse(2) schedule(static)
    for (int d = 0; d < 3; d++)
       for (int a0 = 0; a0 < p.N; a0 += 8)
          for (int it0 = 0; it0 < p.P; it0 += 64) {
@@ -622,7 +623,8 @@ int pimcgpu_download_state(int chain, double *coords, double *angles, double *co
    CK(cudaMemcpyAsync(hang, p.ang + (size_t)chain * nang, nang * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
    CK(cudaMemcpyAsync(hcos, p.cosn + (size_t)chain * nang, nang * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
    CK(cudaStreamSynchronize(G.stream));
-   if (coords)
+   if (coords) {
+      #pragma omp parallel for collapse(2) schedule(static)
       for (int d = 0; d < 3; d++)
          for (int a0 = 0; a0 < p.N; a0 += 8)
             for (int it0 = 0; it0 < p.P; it0 += 64) {
@@ -632,8 +634,10 @@ int pimcgpu_download_state(int chain, double *coords, double *angles, double *co
                   for (int it = it0; it < it1; it++) dst[it] = hpos[((size_t)it * 3 + d) * p.Npad + a];
                }
             }
+   }
    // rotor rows: only the first Q entries of a molecule's row carry angles (README.md:228); the rest keep
    // the reference's initial values phi=0, cos(theta)=1, chi=0 (MCConfigInit, mc_setup.cc:471-487)
+   #pragma omp parallel for schedule(static)
    for (int d = 0; d < 3; d++)
       for (size_t i = 0; i < n; i++) {
          if (angles) angles[d * n + i] = (d == 1) ? 1.0 : 0.0;
