@@ -162,6 +162,15 @@ int pimcgpu_worm_state(int chain, int *st5);                /* Worm.exists, ira,
 int pimcgpu_worm_set(int chain, const int *st5);
 int pimcgpu_worm_counters(double *total7, double *accep7, double *countqw);   /* QWTotal, QWAccep, countQW over all chains */
 
+/* ---- checkpoint for an EXACT restart.  The reference's yw001.conf holds only the x row of MCCoords and
+ *      MCCosine (mc_input.cc:560-609), so its restart is lossy; this blob holds every chain's beads, angles, permutation
+ *      tables, worm, MRG32k3a streams, rotor-potential cache and the step counter.  A context initialised with the same
+ *      system and tables that loads it continues bit-identically.  The driver writes it to the side file yw001.b200 and
+ *      leaves yw001.stat/.conf/.tabl/.worm byte-compatible.                                                        ---- */
+long pimcgpu_checkpoint_bytes(void);
+int  pimcgpu_checkpoint_save(void *buf, long nbytes);
+int  pimcgpu_checkpoint_load(const void *buf, long nbytes);
+
 /* instantaneous area estimators of one chain, out[28]: area_perp, area_parl, inert_perp, inert_parl of
  * GetAreaEstimators (linear dopant; inertia sums before the division by NumbTimes), then area_proj[3] and
  * inert3D[9] of GetAreaEstim3D in the space-fixed frame, then the same in the dopant-fixed frame             */

@@ -830,6 +830,64 @@ int pimcgpu_worm_counters(double *total7, double *accep7, double *countqw)
    return 0;
 }
 
+// ---- checkpoint (N4) ----
+namespace {
+struct CkHeader { char magic[8]; int version, N, P, Q, nchains, S, Npad, NMpad, ntypes, worm_on; long step; long chain_offset; };
+struct CkItem { void *dev; size_t bytes; };
+std::vector<CkItem> checkpoint_items()
+{
+   const Params &p = G.p;
+   const size_t C = p.nchains, Qx = std::max(1, p.Q);
+   return {
+      {p.pos, C * p.P * 3 * p.Npad * sizeof(double)}, {p.ang, C * Qx * 3 * p.NMpad * sizeof(double)}, {p.cosn, C * Qx * 3 * p.NMpad * sizeof(double)},
+      {p.pindex, C * p.N * sizeof(int)}, {p.rindex, C * p.N * sizeof(int)}, {p.cyc_start, C * (p.N + 1) * sizeof(int)}, {p.cyc_atoms, C * p.N * sizeof(int)},
+      {p.ncyc, C * MAXT * sizeof(int)}, {p.wstate, C * 8 * sizeof(int)}, {p.rng, C * p.S * 6 * sizeof(uint32_t)},
+      {p.vold, C * Qx * p.NMpad * sizeof(double)}, {p.vepoch, C * Qx * p.NMpad * sizeof(int)}, {p.pos_epoch, C * sizeof(int)},
+   };
+}
+}
+long pimcgpu_checkpoint_bytes(void)
+{
+   if (!G.live) return -1;
+   size_t n = sizeof(CkHeader);
+   for (const CkItem &it : checkpoint_items()) n += it.bytes;
+   return (long)n;
+}
+int pimcgpu_checkpoint_save(void *buf, long nbytes)
+{
+   if (!G.live) return fail("pimcgpu_checkpoint_save: not initialised");
+   if (!buf || nbytes < pimcgpu_checkpoint_bytes()) return fail("pimcgpu_checkpoint_save: buffer too small");
+   CK(cudaStreamSynchronize(G.stream));
+   CkHeader h;
+   memset(&h, 0, sizeof h);
+   memcpy(h.magic, "PIMCB200", 8);
+   h.version = 1; h.N = G.p.N; h.P = G.p.P; h.Q = G.p.Q; h.nchains = G.p.nchains; h.S = G.p.S; h.Npad = G.p.Npad; h.NMpad = G.p.NMpad;
+   h.ntypes = G.p.ntypes; h.worm_on = G.p.worm_on; h.step = G.step; h.chain_offset = G.sys.chain_offset;
+   char *q = (char *)buf;
+   memcpy(q, &h, sizeof h); q += sizeof h;
+   for (const CkItem &it : checkpoint_items()) { CK(cudaMemcpy(q, it.dev, it.bytes, cudaMemcpyDeviceToHost)); q += it.bytes; }
+   return 0;
+}
+int pimcgpu_checkpoint_load(const void *buf, long nbytes)
+{
+   if (!G.live) return fail("pimcgpu_checkpoint_load: not initialised");
+   if (!buf || nbytes < (long)sizeof(CkHeader)) return fail("pimcgpu_checkpoint_load: truncated checkpoint");
+   CkHeader h;
+   memcpy(&h, buf, sizeof h);
+   if (memcmp(h.magic, "PIMCB200", 8) || h.version != 1) return fail("pimcgpu_checkpoint_load: not a pimcgpu checkpoint (version 1)");
+   if (h.N != G.p.N || h.P != G.p.P || h.Q != G.p.Q || h.nchains != G.p.nchains || h.S != G.p.S || h.Npad != G.p.Npad || h.NMpad != G.p.NMpad ||
+       h.ntypes != G.p.ntypes || h.worm_on != G.p.worm_on || h.chain_offset != G.sys.chain_offset)
+      return fail("pimcgpu_checkpoint_load: the checkpoint belongs to a different system (N %d P %d Q %d chains %d offset %ld)", h.N, h.P, h.Q, h.nchains, h.chain_offset);
+   if (nbytes < pimcgpu_checkpoint_bytes()) return fail("pimcgpu_checkpoint_load: truncated checkpoint");
+   CK(cudaStreamSynchronize(G.stream));
+   const char *q = (const char *)buf + sizeof h;
+   for (const CkItem &it : checkpoint_items()) { CK(cudaMemcpy(it.dev, q, it.bytes, cudaMemcpyHostToDevice)); q += it.bytes; }
+   CK(cudaMemcpy(G.h_pindex.data(), G.p.pindex, (size_t)G.p.nchains * G.p.N * sizeof(int), cudaMemcpyDeviceToHost));
+   G.step = h.step;
+   G.seeded = true;
+   return 0;
+}
+
 int pimcgpu_chain_areas(int chain, double *out28)
 {
    if (!G.live) return fail("pimcgpu_chain_areas: not initialised");

@@ -31,6 +31,7 @@
 #include <thread>
 #include <algorithm>
 #include <array>
+#include <iterator>
 #include <sys/stat.h>
 
 #ifdef PIMC_WITH_NCCL
@@ -60,7 +61,7 @@ struct Deck {
    vector<Species> types;
    string outdir = "./", prefix = "pimc";
    int P = 0, Q = 0, ispher = 0, minimage = 0, rotden_type = 0, read_coords = 0, worm = 0;
-   int rot_odevn = 0, rnratio = 1, refl[3] = {0, 0, 0}, rotsym = 0, nfold = 1, worm_m = 0;
+   int rot_odevn = 0, rnratio = 1, refl[3] = {0, 0, 0}, rotsym = 0, nfold = 1, worm_m = 0, restart = 0;
    string worm_type;
    double worm_c = 0;
    double rot_eoff = 0, xrot = 0, yrot = 0, zrot = 0;
@@ -126,6 +127,7 @@ static Deck read_deck(const char *path)
       else if (key == "ROTSYM") { d.rotsym = 1; inf >> d.nfold; }
       else if (key == "WORM") { d.worm = 1; inf >> d.worm_type >> d.worm_c >> d.worm_m; }       // mc_input.cc:286-293
       else if (key == "MINIMAGE") d.minimage = 1;
+      else if (key == "RESTART") d.restart = 1;                                               // mc_input.cc:117-120
       else if (key == "READMCCOORDS") d.read_coords = 1;
       else if (key == "MCSKIP_RATIO") inf >> d.skip_ratio;
       else if (key == "MCSKIP_TOTAL") inf >> d.skip_total;
@@ -324,6 +326,21 @@ int main(int argc, char **argv)
    }
    ck(pimcgpu_upload_state(-1, coords.data(), angles.data(), bstype >= 0 ? pindex.data() : nullptr), "pimcgpu_upload_state");
    ck(pimcgpu_seed(seed), "pimcgpu_seed");
+   // RESTART (mc_main.cc:223-231): block counter from yw001.stat; the full sampler state -- every chain's beads, angles,
+   // permutation tables, worm, MRG32k3a streams -- from this rank's side file yw001.b200[.rank] (row N4)
+   long start_block = 0;
+   const string ckname = ranks > 1 ? "yw001.b200." + to_string(rank) : string("yw001.b200");
+   if (d.restart) {
+      ifstream fs("yw001.stat");
+      string key2;
+      if (!fs.good()) die("StatusIO", "Can't open input file  [yw001.stat]");
+      while (fs >> key2) { if (key2 == "STARTBLOCK") fs >> start_block; string rest; getline(fs, rest); }
+      ifstream fc(ckname, ios::binary);
+      if (!fc.good()) die("ConfigIO", "Can't open input file  [" + ckname + "]");
+      vector<char> blob((istreambuf_iterator<char>(fc)), istreambuf_iterator<char>());
+      ck(pimcgpu_checkpoint_load(blob.data(), (long)blob.size()), "pimcgpu_checkpoint_load");
+      if (rank == 0) cout << "RESTART at block " << start_block << ", step " << pimcgpu_step_counter() << endl;
+   }
 
 #ifdef PIMC_WITH_NCCL
    ncclComm_t comm = nullptr;
@@ -349,7 +366,7 @@ int main(int argc, char **argv)
    auto t_start = chrono::steady_clock::now();
    double bead_updates = 0;
 
-   for (long block = 1; block <= d.blocks; block++) {
+   for (long block = start_block + 1; block <= start_block + d.blocks; block++) {
       ck(pimcgpu_accum_reset(), "pimcgpu_accum_reset");
       const long steps_block = d.passes * P;
       long done = 0;
@@ -376,6 +393,14 @@ int main(int argc, char **argv)
       ck(pimcgpu_block_scalars(&sc), "pimcgpu_block_scalars");
       for (int t = 0; t < sys.ntypes; t++)
          bead_updates += sc.mctotal[t][0] * P + sc.mctotal[t][1] * ((1 << d.types[t].levels) - 1) + sc.mctotal[t][2];
+      {  // side file with the full state of this rank's chains, written before the reference-format files
+         vector<char> blob(pimcgpu_checkpoint_bytes());
+         ck(pimcgpu_checkpoint_save(blob.data(), (long)blob.size()), "pimcgpu_checkpoint_save");
+         ofstream f(ckname + ".tmp", ios::binary);
+         f.write(blob.data(), blob.size());
+         f.close();
+         rename((ckname + ".tmp").c_str(), ckname.c_str());
+      }
       if (rank != 0) continue;
       // MCSaveAcceptRatio, mc_main.cc:879-943
       cout << "BLOCK:" << setw(8) << block << BLANK << "PASS:" << setw(8) << d.passes << BLANK << "STEP:" << setw(8) << steps_block << BLANK;
@@ -484,7 +509,7 @@ int main(int argc, char **argv)
       }
       // checkpoint, mc_main.cc:471-483: yw001.stat / .conf / .tabl in the reference's byte layout, chain 0
       ck(pimcgpu_download_state(0, coords.data(), angles.data(), cosine.data(), bstype >= 0 ? pindex.data() : nullptr), "pimcgpu_download_state");
-      { ofstream f("yw001.stat"); f << "STARTBLOCK " << 0 << endl; }
+      { ofstream f("yw001.stat"); f << "STARTBLOCK " << block << endl; }
       {
          ofstream f("yw001.conf", ios::binary);
          streamsize size = sizeof(double) * n;

@@ -26,7 +26,7 @@ EXPORTS = [
     "pimcgpu_eval_lpot2d", "pimcgpu_eval_srotdens", "pimcgpu_eval_rotden", "pimcgpu_eval_vcord", "pimcgpu_eval_caleng",
     "pimcgpu_pot_energy_slice", "pimcgpu_rng_draws", "pimcgpu_fp64_peak", "pimcgpu_host_spline",
     "pimcgpu_host_stream_state", "pimcgpu_host_lut", "pimcgpu_accum_offset", "pimcgpu_symmetry_moves", "pimcgpu_symmetry_ops",
-    "pimcgpu_chain_areas", "pimcgpu_worm_moves", "pimcgpu_worm_state", "pimcgpu_worm_set", "pimcgpu_worm_counters",
+    "pimcgpu_checkpoint_bytes", "pimcgpu_checkpoint_save", "pimcgpu_checkpoint_load", "pimcgpu_chain_areas", "pimcgpu_worm_moves", "pimcgpu_worm_state", "pimcgpu_worm_set", "pimcgpu_worm_counters",
 ]
 
 
@@ -90,6 +90,7 @@ def lib():
         L.pimcgpu_rng_draws.argtypes = [C.c_long, C.c_int, c_dp]
         L.pimcgpu_accum_download.argtypes = [c_dp, C.c_long]
         L.pimcgpu_accum_offset.restype = C.c_long
+        L.pimcgpu_checkpoint_bytes.restype = C.c_long
         L.pimcgpu_accum_offset.argtypes = [C.c_char_p]
         _lib = L
     return _lib
@@ -240,6 +241,16 @@ class PimcGpu:
         out = np.zeros(28)
         _ck(self.L.pimcgpu_chain_areas(C.c_int(chain), _dp(out)))
         return dict(lin=out[0:4], sff_area=out[4:7], sff_inert=out[7:16], mff_area=out[16:19], mff_inert=out[19:28])
+
+    # checkpoint (N4) ---------------------------------------------------------------------------
+    def checkpoint_save(self):
+        n = self.L.pimcgpu_checkpoint_bytes()
+        buf = (C.c_char * n)()
+        _ck(self.L.pimcgpu_checkpoint_save(buf, C.c_long(n)))
+        return bytes(buf)
+
+    def checkpoint_load(self, blob):
+        _ck(self.L.pimcgpu_checkpoint_load(C.c_char_p(blob), C.c_long(len(blob))))
 
     # worm --------------------------------------------------------------------------------------
     def worm_moves(self, sync=True):

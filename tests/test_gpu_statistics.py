@@ -196,3 +196,43 @@ def test_cxx_driver_writes_reference_formats(pkg, tmp_path):
         assert os.path.exists(tmp_path / f), f
     assert open(tmp_path / "yw001.stat").read().startswith("STARTBLOCK ")
     assert os.path.getsize(tmp_path / "yw001.conf") == 8 + 2 * 8 * 4      # streamsize + x row + cosine x row (N*P = 4)
+
+
+def test_cxx_driver_worm_deck_and_restart(pkg, tmp_path):
+    """pimc_b200 on the reference's examples/N2O_5pH2 deck with its own WORM line (2-D potential file written in the
+    README.md:78-123 format): the exchange / superfluid output files appear in the reference's layout, and a RESTART run
+    continues from the side-file checkpoint with the block counter of yw001.stat (rows N1, N4)."""
+    drv = os.path.join(ROOT, "moribs-pimc_b200", "driver", "pimc_b200")
+    if not os.path.exists(drv):
+        pytest.skip("driver binary not built")
+    d = os.path.join(pkg.configs.DECKS, "N2O_5pH2_0.5K_512_128")
+    shutil.copy(os.path.join(d, "parah2.pot"), tmp_path)
+    shutil.copy(os.path.join(d, "N2O_T0.5t128.rot"), tmp_path)
+    rg, cg, v = pkg.configs.synth_pot2d(rsize=401, csize=201, dr=0.025, dc=0.01)
+    pkg.configs.write_pot2d(str(tmp_path / "h2n2ogr.pot"), rg, cg, v, 0.025, 0.01)
+    deck = open(os.path.join(d, "qmc.input")).read()
+    deck = deck.replace("OUTPUTDIR        ./results/", "OUTPUTDIR        ./").replace("NUMBEROFPASSES     5000 ", "NUMBEROFPASSES     2 ")
+    deck = deck.replace("NUMBEROFBLOCKS     300 5 ", "NUMBEROFBLOCKS     4 1 ")
+    assert "WORM       H2    2.9  8" in deck and "NUMBEROFBLOCKS     4 1" in deck and "NUMBEROFPASSES     2" in deck
+    open(tmp_path / "qmc.input", "w").write(deck)
+    out = subprocess.run([drv, "--chains", "8"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "WORM: open/close" in out.stdout
+    eng = np.loadtxt(tmp_path / "gr.eng", ndmin=2)
+    assert eng.shape == (3, 10) and list(eng[:, 0]) == [2, 3, 4]
+    prl = open(tmp_path / "gr.prl").read().split("\n")
+    first = prl[0].split()
+    assert len(first) == 1 + 3 + 5 and abs(float(first[3]) - 1.0) < 1e-9          # block, ground, excited, norm check, 5 loop weights
+    sup = np.loadtxt(tmp_path / "gr.sup", ndmin=2)
+    sff = np.loadtxt(tmp_path / "gr.sffs3d", ndmin=2)
+    assert sup.shape == (3, 7) and sff.shape == (3, 16) and np.all(np.isfinite(sup)) and np.all(sff[:, [1, 5, 9]] > 0)
+    assert os.path.getsize(tmp_path / "yw001.worm") == 80 + 6 * 4 + 4 + 8 + 8 or os.path.getsize(tmp_path / "yw001.worm") > 100
+    assert open(tmp_path / "yw001.stat").read().split() == ["STARTBLOCK", "4"]
+    # restart: two more blocks, numbered 5 and 6, appended to the same files
+    open(tmp_path / "qmc.input", "w").write(deck.replace("NUMBEROFBLOCKS     4 1 ", "NUMBEROFBLOCKS     2 0 ") + "RESTART\n")
+    out = subprocess.run([drv, "--chains", "8"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "RESTART at block 4" in out.stdout
+    eng = np.loadtxt(tmp_path / "gr.eng", ndmin=2)
+    assert list(eng[:, 0]) == [2, 3, 4, 5, 6]
+    assert open(tmp_path / "yw001.stat").read().split() == ["STARTBLOCK", "6"]

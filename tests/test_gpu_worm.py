@@ -120,3 +120,37 @@ def test_schedule_with_worm(pkg, name):
     nclosed = sum(1 - G.worm_state(c)[0] for c in range(2))
     assert acc[0] == nclosed
     G.close()
+
+
+@pytest.mark.parametrize("name", ["C2", "C5"])
+def test_checkpoint_restart_is_exact(pkg, name):
+    """N4: a context that loads pimcgpu_checkpoint_save's blob continues bit-identically (beads, angles, permutation
+    tables, worm, MRG32k3a streams, rotor-potential cache, step counter), here with exchange sampling switched on."""
+    cfg = make(pkg, name)
+    s = cfg.system
+    s.worm = (s.worm[0], 0.003, s.worm[2])
+    nb = s.types[0].numb
+    G = pkg.gpu.PimcGpu(cfg, nchains=2, chain_offset=4)
+    G.seed((5, 6, 7, 8, 9, 10))
+    n1, n2 = s.P + 7, 2 * s.P + 3
+    G.steps(n1)
+    blob = G.checkpoint_save()
+    G.steps(n2)
+    ref = [G.download(c) for c in range(2)]
+    refw = [G.worm_state(c) for c in range(2)]
+    refp = [G.download_perm(c) for c in range(2)]
+    G.close()
+    G2 = pkg.gpu.PimcGpu(cfg, nchains=2, chain_offset=4)
+    G2.checkpoint_load(blob)
+    assert G2.L.pimcgpu_step_counter() == n1
+    G2.steps(n2)
+    for c in range(2):
+        got = G2.download(c)
+        assert np.array_equal(got[0], ref[c][0]) and np.array_equal(got[1], ref[c][1])
+        assert G2.worm_state(c) == refw[c] and np.array_equal(G2.download_perm(c), refp[c])
+    # a blob of another system is refused
+    G2.close()
+    other = pkg.gpu.PimcGpu(cfg, nchains=3, chain_offset=4)
+    with pytest.raises(pkg.gpu.PimcGpuError, match="different system"):
+        other.checkpoint_load(blob)
+    other.close()
