@@ -203,6 +203,38 @@ int pimcgpu_host_spline(int n, const double *x, const double *y, double *y2, dou
 int pimcgpu_host_stream_state(const unsigned long seed6[6], long stream, unsigned long state6[6]);
 int pimcgpu_host_lut(int n, const double *x, int *lut /* [4n] */, double *scale);   /* returns the table length */
 
+/* ---- rotational density-matrix table generators on the device (csrc/pimc_tablegen.cu).  They need no
+ *      pimcgpu_init context.  Each replaces one of the reference's Fortran pre-processing programs and takes that
+ *      program's command-line arguments in the same order; outputs are host arrays in the layout the programs write.
+ *      There is no CPU fallback: without a CUDA device they fail with a message.                                     ---- */
+/* nmv_prop/asymrho.f (asymrho.x T P iodevn ith0 ithend A B C maxj; a-run:4): theta planes ith0..ith1 (degrees, 0..180) of the
+ * asymmetric-top propagator, energy and energy-square estimators; rho/eng/esq are [ith1-ith0+1][361 phi][361 chi], i.e. the
+ * line order of rho.denXXX_rho/_eng/_esq (asymrho.f:713-725) and, for ith0=0, ith1=180, of the complete table read by
+ * init_rot3D (mc_poten.cc:462-499).  info[16] (may be NULL) = the log lines "AT BETA" Z,E(cm-1),Cv for even k, odd k, classical
+ * (asymrho.f:354-368), "AT TAU" Z,E for even, odd, classical (:413-425), emax.  Errors mirror the Fortran STOPs
+ * (maxj > 876, iodevn outside -1..1, 'too large contribution from emax', QL 'FAIL').                                         */
+int pimcgpu_gen_asymrho(double temprt, int nslice, int iodevn, int ith0, int ith1, double Arot, double Brot, double Crot,
+                        int maxj, double *rho, double *eng, double *esq, double *info);
+/* symtop_prop/symrho.f (symrho.x T P kmod ith0 ithend Bz Bxy maxj; a-run:4); same output layout; info[5] = ztau, zbeta,
+ * Ebeta (K), Esqrt (K^2), Cv (symrho.f:100-104); error 'pmax too large' as symrho.f:115-118                                  */
+int pimcgpu_gen_symrho(double temprt, int nslice, int kmod, int ith0, int ith1, double Bz, double Bxy, int maxj, double *rho,
+                       double *eng, double *esq, double *info);
+/* linear_prop/linden.f (linden.x T P B npt iodevn): out[npt][4] = cos(gamma), rho, erot, erotsq -- the four columns of
+ * linden.out / <type>_T<T>t<Q>.rot read by init_rotdens (mc_poten.cc:518-545); bit-identical to the Fortran's arithmetic.
+ * info[4] = tau, lmax, "Erot at Beta", "Cv at Beta" (linden.f:72-82)                                                         */
+int pimcgpu_gen_linden(double temprt, int nslice, double bconst, int npt, int iodevn, double *out, double *info);
+/* parity entry point: Wigner d^j_{mk}(theta) in the convention of wigd (asymrho.f:1006-1039), d[(maxj+1)][2maxj+1][2maxj+1] */
+int pimcgpu_gen_wigner_d(int maxj, double theta, double *d);
+/* device milliseconds of the last pimcgpu_gen_asymrho call: eigen-solve + projectors + Fourier coefficients, phi stage,
+ * chi GEMM, combine                                                                                                          */
+int pimcgpu_gen_timing(double *ms4);
+/* host-side writers in the Fortran edit descriptors of the generators: E15.8 (scale1p = 0; asymrho.f:721-723) or 1P,E15.8
+ * (scale1p = 1; linden.f:68) into buf[16]; one E15.8 value per line (append != 0 continues a file, as compile.x concatenates
+ * planes); the four-column .rot file                                                                                         */
+void pimcgpu_format_e15_8(double v, int scale1p, char *buf);
+int  pimcgpu_write_e15_8(const char *path, const double *v, long n, int append);
+int  pimcgpu_write_rot(const char *path, const double *out4, int npt);
+
 /* measured FP64 FMA throughput of the current device in TFLOP/s (roofline denominator; not part of the path) */
 int pimcgpu_fp64_peak(double *tflops);
 

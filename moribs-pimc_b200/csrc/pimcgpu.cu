@@ -31,6 +31,9 @@ int fail(const char *fmt, ...)
    g_err = buf;
    return 1;
 }
+}  // namespace
+namespace pimc { int set_error(const char *msg) { g_err = msg; return 1; } }   // for the other translation units (pimc_tablegen.cu)
+namespace {
 #define CK(call)                                                                            \
    do {                                                                                     \
       cudaError_t e_ = (call);                                                              \

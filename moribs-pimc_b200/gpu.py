@@ -27,6 +27,8 @@ EXPORTS = [
     "pimcgpu_pot_energy_slice", "pimcgpu_rng_draws", "pimcgpu_fp64_peak", "pimcgpu_host_spline",
     "pimcgpu_host_stream_state", "pimcgpu_host_lut", "pimcgpu_accum_offset", "pimcgpu_symmetry_moves", "pimcgpu_symmetry_ops",
     "pimcgpu_checkpoint_bytes", "pimcgpu_checkpoint_save", "pimcgpu_checkpoint_load", "pimcgpu_chain_areas", "pimcgpu_worm_moves", "pimcgpu_worm_state", "pimcgpu_worm_set", "pimcgpu_worm_counters",
+    "pimcgpu_gen_asymrho", "pimcgpu_gen_symrho", "pimcgpu_gen_linden", "pimcgpu_gen_wigner_d", "pimcgpu_gen_timing",
+    "pimcgpu_format_e15_8", "pimcgpu_write_e15_8", "pimcgpu_write_rot",
 ]
 
 
@@ -62,13 +64,20 @@ class GpuScalars(C.Structure):
 
 
 def build(force: bool = False) -> str:
-    """nvcc cross-compile of the in-tree library for sm_100a (works without a GPU)."""
-    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
-    srcs.append(os.path.join(os.path.dirname(HERE), "include", "pimcgpu.h"))
-    if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(s) for s in srcs):
-        return LIB
-    cmd = ["nvcc"] + NVCC_FLAGS + ["-o", LIB, os.path.join(CSRC, "pimcgpu.cu")]
-    subprocess.check_call(cmd)
+    """nvcc cross-compile of the in-tree library for sm_100a (works without a GPU): one object per translation unit
+    (pimcgpu.cu = the sampling path, pimc_tablegen.cu = the rho-table generators), linked into libpimcgpu.so."""
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
+    hdrs.append(os.path.join(os.path.dirname(HERE), "include", "pimcgpu.h"))
+    units = {"pimcgpu.cu": hdrs, "pimc_tablegen.cu": hdrs[-1:]}
+    objs, relink = [], force or not os.path.exists(LIB)
+    for cu, deps in units.items():
+        src, obj = os.path.join(CSRC, cu), os.path.join(CSRC, cu[:-3] + ".o")
+        objs.append(obj)
+        if force or not os.path.exists(obj) or any(os.path.getmtime(obj) < os.path.getmtime(d) for d in [src] + deps):
+            subprocess.check_call(["nvcc"] + [f for f in NVCC_FLAGS if f != "-shared"] + ["-c", "-o", obj, src])
+            relink = True
+    if relink or any(os.path.getmtime(LIB) < os.path.getmtime(o) for o in objs):
+        subprocess.check_call(["nvcc", "-shared", "-Xcompiler", "-fopenmp", "-o", LIB] + objs)
     return LIB
 
 
@@ -92,6 +101,7 @@ def lib():
         L.pimcgpu_accum_offset.restype = C.c_long
         L.pimcgpu_checkpoint_bytes.restype = C.c_long
         L.pimcgpu_accum_offset.argtypes = [C.c_char_p]
+        L.pimcgpu_format_e15_8.restype = None
         _lib = L
     return _lib
 
@@ -117,6 +127,68 @@ class PimcGpuError(RuntimeError):
 def _ck(rc):
     if rc:
         raise PimcGpuError(lib().pimcgpu_last_error().decode())
+
+
+# ---- rho-table generators (csrc/pimc_tablegen.cu; no context needed) -------------------------------------
+NPLANE = 361 * 361
+
+
+def _planes(nt):
+    return [np.zeros((nt, 361, 361)) for _ in range(3)]
+
+
+def gen_asymrho(T, nslice, iodevn, ith0, ith1, A, B, Cc, maxj):
+    """asymrho.x T P iodevn ith0 ithend A B C maxj -> rho, eng, esq [ntheta][361][361], info[16]"""
+    r, e, q = _planes(ith1 - ith0 + 1)
+    info = np.zeros(16)
+    _ck(lib().pimcgpu_gen_asymrho(C.c_double(T), C.c_int(nslice), C.c_int(iodevn), C.c_int(ith0), C.c_int(ith1), C.c_double(A),
+                                  C.c_double(B), C.c_double(Cc), C.c_int(maxj), _dp(r), _dp(e), _dp(q), _dp(info)))
+    return r, e, q, info
+
+
+def gen_timing():
+    ms = np.zeros(4)
+    _ck(lib().pimcgpu_gen_timing(_dp(ms)))
+    return ms
+
+
+def gen_symrho(T, nslice, kmod, ith0, ith1, Bz, Bxy, maxj):
+    """symrho.x T P kmod ith0 ithend Bz Bxy maxj -> rho, eng, esq [ntheta][361][361], info[5]"""
+    r, e, q = _planes(ith1 - ith0 + 1)
+    info = np.zeros(5)
+    _ck(lib().pimcgpu_gen_symrho(C.c_double(T), C.c_int(nslice), C.c_int(kmod), C.c_int(ith0), C.c_int(ith1), C.c_double(Bz),
+                                 C.c_double(Bxy), C.c_int(maxj), _dp(r), _dp(e), _dp(q), _dp(info)))
+    return r, e, q, info
+
+
+def gen_linden(T, nslice, bconst, npt, iodevn):
+    """linden.x T P B npt iodevn -> out[npt][4] (cos gamma, rho, erot, erotsq), info[4]"""
+    out = np.zeros((npt, 4))
+    info = np.zeros(4)
+    _ck(lib().pimcgpu_gen_linden(C.c_double(T), C.c_int(nslice), C.c_double(bconst), C.c_int(npt), C.c_int(iodevn), _dp(out), _dp(info)))
+    return out, info
+
+
+def gen_wigner_d(maxj, theta):
+    d = np.zeros((maxj + 1, 2 * maxj + 1, 2 * maxj + 1))
+    _ck(lib().pimcgpu_gen_wigner_d(C.c_int(maxj), C.c_double(theta), _dp(d)))
+    return d
+
+
+def format_e15_8(v, scale1p=False):
+    b = C.create_string_buffer(16)
+    lib().pimcgpu_format_e15_8(C.c_double(v), C.c_int(1 if scale1p else 0), b)
+    return b.value.decode()
+
+
+def write_e15_8(path, v, append=False):
+    a = np.ascontiguousarray(v, dtype=np.float64).ravel()
+    _ck(lib().pimcgpu_write_e15_8(path.encode(), _dp(a), C.c_long(a.size), C.c_int(1 if append else 0)))
+
+
+def write_rot(path, out4):
+    a = np.ascontiguousarray(out4, dtype=np.float64)
+    _ck(lib().pimcgpu_write_rot(path.encode(), _dp(a), C.c_int(a.shape[0])))
 
 
 class PimcGpu:

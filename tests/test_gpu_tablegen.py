@@ -1,0 +1,219 @@
+"""GPU parity tests of the rho-table generators (csrc/pimc_tablegen.cu) through the C ABI.
+
+Checkers: (1) the reference's OWN golden outputs (tests/golden/tablegen/ref_*.npz: nmv_prop/rho.den010_*, nmv_prop/log,
+symtop_prop/rho.den0{00,10}_*, the two .rot files of examples/), (2) the quad-precision oracle's outputs for a small
+asymmetric top and for Wigner d matrices (oracle_asym_small.npz; the oracle itself is run again where it is fast).
+
+Bars: linear rotor -- BYTE-identical .rot files.  Tops -- the device evaluates the same sums in a factorised order, and
+the reference's tables carry rounding noise of ~1e-15 max|rho| from their alternating sums: half a unit of the last
+printed digit (E15.8) + that noise against the golden files; 1e-12 max|rho| against the oracle's doubles.
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden", "tablegen")
+
+
+def ulp8(g):
+    g = np.abs(np.asarray(g, dtype=float))
+    return 10.0 ** (np.floor(np.log10(np.maximum(g, 1e-300))) + 1 - 8)
+
+
+@pytest.fixture(scope="module")
+def gpu(pkg):
+    return pkg.gpu
+
+
+@pytest.fixture(scope="module")
+def tg():
+    from oracle import tablegen_py
+    return tablegen_py
+
+
+def test_wigner_d_recurrence_vs_quad_precision_sum(gpu):
+    """FP64 upward recurrence in j against Zare's sum evaluated in real*16 (wigd, asymrho.f:1006-1039)"""
+    f = np.load(os.path.join(GOLD, "oracle_asym_small.npz"))
+    for maxj, n in ((24, 3), (66, 2)):
+        for it in range(n):
+            th = float(f[f"wigd_j{maxj}_{it}_theta"])
+            d = gpu.gen_wigner_d(maxj, th)
+            js = f[f"wigd_j{maxj}_{it}_js"]
+            ref = f[f"wigd_j{maxj}_{it}"]
+            err = np.abs(d[js] - ref).max()
+            assert err < 2e-13, (maxj, th, err)
+    # closed forms at the poles: d(0) = delta_mk, d(pi) = (-1)^(j-k) delta_{m,-k} in this convention
+    maxj = 30
+    d0, dpi = gpu.gen_wigner_d(maxj, 0.0), gpu.gen_wigner_d(maxj, np.pi)
+    for j in (0, 1, 7, 30):
+        w = np.arange(-j, j + 1) + maxj
+        assert np.abs(d0[j][np.ix_(w, w)] - np.eye(2 * j + 1)).max() < 1e-13
+        anti = np.abs(dpi[j][np.ix_(w, w)])
+        assert np.abs(anti - np.eye(2 * j + 1)[::-1]).max() < 1e-10
+    # unitarity of every d^j at a generic angle
+    d = gpu.gen_wigner_d(maxj, 1.234)
+    for j in range(maxj + 1):
+        w = np.arange(-j, j + 1) + maxj
+        m = d[j][np.ix_(w, w)]
+        assert np.abs(m @ m.T - np.eye(2 * j + 1)).max() < 5e-13
+
+
+def test_wigner_d_against_live_oracle(gpu, tg):
+    maxj, th = 12, 2.2
+    d = gpu.gen_wigner_d(maxj, th)
+    for j in (0, 1, 5, 12):
+        for m in range(-j, j + 1):
+            for k in range(-j, j + 1):
+                assert abs(d[j, m + maxj, k + maxj] - tg.wigd(j, m, k, th)) < 1e-14
+
+
+def test_asymrho_reference_golden_plane(gpu):
+    """asymrho.x 0.37 128 -1 10 10 0.6666525 0.2306476 0.1769383 66 (nmv_prop/a-run) against nmv_prop/rho.den010_*"""
+    f = np.load(os.path.join(GOLD, "ref_asymrho_den010.npz"))
+    T, ns, io, i0, i1, A, B, C, maxj = f["args"]
+    r, e, q, info = gpu.gen_asymrho(float(T), int(ns), int(io), int(i0), int(i1), float(A), float(B), float(C), int(maxj))
+    r, e, q = r[0], e[0], q[0]
+    rmax = np.abs(f["rho"]).max()
+    noise = 1e-13 * rmax                                     # the reference's own rounding noise (values down to -1e-14 in the file)
+    assert np.all(np.abs(r - f["rho"]) <= 0.51 * ulp8(f["rho"]) + noise)
+    good = np.abs(f["rho"]) > 1e-4 * rmax
+    assert good.sum() > 2000
+    assert np.all(np.abs(e - f["eng"])[good] <= 0.51 * ulp8(f["eng"])[good] + 1e-8 * np.abs(f["eng"])[good])
+    assert np.all(np.abs(q - f["esq"])[good] <= 0.51 * ulp8(f["esq"])[good] + 1e-8 * np.abs(f["esq"])[good])
+    txt = [gpu.format_e15_8(v) for v in r[good]]
+    ref = [gpu.format_e15_8(v) for v in f["rho"][good]]
+    same = sum(a == b for a, b in zip(txt, ref))
+    assert same >= 0.97 * len(ref), (same, len(ref))         # identical text; the rest differ by one unit of the last digit
+    # log lines "AT BETA" / "AT TAU" (F12.6)
+    i = info
+    mine = np.array([[i[0], i[1], i[1] / 0.6950356, i[2]], [i[3], i[4], i[4] / 0.6950356, i[5]], [i[6], i[7], i[7] / 0.6950356, i[8]]])
+    assert np.all(np.abs(mine - f["at_beta"]) <= 0.5000001e-6)
+    mine_tau = np.array([[i[9], i[10], i[10] / 0.6950356], [i[11], i[12], i[12] / 0.6950356], [i[13], i[14], i[14] / 0.6950356]])
+    assert np.all(np.abs(mine_tau - f["at_tau"]) <= 0.51e-5 * np.maximum(1.0, np.abs(f["at_tau"])))
+    # the plane obeys the symmetries the reference imposes by copying
+    assert np.array_equal(r, r.T) and np.array_equal(e, e.T)
+
+
+@pytest.mark.parametrize("io", [-1, 0, 1])
+def test_asymrho_small_top_vs_oracle_planes(gpu, io):
+    """whole theta planes (direct region + symmetry fill, every 5th degree) of a water-like top, all three iodevn"""
+    f = np.load(os.path.join(GOLD, "oracle_asym_small.npz"))
+    T, ns, A, B, C, maxj = f["args"]
+    r, e, q, info = gpu.gen_asymrho(float(T), int(ns), io, 0, 180, float(A), float(B), float(C), int(maxj))
+    assert np.allclose(info, f[f"io{io}_info"], rtol=1e-12, atol=0)
+    for ith in (0, 37, 90, 180):
+        ref = f[f"io{io}_th{ith}"]
+        rmax = np.abs(ref[0]).max()
+        got = np.stack([r[ith], e[ith], q[ith]])[:, ::5, ::5]
+        assert np.abs(got[0] - ref[0]).max() <= 1e-12 * rmax, (io, ith)
+        good = np.abs(ref[0]) > 1e-6 * rmax
+        assert good.sum() > 100
+        assert np.all(np.abs(got[1] - ref[1])[good] <= 1e-9 * np.abs(ref[1])[good] + 1e-9)
+        assert np.all(np.abs(got[2] - ref[2])[good] <= 1e-9 * np.abs(ref[2])[good] + 1e-7)
+
+
+def test_asymrho_live_oracle_points_and_sum_rules(gpu, tg):
+    T, ns, A, B, C, maxj = 5.0, 4, 9.0, 3.0, 2.0, 14
+    r, e, q, info = gpu.gen_asymrho(T, ns, -1, 0, 180, A, B, C, maxj)
+    o = tg.AsymRho(T, ns, -1, A, B, C, maxj)
+    rmax = np.abs(r).max()
+    rng = np.random.default_rng(7)
+    for _ in range(40):
+        ith, iphi = int(rng.integers(0, 181)), int(rng.integers(0, 361))
+        ichi = int(rng.integers(0, tg.maxchi(iphi) + 1))
+        v = o.point(ith, iphi, ichi)
+        assert abs(r[ith, iphi, ichi] - v[0]) <= 1e-12 * rmax
+        if abs(v[0]) > 1e-6 * rmax:
+            assert abs(e[ith, iphi, ichi] - v[1]) <= 1e-9 * abs(v[1]) + 1e-9
+            assert abs(q[ith, iphi, ichi] - v[2]) <= 1e-9 * abs(v[2]) + 1e-7
+    # size-independent properties of the full 181 x 361 x 361 table:
+    # rho(identity) = Z(tau)/8pi^2 and E(identity) = <E> at tau (sum over m of c_m^2 = 1)
+    assert abs(r[0, 0, 0] * 8 * np.pi ** 2 - info[13]) <= 1e-12 * info[13]
+    assert abs(e[0, 0, 0] - info[14]) <= 1e-11 * abs(info[14])
+    # at theta = 0 the rotation depends on phi + chi only
+    for (a, b) in ((10, 20), (100, 3), (200, 100)):
+        assert abs(r[0, a, b] - r[0, a + b, 0]) <= 1e-12 * rmax
+    # phi <-> chi symmetry and the 360-degree period
+    assert np.array_equal(r, np.swapaxes(r, 1, 2))
+    assert np.abs(r[:, 0, :] - r[:, 360, :]).max() <= 1e-12 * rmax
+    o.close()
+
+
+def test_asymrho_errors_mirror_the_fortran_stops(gpu):
+    with pytest.raises(gpu.PimcGpuError, match="too large contribution from emax"):
+        gpu.gen_asymrho(300.0, 1, -1, 0, 0, 0.6666525, 0.2306476, 0.1769383, 10)
+    with pytest.raises(gpu.PimcGpuError, match="iodevn can only be"):
+        gpu.gen_asymrho(0.37, 128, 2, 0, 0, 0.6666525, 0.2306476, 0.1769383, 66)
+    with pytest.raises(gpu.PimcGpuError, match="876"):
+        gpu.gen_asymrho(0.37, 128, -1, 0, 0, 0.6666525, 0.2306476, 0.1769383, 900)
+    with pytest.raises(gpu.PimcGpuError, match="pmax too large"):
+        gpu.gen_symrho(300.0, 1, 1, 0, 0, 0.5, 0.3, 10)
+
+
+@pytest.mark.parametrize("ith", [0, 10])
+def test_symrho_reference_golden_planes(gpu, ith):
+    """symrho.x 0.37 128 1 ith ith 0.5 0.3 66 (symtop_prop/a-run) against symtop_prop/rho.den0{00,10}_*"""
+    f = np.load(os.path.join(GOLD, f"ref_symrho_den{ith:03d}.npz"))
+    T, ns, kmod, _, _, Bz, Bxy, maxj = f["args"]
+    r, e, q, info = gpu.gen_symrho(float(T), int(ns), int(kmod), ith, ith, float(Bz), float(Bxy), int(maxj))
+    r, e, q = r[0], e[0], q[0]
+    rmax = np.abs(f["rho"]).max()
+    assert np.all(np.abs(r - f["rho"]) <= 0.51 * ulp8(f["rho"]) + 1e-14 * rmax)
+    good = np.abs(f["rho"]) > 1e-5 * rmax
+    assert good.sum() > 10000
+    assert np.all(np.abs(e - f["eng"])[good] <= 0.51 * ulp8(f["eng"])[good] + 2e-6)
+    if "esq" in f.files:
+        assert np.all(np.abs(q - f["esq"])[good] <= 0.51 * ulp8(f["esq"])[good] + 2e-3)
+    same = sum(gpu.format_e15_8(a) == gpu.format_e15_8(b) for a, b in zip(r[good][::7], f["rho"][good][::7]))
+    assert same >= 0.98 * len(r[good][::7])
+
+
+def test_symrho_vs_live_oracle_kmod(gpu, tg):
+    for kmod, ith in ((1, 25), (3, 90), (2, 180)):
+        r, e, q, info = gpu.gen_symrho(2.0, 8, kmod, ith, ith, 5.0, 2.5, 30)
+        ro, eo, qo, io = tg.symrho_plane(2.0, 8, kmod, ith, 5.0, 2.5, 30)
+        rmax = np.abs(ro).max()
+        assert np.abs(r[0] - ro).max() <= 1e-13 * rmax
+        good = np.abs(ro) > 1e-6 * rmax
+        assert np.all(np.abs(e[0] - eo)[good] <= 1e-9 * np.abs(eo)[good] + 1e-9)
+        assert np.all(np.abs(q[0] - qo)[good] <= 1e-9 * np.abs(qo)[good] + 1e-7)
+        assert np.allclose(info, io, rtol=1e-13)
+
+
+@pytest.mark.parametrize("name", ["N2O", "CO2"])
+def test_linden_byte_identical_to_reference_rot_files(gpu, name, tmp_path):
+    f = np.load(os.path.join(GOLD, f"ref_linden_{name}.npz"))
+    T, ns, B, npt, io = f["args"]
+    out, info = gpu.gen_linden(float(T), int(ns), float(B), int(npt), int(io))
+    p, pref = str(tmp_path / "linden.out"), str(tmp_path / "ref.rot")
+    gpu.write_rot(p, out)
+    gpu.write_rot(pref, f["table"])                              # text -> float64 -> text is the identity (make_fixtures.py)
+    assert open(p, "rb").read() == open(pref, "rb").read()
+    first = open(p).readline()
+    assert first.startswith(" -1.00000000E+00") and len(first) == 65
+
+
+def test_linden_bit_identical_to_oracle_all_iodevn(gpu, tg):
+    for io in (-1, 0, 1):
+        out, info = gpu.gen_linden(1.5, 16, 1.92253, 501, io)
+        oo, oi = tg.linden(1.5, 16, 1.92253, 501, io)
+        assert np.array_equal(out, oo)
+        assert np.allclose(info, oi, rtol=1e-14)
+
+
+def test_table_files_roundtrip_through_the_e15_8_writer(gpu, tmp_path):
+    """planes written like rho.denXXX_rho and concatenated like nmv_prop/compile.x; read back as init_rot3D does"""
+    r, e, q, _ = gpu.gen_asymrho(10.0, 2, -1, 3, 4, 27.877, 14.512, 9.285, 10)
+    p = str(tmp_path / "X_T10t2.rho")
+    gpu.write_e15_8(p, r[0])
+    gpu.write_e15_8(p, r[1], append=True)
+    back = np.loadtxt(p)
+    assert back.size == 2 * 361 * 361
+    assert np.all(np.abs(back - r.ravel()) <= 0.51 * ulp8(r.ravel()))
+    lines = open(p).read().split("\n")
+    assert all(len(l) == 15 for l in lines[:-1]) and lines[-1] == ""
+    assert lines[0] == gpu.format_e15_8(r[0, 0, 0])
