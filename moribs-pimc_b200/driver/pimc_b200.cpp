@@ -185,6 +185,14 @@ static vector<double> read_numbers(const string &path, size_t n)
    return v;
 }
 
+// values as a run would read them back from the generated files (E15.8 / 1P,E15.8 text)
+static string fortran_1p(double v) { char b[16]; pimcgpu_format_e15_8(v, 1, b); return b; }
+static void round_e15_8(vector<double> &v)
+{
+#pragma omp parallel for schedule(static)
+   for (long i = 0; i < (long)v.size(); i++) { char b[32]; snprintf(b, sizeof b, "%.7E", v[i]); v[i] = strtod(b, nullptr); }
+}
+
 static string cxx_double(double x) { ostringstream o; o << x; return o.str(); }     // how init_rot3D spells the temperature
 
 struct Writer {
@@ -275,13 +283,41 @@ int main(int argc, char **argv)
       if (d.rotden_type == 1) {
          // InitRotDensity loads nothing for the rattle-and-shake propagator (mc_poten.cc:148-164)
       } else if (s.molecule == 1) {
-         trot = read_columns(base + ".rot", 4);
+         if (!ifstream(base + ".rot").good() && d.xrot > 0.0) {
+            // table absent: what linden.x T Q B 1500 iodevn writes (linear_prop/README), generated on the device
+            cout << "generating " << base << ".rot on the device (linden: B=" << d.xrot << " cm-1, 1500 points)" << endl;
+            vector<double> t4(1500 * 4);
+            ck(pimcgpu_gen_linden(d.temperature, Q, d.xrot, 1500, d.rot_odevn, t4.data(), nullptr), "pimcgpu_gen_linden");
+            if (rank == 0) ck(pimcgpu_write_rot((base + ".rot").c_str(), t4.data(), 1500), "pimcgpu_write_rot");
+            trot.assign(4, vector<double>(1500));
+            for (int i = 0; i < 1500; i++) for (int k = 0; k < 4; k++) trot[k][i] = strtod(fortran_1p(t4[4 * i + k]).c_str(), nullptr);
+         } else
+            trot = read_columns(base + ".rot", 4);
          tab.nrot = (int)trot[0].size(); tab.rotgrid = trot[0].data(); tab.rotdens = trot[1].data(); tab.rotderv = trot[2].data(); tab.rotesqr = trot[3].data();
       } else {
          cout << base << ".rho " << base << ".eng " << base << ".esq" << endl;
+         if (!ifstream(base + ".rho").good() && d.xrot > 0.0 && d.yrot > 0.0 && d.zrot > 0.0) {
+            // tables absent: what 181 asymrho.x jobs + compile.x produce (nmv_prop/README), generated on the device from the
+            // ROTDENSI constants.  rotmat (asymrho.f:792-813) quantises along z: Arot = X_Rot, Brot = Z_Rot, Crot = Y_Rot.
+            // maxj: first j whose lowest level falls under the generator's own cut (2j+1)/8pi^2 e^{-tau E} < 1e-16 (:520)
+            const double tau = 1.0 / (0.6950356 * d.temperature) / Q, cmin = std::min(d.xrot, std::min(d.yrot, d.zrot));
+            int maxj = 4;
+            while (maxj < 876 && (2 * maxj + 1) / (8.0 * M_PI * M_PI) * exp(-tau * cmin * maxj * (maxj + 1.0)) >= 1e-16) maxj++;
+            cout << "generating the tables on the device (asymrho: A=" << d.xrot << " B=" << d.zrot << " C=" << d.yrot << " cm-1, maxj=" << maxj << ")" << endl;
+            rho.resize(PIMCGPU_SIZE_ROTDEN); erot.resize(PIMCGPU_SIZE_ROTDEN); esq.resize(PIMCGPU_SIZE_ROTDEN);
+            ck(pimcgpu_gen_asymrho(d.temperature, Q, d.rot_odevn, 0, 180, d.xrot, d.zrot, d.yrot, maxj, rho.data(), erot.data(), esq.data(), nullptr), "pimcgpu_gen_asymrho");
+            // the run uses the values a later run would read back from the files: 8 significant digits (E15.8)
+            round_e15_8(rho); round_e15_8(erot); round_e15_8(esq);
+            if (rank == 0) {
+               ck(pimcgpu_write_e15_8((base + ".rho").c_str(), rho.data(), PIMCGPU_SIZE_ROTDEN, 0), "pimcgpu_write_e15_8");
+               ck(pimcgpu_write_e15_8((base + ".eng").c_str(), erot.data(), PIMCGPU_SIZE_ROTDEN, 0), "pimcgpu_write_e15_8");
+               ck(pimcgpu_write_e15_8((base + ".esq").c_str(), esq.data(), PIMCGPU_SIZE_ROTDEN, 0), "pimcgpu_write_e15_8");
+            }
+         } else {
          rho = read_numbers(base + ".rho", PIMCGPU_SIZE_ROTDEN);
          erot = read_numbers(base + ".eng", PIMCGPU_SIZE_ROTDEN);
          esq = read_numbers(base + ".esq", PIMCGPU_SIZE_ROTDEN);
+         }
          tab.rho3d = rho.data(); tab.erot3d = erot.data(); tab.esq3d = esq.data();
       }
    }

@@ -30,9 +30,11 @@ K = 2 * np_
 rows = 181 * 3 * 361
 gemm_flop = 2.0 * 2 * rows * K * 384                  # both parity classes, padded N
 useful_flop = 2.0 * rows * (2 * 67 + 2 * 66) * 361
-t = time.time()
-rs, es, qs, _ = gpu.gen_symrho(0.37, 128, 1, 0, 180, 0.5, 0.3, 66)
-wall_sym = time.time() - t
+wall_sym = []
+for rep in range(3):
+    t = time.time()
+    rs, es, qs, _ = gpu.gen_symrho(0.37, 128, 1, 0, 180, 0.5, 0.3, 66)
+    wall_sym.append(time.time() - t)
 t = time.time()
 out, _ = gpu.gen_linden(0.5, 128, 1.92253, 1500, -1)
 wall_lin = time.time() - t
