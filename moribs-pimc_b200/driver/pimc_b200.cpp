@@ -284,13 +284,16 @@ int main(int argc, char **argv)
          // InitRotDensity loads nothing for the rattle-and-shake propagator (mc_poten.cc:148-164)
       } else if (s.molecule == 1) {
          if (!ifstream(base + ".rot").good() && d.xrot > 0.0) {
-            // table absent: what linden.x T Q B 1500 iodevn writes (linear_prop/README), generated on the device
-            cout << "generating " << base << ".rot on the device (linden: B=" << d.xrot << " cm-1, 1500 points)" << endl;
-            vector<double> t4(1500 * 4);
-            ck(pimcgpu_gen_linden(d.temperature, Q, d.xrot, 1500, d.rot_odevn, t4.data(), nullptr), "pimcgpu_gen_linden");
-            if (rank == 0) ck(pimcgpu_write_rot((base + ".rot").c_str(), t4.data(), 1500), "pimcgpu_write_rot");
-            trot.assign(4, vector<double>(1500));
-            for (int i = 0; i < 1500; i++) for (int k = 0; k < 4; k++) trot[k][i] = strtod(fortran_1p(t4[4 * i + k]).c_str(), nullptr);
+            // table absent: what linden.x T Q B npt iodevn writes (linear_prop/README uses 1500 points), generated on the
+            // device.  rho falls by 1/e over 2 B tau in cos(gamma) (linden.f:129): at least ten grid points per decay length
+            const double btau = d.xrot * 1.4387752224 / (d.temperature * Q);
+            const int npt = (int)std::min(20001.0, std::max(1500.0, ceil(10.0 / btau) + 1.0));
+            cout << "generating " << base << ".rot on the device (linden: B=" << d.xrot << " cm-1, " << npt << " points)" << endl;
+            vector<double> t4((size_t)npt * 4);
+            ck(pimcgpu_gen_linden(d.temperature, Q, d.xrot, npt, d.rot_odevn, t4.data(), nullptr), "pimcgpu_gen_linden");
+            if (rank == 0) ck(pimcgpu_write_rot((base + ".rot").c_str(), t4.data(), npt), "pimcgpu_write_rot");
+            trot.assign(4, vector<double>(npt));
+            for (int i = 0; i < npt; i++) for (int k = 0; k < 4; k++) trot[k][i] = strtod(fortran_1p(t4[4 * i + k]).c_str(), nullptr);
          } else
             trot = read_columns(base + ".rot", 4);
          tab.nrot = (int)trot[0].size(); tab.rotgrid = trot[0].data(); tab.rotdens = trot[1].data(); tab.rotderv = trot[2].data(); tab.rotesqr = trot[3].data();

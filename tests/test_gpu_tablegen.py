@@ -276,8 +276,12 @@ def test_cxx_driver_generates_missing_rot_table(pkg, tmp_path):
     assert "generating CO2_T100t4.rot on the device" in out.stdout
     sub = tmp_path / "cli"
     sub.mkdir()
-    o2 = subprocess.run([exe, "linden", "100", "4", "0.39021", "1500", "-1"], cwd=sub, capture_output=True, text=True, timeout=120)
+    npt = max(1500, int(np.ceil(10.0 / (0.39021 * 1.4387752224 / (100.0 * 4)))) + 1)     # ten grid points per decay length of rho
+    assert f"{npt} points" in out.stdout
+    o2 = subprocess.run([exe, "linden", "100", "4", "0.39021", str(npt), "-1"], cwd=sub, capture_output=True, text=True, timeout=120)
     assert o2.returncode == 0
     assert open(tmp_path / "CO2_T100t4.rot", "rb").read() == open(sub / "linden.out", "rb").read()
     vals = np.loadtxt(tmp_path / "CO2_monomer.eng", ndmin=2)
-    assert vals.shape[0] == 4 and np.all(np.abs(vals[:, 4] - 97.0) < 6.0)          # rotational energy of CO2 at 100 K, 4 slices
+    exact = float(o2.stdout.split("Erot at Beta:")[1].split()[0])                         # linden.f:81, 99.8 K
+    assert abs(exact - 99.81) < 0.01
+    assert vals.shape[0] == 4 and abs(vals[:, 4].mean() - exact) < 3.0                    # free rotor: no Trotter error
