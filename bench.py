@@ -206,6 +206,9 @@ def main():
     ap.add_argument("--team", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--worm", action="store_true", help="keep the deck's WORM line (C2, C3): exchange sampled with the worm algorithm")
+    ap.add_argument("--tables", default="synthetic", choices=["synthetic", "generated"],
+                    help="C1-C4: 'generated' replaces the analytic stand-in of the rho/E/E2 tables (SURVEY 8d fallback) by the tables the "
+                         "device generator makes from the molecule's rotational constants (asymrho, 8 printed digits)")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
@@ -224,6 +227,14 @@ def main():
     pkg = ge.load_package()
     cfg = pkg.configs.make_config(args.workload, worm=args.worm)
     s = cfg.system
+    tables_note = "shipped .rot file" if "rotlin" in cfg.tables else "analytic stand-in (SURVEY 8d)"
+    if args.tables == "generated" and "rot3d" in cfg.tables:
+        mol = [t.name for t in s.types if t.molecule == 2][0]
+        A, B, C = pkg.configs.ROT_CONSTANTS[mol]
+        maxj = pkg.gpu.asym_auto_maxj(s.temperature, s.Q, A, B, C)
+        r3, e3, q3, _ = pkg.gpu.gen_asymrho(s.temperature, s.Q, -1, 0, 180, A, B, C, maxj)
+        cfg.tables["rot3d"] = tuple(x.reshape(-1) for x in (r3, e3, q3))
+        tables_note = f"generated on the device: asymrho {s.temperature} {s.Q} -1 0 180 {A} {B} {C} {maxj} ({pkg.gpu.gen_timing().sum():.1f} ms)"
     chains = args.chains or (8 if args.workload == "C5" else 148)
     G = pkg.gpu.PimcGpu(cfg, nchains=chains, chain_offset=rank * chains, device=local, ctas_per_chain=args.cpc,
                         threads_per_cta=args.threads, team=args.team)
@@ -313,7 +324,7 @@ def main():
             "metric": "pimc_bead_updates_per_sec", "value": value, "unit": "bead-updates/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_kernel / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args.workload, s, chains), "chains_per_gpu": chains, "step": "one MC pass = P iterations of the time loop",
+            "config": {"workload": workload_name(args.workload, s, chains), "rotor_tables": tables_note, "chains_per_gpu": chains, "step": "one MC pass = P iterations of the time loop",
                        "l2": "flushed (256 MB write) between timed passes; the state is L2/SMEM-resident by design inside a pass",
                        "parallelism": f"independent chains x{world} GPUs, NCCL all-reduce of accumulators per block",
                        "geometry": G.geometry()},

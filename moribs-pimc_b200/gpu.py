@@ -146,6 +146,17 @@ def gen_asymrho(T, nslice, iodevn, ith0, ith1, A, B, Cc, maxj):
     return r, e, q, info
 
 
+def asym_auto_maxj(T, nslice, A, B, Cc):
+    """first j whose lowest level falls under the generator's own cut (2j+1)/8pi^2 e^{-tau E} < 1e-16 (asymrho.f:520);
+    the rule pimc_b200 uses when it generates missing tables"""
+    tau = 1.0 / (0.6950356 * T) / nslice
+    cmin = min(A, B, Cc)
+    j = 4
+    while j < 876 and (2 * j + 1) / (8.0 * np.pi ** 2) * np.exp(-tau * cmin * j * (j + 1.0)) >= 1e-16:
+        j += 1
+    return j
+
+
 def gen_timing():
     ms = np.zeros(4)
     _ck(lib().pimcgpu_gen_timing(_dp(ms)))
