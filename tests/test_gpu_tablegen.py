@@ -291,22 +291,25 @@ def test_free_asymmetric_top_sampled_with_generated_tables_reproduces_exact_ener
     """End to end: tables generated on the device -> rotational moves + GetRotE3D on the device -> <E_rot> of ONE free
     water-like top equals the exact thermal energy sum_n (2J+1) E_n e^{-beta E_n} / Z that asymrho prints as 'AT BETA ...
     CLASSICAL' (asymrho.f:346-368; SURVEY 8c golden vector 3).  The Noya propagator is exact at every tau, so there is no
-    Trotter error for a free rotor and the only deviation is statistical."""
-    T, Q = 20.0, 16
+    Trotter error for a free rotor and the only deviation is statistical.  At 50 K the exact value (70.24 K) lies 6 % under
+    the classical 3/2 kT = 75 K, twenty standard errors of this run.  (Step 0.3: with the deck's 0.15 at 20 K / 16 slices the
+    ring of orientations changes its SO(3) homotopy class too rarely and the block means drift -- profiles/free_top_check.py.)"""
+    T, Q = 50.0, 8
     A, B, C = pkg.configs.ROT_CONSTANTS["H2O"]
     maxj = gpu.asym_auto_maxj(T, Q, A, B, C)
     r, e, q, info = gpu.gen_asymrho(T, Q, -1, 0, 180, A, B, C, maxj)
     exact = info[7] / 0.6950356                                   # K
-    assert 15.0 < exact < 40.0
-    cfg = pkg.configs.make_config("C4", P=16, Q=Q, big_tables=False, temperature=T)
+    assert 69.0 < exact < 71.0
+    cfg = pkg.configs.make_config("C4", P=64, Q=Q, big_tables=False, temperature=T)
     cfg.system.types[0].numb = 1
+    cfg.system.types[0].rtstep = 0.3
     cfg.coords, cfg.angles = pkg.configs.cluster_config(cfg.system, 3)
     cfg.tables["rot3d"] = (r.reshape(-1), e.reshape(-1), q.reshape(-1))
-    G = gpu.PimcGpu(cfg, nchains=64)
+    G = gpu.PimcGpu(cfg, nchains=148)
     G.seed((4242,) * 6)
     G.steps(400 * cfg.system.P)
     rows = []
-    for b in range(24):
+    for b in range(40):
         G.accum_reset()
         for k in range(250):
             G.steps(8, sync=False)
@@ -318,6 +321,6 @@ def test_free_asymmetric_top_sampled_with_generated_tables_reproduces_exact_ener
     G.close()
     rows = np.array(rows)
     mean, err = rows.mean(), rows.std(ddof=1) / np.sqrt(len(rows))
-    print(f"free top: <E_rot> = {mean:.4f} +- {err:.4f} K, exact {exact:.4f} K, maxj {maxj}, rotational acceptance {acc[0][2] / max(tot[0][2], 1):.3f}")
-    assert abs(mean - exact) < 2.5 * err + 1e-3 * exact
-    assert err < 0.02 * exact
+    print(f"free top: <E_rot> = {mean:.4f} +- {err:.4f} K, exact {exact:.4f} K, 3/2 kT = {1.5 * T} K, maxj {maxj}, rotational acceptance {acc[0][2] / max(tot[0][2], 1):.3f}")
+    assert abs(mean - exact) < 2.5 * err + 2e-3 * exact
+    assert err < 0.01 * exact and abs(mean - 1.5 * T) > 8 * err
