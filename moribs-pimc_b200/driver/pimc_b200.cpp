@@ -16,6 +16,7 @@
 // mc_qworm.cc) are honoured on the device; yw001.worm is written in the reference's layout for chain 0.  yw001.rand (SPRNG state) has no
 // counterpart: the MRG32k3a package seed and step counter are written to yw001.mrg instead.
 #include "../../include/pimcgpu.h"
+#include "pimc_writers.h"
 
 #include <cmath>
 #include <cstdio>
@@ -397,6 +398,13 @@ int main(int argc, char **argv)
    long n_acc = 0, off_gr1d = 0, off_gr2d = 0, off_gr3d = 0, off_rcf = 0, off_rel = 0;
    ck(pimcgpu_accum_layout(&n_acc, nullptr, &off_gr1d, &off_gr2d, &off_gr3d, &off_rcf, &off_rel), "pimcgpu_accum_layout");
    vector<double> acc(n_acc), gr1d_sum(PIMCGPU_BINSR, 0.0), rcf_sum(max(1, Q), 0.0);
+   // _gr2D_sum, _gr3D_sum, _relthe_sum/_relphi_sum/_relchi_sum (mc_estim.cc:40-49): accumulated over the blocks by the host
+   vector<double> gr2d_sum((size_t)PIMCGPU_BINSR * PIMCGPU_BINST, 0.0), rel_sum(PIMCGPU_BINST + 2 * PIMCGPU_BINSC, 0.0);
+   vector<double> gr3d_sum(off_gr3d >= 0 ? (size_t)PIMCGPU_BINSR * PIMCGPU_BINST * PIMCGPU_BINSC : 0, 0.0);
+   DensityWriters dw;
+   dw.P = P; dw.Q = Q; dw.ntypes = sys.ntypes; dw.imtype = imtype;
+   for (int t = 0; t < sys.ntypes; t++) { dw.numb[t] = d.types[t].numb; dw.molecule[t] = d.types[t].molecule; if (!d.types[t].molecule) dw.atype = t; }
+   dw.volume = sys.box[0] * sys.box[1] * sys.box[2];
    const string fname = d.outdir + d.prefix;
    const double beta = 1.0 / d.temperature, rottau = Q ? beta / Q : 0.0;
    double kin_tot = 0, pot_tot = 0, rot_tot = 0, rotsq_tot = 0, cv_tot = 0, cvt_tot = 0, cvr_tot = 0, total_count = 0, sums = 0;
@@ -501,6 +509,19 @@ int main(int argc, char **argv)
             for (int ir = 0; ir < PIMCGPU_BINSR; ir++)
                fg << setw(IO_WIDTH) << (ir + 0.5) * dr << BLANK << setw(IO_WIDTH) << gr1d_sum[ir] / (norma * (na * (na - 1)) / 2.0) << BLANK << endl;
          }
+      }
+      if (block > d.eq_blocks && sc.count > 0 && imtype >= 0) {
+         // density part of MCSaveBlockAverages (mc_main.cc:715-737) and the accumulated densities (:451-461)
+         const double ac = sc.count, tc = total_count;
+         ostringstream bc; bc << setw(3) << setfill('0') << block;
+         const string bname = fname + bc.str();
+         const double *g1 = &acc[off_gr1d], *g2 = &acc[off_gr2d], *g3 = off_gr3d >= 0 ? &acc[off_gr3d] : nullptr;
+         for (size_t i = 0; i < gr2d_sum.size(); i++) gr2d_sum[i] += g2[i];
+         for (size_t i = 0; i < gr3d_sum.size(); i++) gr3d_sum[i] += g3[i];
+         for (size_t i = 0; i < rel_sum.size(); i++) rel_sum[i] += acc[off_rel + i];
+         // the reference rewrites the 180 MB <prefix>_sum.g3d after every block (mc_main.cc:458); PIMC_G3D_LAST_ONLY=1 defers it
+         const bool g3d_now = block == start_block + d.blocks || !getenv("PIMC_G3D_LAST_ONLY");
+         dw.block_and_total(fname, bname, ac, tc, g1, g2, g3, &acc[off_rel], gr2d_sum.data(), gr3d_sum.empty() ? nullptr : gr3d_sum.data(), rel_sum.data(), g3d_now);
       }
       if (block > d.eq_blocks && sc.count > 0 && bstype >= 0) {
          const double ac = sc.count, bmass = d.types[bstype].mass;

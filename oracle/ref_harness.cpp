@@ -262,6 +262,38 @@ void ref_zero_relbins(void)
    for (int i = 0; i < 50; i++) _relthe_sum[i] = 0;
    for (int i = 0; i < 100; i++) { _relphi_sum[i] = 0; _relchi_sum[i] = 0; }
 }
+// The reference's own density writers (mc_estim.cc:1327-1820,1930-1995) on test-supplied histograms: block and accumulated
+// arrays are both set to the given counts; files appear under `prefix` exactly as MCSaveBlockAverages / main write them.
+extern double **_gr1D_sum;
+extern double ***_gr2D_sum;
+extern double **_gr3D_sum;
+void ref_save_densities(const char *prefix, double acount, const double *gr1d, const double *gr2d, const double *gr3d, const double *rel)
+{
+   for (int id = 0; id < NumbTypes; id++) {
+      if (MCAtom[id].molecule) continue;
+      for (int i = 0; i < 300; i++) { _gr1D[id][i] = gr1d[i]; _gr1D_sum[id][i] = gr1d[i]; }
+   }
+   if (IMPURITY && MCAtom[IMTYPE].molecule == 1)
+      for (int i = 0; i < 300; i++) for (int j = 0; j < 50; j++) { _gr2D[0][i][j] = gr2d[i * 50 + j]; _gr2D_sum[0][i][j] = gr2d[i * 50 + j]; }
+   if (IMPURITY && MCAtom[IMTYPE].molecule == 2) {
+      for (int id = 0; id < NumbTypes; id++)
+         for (long i = 0; i < 300L * 50 * 100; i++) { double v = (MCAtom[id].molecule == 0) ? gr3d[i] : 0.0; _gr3D[id][i] = v; _gr3D_sum[id][i] = v; }
+      for (int i = 0; i < 50; i++) _relthe_sum[i] = rel[i];
+      for (int i = 0; i < 100; i++) { _relphi_sum[i] = rel[50 + i]; _relchi_sum[i] = rel[150 + i]; }
+   }
+   if (IMPURITY && MCAtom[IMTYPE].molecule == 1) {          // mc_main.cc:718-724, 453-454
+      SaveDensities1D(prefix, acount);
+      SaveDensities2D(prefix, acount, MC_BLOCK);
+      SaveDensities2D(prefix, acount, MC_TOTAL);
+   }
+   if (IMPURITY && MCAtom[IMTYPE].molecule == 2) {          // mc_main.cc:726-737, 456-461
+      SaveDensities1D(prefix, acount);
+      SaveRho1D(prefix, acount, MC_BLOCK);
+      SaveRhoThetaChi(prefix, acount, MC_BLOCK);
+      SaveDensities3D(prefix, acount, MC_TOTAL);
+      SaveRho1D(prefix, acount, MC_TOTAL);
+   }
+}
 void ref_GetAreaEstimators(double *areas, double *area2, double *inert)
 {
    GetAreaEstimators();

@@ -1,0 +1,100 @@
+"""CPU test of the driver's density writers (moribs-pimc_b200/driver/pimc_writers.h) against the reference's OWN
+Save* functions (SaveDensities1D, SaveDensities2D, SaveRho1D, SaveRhoThetaChi, SaveDensities3D; mc_estim.cc:1327-1820,
+1930-1995) driven through oracle/_ref on the same seeded histograms: every output file must be byte-identical.
+Where oracle/_ref is absent the files are checked against the digests committed in tests/golden/writers.json
+(made by this test when run with MAKE_WRITER_FIXTURE=1 next to the reference)."""
+import hashlib
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FIXTURE = os.path.join(ROOT, "tests", "golden", "writers.json")
+CASES = {"C5": dict(P=32, Q=8, nsolv=6), "C1": dict(P=64, Q=16), "C4": dict(P=64, Q=32)}
+
+SCRIPT = r'''
+import sys, os, json, hashlib, ctypes as C, subprocess
+import numpy as np
+sys.path.insert(0, %(root)r)
+name, work, use_ref = %(name)r, %(work)r, %(use_ref)r
+import __graft_entry__ as ge
+pkg = ge.load_package()
+cfg = pkg.configs.make_config(name, big_tables=(name not in ("C1", "C4")), **%(kw)r)
+if name == "C1":                                  # tables are irrelevant for the writers; keep the process small
+    cfg.tables["pot3d"] = (3, 181, 181, 4.0, 20.0, np.zeros(3 * 181 * 181))
+if name in ("C1", "C4"):
+    z = np.zeros(181 * 361 * 361)
+    cfg.tables["rot3d"] = (z, z, z)
+s = cfg.system
+rng = np.random.default_rng(11)
+g1 = rng.integers(0, 500, 300).astype(float)
+g2 = rng.integers(0, 60, 300 * 50).astype(float)
+g3 = rng.integers(0, 7, 300 * 50 * 100).astype(float)
+rel = rng.integers(0, 900, 250).astype(float)
+acount = 1234.0
+dp = C.POINTER(C.c_double)
+P_ = lambda a: a.ctypes.data_as(dp)
+os.makedirs(work + "/mine", exist_ok=True); os.makedirs(work + "/ref", exist_ok=True)
+shim = C.CDLL(%(shim)r)
+numb = np.array([t.numb for t in s.types], dtype=np.int32); mol = np.array([t.molecule for t in s.types], dtype=np.int32)
+box = (s.N / s.density) ** (1.0 / 3.0)
+shim.shim_save_densities((work + "/mine/gr").encode(), C.c_int(s.P), C.c_int(s.Q), C.c_int(len(s.types)), numb.ctypes.data_as(C.POINTER(C.c_int)),
+                         mol.ctypes.data_as(C.POINTER(C.c_int)), C.c_double(box ** 3), C.c_double(acount), P_(g1), P_(g2), P_(g3), P_(rel))
+out = {}
+if use_ref:
+    from oracle import oracle_py as op
+    R = op.Ref(cfg)
+    R.lib.ref_save_densities((work + "/ref/gr").encode(), C.c_double(acount), P_(g1), P_(g2), P_(g3), P_(rel))
+    for f in sorted(os.listdir(work + "/ref")):
+        a = open(work + "/ref/" + f, "rb").read()
+        b = open(work + "/mine/" + f, "rb").read() if os.path.exists(work + "/mine/" + f) else b""
+        out[f] = {"identical": a == b, "bytes": len(a), "md5": hashlib.md5(a).hexdigest()}
+    out["_only_mine"] = sorted(set(os.listdir(work + "/mine")) - set(os.listdir(work + "/ref")))
+else:
+    for f in sorted(os.listdir(work + "/mine")):
+        a = open(work + "/mine/" + f, "rb").read()
+        out[f] = {"bytes": len(a), "md5": hashlib.md5(a).hexdigest()}
+print("RESULT " + json.dumps(out))
+'''
+
+
+@pytest.fixture(scope="module")
+def shim(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("shim") / "libwshim.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so, os.path.join(ROOT, "tests", "writers_shim.cpp")])
+    return so
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_density_writers_byte_identical_to_reference(name, shim, tmp_path):
+    use_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libpimcref.so"))
+    code = SCRIPT % dict(root=ROOT, name=name, work=str(tmp_path), use_ref=use_ref, kw=CASES[name], shim=shim)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    line = [l for l in out.stdout.splitlines() if l.startswith("RESULT ")]
+    assert line, out.stdout[-2000:] + out.stderr[-2000:]
+    res = json.loads(line[-1][7:])
+    expect = {"C5": {"gr.gra", "gr.gri", "gr.grt", "gr.g2d", "gr_sum.g2d"},
+              "C1": {"gr.gra", "gr.gri", "gr.grt", "gr.grc", "gr.gtc", "gr_sum.g3d", "gr_sum.gri", "gr_sum.grt", "gr_sum.grc", "gr_sum.eulphi", "gr_sum.eulchi", "gr_sum.eulthe"}}
+    expect["C4"] = expect["C1"]
+    fixture = json.load(open(FIXTURE)) if os.path.exists(FIXTURE) else {}
+    if use_ref:
+        assert res.pop("_only_mine") == []
+        assert set(res) == expect[name]
+        for f, r in res.items():
+            assert r["identical"], f"{name}: {f} differs from the reference's writer"
+            assert r["bytes"] > 1000
+        if os.environ.get("MAKE_WRITER_FIXTURE"):
+            fixture[name] = {f: {"bytes": r["bytes"], "md5": r["md5"]} for f, r in res.items()}
+            json.dump(fixture, open(FIXTURE, "w"), indent=1, sort_keys=True)
+        elif name in fixture:
+            assert {f: r["md5"] for f, r in res.items()} == {f: r["md5"] for f, r in fixture[name].items()}
+    else:
+        if name not in fixture:
+            pytest.skip("neither oracle/_ref nor the digest fixture is available")
+        assert set(res) == set(fixture[name])
+        for f, r in res.items():
+            assert r["md5"] == fixture[name][f]["md5"], f"{name}: {f} differs from the reference's writer (digest)"
