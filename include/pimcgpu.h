@@ -144,7 +144,9 @@ void  *pimcgpu_stream(void);                       /* cudaStream_t the library l
  *   "scalars" "gr1d" "gr2d" "gr3d" "rcf" "relbins"  as in pimcgpu_accum_layout
  *   "area"   40 doubles: _areas[PERP,PARL] _area2[2] _inert[2] (GetAreaEstimators, mc_estim.cc:2087-2250), then
  *            _areas3DSFF[6] _inert3DSFF[9] _areas3DMFF[6] _inert3DMFF[9] (GetAreaEstim3D, :2252-2594)
- *   "ploops" one double per boson: _ploops (GetExchangeLength, :1997-2019)                       */
+ *   "ploops" one double per boson: _ploops (GetExchangeLength, :1997-2019)
+ *   "rcfcnt" Q doubles: rows 1..9 of the block array _rcf, i.e. the number of time origins with n(0).n(t) < PLONE
+ *            (GetRCF, :1127-1137; the Legendre call is commented out, so every row holds this count)      */
 long   pimcgpu_accum_offset(const char *name);
 
 /* ---- symmetry operations of MCGetAverage (mc_main.cc:647-692): Reflect_MF_XZ/YZ/XY (mc_piqmc.cc:1385-1708) and

@@ -22,12 +22,12 @@ constexpr double MAX_RADIUS = 15.0, MIN_RADIUS = 0.0;        // mc_estim.cc:29-3
 struct EstBuffers {
    double *partials;      // [c][EST_BLOCKS][NPART]
    double *chain_e;       // [c][8]: skin, spot, srot, ErotSQ, Erot_termSQ
-   double *chain_rcf;     // [c][Q]
+   double *chain_rcf;     // [c][2][Q]: sum_it0 n(it0).n(it0+itc), then the number of it0 with n.n < PLONE (rows 1..9 of _rcf)
    double *acc;           // accumulator buffer
    double *com;           // [c][P][3] total centre of mass per slice (space-fixed-frame area estimator)
    double *area_partials; // [c][EST_BLOCKS][NAREA]
    double *chain_area;    // [c][NAREA]
-   long off_gr1d, off_gr2d, off_gr3d, off_rcf, off_relbins, off_area, off_ploops;
+   long off_gr1d, off_gr2d, off_gr3d, off_rcf, off_relbins, off_area, off_ploops, off_rcfcnt;
    int has_gr3d;
    const int *pairs;      // [npairs][2]
    int npairs;
@@ -391,15 +391,19 @@ __global__ void est_rcf_kernel(const __grid_constant__ Params p, const __grid_co
    const int c = blockIdx.y, Q = p.Q;
    const int itc = blockIdx.x * blockDim.x + threadIdx.x;
    if (itc >= Q) return;
-   double s = 0.0;
+   double s = 0.0, below = 0.0;
    for (int it0 = 0; it0 < Q; it0++) {
       int tc = (it0 + itc) % Q;
       double p0 = 0.0;
       #pragma unroll
       for (int d = 0; d < 3; d++) p0 += p.cosn[ang_index(p, c, it0, d, 0)] * p.cosn[ang_index(p, c, tc, d, 0)];
       s += p0;
+      // rows 1..9 of the BLOCK array: `if (p0<PLONE)` governs `_rcf[in][itc] += pleg` with pleg = 1 since the Legendre call is
+      // commented out (mc_estim.cc:1127-1137, PLONE = 0.9999999 mc_confg.h:64); _rcf_sum[in] gets 1 unconditionally
+      if (p0 < 0.9999999) below += 1.0;
    }
-   e.chain_rcf[(size_t)c * Q + itc] = s;
+   e.chain_rcf[(size_t)c * 2 * Q + itc] = s;
+   e.chain_rcf[(size_t)c * 2 * Q + Q + itc] = below;
 }
 
 // per-chain totals, Cv algebra (mc_main.cc:589-616), accumulation in chain order
@@ -468,10 +472,11 @@ __global__ void est_finalize_kernel(const __grid_constant__ Params p, const __gr
    }
    if (accumulate && Q > 0)
       for (int itc = tid; itc < Q; itc += gridDim.x * blockDim.x) {
-         double s = 0.0;
+         double s = 0.0, b = 0.0;
          for (int c = 0; c < p.nchains; c++)
-            if (!(p.worm_on && p.wstate[(size_t)c * 8])) s += e.chain_rcf[(size_t)c * Q + itc];
+            if (!(p.worm_on && p.wstate[(size_t)c * 8])) { s += e.chain_rcf[(size_t)c * 2 * Q + itc]; b += e.chain_rcf[(size_t)c * 2 * Q + Q + itc]; }
          e.acc[e.off_rcf + itc] += s;
+         e.acc[e.off_rcfcnt + itc] += b;
       }
 }
 

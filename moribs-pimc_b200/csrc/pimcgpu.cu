@@ -532,10 +532,11 @@ int pimcgpu_init(const pimcgpu_system *sys, const pimcgpu_tables *tab)
    e.has_gr3d = (need3d || needsph) ? 1 : 0;
    e.off_gr1d = 32; e.off_gr2d = e.off_gr1d + BINSR; e.off_rcf = e.off_gr2d + (long)BINSR * BINST;
    e.off_relbins = e.off_rcf + std::max(1, p.Q); e.off_area = e.off_relbins + BINST + 2 * BINSC;
-   e.off_ploops = e.off_area + NAREA_ACC; e.off_gr3d = e.off_ploops + std::max(1, p.bstype >= 0 ? p.numb[p.bstype] : 1);
+   e.off_ploops = e.off_area + NAREA_ACC; e.off_rcfcnt = e.off_ploops + std::max(1, p.bstype >= 0 ? p.numb[p.bstype] : 1);
+   e.off_gr3d = e.off_rcfcnt + std::max(1, p.Q);
    G.nacc = e.off_gr3d + (e.has_gr3d ? (long)BINSR * BINST * BINSC : 0);
    if (dalloc(&e.com, C * p.P * 3) || dalloc(&e.area_partials, C * EST_BLOCKS * NAREA) || dalloc(&e.chain_area, C * NAREA) || dalloc(&G.d_ops, C * 4)) return 1;
-   if (dalloc(&e.acc, G.nacc) || dalloc(&e.partials, C * EST_BLOCKS * NPART) || dalloc(&e.chain_e, C * 8) || dalloc(&e.chain_rcf, C * std::max(1, p.Q))) return 1;
+   if (dalloc(&e.acc, G.nacc) || dalloc(&e.partials, C * EST_BLOCKS * NPART) || dalloc(&e.chain_e, C * 8) || dalloc(&e.chain_rcf, C * 2 * std::max(1, p.Q))) return 1;
    CK(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
    CK(cudaDeviceSynchronize());
    G.live = true;
@@ -914,6 +915,7 @@ long pimcgpu_accum_offset(const char *name)
    if (n == "relbins") return G.e.off_relbins;
    if (n == "area") return G.e.off_area;
    if (n == "ploops") return G.e.off_ploops;
+   if (n == "rcfcnt") return G.e.off_rcfcnt;
    return -1;
 }
 
@@ -933,7 +935,7 @@ int pimcgpu_chain_rcf(int chain, double *rcf0)
    if (chain < 0 || chain >= G.p.nchains || G.p.Q <= 0) return fail("pimcgpu_chain_rcf: bad chain or no rotation");
    if (launch_estimators(0, 0)) return 1;
    CK(cudaStreamSynchronize(G.stream));
-   CK(cudaMemcpy(rcf0, G.e.chain_rcf + (size_t)chain * G.p.Q, G.p.Q * sizeof(double), cudaMemcpyDeviceToHost));
+   CK(cudaMemcpy(rcf0, G.e.chain_rcf + (size_t)chain * 2 * G.p.Q, G.p.Q * sizeof(double), cudaMemcpyDeviceToHost));
    return 0;
 }
 

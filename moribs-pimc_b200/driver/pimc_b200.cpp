@@ -397,7 +397,7 @@ int main(int argc, char **argv)
 
    long n_acc = 0, off_gr1d = 0, off_gr2d = 0, off_gr3d = 0, off_rcf = 0, off_rel = 0;
    ck(pimcgpu_accum_layout(&n_acc, nullptr, &off_gr1d, &off_gr2d, &off_gr3d, &off_rcf, &off_rel), "pimcgpu_accum_layout");
-   vector<double> acc(n_acc), gr1d_sum(PIMCGPU_BINSR, 0.0), rcf_sum(max(1, Q), 0.0);
+   vector<double> acc(n_acc), gr1d_sum(PIMCGPU_BINSR, 0.0), rcf_sum(max(1, Q), 0.0), rcf_rows_sum(max(1, Q), 0.0);
    // _gr2D_sum, _gr3D_sum, _relthe_sum/_relphi_sum/_relchi_sum (mc_estim.cc:40-49): accumulated over the blocks by the host
    vector<double> gr2d_sum((size_t)PIMCGPU_BINSR * PIMCGPU_BINST, 0.0), rel_sum(PIMCGPU_BINST + 2 * PIMCGPU_BINSC, 0.0);
    vector<double> gr3d_sum(off_gr3d >= 0 ? (size_t)PIMCGPU_BINSR * PIMCGPU_BINST * PIMCGPU_BINSC : 0, 0.0);
@@ -408,8 +408,8 @@ int main(int argc, char **argv)
    const string fname = d.outdir + d.prefix;
    const double beta = 1.0 / d.temperature, rottau = Q ? beta / Q : 0.0;
    double kin_tot = 0, pot_tot = 0, rot_tot = 0, rotsq_tot = 0, cv_tot = 0, cvt_tot = 0, cvr_tot = 0, total_count = 0, sums = 0;
-   ofstream fsum;
-   if (rank == 0) { fsum.open(fname + "_sum.eng"); Writer::setout(fsum); }
+   FILE *fsum = nullptr;
+   if (rank == 0) fsum = fopen((fname + "_sum.eng").c_str(), "w");
    auto t_start = chrono::steady_clock::now();
    double bead_updates = 0;
 
@@ -465,50 +465,24 @@ int main(int argc, char **argv)
       }
       if (block > d.eq_blocks && sc.count > 0) {
          const double ac = sc.count;
-         // SaveEnergy, mc_main.cc:764-795
-         ofstream fe(fname + ".eng", ios::app);
-         Writer::setout(fe);
-         fe << setw(IO_WIDTH_BLOCK) << block << BLANK << setw(IO_WIDTH) << sc.kin / ac << BLANK << setw(IO_WIDTH) << sc.pot / ac << BLANK
-            << setw(IO_WIDTH) << (sc.kin + sc.pot) / ac << BLANK << setw(IO_WIDTH) << sc.rot / ac << BLANK << setw(IO_WIDTH) << sc.rotsq / ac << BLANK
-            << setw(IO_WIDTH) << (sc.kin + sc.pot + sc.rot) / ac << BLANK << setw(IO_WIDTH) << sc.cv / ac << BLANK << setw(IO_WIDTH) << sc.cv_trans / ac << BLANK
-            << setw(IO_WIDTH) << sc.cv_rot / ac << BLANK << endl;
-         // SaveSumEnergy, mc_main.cc:797-836 (written once per block here)
+         BlockWriters::energy(fname, block, ac, sc.kin, sc.pot, sc.rot, sc.rotsq, sc.cv, sc.cv_trans, sc.cv_rot);                 // SaveEnergy
+         // SaveSumEnergy, mc_main.cc:797-836 (the reference appends a row every MCSKIP_TOTAL passes; here once per block)
          kin_tot += sc.kin; pot_tot += sc.pot; rot_tot += sc.rot; rotsq_tot += sc.rotsq; cv_tot += sc.cv; cvt_tot += sc.cv_trans; cvr_tot += sc.cv_rot;
          total_count += ac; sums += 1.0;
-         const double tc = total_count, T = d.temperature;
-         double Cv = 0.5 * (double)(3 * N * P * T) - (kin_tot + pot_tot + rot_tot) / tc;
-         Cv = -(Cv * Cv + cv_tot / tc) * beta / T;
-         double Cvt = 0.5 * (double)(3 * N * P * T) - kin_tot / tc;
-         Cvt = -(Cvt * Cvt + cvt_tot / tc) * beta / T;
-         double Cvr = -rot_tot / tc;
-         Cvr = -(Cvr * Cvr + cvr_tot / tc) * beta / T;
-         fsum << setw(IO_WIDTH_BLOCK) << sums << BLANK << setw(IO_WIDTH) << kin_tot / tc << BLANK << setw(IO_WIDTH) << pot_tot / tc << BLANK
-              << setw(IO_WIDTH) << (kin_tot + pot_tot) / tc << BLANK << setw(IO_WIDTH) << rot_tot / tc << BLANK << setw(IO_WIDTH) << rotsq_tot / tc << BLANK
-              << setw(IO_WIDTH) << (kin_tot + pot_tot + rot_tot) / tc << BLANK << setw(IO_WIDTH) << Cv << BLANK << setw(IO_WIDTH) << Cvt << BLANK
-              << setw(IO_WIDTH) << Cvr << BLANK << endl;
-         // SaveRCF (block and accumulated), mc_estim.cc:1141-1191
-         if (Q) {
-            for (int it = 0; it < Q; it++) rcf_sum[it] += acc[off_rcf + it];
-            for (int mode = 0; mode < 2; mode++) {
-               ostringstream bc; bc << setw(3) << setfill('0') << block;
-               ofstream fr(mode == 0 ? fname + bc.str() + ".rcf" : fname + "_sum.rcf");
-               Writer::setout(fr);
-               const double norm = (mode == 0 ? ac : tc) * (double)Q;
-               for (int it = 0; it <= Q; it++)
-                  fr << setw(IO_WIDTH) << (double)it * rottau << BLANK << setw(IO_WIDTH) << (mode == 0 ? acc[off_rcf + it % Q] : rcf_sum[it % Q]) / norm << BLANK << endl;
-            }
+         const double tc = total_count;
+         BlockWriters::sum_energy(fsum, sums, tc, kin_tot, pot_tot, rot_tot, rotsq_tot, cv_tot, cvt_tot, cvr_tot, N, P, d.temperature);
+         if (Q) {   // SaveRCF, block and accumulated (mc_main.cc:739-740, 463-464)
+            const long orc = pimcgpu_accum_offset("rcfcnt");
+            for (int it = 0; it < Q; it++) { rcf_sum[it] += acc[off_rcf + it]; rcf_rows_sum[it] += (double)Q * ac; }   // _rcf_sum[1..9] += 1 per time origin
+            ostringstream bc; bc << setw(3) << setfill('0') << block;
+            BlockWriters::rcf(fname + bc.str(), Q, rottau, ac, &acc[off_rcf], &acc[orc]);
+            BlockWriters::rcf(fname + "_sum", Q, rottau, tc, rcf_sum.data(), rcf_rows_sum.data());
          }
          // SaveGraSum, mc_estim.cc:1288-1326
-         int na = 0;
-         for (auto &t : d.types) if (!t.molecule) na = t.numb;
-         if (na > 1) {
-            for (int ir = 0; ir < PIMCGPU_BINSR; ir++) gr1d_sum[ir] += acc[off_gr1d + ir];
-            ofstream fg(fname + "_sum.gra");
-            Writer::setout(fg);
-            const double dr = 15.0 / PIMCGPU_BINSR, norma = dr * tc * (double)P;
-            for (int ir = 0; ir < PIMCGPU_BINSR; ir++)
-               fg << setw(IO_WIDTH) << (ir + 0.5) * dr << BLANK << setw(IO_WIDTH) << gr1d_sum[ir] / (norma * (na * (na - 1)) / 2.0) << BLANK << endl;
-         }
+         int na = 0, natypes = 0;
+         for (auto &t : d.types) if (!t.molecule) { na = t.numb; natypes = 1; }
+         for (int ir = 0; ir < PIMCGPU_BINSR; ir++) gr1d_sum[ir] += acc[off_gr1d + ir];
+         BlockWriters::gra_sum(fname, tc, P, natypes, na, gr1d_sum.data());
       }
       if (block > d.eq_blocks && sc.count > 0 && imtype >= 0) {
          // density part of MCSaveBlockAverages (mc_main.cc:715-737) and the accumulated densities (:451-461)
@@ -529,42 +503,12 @@ int main(int argc, char **argv)
          const long oa = pimcgpu_accum_offset("area"), op = pimcgpu_accum_offset("ploops");
          const int nb = d.types[bstype].numb;
          ck(pimcgpu_download_state(0, nullptr, nullptr, nullptr, pindex.data()), "pimcgpu_download_state");
-         {  // SaveExchangeLength, mc_estim.cc:2021-2085 (GSLOOP_MAX = 7, mc_confg.h:67); the permutation row is chain 0's
-            ofstream f(fname + ".prl", ios::app);
-            Writer::setout(f);
-            f << setw(IO_WIDTH_BLOCK) << block << BLANK;
-            double excited = 0.0, ground = 0.0;
-            for (int cl = 0; cl < nb; cl++) {
-               double norm = (double)(cl + 1) / (ac * (double)nb);
-               if (cl <= 7) excited += acc[op + cl] * norm; else ground += acc[op + cl] * norm;
-            }
-            f << setw(IO_WIDTH) << ground << BLANK << setw(IO_WIDTH) << excited << BLANK << setw(IO_WIDTH) << (ground + excited) << BLANK;
-            for (int cl = 0; cl < nb; cl++) f << setw(IO_WIDTH) << acc[op + cl] * (double)(cl + 1) / (ac * (double)nb) << BLANK;
-            f << endl;
-            for (int a = 0; a < nb; a++) f << setw(IO_WIDTH) << pindex[a] << BLANK;
-            f << 0 << endl;
-         }
-         if (imtype >= 0 && d.types[imtype].molecule == 1) {
-            // SaveAreaEstimators, mc_estim.cc:2596-2640: columns rho_s perp/parl, I_cl perp/parl, normalised areas
-            const double *A = &acc[oa];
-            const double norm = 2.0 / (beta * lambda);
-            ofstream f(fname + ".sup", ios::app);
-            Writer::setout(f);
-            f << setw(IO_WIDTH_BLOCK) << block << BLANK << setw(IO_WIDTH) << A[2] * norm / A[4] << BLANK << setw(IO_WIDTH) << A[3] * norm / A[5] << BLANK
-              << setw(IO_WIDTH) << A[4] * bmass / ac << BLANK << setw(IO_WIDTH) << A[5] * bmass / ac << BLANK
-              << setw(IO_WIDTH) << A[0] * sqrt(norm / A[4]) / ac << BLANK << setw(IO_WIDTH) << A[1] * sqrt(norm / A[5]) / ac << BLANK << endl;
-         }
+         BlockWriters::exchange_length(fname, block, ac, nb, &acc[op], pindex.data());      // the permutation row is chain 0's
+         if (imtype >= 0 && d.types[imtype].molecule == 1) BlockWriters::area_estimators(fname, block, ac, &acc[oa], beta, lambda, bmass);
          for (int iframe = 0; iframe < 2; iframe++) {
-            // SaveAreaEstim3D, mc_estim.cc:2667-2729: 9 components of the classical inertia, 6 of 4m^2/(hbar^2 beta) <A_i A_j>
             if (iframe == 1 && !(imtype >= 0 && d.types[imtype].molecule == 2 && d.ispher == 0)) break;
-            const double *A = &acc[oa + 6 + 15 * iframe], *I = A + 6;
-            const double norm = 2.0 * bmass / (beta * lambda);
-            ofstream f(fname + (iframe ? ".mffs3d" : ".sffs3d"), ios::app);
-            Writer::setout(f);
-            f << setw(IO_WIDTH_BLOCK) << block << BLANK;
-            for (int k = 0; k < 9; k++) f << setw(IO_WIDTH) << I[k] / ac << BLANK;
-            for (int k = 0; k < 6; k++) f << setw(IO_WIDTH) << A[k] * norm / ac << BLANK;
-            f << endl;
+            const double *A = &acc[oa + 6 + 15 * iframe];
+            BlockWriters::area_estim3d(fname, block, ac, A, A + 6, iframe, beta, lambda, bmass);
          }
       }
       // checkpoint, mc_main.cc:471-483: yw001.stat / .conf / .tabl in the reference's byte layout, chain 0

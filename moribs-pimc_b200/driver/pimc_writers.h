@@ -191,4 +191,113 @@ struct DensityWriters {
    }
 };
 
+// The per-block scalar writers of mc_main.cc:764-836 and mc_estim.cc:1141-1191,1288-1326,2021-2085,2596-2729.
+struct BlockWriters {
+   static void num(FILE *f, double v) { fprintf(f, "%14.6e   ", v); }
+   // SaveEnergy, mc_main.cc:764-795: appends one row to <prefix>.eng
+   static void energy(const string &fname, long block, double ac, double kin, double pot, double rot, double rotsq, double cv, double cvt, double cvr)
+   {
+      FILE *f = fopen((fname + ".eng").c_str(), "a");
+      if (!f) return;
+      fprintf(f, "%4ld   ", block);
+      num(f, kin / ac); num(f, pot / ac); num(f, (kin + pot) / ac); num(f, rot / ac); num(f, rotsq / ac); num(f, (kin + pot + rot) / ac);
+      num(f, cv / ac); num(f, cvt / ac); num(f, cvr / ac);
+      fputc('\n', f);
+      fclose(f);
+   }
+   // SaveSumEnergy, mc_main.cc:797-836: one row of the accumulated averages on the open <prefix>_sum.eng
+   static void sum_energy(FILE *f, double numb, double acount, double kin, double pot, double rot, double rotsq, double cv, double cvt, double cvr,
+                          int natoms, int P, double T)
+   {
+      const double beta = 1.0 / T;
+      fprintf(f, "%4.6e   ", numb);
+      num(f, kin / acount); num(f, pot / acount); num(f, (kin + pot) / acount); num(f, rot / acount); num(f, rotsq / acount); num(f, (kin + pot + rot) / acount);
+      double Cv = 0.5 * (double)(3 * natoms * P * T) - (kin + pot + rot) / acount;
+      Cv = Cv * Cv + cv / acount;
+      Cv = -Cv * beta / T;
+      num(f, Cv);
+      double Cvt = 0.5 * (double)(3 * natoms * P * T) - kin / acount;
+      Cvt = Cvt * Cvt + cvt / acount;
+      Cvt = -Cvt * beta / T;
+      num(f, Cvt);
+      double Cvr = -rot / acount;
+      Cvr = Cvr * Cvr + cvr / acount;
+      Cvr = -Cvr * beta / T;
+      num(f, Cvr);
+      fputc('\n', f);
+      fflush(f);
+   }
+   // SaveRCF, mc_estim.cc:1141-1191: <n(0).n(t)>, two blank lines, a comment line, then the nine Legendre rows (all equal: rows1to9)
+   static void rcf(const string &name, int Q, double rottau, double acount, const double *row0, const double *rows1to9)
+   {
+      FILE *f = fopen((name + ".rcf").c_str(), "w");
+      if (!f) return;
+      const double norm = acount * (double)Q;
+      for (int it = 0; it <= Q; it++) { num(f, (double)it * rottau); num(f, row0[it % Q] / norm); fputc('\n', f); }
+      fputs("\n\n#\n", f);
+      for (int it = 0; it <= Q; it++) {
+         num(f, (double)it * rottau);
+         for (int ip = 1; ip < 10; ip++) num(f, rows1to9[it % Q] / norm);
+         fputc('\n', f);
+      }
+      fclose(f);
+   }
+   // SaveGraSum, mc_estim.cc:1288-1326
+   static void gra_sum(const string &fname, double tc, int P, int natomtypes, int numb, const double *gr1d_sum)
+   {
+      FILE *f = fopen((fname + "_sum.gra").c_str(), "w");
+      if (!f) return;
+      const double dr = 15.0 / PIMCGPU_BINSR, norma = dr * tc * (double)P;
+      for (int ir = 0; ir < PIMCGPU_BINSR; ir++) {
+         num(f, ir * dr + 0.5 * dr);
+         for (int id = 0; id < natomtypes; id++) num(f, gr1d_sum[ir] / (norma * (numb * (numb - 1)) / 2.0));
+         fputc('\n', f);
+      }
+      fclose(f);
+   }
+   // SaveExchangeLength, mc_estim.cc:2021-2085 (GSLOOP_MAX = 7, mc_confg.h:67; PrintXYZprl = 0)
+   static void exchange_length(const string &fname, long block, double ac, int nb, const double *ploops, const int *pindex)
+   {
+      FILE *f = fopen((fname + ".prl").c_str(), "a");
+      if (!f) return;
+      fprintf(f, "%4ld   ", block);
+      double excited = 0.0, ground = 0.0;
+      for (int cl = 0; cl < nb; cl++) {
+         const double norm = (double)(cl + 1) / (ac * (double)nb);
+         if (cl <= 7) excited += (ploops[cl] * norm); else ground += (ploops[cl] * norm);
+      }
+      num(f, ground); num(f, excited); num(f, ground + excited);
+      for (int cl = 0; cl < nb; cl++) num(f, ploops[cl] * ((double)(cl + 1) / (ac * (double)nb)));
+      fputc('\n', f);
+      for (int a = 0; a < nb; a++) fprintf(f, "%14d   ", pindex[a]);
+      fputs("0\n", f);
+      fclose(f);
+   }
+   // SaveAreaEstimators, mc_estim.cc:2596-2640: A = _areas[2] _area2[2] _inert[2]
+   static void area_estimators(const string &fname, long block, double ac, const double *A, double beta, double lambda, double mass)
+   {
+      FILE *f = fopen((fname + ".sup").c_str(), "a");
+      if (!f) return;
+      const double norm = 2.0 / (beta * lambda);
+      fprintf(f, "%4ld   ", block);
+      num(f, A[2] * norm / A[4]); num(f, A[3] * norm / A[5]);
+      num(f, A[4] * 1.0 * mass / ac); num(f, A[5] * 1.0 * mass / ac);
+      num(f, A[0] * sqrt(norm / A[4]) / ac); num(f, A[1] * sqrt(norm / A[5]) / ac);
+      fputc('\n', f);
+      fclose(f);
+   }
+   // SaveAreaEstim3D, mc_estim.cc:2670-2729: 9 inertia components, then 6 of 4m^2/(hbar^2 beta) <A_i A_j>
+   static void area_estim3d(const string &fname, long block, double ac, const double *areas6, const double *inert9, int iframe, double beta, double lambda, double bmass)
+   {
+      FILE *f = fopen((fname + (iframe ? ".mffs3d" : ".sffs3d")).c_str(), "a");
+      if (!f) return;
+      const double norm = 2.0 * bmass / (beta * lambda);
+      fprintf(f, "%4ld   ", block);
+      for (int k = 0; k < 9; k++) num(f, inert9[k] / ac);
+      for (int k = 0; k < 6; k++) num(f, areas6[k] * norm / ac);
+      fputc('\n', f);
+      fclose(f);
+   }
+};
+
 #endif

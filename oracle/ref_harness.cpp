@@ -16,6 +16,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <fstream>
+#include <string>
 #include <unistd.h>
 #include <omp.h>
 
@@ -264,9 +266,11 @@ void ref_zero_relbins(void)
 }
 // The reference's own density writers (mc_estim.cc:1327-1820,1930-1995) on test-supplied histograms: block and accumulated
 // arrays are both set to the given counts; files appear under `prefix` exactly as MCSaveBlockAverages / main write them.
+extern "C++" {
 extern double **_gr1D_sum;
 extern double ***_gr2D_sum;
 extern double **_gr3D_sum;
+}
 void ref_save_densities(const char *prefix, double acount, const double *gr1d, const double *gr2d, const double *gr3d, const double *rel)
 {
    for (int id = 0; id < NumbTypes; id++) {
@@ -292,6 +296,52 @@ void ref_save_densities(const char *prefix, double acount, const double *gr1d, c
       SaveRhoThetaChi(prefix, acount, MC_BLOCK);
       SaveDensities3D(prefix, acount, MC_TOTAL);
       SaveRho1D(prefix, acount, MC_TOTAL);
+   }
+}
+// The reference's own per-block writers (SaveEnergy, SaveSumEnergy, SaveRCF, SaveGraSum, SaveExchangeLength,
+// SaveAreaEstimators, SaveAreaEstim3D) on test-supplied accumulator values.
+extern "C++" {
+void SaveEnergy(const char [], double, long int);
+void SaveSumEnergy(double, double);
+extern double **_rcf_sum;
+extern double _kin_total, _pot_total, _rot_total, _rotsq_total, _Cv_total, _Cv_trans_total, _Cv_rot_total;
+extern double _areas3DMFF[6], _inert3DMFF[9], _areas3DSFF[6], _inert3DSFF[9];
+extern std::fstream _feng;
+}
+void ref_save_block(const char *prefix, long block, double acount, const double *scal7, const double *rcf0, const double *rcf19,
+                    const double *gr1d, const double *ploops, const int *pindex, const double *area40)
+{
+   avergCount = acount;
+   _bkin = scal7[0]; _bpot = scal7[1]; _brot = scal7[2]; _brotsq = scal7[3]; _bCv = scal7[4]; _bCv_trans = scal7[5]; _bCv_rot = scal7[6];
+   _kin_total = scal7[0]; _pot_total = scal7[1]; _rot_total = scal7[2]; _rotsq_total = scal7[3]; _Cv_total = scal7[4]; _Cv_trans_total = scal7[5]; _Cv_rot_total = scal7[6];
+   SaveEnergy(prefix, acount, block);
+   std::string fs = std::string(prefix) + "_sum.eng";
+   if (_feng.is_open()) _feng.close();
+   _feng.clear();
+   _feng.open(fs.c_str(), std::ios::out); io_setout(_feng);
+   SaveSumEnergy(acount, 3.0);
+   _feng.close();
+   if (ROTATION) {
+      for (int it = 0; it < NumbRotTimes; it++) {
+         _rcf[0][it] = rcf0[it]; _rcf_sum[0][it] = rcf0[it];
+         for (int ip = 1; ip < NUMB_RCF; ip++) { _rcf[ip][it] = rcf19[it]; _rcf_sum[ip][it] = rcf19[it]; }
+      }
+      SaveRCF(prefix, acount, MC_BLOCK);
+      SaveRCF(prefix, acount, MC_TOTAL);
+   }
+   for (int id = 0; id < NumbTypes; id++)
+      if (!MCAtom[id].molecule) for (int i = 0; i < 300; i++) _gr1D_sum[id][i] = gr1d[i];
+   SaveGraSum(prefix, acount);
+   if (BOSONS) {
+      for (int a = 0; a < MCAtom[BSTYPE].numb; a++) { _ploops[a] = ploops[a]; PIndex[a] = pindex[a]; }
+      PrintXYZprl = 0;
+      SaveExchangeLength(prefix, acount, block);
+      for (int k = 0; k < 2; k++) { _areas[k] = area40[k]; _area2[k] = area40[2 + k]; _inert[k] = area40[4 + k]; }
+      for (int k = 0; k < 6; k++) { _areas3DSFF[k] = area40[6 + k]; _areas3DMFF[k] = area40[21 + k]; }
+      for (int k = 0; k < 9; k++) { _inert3DSFF[k] = area40[12 + k]; _inert3DMFF[k] = area40[27 + k]; }
+      if (MCAtom[IMTYPE].molecule == 1) SaveAreaEstimators(prefix, acount, block);
+      SaveAreaEstim3D(prefix, acount, block, 0);
+      if (MCAtom[IMTYPE].molecule == 2 && ISPHER == 0) SaveAreaEstim3D(prefix, acount, block, 1);
    }
 }
 void ref_GetAreaEstimators(double *areas, double *area2, double *inert)

@@ -1,6 +1,8 @@
 """CPU test of the driver's density writers (moribs-pimc_b200/driver/pimc_writers.h) against the reference's OWN
 Save* functions (SaveDensities1D, SaveDensities2D, SaveRho1D, SaveRhoThetaChi, SaveDensities3D; mc_estim.cc:1327-1820,
-1930-1995) driven through oracle/_ref on the same seeded histograms: every output file must be byte-identical.
+1930-1995; SaveEnergy, SaveSumEnergy mc_main.cc:764-836; SaveRCF, SaveGraSum, SaveExchangeLength, SaveAreaEstimators,
+SaveAreaEstim3D mc_estim.cc:1141-1191,1288-1326,2021-2085,2596-2729) driven through oracle/_ref on the same seeded
+histograms and accumulator values: every output file must be byte-identical.
 Where oracle/_ref is absent the files are checked against the digests committed in tests/golden/writers.json
 (made by this test when run with MAKE_WRITER_FIXTURE=1 next to the reference)."""
 import hashlib
@@ -14,7 +16,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 FIXTURE = os.path.join(ROOT, "tests", "golden", "writers.json")
-CASES = {"C5": dict(P=32, Q=8, nsolv=6), "C1": dict(P=64, Q=16), "C4": dict(P=64, Q=32)}
+CASES = {"C5": dict(P=32, Q=8, nsolv=6), "C1": dict(P=64, Q=16), "C2": dict(P=32, Q=8, nsolv=5), "C4": dict(P=64, Q=32)}
 
 SCRIPT = r'''
 import sys, os, json, hashlib, ctypes as C, subprocess
@@ -23,10 +25,10 @@ sys.path.insert(0, %(root)r)
 name, work, use_ref = %(name)r, %(work)r, %(use_ref)r
 import __graft_entry__ as ge
 pkg = ge.load_package()
-cfg = pkg.configs.make_config(name, big_tables=(name not in ("C1", "C4")), **%(kw)r)
-if name == "C1":                                  # tables are irrelevant for the writers; keep the process small
+cfg = pkg.configs.make_config(name, big_tables=(name not in ("C1", "C2", "C4")), **%(kw)r)
+if name in ("C1", "C2"):                                  # tables are irrelevant for the writers; keep the process small
     cfg.tables["pot3d"] = (3, 181, 181, 4.0, 20.0, np.zeros(3 * 181 * 181))
-if name in ("C1", "C4"):
+if name in ("C1", "C2", "C4"):
     z = np.zeros(181 * 361 * 361)
     cfg.tables["rot3d"] = (z, z, z)
 s = cfg.system
@@ -44,11 +46,33 @@ numb = np.array([t.numb for t in s.types], dtype=np.int32); mol = np.array([t.mo
 box = (s.N / s.density) ** (1.0 / 3.0)
 shim.shim_save_densities((work + "/mine/gr").encode(), C.c_int(s.P), C.c_int(s.Q), C.c_int(len(s.types)), numb.ctypes.data_as(C.POINTER(C.c_int)),
                          mol.ctypes.data_as(C.POINTER(C.c_int)), C.c_double(box ** 3), C.c_double(acount), P_(g1), P_(g2), P_(g3), P_(rel))
+# per-block scalar writers: SaveEnergy, SaveSumEnergy, SaveRCF (block + total), SaveGraSum, SaveExchangeLength, SaveAreaEstimators, SaveAreaEstim3D
+scal7 = np.array([123.456, -987.654, 3.25, 17.5, -4321.0, -2222.0, 11.0]) * acount
+Qn = max(1, s.Q)
+rcf0 = rng.uniform(-1, 1, Qn) * acount * Qn
+rcf19 = rng.integers(0, Qn, Qn).astype(float) * acount
+bos = [t for t in s.types if t.stat == 1]
+nb = bos[0].numb if bos else 0
+ploops = rng.integers(0, 50, max(1, nb)).astype(float)
+pindex = rng.permutation(max(1, nb)).astype(np.int32)
+area40 = rng.uniform(0.5, 3.0, 40) * acount
+imol = [t for t in s.types if t.molecule]
+linear = int(bool(imol) and imol[0].molecule == 1); mff = int(bool(imol) and imol[0].molecule == 2 and not s.ispher)
+atoms = [t for t in s.types if not t.molecule]
+bmass = bos[0].mass if bos else 1.0
+lam = 0.5 * (100.0 * (1.05457266 * 1.05457266) / (1.6605402 * 1.380658)) / bmass            # mc_setup.cc:206-215
+IP_ = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+shim.shim_save_block((work + "/mine/gr").encode(), C.c_long(17), C.c_int(s.N), C.c_int(s.P), C.c_int(s.Q), C.c_double(s.temperature),
+                     C.c_int(1 if atoms else 0), C.c_int(atoms[0].numb if atoms else 0), C.c_int(nb), C.c_int(linear), C.c_int(mff),
+                     C.c_double(lam), C.c_double(bmass), C.c_double(acount), P_(scal7), P_(rcf0), P_(rcf19), P_(g1), P_(ploops), IP_(pindex), P_(area40))
 out = {}
 if use_ref:
     from oracle import oracle_py as op
     R = op.Ref(cfg)
     R.lib.ref_save_densities((work + "/ref/gr").encode(), C.c_double(acount), P_(g1), P_(g2), P_(g3), P_(rel))
+    if bos:
+        assert abs(R.lib.ref_lambda(s.types.index(bos[0])) - lam) < 1e-12 * lam
+    R.lib.ref_save_block((work + "/ref/gr").encode(), C.c_long(17), C.c_double(acount), P_(scal7), P_(rcf0), P_(rcf19), P_(g1), P_(ploops), IP_(pindex), P_(area40))
     for f in sorted(os.listdir(work + "/ref")):
         a = open(work + "/ref/" + f, "rb").read()
         b = open(work + "/mine/" + f, "rb").read() if os.path.exists(work + "/mine/" + f) else b""
@@ -77,16 +101,17 @@ def test_density_writers_byte_identical_to_reference(name, shim, tmp_path):
     line = [l for l in out.stdout.splitlines() if l.startswith("RESULT ")]
     assert line, out.stdout[-2000:] + out.stderr[-2000:]
     res = json.loads(line[-1][7:])
-    expect = {"C5": {"gr.gra", "gr.gri", "gr.grt", "gr.g2d", "gr_sum.g2d"},
-              "C1": {"gr.gra", "gr.gri", "gr.grt", "gr.grc", "gr.gtc", "gr_sum.g3d", "gr_sum.gri", "gr_sum.grt", "gr_sum.grc", "gr_sum.eulphi", "gr_sum.eulchi", "gr_sum.eulthe"}}
-    expect["C4"] = expect["C1"]
+    top = {"gr.gra", "gr.gri", "gr.grt", "gr.grc", "gr.gtc", "gr_sum.g3d", "gr_sum.gri", "gr_sum.grt", "gr_sum.grc", "gr_sum.eulphi", "gr_sum.eulchi", "gr_sum.eulthe"}
+    common = {"gr.eng", "gr_sum.eng", "gr.rcf", "gr_sum.rcf", "gr_sum.gra"}
+    expect = {"C5": {"gr.gra", "gr.gri", "gr.grt", "gr.g2d", "gr_sum.g2d", "gr.prl", "gr.sup", "gr.sffs3d"} | common,
+              "C1": top | common | {"gr.prl", "gr.sffs3d", "gr.mffs3d"}, "C2": top | common | {"gr.prl", "gr.sffs3d", "gr.mffs3d"}, "C4": top | common}
     fixture = json.load(open(FIXTURE)) if os.path.exists(FIXTURE) else {}
     if use_ref:
         assert res.pop("_only_mine") == []
         assert set(res) == expect[name]
         for f, r in res.items():
             assert r["identical"], f"{name}: {f} differs from the reference's writer"
-            assert r["bytes"] > 1000
+            assert r["bytes"] > 50
         if os.environ.get("MAKE_WRITER_FIXTURE"):
             fixture[name] = {f: {"bytes": r["bytes"], "md5": r["md5"]} for f, r in res.items()}
             json.dump(fixture, open(FIXTURE, "w"), indent=1, sort_keys=True)
