@@ -170,3 +170,36 @@ def test_rattle_and_shake_propagator(pkg, name):
     srot, esq, eterm = O.get_rot_energy()
     assert abs(e["rot"] - srot) <= 1e-9 * abs(srot)
     G.close()
+
+
+def test_rcf_legendre_rows_count_time_origins_below_plone(pkg):
+    """Rows 1..9 of the block array _rcf: GetRCF (mc_estim.cc:1127-1137) adds pleg = 1 only where n(t0).n(t0+t) < PLONE
+    (the Legendre call is commented out, so the `if` governs the accumulation).  The device keeps that count per t in the
+    "rcfcnt" region; check it against the downloaded orientations of every chain."""
+    cfg = pkg.configs.make_config("C5", P=32, Q=8, nsolv=6)
+    s = cfg.system
+    G = pkg.gpu.PimcGpu(cfg, nchains=3)
+    G.seed((5, 6, 7, 8, 9, 10))
+    G.steps(3 * s.P)
+    G.accum_reset()
+    G.measure()
+    G.sync()
+    acc, lay = G.accum_download()
+    off = G.L.pimcgpu_accum_offset(b"rcfcnt")
+    assert off > 0
+    Q, P = s.Q, s.P
+    rot0 = sum(t.numb for t in s.types if t.molecule == 0) * P          # first rotor's slices
+    want = np.zeros(Q)
+    want0 = np.zeros(Q)
+    for c in range(3):
+        _, _, cs = G.download(c)
+        n = cs[:, rot0:rot0 + Q]
+        for t0 in range(Q):
+            for t in range(Q):
+                p0 = float(n[:, t0] @ n[:, (t0 + t) % Q])
+                want0[t] += p0
+                want[t] += 1.0 if p0 < 0.9999999 else 0.0
+    assert np.array_equal(acc[off:off + Q], want)
+    assert want[0] == 0 and want[1:].sum() > 0                          # n.n = 1 at t = 0 never counts
+    assert np.abs(acc[lay["rcf"]:lay["rcf"] + Q] - want0).max() < 1e-10 * Q
+    G.close()
