@@ -417,12 +417,30 @@ int main(int argc, char **argv)
       ck(pimcgpu_accum_reset(), "pimcgpu_accum_reset");
       const long steps_block = d.passes * P;
       long done = 0;
+      bool print_xyz = true;                                                                 // MCResetBlockAverage, mc_main.cc:543
       while (done < steps_block) {
          long chunk = min<long>(d.skip_averg, steps_block - done);
          if (block <= d.eq_blocks) chunk = min<long>(steps_block - done, 4L * P);            // no estimators while equilibrating
          ck(pimcgpu_steps(chunk), "pimcgpu_steps");
          done += chunk;
-         if (block > d.eq_blocks && done % d.skip_averg == 0) ck(pimcgpu_measure(), "pimcgpu_measure");
+         if (block > d.eq_blocks && done % d.skip_averg == 0) {
+            ck(pimcgpu_measure(), "pimcgpu_measure");
+            if (print_xyz && rank == 0) {
+               // instantaneous configuration of the block's first measured (closed) path: IOxyzAng into <prefix>NNN.xyz
+               // (PrintXYZprl, mc_main.cc:395-427,543); chain 0
+               int st[5] = {0, 0, 0, 0, 0};
+               if (d.worm) ck(pimcgpu_worm_state(0, st), "pimcgpu_worm_state");
+               if (!st[0]) {
+                  ck(pimcgpu_download_state(0, coords.data(), angles.data(), nullptr, bstype >= 0 ? pindex.data() : nullptr), "pimcgpu_download_state");
+                  vector<string> names; vector<int> numbs;
+                  for (auto &t : d.types) { names.push_back(t.name); numbs.push_back(t.numb); }
+                  ostringstream bc; bc << setw(3) << setfill('0') << block;
+                  XyzWriters::xyz_ang(fname + bc.str(), sys.ntypes, names.data(), numbs.data(), P, coords.data(), angles.data(),
+                                      bstype >= 0 ? d.types[bstype].numb : 0, pindex.data());
+                  print_xyz = false;
+               }
+            }
+         }
       }
       ck(pimcgpu_sync(), "pimcgpu_sync");
       double *dacc = (double *)pimcgpu_accum_device_ptr();                                   // move counters folded in
@@ -542,21 +560,10 @@ int main(int argc, char **argv)
          f.write((char *)&rec, sizeof rec);
       }
       { ofstream f("yw001.mrg"); f << "SEED"; for (int k = 0; k < 6; k++) f << " " << seed[k]; f << "\nSTEP " << pimcgpu_step_counter() << "\nCHAINS " << chains << " RANKS " << ranks << endl; }
-      {
-         // IOxyz, mc_input.cc:690-794
-         ofstream f(fname + ".xyz");
-         Writer::setout(f);
-         f << n << endl << "#" << BLANK << "xyz format:  [atom type]  x y z (Angstrom) " << endl;
-         int atom = 0;
-         for (int t = 0; t < sys.ntypes; t++)
-            for (int k = 0; k < d.types[t].numb; k++, atom++)
-               for (int it = 0; it < P; it++) {
-                  ostringstream lab; lab << d.types[t].name << (k + 1);
-                  f << setw(5) << lab.str() << BLANK;
-                  for (int dd = 0; dd < 3; dd++)
-                     f << setw(IO_WIDTH) << coords[dd * n + (size_t)atom * P + it] << BLANK << setw(IO_WIDTH) << cosine[dd * n + (size_t)atom * P + it] << BLANK;
-                  f << endl;
-               }
+      {  // IOxyz, mc_input.cc:690-794 (the checkpoint-time dump of chain 0, mc_main.cc:476-477)
+         vector<string> names; vector<int> numbs;
+         for (auto &t : d.types) { names.push_back(t.name); numbs.push_back(t.numb); }
+         XyzWriters::xyz(fname + ".xyz", sys.ntypes, names.data(), numbs.data(), P, coords.data(), cosine.data());
       }
    }
    double secs = chrono::duration<double>(chrono::steady_clock::now() - t_start).count();

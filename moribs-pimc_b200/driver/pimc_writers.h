@@ -300,4 +300,49 @@ struct BlockWriters {
    }
 };
 
+// IOxyz (mc_input.cc:690-794) and IOxyzAng (mc_estim.cc:1822-1928): beads of every particle, x/y/z interleaved with the unit
+// axis (IOxyz) or with phi, cos(theta), chi (IOxyzAng, which also lists the permutation of the bosons on its first line).
+// arrays are the reference layout [dim][atom*P + it]
+struct XyzWriters {
+   static void num(FILE *f, double v) { fprintf(f, "%14.6e   ", v); }
+   static void xyz(const string &path, int ntypes, const string *names, const int *numb, int P, const double *coords, const double *cosine)
+   {
+      FILE *f = fopen(path.c_str(), "w");
+      if (!f) return;
+      size_t n = 0;
+      for (int t = 0; t < ntypes; t++) n += (size_t)numb[t] * P;
+      fprintf(f, "%zu\n#   xyz format:  [atom type]  x y z (Angstrom) \n", n);
+      size_t atom = 0;
+      for (int t = 0; t < ntypes; t++)
+         for (int k = 0; k < numb[t]; k++, atom++)
+            for (int it = 0; it < P; it++) {
+               const string lab = names[t] + std::to_string(k + 1);
+               fprintf(f, "%5s   ", lab.c_str());
+               for (int d = 0; d < 3; d++) { num(f, coords[d * n + atom * P + it]); num(f, cosine[d * n + atom * P + it]); }
+               fputc('\n', f);
+            }
+      fclose(f);
+   }
+   static void xyz_ang(const string &name, int ntypes, const string *names, const int *numb, int P, const double *coords, const double *angles,
+                       int nbosons, const int *pindex)
+   {
+      FILE *f = fopen((name + ".xyz").c_str(), "w");
+      if (!f) return;
+      size_t n = 0;
+      for (int t = 0; t < ntypes; t++) n += (size_t)numb[t] * P;
+      fprintf(f, "%zu ", n);
+      for (int a = 0; a < nbosons; a++) fprintf(f, "  %d   ", pindex[a]);
+      fprintf(f, "\n#   xyz format:  [atom type]  x y z (Angstrom) \n");
+      size_t atom = 0;
+      for (int t = 0; t < ntypes; t++)
+         for (int k = 0; k < numb[t]; k++, atom++)
+            for (int it = 0; it < P; it++) {
+               fprintf(f, "%s%d", names[t].c_str(), k + 1);
+               for (int d = 0; d < 3; d++) { num(f, coords[d * n + atom * P + it]); num(f, angles[d * n + atom * P + it]); }
+               fputc('\n', f);
+            }
+      fclose(f);
+   }
+};
+
 #endif

@@ -344,6 +344,12 @@ void ref_save_block(const char *prefix, long block, double acount, const double 
       if (MCAtom[IMTYPE].molecule == 2 && ISPHER == 0) SaveAreaEstim3D(prefix, acount, block, 1);
    }
 }
+// IOxyz / IOxyzAng of the current reference state (set with ref_set_state)
+void ref_write_xyz(const char *path_xyz, const char *prefix_ang)
+{
+   IOxyz(IOWrite, path_xyz);
+   IOxyzAng(IOWrite, prefix_ang);
+}
 void ref_GetAreaEstimators(double *areas, double *area2, double *inert)
 {
    GetAreaEstimators();

@@ -229,12 +229,15 @@ def test_cxx_driver_worm_deck_and_restart(pkg, tmp_path):
     assert os.path.getsize(tmp_path / "yw001.worm") == 80 + 6 * 4 + 4 + 8 + 8 or os.path.getsize(tmp_path / "yw001.worm") > 100
     assert open(tmp_path / "yw001.stat").read().split() == ["STARTBLOCK", "4"]
     # density files of MCSaveBlockAverages / main (mc_main.cc:715-724, 451-454) and the two-part .rcf of SaveRCF
-    for f in ("gr004.gra", "gr004.gri", "gr004.grt", "gr004.g2d", "gr_sum.g2d", "gr_sum.gra", "gr004.rcf", "gr_sum.rcf"):
+    for f in ("gr004.gra", "gr004.gri", "gr004.grt", "gr004.g2d", "gr_sum.g2d", "gr_sum.gra", "gr004.rcf", "gr_sum.rcf", "gr002.xyz", "gr004.xyz"):
         assert os.path.exists(tmp_path / f), f
     g2d = np.loadtxt(tmp_path / "gr_sum.g2d")
     assert g2d.shape == (300 * 50, 3) and g2d[:, 2].sum() > 0
     gri = np.loadtxt(tmp_path / "gr004.gri")
     assert gri.shape == (300, 2) and abs((gri[:, 1] * 4 * np.pi * gri[:, 0] ** 2).sum() * 0.05 - 5.0) < 0.2     # 5 pH2 around the rotor
+    xyz = open(tmp_path / "gr004.xyz").read().split("\n")           # IOxyzAng: bead count + permutation of the 5 pH2, comment, 6 x 512 beads
+    assert xyz[0].split()[0] == "3072" and sorted(int(x) for x in xyz[0].split()[1:]) == [0, 1, 2, 3, 4] and xyz[1].startswith("#") and len(xyz) == 3072 + 3
+    assert xyz[2].startswith("H21") and len(xyz[2].split()) == 7 and xyz[-2].startswith("N2O1")
     rcf = open(tmp_path / "gr004.rcf").read().split("\n")
     assert len(rcf) == 2 * 129 + 4 and rcf[129:132] == ["", "", "#"] and len(rcf[132].split()) == 10
     # restart: two more blocks, numbered 5 and 6, appended to the same files

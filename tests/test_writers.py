@@ -65,6 +65,15 @@ IP_ = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
 shim.shim_save_block((work + "/mine/gr").encode(), C.c_long(17), C.c_int(s.N), C.c_int(s.P), C.c_int(s.Q), C.c_double(s.temperature),
                      C.c_int(1 if atoms else 0), C.c_int(atoms[0].numb if atoms else 0), C.c_int(nb), C.c_int(linear), C.c_int(mff),
                      C.c_double(lam), C.c_double(bmass), C.c_double(acount), P_(scal7), P_(rcf0), P_(rcf19), P_(g1), P_(ploops), IP_(pindex), P_(area40))
+# IOxyz / IOxyzAng of one configuration (cosine = the unit axis the reference derives from the angles)
+cs = np.zeros_like(cfg.angles)
+st = np.sqrt(np.maximum(0.0, 1.0 - cfg.angles[1] ** 2))
+cs[0], cs[1], cs[2] = st * np.cos(cfg.angles[0]), st * np.sin(cfg.angles[0]), cfg.angles[1]
+perm_all = np.arange(s.N, dtype=np.int32)
+if nb:
+    perm_all[:nb] = pindex
+names = (C.c_char_p * len(s.types))(*[t.name.encode() for t in s.types])
+coords_c = np.ascontiguousarray(cfg.coords); angles_c = np.ascontiguousarray(cfg.angles)
 out = {}
 if use_ref:
     from oracle import oracle_py as op
@@ -72,6 +81,11 @@ if use_ref:
     R.lib.ref_save_densities((work + "/ref/gr").encode(), C.c_double(acount), P_(g1), P_(g2), P_(g3), P_(rel))
     if bos:
         assert abs(R.lib.ref_lambda(s.types.index(bos[0])) - lam) < 1e-12 * lam
+    R.set_state(coords_c, angles_c, perm_all)
+    co, ao, cs_ref = R.get_state()                    # the reference's own MCCosine for the IOxyz columns
+    R.lib.ref_write_xyz((work + "/ref/gr.xyz").encode(), (work + "/ref/gr017").encode())
+    shim.shim_write_xyz((work + "/mine/gr.xyz").encode(), (work + "/mine/gr017").encode(), C.c_int(len(s.types)), names, IP_(numb), C.c_int(s.P),
+                        P_(coords_c), P_(angles_c), P_(np.ascontiguousarray(cs_ref)), C.c_int(nb), IP_(perm_all))
     R.lib.ref_save_block((work + "/ref/gr").encode(), C.c_long(17), C.c_double(acount), P_(scal7), P_(rcf0), P_(rcf19), P_(g1), P_(ploops), IP_(pindex), P_(area40))
     for f in sorted(os.listdir(work + "/ref")):
         a = open(work + "/ref/" + f, "rb").read()
@@ -79,6 +93,8 @@ if use_ref:
         out[f] = {"identical": a == b, "bytes": len(a), "md5": hashlib.md5(a).hexdigest()}
     out["_only_mine"] = sorted(set(os.listdir(work + "/mine")) - set(os.listdir(work + "/ref")))
 else:
+    shim.shim_write_xyz((work + "/mine/gr.xyz").encode(), (work + "/mine/gr017").encode(), C.c_int(len(s.types)), names, IP_(numb), C.c_int(s.P),
+                        P_(coords_c), P_(angles_c), P_(np.ascontiguousarray(cs)), C.c_int(nb), IP_(perm_all))
     for f in sorted(os.listdir(work + "/mine")):
         a = open(work + "/mine/" + f, "rb").read()
         out[f] = {"bytes": len(a), "md5": hashlib.md5(a).hexdigest()}
@@ -102,7 +118,7 @@ def test_density_writers_byte_identical_to_reference(name, shim, tmp_path):
     assert line, out.stdout[-2000:] + out.stderr[-2000:]
     res = json.loads(line[-1][7:])
     top = {"gr.gra", "gr.gri", "gr.grt", "gr.grc", "gr.gtc", "gr_sum.g3d", "gr_sum.gri", "gr_sum.grt", "gr_sum.grc", "gr_sum.eulphi", "gr_sum.eulchi", "gr_sum.eulthe"}
-    common = {"gr.eng", "gr_sum.eng", "gr.rcf", "gr_sum.rcf", "gr_sum.gra"}
+    common = {"gr.eng", "gr_sum.eng", "gr.rcf", "gr_sum.rcf", "gr_sum.gra", "gr.xyz", "gr017.xyz"}
     expect = {"C5": {"gr.gra", "gr.gri", "gr.grt", "gr.g2d", "gr_sum.g2d", "gr.prl", "gr.sup", "gr.sffs3d"} | common,
               "C1": top | common | {"gr.prl", "gr.sffs3d", "gr.mffs3d"}, "C2": top | common | {"gr.prl", "gr.sffs3d", "gr.mffs3d"}, "C4": top | common}
     fixture = json.load(open(FIXTURE)) if os.path.exists(FIXTURE) else {}

@@ -34,3 +34,12 @@ extern "C" void shim_save_block(const char *prefix, long block, int natoms, int 
       if (mff) BlockWriters::area_estim3d(fname, block, acount, area40 + 21, area40 + 27, 1, beta, lambda, bmass);
    }
 }
+
+extern "C" void shim_write_xyz(const char *path_xyz, const char *prefix_ang, int ntypes, const char *const *names, const int *numb, int P,
+                               const double *coords, const double *angles, const double *cosine, int nbosons, const int *pindex)
+{
+   std::string nm[PIMCGPU_MAX_TYPES];
+   for (int t = 0; t < ntypes; t++) nm[t] = names[t];
+   XyzWriters::xyz(path_xyz, ntypes, nm, numb, P, coords, cosine);
+   XyzWriters::xyz_ang(prefix_ang, ntypes, nm, numb, P, coords, angles, nbosons, pindex);
+}
