@@ -58,6 +58,7 @@ struct Context {
    std::vector<int> h_pindex;       // [c][N]
    double *stage = nullptr;         // pinned host staging: [c][pos | ang | cosn] in the device layout
    size_t stage_chain = 0;          // doubles per chain in `stage`
+   double *d_raw = nullptr;         // device scratch [3][N*P]: one chain's beads in the reference layout (import/export transposes)
 } G;
 
 template <class T> int dalloc(T **ptr, size_t n)
@@ -435,6 +436,7 @@ int pimcgpu_init(const pimcgpu_system *sys, const pimcgpu_tables *tab)
    G.stage_chain = (size_t)p.P * 3 * p.Npad + 2 * (size_t)std::max(1, p.Q) * 3 * p.NMpad;
    CK(cudaHostAlloc((void **)&G.stage, C * G.stage_chain * sizeof(double), cudaHostAllocDefault));
    memset(G.stage, 0, C * G.stage_chain * sizeof(double));
+   if (dalloc(&G.d_raw, (size_t)3 * p.N * p.P)) return 1;
    // ---- execution geometry ----
    int seg_max = 1, seg_min = 1 << 30;
    for (int t = 0; t < p.ntypes; t++) { seg_max = std::max(seg_max, 1 << p.levels[t]); seg_min = std::min(seg_min, 1 << p.levels[t]); }
@@ -545,6 +547,40 @@ int pimcgpu_init(const pimcgpu_system *sys, const pimcgpu_tables *tab)
    return 0;
 }
 
+}  // extern "C"
+namespace {
+// Beads between the reference layout raw[d][atom*P + it] (mc_setup.cc:139-148) and the device layout pos[it][d][Npad]:
+// a tiled transpose through shared memory, both sides coalesced.  to_device != 0 imports, else exports.
+__global__ void state_transpose_kernel(double *pos, double *raw, int N, int P, int Npad, int to_device)
+{
+   __shared__ double tile[32][33];
+   const int d = blockIdx.z, it0 = blockIdx.x * 32, a0 = blockIdx.y * 32;
+   const size_t n = (size_t)N * P;
+   if (to_device) {
+      for (int r = threadIdx.y; r < 32; r += blockDim.y) {          // r: atom in tile, x: slice
+         const int a = a0 + r, it = it0 + threadIdx.x;
+         if (a < N && it < P) tile[r][threadIdx.x] = raw[d * n + (size_t)a * P + it];
+      }
+      __syncthreads();
+      for (int r = threadIdx.y; r < 32; r += blockDim.y) {          // r: slice in tile, x: atom
+         const int it = it0 + r, a = a0 + threadIdx.x;
+         if (a < N && it < P) pos[((size_t)it * 3 + d) * Npad + a] = tile[threadIdx.x][r];
+      }
+   } else {
+      for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+         const int it = it0 + r, a = a0 + threadIdx.x;
+         if (a < N && it < P) tile[threadIdx.x][r] = pos[((size_t)it * 3 + d) * Npad + a];
+      }
+      __syncthreads();
+      for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+         const int a = a0 + r, it = it0 + threadIdx.x;
+         if (a < N && it < P) raw[d * n + (size_t)a * P + it] = tile[r][threadIdx.x];
+      }
+   }
+}
+}  // namespace
+extern "C" {
+
 int pimcgpu_upload_state(int chain, const double *coords, const double *angles, const int *pindex)
 {
    if (!G.live) return fail("pimcgpu_upload_state: not initialised");
@@ -555,17 +591,8 @@ int pimcgpu_upload_state(int chain, const double *coords, const double *angles, 
    const int cfirst = chain < 0 ? 0 : chain;
    double *hpos = G.stage + (size_t)cfirst * G.stage_chain, *hang = hpos + npos, *hcos = hang + nang;
    CK(cudaStreamSynchronize(G.stream));          // the staging area may still be in flight
-   // [dim][atom][it] -> [it][dim][atom], tiled so both sides stay within a few cache lines; host threads over the tiles
-   #pragma omp parallel for collapse(2) schedule(static)
-   for (int d = 0; d < 3; d++)
-      for (int a0 = 0; a0 < p.N; a0 += 8)
-         for (int it0 = 0; it0 < p.P; it0 += 64) {
-            const int a1 = std::min(p.N, a0 + 8), it1 = std::min(p.P, it0 + 64);
-            for (int a = a0; a < a1; a++) {
-               const double *src = coords + d * n + (size_t)a * p.P;
-               for (int it = it0; it < it1; it++) hpos[((size_t)it * 3 + d) * p.Npad + a] = src[it];
-            }
-         }
+   // beads: the caller's [dim][atom*P + it] array goes to the device as it is and is transposed there (state_transpose_kernel)
+   CK(cudaMemcpyAsync(G.d_raw, coords, 3 * n * sizeof(double), cudaMemcpyHostToDevice, G.stream));
    if (p.imtype >= 0)
       for (int q = 0; q < p.Q; q++)
          for (int m = 0; m < p.NM; m++) {
@@ -599,7 +626,8 @@ int pimcgpu_upload_state(int chain, const double *coords, const double *angles, 
    while ((int)cstart.size() < p.N + 1) cstart.push_back((int)catoms.size());
    int c0 = chain < 0 ? 0 : chain, c1 = chain < 0 ? p.nchains : chain + 1;
    for (int c = c0; c < c1; c++) {
-      CK(cudaMemcpyAsync(p.pos + (size_t)c * npos, hpos, npos * sizeof(double), cudaMemcpyHostToDevice, G.stream));
+      state_transpose_kernel<<<dim3((p.P + 31) / 32, (p.N + 31) / 32, 3), dim3(32, 8), 0, G.stream>>>(p.pos + (size_t)c * npos, G.d_raw, p.N, p.P, p.Npad, 1);
+      CK(cudaGetLastError());
       CK(cudaMemcpyAsync(p.ang + (size_t)c * nang, hang, nang * sizeof(double), cudaMemcpyHostToDevice, G.stream));
       CK(cudaMemcpyAsync(p.cosn + (size_t)c * nang, hcos, nang * sizeof(double), cudaMemcpyHostToDevice, G.stream));
       CK(cudaMemcpyAsync(p.pindex + (size_t)c * p.N, gp.data(), p.N * sizeof(int), cudaMemcpyHostToDevice, G.stream));
@@ -623,22 +651,14 @@ int pimcgpu_download_state(int chain, double *coords, double *angles, double *co
    const size_t n = (size_t)p.N * p.P;
    const size_t npos = (size_t)p.P * 3 * p.Npad, nang = (size_t)std::max(1, p.Q) * 3 * p.NMpad;
    double *hpos = G.stage + (size_t)chain * G.stage_chain, *hang = hpos + npos, *hcos = hang + nang;
-   CK(cudaMemcpyAsync(hpos, p.pos + (size_t)chain * npos, npos * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
+   if (coords) {   // transposed on the device into the reference layout, then one copy into the caller's array
+      state_transpose_kernel<<<dim3((p.P + 31) / 32, (p.N + 31) / 32, 3), dim3(32, 8), 0, G.stream>>>(p.pos + (size_t)chain * npos, G.d_raw, p.N, p.P, p.Npad, 0);
+      CK(cudaGetLastError());
+      CK(cudaMemcpyAsync(coords, G.d_raw, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
+   }
    CK(cudaMemcpyAsync(hang, p.ang + (size_t)chain * nang, nang * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
    CK(cudaMemcpyAsync(hcos, p.cosn + (size_t)chain * nang, nang * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
    CK(cudaStreamSynchronize(G.stream));
-   if (coords) {
-      #pragma omp parallel for collapse(2) schedule(static)
-      for (int d = 0; d < 3; d++)
-         for (int a0 = 0; a0 < p.N; a0 += 8)
-            for (int it0 = 0; it0 < p.P; it0 += 64) {
-               const int a1 = std::min(p.N, a0 + 8), it1 = std::min(p.P, it0 + 64);
-               for (int a = a0; a < a1; a++) {
-                  double *dst = coords + d * n + (size_t)a * p.P;
-                  for (int it = it0; it < it1; it++) dst[it] = hpos[((size_t)it * 3 + d) * p.Npad + a];
-               }
-            }
-   }
    // rotor rows: only the first Q entries of a molecule's row carry angles (README.md:228); the rest keep
    // the reference's initial values phi=0, cos(theta)=1, chi=0 (MCConfigInit, mc_setup.cc:471-487)
    #pragma omp parallel for schedule(static)
