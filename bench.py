@@ -282,7 +282,13 @@ def main():
     value = per_step_units * world * args.steps / t_kernel
 
     # ---- end to end through the C ABI with host buffers: upload -> pass -> estimators -> (all-reduce) -> download ----
-    host = [G.download(c)[:2] for c in range(chains)]
+    # host state lives in pinned buffers allocated once, as the reference's MCCoords / MCAngles do (mc_setup.cc:135-163)
+    n_beads = s.N * P
+    pinned = [(torch.empty((3, n_beads), dtype=torch.float64, pin_memory=True), torch.empty((3, n_beads), dtype=torch.float64, pin_memory=True))
+              for _ in range(chains)]
+    host = [(pc.numpy(), pa.numpy()) for pc, pa in pinned]
+    for c in range(chains):
+        G.download_into(c, host[c][0], host[c][1])
     h2d = chains * ((P * 3 * ((s.N + 3) // 4 * 4) + 2 * max(1, s.Q) * 3 * max(1, sum(t.numb for t in s.types if t.molecule))) * 8 + (3 * s.N + 3) * 4)
     d2h = h2d - chains * (3 * s.N + 3) * 4 + lay["n_total"] * 8
     barrier()
@@ -300,7 +306,8 @@ def main():
             torch.cuda.current_stream().synchronize()
         G.sync()
         accum, _ = G.accum_download()
-        host = [G.download(c)[:2] for c in range(chains)]
+        for c in range(chains):
+            G.download_into(c, host[c][0], host[c][1])
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - w0
     if dist:

@@ -279,6 +279,11 @@ class PimcGpu:
         _ck(self.L.pimcgpu_download_state(C.c_int(chain), _dp(c), _dp(a), _dp(cs), None))
         return c, a, cs
 
+    def download_into(self, chain, coords, angles, cosine=None):
+        """download_state into caller-owned arrays [3][N*P] (e.g. pinned host memory that lives across steps, like the
+        reference's MCCoords / MCAngles / MCCosine which are allocated once, mc_setup.cc:135-163)"""
+        _ck(self.L.pimcgpu_download_state(C.c_int(chain), _dp(coords), _dp(angles), _dp(cosine), None))
+
     def seed(self, seed6=(12345,) * 6):
         _ck(self.L.pimcgpu_seed((C.c_ulong * 6)(*seed6)))
 
