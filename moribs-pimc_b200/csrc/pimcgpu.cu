@@ -661,7 +661,7 @@ int pimcgpu_download_state(int chain, double *coords, double *angles, double *co
    CK(cudaStreamSynchronize(G.stream));
    // rotor rows: only the first Q entries of a molecule's row carry angles (README.md:228); the rest keep
    // the reference's initial values phi=0, cos(theta)=1, chi=0 (MCConfigInit, mc_setup.cc:471-487)
-   #pragma omp parallel for schedule(static)
+   #pragma omp parallel for collapse(2) schedule(static)
    for (int d = 0; d < 3; d++)
       for (size_t i = 0; i < n; i++) {
          if (angles) angles[d * n + i] = (d == 1) ? 1.0 : 0.0;

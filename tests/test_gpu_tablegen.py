@@ -62,6 +62,18 @@ def test_wigner_d_recurrence_vs_quad_precision_sum(gpu):
         assert np.abs(m @ m.T - np.eye(2 * j + 1)).max() < 5e-13
 
 
+def test_wigner_d_large_j_stays_unitary(gpu):
+    """the carried exponent keeps the recurrence alive where the start value underflows FP64 (theta near 0 and pi, j up to 200)"""
+    maxj = 200
+    for th in (0.02, 1.0, np.pi - 0.02):
+        d = gpu.gen_wigner_d(maxj, th)
+        for j in (90, 150, 200):
+            w = np.arange(-j, j + 1) + maxj
+            m = d[j][np.ix_(w, w)]
+            assert np.abs(m @ m.T - np.eye(2 * j + 1)).max() < 5e-11, (th, j)
+            assert abs(np.trace(m) - np.sin((j + 0.5) * th) / np.sin(0.5 * th)) < 1e-9 * (2 * j + 1)      # character of the rotation
+
+
 def test_wigner_d_against_live_oracle(gpu, tg):
     maxj, th = 12, 2.2
     d = gpu.gen_wigner_d(maxj, th)
