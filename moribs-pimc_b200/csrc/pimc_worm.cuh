@@ -47,6 +47,9 @@ struct WormShared {
    int it0, it1, atom0, atom1, use_path, diff, go, changed, perm_changed;
    double path[(WORM_MAXM + 2) * 3];     // swap: the proposed path, point k = it - it0
    double result;
+   int ng;                               // gaussians of the coming Levy bridge, drawn as one batch (worm_gauss_batch)
+   double us[6 * (WORM_MAXM + 1)];       // their uniforms in stream order
+   double gs[3 * (WORM_MAXM + 1)];       // sqrt(-log u1) cos(2 pi u2), still to be divided by sqrt(alpha)
 };
 
 // sum over the open interval (it0, it1) of PotEnergy(atom(it), pos, it mod P) -- get_potential, mc_qworm.cc:400-422 -- with
@@ -90,18 +93,28 @@ __device__ double worm_pot_sum(const Params &p, const SmallTables &t, int c, con
    return tot;
 }
 
-struct WormRng { Mrg g; };
-__device__ __forceinline__ double w_gauss(Mrg &g, double alpha)          // mc_randg.cc:138-150
-{
-   const double r1 = mrg_u01(g), r2 = mrg_u01(g);
-   const double x1 = sqrt(-log(r1)) * cos(2.0 * PI * r2);
-   return (x1 / sqrt(alpha));
-}
 __device__ __forceinline__ int w_nrnd(Mrg &g, int n) { return (int)floor(n * mrg_u01(g)); }
 
+// The gaussians of one Levy bridge as a batch (all threads of the CTA): thread 0 draws the 2 ng uniforms in the stream's
+// order, the transcendental part of gauss (mc_randg.cc:138-150) is evaluated by ng threads at once, and thread 0 consumes
+// gs[] in program order -- same draws, same operations, same bits as the sequential w_gauss, without ~500 cycles of
+// dependent log/cos/sqrt latency per number on the one thread that carries the worm's control flow.
+__device__ __forceinline__ void worm_gauss_batch(WormShared &w, Mrg &g)
+{
+   __syncthreads();                                   // w.ng published by thread 0
+   const int ng = w.ng;
+   if (ng <= 0) return;
+   if (threadIdx.x == 0)
+      for (int k = 0; k < 2 * ng; k++) w.us[k] = mrg_u01(g);
+   __syncthreads();
+   for (int k = threadIdx.x; k < ng; k += blockDim.x) w.gs[k] = sqrt(-log(w.us[2 * k])) * cos(2.0 * PI * w.us[2 * k + 1]);
+   __syncthreads();
+}
+
 // sample_middle, mc_qworm.cc:240-287, in the recursion's own (pre-)order; thread 0 only.  Points live in the state
-// (path == nullptr; atom0 before the wrap, atom2 after it) or in the proposed path of the swap.
-__device__ void worm_sample_middle(const Params &p, int c, Mrg &g, int it0r, int it2r, int atom0r, int atom2r, double *path)
+// (path == nullptr; atom0 before the wrap, atom2 after it) or in the proposed path of the swap.  The gaussians come from the
+// batch gs[] (index gi advances in program order).
+__device__ void worm_sample_middle(const Params &p, int c, const double *gs, int &gi, int it0r, int it2r, int atom0r, int atom2r, double *path)
 {
    const int P = p.P, base = p.first[p.worm_type];
    int stk[16][4], sp = 0;
@@ -122,7 +135,7 @@ __device__ void worm_sample_middle(const Params &p, int c, Mrg &g, int it0r, int
          if (path) { x0 = path[(it0 - it0r) * 3 + d]; x2 = path[(it2 - it0r) * 3 + d]; }
          else { x0 = p.pos[pos_index(p, c, pt0, d, base + atom0)]; x2 = p.pos[pos_index(p, c, pt2, d, base + atom2)]; }
          double x1 = (s2 * x0 + s0 * x2) / (s0 + s2);
-         x1 += w_gauss(g, gkin);
+         x1 += (gs[gi++] / sqrt(gkin));
          if (path) path[(it1 - it0r) * 3 + d] = x1;
          else p.pos[pos_index(p, c, pt1, d, base + atom1)] = x1;
       }
@@ -213,16 +226,24 @@ __device__ void worm_sweep_cta(const Params &p, const SmallTables &t, int c, dou
    const bool bose_worm = p.bstype >= 0 && p.worm_type == p.bstype;
    for (int atom = 0; atom < numb; atom++) {
       // ---------------- open / close ----------------
-      int segm = 0;
+      int segm = 0, gi = 0;
+      if (tid == 0) {
+         w.ng = 0;
+         if (w.st[0]) {
+            segm = w.st[2] - w.st[1];
+            if (segm < 0) segm += P;
+            if (segm <= p.worm_m && segm >= 2) w.ng = 3 * (segm - 1);
+         }
+      }
+      worm_gauss_batch(w, g);
       if (tid == 0) {
          qw[14] += 1.0;
          w.go = 0;
          if (w.st[0]) {                                     // qworm_close, mc_qworm.cc:184-238
             qw[QW_CLOSE] += 1.0;
-            segm = w.st[2] - w.st[1];
-            if (segm < 0) segm += P;
             if (segm <= p.worm_m) {
-               worm_sample_middle(p, c, g, w.st[1], w.st[1] + segm, w.st[3], w.st[4], nullptr);
+               gi = 0;
+               worm_sample_middle(p, c, w.gs, gi, w.st[1], w.st[1] + segm, w.st[3], w.st[4], nullptr);
                w.go = 1;
             }
          } else {                                           // qworm_open, mc_qworm.cc:155-182
@@ -264,34 +285,46 @@ __device__ void worm_sweep_cta(const Params &p, const SmallTables &t, int c, dou
       }
       __syncthreads();
       // ---------------- advance / recede ----------------
-      if (w.st[0]) {
+      if (w.st[0]) {                                        // block-uniform: w.st is shared and only thread 0 writes it between barriers
+         double r = 0.0;
+         int steps = 0, sg = 0;
+         if (tid == 0) {
+            // the draws that precede the bridge's gaussians in the stream: advance-or-recede, then the length of the move
+            r = mrg_u01(g);
+            steps = w_nrnd(g, p.worm_m) + 1;
+            w.ng = 0;
+            if (r > 0.5) {
+               sg = w.st[2] - w.st[1];
+               if (sg < 0) sg += P;
+               if (sg - steps > 0) w.ng = 3 * steps;         // the new head, then the steps - 1 beads between
+            }
+         }
+         worm_gauss_batch(w, g);
          if (tid == 0) {
             qw[14] += 1.0;
             w.go = 0;
-            const double r = mrg_u01(g);
             if (r > 0.5) {                                  // qworm_advance, mc_qworm.cc:299-357
                qw[QW_ADVANCE] += 1.0;
-               int sg = w.st[2] - w.st[1];
-               if (sg < 0) sg += P;
-               const int advance = w_nrnd(g, p.worm_m) + 1;
+               const int advance = steps;
                if (sg - advance > 0) {
                   const int it0 = w.st[1], it2 = w.st[1] + advance;
                   const int ira_new = it2 % P;
                   int atom_i_new = w.st[3];
                   if (ira_new != it2) atom_i_new = w.st[4];
                   const double gvar = 1.0 / ((double)advance * p.worm_twave2);
+                  gi = 0;
                   #pragma unroll
                   for (int d = 0; d < 3; d++)
-                     p.pos[pos_index(p, c, it2 % P, d, base + atom_i_new)] = p.pos[pos_index(p, c, it0 % P, d, base + w.st[3])] + w_gauss(g, gvar);
-                  worm_sample_middle(p, c, g, it0, it2, w.st[3], atom_i_new, nullptr);
+                     p.pos[pos_index(p, c, it2 % P, d, base + atom_i_new)] = p.pos[pos_index(p, c, it0 % P, d, base + w.st[3])] + (w.gs[gi++] / sqrt(gvar));
+                  worm_sample_middle(p, c, w.gs, gi, it0, it2, w.st[3], atom_i_new, nullptr);
                   w.it0 = it0; w.it1 = it2 + 1; w.atom0 = w.st[3]; w.atom1 = atom_i_new; w.use_path = 0; w.diff = 0;
                   w.go = 1;
                }
             } else {                                        // qworm_recede, mc_qworm.cc:359-398
                qw[QW_RECEDE] += 1.0;
-               int sg = w.st[1] - w.st[2];
+               sg = w.st[1] - w.st[2];
                if (sg < 0) sg += P;
-               const int recede = w_nrnd(g, p.worm_m) + 1;
+               const int recede = steps;
                if ((sg - recede) >= 1) {
                   int it0 = w.st[1] - recede, it1 = w.st[1];
                   int atom0 = w.st[3];
@@ -325,9 +358,11 @@ __device__ void worm_sweep_cta(const Params &p, const SmallTables &t, int c, dou
          if (tid == 0) qw[14] += 1.0;
          if (w.st[0]) {
             double pnorm_old = 0.0;
+            int sw_atom0 = -1, sw_atom1 = -1;
             if (tid == 0) {
                qw[QW_SWAP] += 1.0;
                w.go = 0;
+               w.ng = 0;
                const int sg = p.worm_m, it0 = w.st[1], it1 = it0 + sg, pit0 = it0, pit1 = it1 % P, atomw = w.st[3];
                int count = worm_get_ptable(p, c, w.st, atomw, pit0, pit1, sg, it1, dr2_list, atm_list, ptable);
                if (count > 0) {
@@ -347,11 +382,18 @@ __device__ void worm_sweep_cta(const Params &p, const SmallTables &t, int c, dou
                         w.path[0 * 3 + d] = p.pos[pos_index(p, c, pit0, d, base + atomw)];
                         w.path[sg * 3 + d] = p.pos[pos_index(p, c, pit1, d, base + atom1)];
                      }
-                     worm_sample_middle(p, c, g, it0, it1, atom0, atom1, w.path);
-                     w.it0 = it0; w.it1 = it1; w.atom0 = atom0; w.atom1 = atom1; w.use_path = 1; w.diff = 1;
-                     w.go = 1;
+                     sw_atom0 = atom0; sw_atom1 = atom1;
+                     if (sg >= 2) w.ng = 3 * (sg - 1);
                   }
                }
+            }
+            worm_gauss_batch(w, g);
+            if (tid == 0 && sw_atom1 >= 0) {
+               const int sg = p.worm_m, it0 = w.st[1], it1 = it0 + sg;
+               gi = 0;
+               worm_sample_middle(p, c, w.gs, gi, it0, it1, sw_atom0, sw_atom1, w.path);
+               w.it0 = it0; w.it1 = it1; w.atom0 = sw_atom0; w.atom1 = sw_atom1; w.use_path = 1; w.diff = 1;
+               w.go = 1;
             }
             __syncthreads();
             if (w.go) {

@@ -7,7 +7,7 @@ import __graft_entry__ as ge
 pkg = ge.load_package()
 w, chains, warm, nsteps = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
 geo = [int(x) for x in sys.argv[5:8]] + [0] * 3
-cfg = pkg.configs.make_config(w)
+cfg = pkg.configs.make_config(w, worm=bool(os.environ.get("PROF_WORM")))      # PROF_WORM=1 keeps the deck's WORM line (C2, C3)
 G = pkg.gpu.PimcGpu(cfg, nchains=chains, ctas_per_chain=geo[0], threads_per_cta=geo[1], team=geo[2])
 G.seed((12345,) * 6)
 G.steps(warm)
