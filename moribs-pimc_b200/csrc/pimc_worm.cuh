@@ -47,6 +47,8 @@ struct WormShared {
    int it0, it1, atom0, atom1, use_path, diff, go, changed, perm_changed;
    double path[(WORM_MAXM + 2) * 3];     // swap: the proposed path, point k = it - it0
    double result;
+   int count;                            // entries of the permutation table (worm_get_ptable)
+   int wb;                               // 1: the bridge of a close/advance move sits in path[] and goes to the state before the sums
    int ng;                               // gaussians of the coming Levy bridge, drawn as one batch (worm_gauss_batch)
    double us[6 * (WORM_MAXM + 1)];       // their uniforms in stream order
    double gs[3 * (WORM_MAXM + 1)];       // sqrt(-log u1) cos(2 pi u2), still to be divided by sqrt(alpha)
@@ -146,38 +148,54 @@ __device__ void worm_sample_middle(const Params &p, int c, const double *gs, int
 }
 
 // get_ptable, mc_qworm.cc:577-643: neighbours of world line atomw at slice pt0 among the beads at slice pt1, sorted by
-// distance (mmsort, mc_utils.cc:206-231), weights exp(-dr^2 / (segm * 4 lambda tau)); entries 1..count.  Thread 0 only.
-__device__ int worm_get_ptable(const Params &p, int c, const int *st, int atomw, int pt0, int pt1, int segm, int t1,
-                               double *dr2_list, int *atm_list, double *ptable)
+// distance (mmsort, mc_utils.cc:206-231), weights exp(-dr^2 / (segm * 4 lambda tau)); entries 1..count.  All threads of the
+// CTA: one thread per candidate world line for the distances, thread 0 for the (order-preserving) compaction and the
+// insertion sort, one thread per entry for the weights.  `flag` is an int scratch of numb entries.
+__device__ int worm_get_ptable(const Params &p, int c, WormShared &w, int atomw, int pt0, int pt1, int segm, int t1,
+                               double *dr2_list, int *atm_list, double *ptable, int *flag)
 {
    const int base = p.first[p.worm_type], numb = p.numb[p.worm_type];
    const int *rindex = p.rindex + (size_t)c * p.N;
-   int count = 0;
-   for (int atom1 = 0; atom1 < numb; atom1++)
+   const int *st = w.st;
+   for (int atom1 = threadIdx.x; atom1 < numb; atom1 += blockDim.x) {
+      int ok = 0;
+      double dr2 = 0.0;
       if (worm_world_line(st, atom1, pt1)) {
          int atom0 = atom1;
          if (t1 != pt1) atom0 = rindex[base + atom1] - base;
          if (atom0 != st[3]) {
-            double dr2 = 0.0;
             #pragma unroll
             for (int d = 0; d < 3; d++) {
                double dx = p.pos[pos_index(p, c, pt0, d, base + atomw)] - p.pos[pos_index(p, c, pt1, d, base + atom1)];
                if (p.minimage) dx -= (p.box[d] * rint(dx / p.box[d]));
                dr2 += (dx * dx);
             }
-            if (dr2 < p.worm_cutoff2) { count++; dr2_list[count] = dr2; atm_list[count] = atom1; }
+            if (dr2 < p.worm_cutoff2) ok = 1;
          }
       }
-   for (int j = 2; j <= count; j++) {
-      const double dtmp = dr2_list[j];
-      const int itmp = atm_list[j];
-      int i = j - 1;
-      while ((i > 0) && (dr2_list[i] > dtmp)) { dr2_list[i + 1] = dr2_list[i]; atm_list[i + 1] = atm_list[i]; i--; }
-      dr2_list[i + 1] = dtmp; atm_list[i + 1] = itmp;
+      flag[atom1] = ok;
+      ptable[1 + atom1] = dr2;                          // candidate scratch until the weights are written
    }
-   if (count > WORM_MAXNEIGHBORS) count = WORM_MAXNEIGHBORS;
+   __syncthreads();
+   if (threadIdx.x == 0) {
+      int count = 0;
+      for (int atom1 = 0; atom1 < numb; atom1++)
+         if (flag[atom1]) { count++; dr2_list[count] = ptable[1 + atom1]; atm_list[count] = atom1; }
+      for (int j = 2; j <= count; j++) {
+         const double dtmp = dr2_list[j];
+         const int itmp = atm_list[j];
+         int i = j - 1;
+         while ((i > 0) && (dr2_list[i] > dtmp)) { dr2_list[i + 1] = dr2_list[i]; atm_list[i + 1] = atm_list[i]; i--; }
+         dr2_list[i + 1] = dtmp; atm_list[i + 1] = itmp;
+      }
+      if (count > WORM_MAXNEIGHBORS) count = WORM_MAXNEIGHBORS;
+      w.count = count;
+   }
+   __syncthreads();
+   const int count = w.count;
    const double norm = 1.0 / ((double)segm * p.worm_twave2);
-   for (int ic = 1; ic <= count; ic++) ptable[ic] = exp(-norm * dr2_list[ic]);
+   for (int ic = 1 + threadIdx.x; ic <= count; ic += blockDim.x) ptable[ic] = exp(-norm * dr2_list[ic]);
+   __syncthreads();
    return count;
 }
 
@@ -200,6 +218,19 @@ __device__ void worm_rebuild_cycles(const Params &p, int c, int *seen /* [N] scr
       }
    }
    while (ns < N + 1) cstart[ns++] = na;
+}
+
+// beads 1 .. it1-it0-1 of a bridge built in path[] go to the state (close, advance): before the wrap they belong to atom0,
+// after it to atom1 -- the assignment sample_middle makes.  All threads; the potential sums that follow read the state.
+__device__ __forceinline__ void worm_write_back(const Params &p, int c, const WormShared &w)
+{
+   if (!w.wb) return;
+   const int P = p.P, base = p.first[p.worm_type], it0 = w.it0, n = w.it1 - w.it0 - 1;
+   for (int i = threadIdx.x; i < n * 3; i += blockDim.x) {
+      const int k = 1 + i / 3, d = i % 3, it = it0 + k, pit = it % P;
+      p.pos[pos_index(p, c, pit, d, base + (pit != it ? w.atom1 : w.atom0))] = w.path[k * 3 + d];
+   }
+   __syncthreads();
 }
 
 // MCWormMove, mc_qworm.cc:93-125, for chain c by the calling CTA.  `scratch` holds WormShared and the neighbour lists.
@@ -239,11 +270,19 @@ __device__ void worm_sweep_cta(const Params &p, const SmallTables &t, int c, dou
       if (tid == 0) {
          qw[14] += 1.0;
          w.go = 0;
+         w.wb = 0;
          if (w.st[0]) {                                     // qworm_close, mc_qworm.cc:184-238
             qw[QW_CLOSE] += 1.0;
             if (segm <= p.worm_m) {
+               // the bridge is built in shared memory (no dependent global round trips) and written to the state by all threads
                gi = 0;
-               worm_sample_middle(p, c, w.gs, gi, w.st[1], w.st[1] + segm, w.st[3], w.st[4], nullptr);
+               #pragma unroll
+               for (int d = 0; d < 3; d++) {
+                  w.path[d] = p.pos[pos_index(p, c, w.st[1], d, base + w.st[3])];
+                  w.path[segm * 3 + d] = p.pos[pos_index(p, c, w.st[2], d, base + w.st[4])];
+               }
+               worm_sample_middle(p, c, w.gs, gi, w.st[1], w.st[1] + segm, w.st[3], w.st[4], w.path);
+               w.wb = 1;
                w.go = 1;
             }
          } else {                                           // qworm_open, mc_qworm.cc:155-182
@@ -260,6 +299,7 @@ __device__ void worm_sweep_cta(const Params &p, const SmallTables &t, int c, dou
       }
       __syncthreads();
       if (w.go) {
+         worm_write_back(p, c, w);
          // qw_open_prob, mc_qworm.cc:127-153
          const double pot = worm_pot_sum<KIND>(p, t, c, w, red);
          if (tid == 0) {
@@ -303,6 +343,7 @@ __device__ void worm_sweep_cta(const Params &p, const SmallTables &t, int c, dou
          if (tid == 0) {
             qw[14] += 1.0;
             w.go = 0;
+            w.wb = 0;
             if (r > 0.5) {                                  // qworm_advance, mc_qworm.cc:299-357
                qw[QW_ADVANCE] += 1.0;
                const int advance = steps;
@@ -314,10 +355,13 @@ __device__ void worm_sweep_cta(const Params &p, const SmallTables &t, int c, dou
                   const double gvar = 1.0 / ((double)advance * p.worm_twave2);
                   gi = 0;
                   #pragma unroll
-                  for (int d = 0; d < 3; d++)
-                     p.pos[pos_index(p, c, it2 % P, d, base + atom_i_new)] = p.pos[pos_index(p, c, it0 % P, d, base + w.st[3])] + (w.gs[gi++] / sqrt(gvar));
-                  worm_sample_middle(p, c, w.gs, gi, it0, it2, w.st[3], atom_i_new, nullptr);
+                  for (int d = 0; d < 3; d++) {
+                     w.path[d] = p.pos[pos_index(p, c, it0 % P, d, base + w.st[3])];
+                     w.path[advance * 3 + d] = w.path[d] + (w.gs[gi++] / sqrt(gvar));          // the new head
+                  }
+                  worm_sample_middle(p, c, w.gs, gi, it0, it2, w.st[3], atom_i_new, w.path);
                   w.it0 = it0; w.it1 = it2 + 1; w.atom0 = w.st[3]; w.atom1 = atom_i_new; w.use_path = 0; w.diff = 0;
+                  w.wb = 1;
                   w.go = 1;
                }
             } else {                                        // qworm_recede, mc_qworm.cc:359-398
@@ -337,6 +381,7 @@ __device__ void worm_sweep_cta(const Params &p, const SmallTables &t, int c, dou
          }
          __syncthreads();
          if (w.go) {
+            worm_write_back(p, c, w);
             const double pot = worm_pot_sum<KIND>(p, t, c, w, red);
             if (tid == 0) {
                bool acc = false;
@@ -359,12 +404,16 @@ __device__ void worm_sweep_cta(const Params &p, const SmallTables &t, int c, dou
          if (w.st[0]) {
             double pnorm_old = 0.0;
             int sw_atom0 = -1, sw_atom1 = -1;
+            int count;
+            {
+               const int sg = p.worm_m, it0 = w.st[1], it1 = it0 + sg;
+               count = worm_get_ptable(p, c, w, w.st[3], it0, it1 % P, sg, it1, dr2_list, atm_list, ptable, seen);
+            }
             if (tid == 0) {
                qw[QW_SWAP] += 1.0;
                w.go = 0;
                w.ng = 0;
                const int sg = p.worm_m, it0 = w.st[1], it1 = it0 + sg, pit0 = it0, pit1 = it1 % P, atomw = w.st[3];
-               int count = worm_get_ptable(p, c, w.st, atomw, pit0, pit1, sg, it1, dr2_list, atm_list, ptable);
                if (count > 0) {
                   // atom2swap, mc_qworm.cc:645-667
                   for (int ic = 1; ic <= count; ic++) pnorm_old += ptable[ic];
@@ -398,10 +447,10 @@ __device__ void worm_sweep_cta(const Params &p, const SmallTables &t, int c, dou
             __syncthreads();
             if (w.go) {
                const double pot = worm_pot_sum<KIND>(p, t, c, w, red);
+               const int count2 = worm_get_ptable(p, c, w, w.atom0, w.it0, w.it1 % P, p.worm_m, w.it1, dr2_list, atm_list, ptable, seen);
                if (tid == 0) {
-                  const int sg = p.worm_m, it0 = w.it0, it1 = w.it1, pit0 = it0, pit1 = it1 % P;
                   double prob = exp(-pot * p.tau);
-                  const int count = worm_get_ptable(p, c, w.st, w.atom0, pit0, pit1, sg, it1, dr2_list, atm_list, ptable);
+                  const int count = count2;
                   double pnorm_new = 0.0;
                   for (int ic = 1; ic <= count; ic++) pnorm_new += ptable[ic];
                   prob *= (pnorm_old / pnorm_new);
