@@ -40,6 +40,7 @@ struct Params {
    // worm (WORM line, MCWormInit mc_qworm.cc:48-82): type, m-tilde, C * density, 4 lambda tau, neighbour cutoff^2
    int worm_on, worm_type, worm_m;
    double worm_norm, worm_twave2, worm_cutoff2;
+   const uint32_t *worm_jump;   // [k][18]: the MRG32k3a transition matrices A1^(2k), A2^(2k) (skip-ahead of the worm's gaussian batches)
    int *wstate;                  // [c][8]: Worm.exists, ira, masha, atom_i, atom_m (atoms numbered inside the worm type)
    int *rindex;                  // [c][N] previous world line (RIndex), global atom index like pindex
    double *qwc;                  // [c][16]: QWTotal[7], QWAccep[7], countQW
@@ -119,6 +120,23 @@ __device__ __forceinline__ double mrg_u01(Mrg &g)
    g.s[3] = g.s[4]; g.s[4] = g.s[5]; g.s[5] = p2;
    const double norm = 1.0 / (4294967087.0 + 1.0);
    return (p1 > p2) ? (double)(p1 - p2) * norm : ((double)p1 - (double)p2 + 4294967087.0) * norm;
+}
+// skip-ahead: state <- (J1 s1 mod m1, J2 s2 mod m2) with the 3x3 matrices in J[0..8], J[9..17] (row major)
+__device__ __forceinline__ void mrg_jump(Mrg &g, const uint32_t *J)
+{
+   uint32_t o[6];
+   #pragma unroll
+   for (int r = 0; r < 3; r++) {
+      uint64_t a = 0, b = 0;
+      #pragma unroll
+      for (int c = 0; c < 3; c++) {
+         a = (a + ((uint64_t)J[r * 3 + c] * g.s[c]) % MRG_M1) % MRG_M1;
+         b = (b + ((uint64_t)J[9 + r * 3 + c] * g.s[3 + c]) % MRG_M2) % MRG_M2;
+      }
+      o[r] = (uint32_t)a; o[3 + r] = (uint32_t)b;
+   }
+   #pragma unroll
+   for (int i = 0; i < 6; i++) g.s[i] = o[i];
 }
 __device__ __forceinline__ void mrg_load(Mrg &g, const uint32_t *st)
 {

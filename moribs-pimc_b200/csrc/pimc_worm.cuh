@@ -50,7 +50,7 @@ struct WormShared {
    int count;                            // entries of the permutation table (worm_get_ptable)
    int wb;                               // 1: the bridge of a close/advance move sits in path[] and goes to the state before the sums
    int ng;                               // gaussians of the coming Levy bridge, drawn as one batch (worm_gauss_batch)
-   double us[6 * (WORM_MAXM + 1)];       // their uniforms in stream order
+   uint32_t gstate[2][6];                // the worm stream before the batch / after it
    double gs[3 * (WORM_MAXM + 1)];       // sqrt(-log u1) cos(2 pi u2), still to be divided by sqrt(alpha)
 };
 
@@ -97,20 +97,27 @@ __device__ double worm_pot_sum(const Params &p, const SmallTables &t, int c, con
 
 __device__ __forceinline__ int w_nrnd(Mrg &g, int n) { return (int)floor(n * mrg_u01(g)); }
 
-// The gaussians of one Levy bridge as a batch (all threads of the CTA): thread 0 draws the 2 ng uniforms in the stream's
-// order, the transcendental part of gauss (mc_randg.cc:138-150) is evaluated by ng threads at once, and thread 0 consumes
-// gs[] in program order -- same draws, same operations, same bits as the sequential w_gauss, without ~500 cycles of
-// dependent log/cos/sqrt latency per number on the one thread that carries the worm's control flow.
-__device__ __forceinline__ void worm_gauss_batch(WormShared &w, Mrg &g)
+// The gaussians of one Levy bridge as a batch (all threads of the CTA).  Gaussian k uses draws 2k and 2k+1 of the worm's
+// stream: thread k jumps a copy of the generator ahead by 2k steps with the tabulated transition matrices (exact integer
+// arithmetic), draws its two uniforms and evaluates the transcendental part of gauss (mc_randg.cc:138-150); thread 0 then
+// continues with the state behind the last draw and consumes gs[] in program order -- same draws, same operations, same bits
+// as the sequential form, without its ~600 cycles of dependent latency per number on the thread that carries the control flow.
+__device__ __forceinline__ void worm_gauss_batch(const Params &p, WormShared &w, Mrg &g)
 {
-   __syncthreads();                                   // w.ng published by thread 0
+   if (threadIdx.x == 0) mrg_store(g, w.gstate[0]);
+   __syncthreads();                                   // w.ng and the generator published by thread 0
    const int ng = w.ng;
    if (ng <= 0) return;
-   if (threadIdx.x == 0)
-      for (int k = 0; k < 2 * ng; k++) w.us[k] = mrg_u01(g);
+   for (int k = threadIdx.x; k < ng; k += blockDim.x) {
+      Mrg h;
+      mrg_load(h, w.gstate[0]);
+      mrg_jump(h, p.worm_jump + (size_t)k * 18);
+      const double u1 = mrg_u01(h), u2 = mrg_u01(h);
+      w.gs[k] = sqrt(-log(u1)) * cos(2.0 * PI * u2);
+      if (k == ng - 1) mrg_store(h, w.gstate[1]);
+   }
    __syncthreads();
-   for (int k = threadIdx.x; k < ng; k += blockDim.x) w.gs[k] = sqrt(-log(w.us[2 * k])) * cos(2.0 * PI * w.us[2 * k + 1]);
-   __syncthreads();
+   if (threadIdx.x == 0) mrg_load(g, w.gstate[1]);
 }
 
 // sample_middle, mc_qworm.cc:240-287, in the recursion's own (pre-)order; thread 0 only.  Points live in the state
@@ -266,7 +273,7 @@ __device__ void worm_sweep_cta(const Params &p, const SmallTables &t, int c, dou
             if (segm <= p.worm_m && segm >= 2) w.ng = 3 * (segm - 1);
          }
       }
-      worm_gauss_batch(w, g);
+      worm_gauss_batch(p, w, g);
       if (tid == 0) {
          qw[14] += 1.0;
          w.go = 0;
@@ -339,7 +346,7 @@ __device__ void worm_sweep_cta(const Params &p, const SmallTables &t, int c, dou
                if (sg - steps > 0) w.ng = 3 * steps;         // the new head, then the steps - 1 beads between
             }
          }
-         worm_gauss_batch(w, g);
+         worm_gauss_batch(p, w, g);
          if (tid == 0) {
             qw[14] += 1.0;
             w.go = 0;
@@ -436,7 +443,7 @@ __device__ void worm_sweep_cta(const Params &p, const SmallTables &t, int c, dou
                   }
                }
             }
-            worm_gauss_batch(w, g);
+            worm_gauss_batch(p, w, g);
             if (tid == 0 && sw_atom1 >= 0) {
                const int sg = p.worm_m, it0 = w.st[1], it1 = it0 + sg;
                gi = 0;

@@ -311,6 +311,18 @@ int pimcgpu_init(const pimcgpu_system *sys, const pimcgpu_tables *tab)
       p.worm_norm = sys->worm_c * density;                     // Worm.c * numb * NumbTimes * Worm.m after MCWormInit's rescaling
       p.worm_twave2 = 4.0 * p.lambda[p.worm_type] * p.tau;     // twave2, mc_setup.cc:394
       p.worm_cutoff2 = 100.0 * 100.0 * ((double)p.worm_m * p.worm_twave2);
+      {  // skip-ahead matrices of the worm's gaussian batches: A^(2k), k = 0 .. 3 (WORM_MAXM + 1), A = one step of MRG32k3a
+         const int nj = 3 * (WORM_MAXM + 1) + 1;
+         u64 A1[3][3] = {{0, 1, 0}, {0, 0, 1}, {M1 - 810728ull, 1403580ull, 0}}, A2[3][3] = {{0, 1, 0}, {0, 0, 1}, {M2 - 1370589ull, 0, 527612ull}};
+         u64 S1[3][3], S2[3][3], W1[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}, W2[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+         matmat(A1, A1, S1, M1); matmat(A2, A2, S2, M2);
+         std::vector<uint32_t> jt((size_t)nj * 18);
+         for (int k = 0; k < nj; k++) {
+            for (int r = 0; r < 3; r++) for (int cc = 0; cc < 3; cc++) { jt[(size_t)k * 18 + r * 3 + cc] = (uint32_t)W1[r][cc]; jt[(size_t)k * 18 + 9 + r * 3 + cc] = (uint32_t)W2[r][cc]; }
+            matmat(S1, W1, W1, M1); matmat(S2, W2, W2, M2);
+         }
+         if (dupload(&p.worm_jump, jt.data(), jt.size())) return 1;
+      }
    }
    if (p.rotden_type == 1) {
       if (p.Q <= 0) return fail("pimcgpu_init: ROTDENSI 1 without ROTATION");
