@@ -51,6 +51,9 @@ struct WormShared {
    int wb;                               // 1: the bridge of a close/advance move sits in path[] and goes to the state before the sums
    int ng;                               // gaussians of the coming Levy bridge, drawn as one batch (worm_gauss_batch)
    uint32_t gstate[2][6];                // the worm stream before the batch / after it
+   // the recursion of sample_middle as a node list in its own pre-order (worm_bridge_plan): points relative to the left end
+   short nd_it0[WORM_MAXM + 1], nd_it1[WORM_MAXM + 1], nd_it2[WORM_MAXM + 1], nd_depth[WORM_MAXM + 1];
+   int nnodes, ndepth, gi0;
    double gs[3 * (WORM_MAXM + 1)];       // sqrt(-log u1) cos(2 pi u2), still to be divided by sqrt(alpha)
 };
 
@@ -120,37 +123,45 @@ __device__ __forceinline__ void worm_gauss_batch(const Params &p, WormShared &w,
    if (threadIdx.x == 0) mrg_load(g, w.gstate[1]);
 }
 
-// sample_middle, mc_qworm.cc:240-287, in the recursion's own (pre-)order; thread 0 only.  Points live in the state
-// (path == nullptr; atom0 before the wrap, atom2 after it) or in the proposed path of the swap.  The gaussians come from the
-// batch gs[] (index gi advances in program order).
-__device__ void worm_sample_middle(const Params &p, int c, const double *gs, int &gi, int it0r, int it2r, int atom0r, int atom2r, double *path)
+// sample_middle, mc_qworm.cc:240-287: the recursion (midpoint it1 = rint((it0 + it2)/2), left half first) is laid out by
+// thread 0 as a node list in its own pre-order -- node k consumes the gaussians gi0 + 3k .. gi0 + 3k + 2 exactly as the
+// recursive form does -- and then filled level by level by all threads: nodes of one depth only depend on shallower ones.
+// The bridge lives in path[] (point index = it - it0r), both end points already in place.
+__device__ void worm_bridge_plan(WormShared &w, int it0r, int it2r, int gi0)
 {
-   const int P = p.P, base = p.first[p.worm_type];
-   int stk[16][4], sp = 0;
-   stk[sp][0] = it0r; stk[sp][1] = it2r; stk[sp][2] = atom0r; stk[sp][3] = atom2r; sp++;
+   int stk[16][3], sp = 0, n = 0, maxd = -1;
+   stk[sp][0] = it0r; stk[sp][1] = it2r; stk[sp][2] = 0; sp++;
    while (sp > 0) {
       sp--;
-      const int it0 = stk[sp][0], it2 = stk[sp][1], atom0 = stk[sp][2], atom2 = stk[sp][3];
+      const int it0 = stk[sp][0], it2 = stk[sp][1], dep = stk[sp][2];
       if ((it2 - it0) < 2) continue;
       const int it1 = (int)rint(0.5 * (double)(it0 + it2));
-      const int pt0 = it0 % P, pt1 = it1 % P, pt2 = it2 % P;
-      int atom1 = atom0;
-      if ((pt1 != it1) && (pt0 == it0)) atom1 = atom2;
-      const double s0 = (double)(it1 - it0), s2 = (double)(it2 - it1);
-      const double gkin = (s0 + s2) / (p.worm_twave2 * s0 * s2);
-      #pragma unroll
-      for (int d = 0; d < 3; d++) {
-         double x0, x2;
-         if (path) { x0 = path[(it0 - it0r) * 3 + d]; x2 = path[(it2 - it0r) * 3 + d]; }
-         else { x0 = p.pos[pos_index(p, c, pt0, d, base + atom0)]; x2 = p.pos[pos_index(p, c, pt2, d, base + atom2)]; }
-         double x1 = (s2 * x0 + s0 * x2) / (s0 + s2);
-         x1 += (gs[gi++] / sqrt(gkin));
-         if (path) path[(it1 - it0r) * 3 + d] = x1;
-         else p.pos[pos_index(p, c, pt1, d, base + atom1)] = x1;
-      }
+      w.nd_it0[n] = (short)(it0 - it0r); w.nd_it1[n] = (short)(it1 - it0r); w.nd_it2[n] = (short)(it2 - it0r); w.nd_depth[n] = (short)dep;
+      n++;
+      if (dep > maxd) maxd = dep;
       // left half first, then the right half: push right, then left
-      stk[sp][0] = it1; stk[sp][1] = it2; stk[sp][2] = atom1; stk[sp][3] = atom2; sp++;
-      stk[sp][0] = it0; stk[sp][1] = it1; stk[sp][2] = atom0; stk[sp][3] = atom1; sp++;
+      stk[sp][0] = it1; stk[sp][1] = it2; stk[sp][2] = dep + 1; sp++;
+      stk[sp][0] = it0; stk[sp][1] = it1; stk[sp][2] = dep + 1; sp++;
+   }
+   w.nnodes = n; w.ndepth = maxd + 1; w.gi0 = gi0;
+}
+// all threads, after a barrier that published the plan, the end points and gs[]
+__device__ __forceinline__ void worm_bridge_fill(const Params &p, WormShared &w)
+{
+   const int nn = w.nnodes, nd = w.ndepth, gi0 = w.gi0;
+   for (int dep = 0; dep < nd; dep++) {
+      for (int t = threadIdx.x; t < 3 * nn; t += blockDim.x) {
+         const int k = t / 3, d = t - 3 * k;
+         if (w.nd_depth[k] != dep) continue;
+         const int i0 = w.nd_it0[k], i1 = w.nd_it1[k], i2 = w.nd_it2[k];
+         const double s0 = (double)(i1 - i0), s2 = (double)(i2 - i1);
+         const double gkin = (s0 + s2) / (p.worm_twave2 * s0 * s2);
+         const double x0 = w.path[i0 * 3 + d], x2 = w.path[i2 * 3 + d];
+         double x1 = (s2 * x0 + s0 * x2) / (s0 + s2);
+         x1 += (w.gs[gi0 + 3 * k + d] / sqrt(gkin));
+         w.path[i1 * 3 + d] = x1;
+      }
+      __syncthreads();
    }
 }
 
@@ -278,6 +289,7 @@ __device__ void worm_sweep_cta(const Params &p, const SmallTables &t, int c, dou
          qw[14] += 1.0;
          w.go = 0;
          w.wb = 0;
+         w.nnodes = 0; w.ndepth = 0;
          if (w.st[0]) {                                     // qworm_close, mc_qworm.cc:184-238
             qw[QW_CLOSE] += 1.0;
             if (segm <= p.worm_m) {
@@ -288,7 +300,7 @@ __device__ void worm_sweep_cta(const Params &p, const SmallTables &t, int c, dou
                   w.path[d] = p.pos[pos_index(p, c, w.st[1], d, base + w.st[3])];
                   w.path[segm * 3 + d] = p.pos[pos_index(p, c, w.st[2], d, base + w.st[4])];
                }
-               worm_sample_middle(p, c, w.gs, gi, w.st[1], w.st[1] + segm, w.st[3], w.st[4], w.path);
+               worm_bridge_plan(w, w.st[1], w.st[1] + segm, 0);
                w.wb = 1;
                w.go = 1;
             }
@@ -306,6 +318,7 @@ __device__ void worm_sweep_cta(const Params &p, const SmallTables &t, int c, dou
       }
       __syncthreads();
       if (w.go) {
+         worm_bridge_fill(p, w);
          worm_write_back(p, c, w);
          // qw_open_prob, mc_qworm.cc:127-153
          const double pot = worm_pot_sum<KIND>(p, t, c, w, red);
@@ -351,6 +364,7 @@ __device__ void worm_sweep_cta(const Params &p, const SmallTables &t, int c, dou
             qw[14] += 1.0;
             w.go = 0;
             w.wb = 0;
+            w.nnodes = 0; w.ndepth = 0;
             if (r > 0.5) {                                  // qworm_advance, mc_qworm.cc:299-357
                qw[QW_ADVANCE] += 1.0;
                const int advance = steps;
@@ -366,7 +380,7 @@ __device__ void worm_sweep_cta(const Params &p, const SmallTables &t, int c, dou
                      w.path[d] = p.pos[pos_index(p, c, it0 % P, d, base + w.st[3])];
                      w.path[advance * 3 + d] = w.path[d] + (w.gs[gi++] / sqrt(gvar));          // the new head
                   }
-                  worm_sample_middle(p, c, w.gs, gi, it0, it2, w.st[3], atom_i_new, w.path);
+                  worm_bridge_plan(w, it0, it2, gi);
                   w.it0 = it0; w.it1 = it2 + 1; w.atom0 = w.st[3]; w.atom1 = atom_i_new; w.use_path = 0; w.diff = 0;
                   w.wb = 1;
                   w.go = 1;
@@ -388,6 +402,7 @@ __device__ void worm_sweep_cta(const Params &p, const SmallTables &t, int c, dou
          }
          __syncthreads();
          if (w.go) {
+            worm_bridge_fill(p, w);
             worm_write_back(p, c, w);
             const double pot = worm_pot_sum<KIND>(p, t, c, w, red);
             if (tid == 0) {
@@ -446,13 +461,13 @@ __device__ void worm_sweep_cta(const Params &p, const SmallTables &t, int c, dou
             worm_gauss_batch(p, w, g);
             if (tid == 0 && sw_atom1 >= 0) {
                const int sg = p.worm_m, it0 = w.st[1], it1 = it0 + sg;
-               gi = 0;
-               worm_sample_middle(p, c, w.gs, gi, it0, it1, sw_atom0, sw_atom1, w.path);
+               worm_bridge_plan(w, it0, it1, 0);
                w.it0 = it0; w.it1 = it1; w.atom0 = sw_atom0; w.atom1 = sw_atom1; w.use_path = 1; w.diff = 1;
                w.go = 1;
             }
             __syncthreads();
             if (w.go) {
+               worm_bridge_fill(p, w);
                const double pot = worm_pot_sum<KIND>(p, t, c, w, red);
                const int count2 = worm_get_ptable(p, c, w, w.atom0, w.it0, w.it1 % P, p.worm_m, w.it1, dr2_list, atm_list, ptable, seen);
                if (tid == 0) {
