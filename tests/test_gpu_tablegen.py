@@ -263,6 +263,21 @@ def test_pimc_tables_cli_reproduces_reference_files_and_log(pkg, gpu, tmp_path):
     assert np.all(np.abs(mine - f["rho"]) <= 1.01 * ulp8(f["rho"]) + 1e-13 * rmax)
     reg = open(tmp_path / "rho.den010").readline()
     assert reg.startswith("   10    0    0  0.62732329E+01  0.26821019E+01 -0.14376686E+04") or reg.startswith("   10    0    0  0.6273232")
+    # symmetric top: symtop_prop/a-run, compared with symtop_prop/rho.den010_rho; --table concatenates like compile.x
+    out = subprocess.run([exe, "symrho", "0.37", "128", "1", "10", "10", "0.5", "0.3", "66"], cwd=tmp_path, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "ztau=" in out.stdout, out.stdout + out.stderr
+    fs = np.load(os.path.join(GOLD, "ref_symrho_den010.npz"))
+    mine = np.loadtxt(tmp_path / "rho.den010_rho").reshape(361, 361)
+    assert np.all(np.abs(mine - fs["rho"]) <= 1.01 * ulp8(fs["rho"]) + 1e-14 * np.abs(fs["rho"]).max())
+    sub = tmp_path / "full"
+    sub.mkdir()
+    out = subprocess.run([exe, "symrho", "5", "4", "1", "0", "180", "5.0", "2.5", "20", "--table", "X_T5t4"], cwd=sub, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert os.path.getsize(sub / "X_T5t4.rho") == 181 * 361 * 361 * 16 == os.path.getsize(sub / "X_T5t4.esq")
+    cat = b"".join(open(sub / f"rho.den{i:03d}_eng", "rb").read() for i in (0, 1, 180))
+    full = open(sub / "X_T5t4.eng", "rb").read()
+    n1 = 361 * 361 * 16
+    assert full[:2 * n1] == cat[:2 * n1] and full[-n1:] == cat[-n1:]
     # usage / error paths
     bad = subprocess.run([exe, "asymrho", "300", "1", "-1", "0", "0", "0.6666525", "0.2306476", "0.1769383", "10"], cwd=tmp_path, capture_output=True, text=True)
     assert bad.returncode == 1 and "too large contribution from emax" in bad.stdout
