@@ -61,6 +61,11 @@ est_energy_kernel(const __grid_constant__ Params p, const __grid_constant__ EstB
    const int P = p.P, N = p.N, Q = p.Q;
    const int gt = b * blockDim.x + threadIdx.x, nt = EST_BLOCKS * blockDim.x;
    if (p.worm_on && p.wstate[(size_t)c * 8]) return;      // G sector: no estimators (mc_main.cc:389-391, mc_estim.cc:506-507)
+   // the pair-distance histogram gets P N(N-1)/2 counts per chain and measurement on a few hundred bins: count in shared
+   // memory (integers, so the result does not depend on the order) and flush once per block
+   __shared__ unsigned int h1[BINSR];
+   for (int i = threadIdx.x; i < BINSR; i += blockDim.x) h1[i] = 0u;
+   __syncthreads();
    SmallTables t;
    t.g1d = p.g1d; t.v1d = p.v1d; t.y2_1d = p.y2_1d; t.lut1d = p.lut1d;
    t.rgrid = p.rgrid; t.rdens = p.rdens; t.rdens2 = p.rdens2; t.lutrot = p.lutrot;
@@ -152,11 +157,14 @@ est_energy_kernel(const __grid_constant__ Params p, const __grid_constant__ EstB
          pot += caleng(sa, sb);
       } else {
          double r = sqrt(dr2);
-         if (with_dens) { int br; bin_r(e, r, &br); if (br < BINSR && br >= 0) atomicAdd(e.acc + e.off_gr1d + br, 1.0); }
+         if (with_dens) { int br; bin_r(e, r, &br); if (br < BINSR && br >= 0) atomicAdd(&h1[br], 1u); }
          pot += spot1d(p, t, r);
       }
    }
    pot = block_sum(pot, red);
+   __syncthreads();
+   for (int i = threadIdx.x; i < BINSR; i += blockDim.x)
+      if (h1[i]) atomicAdd(e.acc + e.off_gr1d + i, (double)h1[i]);
 
    // ---- GetRotE3D (mc_estim.cc:989-1096) / GetRotEnergy (:939-987), RotDenType 0
    double srot = 0.0, sesq = 0.0, sterm = 0.0;
