@@ -496,6 +496,7 @@ __device__ void worm_sweep_cta(const Params &p, const SmallTables &t, int c, dou
                      const double va = p.pos[a], vb = p.pos[b];
                      p.pos[a] = vb; p.pos[b] = va;
                   }
+                  __syncthreads();          // every thread has read the move's description before thread 0 updates the worm
                   if (tid == 0) {
                      qw[7 + QW_SWAP] += 1.0;
                      const int ratomw = rindex[base + atomw] - base, ratom0 = rindex[base + atom0] - base;
