@@ -248,3 +248,37 @@ def test_cxx_driver_worm_deck_and_restart(pkg, tmp_path):
     eng = np.loadtxt(tmp_path / "gr.eng", ndmin=2)
     assert list(eng[:, 0]) == [2, 3, 4, 5, 6]
     assert open(tmp_path / "yw001.stat").read().split() == ["STARTBLOCK", "6"]
+
+
+def test_cxx_driver_two_ranks_equal_one_rank(pkg, tmp_path):
+    """pimc_b200 as two processes (RANK/WORLD_SIZE, one GPU each, NCCL all-reduce of the accumulator buffer per block) on
+    2 x 16 chains writes the same .eng / .rcf rows as one process with 32 chains: global chain c owns the same MRG32k3a
+    streams in both layouts and the block sums are formed after the reduction."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    drv = os.path.join(ROOT, "moribs-pimc_b200", "driver", "pimc_b200")
+    if not os.path.exists(drv):
+        pytest.skip("driver binary not built")
+    d = os.path.join(pkg.configs.DECKS, "CO2_100K_4_4")
+    deck = open(os.path.join(d, "qmc.input")).read().replace("NUMBEROFBLOCKS     2000  500", "NUMBEROFBLOCKS     5  1")
+    deck = deck.replace("OUTPUTDIR        ./g4/1/", "OUTPUTDIR        ./")
+    runs = {}
+    for name, ranks, chains in (("one", 1, 32), ("two", 2, 16)):
+        w = tmp_path / name
+        w.mkdir()
+        for f in ("CO2_T100t4.rot", "CO2_fake.pot"):
+            shutil.copy(os.path.join(d, f), w)
+        open(w / "qmc.input", "w").write(deck)
+        procs = []
+        for r in range(ranks):
+            env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(ranks))
+            procs.append(subprocess.Popen([drv, "--chains", str(chains)], cwd=w, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+        outs = [p.communicate(timeout=600)[0] for p in procs]
+        assert all(p.returncode == 0 for p in procs), "\n".join(o[-1500:] for o in outs)
+        runs[name] = w
+    for f in ("CO2_monomer.eng", "CO2_monomer_sum.eng", "CO2_monomer005.rcf", "CO2_monomer_sum.rcf"):
+        a, b = np.loadtxt(runs["one"] / f), np.loadtxt(runs["two"] / f)
+        assert a.shape == b.shape and a.shape[0] >= 4
+        assert np.allclose(a, b, rtol=2e-6, atol=1e-12), f      # six printed digits; sums differ only by the order of the reduction
+    assert np.loadtxt(runs["one"] / "CO2_monomer.eng").shape == (4, 10)
