@@ -289,3 +289,53 @@ def test_cxx_driver_two_ranks_equal_one_rank(pkg, tmp_path):
         assert a.shape == b.shape and a.shape[0] >= 4
         assert np.allclose(a, b, rtol=2e-6, atol=1e-12), f      # six printed digits; sums differ only by the order of the reduction
     assert np.loadtxt(runs["one"] / "CO2_monomer.eng").shape == (4, 10)
+
+
+def test_cxx_driver_top_deck_with_generated_tables(pkg, tmp_path):
+    """pimc_b200 on the reference's own CPU-runnable example examples/MF_1He_0.37K_512_128 (BASELINE configs[0]): its
+    ROTDENSI line switched on so that the missing HCOOCH3_T0.37t128.rho/.eng/.esq are generated on the device and written
+    under the reference's names, a small synthetic atom-top table in the 3-D file format of README.md:125-149 for the
+    git-LFS potential, REFLECTY as in the deck.  Checks the top branch of the driver end to end: table files, .eng, the 3-D
+    density files of a non-linear dopant, exchange / area files of the single boson, checkpoint files."""
+    drv = os.path.join(ROOT, "moribs-pimc_b200", "driver", "pimc_b200")
+    if not os.path.exists(drv):
+        pytest.skip("driver binary not built")
+    d = os.path.join(pkg.configs.DECKS, "MF_1He_0.37K_512_128")
+    shutil.copy(os.path.join(d, "helium.pot"), tmp_path)
+    rg, thg, chg = 41, 181, 91
+    v = pkg.configs.synth_pot3d(rg, thg, chg, 4.0, 20.0)
+    with open(tmp_path / "MFHe_09_AF.pot", "w") as f:
+        f.write(f"{rg} {thg} {chg} 4.0 20.0\n")
+        np.savetxt(f, v, fmt="%.10e")
+    deck = open(os.path.join(d, "qmc.input")).read()
+    assert "#ROTDENSI 0  -1 0.0 0.6666525 0.1769383 0.2306476 1" in deck
+    deck = deck.replace("#ROTDENSI 0  -1 0.0 0.6666525 0.1769383 0.2306476 1", "ROTDENSI 0  -1 0.0 0.6666525 0.1769383 0.2306476 1")
+    deck = deck.replace("OUTPUTDIR        ./g512/1/", "OUTPUTDIR        ./").replace("NUMBEROFPASSES     200 ", "NUMBEROFPASSES     4 ")
+    deck = deck.replace("NUMBEROFBLOCKS     4000   10 ", "NUMBEROFBLOCKS     3   1 ")
+    assert "NUMBEROFBLOCKS     3   1" in deck and "NUMBEROFPASSES     4" in deck
+    open(tmp_path / "qmc.input", "w").write(deck)
+    env = dict(os.environ, PIMC_G3D_LAST_ONLY="1")
+    out = subprocess.run([drv, "--chains", "32"], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+    assert "generating the tables on the device (asymrho: A=0.666653 B=0.230648 C=0.176938 cm-1, maxj=83)" in out.stdout
+    try:
+        for ext in ("rho", "eng", "esq"):
+            assert os.path.getsize(tmp_path / f"HCOOCH3_T0.37t128.{ext}") == 181 * 361 * 361 * 16
+        head = open(tmp_path / "HCOOCH3_T0.37t128.rho").readline()
+        rho0 = float(head)
+        assert abs(rho0 - 25.7487) < 2e-3                      # rho(identity) = Z(tau)/8 pi^2 of nmv_prop/log: 2033.04 / 78.957
+        eng = np.loadtxt(tmp_path / "HCOOCH3_He.eng", ndmin=2)
+        assert eng.shape == (2, 10) and list(eng[:, 0]) == [2, 3] and np.all(np.isfinite(eng))
+        assert np.all(eng[:, 2] < 0.0)                          # the He atom sits in the well of the synthetic potential
+        for f in ("HCOOCH3_He002.gra", "HCOOCH3_He002.gri", "HCOOCH3_He002.grt", "HCOOCH3_He002.grc", "HCOOCH3_He002.gtc", "HCOOCH3_He_sum.g3d",
+                  "HCOOCH3_He_sum.gri", "HCOOCH3_He_sum.eulphi", "HCOOCH3_He_sum.eulthe", "HCOOCH3_He002.rcf", "HCOOCH3_He.prl", "HCOOCH3_He.sffs3d",
+                  "HCOOCH3_He.mffs3d", "HCOOCH3_He002.xyz", "HCOOCH3_He.xyz", "yw001.stat", "yw001.conf", "yw001.tabl", "yw001.b200"):
+            assert os.path.exists(tmp_path / f), f
+        gri = np.loadtxt(tmp_path / "HCOOCH3_He_sum.gri")
+        assert gri.shape == (300, 3) and abs(gri[:, 1].sum() * 0.05 - 1.0) < 0.02 and np.all(gri[:, 2] == 0.0)   # one He within 15 A; no top-top density
+        g3d = os.path.getsize(tmp_path / "HCOOCH3_He_sum.g3d")
+        assert g3d == 300 * 50 * 100 * (8 * 17 + 1)              # two species columns x (r, theta, chi, density) per grid line
+    finally:
+        for f in os.listdir(tmp_path):
+            if os.path.getsize(tmp_path / f) > 50_000_000:
+                os.remove(tmp_path / f)
