@@ -317,7 +317,7 @@ def test_cxx_driver_top_deck_with_generated_tables(pkg, tmp_path):
     env = dict(os.environ, PIMC_G3D_LAST_ONLY="1")
     out = subprocess.run([drv, "--chains", "32"], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
-    assert "generating the tables on the device (asymrho: A=" in out.stdout and "maxj=83)" in out.stdout
+    assert "generating the tables on the device (asymrho: A=" in out.stdout and "maxj=84)" in out.stdout
     try:
         for ext in ("rho", "eng", "esq"):
             assert os.path.getsize(tmp_path / f"HCOOCH3_T0.37t128.{ext}") == 181 * 361 * 361 * 16
