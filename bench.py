@@ -296,18 +296,16 @@ def main():
     # ---- end to end through the C ABI with host buffers: upload -> pass -> estimators -> (all-reduce) -> download ----
     # host state lives in pinned buffers allocated once, as the reference's MCCoords / MCAngles do (mc_setup.cc:135-163)
     n_beads = s.N * P
-    pinned = [(torch.empty((3, n_beads), dtype=torch.float64, pin_memory=True), torch.empty((3, n_beads), dtype=torch.float64, pin_memory=True))
-              for _ in range(chains)]
-    host = [(pc.numpy(), pa.numpy()) for pc, pa in pinned]
-    for c in range(chains):
-        G.download_into(c, host[c][0], host[c][1])
+    pin_c = torch.empty((chains, 3, n_beads), dtype=torch.float64, pin_memory=True)
+    pin_a = torch.empty((chains, 3, n_beads), dtype=torch.float64, pin_memory=True)
+    host_c, host_a = pin_c.numpy(), pin_a.numpy()
+    G.download_all_into(host_c, host_a)
     h2d = chains * ((P * 3 * ((s.N + 3) // 4 * 4) + 2 * max(1, s.Q) * 3 * max(1, sum(t.numb for t in s.types if t.molecule))) * 8 + (3 * s.N + 3) * 4)
     d2h = h2d - chains * (3 * s.N + 3) * 4 + lay["n_total"] * 8
     barrier()
     w0 = time.perf_counter()
     for _ in range(args.steps):
-        for c in range(chains):
-            G.upload(c, host[c][0], host[c][1], cfg.perm)
+        G.upload_all(host_c, host_a, cfg.perm)                  # every chain's beads, angles and permutation: one call
         G.accum_reset()
         G.steps(P, sync=False)
         G.measure()
@@ -318,8 +316,7 @@ def main():
             torch.cuda.current_stream().synchronize()
         G.sync()
         accum, _ = G.accum_download()
-        for c in range(chains):
-            G.download_into(c, host[c][0], host[c][1])
+        G.download_all_into(host_c, host_a)
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - w0
     if dist:

@@ -114,6 +114,11 @@ const char *pimcgpu_last_error(void);
 int pimcgpu_upload_state(int chain, const double *coords, const double *angles, const int *pindex);
 int pimcgpu_download_state(int chain, double *coords, double *angles, double *cosine, int *pindex);
 
+/* the same for chains first .. first+count-1 in one call: arrays [count][3][N*P], pindex [count][numb of the BOSE species] or
+ * NULL (identity); one host<->device copy and one transposing kernel for the whole batch instead of per-chain round trips   */
+int pimcgpu_upload_states(int first, int count, const double *coords, const double *angles, const int *pindex);
+int pimcgpu_download_states(int first, int count, double *coords, double *angles, double *cosine);
+
 /* ---- MRG32k3a package seed: RngStream::SetPackageSeed (rngstream.cc:346-353) ---- */
 int pimcgpu_seed(const unsigned long seed6[6]);
 

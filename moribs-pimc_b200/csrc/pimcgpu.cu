@@ -59,6 +59,7 @@ struct Context {
    double *stage = nullptr;         // pinned host staging: [c][pos | ang | cosn] in the device layout
    size_t stage_chain = 0;          // doubles per chain in `stage`
    double *d_raw = nullptr;         // device scratch [3][N*P]: one chain's beads in the reference layout (import/export transposes)
+   double *d_raw_all = nullptr;     // the same for every chain (batched pimcgpu_upload_states / _download_states), allocated on first use
 } G;
 
 template <class T> int dalloc(T **ptr, size_t n)
@@ -566,8 +567,10 @@ namespace {
 __global__ void state_transpose_kernel(double *pos, double *raw, int N, int P, int Npad, int to_device)
 {
    __shared__ double tile[32][33];
-   const int d = blockIdx.z, it0 = blockIdx.x * 32, a0 = blockIdx.y * 32;
+   const int d = blockIdx.z % 3, it0 = blockIdx.x * 32, a0 = blockIdx.y * 32;
    const size_t n = (size_t)N * P;
+   pos += (size_t)(blockIdx.z / 3) * P * 3 * Npad;          // blockIdx.z = 3 * chain + dim: consecutive chains of a batch
+   raw += (size_t)(blockIdx.z / 3) * 3 * n;
    if (to_device) {
       for (int r = threadIdx.y; r < 32; r += blockDim.y) {          // r: atom in tile, x: slice
          const int a = a0 + r, it = it0 + threadIdx.x;
@@ -691,6 +694,124 @@ int pimcgpu_download_state(int chain, double *coords, double *angles, double *co
    if (pindex && p.bstype >= 0) {
       CK(cudaMemcpy(G.h_pindex.data() + (size_t)chain * p.N, p.pindex + (size_t)chain * p.N, p.N * sizeof(int), cudaMemcpyDeviceToHost));   // the worm's swaps change it
       for (int a = 0; a < p.numb[p.bstype]; a++) pindex[a] = G.h_pindex[(size_t)chain * p.N + p.first[p.bstype] + a] - p.first[p.bstype];
+   }
+   return 0;
+}
+
+// ---- batched state transfer: chains first .. first+count-1 in one go (arrays [count][3][N*P], permutations [count][nb]) ----
+static int permutation_tables(const Params &p, const int *pindex, int *gp, int *gr, int *cstart, int *catoms, int *ncyc, const char *who)
+{
+   for (int a = 0; a < p.N; a++) gp[a] = a;
+   if (pindex && p.bstype >= 0)
+      for (int a = 0; a < p.numb[p.bstype]; a++) {
+         if (pindex[a] < 0 || pindex[a] >= p.numb[p.bstype]) return fail("%s: bad permutation entry", who);
+         gp[p.first[p.bstype] + a] = p.first[p.bstype] + pindex[a];
+      }
+   for (int a = 0; a < p.N; a++) gr[gp[a]] = a;
+   std::vector<char> seen(p.N, 0);
+   int ns = 0, na = 0;
+   for (int t = 0; t < MAXT; t++) ncyc[t] = 0;
+   for (int t = 0; t < p.ntypes; t++)
+      for (int a = p.first[t]; a < p.first[t] + p.numb[t]; a++) {
+         if (seen[a]) continue;
+         cstart[ns++] = na;
+         int b = a, guard = 0;
+         do { catoms[na++] = b; seen[b] = 1; b = gp[b]; } while (b != a && ++guard <= p.N);
+         if (b != a) return fail("%s: permutation is not a bijection", who);
+         ncyc[t]++;
+      }
+   while (ns < p.N + 1) cstart[ns++] = na;
+   return 0;
+}
+
+int pimcgpu_upload_states(int first, int count, const double *coords, const double *angles, const int *pindex)
+{
+   if (!G.live) return fail("pimcgpu_upload_states: not initialised");
+   const Params &p = G.p;
+   if (first < 0 || count < 1 || first + count > p.nchains) return fail("pimcgpu_upload_states: chains %d..%d out of range", first, first + count - 1);
+   const size_t n = (size_t)p.N * p.P;
+   const size_t npos = (size_t)p.P * 3 * p.Npad, nang = (size_t)std::max(1, p.Q) * 3 * p.NMpad;
+   if (!G.d_raw_all && dalloc(&G.d_raw_all, (size_t)p.nchains * 3 * n)) return 1;
+   CK(cudaStreamSynchronize(G.stream));          // the staging area may still be in flight
+   CK(cudaMemcpyAsync(G.d_raw_all, coords, (size_t)count * 3 * n * sizeof(double), cudaMemcpyHostToDevice, G.stream));
+   state_transpose_kernel<<<dim3((p.P + 31) / 32, (p.N + 31) / 32, 3 * count), dim3(32, 8), 0, G.stream>>>(p.pos + (size_t)first * npos, G.d_raw_all, p.N, p.P, p.Npad, 1);
+   CK(cudaGetLastError());
+   if (p.imtype >= 0) {
+      #pragma omp parallel for schedule(static)
+      for (int cc = 0; cc < count; cc++) {
+         double *hang = G.stage + (size_t)(first + cc) * G.stage_chain + npos, *hcos = hang + nang;
+         const double *ang = angles + (size_t)cc * 3 * n;
+         for (int q = 0; q < p.Q; q++)
+            for (int m = 0; m < p.NM; m++) {
+               const size_t src = (size_t)(p.first[p.imtype] + m) * p.P + q;
+               const double phi = ang[0 * n + src], cost = ang[1 * n + src], chi = ang[2 * n + src];
+               const double sint = sqrt(1.0 - cost * cost);         // MCCosine from (phi, cos theta), mc_main.cc:192-199
+               const size_t b = (size_t)q * 3 * p.NMpad + m;
+               hang[b] = phi; hang[b + p.NMpad] = cost; hang[b + 2 * p.NMpad] = chi;
+               hcos[b] = sint * cos(phi); hcos[b + p.NMpad] = sint * sin(phi); hcos[b + 2 * p.NMpad] = cost;
+            }
+      }
+      const double *s0 = G.stage + (size_t)first * G.stage_chain + npos;
+      CK(cudaMemcpy2DAsync(p.ang + (size_t)first * nang, nang * sizeof(double), s0, G.stage_chain * sizeof(double), nang * sizeof(double), count, cudaMemcpyHostToDevice, G.stream));
+      CK(cudaMemcpy2DAsync(p.cosn + (size_t)first * nang, nang * sizeof(double), s0 + nang, G.stage_chain * sizeof(double), nang * sizeof(double), count, cudaMemcpyHostToDevice, G.stream));
+   }
+   const int nb = p.bstype >= 0 ? p.numb[p.bstype] : 0;
+   std::vector<int> gp((size_t)count * p.N), gr((size_t)count * p.N), cst((size_t)count * (p.N + 1)), cat((size_t)count * p.N), ncy((size_t)count * MAXT);
+   for (int cc = 0; cc < count; cc++)
+      if (permutation_tables(p, pindex ? pindex + (size_t)cc * nb : nullptr, &gp[(size_t)cc * p.N], &gr[(size_t)cc * p.N], &cst[(size_t)cc * (p.N + 1)],
+                             &cat[(size_t)cc * p.N], &ncy[(size_t)cc * MAXT], "pimcgpu_upload_states")) return 1;
+   CK(cudaMemcpyAsync(p.pindex + (size_t)first * p.N, gp.data(), gp.size() * sizeof(int), cudaMemcpyHostToDevice, G.stream));
+   CK(cudaMemcpyAsync(p.rindex + (size_t)first * p.N, gr.data(), gr.size() * sizeof(int), cudaMemcpyHostToDevice, G.stream));
+   CK(cudaMemcpyAsync(p.cyc_start + (size_t)first * (p.N + 1), cst.data(), cst.size() * sizeof(int), cudaMemcpyHostToDevice, G.stream));
+   CK(cudaMemcpyAsync(p.cyc_atoms + (size_t)first * p.N, cat.data(), cat.size() * sizeof(int), cudaMemcpyHostToDevice, G.stream));
+   CK(cudaMemcpyAsync(p.ncyc + (size_t)first * MAXT, ncy.data(), ncy.size() * sizeof(int), cudaMemcpyHostToDevice, G.stream));
+   CK(cudaMemsetAsync(p.wstate + (size_t)first * 8, 0, (size_t)count * 8 * sizeof(int), G.stream));                          // uploaded paths are closed
+   CK(cudaMemsetAsync(p.vepoch + (size_t)first * std::max(1, p.Q) * p.NMpad, 0xff, (size_t)count * std::max(1, p.Q) * p.NMpad * sizeof(int), G.stream));
+   std::copy(gp.begin(), gp.end(), G.h_pindex.begin() + (size_t)first * p.N);
+   CK(cudaStreamSynchronize(G.stream));
+   return 0;
+}
+
+int pimcgpu_download_states(int first, int count, double *coords, double *angles, double *cosine)
+{
+   if (!G.live) return fail("pimcgpu_download_states: not initialised");
+   const Params &p = G.p;
+   if (first < 0 || count < 1 || first + count > p.nchains) return fail("pimcgpu_download_states: chains %d..%d out of range", first, first + count - 1);
+   const size_t n = (size_t)p.N * p.P;
+   const size_t npos = (size_t)p.P * 3 * p.Npad, nang = (size_t)std::max(1, p.Q) * 3 * p.NMpad;
+   if (!G.d_raw_all && dalloc(&G.d_raw_all, (size_t)p.nchains * 3 * n)) return 1;
+   if (coords) {
+      state_transpose_kernel<<<dim3((p.P + 31) / 32, (p.N + 31) / 32, 3 * count), dim3(32, 8), 0, G.stream>>>(p.pos + (size_t)first * npos, G.d_raw_all, p.N, p.P, p.Npad, 0);
+      CK(cudaGetLastError());
+      CK(cudaMemcpyAsync(coords, G.d_raw_all, (size_t)count * 3 * n * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
+   }
+   double *s0 = G.stage + (size_t)first * G.stage_chain + npos;
+   if (angles || cosine) {
+      CK(cudaMemcpy2DAsync(s0, G.stage_chain * sizeof(double), p.ang + (size_t)first * nang, nang * sizeof(double), nang * sizeof(double), count, cudaMemcpyDeviceToHost, G.stream));
+      CK(cudaMemcpy2DAsync(s0 + nang, G.stage_chain * sizeof(double), p.cosn + (size_t)first * nang, nang * sizeof(double), nang * sizeof(double), count, cudaMemcpyDeviceToHost, G.stream));
+   }
+   CK(cudaStreamSynchronize(G.stream));
+   if (angles || cosine) {
+      // rotor rows: only the first Q entries carry angles; the rest keep phi = 0, cos(theta) = 1, chi = 0 (MCConfigInit, mc_setup.cc:471-487)
+      #pragma omp parallel for schedule(static)
+      for (int cc = 0; cc < count; cc++) {
+         const double *hang = G.stage + (size_t)(first + cc) * G.stage_chain + npos, *hcos = hang + nang;
+         double *ang = angles ? angles + (size_t)cc * 3 * n : nullptr, *cs = cosine ? cosine + (size_t)cc * 3 * n : nullptr;
+         for (int d = 0; d < 3; d++)
+            for (size_t i = 0; i < n; i++) {
+               if (ang) ang[d * n + i] = (d == 1) ? 1.0 : 0.0;
+               if (cs) cs[d * n + i] = (d == 2) ? 1.0 : 0.0;
+            }
+         if (p.imtype >= 0)
+            for (int q = 0; q < p.Q; q++)
+               for (int m = 0; m < p.NM; m++) {
+                  const size_t dst = (size_t)(p.first[p.imtype] + m) * p.P + q, b = (size_t)q * 3 * p.NMpad + m;
+                  for (int d = 0; d < 3; d++) {
+                     if (ang) ang[d * n + dst] = hang[b + d * p.NMpad];
+                     if (cs) cs[d * n + dst] = hcos[b + d * p.NMpad];
+                  }
+               }
+      }
    }
    return 0;
 }

@@ -27,6 +27,7 @@ EXPORTS = [
     "pimcgpu_pot_energy_slice", "pimcgpu_rng_draws", "pimcgpu_fp64_peak", "pimcgpu_host_spline",
     "pimcgpu_host_stream_state", "pimcgpu_host_lut", "pimcgpu_accum_offset", "pimcgpu_symmetry_moves", "pimcgpu_symmetry_ops",
     "pimcgpu_checkpoint_bytes", "pimcgpu_checkpoint_save", "pimcgpu_checkpoint_load", "pimcgpu_chain_areas", "pimcgpu_worm_moves", "pimcgpu_worm_state", "pimcgpu_worm_set", "pimcgpu_worm_counters",
+    "pimcgpu_upload_states", "pimcgpu_download_states",
     "pimcgpu_gen_asymrho", "pimcgpu_gen_symrho", "pimcgpu_gen_linden", "pimcgpu_gen_wigner_d", "pimcgpu_gen_timing",
     "pimcgpu_format_e15_8", "pimcgpu_write_e15_8", "pimcgpu_write_rot",
 ]
@@ -283,6 +284,22 @@ class PimcGpu:
         """download_state into caller-owned arrays [3][N*P] (e.g. pinned host memory that lives across steps, like the
         reference's MCCoords / MCAngles / MCCosine which are allocated once, mc_setup.cc:135-163)"""
         _ck(self.L.pimcgpu_download_state(C.c_int(chain), _dp(coords), _dp(angles), _dp(cosine), None))
+
+    def upload_all(self, coords, angles, perm=None, first=0):
+        """batched upload: coords/angles [count][3][N*P] (contiguous), perm [count][nb] or one permutation for all chains or None"""
+        c = np.ascontiguousarray(coords, dtype=np.float64)
+        a = np.ascontiguousarray(angles, dtype=np.float64)
+        count = c.shape[0]
+        p = None
+        if perm is not None:
+            p = np.ascontiguousarray(perm, dtype=np.int32)
+            if p.ndim == 1:
+                p = np.ascontiguousarray(np.tile(p, (count, 1)))
+        _ck(self.L.pimcgpu_upload_states(C.c_int(first), C.c_int(count), _dp(c), _dp(a), _ip(p)))
+
+    def download_all_into(self, coords, angles, cosine=None, first=0):
+        """batched download into caller-owned contiguous arrays [count][3][N*P]"""
+        _ck(self.L.pimcgpu_download_states(C.c_int(first), C.c_int(coords.shape[0]), _dp(coords), _dp(angles), _dp(cosine)))
 
     def seed(self, seed6=(12345,) * 6):
         _ck(self.L.pimcgpu_seed((C.c_ulong * 6)(*seed6)))

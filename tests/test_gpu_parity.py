@@ -343,3 +343,46 @@ def test_minimum_image_and_error_paths(pkg):
     with pytest.raises(pkg.gpu.PimcGpuError):
         G.seed((0, 0, 0, 1, 2, 3))                                   # CheckSeed: first triple all zero
     G.close()
+
+
+def test_batched_state_transfer_equals_per_chain_calls(pkg):
+    """pimcgpu_upload_states / pimcgpu_download_states move every chain in one call (one copy + one transposing kernel);
+    the device state and the trajectory that follows must be those of the per-chain entry points."""
+    cfg = make(pkg, "C2")
+    s = cfg.system
+    n, C = s.N * s.P, 5
+    rng = np.random.default_rng(3)
+    nb = s.types[0].numb
+    coords = np.stack([cfg.coords + 0.01 * rng.standard_normal(cfg.coords.shape) for _ in range(C)])
+    angles = np.stack([cfg.angles.copy() for _ in range(C)])
+    rot0 = nb * s.P
+    for c in range(C):
+        angles[c, 0, rot0:rot0 + s.Q] = rng.uniform(0, 2 * np.pi, s.Q)
+        angles[c, 1, rot0:rot0 + s.Q] = rng.uniform(-0.9, 0.9, s.Q)
+        angles[c, 2, rot0:rot0 + s.Q] = rng.uniform(0, 2 * np.pi, s.Q)
+    perms = np.stack([rng.permutation(nb) for _ in range(C)]).astype(np.int32)
+    results = []
+    for batched in (True, False):
+        G = pkg.gpu.PimcGpu(cfg, nchains=C)
+        if batched:
+            G.upload_all(coords, angles, perms)
+        else:
+            for c in range(C):
+                G.upload(c, coords[c], angles[c], perms[c])
+        # what was uploaded comes back, through either download path
+        ca, aa, sa = (np.zeros((C, 3, n)) for _ in range(3))
+        G.download_all_into(ca, aa, sa)
+        for c in range(C):
+            c1, a1, s1 = G.download(c)
+            assert np.array_equal(c1, ca[c]) and np.array_equal(a1, aa[c]) and np.array_equal(s1, sa[c])
+            assert np.array_equal(c1, coords[c])
+            assert np.array_equal(a1[:, rot0:rot0 + s.Q], angles[c][:, rot0:rot0 + s.Q])
+            assert np.array_equal(G.download_perm(c), perms[c])
+        G.seed((21, 22, 23, 24, 25, 26))
+        G.steps(s.P + 7)
+        G.download_all_into(ca, aa, sa)
+        results.append((ca.copy(), aa.copy(), G.counters()))
+        G.close()
+    assert np.array_equal(results[0][0], results[1][0]) and np.array_equal(results[0][1], results[1][1])
+    assert np.array_equal(results[0][2][0], results[1][2][0]) and np.array_equal(results[0][2][1], results[1][2][1])
+    assert results[0][2][1].sum() > 0
