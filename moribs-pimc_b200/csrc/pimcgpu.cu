@@ -239,6 +239,7 @@ void pimcgpu_finalize(void)
    cudaStreamSynchronize(G.stream);
    for (void *q : G.allocs) cudaFree(q);
    G.allocs.clear();
+   G.d_raw = nullptr; G.d_raw_all = nullptr;          // lazily allocated scratch belongs to the context that is going away
    if (G.stream) cudaStreamDestroy(G.stream);
    G.stream = nullptr;
    if (G.stage) cudaFreeHost(G.stage);
