@@ -418,6 +418,7 @@ int main(int argc, char **argv)
       const long steps_block = d.passes * P;
       long done = 0;
       bool print_xyz = true;                                                                 // MCResetBlockAverage, mc_main.cc:543
+      long sum_row_at = -1;                                                                  // step of this block's last _sum.eng row
       while (done < steps_block) {
          long chunk = min<long>(d.skip_averg, steps_block - done);
          if (block <= d.eq_blocks) chunk = min<long>(steps_block - done, 4L * P);            // no estimators while equilibrating
@@ -438,6 +439,35 @@ int main(int argc, char **argv)
                   XyzWriters::xyz_ang(fname + bc.str(), sys.ntypes, names.data(), numbs.data(), P, coords.data(), angles.data(),
                                       bstype >= 0 ? d.types[bstype].numb : 0, pindex.data());
                   print_xyz = false;
+               }
+            }
+            if (done % d.skip_total == 0) {
+               // SaveSumEnergy every MCSKIP_TOTAL steps of a measuring block (mc_main.cc:431-437): totals of the finished blocks
+               // plus what this block has accumulated so far, summed over the ranks (eight scalars through a scratch buffer; the
+               // accumulator buffer itself is only reduced at the end of the block)
+               pimcgpu_scalars part;
+               bool have = false;
+#ifdef PIMC_WITH_NCCL
+               if (comm) {
+                  static double *d_tmp8 = nullptr;
+                  if (!d_tmp8 && cudaMalloc((void **)&d_tmp8, 8 * sizeof(double)) != cudaSuccess) die("cuda", "cudaMalloc failed");
+                  double h8[8];
+                  cudaStream_t st = (cudaStream_t)pimcgpu_stream();
+                  const double *dacc8 = (const double *)pimcgpu_accum_device_ptr();
+                  cudaMemcpyAsync(d_tmp8, dacc8, sizeof h8, cudaMemcpyDeviceToDevice, st);
+                  if (ncclAllReduce(d_tmp8, d_tmp8, 8, ncclDouble, ncclSum, comm, st) != ncclSuccess) die("nccl", "ncclAllReduce failed");
+                  cudaMemcpyAsync(h8, d_tmp8, sizeof h8, cudaMemcpyDeviceToHost, st);
+                  cudaStreamSynchronize(st);
+                  part.count = h8[0]; part.kin = h8[1]; part.pot = h8[2]; part.rot = h8[3]; part.rotsq = h8[4]; part.cv = h8[5]; part.cv_trans = h8[6]; part.cv_rot = h8[7];
+                  have = true;
+               }
+#endif
+               if (!have) ck(pimcgpu_block_scalars(&part), "pimcgpu_block_scalars");
+               if (rank == 0 && part.count > 0) {
+                  sums += 1.0;
+                  BlockWriters::sum_energy(fsum, sums, total_count + part.count, kin_tot + part.kin, pot_tot + part.pot, rot_tot + part.rot, rotsq_tot + part.rotsq,
+                                           cv_tot + part.cv, cvt_tot + part.cv_trans, cvr_tot + part.cv_rot, N, P, d.temperature);
+                  sum_row_at = done;
                }
             }
          }
@@ -484,11 +514,15 @@ int main(int argc, char **argv)
       if (block > d.eq_blocks && sc.count > 0) {
          const double ac = sc.count;
          BlockWriters::energy(fname, block, ac, sc.kin, sc.pot, sc.rot, sc.rotsq, sc.cv, sc.cv_trans, sc.cv_rot);                 // SaveEnergy
-         // SaveSumEnergy, mc_main.cc:797-836 (the reference appends a row every MCSKIP_TOTAL passes; here once per block)
+         // SaveSumEnergy, mc_main.cc:797-836: rows every MCSKIP_TOTAL steps come from the step loop above; a block whose length is
+         // not a multiple of MCSKIP_TOTAL still gets its closing row here (the reference would write none)
          kin_tot += sc.kin; pot_tot += sc.pot; rot_tot += sc.rot; rotsq_tot += sc.rotsq; cv_tot += sc.cv; cvt_tot += sc.cv_trans; cvr_tot += sc.cv_rot;
-         total_count += ac; sums += 1.0;
+         total_count += ac;
          const double tc = total_count;
-         BlockWriters::sum_energy(fsum, sums, tc, kin_tot, pot_tot, rot_tot, rotsq_tot, cv_tot, cvt_tot, cvr_tot, N, P, d.temperature);
+         if (sum_row_at != steps_block) {
+            sums += 1.0;
+            BlockWriters::sum_energy(fsum, sums, tc, kin_tot, pot_tot, rot_tot, rotsq_tot, cv_tot, cvt_tot, cvr_tot, N, P, d.temperature);
+         }
          if (Q) {   // SaveRCF, block and accumulated (mc_main.cc:739-740, 463-464)
             const long orc = pimcgpu_accum_offset("rcfcnt");
             for (int it = 0; it < Q; it++) { rcf_sum[it] += acc[off_rcf + it]; rcf_rows_sum[it] += (double)Q * ac; }   // _rcf_sum[1..9] += 1 per time origin
