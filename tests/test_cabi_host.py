@@ -45,6 +45,36 @@ def test_no_cpu_fallback(pkg):
     assert L.pimcgpu_eval_spot1d(4, out.ctypes.data_as(C.POINTER(C.c_double)), out.ctypes.data_as(C.POINTER(C.c_double)), None) != 0
 
 
+def test_table_generators_fail_loudly_without_gpu_and_formatters_work_on_host(pkg, tmp_path):
+    """The generators are device code with no CPU path; the Fortran edit descriptors and file writers are host code and must
+    agree with the oracle's formatter (which is pinned on the reference's files)."""
+    import subprocess
+    from oracle import tablegen_py as tg
+    g = pkg.gpu
+    for v in (6.2732329, -0.50630561, 0.0, -1437.6686, 9.99999999e-5, 1.5e-120, -3.25e+105, 1.0, 0.099999999999):
+        assert g.format_e15_8(v) == tg.fmt_e15_8(v)
+        assert g.format_e15_8(v, True) == tg.fmt_e15_8(v, True)[:15]
+    vals = np.array([1.0, -2.5e-7, 3.0e10, 0.0])
+    p = str(tmp_path / "t.rho")
+    g.write_e15_8(p, vals)
+    g.write_e15_8(p, vals[:2], append=True)
+    assert open(p).read() == "".join(tg.fmt_e15_8(v) + "\n" for v in list(vals) + list(vals[:2]))
+    rot = np.arange(8.0).reshape(2, 4) - 3.5
+    g.write_rot(str(tmp_path / "t.rot"), rot)
+    assert open(tmp_path / "t.rot").readlines() == tg.rot_lines(rot)
+    if _has_gpu():
+        return
+    for call in (lambda: g.gen_linden(0.5, 128, 0.419, 100, -1), lambda: g.gen_asymrho(10.0, 2, -1, 0, 0, 27.9, 14.5, 9.3, 10),
+                 lambda: g.gen_symrho(5.0, 4, 1, 0, 0, 5.0, 2.5, 20), lambda: g.gen_wigner_d(4, 0.3)):
+        with pytest.raises(g.PimcGpuError, match="no CUDA device"):
+            call()
+    exe = os.path.join(ROOT, "moribs-pimc_b200", "driver", "pimc_tables")
+    if os.path.exists(exe):
+        out = subprocess.run([exe, "linden", "0.5", "128", "0.419", "1400", "-1"], cwd=tmp_path, capture_output=True, text=True)
+        assert out.returncode == 1 and "no CUDA device" in out.stdout and not os.path.exists(tmp_path / "linden.out")
+        assert subprocess.run([exe], capture_output=True, text=True).stdout.startswith("usage: pimc_tables asymrho")
+
+
 def test_host_spline_setup_matches_oracle(pkg):
     from oracle import oracle_py as op
     L = pkg.gpu.lib()
