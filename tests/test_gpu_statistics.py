@@ -116,7 +116,7 @@ for b in range(nblocks):
             R.lib.ref_MCGetAverage(op._dp(out7)); n += 1
     R.lib.ref_get_exchange_acc(op._dp(pl), op._dp(a6), op._dp(i9))
     exch = float(sum((l + 1) * pl[l] for l in range(1, nb)) / (n * nb))
-    rows.append([out7[0] / n, out7[1] / n, exch, (a6[0] + a6[2] + a6[5]) / n, n])
+    rows.append([out7[0] / n, out7[1] / n, exch, (a6[0] + a6[2] + a6[5]) / n, n, out7[2] / n])
 print("ROWS " + json.dumps(rows))
 '''
 
@@ -160,14 +160,17 @@ def test_exchange_sampling_matches_reference(pkg):
         n = acc[0]
         pl = acc[lay["ploops"]:lay["ploops"] + nb]
         a6 = acc[lay["area"] + 6:lay["area"] + 12]
-        rows.append([acc[1] / n, acc[2] / n, float(sum((l + 1) * pl[l] for l in range(1, nb)) / (n * nb)), (a6[0] + a6[2] + a6[5]) / n, n])
+        rows.append([acc[1] / n, acc[2] / n, float(sum((l + 1) * pl[l] for l in range(1, nb)) / (n * nb)), (a6[0] + a6[2] + a6[5]) / n, n, acc[3] / n])
     g = np.array(rows)
     wt, wa, _ = G.worm_counters()
     G.close()
     print("closed-sector fraction: gpu", g[:, 4].mean() / (32 * 3200 / skip), "reference", r[:, 4].mean() / (per_block / skip), "swap acceptance (gpu)", wa[6] / max(wt[6], 1))
     assert abs(g[:, 4].mean() / (32 * 3200 / skip) - r[:, 4].mean() / (per_block / skip)) < 0.03
     assert g[:, 2].mean() > 0.01 and r[:, 2].mean() > 0.01, "no exchange sampled"
-    compare(g, r, [(0, "K"), (1, "V"), (2, "exchange fraction"), (3, "<A.A> space-fixed")])
+    cols = [(0, "K"), (1, "V"), (2, "exchange fraction"), (3, "<A.A> space-fixed")]
+    if r.shape[1] > 5:
+        cols.append((5, "E_rot (GetRotE3D, top)"))
+    compare(g, r, cols)
 
 
 def test_cxx_driver_writes_reference_formats(pkg, tmp_path):
