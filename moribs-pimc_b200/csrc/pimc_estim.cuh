@@ -414,7 +414,25 @@ __global__ void est_rcf_kernel(const __grid_constant__ Params p, const __grid_co
    e.chain_rcf[(size_t)c * 2 * Q + Q + itc] = below;
 }
 
-// per-chain totals, Cv algebra (mc_main.cc:589-616), accumulation in chain order
+// per-chain totals of the block partials, one thread per (chain, quantity), blocks summed in their fixed order
+__global__ void est_chain_totals_kernel(const __grid_constant__ Params p, const __grid_constant__ EstBuffers e)
+{
+   const int per = 5 + NAREA;
+   const int t = blockIdx.x * blockDim.x + threadIdx.x;
+   if (t >= p.nchains * per) return;
+   const int c = t / per, k = t % per;
+   if (p.worm_on && p.wstate[(size_t)c * 8]) return;       // G sector: the estimator kernels wrote nothing for this chain
+   double s = 0.0;
+   if (k < 5) {
+      for (int b = 0; b < EST_BLOCKS; b++) s += e.partials[((size_t)c * EST_BLOCKS + b) * NPART + k];
+      e.chain_e[(size_t)c * 8 + k] = s;            // raw sums; est_finalize_kernel turns them into the estimators
+   } else if (p.bstype >= 0) {
+      for (int b = 0; b < EST_BLOCKS; b++) s += e.area_partials[((size_t)c * EST_BLOCKS + b) * NAREA + (k - 5)];
+      e.chain_area[(size_t)c * NAREA + (k - 5)] = s;
+   }
+}
+
+// Cv algebra (mc_main.cc:589-616), accumulation in chain order
 __global__ void est_finalize_kernel(const __grid_constant__ Params p, const __grid_constant__ EstBuffers e, int accumulate)
 {
    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -422,14 +440,10 @@ __global__ void est_finalize_kernel(const __grid_constant__ Params p, const __gr
    if (tid == 0) {
       for (int c = 0; c < p.nchains; c++) {
          if (p.worm_on && p.wstate[(size_t)c * 8]) continue;      // a chain in the G sector contributes no sample
-         double r2 = 0, pot = 0, srot = 0, sesq = 0, sterm = 0;
-         for (int b = 0; b < EST_BLOCKS; b++) {
-            const double *o = e.partials + ((size_t)c * EST_BLOCKS + b) * NPART;
-            r2 += o[0]; pot += o[1]; srot += o[2]; sesq += o[3]; sterm += o[4];
-         }
+         double *ce = e.chain_e + (size_t)c * 8;               // raw block sums from est_chain_totals_kernel
+         const double r2 = ce[0], pot = ce[1], srot = ce[2], sesq = ce[3], sterm = ce[4];
          double skin = (double)p.P * p.temperature * (0.5 * (double)(3 * p.N) - r2);
          double spot = pot / (double)p.P;
-         double *ce = e.chain_e + (size_t)c * 8;
          ce[0] = skin; ce[1] = spot; ce[2] = srot; ce[3] = sesq; ce[4] = sterm;
          if (accumulate) {
             double nd = (double)(3 * p.N);
@@ -447,12 +461,7 @@ __global__ void est_finalize_kernel(const __grid_constant__ Params p, const __gr
       const bool lin = p.imtype >= 0 && p.molecule[p.imtype] == 1, mff = p.imtype >= 0 && p.molecule[p.imtype] == 2 && p.ispher == 0;
       for (int c = 0; c < p.nchains; c++) {
          if (p.worm_on && p.wstate[(size_t)c * 8]) continue;
-         double *ca = e.chain_area + (size_t)c * NAREA;
-         for (int k = 0; k < NAREA; k++) {
-            double s = 0.0;
-            for (int b = 0; b < EST_BLOCKS; b++) s += e.area_partials[((size_t)c * EST_BLOCKS + b) * NAREA + k];
-            ca[k] = s;
-         }
+         const double *ca = e.chain_area + (size_t)c * NAREA;   // summed by est_chain_totals_kernel
          if (!accumulate) continue;
          double *a = e.acc + e.off_area;
          if (lin) {            // mc_estim.cc:2242-2249

@@ -222,6 +222,7 @@ int launch_estimators(int with_dens, int accumulate)
       est_com_kernel<<<(unsigned)((n + 255) / 256), 256, 0, G.stream>>>(G.p, G.e);
       est_area_kernel<<<G.p.nchains * EST_BLOCKS, EST_THREADS, 0, G.stream>>>(G.p, G.e);
    }
+   est_chain_totals_kernel<<<(G.p.nchains * (5 + NAREA) + 127) / 128, 128, 0, G.stream>>>(G.p, G.e);
    est_finalize_kernel<<<8, 128, 0, G.stream>>>(G.p, G.e, accumulate);
    CK(cudaGetLastError());
    return 0;

@@ -12,23 +12,21 @@ s = cfg.system
 G = pkg.gpu.PimcGpu(cfg, nchains=chains)
 G.seed((12345,) * 6)
 n = s.N * s.P
-pinned = [(torch.empty((3, n), dtype=torch.float64, pin_memory=True), torch.empty((3, n), dtype=torch.float64, pin_memory=True)) for _ in range(chains)]
-host = [(a.numpy(), b.numpy()) for a, b in pinned]
-for c in range(chains):
-    G.download_into(c, host[c][0], host[c][1])
+pin_c = torch.empty((chains, 3, n), dtype=torch.float64, pin_memory=True)
+pin_a = torch.empty((chains, 3, n), dtype=torch.float64, pin_memory=True)
+host_c, host_a = pin_c.numpy(), pin_a.numpy()
+G.download_all_into(host_c, host_a)
 G.steps(s.P)
 t = {k: 0.0 for k in ("upload", "steps", "measure", "accum", "download")}
 reps = 5
 for _ in range(reps):
     t0 = time.perf_counter()
-    for c in range(chains):
-        G.upload(c, host[c][0], host[c][1], cfg.perm)
+    G.upload_all(host_c, host_a, cfg.perm)
     G.sync(); t1 = time.perf_counter()
     G.accum_reset(); G.steps(s.P, sync=False); G.sync(); t2 = time.perf_counter()
     G.measure(); G.sync(); t3 = time.perf_counter()
     acc, _ = G.accum_download(); t4 = time.perf_counter()
-    for c in range(chains):
-        G.download_into(c, host[c][0], host[c][1])
+    G.download_all_into(host_c, host_a)
     t5 = time.perf_counter()
     for k, v in zip(t, (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4)):
         t[k] += v
