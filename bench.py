@@ -300,6 +300,8 @@ def main():
     pin_a = torch.empty((chains, 3, n_beads), dtype=torch.float64, pin_memory=True)
     host_c, host_a = pin_c.numpy(), pin_a.numpy()
     G.download_all_into(host_c, host_a)
+    pin_acc = torch.empty(lay["n_total"], dtype=torch.float64, pin_memory=True)
+    host_acc = pin_acc.numpy()
     h2d = chains * ((P * 3 * ((s.N + 3) // 4 * 4) + 2 * max(1, s.Q) * 3 * max(1, sum(t.numb for t in s.types if t.molecule))) * 8 + (3 * s.N + 3) * 4)
     d2h = h2d - chains * (3 * s.N + 3) * 4 + lay["n_total"] * 8
     barrier()
@@ -315,7 +317,7 @@ def main():
             dist.all_reduce(acc_t)
             torch.cuda.current_stream().synchronize()
         G.sync()
-        accum, _ = G.accum_download()
+        G.accum_download_into(host_acc)
         G.download_all_into(host_c, host_a)
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - w0

@@ -399,6 +399,11 @@ class PimcGpu:
         _ck(self.L.pimcgpu_accum_download(_dp(out), C.c_long(len(out))))
         return out, lay
 
+    def accum_download_into(self, out):
+        """accumulator buffer into a caller-owned array (e.g. pinned, reused every block)"""
+        self.L.pimcgpu_accum_device_ptr()          # folds the move counters into the buffer
+        _ck(self.L.pimcgpu_accum_download(_dp(out), C.c_long(len(out))))
+
     def accum_reset(self):
         _ck(self.L.pimcgpu_accum_reset())
 
