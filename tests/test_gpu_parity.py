@@ -386,3 +386,46 @@ def test_batched_state_transfer_equals_per_chain_calls(pkg):
     assert np.array_equal(results[0][0], results[1][0]) and np.array_equal(results[0][1], results[1][1])
     assert np.array_equal(results[0][2][0], results[1][2][0]) and np.array_equal(results[0][2][1], results[1][2][1])
     assert results[0][2][1].sum() > 0
+
+
+def test_full_size_c5_energies_and_checksum_properties(pkg):
+    """BASELINE configs[4] at its full size (N = 101, P = 1024, Q = 128) after a stretch of sampling: the estimators of the
+    device against the oracle on the downloaded configuration, and the size-independent properties
+      sum over all beads of PotEnergy(atom, it) = 2 P <V>          (every pair term appears once per partner), 
+      histogram counts = number of binned pair terms,
+      the state that went through the batched export / import round trip is unchanged."""
+    op = _oracle()
+    cfg = pkg.configs.make_config("C5")
+    s = cfg.system
+    assert (s.N, s.P, s.Q) == (101, 1024, 128)
+    G = pkg.gpu.PimcGpu(cfg, nchains=2)
+    G.seed((9, 8, 7, 6, 5, 4))
+    G.steps(2 * 128 + 3)                               # whole-path sweep, three bisection sweeps, 259 rotational sweeps
+    c, a, _ = G.download(1)
+    O = op.Oracle(cfg)
+    O.set_state(c, a)
+    e = G.chain_energies(1)
+    ko, po = O.get_kin(), O.get_pot(0)
+    assert abs(e["kin"] - ko) <= RTOL * abs(ko)
+    assert abs(e["pot"] - po) <= 1e-9 * abs(po)
+    srot, esq, eterm = O.get_rot_energy()
+    assert abs(e["rot"] - srot) <= 1e-9 * abs(srot) and abs(e["erotsq"] - esq) <= 1e-9 * abs(esq)
+    pe = G.pot_energy_slice(1)                          # [N][P]
+    assert abs(pe.sum() / (2.0 * s.P) - e["pot"]) <= 1e-10 * abs(e["pot"])
+    for (atom, it) in ((0, 0), (57, 511), (100, 1023), (100, 64)):
+        assert abs(pe[atom, it] - O.pot_energy_it(atom, it)) <= 1e-9 * max(1e-3, abs(pe[atom, it]))
+    G.accum_reset()
+    G.measure()
+    acc, lay = G.accum_download()
+    assert acc[0] == 2.0
+    npair_aa = 100 * 99 // 2
+    g1 = acc[lay["gr1d"]:lay["gr1d"] + 300]
+    g2 = acc[lay["gr2d"]:lay["gr2d"] + 15000]
+    assert g1.sum() <= 2 * npair_aa * s.P and g1.sum() > 0.5 * 2 * npair_aa * s.P       # pairs inside 15 Angstrom
+    assert g2.sum() <= 2 * 100 * s.P and g2.sum() > 0.9 * 2 * 100 * s.P
+    ca, aa = np.zeros((2, 3, s.N * s.P)), np.zeros((2, 3, s.N * s.P))
+    G.download_all_into(ca, aa)
+    G.upload_all(ca, aa)
+    c2, a2, _ = G.download(1)
+    assert np.array_equal(c2, c) and np.array_equal(a2, a)
+    G.close()
