@@ -351,3 +351,14 @@ def test_free_asymmetric_top_sampled_with_generated_tables_reproduces_exact_ener
     print(f"free top: <E_rot> = {mean:.4f} +- {err:.4f} K, exact {exact:.4f} K, 3/2 kT = {1.5 * T} K, maxj {maxj}, rotational acceptance {acc[0][2] / max(tot[0][2], 1):.3f}")
     assert abs(mean - exact) < 2.5 * err + 2e-3 * exact
     assert err < 0.01 * exact and abs(mean - 1.5 * T) > 8 * err
+
+
+def test_asymrho_large_basis_sum_rules(gpu):
+    """maxj = 150 and 300 (finer imaginary-time steps need larger bases; the reference allows up to 876): rho(identity) = Z(tau)/8 pi^2
+    and E(identity) = <E>(tau) to round-off, phi <-> chi symmetry, finite values"""
+    for maxj, Q in ((150, 512), (300, 2048)):
+        r, e, q, info = gpu.gen_asymrho(0.37, Q, -1, 0, 1, 0.6666525, 0.2306476, 0.1769383, maxj)
+        assert abs(r[0, 0, 0] * 8 * np.pi ** 2 - info[13]) <= 1e-12 * info[13]
+        assert abs(e[0, 0, 0] - info[14]) <= 1e-11 * abs(info[14])
+        assert np.isfinite(r).all() and np.isfinite(e).all() and np.isfinite(q).all()
+        assert np.array_equal(r, np.swapaxes(r, 1, 2))
