@@ -198,6 +198,15 @@ int pimcgpu_eval_vcord(int n, const double *eul, const double *rcom, const doubl
                        int *index);                                                   /* vcord_ vcord.f:1-98 */
 int pimcgpu_eval_caleng(int n, const double *com1, const double *com2, const double *eul1, const double *eul2,
                         double *e);                                                   /* caleng_ caleng_tip4p_gg.f:2-186 */
+/* pure table selectors: identical doubles in, flat index and interpolated value out (bit-exact index contract) */
+int pimcgpu_eval_rotpro(int n, const double *deg /* [n][3] phi, theta, chi in degrees */, double *rho, double *erot,
+                        double *esq, int *index);                                     /* rotpro rotpro_sub.f:1-64; erot, esq in cm^-1; index < 0: out of range (-1-index) */
+int pimcgpu_eval_vcalc(int n, const double *rtc /* [n][3] r bohr, theta deg, chi deg */, double *v, int *index); /* vcalc vcalc.f:1-65 */
+int pimcgpu_eval_deleul(int n, const double *eul1, const double *eul2, double *rel /* [n][3] rad */);      /* deleul rotden.f:32-134 */
+int pimcgpu_eval_vcord_grid(int n, const double *eul, const double *rcom, const double *rpt, double *grid /* [n][3] r bohr, theta deg, chi deg handed to vcalc */); /* vcord.f:86-95 */
+int pimcgpu_eval_vspher(int n, const double *r, double *v, double *rclamp);           /* vspher_ vspher.f:12-544; rclamp = the overwritten r argument (bohr) */
+/* device libm against the host's: which = 0 sin, 1 cos, 2 acos, 3 atan, 4 exp, 5 log, 6 sqrt, 7 fmod(x, 2 pi) */
+int pimcgpu_eval_libm(int which, int n, const double *x, double *y);
 /* PotEnergy(atom, MCCoords, it) for every atom and slice of one chain: v[N][P] (mc_piqmc.cc:1796-1965) */
 int pimcgpu_pot_energy_slice(int chain, double *v);
 /* first n uniforms of MRG32k3a stream `stream` (global stream index, 2^127 spacing): RngStream::RandU01 */

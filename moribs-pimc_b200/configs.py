@@ -18,7 +18,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-DECKS = os.path.join(ROOT, "tests", "golden", "decks")
+DECKS = os.path.join(HERE, "data", "decks")          # the reference's example inputs (qmc.input, *.pot, *.rot, xyz.init) used by the harness
 
 # mc_const.h:50-56 and mc_setup.cc:244-319 (MCInitParams)
 _H1, _H2, _HE4, _C12, _N14, _O16, _S32 = 1.0078, 2.015650642, 4.0026032497, 12.0, 14.003, 15.994915, 31.972
@@ -178,6 +178,15 @@ def load_columns(path: str, ncol: int) -> np.ndarray:
             continue
         rows.append([float(x) for x in tok[:ncol]])
     return np.ascontiguousarray(np.array(rows, dtype=np.float64).T)
+
+
+def load_vspher_table() -> np.ndarray:
+    """the 501-entry DATA table of vspher.f:15-517 as the driver compiles it in (data/vspher_table.h, hex doubles)"""
+    import re
+    txt = open(os.path.join(HERE, "data", "vspher_table.h")).read()
+    v = np.array([float.fromhex(x) for x in re.findall(r"-?0x[0-9a-f.]+p[-+]\d+", txt)])
+    assert len(v) == 501
+    return v
 
 
 def load_xyz_init(path: str, nbeads: int, nboson: int):
@@ -380,6 +389,23 @@ def make_config(name: str, P: Optional[int] = None, Q: Optional[int] = None, nso
         if Q: s.Q = Q
         if big_tables:
             tables["rot3d"] = synth_rot3d(s.temperature, s.Q, *ROT_CONSTANTS["H2O"])
+        coords, angles = cluster_config(s, seed)
+    elif name == "SPH":
+        # spherical treatment of a non-linear dopant (negative species count, mc_input.cc:152-156): the SO2 deck with
+        # ROTATION removed (ISPHER is not compatible with it, mc_input.cc:463-464) and the vspher_ radial table
+        d = _deck("SO2_4pH2_0.37K_1024_256")
+        s = parse_qmc_input(os.path.join(d, "qmc.input"))
+        s.worm = None
+        s.ispher = 1
+        s.Q = 0
+        s.reflect, s.rotsym = (0, 0, 0), 0
+        for t in s.types:
+            t.rtstep = 0.0
+        if P: s.temperature *= float(s.P) / P; s.P = P
+        if nsolv is not None: s.types[0].numb = nsolv
+        g1 = load_columns(os.path.join(d, "isoH2H208.pot"), 2)
+        tables["pot1d"] = (g1[0].copy(), g1[1].copy())
+        tables["vspher"] = load_vspher_table()
         coords, angles = cluster_config(s, seed)
     elif name == "CO2":
         # examples/CO2_100K_4_4: one free linear rotor (zero potential), the only deck of the reference whose files are all in the tree

@@ -454,17 +454,12 @@ __device__ __forceinline__ double rsline(const Params &p, double dprd, double *e
    return -r;
 }
 
-// rotden_ (rotden.f:1-31) + rotpro (rotpro_sub.f:1-64).  Returns rho; erot/esq only when the
-// pointers are non-null (moves need rho alone).  *istop mirrors the Fortran's out-of-range flag.
-__device__ __forceinline__ double rotden(const Params &p, const Mat3 &r1, const Mat3 &r2, double *rel, double *erot,
-                                         double *esq, int *index, int *istop)
+// rotpro (rotpro_sub.f:1-64): a pure function of the three relative angles in DEGREES -- index selection by int()
+// truncation (:7-9), forward differences along chi, phi, theta, zero difference on the last grid line.
+// erot/esq are still in the tables' cm^-1 units here (rotden_ converts).
+__device__ __forceinline__ double rotpro(const Params &p, double phi, double theta, double chi, double *erot, double *esq,
+                                         int *index, int *istop)
 {
-   double phi, theta, chi;
-   deleul(r1, r2, phi, theta, chi);
-   if (rel) { rel[0] = phi; rel[1] = theta; rel[2] = chi; }
-   phi = phi * 180.0 / PI;
-   theta = theta * 180.0 / PI;
-   chi = chi * 180.0 / PI;
    int ichi = (int)chi, iphi = (int)phi, itheta = (int)theta;
    if (ichi > 360 || ichi < 0) { ichi = 0; if (istop) *istop = 1; }
    if (iphi > 360 || iphi < 0) { iphi = 0; if (istop) *istop = 1; }
@@ -479,19 +474,64 @@ __device__ __forceinline__ double rotden(const Params &p, const Mat3 &r1, const 
    double rho = rho0 + (__ldg(p.rho3 + kc) - rho0) * fc + (__ldg(p.rho3 + kp) - rho0) * fp + (__ldg(p.rho3 + kt) - rho0) * ft;
    if (erot) {
       double e0 = __ldg(p.erot3 + ind);
-      double e = e0 + (__ldg(p.erot3 + kc) - e0) * fc + (__ldg(p.erot3 + kp) - e0) * fp + (__ldg(p.erot3 + kt) - e0) * ft;
-      *erot = e / WNO2K;
+      *erot = e0 + (__ldg(p.erot3 + kc) - e0) * fc + (__ldg(p.erot3 + kp) - e0) * fp + (__ldg(p.erot3 + kt) - e0) * ft;
       double q0 = __ldg(p.esq3 + ind);
-      double q = q0 + (__ldg(p.esq3 + kc) - q0) * fc + (__ldg(p.esq3 + kp) - q0) * fp + (__ldg(p.esq3 + kt) - q0) * ft;
-      *esq = q / (WNO2K * WNO2K);
+      *esq = q0 + (__ldg(p.esq3 + kc) - q0) * fc + (__ldg(p.esq3 + kp) - q0) * fp + (__ldg(p.esq3 + kt) - q0) * ft;
    }
    return rho;
 }
 
-// vcord_ (vcord.f:1-98) + vcalc (vcalc.f:1-65) for a rotor with rotation matrix `rm` at `rcom`
-// and a point particle at `rpt`.  rtc (optional) receives radret, theret, chiret.
+// rotden_ (rotden.f:1-31): deleul, radians -> degrees, rotpro, cm^-1 -> K.  Returns rho; erot/esq only when the
+// pointers are non-null (moves need rho alone).  *istop mirrors the Fortran's out-of-range flag.
+__device__ __forceinline__ double rotden(const Params &p, const Mat3 &r1, const Mat3 &r2, double *rel, double *erot,
+                                         double *esq, int *index, int *istop)
+{
+   double phi, theta, chi;
+   deleul(r1, r2, phi, theta, chi);
+   if (rel) { rel[0] = phi; rel[1] = theta; rel[2] = chi; }
+   phi = phi * 180.0 / PI;
+   theta = theta * 180.0 / PI;
+   chi = chi * 180.0 / PI;
+   const double rho = rotpro(p, phi, theta, chi, erot, esq, index, istop);
+   if (erot) {
+      *erot = *erot / WNO2K;
+      *esq = *esq / (WNO2K * WNO2K);
+   }
+   return rho;
+}
+
+// vcalc (vcalc.f:1-65): a pure function of r (bohr), theta and chi (degrees) -- r clamped to the table's range, indices by
+// int() truncation clamped to the grid (:16-25), forward differences, zero gradient on the last grid line (:33-58)
+__device__ __forceinline__ double vcalc(const Params &p, double r, double theta, double chi, int *index)
+{
+   int maxrpt = p.rg3 - 1, mxthpt = p.thg3 - 1, mxchpt = p.chg3 - 1;
+   if (r < p.rvmin) r = p.rvmin;
+   if (r > p.rvmax) r = p.rvmax;
+   int ir = (int)((r - p.rvmin) / p.rvstep);
+   // "index sits on the last grid line" is decided on the doubles (theta, chi >= 0 here), not by comparing the
+   // clamped integers: ptxas 12.9 fuses min/max/compare into a predicated VIMNMX whose predicate came out
+   // inverted on sm_100a (angular gradient terms silently dropped) -- see DESIGN.md "Toolchain notes".
+   const bool th_last = !(theta < (double)mxthpt), ch_last = !(chi < (double)mxchpt);
+   int ith = th_last ? mxthpt : (int)theta;
+   int ich = ch_last ? mxchpt : (int)chi;
+   if (ith < 0) ith = 0;
+   if (ich < 0) ich = 0;
+   int ind = (ir * p.thg3 + ith) * p.chg3 + ich;
+   if (index) *index = ind;
+   double v0 = __ldg(p.v3d + ind);
+   double gradr = 0.0, delr = 0.0;
+   if (ir != maxrpt) { gradr = (__ldg(p.v3d + ind + p.thg3 * p.chg3) - v0) / p.rvstep; delr = r - (p.rvmin + ir * p.rvstep); }
+   const double gradth = __ldg(p.v3d + (th_last ? ind : ind + p.chg3)) - v0;
+   const double delth = th_last ? 0.0 : theta - (double)ith;
+   const double gradch = __ldg(p.v3d + (ch_last ? ind : ind + 1)) - v0;
+   const double delch = ch_last ? 0.0 : chi - (double)ich;
+   return v0 + gradr * delr + gradth * delth + gradch * delch;
+}
+
+// vcord_ (vcord.f:1-98) for a rotor with rotation matrix `rm` at `rcom` and a point particle at `rpt`.
+// rtc (optional) receives radret, theret, chiret; grid (optional) the arguments handed to vcalc (bohr, degrees).
 __device__ __forceinline__ double vcord(const Params &p, const Mat3 &rm, const double *rcom, const double *rpt,
-                                        double *rtc, int *index)
+                                        double *rtc, int *index, double *grid = nullptr)
 {
    const double small = 1.0e-08, bo2ang = 0.529177249;
    double R[3] = {rpt[0] - rcom[0], rpt[1] - rcom[1], rpt[2] - rcom[2]};
@@ -523,41 +563,20 @@ __device__ __forceinline__ double vcord(const Params &p, const Mat3 &rm, const d
    double r = radwff / bo2ang;
    double theta = thewff * 180.0 / PI;
    double chi = chiwff * 180.0 / PI;
-   // vcalc
-   int maxrpt = p.rg3 - 1, mxthpt = p.thg3 - 1, mxchpt = p.chg3 - 1;
-   if (r < p.rvmin) r = p.rvmin;
-   if (r > p.rvmax) r = p.rvmax;
-   int ir = (int)((r - p.rvmin) / p.rvstep);
-   // "index sits on the last grid line" is decided on the doubles (theta, chi >= 0 here), not by comparing the
-   // clamped integers: ptxas 12.9 fuses min/max/compare into a predicated VIMNMX whose predicate came out
-   // inverted on sm_100a (angular gradient terms silently dropped) -- see DESIGN.md "Toolchain notes".
-   const bool th_last = !(theta < (double)mxthpt), ch_last = !(chi < (double)mxchpt);
-   int ith = th_last ? mxthpt : (int)theta;
-   int ich = ch_last ? mxchpt : (int)chi;
-   if (ith < 0) ith = 0;
-   if (ich < 0) ich = 0;
-   int ind = (ir * p.thg3 + ith) * p.chg3 + ich;
-   if (index) *index = ind;
-   double v0 = __ldg(p.v3d + ind);
-   double gradr = 0.0, delr = 0.0;
-   if (ir != maxrpt) { gradr = (__ldg(p.v3d + ind + p.thg3 * p.chg3) - v0) / p.rvstep; delr = r - (p.rvmin + ir * p.rvstep); }
-   const double gradth = __ldg(p.v3d + (th_last ? ind : ind + p.chg3)) - v0;
-   const double delth = th_last ? 0.0 : theta - (double)ith;
-   const double gradch = __ldg(p.v3d + (ch_last ? ind : ind + 1)) - v0;
-   const double delch = ch_last ? 0.0 : chi - (double)ich;
-#ifdef PIMC_VCORD_DEBUG
-   printf("dbg ir %d ith %d ich %d mx %d %d %d gr %g dr %g gt %g dt %g gc %g dc %g theta %.12g chi %.12g\n", ir, ith, ich, maxrpt, mxthpt, mxchpt, gradr, delr, gradth, delth, gradch, delch, theta, chi);
-#endif
-   return v0 + gradr * delr + gradth * delth + gradch * delch;
+   if (grid) { grid[0] = r; grid[1] = theta; grid[2] = chi; }
+   return vcalc(p, r, theta, chi, index);
 }
 
-// vspher_, vspher.f:519-543 (r in Angstrom)
-__device__ __forceinline__ double vspher(const Params &p, double r)
+// vspher_, vspher.f:519-543 (r in Angstrom).  ang2bo is a REAL*4 literal widened to double in the Fortran PARAMETER
+// statement (no D exponent), like the table entries.  *rclamp (optional) receives what the Fortran leaves in its `r`
+// argument: the clamped distance in bohr, which GetPotEnergy_Densities then bins (mc_estim.cc:631-637).
+__device__ __forceinline__ double vspher(const Params &p, double r, double *rclamp = nullptr)
 {
-   const double r0 = 3.0, rmax = 26.0, rstep = 0.046, ang2bo = 0.5291772;
+   const double r0 = 3.0, rmax = 26.0, rstep = 0.046, ang2bo = (double)0.5291772f;
    r = r / ang2bo;
    if (r < r0) r = r0;
    if (r > rmax) r = rmax;
+   if (rclamp) *rclamp = r;
    int ir = (int)((r - r0) / rstep);
    double v0 = __ldg(p.vspher + ir);
    if (ir == 500) return v0;

@@ -131,10 +131,8 @@ est_energy_kernel(const __grid_constant__ Params p, const __grid_constant__ EstB
          } else {
             // vspher_ overwrites its r argument with the clamped value in bohr, which is then binned (mc_estim.cc:631-637)
             double r = sqrt(dr2);
-            v = vspher(p, r);
-            double rb = r / 0.5291772;
-            rb = rb < 3.0 ? 3.0 : (rb > 26.0 ? 26.0 : rb);
-            rtc[0] = rb; rtc[1] = 0.0; rtc[2] = 0.0;
+            v = vspher(p, r, &rtc[0]);
+            rtc[1] = 0.0; rtc[2] = 0.0;
          }
          if (with_dens && e.has_gr3d) {   // bin_3Ddensity, mc_estim.cc:1252-1273
             int br; bin_r(e, rtc[0], &br);
@@ -637,6 +635,61 @@ __global__ void eval_vcord_kernel(const __grid_constant__ Params p, int n, const
    Mat3 a;
    matpre(eul[3 * i], eul[3 * i + 1], eul[3 * i + 2], a);
    int k; v[i] = vcord(p, a, rcom + 3 * i, rpt + 3 * i, rtc + 3 * i, &k); idx[i] = k;
+}
+__global__ void eval_rotpro_kernel(const __grid_constant__ Params p, int n, const double *deg, double *rho, double *erot, double *esq, int *idx)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) return;
+   double er, es; int k, istop = 0;
+   rho[i] = rotpro(p, deg[3 * i], deg[3 * i + 1], deg[3 * i + 2], &er, &es, &k, &istop);
+   erot[i] = er; esq[i] = es; idx[i] = istop ? -1 - k : k;
+}
+__global__ void eval_vcalc_kernel(const __grid_constant__ Params p, int n, const double *rtc, double *v, int *idx)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) return;
+   int k; v[i] = vcalc(p, rtc[3 * i], rtc[3 * i + 1], rtc[3 * i + 2], &k); idx[i] = k;
+}
+__global__ void eval_deleul_kernel(int n, const double *e1, const double *e2, double *rel)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) return;
+   Mat3 a, b;
+   matpre(e1[3 * i], e1[3 * i + 1], e1[3 * i + 2], a);
+   matpre(e2[3 * i], e2[3 * i + 1], e2[3 * i + 2], b);
+   deleul(a, b, rel[3 * i], rel[3 * i + 1], rel[3 * i + 2]);
+}
+__global__ void eval_vcord_grid_kernel(const __grid_constant__ Params p, int n, const double *eul, const double *rcom, const double *rpt, double *grid)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) return;
+   Mat3 a;
+   matpre(eul[3 * i], eul[3 * i + 1], eul[3 * i + 2], a);
+   vcord(p, a, rcom + 3 * i, rpt + 3 * i, nullptr, nullptr, grid + 3 * i);
+}
+__global__ void eval_vspher_kernel(const __grid_constant__ Params p, int n, const double *r, double *v, double *rc)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) return;
+   double c; v[i] = vspher(p, r[i], &c); rc[i] = c;
+}
+__global__ void eval_libm_kernel(int which, int n, const double *x, double *y)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) return;
+   const double a = x[i];
+   double r = 0.0;
+   switch (which) {
+      case 0: r = sin(a); break;
+      case 1: r = cos(a); break;
+      case 2: r = acos(a); break;
+      case 3: r = atan(a); break;
+      case 4: r = exp(a); break;
+      case 5: r = log(a); break;
+      case 6: r = sqrt(a); break;
+      case 7: r = fmod(a, 2.0 * PI); break;
+   }
+   y[i] = r;
 }
 __global__ void eval_caleng_kernel(int n, const double *c1, const double *c2, const double *e1, const double *e2, double *e)
 {

@@ -1226,6 +1226,53 @@ int pimcgpu_eval_caleng(int n, const double *c1, const double *c2, const double 
    eval_caleng_kernel<<<(n + 127) / 128, 128>>>(n, a1, a2, b1, b2, de);
    return back(e, de, n);
 }
+int pimcgpu_eval_rotpro(int n, const double *deg, double *rho, double *erot, double *esq, int *index)
+{
+   if (!G.live || !G.p.rho3) return fail("pimcgpu_eval_rotpro: no top density-matrix tables loaded");
+   DevBuf b; const double *dd = b.in(deg, 3 * (size_t)n);
+   double *dr = b.out<double>(n), *de = b.out<double>(n), *dq = b.out<double>(n); int *di = b.out<int>(n);
+   eval_rotpro_kernel<<<(n + 127) / 128, 128>>>(G.p, n, dd, dr, de, dq, di);
+   return back(rho, dr, n) || back(erot, de, n) || back(esq, dq, n) || back(index, di, n);
+}
+int pimcgpu_eval_vcalc(int n, const double *rtc, double *v, int *index)
+{
+   if (!G.live || !G.p.v3d) return fail("pimcgpu_eval_vcalc: no 3-D potential table loaded");
+   DevBuf b; const double *dt = b.in(rtc, 3 * (size_t)n); double *dv = b.out<double>(n); int *di = b.out<int>(n);
+   eval_vcalc_kernel<<<(n + 127) / 128, 128>>>(G.p, n, dt, dv, di);
+   return back(v, dv, n) || back(index, di, n);
+}
+int pimcgpu_eval_deleul(int n, const double *e1, const double *e2, double *rel)
+{
+   int ndev = 0;
+   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("pimcgpu_eval_deleul: no CUDA device");
+   DevBuf b; const double *d1 = b.in(e1, 3 * (size_t)n), *d2 = b.in(e2, 3 * (size_t)n); double *dr = b.out<double>(3 * (size_t)n);
+   eval_deleul_kernel<<<(n + 127) / 128, 128>>>(n, d1, d2, dr);
+   return back(rel, dr, 3 * (size_t)n);
+}
+int pimcgpu_eval_vcord_grid(int n, const double *eul, const double *rcom, const double *rpt, double *grid)
+{
+   if (!G.live || !G.p.v3d) return fail("pimcgpu_eval_vcord_grid: no 3-D potential table loaded");
+   DevBuf b; const double *de = b.in(eul, 3 * (size_t)n), *dc = b.in(rcom, 3 * (size_t)n), *dp = b.in(rpt, 3 * (size_t)n);
+   double *dg = b.out<double>(3 * (size_t)n);
+   eval_vcord_grid_kernel<<<(n + 127) / 128, 128>>>(G.p, n, de, dc, dp, dg);
+   return back(grid, dg, 3 * (size_t)n);
+}
+int pimcgpu_eval_vspher(int n, const double *r, double *v, double *rclamp)
+{
+   if (!G.live || !G.p.vspher) return fail("pimcgpu_eval_vspher: no spherical table loaded (ISPHER = 0)");
+   DevBuf b; const double *dr = b.in(r, n); double *dv = b.out<double>(n), *dc = b.out<double>(n);
+   eval_vspher_kernel<<<(n + 127) / 128, 128>>>(G.p, n, dr, dv, dc);
+   return back(v, dv, n) || back(rclamp, dc, n);
+}
+int pimcgpu_eval_libm(int which, int n, const double *x, double *y)
+{
+   int ndev = 0;
+   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("pimcgpu_eval_libm: no CUDA device");
+   if (which < 0 || which > 7) return fail("pimcgpu_eval_libm: unknown function %d", which);
+   DevBuf b; const double *dx = b.in(x, n); double *dy = b.out<double>(n);
+   eval_libm_kernel<<<(n + 127) / 128, 128>>>(which, n, dx, dy);
+   return back(y, dy, n);
+}
 int pimcgpu_pot_energy_slice(int chain, double *v)
 {
    if (!G.live) return fail("pimcgpu_pot_energy_slice: not initialised");

@@ -16,6 +16,7 @@
 // mc_qworm.cc) are honoured on the device; yw001.worm is written in the reference's layout for chain 0.  yw001.rand (SPRNG state) has no
 // counterpart: the MRG32k3a package seed and step counter are written to yw001.mrg instead.
 #include "../../include/pimcgpu.h"
+#include "../data/vspher_table.h"
 #include "pimc_writers.h"
 
 #include <cmath>
@@ -278,6 +279,7 @@ int main(int argc, char **argv)
          cout << "Rgrd=" << tab.rgrd << " THgrd=" << tab.thgrd << " CHgrd=" << tab.chgrd << " Rvmin=" << tab.rvmin << " Rvmax=" << tab.rvmax << endl;
       }
    }
+   if (d.ispher) tab.vspher = PIMC_VSPHER_TABLE;      // negative species count: spherical H2O-pH2 treatment, DATA table of vspher.f:15-517
    if (Q > 0 && imtype >= 0) {
       const Species &s = d.types[imtype];
       string base = s.name + "_T" + cxx_double(d.temperature) + "t" + to_string(Q);          // mc_poten.cc:443-458,518-524

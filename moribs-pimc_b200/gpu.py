@@ -30,6 +30,7 @@ EXPORTS = [
     "pimcgpu_upload_states", "pimcgpu_download_states",
     "pimcgpu_gen_asymrho", "pimcgpu_gen_symrho", "pimcgpu_gen_linden", "pimcgpu_gen_wigner_d", "pimcgpu_gen_timing",
     "pimcgpu_format_e15_8", "pimcgpu_write_e15_8", "pimcgpu_write_rot",
+    "pimcgpu_eval_rotpro", "pimcgpu_eval_vcalc", "pimcgpu_eval_deleul", "pimcgpu_eval_vcord_grid", "pimcgpu_eval_vspher", "pimcgpu_eval_libm",
 ]
 
 
@@ -113,6 +114,14 @@ def _dp(a):
 
 def _ip(a):
     return a.ctypes.data_as(c_ip) if a is not None else None
+
+
+def eval_libm(which, x):
+    """device libm: which = sin, cos, acos, atan, exp, log, sqrt, fmod2pi"""
+    names = ("sin", "cos", "acos", "atan", "exp", "log", "sqrt", "fmod2pi")
+    x = np.ascontiguousarray(x, dtype=np.float64); y = np.zeros_like(x)
+    _ck(lib().pimcgpu_eval_libm(C.c_int(names.index(which)), C.c_int(len(x)), _dp(x), _dp(y)))
+    return y
 
 
 def fp64_peak_tflops() -> float:
@@ -454,6 +463,37 @@ class PimcGpu:
         n = len(a[0]); e = np.zeros(n)
         _ck(self.L.pimcgpu_eval_caleng(n, *[_dp(x) for x in a], _dp(e)))
         return e
+
+    def eval_rotpro(self, deg):
+        """rotpro on (phi, theta, chi) in degrees [n][3] -> rho, erot, esq (table units), flat index"""
+        d = np.ascontiguousarray(deg, dtype=np.float64); n = len(d)
+        rho, erot, esq = np.zeros(n), np.zeros(n), np.zeros(n); idx = np.zeros(n, dtype=np.int32)
+        _ck(self.L.pimcgpu_eval_rotpro(n, _dp(d), _dp(rho), _dp(erot), _dp(esq), _ip(idx)))
+        return rho, erot, esq, idx
+
+    def eval_vcalc(self, rtc):
+        """vcalc on (r bohr, theta deg, chi deg) [n][3] -> V, flat index"""
+        d = np.ascontiguousarray(rtc, dtype=np.float64); n = len(d)
+        v = np.zeros(n); idx = np.zeros(n, dtype=np.int32)
+        _ck(self.L.pimcgpu_eval_vcalc(n, _dp(d), _dp(v), _ip(idx)))
+        return v, idx
+
+    def eval_deleul(self, e1, e2):
+        e1 = np.ascontiguousarray(e1, dtype=np.float64); e2 = np.ascontiguousarray(e2, dtype=np.float64)
+        rel = np.zeros((len(e1), 3))
+        _ck(self.L.pimcgpu_eval_deleul(len(e1), _dp(e1), _dp(e2), _dp(rel)))
+        return rel
+
+    def eval_vcord_grid(self, eul, rcom, rpt):
+        eul, rcom, rpt = (np.ascontiguousarray(x, dtype=np.float64) for x in (eul, rcom, rpt))
+        g = np.zeros((len(eul), 3))
+        _ck(self.L.pimcgpu_eval_vcord_grid(len(eul), _dp(eul), _dp(rcom), _dp(rpt), _dp(g)))
+        return g
+
+    def eval_vspher(self, r):
+        r = np.ascontiguousarray(r, dtype=np.float64); v = np.zeros_like(r); rc = np.zeros_like(r)
+        _ck(self.L.pimcgpu_eval_vspher(len(r), _dp(r), _dp(v), _dp(rc)))
+        return v, rc
 
     def pot_energy_slice(self, chain=0):
         v = np.zeros((self.N, self.P))

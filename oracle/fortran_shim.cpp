@@ -210,7 +210,8 @@ double vcalc(double r, double theta, double chi, double r0, double rmax, double 
    return v0 + gradr * delr + gradth * delth + gradch * delch;
 }
 
-const double *g_vspher_table = nullptr;   // 501 entries, set by oracle_set_vspher_table
+#include "../moribs-pimc_b200/data/vspher_table.h"   // DATA vtable of vspher.f:15-517, extracted by oracle/extract_vspher.py (input data)
+const double *g_vspher_table = PIMC_VSPHER_TABLE;   // 501 entries; oracle_set_vspher_table may point it elsewhere
 
 void reflect_finish(double *hatx, double *haty, double *hatz, double *eulang)
 {
@@ -231,7 +232,28 @@ extern "C" {
 int oracle_last_rotden_index = -1;
 int oracle_last_vcord_index = -1;
 
-void oracle_set_vspher_table(const double *t501) { g_vspher_table = t501; }
+void oracle_set_vspher_table(const double *t501) { g_vspher_table = t501 ? t501 : PIMC_VSPHER_TABLE; }
+
+// pure-function views of the table look-ups (test hooks: the same doubles go to the device's selectors)
+// rotpro_sub.f:1-64: angles in degrees; erot/esq in the tables' units (cm^-1)
+void oracle_rotpro(double phi, double theta, double chi, const double *rhoprp, const double *erotpr, const double *erotsq,
+                   double *rho, double *erot, double *esq, int *index, int *jstop)
+{
+   *jstop = 0;
+   rotpro(chi, phi, theta, rho, erot, esq, rhoprp, erotpr, erotsq, jstop, index);
+}
+// vcalc.f:1-65: r in bohr, theta and chi in degrees
+double oracle_vcalc(double r, double theta, double chi, double r0, double rmax, double rstep, int nrgrd, int nthgrd, int nchgrd,
+                    const double *vtable, int *index)
+{
+   return vcalc(r, theta, chi, r0, rmax, rstep, nrgrd, nthgrd, nchgrd, vtable, index);
+}
+// deleul, rotden.f:32-134: relative Euler angles (radians) of two orientations
+void oracle_deleul(const double *e1, const double *e2, double *rel)
+{
+   int istop = 0;
+   deleul(e1, e2, rel, &istop);
+}
 
 // rotden.f:1-31
 void rotden_(double *Eulan1, double *Eulan2, double *Eulrel, double *rho, double *erot, double *esq,
@@ -349,7 +371,7 @@ void caleng_(double *com_1, double *com_2, double *E_2H2O, double *Eulang_1, dou
 // is handed in through oracle_set_vspher_table (oracle/_ref extracts it at build time).
 void vspher_(double *r, double *vpot)
 {
-   const double r0 = 3.0, rmax = 26.0, rstep = 0.046, ang2bo = 0.5291772;
+   const double r0 = 3.0, rmax = 26.0, rstep = 0.046, ang2bo = (double)0.5291772f;   // REAL*4 literal widened (vspher.f:519 has no D exponent)
    const int maxrpt = 500;
    if (!g_vspher_table) { printf("vspher_: table not set\n"); exit(1); }
    *r = *r / ang2bo;

@@ -151,6 +151,33 @@ class Oracle:
         v = self.lib.orc_vcord(self.h, _dp(eul), _dp(rcom), _dp(rpt), _dp(rtc), C.byref(idx))
         return v, rtc, idx.value
 
+    def rotpro(self, deg3):
+        """rotpro_sub.f on (phi, theta, chi) in degrees -> rho, erot, esq (table units), flat index, jstop"""
+        d = np.ascontiguousarray(deg3, dtype=np.float64)
+        rho, erot, esq = C.c_double(), C.c_double(), C.c_double(); idx, js = C.c_int(), C.c_int()
+        self.lib.orc_rotpro(self.h, _dp(d), C.byref(rho), C.byref(erot), C.byref(esq), C.byref(idx), C.byref(js))
+        return rho.value, erot.value, esq.value, idx.value, js.value
+
+    def vcalc(self, rtc):
+        """vcalc.f on (r bohr, theta deg, chi deg) -> V, flat index"""
+        d = np.ascontiguousarray(rtc, dtype=np.float64); idx = C.c_int()
+        self.lib.orc_vcalc.restype = C.c_double
+        v = self.lib.orc_vcalc(self.h, _dp(d), C.byref(idx))
+        return v, idx.value
+
+    def deleul(self, e1, e2):
+        e1 = np.ascontiguousarray(e1, dtype=np.float64); e2 = np.ascontiguousarray(e2, dtype=np.float64)
+        rel = np.zeros(3)
+        self.lib.orc_deleul(_dp(e1), _dp(e2), _dp(rel))
+        return rel
+
+    def vspher(self, r):
+        """vspher_ -> (V, the clamped r in bohr the Fortran leaves in its argument)"""
+        rc = C.c_double()
+        self.lib.orc_vspher.restype = C.c_double
+        v = self.lib.orc_vspher(C.c_double(r), C.byref(rc))
+        return v, rc.value
+
     def caleng(self, c1, c2, e1, e2):
         a = [np.ascontiguousarray(x, dtype=np.float64) for x in (c1, c2, e1, e2)]
         return self.lib.orc_caleng(*[_dp(x) for x in a])

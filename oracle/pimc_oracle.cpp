@@ -32,6 +32,9 @@ void rflmfy_(double *, double *, double *, double *, double *);
 void rflmfz_(double *, double *, double *, double *, double *);
 void oracle_set_vspher_table(const double *);
 extern int oracle_last_rotden_index, oracle_last_vcord_index;
+void oracle_rotpro(double, double, double, const double *, const double *, const double *, double *, double *, double *, int *, int *);
+double oracle_vcalc(double, double, double, double, double, double, int, int, int, const double *, int *);
+void oracle_deleul(const double *, const double *, double *);
 }
 
 namespace {
@@ -1581,6 +1584,23 @@ double orc_vcord(orc_t *o, const double *eul, const double *rcom, const double *
 {
    double v = vcord_call(o, eul, rcom, rpt, rtc);
    if (index) *index = oracle_last_vcord_index;
+   return v;
+}
+// pure table look-ups on this handle's tables (identical doubles in -> indices and values out)
+void orc_rotpro(orc_t *o, const double *deg3 /* phi, theta, chi */, double *rho, double *erot, double *esq, int *index, int *jstop)
+{
+   oracle_rotpro(deg3[0], deg3[1], deg3[2], o->rho3, o->erot3, o->esq3, rho, erot, esq, index, jstop);
+}
+double orc_vcalc(orc_t *o, const double *rtc /* r bohr, theta deg, chi deg */, int *index)
+{
+   return oracle_vcalc(rtc[0], rtc[1], rtc[2], o->rvmin, o->rvmax, o->rvstep, o->rg3, o->thg3, o->chg3, o->v3d, index);
+}
+void orc_deleul(const double *e1, const double *e2, double *rel) { oracle_deleul(e1, e2, rel); }
+double orc_vspher(double r, double *rclamp)
+{
+   double rr = r, v;
+   vspher_(&rr, &v);
+   if (rclamp) *rclamp = rr;
    return v;
 }
 double orc_caleng(const double *c1, const double *c2, const double *e1, const double *e2)

@@ -52,6 +52,11 @@ void orc_set_rotlin(orc_t *, int n, const double *grid, const double *dens, cons
                     const double *esqr);
 void orc_set_rot3d(orc_t *, const double *rho, const double *erot, const double *esq);
 void orc_set_vspher(orc_t *, const double *t501);
+/* pure table look-ups (test hooks): rotpro_sub.f angles in degrees, vcalc.f r in bohr + degrees, deleul, vspher (clamped r out) */
+void orc_rotpro(orc_t *, const double *deg3, double *rho, double *erot, double *esq, int *index, int *jstop);
+double orc_vcalc(orc_t *, const double *rtc, int *index);
+void orc_deleul(const double *e1, const double *e2, double *rel);
+double orc_vspher(double r, double *rclamp);
 void orc_get_pot1d_setup(orc_t *, double *y2, double *alpha_unode_c6);
 
 /* state */

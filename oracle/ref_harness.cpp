@@ -127,7 +127,7 @@ int ref_init(const char *workdir, double *vtab, int rg, int thg, int chg, double
             if (vtab) {
                vtable = vtab; Rgrd = rg; THgrd = thg; CHgrd = chg; Rvmin = rvmin; Rvmax = rvmax;
                Rvstep = (Rvmax - Rvmin) / (double)(Rgrd - 1);
-            } else init_pot3D(atype);
+            } else if (!ISPHER) init_pot3D(atype);      // ISPHER = 1 never reads vtable (vspher_ carries its own DATA table)
          }
       } else init_pot1D(atype);
    }
@@ -472,6 +472,21 @@ void ref_get_exchange_acc(double *ploops, double *sff_area6, double *sff_inert9)
    for (int i = 0; i < MCAtom[BSTYPE].numb; i++) ploops[i] = _ploops[i];
    for (int i = 0; i < 6; i++) sff_area6[i] = _areas3DSFF[i];
    for (int i = 0; i < 9; i++) sff_inert9[i] = _inert3DSFF[i];
+}
+// every block accumulator the observables of north_star need, as MCGetAverage left them: _rcf[0][0..Q-1],
+// linear-dopant area sums {_areas[2], _area2[2], _inert[2]} and the 3-D tensors {areas6, inert9} in both frames
+void ref_get_block_acc(double *rcf0, double *lin6, double *sff15, double *mff15)
+{
+   if (rcf0) for (int i = 0; i < NumbRotTimes; i++) rcf0[i] = _rcf[0][i];
+   if (lin6) for (int i = 0; i < 2; i++) { lin6[i] = _areas[i]; lin6[2 + i] = _area2[i]; lin6[4 + i] = _inert[i]; }
+   if (sff15) { for (int i = 0; i < 6; i++) sff15[i] = _areas3DSFF[i]; for (int i = 0; i < 9; i++) sff15[6 + i] = _inert3DSFF[i]; }
+   if (mff15) { for (int i = 0; i < 6; i++) mff15[i] = _areas3DMFF[i]; for (int i = 0; i < 9; i++) mff15[6 + i] = _inert3DMFF[i]; }
+}
+void ref_reset_area_acc(void)
+{
+   for (int i = 0; i < 2; i++) { _areas[i] = 0.0; _area2[i] = 0.0; _inert[i] = 0.0; }
+   for (int i = 0; i < 6; i++) { _areas3DSFF[i] = 0.0; _areas3DMFF[i] = 0.0; }
+   for (int i = 0; i < 9; i++) { _inert3DSFF[i] = 0.0; _inert3DMFF[i] = 0.0; }
 }
 void ref_reset_exchange_acc(void)
 {

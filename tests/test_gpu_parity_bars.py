@@ -1,0 +1,494 @@
+"""GPU parity at the bars BASELINE.json's north_star states, split the way SURVEY.md section 7 asks:
+
+ (1) TABLE-INDEX SELECTION IS BIT-EXACT: the selectors of rotpro (rotpro_sub.f:7-9), vcalc (vcalc.f:16-25), LPot2D
+     (mc_poten.cc:696-704) and splint (mc_utils.cc:170-176) are pure functions of a few doubles; device and oracle are fed
+     the SAME doubles and the flat indices must be identical for every point, grid lines and range ends included;
+ (2) what is NOT bit-identical between the device and the host is libm (sin/cos/acos/atan): bounded separately in ulps;
+ (3) composed leaves (Euler angles -> relative angles -> degrees -> table): the device's own intermediate doubles are
+     pushed through the oracle's selector (identical index, value to 1e-12), and the value differences against the oracle's
+     end-to-end result are asserted at 1e-10 wherever the geometry is well conditioned, and explained by the measured
+     angle drift times the table gradient everywhere;
+ (4) the Fortran leaves are pinned as far as the reference's tree allows: a real asymrho table plane (nmv_prop/rho.den010_*)
+     through rotpro, an independent first-principles TIP4P evaluation for caleng_, rotation invariance of vcord_;
+ (5) per-slice potential / kinetic / rotational energies at 1e-10 on the FULL-SIZE configurations C1-C4 (shipped
+     xyz.init of C2/C3, P = 4096 / Q = 2048 for C4) with the full-size tables;
+ (6) ISPHER = 1 (vspher_, row a21): leaf, PotEnergy and the clamped-r binning quirk.
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+RTOL = 1e-10
+
+
+def _oracle():
+    from oracle import oracle_py as op
+    return op
+
+
+def ulp_diff(a, b):
+    """distance in units of the last place of b (float64)"""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.abs(a - b) / np.spacing(np.maximum(np.abs(b), 1e-300))
+
+
+def _unit(rng, n):
+    u = rng.standard_normal((n, 3))
+    return u / np.linalg.norm(u, axis=1)[:, None]
+
+
+def _euler(rng, n):
+    return np.c_[rng.uniform(0, 2 * np.pi, n), np.arccos(rng.uniform(-1, 1, n)), rng.uniform(0, 2 * np.pi, n)]
+
+
+@pytest.fixture(scope="module")
+def c1(pkg):
+    """He + HCOOCH3 top with the full-size tables (181x361x361 rho/E/E^2, 501x181x181 potential)"""
+    op = _oracle()
+    cfg = pkg.configs.make_config("C1", P=64, Q=16)
+    return cfg, op.Oracle(cfg)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# (1) pure selectors
+# ----------------------------------------------------------------------------------------------------------------------
+def test_rotpro_selector_bit_exact(pkg, c1):
+    cfg, O = c1
+    G = pkg.gpu.PimcGpu(cfg)
+    rng = np.random.default_rng(101)
+    n = 20000
+    deg = np.c_[rng.uniform(0, 360, n), rng.uniform(0, 180, n), rng.uniform(0, 360, n)]
+    # grid lines, last grid lines, one ulp either side of a grid line
+    k = rng.integers(0, 360, 3000).astype(float)
+    edge = np.c_[k, np.minimum(k, 179.0), k[::-1]]
+    special = np.array([[0, 0, 0], [360, 180, 360], [360, 0, 0], [0, 180, 0], [0, 0, 360], [359.99999999999994, 179.99999999999997, 359.99999999999994],
+                        [1e-300, 1e-300, 1e-300], [360.0, 90.5, 12.25], [12.25, 180.0, 360.0]])
+    deg = np.r_[deg, edge, np.nextafter(edge, -1.0).clip(0), np.nextafter(edge, 1e9), special]
+    rho, erot, esq, idx = G.eval_rotpro(deg)
+    o = np.array([O.rotpro(d) for d in deg])
+    assert np.array_equal(idx, o[:, 3].astype(np.int64)), f"{(idx != o[:, 3]).sum()} rho-table indices differ on identical doubles"
+    assert np.all(o[:, 4] == 0)
+    for name, g, r in (("rho", rho, o[:, 0]), ("erot", erot, o[:, 1]), ("esq", esq, o[:, 2])):
+        err = np.max(np.abs(g - r) / np.maximum(np.abs(r), 1e-300))
+        print(f"rotpro {name}: max relative difference on identical inputs {err:.2e}")
+        assert err < 1e-12
+    # out-of-range angles: the Fortran resets the index to 0 and raises jstop (rotpro_sub.f:10-24)
+    bad = np.array([[361.5, 10.0, 10.0], [10.0, 181.2, 10.0], [10.0, 10.0, 400.0], [-1.5, 10.0, 10.0]])
+    _, _, _, ib = G.eval_rotpro(bad)
+    ob = np.array([O.rotpro(d) for d in bad])
+    assert np.all(ob[:, 4] == 1) and np.array_equal(ib, -1 - ob[:, 3].astype(np.int64))
+    G.close()
+
+
+@pytest.mark.parametrize("name", ["C1", "C3"])
+def test_vcalc_selector_bit_exact(pkg, name):
+    """chi grids of 181 (C1/C2) and 91 (C3) points; r clamped to the table's range in bohr"""
+    op = _oracle()
+    cfg = pkg.configs.make_config(name, P=64, Q=16)
+    O = op.Oracle(cfg)
+    G = pkg.gpu.PimcGpu(cfg)
+    rg, thg, chg, rmin, rmax, _ = cfg.tables["pot3d"]
+    rng = np.random.default_rng(102)
+    n = 20000
+    rtc = np.c_[rng.uniform(rmin - 1.0, rmax + 1.0, n), rng.uniform(0, 180, n), rng.uniform(0, chg - 1.0, n)]
+    step = (rmax - rmin) / (rg - 1)
+    kr = rmin + step * rng.integers(0, rg, 3000)
+    kt = rng.integers(0, thg, 3000).astype(float)
+    kc = rng.integers(0, chg, 3000).astype(float)
+    edge = np.c_[kr, kt, kc]
+    special = np.array([[rmin, 0, 0], [rmax, 180, chg - 1.0], [rmax, 0, 0], [rmin, 180.0, 0], [rmin, 0, chg - 1.0], [rmax + 5, 180.0, chg + 20.0],
+                        [rmin - 5, 179.99999999999997, chg - 1.0 - 1e-13]])
+    rtc = np.r_[rtc, edge, np.nextafter(edge, -1.0).clip(0), np.nextafter(edge, 1e9), special]
+    v, idx = G.eval_vcalc(rtc)
+    o = np.array([O.vcalc(x) for x in rtc])
+    assert np.array_equal(idx, o[:, 1].astype(np.int64)), f"{(idx != o[:, 1]).sum()} potential-table indices differ on identical doubles"
+    err = np.max(np.abs(v - o[:, 0]) / np.maximum(np.abs(o[:, 0]), 1e-6))
+    print(f"vcalc[{name}]: max relative difference on identical inputs {err:.2e}")
+    assert err < 1e-12
+    G.close()
+
+
+def test_lpot2d_and_splint_selectors_on_grid_lines(pkg):
+    """LPot2D cell indices and the splint interval on exact grid points and one ulp either side of them"""
+    op = _oracle()
+    cfg = pkg.configs.make_config("C5", P=32, Q=8, nsolv=6)
+    G = pkg.gpu.PimcGpu(cfg)
+    O = op.Oracle(cfg)
+    rg, cg, _ = cfg.tables["pot2d"]
+    rng = np.random.default_rng(103)
+    ri = rg[rng.integers(0, len(rg), 4000)]
+    ci = cg[rng.integers(0, len(cg), 4000)]
+    r = np.r_[ri, np.nextafter(ri, 0), np.nextafter(ri, 99), rg[0] - 0.5, rg[-1] + 0.5, rg[-1], rg[0]]
+    c = np.r_[ci, np.nextafter(ci, -9), np.nextafter(ci, 9), -1.2, 1.2, cg[-1], cg[0]]
+    v, ir, ic = G.eval_lpot2d(r, c)
+    o = np.array([O.lpot2d(a, b) for a, b in zip(r, c)])
+    assert np.array_equal(ir, o[:, 1].astype(np.int64)) and np.array_equal(ic, o[:, 2].astype(np.int64))
+    assert np.max(np.abs(v - o[:, 0]) / np.maximum(np.abs(o[:, 0]), 1e-9)) < RTOL
+    g = cfg.tables["pot1d"][0]
+    x = np.r_[g, np.nextafter(g, 0), np.nextafter(g, 99)]
+    v, k = G.eval_spot1d(x)
+    o = np.array([O.spot1d(a) for a in x])
+    assert np.array_equal(k, o[:, 1].astype(np.int64))
+    assert np.max(np.abs(v - o[:, 0]) / np.maximum(np.abs(o[:, 0]), 1e-300)) < RTOL
+    G.close()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# (2) libm
+# ----------------------------------------------------------------------------------------------------------------------
+def test_device_libm_within_ulps_of_glibc(pkg):
+    """The only arithmetic that is not bit-identical between the device and the host path: CUDA's sin/cos/acos/atan/exp/log
+    against glibc's through numpy.  sqrt and the basic operations are IEEE-exact on both sides."""
+    rng = np.random.default_rng(7)
+    n = 200000
+    cases = {
+        "sin": (rng.uniform(-2 * np.pi, 4 * np.pi, n), np.sin, 2),
+        "cos": (rng.uniform(-2 * np.pi, 4 * np.pi, n), np.cos, 2),
+        "acos": (np.r_[rng.uniform(-1, 1, n), 1 - 10.0 ** rng.uniform(-16, -1, 5000), -1 + 10.0 ** rng.uniform(-16, -1, 5000), -1.0, 1.0, 0.0], np.arccos, 2),
+        "atan": (np.r_[10.0 ** rng.uniform(-12, 12, n), 0.0], np.arctan, 2),
+        "exp": (rng.uniform(-60, 20, n), np.exp, 2),
+        "log": (np.r_[rng.uniform(0, 1, n), 10.0 ** rng.uniform(-300, 300, 5000)], np.log, 2),
+        "sqrt": (10.0 ** rng.uniform(-300, 300, n), np.sqrt, 0),
+        "fmod2pi": (rng.uniform(0, 40, n), lambda x: np.fmod(x, 2 * np.pi), 0),
+    }
+    for name, (x, f, bar) in cases.items():
+        x = x[x != 0.0] if name == "log" else x
+        y = pkg.gpu.eval_libm(name, x)
+        d = ulp_diff(y, f(x))
+        print(f"libm {name}: max {d.max():.2f} ulp, {np.mean(d > 0) * 100:.2f} % of {len(x)} points differ")
+        assert d.max() <= bar, f"{name}: {d.max()} ulp"
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# (3) composed leaves
+# ----------------------------------------------------------------------------------------------------------------------
+def test_rotden_composed_through_device_intermediates(pkg, c1):
+    """rotden_ = deleul -> degrees -> rotpro.  The device's relative angles go through the ORACLE's degrees conversion and
+    selector: index identical to the device's, values to 1e-12 -- so the only device/host difference is the angle drift
+    of deleul (sincos/acos ulps, conditioned by 1/sin(theta_rel)), which is measured and bounded here."""
+    cfg, O = c1
+    G = pkg.gpu.PimcGpu(cfg)
+    rng = np.random.default_rng(11)
+    n = 6000
+    e1 = _euler(rng, n)
+    e2 = e1 + 0.15 * rng.standard_normal((n, 3))          # neighbouring slices: small relative rotation
+    e2[:, 1] = np.clip(e2[:, 1], 0, np.pi)
+    e2[: n // 4] = _euler(rng, n // 4)
+    rho, erot, esq, idx = G.eval_rotden(e1, e2)
+    rel = G.eval_deleul(e1, e2)
+    # (a) the device's own angles through the oracle's conversion and selector (Fortran order: angle*180/pi)
+    deg = rel * 180.0 / np.pi
+    o = np.array([O.rotpro(d) for d in deg])
+    assert np.array_equal(idx, o[:, 3].astype(np.int64)), "device index != oracle selector on the device's own angles"
+    wn = 0.6950356
+    for name, g, r in (("rho", rho, o[:, 0]), ("erot", erot, o[:, 1] / wn), ("esq", esq, o[:, 2] / (wn * wn))):
+        err = np.max(np.abs(g - r) / np.maximum(np.abs(r), 1e-300))
+        print(f"rotden {name} via device angles: {err:.2e}")
+        assert err < 1e-12
+    # (b) angle drift device vs oracle, scaled by the conditioning of the extraction
+    orel = np.array([O.deleul(a, b) for a, b in zip(e1, e2)])
+    drift = np.abs(rel - orel)
+    st = np.abs(np.sin(orel[:, 1]))
+    # acos of a ratio m/sin(theta): relative perturbations of a few ulp are amplified by 1/sin(theta_rel) and by 1/|sin(angle)|
+    cond = 1.0 / np.maximum(st, 1e-12)
+    cphi = 1.0 / np.maximum(np.abs(np.sin(orel[:, 0])), 1e-12)
+    cchi = 1.0 / np.maximum(np.abs(np.sin(orel[:, 2])), 1e-12)
+    bound = 16 * np.finfo(float).eps * np.c_[cond * cphi, cond, cond * cchi] + 8 * np.finfo(float).eps * 2 * np.pi
+    wrapped = np.minimum(drift, np.abs(2 * np.pi - drift))      # phi/chi at the 0 / 2 pi seam
+    drift[:, 0], drift[:, 2] = wrapped[:, 0], wrapped[:, 2]
+    print(f"deleul angle drift: max {drift.max():.2e} rad, max drift/bound {np.max(drift / bound):.2f}")
+    assert np.all(drift <= bound)
+    # (c) end to end at 1e-10 wherever the extraction is well conditioned (cond < 1e3) and the index agrees
+    oo = [O.rotden(a, b) for a, b in zip(e1, e2)]
+    oidx = np.array([x[3] for x in oo]); orho, oerot, oesq = (np.array([x[i] for x in oo]) for i in range(3))
+    same = idx == oidx
+    # an index may differ only where an angle in degrees sits within the drift of an integer
+    odeg = orel * 180.0 / np.pi
+    near = np.min(np.abs(odeg - np.rint(odeg)), axis=1)
+    assert np.all(near[~same] <= (drift.max(axis=1) * 180.0 / np.pi)[~same] + 1e-300), "index differs away from a grid line"
+    well = same & (cond * np.maximum(cphi, cchi) < 1e3)
+    print(f"rotden end to end: {same.mean() * 100:.3f} % identical indices, {well.mean() * 100:.1f} % well conditioned")
+    assert same.mean() > 0.999 and well.mean() > 0.9
+    for name, g, r in (("rho", rho, orho), ("erot", erot, oerot), ("esq", esq, oesq)):
+        err = np.abs(g - r) / np.maximum(np.abs(r), 1e-290)
+        print(f"   {name}: max relative difference {err[well].max():.2e} (well conditioned), {err[same].max():.2e} (all)")
+        assert err[well].max() < RTOL
+    # everywhere: the difference is the table gradient times the measured angle drift (degrees), nothing else
+    dd = np.abs(deg - odeg)
+    dd[:, 0] = np.minimum(dd[:, 0], np.abs(360.0 - dd[:, 0])); dd[:, 2] = np.minimum(dd[:, 2], np.abs(360.0 - dd[:, 2]))
+    t = cfg.tables["rot3d"][0]
+    ii = oidx[same]
+    grad = np.c_[np.abs(t[np.minimum(ii + 361, len(t) - 1)] - t[ii]), np.abs(t[np.minimum(ii + 361 * 361, len(t) - 1)] - t[ii]), np.abs(t[np.minimum(ii + 1, len(t) - 1)] - t[ii])]
+    explained = (grad * dd[same]).sum(axis=1) * 1.0000001 + 1e-13 * np.abs(orho[same])
+    assert np.all(np.abs(rho[same] - orho[same]) <= explained + 1e-300)
+    G.close()
+
+
+def test_vcord_composed_through_device_intermediates(pkg, c1):
+    cfg, O = c1
+    G = pkg.gpu.PimcGpu(cfg)
+    rng = np.random.default_rng(12)
+    n = 6000
+    eul = _euler(rng, n)
+    rcom = rng.uniform(-1, 1, (n, 3))
+    rpt = rcom + rng.uniform(2.2, 9.0, (n, 1)) * _unit(rng, n)
+    v, rtc, vidx = G.eval_vcord(eul, rcom, rpt)
+    grid = G.eval_vcord_grid(eul, rcom, rpt)
+    o = np.array([O.vcalc(x) for x in grid])
+    assert np.array_equal(vidx, o[:, 1].astype(np.int64)), "device index != oracle selector on the device's own (r, theta, chi)"
+    assert np.max(np.abs(v - o[:, 0]) / np.maximum(np.abs(o[:, 0]), 1e-6)) < 1e-12
+    oo = [O.vcord(a, b, c) for a, b, c in zip(eul, rcom, rpt)]
+    ov = np.array([x[0] for x in oo]); ortc = np.array([x[1] for x in oo]); oidx = np.array([x[2] for x in oo])
+    drift = np.abs(rtc - ortc)
+    print(f"vcord (r, theta, chi) drift: {drift.max(axis=0)}")
+    # theta = acos(z.R/|R|): conditioned by 1/sin(theta); chi = atan(|Ry/Rx|) is well conditioned; r is a sqrt (exact ops + FMA)
+    st = np.maximum(np.abs(np.sin(ortc[:, 1])), 1e-12)
+    assert np.all(drift[:, 0] <= 4 * np.spacing(ortc[:, 0])) and np.all(drift[:, 1] <= 16 * np.finfo(float).eps / st + 4e-16) and np.all(drift[:, 2] <= 3e-15)
+    same = vidx == oidx
+    deg = np.c_[ortc[:, 1] * 180 / np.pi, np.minimum(ortc[:, 2], 2 * np.pi - ortc[:, 2]) * 180 / np.pi]
+    near = np.min(np.abs(deg - np.rint(deg)), axis=1)
+    rb = ortc[:, 0] / 0.529177249
+    rq = (np.clip(rb, 4.0, 20.0) - 4.0) / ((20.0 - 4.0) / 500)
+    near = np.minimum(near, np.abs(rq - np.rint(rq)))
+    assert np.all(near[~same] < 1e-9), "index differs away from a grid line"
+    well = same & (st > 1e-3)
+    err = np.abs(v - ov) / np.maximum(np.abs(ov), 1e-6)
+    print(f"vcord end to end: {same.mean() * 100:.3f} % identical indices; max relative difference {err[well].max():.2e} (sin theta > 1e-3), {err[same].max():.2e} (all)")
+    assert same.mean() > 0.999 and err[well].max() < RTOL
+    G.close()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# (4) pins of the Fortran leaves
+# ----------------------------------------------------------------------------------------------------------------------
+def test_rotpro_on_the_references_own_table_plane(pkg):
+    """nmv_prop/rho.den010_{rho,eng,esq}: the theta = 10 degree plane of a REAL asymrho table from the reference's tree
+    (fixture tests/golden/tablegen/ref_asymrho_den010.npz).  The plane is placed at itheta = 10 and 11 of an otherwise
+    smooth table; the device look-up on that plane must equal (i) the oracle's rotpro and (ii) an independent numpy
+    forward-difference interpolation written from rotpro_sub.f:26-61 -- to 1e-12, indices identical."""
+    op = _oracle()
+    fx = os.path.join(ROOT, "tests", "golden", "tablegen", "ref_asymrho_den010.npz")
+    if not os.path.exists(fx):
+        pytest.skip("fixture missing")
+    z = np.load(fx)
+    plane = {k: z[k].reshape(361, 361) for k in ("rho", "eng", "esq")}
+    cfg = pkg.configs.make_config("C1", P=64, Q=16)
+    tabs = [t.reshape(181, 361, 361).copy() for t in cfg.tables["rot3d"]]
+    for t, k in zip(tabs, ("rho", "eng", "esq")):
+        t[10] = plane[k]; t[11] = plane[k] * 1.03
+    cfg.tables["rot3d"] = tuple(np.ascontiguousarray(t.reshape(-1)) for t in tabs)
+    G = pkg.gpu.PimcGpu(cfg)
+    O = op.Oracle(cfg)
+    rng = np.random.default_rng(5)
+    n = 20000
+    deg = np.c_[rng.uniform(0, 360, n), rng.uniform(10, 11, n), rng.uniform(0, 360, n)]
+    rho, erot, esq, idx = G.eval_rotpro(deg)
+    o = np.array([O.rotpro(d) for d in deg])
+    assert np.array_equal(idx, o[:, 3].astype(np.int64))
+    ip, it, ic = deg[:, 0].astype(int), deg[:, 1].astype(int), deg[:, 2].astype(int)
+    assert np.array_equal(idx, (it * 361 + ip) * 361 + ic)
+    for g, col, t in ((rho, 0, tabs[0]), (erot, 1, tabs[1]), (esq, 2, tabs[2])):
+        f0 = t[it, ip, ic]
+        ind = f0 + (t[it, ip, ic + 1] - f0) * (deg[:, 2] - ic) + (t[it, ip + 1, ic] - f0) * (deg[:, 0] - ip) + (t[it + 1, ip, ic] - f0) * (deg[:, 1] - it)
+        scale = np.maximum(np.abs(ind), 1e-12 * np.abs(t[10]).max())
+        assert np.max(np.abs(g - o[:, col]) / scale) < 1e-12
+        assert np.max(np.abs(g - ind) / scale) < 1e-12
+    G.close()
+
+
+def _rotmat(e):
+    """matpre (rotden.f:136-163) in numpy, independent of the repo's C++/CUDA code"""
+    cp, sp, ct, st, ck, sk = np.cos(e[0]), np.sin(e[0]), np.cos(e[1]), np.sin(e[1]), np.cos(e[2]), np.sin(e[2])
+    return np.array([[cp * ct * ck - sp * sk, -cp * ct * sk - sp * ck, cp * st],
+                     [sp * ct * ck + cp * sk, -sp * ct * sk + cp * ck, sp * st],
+                     [-st * ck, st * sk, ct]])
+
+
+def test_caleng_against_first_principles_tip4p(pkg):
+    """TIP4P from its definition, independent of both the device code and the oracle's restatement: sites O(0,0,.06562)
+    H(+-.7557,0,-.5223) M(0,0,-.08438) Angstrom in the body frame (caleng_tip4p_gg.f:37-39), O-O Lennard-Jones
+    6e5/r^12 - 610/r^6 kcal/mol, charges qM = -1.04, qH = 0.52 e with e^2/(4 pi eps0) = hartree*bohr
+    (3.1577465e5 K x 0.52917721092 Angstrom), 1 kcal/mol = 503.218978939 K."""
+    rng = np.random.default_rng(21)
+    n = 3000
+    c1 = rng.uniform(-1, 1, (n, 3)); c2 = c1 + rng.uniform(2.4, 8.0, (n, 1)) * _unit(rng, n)
+    e1, e2 = _euler(rng, n), _euler(rng, n)
+    cfg = pkg.configs.make_config("C4", P=64, Q=32)
+    G = pkg.gpu.PimcGpu(cfg)
+    G_e = G.eval_caleng(c1, c2, e1, e2)
+    G.close()
+    body = {"O": np.array([0, 0, 0.06562]), "H1": np.array([0.7557, 0, -0.5223]), "H2": np.array([-0.7557, 0, -0.5223]), "M": np.array([0, 0, -0.08438])}
+    q = {"H1": 0.52, "H2": 0.52, "M": -1.04}
+    coul = 3.1577465e5 * 0.52917721092
+    ref = np.zeros(n)
+    for i in range(n):
+        Ra, Rb = _rotmat(e1[i]), _rotmat(e2[i])
+        sa = {k: c1[i] + Ra @ v for k, v in body.items()}
+        sb = {k: c2[i] + Rb @ v for k, v in body.items()}
+        roo = np.linalg.norm(sa["O"] - sb["O"])
+        e = (6.0e5 / roo ** 12 - 610.0 / roo ** 6) * 503.218978939
+        for ka, qa in q.items():
+            for kb, qb in q.items():
+                e += qa * qb * coul / np.linalg.norm(sa[ka] - sb[kb])
+        ref[i] = e
+    # ten terms of both signs: bound the error by the sum of magnitudes, not by the (possibly cancelling) total
+    scale = np.maximum(np.abs(ref), 1.0)
+    err = np.max(np.abs(G_e - ref) / scale)
+    print(f"caleng vs independent TIP4P: max difference / max(|E|, 1 K) = {err:.2e}")
+    assert err < RTOL
+
+
+def test_vcord_invariances(pkg, c1):
+    """Properties vcord_ must have whatever its implementation: V depends on the particle's position only through the
+    body-frame (r, theta, chi) -- a rigid rotation of the whole system leaves it unchanged (checked through (r, theta, chi)
+    to 1e-12 and V to 1e-10 away from grid lines), translation invariance, and the returned body-frame coordinates equal
+    an independent numpy projection onto the matpre axes."""
+    cfg, O = c1
+    G = pkg.gpu.PimcGpu(cfg)
+    rng = np.random.default_rng(33)
+    n = 4000
+    eul = _euler(rng, n)
+    rcom = rng.uniform(-1, 1, (n, 3))
+    d = rng.uniform(2.5, 8.0, (n, 1)) * _unit(rng, n)
+    v0, rtc0, i0 = G.eval_vcord(eul, rcom, rcom + d)
+    # independent projection
+    R = np.array([_rotmat(e) for e in eul])                       # columns = body axes in the space frame
+    body = np.einsum("nij,ni->nj", R, d)
+    r = np.linalg.norm(d, axis=1)
+    th = np.arccos(np.clip(body[:, 2] / r, -1, 1))
+    ch = np.mod(np.arctan2(body[:, 1], body[:, 0]), 2 * np.pi)
+    assert np.max(np.abs(rtc0[:, 0] - r)) < 1e-12 and np.max(np.abs(rtc0[:, 1] - th)) < 1e-9
+    dch = np.abs(rtc0[:, 2] - ch); dch = np.minimum(dch, 2 * np.pi - dch)
+    assert np.max(dch) < 1e-9
+    # translation
+    shift = rng.uniform(-50, 50, (n, 3))
+    v1, rtc1, i1 = G.eval_vcord(eul, rcom + shift, rcom + shift + d)
+    assert np.max(np.abs(rtc1 - rtc0)) < 1e-12
+    same = i1 == i0
+    assert same.mean() > 0.999 and np.max(np.abs(v1 - v0)[same] / np.maximum(np.abs(v0[same]), 1e-6)) < 1e-9
+    # rigid rotation by S: orientation S*R has Euler angles extracted here in numpy; positions rotate with it
+    S = _rotmat(np.array([0.7, 1.1, 2.3]))
+    R2 = np.einsum("ij,njk->nik", S, R)
+    th2 = np.arccos(np.clip(R2[:, 2, 2], -1, 1))
+    ph2 = np.mod(np.arctan2(R2[:, 1, 2], R2[:, 0, 2]), 2 * np.pi)
+    ch2 = np.mod(np.arctan2(R2[:, 2, 1], -R2[:, 2, 0]), 2 * np.pi)
+    eul2 = np.c_[ph2, th2, ch2]
+    d2 = d @ S.T
+    v2, rtc2, i2 = G.eval_vcord(eul2, rcom, rcom + d2)
+    dd = np.abs(rtc2 - rtc0); dd[:, 2] = np.minimum(dd[:, 2], 2 * np.pi - dd[:, 2])
+    st = np.maximum(np.sin(th), 1e-6)
+    assert np.max(dd[:, 0]) < 1e-12 and np.max(dd[:, 1] * st) < 1e-12 and np.max(dd[:, 2] * st) < 1e-11
+    same = i2 == i0
+    assert same.mean() > 0.99 and np.max(np.abs(v2 - v0)[same] / np.maximum(np.abs(v0[same]), 1e-6)) < 1e-8
+    G.close()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# (5) full-size configurations
+# ----------------------------------------------------------------------------------------------------------------------
+def _bead_scale(po):
+    """scale of the per-bead comparison: a bead's potential is a sum of pair terms of both signs, so the bar is relative
+    to max(|E_bead|, typical |E_bead|) -- stated here, printed below"""
+    return np.maximum(np.abs(po), np.median(np.abs(po)))
+
+
+@pytest.mark.parametrize("name,nsteps", [("C1", 40), ("C2", 40), ("C3", 40), ("C4", 24)])
+def test_full_size_configurations(pkg, name, nsteps):
+    """BASELINE configs[0..3] at the decks' own sizes with the full-size tables: C1 (P=512, Q=128), C2 (N=9, shipped
+    xyz.init with its permutation), C3 (N=5, P=1024, Q=256, shipped xyz.init), C4 (P=4096, Q=2048, TIP4P).  First on the
+    start configuration (for C2/C3 the equilibrated configuration the reference ships), then on the configuration the
+    device reaches after a stretch of sampling: PotEnergy of every bead, <K>, <V>, <E_rot>, E^2 sums, the correlation
+    function and the histograms against the oracle -- at 1e-10."""
+    op = _oracle()
+    cfg = pkg.configs.make_config(name)
+    s = cfg.system
+    assert (s.P, s.Q) == {"C1": (512, 128), "C2": (512, 128), "C3": (1024, 256), "C4": (4096, 2048)}[name]
+    G = pkg.gpu.PimcGpu(cfg, nchains=2)
+    O = op.Oracle(cfg)
+    G.seed((5, 6, 7, 8, 9, 10))
+    for stage in ("start", "sampled"):
+        if stage == "sampled":
+            G.steps(nsteps)
+            c, a, _ = G.download(1)
+            perm = G.download_perm(1) if cfg.perm is not None else None
+            O.set_state(c, a, perm)
+        pe = G.pot_energy_slice(1)
+        po = np.array([[O.pot_energy_it(at, it) for it in range(s.P)] for at in range(s.N)])
+        err = np.max(np.abs(pe - po) / _bead_scale(po))
+        e = G.chain_energies(1)
+        ko, vo = O.get_kin(), O.get_pot(0)
+        srot, esq, eterm = O.get_rot_energy()
+        errs = dict(bead=err, K=abs(e["kin"] - ko) / abs(ko), V=abs(e["pot"] - vo) / abs(vo), Erot=abs(e["rot"] - srot) / abs(srot),
+                    Esq=abs(e["erotsq"] - esq) / abs(esq), Eterm=abs(e["eterm"] - eterm) / abs(eterm))
+        rcf = np.max(np.abs(G.chain_rcf(1) - O.get_rcf())) / s.Q
+        print(f"{name} {stage}: " + " ".join(f"{k} {v:.2e}" for k, v in errs.items()) + f" rcf {rcf:.2e}")
+        for k, v in errs.items():
+            assert v < RTOL, f"{name} {stage} {k}: {v}"
+        assert rcf < RTOL
+        assert abs(pe.sum() / (2.0 * s.P) - e["pot"]) <= RTOL * abs(e["pot"])          # every pair term appears once per partner
+    G.close()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# (6) ISPHER = 1
+# ----------------------------------------------------------------------------------------------------------------------
+def test_vspher_table_fixture_matches_the_header(pkg):
+    """the table the driver compiles in == the committed text fixture (both made by oracle/extract_vspher.py)"""
+    t = pkg.configs.load_vspher_table()
+    g = np.loadtxt(os.path.join(ROOT, "tests", "golden", "vspher_table.txt"))
+    assert t.shape == (501,) and np.array_equal(t, g)
+    assert np.array_equal(t, t.astype(np.float32).astype(np.float64))          # REAL*4 literals widened to double
+
+
+def test_ispher_leaf_potential_and_clamped_binning(pkg):
+    """Row a21: negative species count (mc_input.cc:152-156) -> vspher_ (vspher.f:12-544) in PotEnergy
+    (mc_piqmc.cc:1913-1922) and in GetPotEnergy_Densities, which bins the clamped r in BOHR that vspher_ leaves in its
+    argument (mc_estim.cc:631-637)."""
+    op = _oracle()
+    cfg = pkg.configs.make_config("SPH", P=64, nsolv=4)
+    s = cfg.system
+    assert s.ispher == 1 and s.Q == 0
+    G = pkg.gpu.PimcGpu(cfg, nchains=2)
+    O = op.Oracle(cfg)
+    rng = np.random.default_rng(9)
+    a2b = float(np.float32(0.5291772))
+    r = np.r_[rng.uniform(0.5, 16.0, 20000), 3.0 * a2b, 26.0 * a2b, (3.0 + 0.046 * np.arange(501)) * a2b, 0.1, 40.0]
+    v, rc = G.eval_vspher(r)
+    o = np.array([O.vspher(x) for x in r])
+    assert np.array_equal(rc, o[:, 1]), "clamped r (bohr) differs"
+    assert np.max(np.abs(v - o[:, 0]) / np.maximum(np.abs(o[:, 0]), 1e-6)) < 1e-12
+    assert rc.min() == 3.0 and rc.max() == 26.0
+    # PotEnergy of every bead and the estimators
+    pe = G.pot_energy_slice(1)
+    po = np.array([[O.pot_energy_it(at, it) for it in range(s.P)] for at in range(s.N)])
+    assert np.max(np.abs(pe - po) / _bead_scale(po)) < RTOL
+    e = G.chain_energies(1)
+    assert abs(e["kin"] - O.get_kin()) <= RTOL * abs(O.get_kin()) and abs(e["pot"] - O.get_pot(0)) <= RTOL * abs(O.get_pot(0))
+    # moves: the device trajectory equals the oracle's replay (bisection + whole-path moves through vspher)
+    seed = (3, 1, 4, 1, 5, 9)
+    G.seed(seed); O.sched_seed(seed, 1)
+    nst = 2 * s.P + 3
+    G.steps(nst); O.sched_run(0, nst)
+    cg, _, _ = G.download(1)
+    co, _, _ = O.get_state()
+    assert np.abs(cg - co).max() < 1e-9
+    # density binning: the atom-top histogram holds the CLAMPED distance in bohr
+    G2 = pkg.gpu.PimcGpu(cfg, nchains=1)
+    G2.upload(0, co, cfg.angles, cfg.perm)
+    G2.accum_reset(); G2.seed(seed); G2.measure()
+    acc, lay = G2.accum_download()
+    O.reset_hist(); O.get_pot(1)
+    h = O.get_hist()
+    g3 = acc[lay["gr3d"]:lay["gr3d"] + 1500000]
+    assert g3.sum() == h["gr3d_atoms"].sum() == s.types[0].numb * s.P
+    assert np.abs(g3 - h["gr3d_atoms"]).sum() <= 2
+    # all counts sit in the theta = chi = 0 bin, radial bin of r_clamped[bohr]/0.05
+    nz = np.nonzero(g3.reshape(300, 50, 100))
+    assert np.all(nz[1] == 0) and np.all(nz[2] == 0)
+    d = np.linalg.norm(co[:, :s.types[0].numb * s.P].reshape(3, -1, s.P) - co[:, -s.P:][:, None, :], axis=0)
+    assert nz[0].min() >= int(min(np.clip(d.min() / a2b, 3.0, 26.0) / 0.05 - 1, 299))
+    assert np.array_equal(acc[lay["gr1d"]:lay["gr1d"] + 300], h["gr1d"])
+    G2.close()

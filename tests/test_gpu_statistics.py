@@ -92,6 +92,63 @@ def test_rotor_in_solvent_cluster_matches_reference(pkg):
     compare(g, r, [(0, "K"), (1, "V"), (2, "E_rot")])
 
 
+def _stats_case(pkg, case, nchains, gpu_per_block, min_sigma_cols=()):
+    """Converged observables of north_star -- <K>, <V>, <E_rot>, the orientational correlation <n(0).n(t)> (GetRCF) and the
+    superfluid fractions of the .sup / .sffs3d / .mffs3d files -- sampled by the CUDA path against a committed fixture of the
+    REFERENCE's own sampling (tests/golden/stats/<case>_ref.json, made here by profiles/stats_ref.py from oracle/_ref:
+    the reference's unmodified move and estimator objects).  2 sigma of the combined block errors, column by column."""
+    import json
+    sys.path.insert(0, os.path.join(ROOT, "profiles"))
+    import stats_ref
+    fx = os.path.join(ROOT, "tests", "golden", "stats", case + "_ref.json")
+    if not os.path.exists(fx):
+        pytest.skip("fixture missing: run profiles/stats_ref.py where /root/reference exists")
+    d = json.load(open(fx))
+    r = np.array(d["rows"])
+    cfg = pkg.configs.make_config(d["config"], **d["kw"])
+    s = cfg.system
+    skip = d["skip"]
+    G = pkg.gpu.PimcGpu(cfg, nchains=nchains)
+    G.seed((12345,) * 6)
+    G.steps(200 * s.P)
+    rows = []
+    for b in range(len(r)):
+        G.accum_reset()
+        for k in range(gpu_per_block // skip):
+            G.steps(skip, sync=False)
+            G.measure()
+        G.sync()
+        acc, lay = G.accum_download()
+        n = acc[0]
+        a = acc[lay["area"]:lay["area"] + 36]
+        rcf = acc[lay["rcf"]:lay["rcf"] + max(1, s.Q)]
+        rows.append(stats_ref.observables(s, n, acc[1], acc[2], acc[3], rcf, a[0:6], a[6:21], a[21:36], d["lambda_bose"], d["mass_bose"]))
+    G.close()
+    g = np.array(rows)
+    cols = [(i, c) for i, c in enumerate(d["columns"]) if np.any(r[:, i] != 0.0)]
+    assert len(cols) >= 6
+    compare(g, r, cols)
+    return g, r
+
+
+def test_top_in_helium_without_worm_matches_reference(pkg):
+    """C1-like: He4 + HCOOCH3 asymmetric top (P=64, Q=16, 1 K), MCRotations3D without the worm, REFLECTY as in the deck:
+    energies, <n(0).n(t)> at t = 1, Q/4, Q/2 and the superfluid fraction 4m^2<A_i^2>/(beta hbar^2 I_ii) of the helium path
+    in the space-fixed and the dopant-fixed frame (.sffs3d / .mffs3d columns)."""
+    _stats_case(pkg, "top_He_C1_P64_Q16_1K", nchains=32, gpu_per_block=3200)
+
+
+def test_tip4p_dimer_matches_reference(pkg):
+    """C4-like: two TIP4P waters (caleng_ path), P=64, Q=32: energies and <n(0).n(t)>."""
+    _stats_case(pkg, "tip4p_C4_P64_Q32", nchains=32, gpu_per_block=1600)
+
+
+def test_linear_dopant_cluster_with_superfluid_fraction_matches_reference(pkg):
+    """reduced C5 (N2O + 6 pH2 bosons, P=64, Q=16, 2 K): energies, <n(0).n(t)> and the .sup superfluid fractions
+    _area2*norm/_inert perpendicular / parallel to the rotor axis (mc_estim.cc:2626-2627)."""
+    _stats_case(pkg, "lin_C5_P64_Q16_6H2_2K", nchains=32, gpu_per_block=3200)
+
+
 WORM_REF_SCRIPT = r'''
 import sys, json, numpy as np
 sys.path.insert(0, %(root)r)
