@@ -303,7 +303,7 @@ def main():
     pin_acc = torch.empty(lay["n_total"], dtype=torch.float64, pin_memory=True)
     host_acc = pin_acc.numpy()
     h2d = chains * ((P * 3 * ((s.N + 3) // 4 * 4) + 2 * max(1, s.Q) * 3 * max(1, sum(t.numb for t in s.types if t.molecule))) * 8 + (3 * s.N + 3) * 4)
-    d2h = h2d - chains * (3 * s.N + 3) * 4 + lay["n_total"] * 8
+    d2h = h2d - chains * (3 * s.N + 3) * 4 + lay["n_total"] * 8        # beads, rotor angle / axis rows, accumulators
     barrier()
     w0 = time.perf_counter()
     for _ in range(args.steps):
@@ -318,7 +318,7 @@ def main():
             torch.cuda.current_stream().synchronize()
         G.sync()
         G.accum_download_into(host_acc)
-        G.download_all_into(host_c, host_a)
+        G.download_rows_into(host_c, host_a)                    # beads + the rotor rows of MCAngles (the arrays live across steps)
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - w0
     if dist:

@@ -118,6 +118,10 @@ int pimcgpu_download_state(int chain, double *coords, double *angles, double *co
  * NULL (identity); one host<->device copy and one transposing kernel for the whole batch instead of per-chain round trips   */
 int pimcgpu_upload_states(int first, int count, const double *coords, const double *angles, const int *pindex);
 int pimcgpu_download_states(int first, int count, double *coords, double *angles, double *cosine);
+/* as above, but `angles` / `cosine` only receive the rows the moves change -- [rotor atom * P + q], q < NumbRotTimes; the
+ * other entries of the caller's MCAngles / MCCosine (allocated once, mc_setup.cc:135-163; never written after MCConfigInit,
+ * :471-487) are left untouched: 6 Q doubles per rotor and chain cross the bus instead of 6 N P                                  */
+int pimcgpu_download_states_rows(int first, int count, double *coords, double *angles, double *cosine);
 
 /* ---- MRG32k3a package seed: RngStream::SetPackageSeed (rngstream.cc:346-353) ---- */
 int pimcgpu_seed(const unsigned long seed6[6]);

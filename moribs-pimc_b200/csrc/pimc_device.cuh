@@ -50,12 +50,15 @@ struct Params {
    int n1d, nlut1d;  const double *g1d, *v1d, *y2_1d; const int *lut1d; double alpha, unode, c6, lut1d_scale;
    int uniform1d; double x0_1d, xn_1d, invh_1d;      // 1-D grid end points; uniform grid: interval index = (r - x0)/h directly
    const SplineRec *rec1d;       // packed per-interval records of the 1-D potential spline
+   int poly1d;                   // the 1-D grid is uniform to rounding: per-interval cubic in t = (r - x_k)/h, {c0, c1} and {c2, c3}
+   const double2 *pa1d, *pb1d;   // in two arrays of 16-byte entries (two conflict-poor 128-bit shared-memory loads per evaluation)
    int rs2d, cs2d;   const double *rg2d, *cg2d, *v2d; double dr2d, dc2d;
    const double *irg2d, *icg2d;  // 1/(grid[i+1]-grid[i]) of the 2-D potential axes
    double inv_dr2d, inv_dc2d;
    const double2 *cell2d;        // [(rs-1)][cs] row pairs {V[ir][ic], V[ir+1][ic]}: a bilinear cell is two adjacent 16-byte
                                  // entries (32 contiguous bytes, 2x the table instead of 4x so the hot region stays in L2)
    const double2 *rgi2d, *cgi2d; // {grid[i], 1/(grid[i+1]-grid[i])} of the two axes
+   const double *cell4;          // [(rs-1)][(cs-1)][4] whole cells {V[ir][ic], V[ir+1][ic], V[ir][ic+1], V[ir+1][ic+1]}, 32-byte aligned
    int rg3, thg3, chg3; const double *v3d; double rvmin, rvmax, rvstep;
    int nrot, nlutrot; const double *rgrid, *rdens, *rderv, *resqr, *rdens2, *rderv2, *resqr2; const int *lutrot; double lutrot_scale;
    const SplineRec *recrot;      // packed records of the linear-rotor density spline (rho column)
@@ -84,6 +87,12 @@ struct Params {
    int swbar;                    // chain barrier in global memory (cooperative grid) instead of the cluster barrier
    unsigned *barrier;            // [c][32] arrival counters of the software chain barrier (zeroed before every launch)
    int rot_fused;                // one-rotor system, even Q: potential sums of all Q proposals in one stage, decisions pipelined (rot_sweep_pipe)
+   // geometry cache of the rotor-atom terms of a linear rotor (rot_potential_cached): the positions only change in the
+   // translational sweeps, so between two of them every (slice, partner) term keeps its unit vector (p_j - p_g)/r, its
+   // radial cell row and its radial weight; a rotational proposal only changes cos(theta) = n.u
+   int geo_on, geo_items, geo_n; // enabled; real items per rot slice = R x (N - 1); padded stride
+   double *geo;                  // [c][q][4][geo_n]: ux, uy, uz, radial weight dr
+   int *geo_i;                   // [c][q][geo_n]: ir * cs2d (row offset of the radial cell in cell2d)
 };
 
 __host__ __device__ inline size_t pos_index(const Params &p, int c, int it, int d, int a)
@@ -183,6 +192,7 @@ struct SmallTables {
    const double *rgrid, *rdens, *rdens2; const int *lutrot;
    const SplineRec *rec1d, *recrot;
    const double2 *rgi2d, *cgi2d;   // axis tables of the 2-D potential (shared memory in the move kernel)
+   const double2 *pa1d, *pb1d;     // per-interval cubic of the 1-D potential (shared memory in the move kernel)
 };
 
 // interval search + cubic evaluation on the packed records: same interval as the reference's bisection search
@@ -254,6 +264,22 @@ __device__ __forceinline__ double spot1d_try(const Params &p, const SmallTables 
    return a * rc.ylo + bb * rc.yhi + ((a * a * a - a) * rc.clo + (bb * bb * bb - bb) * rc.chi);
 }
 
+// The same spline piece as a cubic in t = (r - x_k)/h on a grid that is uniform to rounding (parah2.pot, isoH2H208.pot):
+// c0 + t(c1 + t(c2 + t c3)) with c0 = y_k, c1 = y_k+1 - y_k - 2C_k - C_k+1, c2 = 3C_k, c3 = C_k+1 - C_k, C = y'' h^2/6
+// (splint's a y_k + b y_k+1 + (a^3 - a)C_k + (b^3 - b)C_k+1 with a = 1 - t, b = t, mc_utils.cc:178-185).  The interval
+// comes from the quotient; a point within rounding of a knot may land in the neighbouring piece, where the C^2 spline
+// has the same value to rounding.  `bad` is set beyond either end of the grid (the caller redoes those with spot1d_move).
+__device__ __forceinline__ double spot1d_poly(const Params &p, const SmallTables &t, double r, bool &bad)
+{
+   const double xq = (r - p.x0_1d) * p.invh_1d;
+   int k = (int)xq;
+   k = max(0, min(k, p.n1d - 2));
+   bad |= !(r > p.x0_1d && r < p.xn_1d);
+   const double tt = xq - (double)k;
+   const double2 A = t.pa1d[k], B = t.pb1d[k];
+   return fma(fma(fma(B.y, tt, B.x), tt, A.y), tt, A.x);
+}
+
 // floor(x/delta) by true division: the rare exact path of lpot2d's index selection, kept out of line so ptxas does
 // not if-convert the FP64 division into the common path
 __device__ __noinline__ double exact_floor_div(double x, double delta) { return floor(x / delta); }
@@ -264,6 +290,11 @@ __device__ __forceinline__ void load_cell(const double2 *cell, double &y1, doubl
 {
    const double2 a = __ldg(cell), b = __ldg(cell + 1);
    y1 = a.x; y2 = a.y; y4 = b.x; y3 = b.y;
+}
+// one bilinear cell from the whole-cell table: a single 256-bit gather (LDG.E.256 on sm_100a)
+__device__ __forceinline__ void load_cell4(const double *cell, double &y1, double &y2, double &y3, double &y4)
+{
+   asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(y1), "=d"(y2), "=d"(y4), "=d"(y3) : "l"(cell));
 }
 // index selection of LPot2D, mc_poten.cc:696-704: floor((x - xmin)/delta) exactly as the reference -- the product with
 // the stored reciprocal decides unless it lands within 1e-7 of an integer, where the true quotient is taken

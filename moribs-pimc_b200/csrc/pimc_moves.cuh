@@ -55,6 +55,7 @@ struct RotSlot {
    double vcache;             // pipelined sweep: cached potential sum of the current orientation ...
    int vep, epoch;            // ... the position epoch it belongs to, and the epoch seen by the current sweep
    int need_old, bad;
+   int gep;                   // position epoch the geometry cache of this slice was filled at (-1: never)
 };
 
 struct Ctx {
@@ -196,7 +197,10 @@ __device__ __forceinline__ double partner_sum_diff(const Params &p, const SmallT
          }
          double e[4];
          bool bad = !p.uniform1d;
-         if (p.uniform1d) {
+         if (p.poly1d) {
+            #pragma unroll
+            for (int u = 0; u < 4; u++) e[u] = spot1d_poly(p, t, rn[u], bad) - spot1d_poly(p, t, ro[u], bad);
+         } else if (p.uniform1d) {
             #pragma unroll
             for (int u = 0; u < 4; u++) e[u] = spot1d_try(p, t, rn[u], bad) - spot1d_try(p, t, ro[u], bad);
          }
@@ -496,28 +500,33 @@ __device__ __forceinline__ double rot_potential(const Params &p, Ctx &x, int g, 
       Mat3 ro;
       #pragma unroll
       for (int i = 0; i < 9; i++) ro.m[i / 3][i % 3] = o[i];
-      for (int j = x.gl; j < N; j += x.G) {
+      // rotor partners: the partner's orientation is the same for all R slices, one partner per lane
+      const int m0 = p.first[p.imtype];
+      for (int j = m0 + x.gl; j < m0 + p.numb[p.imtype]; j += x.G) {
          if (j == g) continue;
-         if (type_of(p, j) == p.imtype) {           // rotor partner: its orientation is the same for all R slices
-            Mat3 rb;
-            load_rotmat(p, c, q, j - p.first[p.imtype], rb);
-            for (int r = 0; r < R; r++) {
-               double pg[3], pj[3];
-               #pragma unroll
-               for (int d = 0; d < 3; d++) { pg[d] = p.pos[pos_index(p, c, it0 + r, d, g)]; pj[d] = p.pos[pos_index(p, c, it0 + r, d, j)]; }
-               Tip4pSites sa, sb;
-               tip4p_sites(ro, pg, sa);
-               tip4p_sites(rb, pj, sb);
-               v += caleng(sa, sb);
-            }
-         } else {
-            for (int r = 0; r < R; r++) {
-               if (!partner_on_line<KIND>(p, c, j, it0 + r)) continue;
-               double pg[3], pj[3];
-               #pragma unroll
-               for (int d = 0; d < 3; d++) { pg[d] = p.pos[pos_index(p, c, it0 + r, d, g)]; pj[d] = p.pos[pos_index(p, c, it0 + r, d, j)]; }
-               v += p.ispher ? vspher(p, sqrt(dist2(pg, pj))) : vcord(p, ro, pg, pj, nullptr, nullptr);
-            }
+         Mat3 rb;
+         load_rotmat(p, c, q, j - m0, rb);
+         for (int r = 0; r < R; r++) {
+            double pg[3], pj[3];
+            #pragma unroll
+            for (int d = 0; d < 3; d++) { pg[d] = p.pos[pos_index(p, c, it0 + r, d, g)]; pj[d] = p.pos[pos_index(p, c, it0 + r, d, j)]; }
+            Tip4pSites sa, sb;
+            tip4p_sites(ro, pg, sa);
+            tip4p_sites(rb, pj, sb);
+            v += caleng(sa, sb);
+         }
+      }
+      // atom partners: the (atom, slice) terms dealt flat to the lanes of the group, so a lone atom's R terms (C1) are
+      // evaluated side by side instead of one after the other
+      if (p.ntypes > 1) {
+         const int at = 1 - p.imtype, a0 = p.first[at], nitems = p.numb[at] * R;
+         for (int i = x.gl; i < nitems; i += x.G) {
+            const int jj = i / R, r = i - jj * R, j = a0 + jj;
+            if (!partner_on_line<KIND>(p, c, j, it0 + r)) continue;
+            double pg[3], pj[3];
+            #pragma unroll
+            for (int d = 0; d < 3; d++) { pg[d] = p.pos[pos_index(p, c, it0 + r, d, g)]; pj[d] = p.pos[pos_index(p, c, it0 + r, d, j)]; }
+            v += p.ispher ? vspher(p, sqrt(dist2(pg, pj))) : vcord(p, ro, pg, pj, nullptr, nullptr);
          }
       }
    } else {
@@ -555,6 +564,91 @@ __device__ __forceinline__ double rot_potential(const Params &p, Ctx &x, int g, 
       }
    }
    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// geometry cache of a linear rotor's partner terms (one rotor, partners are atoms, no worm, no minimum image).
+// Item k = r * (N - 1) + jj of rot slice q is the pair (translational slice q R + r, jj-th atom other than the rotor).
+// Thread gl of the slice's rot group owns the items k = gl, gl + G, ... in BOTH the fill and the evaluation, so a
+// thread only ever reads what it wrote itself: no barrier between the two.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void geo_fill(const Params &p, Ctx &x, int g, int q)
+{
+   const int c = x.c, NA = p.N - 1, it0 = q * p.R;
+   double *gb = p.geo + ((size_t)c * p.Q + q) * 4 * p.geo_n;
+   int *gi = p.geo_i + ((size_t)c * p.Q + q) * p.geo_n;
+   const double rmin = x.t.rgi2d[0].x;
+   for (int k = x.gl; k < p.geo_items; k += x.G) {
+      const int r = k / NA, jj = k - r * NA, j = jj < g ? jj : jj + 1, it = it0 + r;
+      const double dx = p.pos[pos_index(p, c, it, 0, j)] - p.pos[pos_index(p, c, it, 0, g)];
+      const double dy = p.pos[pos_index(p, c, it, 1, j)] - p.pos[pos_index(p, c, it, 1, g)];
+      const double dz = p.pos[pos_index(p, c, it, 2, j)] - p.pos[pos_index(p, c, it, 2, g)];
+      double rr, invr;
+      fast_r_invr(dx * dx + dy * dy + dz * dz, rr, invr);
+      const int ir = lpot_index(rr - rmin, p.inv_dr2d, p.dr2d, p.rs2d);          // LPot2D radial cell, mc_poten.cc:696-701
+      const double2 gr = x.t.rgi2d[ir];
+      gb[k] = dx * invr; gb[p.geo_n + k] = dy * invr; gb[2 * p.geo_n + k] = dz * invr;
+      gb[3 * p.geo_n + k] = (rr - gr.x) * gr.y;
+      gi[k] = ir * (p.cs2d - 1);          // row offset in the whole-cell table
+   }
+}
+
+// four cached items against one orientation n: cos(theta) = n.u, angular cell, the four cell gathers, the bilinear forms
+__device__ __forceinline__ double geo_eval4(const Params &p, const SmallTables &t, double cmin, double n0, double n1, double n2,
+                                            const double *ux, const double *uy, const double *uz, const double *dr, const int *ib, const bool *ok)
+{
+   double cs[4];
+   int ic[4];
+   #pragma unroll
+   for (int u = 0; u < 4; u++) {
+      cs[u] = n0 * ux[u] + n1 * uy[u] + n2 * uz[u];
+      ic[u] = lpot_index(cs[u] - cmin, p.inv_dc2d, p.dc2d, p.cs2d);            // LPot2D angular cell, mc_poten.cc:702-704
+   }
+   double y1[4], y2[4], y3[4], y4[4];
+   #pragma unroll
+   for (int u = 0; u < 4; u++) load_cell4(p.cell4 + 4 * (size_t)(ib[u] + ic[u]), y1[u], y2[u], y3[u], y4[u]);
+   double v = 0.0;
+   #pragma unroll
+   for (int u = 0; u < 4; u++) {
+      const double2 gc = t.cgi2d[ic[u]];
+      const double dc = (cs[u] - gc.x) * gc.y;
+      const double lo = y1[u] + dr[u] * (y2[u] - y1[u]);         // V at cos(theta)_ic, interpolated in r
+      const double hi = y4[u] + dr[u] * (y3[u] - y4[u]);         // V at cos(theta)_ic+1
+      const double e = lo + dc * (hi - lo);
+      v += ok[u] ? e : 0.0;
+   }
+   return v;
+}
+
+// sum over the cached items of rot slice q of LPot2D(r, cos(theta) = n.u) for ONE orientation (NO = 1) or for the
+// proposed and the current orientation (NO = 2: the geometry loads are shared).  Four items per lane in flight.
+template <int NO>
+__device__ __forceinline__ void rot_potential_cached(const Params &p, Ctx &x, int q, const double *o0, const double *o1, double *vout)
+{
+   const int c = x.c, G = x.G, n = p.geo_items, gn = p.geo_n;
+   const double *gx = p.geo + ((size_t)c * p.Q + q) * 4 * gn, *gy = gx + gn, *gz = gy + gn, *gd = gz + gn;
+   const int *gi = p.geo_i + ((size_t)c * p.Q + q) * gn;
+   const double cmin = x.t.cgi2d[0].x;
+   const double a0 = o0[0], a1 = o0[1], a2 = o0[2];
+   double b0 = 0.0, b1 = 0.0, b2 = 0.0;
+   if (NO == 2) { b0 = o1[0]; b1 = o1[1]; b2 = o1[2]; }
+   double v0 = 0.0, v1 = 0.0;
+   for (int k0 = x.gl; k0 < n; k0 += 4 * G) {
+      double ux[4], uy[4], uz[4], dr[4];
+      int ib[4];
+      bool ok[4];
+      #pragma unroll
+      for (int u = 0; u < 4; u++) {
+         const int k = k0 + u * G;
+         ok[u] = k < n;
+         const int kk = ok[u] ? k : k0;                 // masked slots repeat the first item of the batch (a valid look-up)
+         ux[u] = gx[kk]; uy[u] = gy[kk]; uz[u] = gz[kk]; dr[u] = gd[kk]; ib[u] = gi[kk];
+      }
+      v0 += geo_eval4(p, x.t, cmin, a0, a1, a2, ux, uy, uz, dr, ib, ok);
+      if (NO == 2) v1 += geo_eval4(p, x.t, cmin, b0, b1, b2, ux, uy, uz, dr, ib, ok);
+   }
+   vout[0] = v0;
+   if (NO == 2) vout[1] = v1;
 }
 
 // proposal of a rotational step (mc_piqmc.cc:950-995 top, :796-814 linear): angles in (cost, phi, chi), the
@@ -884,8 +978,17 @@ __device__ void rot_sweep_pipe(const Params &p, Ctx &x, int type, int *err)
       MARK(x, 3);
       double vnew = 0.0, vold = 0.0;
       if (active) {
-         vnew = rot_potential<KIND>(p, x, g, q, sl->a);
-         if (sl->need_old) vold = rot_potential<KIND>(p, x, g, q, sl->b);
+         if ((KIND & 7) == 1 && p.geo_on) {
+            // linear rotor among atoms: distance part of every term from the cache, refilled after a translational sweep
+            const bool refill = sl->gep != sl->epoch;
+            if (refill) geo_fill(p, x, g, q);
+            double vv[2];
+            if (sl->need_old) { rot_potential_cached<2>(p, x, q, sl->a, sl->b, vv); vnew = vv[0]; vold = vv[1]; }
+            else { rot_potential_cached<1>(p, x, q, sl->a, nullptr, vv); vnew = vv[0]; }
+         } else {
+            vnew = rot_potential<KIND>(p, x, g, q, sl->a);
+            if (sl->need_old) vold = rot_potential<KIND>(p, x, g, q, sl->b);
+         }
       }
       MARK(x, 4);
       const int gw = (G < 32) ? G : 32;
@@ -900,6 +1003,7 @@ __device__ void rot_sweep_pipe(const Params &p, Ctx &x, int type, int *err)
          }
          if (!sl->need_old) vold = sl->vcache;
          sl->vnew = vnew; sl->vold = vold;
+         sl->gep = sl->epoch;
       }
       group_sync(x);
    }
@@ -933,6 +1037,7 @@ __device__ __forceinline__ void stage_tables(const Params &p, SmallTables &t, do
    t.g1d = p.g1d; t.v1d = p.v1d; t.y2_1d = p.y2_1d; t.lut1d = p.lut1d; t.rec1d = p.rec1d;
    t.rgrid = p.rgrid; t.rdens = p.rdens; t.rdens2 = p.rdens2; t.lutrot = p.lutrot; t.recrot = p.recrot;
    t.rgi2d = p.rgi2d; t.cgi2d = p.cgi2d;
+   t.pa1d = p.pa1d; t.pb1d = p.pb1d;
    if (p.rs2d) {
       double2 *d2 = reinterpret_cast<double2 *>(cursor);
       for (int i = threadIdx.x; i < p.rs2d; i += blockDim.x) d2[i] = p.rgi2d[i];
@@ -951,7 +1056,15 @@ __device__ __forceinline__ void stage_tables(const Params &p, SmallTables &t, do
       t.lutrot = li;
       cursor += ((p.nlutrot + 1) / 2 + 1) & ~1;
    }
-   if (p.n1d) {
+   if (p.n1d && p.poly1d) {
+      // uniform grid: only the per-interval cubics go to shared memory; the packed records (ends of the grid, the
+      // one-off evaluations outside the batched sums) are read from global memory
+      double2 *d2 = reinterpret_cast<double2 *>(cursor);
+      const int nk = p.n1d - 1;
+      for (int i = threadIdx.x; i < nk; i += blockDim.x) { d2[i] = p.pa1d[i]; d2[nk + i] = p.pb1d[i]; }
+      t.pa1d = d2; t.pb1d = d2 + nk;
+      cursor += 4 * (size_t)nk;
+   } else if (p.n1d) {
       const int nd = (p.n1d - 1) * (int)(sizeof(SplineRec) / sizeof(double));
       const double *src = reinterpret_cast<const double *>(p.rec1d);
       for (int i = threadIdx.x; i < nd; i += blockDim.x) cursor[i] = src[i];
@@ -1030,6 +1143,7 @@ pimc_steps_kernel(const __grid_constant__ Params p, long t0, long nsteps, int *e
          }
          sl->vcache = p.vold[((size_t)x.c * p.Q + q) * p.NMpad];
          sl->vep = p.vepoch[((size_t)x.c * p.Q + q) * p.NMpad];
+         sl->gep = -1;
       }
       __syncthreads();
    } else x.slot = reinterpret_cast<RotSlot *>(cursor) + x.grp;      // one slot per rot group

@@ -177,7 +177,8 @@ size_t smem_bytes(const Params &p, int threads)
    size_t d = 40;
    auto pad = [](int n) { return (size_t)((n + 1) & ~1); };
    auto padi = [](int n) { return (size_t)(((n + 1) / 2 + 1) & ~1); };
-   if (p.n1d) d += pad((p.n1d - 1) * (int)(sizeof(SplineRec) / sizeof(double))) + (p.uniform1d ? 0 : padi(p.nlut1d));
+   if (p.n1d && p.poly1d) d += 4 * (size_t)(p.n1d - 1);
+   else if (p.n1d) d += pad((p.n1d - 1) * (int)(sizeof(SplineRec) / sizeof(double))) + (p.uniform1d ? 0 : padi(p.nlut1d));
    if (p.rs2d) d += 2 * (size_t)(p.rs2d + p.cs2d);
    if (p.nrot && p.rot_in_smem) d += pad((p.nrot - 1) * (int)(sizeof(SplineRec) / sizeof(double))) + padi(p.nlutrot);
    if (!p.segbuf_global) d += (size_t)(threads / p.team) * p.team_buf_n;
@@ -375,6 +376,20 @@ int pimcgpu_init(const pimcgpu_system *sys, const pimcgpu_tables *tab)
       build_lut(g, lut, p.lut1d_scale, p.uniform1d ? 4 : 16);
       p.n1d = n; p.nlut1d = (int)lut.size();
       std::vector<SplineRec> rec = make_records(g, v, y2);
+      // grid uniform to rounding: per-interval cubic in t = (r - x_k)/h for the batched pair sums of the move kernel
+      // (systems with a non-linear top evaluate their few atom-atom terms one by one from the packed records)
+      const bool top_system = p.imtype >= 0 && p.molecule[p.imtype] == 2;
+      p.poly1d = (dev <= 1e-12 * havg * n && !top_system && !getenv("PIMC_NO_POLY1D")) ? 1 : 0;
+      if (p.poly1d) {
+         std::vector<double2> pa(n - 1), pb(n - 1);
+         for (int k = 0; k < n - 1; k++) {
+            const long double h = (long double)g[k + 1] - (long double)g[k];
+            const long double c0 = (long double)y2[k] * h * h / 6.0L, c1 = (long double)y2[k + 1] * h * h / 6.0L;
+            pa[k] = make_double2(v[k], (double)((long double)v[k + 1] - (long double)v[k] - 2.0L * c0 - c1));
+            pb[k] = make_double2((double)(3.0L * c0), (double)(c1 - c0));
+         }
+         if (dupload(&p.pa1d, pa.data(), pa.size()) || dupload(&p.pb1d, pb.data(), pb.size())) return 1;
+      }
       if (dupload(&p.g1d, g.data(), n) || dupload(&p.v1d, v.data(), n) || dupload(&p.y2_1d, y2.data(), n) || dupload(&p.lut1d, lut.data(), lut.size()) ||
           dupload(&p.rec1d, rec.data(), rec.size())) return 1;
    }
@@ -396,6 +411,18 @@ int pimcgpu_init(const pimcgpu_system *sys, const pimcgpu_tables *tab)
          std::vector<double2> rgi(rs), cgi(cs);
          for (int i = 0; i < rs; i++) rgi[i] = make_double2(tab->rgrid2d[i], ir[i]);
          for (int i = 0; i < cs; i++) cgi[i] = make_double2(tab->cgrid2d[i], ic[i]);
+         // whole-cell copy for the cached rotational sums: the four corners of cell (ir, ic) as ONE aligned 32-byte record
+         // {V[ir][ic], V[ir+1][ic], V[ir][ic+1], V[ir+1][ic+1]} -- a single 256-bit gather per evaluation
+         {
+            std::vector<double> c4((size_t)(rs - 1) * (cs - 1) * 4);
+            for (int i = 0; i < rs - 1; i++)
+               for (int j = 0; j < cs - 1; j++) {
+                  double *q = &c4[((size_t)i * (cs - 1) + j) * 4];
+                  q[0] = tab->pot2d[(size_t)i * cs + j]; q[1] = tab->pot2d[(size_t)(i + 1) * cs + j];
+                  q[2] = tab->pot2d[(size_t)i * cs + j + 1]; q[3] = tab->pot2d[(size_t)(i + 1) * cs + j + 1];
+               }
+            if (dupload(&p.cell4, c4.data(), c4.size())) return 1;
+         }
          if (dupload(&p.cell2d, cell.data(), cell.size()) || dupload(&p.rgi2d, rgi.data(), rgi.size()) || dupload(&p.cgi2d, cgi.data(), cgi.size())) return 1;
       }
    }
@@ -494,10 +521,15 @@ int pimcgpu_init(const pimcgpu_system *sys, const pimcgpu_tables *tab)
       break;
    }
    if (threads % 32 || threads > PIMC_MAX_THREADS || threads < 32) return fail("pimcgpu_init: threads_per_cta must be a multiple of 32 in [32,%d]", PIMC_MAX_THREADS);
-   if (cpc > 16 || (cpc & (cpc - 1))) return fail("pimcgpu_init: ctas_per_chain must be a power of two <= 16");
+   if (cpc > 32 || (cpc & (cpc - 1))) return fail("pimcgpu_init: ctas_per_chain must be a power of two <= 32");
    if (sys->team <= 0) {
       // more threads than one team per segment can use: widen the teams (several warps per segment)
       while (team < 128 && (long)cpc * threads / team >= 2L * nseg_widest && std::max(1, p.N - 1) >= 2 * team && 2 * team <= threads) team *= 2;
+   }
+   if (sys->team <= 0) {
+      // the gaussians and the bead updates of a segment use every lane of its team (not only the partner sums): widen up
+      // to half a warp while the chain has more threads than segments (C1: 2 -> 16 lanes, +16 % measured)
+      while (team < 16 && (long)cpc * threads / (2 * team) >= nseg_widest) team *= 2;
    }
    if (team > threads) team = pow2floor(threads);
    if (team > 32 && threads / team > 15) return fail("pimcgpu_init: a team wider than a warp needs at most 15 teams per CTA");
@@ -524,6 +556,14 @@ int pimcgpu_init(const pimcgpu_system *sys, const pimcgpu_tables *tab)
    if (smem_bytes(p, threads) > 200 * 1024) p.rot_in_smem = 0;
    if (p.segbuf_global && dalloc(&p.segbuf, C * p.nseg_max * p.team_buf_n)) return 1;
    if (dalloc(&p.barrier, C * 32)) return 1;
+   // geometry cache of the rotor-atom terms (rot_potential_cached): one linear rotor among atoms, pipelined sweep, no worm
+   p.geo_on = 0;
+   if (p.rot_fused && p.imtype >= 0 && p.molecule[p.imtype] == 1 && !p.worm_on && !p.minimage && p.N > 1 && p.rs2d > 0 && !getenv("PIMC_NO_GEO")) {
+      p.geo_items = p.R * (p.N - 1);
+      p.geo_n = (p.geo_items + 31) / 32 * 32;
+      if (dalloc(&p.geo, C * p.Q * 4 * p.geo_n) || dalloc(&p.geo_i, C * p.Q * p.geo_n)) return 1;
+      p.geo_on = 1;
+   }
    G.smem = smem_bytes(p, threads);
    if (G.smem > 227 * 1024) return fail("pimcgpu_init: %zu bytes of shared memory per CTA exceed the 227 KB limit", G.smem);
    G.kind = p.imtype >= 0 && p.Q > 0 ? p.molecule[p.imtype] : (p.imtype >= 0 ? p.molecule[p.imtype] : 0);
@@ -739,7 +779,8 @@ int pimcgpu_upload_states(int first, int count, const double *coords, const doub
    state_transpose_kernel<<<dim3((p.P + 31) / 32, (p.N + 31) / 32, 3 * count), dim3(32, 8), 0, G.stream>>>(p.pos + (size_t)first * npos, G.d_raw_all, p.N, p.P, p.Npad, 1);
    CK(cudaGetLastError());
    if (p.imtype >= 0) {
-      #pragma omp parallel for schedule(static)
+      // a few thousand sincos at most: an OpenMP team only pays off for many chains (and eight ranks share the host)
+      #pragma omp parallel for schedule(static) if ((long)count * p.Q * p.NM > 65536) num_threads(4)
       for (int cc = 0; cc < count; cc++) {
          double *hang = G.stage + (size_t)(first + cc) * G.stage_chain + npos, *hcos = hang + nang;
          const double *ang = angles + (size_t)cc * 3 * n;
@@ -795,7 +836,7 @@ int pimcgpu_download_states(int first, int count, double *coords, double *angles
    CK(cudaStreamSynchronize(G.stream));
    if (angles || cosine) {
       // rotor rows: only the first Q entries carry angles; the rest keep phi = 0, cos(theta) = 1, chi = 0 (MCConfigInit, mc_setup.cc:471-487)
-      #pragma omp parallel for schedule(static)
+      #pragma omp parallel for schedule(static) num_threads(std::min(count, 8))
       for (int cc = 0; cc < count; cc++) {
          const double *hang = G.stage + (size_t)(first + cc) * G.stage_chain + npos, *hcos = hang + nang;
          double *ang = angles ? angles + (size_t)cc * 3 * n : nullptr, *cs = cosine ? cosine + (size_t)cc * 3 * n : nullptr;
@@ -815,6 +856,46 @@ int pimcgpu_download_states(int first, int count, double *coords, double *angles
                }
       }
    }
+   return 0;
+}
+
+// Like pimcgpu_download_states, but only the rows the moves ever change are written to `angles` / `cosine`: entries
+// [rotor atom * P + q], q < Q.  Everything else in the caller's arrays is left as it is -- the reference allocates
+// MCAngles / MCCosine once (mc_setup.cc:135-163) and never touches the other rows after MCConfigInit (:471-487), so a
+// driver that keeps its arrays across blocks gets the reference's contents with 6 Q NM doubles per chain instead of 6 N P.
+int pimcgpu_download_states_rows(int first, int count, double *coords, double *angles, double *cosine)
+{
+   if (!G.live) return fail("pimcgpu_download_states_rows: not initialised");
+   const Params &p = G.p;
+   if (first < 0 || count < 1 || first + count > p.nchains) return fail("pimcgpu_download_states_rows: chains %d..%d out of range", first, first + count - 1);
+   const size_t n = (size_t)p.N * p.P;
+   const size_t npos = (size_t)p.P * 3 * p.Npad, nang = (size_t)std::max(1, p.Q) * 3 * p.NMpad;
+   if (!G.d_raw_all && dalloc(&G.d_raw_all, (size_t)p.nchains * 3 * n)) return 1;
+   if (coords) {
+      state_transpose_kernel<<<dim3((p.P + 31) / 32, (p.N + 31) / 32, 3 * count), dim3(32, 8), 0, G.stream>>>(p.pos + (size_t)first * npos, G.d_raw_all, p.N, p.P, p.Npad, 0);
+      CK(cudaGetLastError());
+      CK(cudaMemcpyAsync(coords, G.d_raw_all, (size_t)count * 3 * n * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
+   }
+   double *s0 = G.stage + (size_t)first * G.stage_chain + npos;
+   const bool rows = (angles || cosine) && p.imtype >= 0 && p.Q > 0;
+   if (rows) {
+      CK(cudaMemcpy2DAsync(s0, G.stage_chain * sizeof(double), p.ang + (size_t)first * nang, nang * sizeof(double), nang * sizeof(double), count, cudaMemcpyDeviceToHost, G.stream));
+      CK(cudaMemcpy2DAsync(s0 + nang, G.stage_chain * sizeof(double), p.cosn + (size_t)first * nang, nang * sizeof(double), nang * sizeof(double), count, cudaMemcpyDeviceToHost, G.stream));
+   }
+   CK(cudaStreamSynchronize(G.stream));
+   if (rows)
+      for (int cc = 0; cc < count; cc++) {
+         const double *hang = G.stage + (size_t)(first + cc) * G.stage_chain + npos, *hcos = hang + nang;
+         double *ang = angles ? angles + (size_t)cc * 3 * n : nullptr, *cs = cosine ? cosine + (size_t)cc * 3 * n : nullptr;
+         for (int q = 0; q < p.Q; q++)
+            for (int m = 0; m < p.NM; m++) {
+               const size_t dst = (size_t)(p.first[p.imtype] + m) * p.P + q, b = (size_t)q * 3 * p.NMpad + m;
+               for (int d = 0; d < 3; d++) {
+                  if (ang) ang[d * n + dst] = hang[b + d * p.NMpad];
+                  if (cs) cs[d * n + dst] = hcos[b + d * p.NMpad];
+               }
+            }
+      }
    return 0;
 }
 
@@ -1109,16 +1190,15 @@ int pimcgpu_accum_layout(long *n_total, long *off_scalars, long *off_gr1d, long 
 void *pimcgpu_accum_device_ptr(void)
 {
    if (!G.live) return nullptr;
-   fold_counters_kernel<<<1, 32, 0, G.stream>>>(G.p, G.e.acc);
-   cudaStreamSynchronize(G.stream);
+   fold_counters_kernel<<<1, 32, 0, G.stream>>>(G.p, G.e.acc);      // ordered on the library's stream: no host round trip here
    return G.e.acc;
 }
 int pimcgpu_accum_download(double *host, long n)
 {
    if (!G.live) return fail("pimcgpu_accum_download: not initialised");
    if (n > G.nacc) n = G.nacc;
+   CK(cudaMemcpyAsync(host, G.e.acc, n * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
    CK(cudaStreamSynchronize(G.stream));
-   CK(cudaMemcpy(host, G.e.acc, n * sizeof(double), cudaMemcpyDeviceToHost));
    return 0;
 }
 int pimcgpu_accum_reset(void)

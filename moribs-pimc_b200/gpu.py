@@ -27,7 +27,7 @@ EXPORTS = [
     "pimcgpu_pot_energy_slice", "pimcgpu_rng_draws", "pimcgpu_fp64_peak", "pimcgpu_host_spline",
     "pimcgpu_host_stream_state", "pimcgpu_host_lut", "pimcgpu_accum_offset", "pimcgpu_symmetry_moves", "pimcgpu_symmetry_ops",
     "pimcgpu_checkpoint_bytes", "pimcgpu_checkpoint_save", "pimcgpu_checkpoint_load", "pimcgpu_chain_areas", "pimcgpu_worm_moves", "pimcgpu_worm_state", "pimcgpu_worm_set", "pimcgpu_worm_counters",
-    "pimcgpu_upload_states", "pimcgpu_download_states",
+    "pimcgpu_upload_states", "pimcgpu_download_states", "pimcgpu_download_states_rows",
     "pimcgpu_gen_asymrho", "pimcgpu_gen_symrho", "pimcgpu_gen_linden", "pimcgpu_gen_wigner_d", "pimcgpu_gen_timing",
     "pimcgpu_format_e15_8", "pimcgpu_write_e15_8", "pimcgpu_write_rot",
     "pimcgpu_eval_rotpro", "pimcgpu_eval_vcalc", "pimcgpu_eval_deleul", "pimcgpu_eval_vcord_grid", "pimcgpu_eval_vspher", "pimcgpu_eval_libm",
@@ -309,6 +309,10 @@ class PimcGpu:
     def download_all_into(self, coords, angles, cosine=None, first=0):
         """batched download into caller-owned contiguous arrays [count][3][N*P]"""
         _ck(self.L.pimcgpu_download_states(C.c_int(first), C.c_int(coords.shape[0]), _dp(coords), _dp(angles), _dp(cosine)))
+
+    def download_rows_into(self, coords, angles, cosine=None, first=0):
+        """batched download that writes only the rotor rows of angles / cosine (the caller's arrays live across steps)"""
+        _ck(self.L.pimcgpu_download_states_rows(C.c_int(first), C.c_int(coords.shape[0]), _dp(coords), _dp(angles), _dp(cosine)))
 
     def seed(self, seed6=(12345,) * 6):
         _ck(self.L.pimcgpu_seed((C.c_ulong * 6)(*seed6)))

@@ -19,11 +19,10 @@ sys.path.insert(0, ROOT)
 
 # name -> (config, make_config kwargs, blocks, steps per block, steps between measurements, equilibration passes)
 CASES = {
-    "top_He_C1_P64_Q16_1K": ("C1", dict(P=64, Q=16, temperature=1.0), 48, 12800, 16, 200),
-    "tip4p_C4_P64_Q32": ("C4", dict(P=64, Q=32), 48, 6400, 16, 200),
-    "lin_C5_P64_Q16_6H2_2K": ("C5", dict(P=64, Q=16, nsolv=6, temperature=2.0), 48, 12800, 16, 200),
+    "top_He_C1_P64_Q16_1K": ("C1", dict(P=64, Q=16, temperature=1.0), 64, 25600, 16, 3000),
+    "tip4p_C4_P64_Q32": ("C4", dict(P=64, Q=32), 64, 25600, 16, 3000),
+    "lin_C5_P64_Q16_6H2_2K": ("C5", dict(P=64, Q=16, nsolv=6, temperature=2.0), 64, 25600, 16, 3000),
 }
-HBAR2_2M = None
 
 
 def observables(s, n, k, v, e, rcf, lin6, sff15, mff15, lam_b, mass_b):
@@ -48,6 +47,17 @@ def observables(s, n, k, v, e, rcf, lin6, sff15, mff15, lam_b, mass_b):
     else:
         row += [0.0] * 6
     return row
+
+
+def blocked_sem(x):
+    """standard error of the mean of a correlated series by the blocking method: blocks are merged pairwise while at
+    least eight remain and the LARGEST estimate is kept (slow modes make single-level estimates too small)"""
+    y = np.asarray(x, dtype=float)
+    best = 0.0
+    while len(y) >= 8:
+        best = max(best, y.std(ddof=1) / np.sqrt(len(y)))
+        y = y[:len(y) // 2 * 2].reshape(-1, 2).mean(axis=1)
+    return best
 
 
 COLS = ["K", "V", "E_rot", "rcf(1)", "rcf(Q/4)", "rcf(Q/2)", "fs_perp(.sup)", "fs_par(.sup)", "fs_xx(sff)", "fs_yy(sff)", "fs_zz(sff)",
@@ -96,4 +106,4 @@ if __name__ == "__main__":
         r = np.array(d["rows"])
         print(case, "->", path)
         for i, c in enumerate(COLS):
-            print(f"   {c:16s} {r[:, i].mean(): .6g} +- {r[:, i].std(ddof=1) / np.sqrt(len(r)):.3g}")
+            print(f"   {c:16s} {r[:, i].mean(): .6g} +- {blocked_sem(r[:, i]):.3g}")

@@ -66,10 +66,21 @@ def gpu_blocks(pkg, name, kw, nchains, nblocks, per_block, skip):
     return np.array(rows)
 
 
+def blocked_sem(x):
+    """standard error of a correlated series by the blocking method (blocks merged pairwise while eight remain, largest
+    estimate kept): the block rows of one Markov chain are not independent when slow modes outlive a block"""
+    y = np.asarray(x, dtype=float)
+    best = y.std(ddof=1) / np.sqrt(len(y))
+    while len(y) >= 8:
+        best = max(best, y.std(ddof=1) / np.sqrt(len(y)))
+        y = y[:len(y) // 2 * 2].reshape(-1, 2).mean(axis=1)
+    return best
+
+
 def compare(g, r, cols):
     for i, nm in cols:
         mg, mr = g[:, i].mean(), r[:, i].mean()
-        sg, sr = g[:, i].std(ddof=1) / np.sqrt(len(g)), r[:, i].std(ddof=1) / np.sqrt(len(r))
+        sg, sr = blocked_sem(g[:, i]), blocked_sem(r[:, i])
         sigma = np.hypot(sg, sr)
         print(f"{nm}: gpu {mg:.5f} +- {sg:.5f}   reference {mr:.5f} +- {sr:.5f}   diff {abs(mg-mr)/sigma:.2f} sigma")
         assert abs(mg - mr) < 2.0 * sigma + 1e-9 * abs(mr), f"{nm}: {mg} vs {mr} (sigma {sigma})"
@@ -110,7 +121,7 @@ def _stats_case(pkg, case, nchains, gpu_per_block, min_sigma_cols=()):
     skip = d["skip"]
     G = pkg.gpu.PimcGpu(cfg, nchains=nchains)
     G.seed((12345,) * 6)
-    G.steps(200 * s.P)
+    G.steps(2000 * s.P)          # equilibration: the lattice start relaxes over ~1000 passes (slow cluster modes)
     rows = []
     for b in range(len(r)):
         G.accum_reset()
