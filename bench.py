@@ -118,9 +118,68 @@ def sample_size(s):
     return max(1, min(s.P, 64))
 
 
+def _reference_child(args):
+    """one reference chain in this process (the reference keeps its state in globals): prints {"t_step", "t_mol"}"""
+    from oracle import oracle_py as op
+    pkg = ge.load_package()
+    cfg = pkg.configs.make_config(args.workload)
+    s = cfg.system
+    threads = int(os.environ.get("OMP_NUM_THREADS", "1"))
+    cpus = os.environ.get("PIMC_REF_CPUS")
+    if cpus:
+        try:
+            os.sched_setaffinity(0, {int(c) for c in cpus.split(",")})
+        except OSError:
+            pass
+    fast = op.ref_available(fast=True)
+    sys.stdout.flush()
+    saved = os.dup(1)                                              # the reference chats on stdout (cout); keep ours to one JSON line
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    os.dup2(devnull, 1)
+    try:
+        R = op.Ref(cfg, nthreads=threads, fast=fast)
+        R.lib.ref_run_steps.restype = __import__("ctypes").c_double
+        nsamp = sample_size(s)
+        t0 = 1                                                     # samples start after time 0: the whole-path sweep is
+        for _ in range(args.warmup):                               # timed once, separately, and added pro rata below
+            R.lib.ref_run_steps(t0, nsamp); t0 += nsamp
+        t_mol = R.lib.ref_run_steps(0, 1)                          # one step at time == 0: molecular + 1 ordinary step
+        tt = 0.0
+        for _ in range(args.steps):
+            tt += R.lib.ref_run_steps(t0, nsamp); t0 += nsamp
+    finally:
+        os.dup2(saved, 1)
+    print(json.dumps({"t_step": tt / (args.steps * nsamp), "t_mol": t_mol, "fast": bool(fast)}))
+
+
+def _spawn_reference(args, nproc, threads, cpus_of):
+    """`nproc` concurrent reference chains, `threads` OpenMP threads each; returns the children's timing dicts"""
+    import subprocess
+    procs = []
+    for k in range(nproc):
+        env = {**os.environ, "PIMC_REF_CHILD": "1", "OMP_NUM_THREADS": str(threads), "OMP_PROC_BIND": "false", "RANK": "0", "WORLD_SIZE": "1"}
+        if cpus_of:
+            env["PIMC_REF_CPUS"] = ",".join(str(c) for c in cpus_of(k))
+        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", args.workload, "--steps", str(args.steps), "--warmup", str(args.warmup)]
+        procs.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, env=env))
+    out = []
+    for pr in procs:
+        o = pr.communicate(timeout=1500)[0]
+        line = [ln for ln in o.splitlines() if ln.startswith("{")]
+        if not line:
+            return None
+        out.append(json.loads(line[-1]))
+    return out
+
+
 def reference_arm(args):
-    """The reference's own CPU implementation of the path (oracle/_ref, its unmodified C++ objects + the C++
-    restatement of its Fortran leaves), all host threads, on a bounded sample of the same workload."""
+    """The reference's own CPU implementation of the path (oracle/_ref: its unmodified C++ objects + the C++ restatement of
+    its Fortran leaves) on the host cores, on a bounded sample of the SAME workload as the GPU arm: `chains` independent
+    Markov chains run side by side, one process each (the reference keeps its state in globals), the cores divided evenly
+    between them as OpenMP threads.  The single-chain figures with one thread and with every core are reported
+    beside it."""
+    if os.environ.get("PIMC_REF_CHILD"):
+        return _reference_child(args)
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -128,44 +187,45 @@ def reference_arm(args):
     pkg = ge.load_package()
     cfg = pkg.configs.make_config(args.workload)
     s = cfg.system
-    cores = os.cpu_count() or 1
-    fast = op.ref_available(fast=True)
-    if not (fast or op.ref_available()):
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    if not (op.ref_available(fast=True) or op.ref_available()):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref was not built (needs /root/reference at build time)"}))
         return
-    sys.stdout.flush()
-    saved = os.dup(1)                                              # the reference chats on stdout (cout); keep ours to one JSON line
-    devnull = os.open(os.devnull, os.O_WRONLY)
-    os.dup2(devnull, 1)
-    try:
-        R = op.Ref(cfg, nthreads=cores, fast=fast)
-    finally:
-        os.dup2(saved, 1)
-    R.lib.ref_run_steps.restype = __import__("ctypes").c_double
+    chains = args.chains or (8 if args.workload == "C5" else 148)
+    nproc = min(chains, cores)
+    threads = max(1, cores // nproc)
+    allowed = sorted(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else list(range(cores))
+    res = _spawn_reference(args, nproc, threads, lambda k: allowed[k * threads:(k + 1) * threads])
+    if not res:
+        print(json.dumps({"impl": "reference", "unavailable": "the reference processes produced no timing"}))
+        return
     nsamp = sample_size(s)
     bu = s.bead_updates_per_pass()
-    per_step = (bu["bisection"] + bu["rotation"]) / s.P          # bead-updates per `time` iteration (one chain)
 
-    def one(t0):
-        return R.lib.ref_run_steps(t0, nsamp), per_step * nsamp
-    t0 = 1                                                         # samples start after time 0: the whole-path sweep is
-    for _ in range(args.warmup):                                   # timed once, separately, and added pro rata below
-        one(t0); t0 += nsamp
-    t_mol = R.lib.ref_run_steps(0, 1)                              # one step at time == 0: molecular + 1 ordinary step
-    tt = nn = 0.0
-    for _ in range(args.steps):
-        dt, n = one(t0); t0 += nsamp
-        tt += dt; nn += n
-    t_step = tt / (args.steps * nsamp)
-    t_pass = t_step * s.P + max(0.0, t_mol - t_step)               # a full pass = P ordinary steps + the time-0 extras
-    value = bu["total"] / t_pass
+    def pass_time(r):
+        return r["t_step"] * s.P + max(0.0, r["t_mol"] - r["t_step"])        # a full pass = P ordinary steps + the time-0 extras
+    t_pass = max(pass_time(r) for r in res)                                    # the slowest of the concurrent chains
+    # `chains` chains on `nproc` concurrent processes: ceil(chains / nproc) rounds of the measured pass time
+    rounds = (chains + nproc - 1) // nproc
+    value = bu["total"] * chains / (t_pass * rounds)
+    single = {}
+    import copy
+    short = copy.copy(args)
+    short.steps, short.warmup = min(args.steps, 3), min(args.warmup, 1)       # side figures: a shorter sample
+    for label, th in (("omp1", 1), ("omp_all", cores)):
+        r1 = _spawn_reference(short, 1, th, None)
+        single[label] = bu["total"] / pass_time(r1[0]) if r1 else None
+    fast = res[0].get("fast")
     line = {"metric": "pimc_bead_updates_per_sec", "value": value, "unit": "bead-updates/s", "impl": "reference", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_pass * rounds, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args.workload, s, 1), "chains": 1, "sample_time_steps": nsamp},
+            "config": {"workload": workload_name(args.workload, s, chains), "chains_per_gpu": chains, "sample_time_steps": nsamp,
+                       "processes": nproc, "omp_threads_per_process": threads},
             "cpu_baseline": {"value": value, "unit": "bead-updates/s", "cores": cores, "kind": "reference",
-                             "sample": f"{args.steps} x {nsamp} iterations of the time loop (mc_main.cc:349-381) of one chain + one time-0 step, scaled to a pass; "
-                                       f"{'-Ofast' if fast else '-O2'} build of the reference objects, OMP threads={cores}"},
+                             "single_chain_omp1": single["omp1"], "single_chain_omp_all": single["omp_all"],
+                             "sample": f"{chains} independent chains as {nproc} concurrent processes x {threads} OpenMP threads; each: {args.steps} x {nsamp} iterations of "
+                                       f"the time loop (mc_main.cc:349-381) + one time-0 step, scaled to a pass; slowest process counts; "
+                                       f"{'-Ofast' if fast else '-O2'} build of the reference objects"},
             "e2e": {"value": value, "unit": "bead-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -182,6 +242,8 @@ def cpu_baseline(pkg, args, cfg):
     """Bounded CPU sample in a subprocess (the reference keeps global state and must not share our CUDA process)."""
     import subprocess
     cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", args.workload, "--steps", "3", "--warmup", "1"]
+    if args.chains:
+        cmd += ["--chains", str(args.chains)]
     try:
         out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env={**os.environ, "RANK": "0", "WORLD_SIZE": "1"})
         for ln in reversed(out.stdout.splitlines()):

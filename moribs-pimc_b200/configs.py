@@ -160,6 +160,11 @@ def write_qmc_input(s: System, path: str, outdir: str = "./out/") -> None:
         lines.append(f"WORM {s.worm[0]} {s.worm[1]!r} {s.worm[2]}")
     if s.minimage:
         lines.append("MINIMAGE")
+    for key, flag in zip(("REFLECTX", "REFLECTY", "REFLECTZ"), s.reflect):      # symmetry moves of MCGetAverage, mc_main.cc:647-692
+        if flag:
+            lines.append(f"{key} {flag}")
+    if s.rotsym:
+        lines.append(f"ROTSYM {s.rotsym}")
     lines += [f"NUMBEROFSLICES {s.P}", f"NUMBEROFPASSES {s.passes}", f"NUMBEROFBLOCKS {s.blocks} {s.eq_blocks}",
               "MCSKIP_RATIO 100000000", "MCSKIP_TOTAL 100000000", f"MCSKIP_AVERG {s.skip_averg}"]
     with open(path, "w") as f:

@@ -58,6 +58,7 @@ struct Params {
    const double2 *cell2d;        // [(rs-1)][cs] row pairs {V[ir][ic], V[ir+1][ic]}: a bilinear cell is two adjacent 16-byte
                                  // entries (32 contiguous bytes, 2x the table instead of 4x so the hot region stays in L2)
    const double2 *rgi2d, *cgi2d; // {grid[i], 1/(grid[i+1]-grid[i])} of the two axes
+   int cell4_on, cell_hint;      // whole-cell table in use (else the row-pair table); L2 eviction-priority hints on the gathers
    const double *cell4;          // [(rs-1)][(cs-1)][4] whole cells {V[ir][ic], V[ir+1][ic], V[ir][ic+1], V[ir+1][ic+1]}, 32-byte aligned
    int rg3, thg3, chg3; const double *v3d; double rvmin, rvmax, rvstep;
    int nrot, nlutrot; const double *rgrid, *rdens, *rderv, *resqr, *rdens2, *rderv2, *resqr2; const int *lutrot; double lutrot_scale;
@@ -90,9 +91,12 @@ struct Params {
    // geometry cache of the rotor-atom terms of a linear rotor (rot_potential_cached): the positions only change in the
    // translational sweeps, so between two of them every (slice, partner) term keeps its unit vector (p_j - p_g)/r, its
    // radial cell row and its radial weight; a rotational proposal only changes cos(theta) = n.u
+   int rot_run;                  // linear rotor, several CTAs per chain: free-running rotational sweeps (rot_run), contiguous slice blocks per CTA
+   int *rot_flags;               // [c][Q] decisions made by every rot slice in this launch (zeroed before every launch)
+   int bis_piped;                // two-warp teams: bisection sweep software-pipelined over the atoms (bisection_sweep_piped)
    int geo_on, geo_items, geo_n; // enabled; real items per rot slice = R x (N - 1); padded stride
-   double *geo;                  // [c][q][4][geo_n]: ux, uy, uz, radial weight dr
-   int *geo_i;                   // [c][q][geo_n]: ir * cs2d (row offset of the radial cell in cell2d)
+   double *geo;                  // [c][q][geo_n][4]: one aligned 32-byte record {ux, uy, uz, w} per item; w = the radial weight dr with
+                                 // the radial cell index ir (< 4096) in the 12 lowest mantissa bits (|error| <= 2^-40 dr)
 };
 
 __host__ __device__ inline size_t pos_index(const Params &p, int c, int it, int d, int a)
@@ -193,7 +197,16 @@ struct SmallTables {
    const SplineRec *rec1d, *recrot;
    const double2 *rgi2d, *cgi2d;   // axis tables of the 2-D potential (shared memory in the move kernel)
    const double2 *pa1d, *pb1d;     // per-interval cubic of the 1-D potential (shared memory in the move kernel)
+   // the same tables as 32-bit shared-window addresses, valid in the move kernel only (stage_tables): explicit ld.shared
+   // instead of generic loads (which take the global-memory scoreboard and an address-window check each)
+   uint32_t s_pa1d, s_pb1d, s_rgi2d, s_cgi2d;
 };
+__device__ __forceinline__ double2 lds_d2(uint32_t base, int i)
+{
+   double2 v;
+   asm("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(base + 16u * (uint32_t)i));
+   return v;
+}
 
 // interval search + cubic evaluation on the packed records: same interval as the reference's bisection search
 // (klo = max{k : x_k <= x}); a, b use the stored 1/h, the curvature terms the stored y'' h^2/6
@@ -276,7 +289,7 @@ __device__ __forceinline__ double spot1d_poly(const Params &p, const SmallTables
    k = max(0, min(k, p.n1d - 2));
    bad |= !(r > p.x0_1d && r < p.xn_1d);
    const double tt = xq - (double)k;
-   const double2 A = t.pa1d[k], B = t.pb1d[k];
+   const double2 A = lds_d2(t.s_pa1d, k), B = lds_d2(t.s_pb1d, k);
    return fma(fma(fma(B.y, tt, B.x), tt, A.y), tt, A.x);
 }
 
@@ -291,10 +304,20 @@ __device__ __forceinline__ void load_cell(const double2 *cell, double &y1, doubl
    const double2 a = __ldg(cell), b = __ldg(cell + 1);
    y1 = a.x; y2 = a.y; y4 = b.x; y3 = b.y;
 }
-// one bilinear cell from the whole-cell table: a single 256-bit gather (LDG.E.256 on sm_100a)
+// one bilinear cell from the whole-cell table: a single 256-bit gather (LDG.E.256 on sm_100a), kept in L2 with priority --
+// the hot part of the table (tens of MB) competes with the streamed geometry records for one L2 partition
 __device__ __forceinline__ void load_cell4(const double *cell, double &y1, double &y2, double &y3, double &y4)
 {
    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(y1), "=d"(y2), "=d"(y4), "=d"(y3) : "l"(cell));
+}
+__device__ __forceinline__ void load_cell4_keep(const double *cell, double &y1, double &y2, double &y3, double &y4)
+{
+   asm("ld.global.nc.L2::evict_last.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(y1), "=d"(y2), "=d"(y4), "=d"(y3) : "l"(cell));
+}
+// one geometry record: streamed once per rotational sweep, must not displace the table in L2
+__device__ __forceinline__ void load_geo4(const double *rec, double &ux, double &uy, double &uz, double &w)
+{
+   asm volatile("ld.global.L1::no_allocate.L2::evict_first.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(ux), "=d"(uy), "=d"(uz), "=d"(w) : "l"(rec) : "memory");
 }
 // index selection of LPot2D, mc_poten.cc:696-704: floor((x - xmin)/delta) exactly as the reference -- the product with
 // the stored reciprocal decides unless it lands within 1e-7 of an integer, where the true quotient is taken
@@ -357,7 +380,7 @@ __device__ __forceinline__ void lpot2d_xn(const Params &p, const SmallTables &t,
    for (int u = 0; u < NB; u++) load_cell(p.cell2d + (size_t)ir[u] * p.cs2d + ic[u], y1[u], y2[u], y3[u], y4[u]);
    #pragma unroll
    for (int u = 0; u < NB; u++) {
-      const double2 gr = t.rgi2d[ir[u]], gc = t.cgi2d[ic[u]];
+      const double2 gr = lds_d2(t.s_rgi2d, ir[u]), gc = lds_d2(t.s_cgi2d, ic[u]);      // move kernel only: axis tables staged in shared memory
       double dr = (r[u] - gr.x) * gr.y;
       double dc = (cost[u] - gc.x) * gc.y;
       out[u] = (1.0 - dr) * (1.0 - dc) * y1[u] + dr * (1.0 - dc) * y2[u] + dr * dc * y3[u] + (1.0 - dr) * dc * y4[u];

@@ -64,6 +64,7 @@ struct Ctx {
    int T, lane_t, team_lane0, team_id, nteams_chain, team_cta;
    int W, tw, wl, wlanes;     // warps per team, this thread's warp inside the team, lane inside that warp, lanes per warp part
    int G, gl, grp, ngrp;      // rot group size, index inside the group, group index in the CTA, groups per CTA
+   unsigned gmask;            // lanes of this thread's rot group inside its warp (all lanes when the group fills or spans warps)
    SmallTables t;
    double *team_buf;   // shared: this thread's team scratch (segment positions, unit normals, stream cache, partial sums)
    double *red;        // shared: 40 doubles
@@ -76,7 +77,7 @@ struct Ctx {
 };
 
 // doubles of scratch per bisection team (host and device use the same formula)
-__host__ __device__ inline int team_buf_doubles(int seg_max) { return (seg_max + 1) * 6 + seg_max * 3 + TEAM_EXTRA; }
+__host__ __device__ inline int team_buf_doubles(int seg_max) { return (seg_max + 1) * 12 + seg_max * 3 + TEAM_EXTRA; }   // two (positions, normals) sets: pipelined sweep
 
 __device__ __forceinline__ void chain_sync(const Params &p, Ctx &x)
 {
@@ -173,7 +174,7 @@ __device__ __forceinline__ bool fast_atoms(const Params &p, int tg)
 }
 template <int KIND>
 __device__ __forceinline__ double partner_sum_diff(const Params &p, const SmallTables &t, int c, int g, const double *pn, const double *po,
-                                                   int it, int lane, int stride)
+                                                   int it, int lane, int stride, int jx = -1)
 {
    double D = 0.0;
    const int N = p.N;
@@ -188,7 +189,7 @@ __device__ __forceinline__ double partner_sum_diff(const Params &p, const SmallT
          #pragma unroll
          for (int u = 0; u < 4; u++) {
             const int j = j0 + u * stride;
-            ok[u] = j < jb && j != g;
+            ok[u] = j < jb && j != g && j != jx;                    // jx: a partner whose term the caller adds later (pipelined sweep)
             const int jj = ok[u] ? j : (g == ja ? ja + 1 : ja);     // masked slots: any atom other than g (a real distance)
             const double qx = px[jj], qy = py[jj], qz = pz[jj];
             double inv_;
@@ -473,6 +474,176 @@ __device__ void bisection_sweep(const Params &p, Ctx &x, int type, int off)
 }
 
 // ---------------------------------------------------------------------------------------------
+// The same sweep software-pipelined over the atoms, for two-warp teams of an atomic species of a spline system.
+// Atom a only feels the outcome of atom a-1 through ONE partner term per bead (the pair action is a sum over partners),
+// so warp (a & 1) of the team proposes atom a -- normals, the midpoints of every level, the partner sums of every level
+// without the partner a-1 -- while the other warp is still deciding atom a-1; once that atom is final it adds the
+// missing term, runs the level tests and writes back.  Draws per stream, order of the level tests, early rejection and
+// the acceptance rule are those of bisection_sweep (the sums of levels below a rejection are computed and dropped); the
+// per-atom critical path shrinks from "everything" to "one partner term + the tests".
+// Hand-over between the two warps: two counters in shared memory (normals drawn up to atom .., final up to atom ..).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_wait_ge(volatile int *flag, int v)
+{
+   while (*flag < v) { }
+   __syncwarp();
+   __threadfence_block();
+}
+__device__ __forceinline__ void warp_post(volatile int *flag, int v)
+{
+   __syncwarp();
+   __threadfence_block();
+   if ((threadIdx.x & 31) == 0) *flag = v;
+}
+
+template <int KIND>
+__device__ void bisection_sweep_piped(const Params &p, Ctx &x, int type, int off)
+{
+   const int c = x.c, P = p.P, N = p.N;
+   const int L = p.levels[type], seg = 1 << L, nseg = P / seg;
+   const int base = p.first[type], na = p.numb[type];
+   const double bnorm = 1.0 / (p.lambda[type] * p.tau);
+   const int nrounds = (nseg + x.nteams_chain - 1) / x.nteams_chain;
+   const int w = x.tw, lane = x.wl;                       // warp of the team (0, 1), lane of the warp
+   const int nother = N - na;
+   bump_pos_epoch(p, x);
+   for (int rd = 0; rd < nrounds; rd++) {
+      const int k = rd * x.nteams_chain + x.team_id;
+      const bool active = k < nseg;
+      const int s0 = active ? (off + k * seg) % P : 0;
+      double *buf = x.team_buf;
+      double *nx = buf + (size_t)w * (p.seg_max + 1) * 6, *xi = nx + (p.seg_max + 1) * 3;      // this warp's positions / normals
+      uint32_t *rc = reinterpret_cast<uint32_t *>(buf + (p.seg_max + 1) * 12);                  // streams of slices s0 .. s0+seg-1
+      double *dsum = buf + (p.seg_max + 1) * 12 + p.seg_max * 3 + w * (MAXLEV + 2);             // this warp's level sums
+      volatile int *flags = reinterpret_cast<volatile int *>(buf + (p.seg_max + 1) * 12 + p.seg_max * 3 + 2 * (MAXLEV + 2));   // [0] normals drawn, [1] atoms final
+      if (active)
+         for (int i = x.lane_t; i < seg * 6; i += x.T) rc[i] = stream_ptr(p, c, (s0 + i / 6) % P)[i % 6];
+      if (x.lane_t == 0) { flags[0] = 0; flags[1] = 0; }
+      team_sync(x);
+      if (active)
+      for (int a = w; a < na; a += 2) {
+         const int gA = base + a;
+         const int gB = (p.stat[type] == 1) ? p.pindex[(size_t)c * N + gA] : gA;
+         // the partner still in flight: atom a-1 (its beads past beta sit on its successor world line)
+         const int hA = a > 0 ? gA - 1 : -1;
+         const int hB = a > 0 ? ((p.stat[type] == 1) ? p.pindex[(size_t)c * N + hA] : hA) : -1;
+         if (lane < 6) {
+            const int e = lane / 3, d = lane - 3 * e, t = e * seg;
+            nx[t * 3 + d] = p.pos[pos_index(p, c, (s0 + t) % P, d, (s0 + t >= P) ? gB : gA)];
+         }
+         // unit normals of the interior slices from the slices' own streams, after those of atom a-1
+         if (a > 0) warp_wait_ge(flags, a);
+         for (int i0 = 0; i0 < (seg - 1) * 3; i0 += 32) {
+            const int i = i0 + lane;
+            const bool valid = i < (seg - 1) * 3;
+            const int t = valid ? 1 + i / 3 : 1, d = i - 3 * (t - 1);
+            Mrg rs;
+            if (valid) {
+               mrg_load(rs, rc + t * 6);
+               double r1 = 0, r2 = 0;
+               for (int kk = 0; kk <= d; kk++) { r1 = mrg_u01(rs); r2 = mrg_u01(rs); }
+               for (int kk = d + 1; kk < 3; kk++) { mrg_u01(rs); mrg_u01(rs); }
+               xi[t * 3 + d] = sqrt(-log(r1)) * cos(2.0 * PI * r2);
+            }
+            __syncwarp();                               // every lane of a slice has read the state before it advances
+            if (valid && d == 2) mrg_store(rs, rc + t * 6);
+            __syncwarp();
+         }
+         warp_post(flags, a + 1);
+         // midpoints of every level, then the partner sums of every level without the partner in flight
+         for (int level = 0; level < L; level++) {
+            const int lss = seg >> level, half = lss >> 1, nmid = 1 << level;
+            const double sq = sqrt(bnorm / (double)lss);
+            for (int i = lane; i < nmid * 3; i += 32) {
+               const int m = i / 3, d = i - 3 * m, t1 = half + m * lss;
+               nx[t1 * 3 + d] = 0.5 * (nx[(t1 - half) * 3 + d] + nx[(t1 + half) * 3 + d]) + xi[t1 * 3 + d] / sq;
+            }
+            __syncwarp();
+         }
+         for (int level = 0; level < L; level++) {
+            const int lss = seg >> level, half = lss >> 1, nmid = 1 << level;
+            double D = 0.0;
+            for (int i = lane; i < nmid * nother; i += 32) {          // partners of the other species (the rotor)
+               const int m = i / nother, jo = i - m * nother;
+               const int j = (jo < base) ? jo : jo + na;
+               const int t1 = half + m * lss, sl = (s0 + t1) % P, g = (s0 + t1 >= P) ? gB : gA;
+               double po[3], pn[3];
+               #pragma unroll
+               for (int d = 0; d < 3; d++) { po[d] = p.pos[pos_index(p, c, sl, d, g)]; pn[d] = nx[t1 * 3 + d]; }
+               D += pair_diff<KIND>(p, x.t, c, g, pn, po, j, sl);
+            }
+            for (int m = 0; m < nmid; m++) {
+               const int t1 = half + m * lss, sl = (s0 + t1) % P;
+               const bool wrap = s0 + t1 >= P;
+               const int g = wrap ? gB : gA;
+               double po[3], pn[3];
+               #pragma unroll
+               for (int d = 0; d < 3; d++) { po[d] = p.pos[pos_index(p, c, sl, d, g)]; pn[d] = nx[t1 * 3 + d]; }
+               D += partner_sum_diff<KIND>(p, x.t, c, g, pn, po, sl, lane, 32, wrap ? hB : hA);
+            }
+            D = team_sum(D, 32);
+            if (lane == 0) dsum[level] = D;
+         }
+         __syncwarp();
+         // atom a-1 is final: its term, the level tests, the write-back
+         if (a > 0) warp_wait_ge(flags + 1, a);
+         double S = 0.0;
+         bool alive = true;
+         int used = 0;
+         Mrg as;
+         if (lane == 0) mrg_load(as, rc);
+         for (int level = 0; level < L && alive; level++) {
+            const int lss = seg >> level, half = lss >> 1, nmid = 1 << level;
+            double e = 0.0;
+            if (a > 0)
+               for (int m = lane; m < nmid; m += 32) {
+                  const int t1 = half + m * lss, sl = (s0 + t1) % P;
+                  const bool wrap = s0 + t1 >= P;
+                  const int g = wrap ? gB : gA, j = wrap ? hB : hA;
+                  double d2n = 0.0, d2o = 0.0;
+                  #pragma unroll
+                  for (int d = 0; d < 3; d++) {
+                     const double pj = __ldcg(p.pos + pos_index(p, c, sl, d, j)), pg = p.pos[pos_index(p, c, sl, d, g)], pn = nx[t1 * 3 + d];
+                     d2n += (pn - pj) * (pn - pj);
+                     d2o += (pg - pj) * (pg - pj);
+                  }
+                  e += spot1d_move(p, x.t, sqrt(d2n)) - spot1d_move(p, x.t, sqrt(d2o));
+               }
+            if (a > 0 && nmid > 1) e = team_sum(e, 32);
+            else e = __shfl_sync(0xffffffffu, e, 0);
+            const double D = dsum[level] + e;
+            const double deltav = (D - S) * (p.tau * (double)half);
+            S += D;
+            if (!(deltav < 0.0)) {
+               double u = 0.0;
+               if (lane == 0) { u = mrg_u01(as); }
+               u = __shfl_sync(0xffffffffu, u, 0);
+               used++;
+               if (!(exp(-deltav) > u)) alive = false;
+            }
+         }
+         if (lane == 0) {
+            if (used > 0) mrg_store(as, rc);
+            double *cn = counter_ptr(p, c, type, 1);
+            atomicAdd(cn, 1.0);
+            if (alive) atomicAdd(cn + 1, 1.0);
+         }
+         if (alive)
+            for (int i = lane; i < (seg - 1) * 3; i += 32) {
+               const int t = 1 + i / 3, d = i % 3;
+               p.pos[pos_index(p, c, (s0 + t) % P, d, (s0 + t >= P) ? gB : gA)] = nx[t * 3 + d];
+            }
+         warp_post(flags + 1, a + 1);
+      }
+      team_sync(x);
+      if (active)
+         for (int i = x.lane_t; i < seg * 6; i += x.T) stream_ptr(p, c, (s0 + i / 6) % P)[i % 6] = rc[i];
+      team_sync(x);
+   }
+   chain_sync(p, x);
+}
+
+// ---------------------------------------------------------------------------------------------
 // rotational Metropolis step at rot slice q for rotor m (MCRot3Dstep mc_piqmc.cc:938-1199,
 // MCRotLinStep :781-936), executed by one rot group:
 //   leader: uniforms, proposal, orientation matrices          -> shared slot          | group sync
@@ -484,7 +655,7 @@ __device__ void bisection_sweep(const Params &p, Ctx &x, int type, int off)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void group_sync(const Ctx &x)
 {
-   if (x.G <= 32) __syncwarp();
+   if (x.G <= 32) __syncwarp(x.gmask);          // groups that share a warp may be in different places (rot_run)
    else if (x.ngrp <= 15) asm volatile("bar.sync %0, %1;" ::"r"(x.grp + 1), "r"(x.G) : "memory");   // one named barrier per rot group
    else __syncthreads();
 }
@@ -576,7 +747,6 @@ __device__ __forceinline__ void geo_fill(const Params &p, Ctx &x, int g, int q)
 {
    const int c = x.c, NA = p.N - 1, it0 = q * p.R;
    double *gb = p.geo + ((size_t)c * p.Q + q) * 4 * p.geo_n;
-   int *gi = p.geo_i + ((size_t)c * p.Q + q) * p.geo_n;
    const double rmin = x.t.rgi2d[0].x;
    for (int k = x.gl; k < p.geo_items; k += x.G) {
       const int r = k / NA, jj = k - r * NA, j = jj < g ? jj : jj + 1, it = it0 + r;
@@ -587,9 +757,9 @@ __device__ __forceinline__ void geo_fill(const Params &p, Ctx &x, int g, int q)
       fast_r_invr(dx * dx + dy * dy + dz * dz, rr, invr);
       const int ir = lpot_index(rr - rmin, p.inv_dr2d, p.dr2d, p.rs2d);          // LPot2D radial cell, mc_poten.cc:696-701
       const double2 gr = x.t.rgi2d[ir];
-      gb[k] = dx * invr; gb[p.geo_n + k] = dy * invr; gb[2 * p.geo_n + k] = dz * invr;
-      gb[3 * p.geo_n + k] = (rr - gr.x) * gr.y;
-      gi[k] = ir * (p.cs2d - 1);          // row offset in the whole-cell table
+      const double dr = (rr - gr.x) * gr.y;
+      const double w = __longlong_as_double((__double_as_longlong(dr) & ~0xfffLL) | (long long)ir);      // ir rides in the low mantissa bits
+      *reinterpret_cast<double4 *>(gb + 4 * (size_t)k) = make_double4(dx * invr, dy * invr, dz * invr, w);
    }
 }
 
@@ -606,11 +776,22 @@ __device__ __forceinline__ double geo_eval4(const Params &p, const SmallTables &
    }
    double y1[4], y2[4], y3[4], y4[4];
    #pragma unroll
-   for (int u = 0; u < 4; u++) load_cell4(p.cell4 + 4 * (size_t)(ib[u] + ic[u]), y1[u], y2[u], y3[u], y4[u]);
+   if (p.cell4_on) {
+      if (p.cell_hint) {
+         #pragma unroll
+         for (int u = 0; u < 4; u++) load_cell4_keep(p.cell4 + 4 * (size_t)(ib[u] + ic[u]), y1[u], y2[u], y3[u], y4[u]);
+      } else {
+         #pragma unroll
+         for (int u = 0; u < 4; u++) load_cell4(p.cell4 + 4 * (size_t)(ib[u] + ic[u]), y1[u], y2[u], y3[u], y4[u]);
+      }
+   } else {
+      #pragma unroll
+      for (int u = 0; u < 4; u++) load_cell(p.cell2d + (size_t)(ib[u] + ic[u]), y1[u], y2[u], y3[u], y4[u]);
+   }
    double v = 0.0;
    #pragma unroll
    for (int u = 0; u < 4; u++) {
-      const double2 gc = t.cgi2d[ic[u]];
+      const double2 gc = lds_d2(t.s_cgi2d, ic[u]);
       const double dc = (cs[u] - gc.x) * gc.y;
       const double lo = y1[u] + dr[u] * (y2[u] - y1[u]);         // V at cos(theta)_ic, interpolated in r
       const double hi = y4[u] + dr[u] * (y3[u] - y4[u]);         // V at cos(theta)_ic+1
@@ -626,8 +807,8 @@ template <int NO>
 __device__ __forceinline__ void rot_potential_cached(const Params &p, Ctx &x, int q, const double *o0, const double *o1, double *vout)
 {
    const int c = x.c, G = x.G, n = p.geo_items, gn = p.geo_n;
-   const double *gx = p.geo + ((size_t)c * p.Q + q) * 4 * gn, *gy = gx + gn, *gz = gy + gn, *gd = gz + gn;
-   const int *gi = p.geo_i + ((size_t)c * p.Q + q) * gn;
+   const double *gb = p.geo + ((size_t)c * p.Q + q) * 4 * gn;
+   const int rowlen = p.cell4_on ? p.cs2d - 1 : p.cs2d;
    const double cmin = x.t.cgi2d[0].x;
    const double a0 = o0[0], a1 = o0[1], a2 = o0[2];
    double b0 = 0.0, b1 = 0.0, b2 = 0.0;
@@ -642,7 +823,13 @@ __device__ __forceinline__ void rot_potential_cached(const Params &p, Ctx &x, in
          const int k = k0 + u * G;
          ok[u] = k < n;
          const int kk = ok[u] ? k : k0;                 // masked slots repeat the first item of the batch (a valid look-up)
-         ux[u] = gx[kk]; uy[u] = gy[kk]; uz[u] = gz[kk]; dr[u] = gd[kk]; ib[u] = gi[kk];
+         load_geo4(gb + 4 * (size_t)kk, ux[u], uy[u], uz[u], dr[u]);
+      }
+      #pragma unroll
+      for (int u = 0; u < 4; u++) {
+         const long long bits = __double_as_longlong(dr[u]);
+         ib[u] = (int)(bits & 0xfffLL) * rowlen;        // row offset of the radial cell in the whole-cell table
+         dr[u] = __longlong_as_double(bits & ~0xfffLL);
       }
       v0 += geo_eval4(p, x.t, cmin, a0, a1, a2, ux, uy, uz, dr, ib, ok);
       if (NO == 2) v1 += geo_eval4(p, x.t, cmin, b0, b1, b2, ux, uy, uz, dr, ib, ok);
@@ -1027,6 +1214,121 @@ __device__ void rot_sweep_pipe(const Params &p, Ctx &x, int type, int *err)
    MARK(x, 10);
 }
 
+// rot slice owned by local slot ls of this CTA: a contiguous block for the free-running sweeps, round-robin otherwise
+__device__ __forceinline__ int owned_slice(const Params &p, const Ctx &x, int ls)
+{
+   return p.rot_run ? x.crank * (p.Q / p.cpc) + ls : ls * p.cpc + x.crank;
+}
+
+// ---------------------------------------------------------------------------------------------
+// `nrun` consecutive rotational sweeps of a linear rotor with no translational sweep in between, free-running: every
+// rot group owns ONE slice for the whole run and loops  propose -> potential sums (gathers) -> wait for the two
+// neighbouring slices -> four density factors, accept, commit -> post  on its own.  An even slice's n-th decision needs
+// the (n-1)-th decisions of its odd neighbours, an odd slice's n-th decision the n-th of its even neighbours: the order
+// "all even, then all odd" of every sweep is kept, but no barrier couples slices that do not depend on each other, so the
+// gathers of the slices that may run ahead fill the time the others spend in their (latency-bound) decisions.
+// Hand-over through global memory: the deciding thread commits (phi, cos theta, n) and then stores the slice's decision
+// count with release semantics; a waiting group polls its two neighbours with acquire loads and reads their axes from L2.
+// Draws, proposals and acceptance are those of rot_step / rot_sweep_pipe.
+// ---------------------------------------------------------------------------------------------
+template <int KIND>
+__device__ void rot_run(const Params &p, Ctx &x, int type, int nrun, int *err)
+{
+   const int c = x.c, Q = p.Q, G = x.G, m = 0;
+   const int g = p.first[type];
+   const int nown = Q / p.cpc, ls = x.grp;
+   const bool active = ls < nown;
+   const int q = x.crank * nown + (active ? ls : 0);
+   RotSlot *sl = x.slot + (active ? ls : 0);
+   int q0 = q - 1, q2 = q + 1;
+   if (q0 < 0) q0 += Q;
+   if (q2 >= Q) q2 -= Q;
+   int *fl = p.rot_flags + (size_t)c * Q;
+   if (active)
+   for (int it = 0; it < nrun; it++) {
+      const int n = x.rot_iter + it;                     // sweeps this slice has completed in this launch
+      MARK(x, 1);
+      if (x.gl == 0) {
+         Mrg rs;
+         mrg_load(rs, x.rrng + ls * 6);
+         const double r1 = mrg_u01(rs), r2 = mrg_u01(rs), r3 = mrg_u01(rs);
+         mrg_store(rs, x.rrng + ls * 6);
+         const int epoch = p.pos_epoch[c];
+         double cost = sl->cur[0], phi = sl->cur[1], chi = sl->cur[2];
+         rot_propose<KIND>(p, type, r1, r2, r3, cost, phi, chi, sl->a);
+         sl->u4 = r3; sl->cost = cost; sl->phi = phi; sl->chi = chi;
+         sl->epoch = epoch;
+         sl->need_old = (sl->vep != epoch) ? 1 : 0;
+         sl->bad = 0;
+      }
+      MARK(x, 2);
+      group_sync(x);
+      double vnew = 0.0, vold = 0.0;
+      if (p.geo_on) {
+         if (sl->gep != sl->epoch) geo_fill(p, x, g, q);
+         double vv[2];
+         if (sl->need_old) { rot_potential_cached<2>(p, x, q, sl->a, sl->b, vv); vnew = vv[0]; vold = vv[1]; }
+         else { rot_potential_cached<1>(p, x, q, sl->a, nullptr, vv); vnew = vv[0]; }
+      } else {
+         vnew = rot_potential<KIND>(p, x, g, q, sl->a);
+         if (sl->need_old) vold = rot_potential<KIND>(p, x, g, q, sl->b);
+      }
+      const int gw = (G < 32) ? G : 32;
+      for (int o = gw >> 1; o > 0; o >>= 1) { vnew += __shfl_xor_sync(x.gmask, vnew, o); vold += __shfl_xor_sync(x.gmask, vold, o); }
+      if (G > 32 && (x.tid & 31) == 0) { x.part[2 * (x.gl >> 5)] = vnew; x.part[2 * (x.gl >> 5) + 1] = vold; }
+      MARK(x, 4);
+      // the two neighbours: odd slices wait for this sweep's even decisions, even slices for the previous sweep's odd ones
+      if (x.gl < 2) {
+         const int target = (q & 1) ? n + 1 : n;
+         const int *f = fl + (x.gl == 0 ? q0 : q2);
+         int v;
+         do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory"); } while (v < target);
+      }
+      group_sync(x);
+      MARK(x, 6);
+      // density factors rho(q0 -> cur), rho(cur -> q2), rho(q0 -> new), rho(new -> q2): neighbour axes from L2
+      if (x.gl < 4) {
+         const int i = x.gl, qq = (i == 0 || i == 2) ? q0 : q2;
+         const double *mid = (i < 2) ? sl->b : sl->a;
+         double dot = 0.0;
+         #pragma unroll
+         for (int d = 0; d < 3; d++) {
+            const double nb = __ldcg(p.cosn + ang_index(p, c, qq, d, m));
+            dot += (i == 0 || i == 2) ? nb * mid[d] : mid[d] * nb;
+         }
+         sl->rho[i] = (p.rotden_type == 1) ? rsline(p, dot, nullptr) : srotdens(p, x.t, dot);
+      }
+      group_sync(x);
+      MARK(x, 7);
+      if (x.gl == 0) {
+         if (G > 32) {
+            vnew = 0.0; vold = 0.0;
+            for (int w = 0; w < (G >> 5); w++) { vnew += x.part[2 * w]; vold += x.part[2 * w + 1]; }
+         }
+         if (!sl->need_old) vold = sl->vcache;
+         int bad = 0;
+         bool acc = rot_accept<KIND>(p, sl->rho, vnew, vold, sl->u4, &bad);
+         if (bad) { acc = false; atomicOr(err, bad); }
+         double *cn = counter_ptr(p, c, type, 2);
+         atomicAdd(cn, 1.0);
+         sl->vcache = acc ? vnew : vold;
+         sl->vep = sl->epoch;
+         sl->gep = sl->epoch;
+         if (acc) {
+            atomicAdd(cn + 1, 1.0);
+            rot_commit<KIND>(p, c, q, m, sl->cost, sl->phi, sl->chi);
+            sl->cur[0] = sl->cost; sl->cur[1] = sl->phi; sl->cur[2] = sl->chi;
+            #pragma unroll
+            for (int i = 0; i < 3; i++) sl->b[i] = sl->a[i];
+         }
+         asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(fl + q), "r"(n + 1) : "memory");
+      }
+      MARK(x, 9);
+   }
+   x.rot_iter += nrun;
+   chain_sync(p, x);
+}
+
 // ---------------------------------------------------------------------------------------------
 // the persistent kernel
 // ---------------------------------------------------------------------------------------------
@@ -1038,11 +1340,13 @@ __device__ __forceinline__ void stage_tables(const Params &p, SmallTables &t, do
    t.rgrid = p.rgrid; t.rdens = p.rdens; t.rdens2 = p.rdens2; t.lutrot = p.lutrot; t.recrot = p.recrot;
    t.rgi2d = p.rgi2d; t.cgi2d = p.cgi2d;
    t.pa1d = p.pa1d; t.pb1d = p.pb1d;
+   t.s_pa1d = t.s_pb1d = t.s_rgi2d = t.s_cgi2d = 0;
    if (p.rs2d) {
       double2 *d2 = reinterpret_cast<double2 *>(cursor);
       for (int i = threadIdx.x; i < p.rs2d; i += blockDim.x) d2[i] = p.rgi2d[i];
       for (int i = threadIdx.x; i < p.cs2d; i += blockDim.x) d2[p.rs2d + i] = p.cgi2d[i];
       t.rgi2d = d2; t.cgi2d = d2 + p.rs2d;
+      t.s_rgi2d = (uint32_t)__cvta_generic_to_shared(d2); t.s_cgi2d = t.s_rgi2d + 16u * (uint32_t)p.rs2d;
       cursor += 2 * (size_t)(p.rs2d + p.cs2d);
    }
    if (p.nrot && p.rot_in_smem) {
@@ -1063,6 +1367,7 @@ __device__ __forceinline__ void stage_tables(const Params &p, SmallTables &t, do
       const int nk = p.n1d - 1;
       for (int i = threadIdx.x; i < nk; i += blockDim.x) { d2[i] = p.pa1d[i]; d2[nk + i] = p.pb1d[i]; }
       t.pa1d = d2; t.pb1d = d2 + nk;
+      t.s_pa1d = (uint32_t)__cvta_generic_to_shared(d2); t.s_pb1d = t.s_pa1d + 16u * (uint32_t)nk;
       cursor += 4 * (size_t)nk;
    } else if (p.n1d) {
       const int nd = (p.n1d - 1) * (int)(sizeof(SplineRec) / sizeof(double));
@@ -1108,6 +1413,7 @@ pimc_steps_kernel(const __grid_constant__ Params p, long t0, long nsteps, int *e
    x.gl = x.tid & (x.G - 1);
    x.grp = x.tid / x.G;
    x.ngrp = blockDim.x / x.G;
+   x.gmask = x.G >= 32 ? 0xffffffffu : (((1u << x.G) - 1u) << ((x.tid & 31) & ~(x.G - 1)));
    x.bar_target = 0;
    x.red_par = 0;
    double *cursor = smem;
@@ -1124,12 +1430,12 @@ pimc_steps_kernel(const __grid_constant__ Params p, long t0, long nsteps, int *e
    if (piped) {
       cursor += (size_t)nown * 3;
       for (int i = x.tid; i < nown * 6; i += blockDim.x) {
-         const int q = (i / 6) * p.cpc + x.crank;
+         const int q = owned_slice(p, x, i / 6);
          if (q < p.Q) x.rrng[i] = stream_ptr(p, x.c, p.P + q)[i % 6];
       }
       x.slot = reinterpret_cast<RotSlot *>(cursor);                  // one slot per owned slice
       for (int ls = x.tid; ls < nown; ls += blockDim.x) {
-         const int q = ls * p.cpc + x.crank;
+         const int q = owned_slice(p, x, ls);
          if (q >= p.Q) continue;
          RotSlot *sl = x.slot + ls;
          const double phi = p.ang[ang_index(p, x.c, q, 0, 0)], cost = p.ang[ang_index(p, x.c, q, 1, 0)], chi = p.ang[ang_index(p, x.c, q, 2, 0)];
@@ -1161,7 +1467,37 @@ pimc_steps_kernel(const __grid_constant__ Params p, long t0, long nsteps, int *e
       tmod[type] = time % tnseg[type];
       toff[type] = time / tnseg[type];
    }
+   const bool use_run = ((KIND & 7) == 1) && piped && p.rot_run;
    for (long s = 0; s < nsteps; s++) {
+      if (use_run) {
+         // translational sweeps of this step, then every rotational sweep up to the next translational one in a single
+         // free-running stretch (rot_run): the rotor is the last species, so its sweep closes the step
+         for (int type = 0; type < p.ntypes; type++) {
+            if (time == 0) molecular_sweep<KIND>(p, x, type);
+            if (tmod[type] == 0) {
+               if (p.bis_piped && x.W == 2 && p.numb[type] > 1 && fast_atoms<KIND>(p, type)) bisection_sweep_piped<KIND>(p, x, type, toff[type]);
+               else bisection_sweep<KIND>(p, x, type, toff[type]);
+            }
+         }
+         int nrun = 1;
+         for (;;) {
+            if (s + nrun >= nsteps) break;
+            bool tr = false;
+            for (int type = 0; type < p.ntypes; type++) tr |= ((time + nrun) % tnseg[type]) == 0;     // includes time + nrun == P
+            if (tr) break;
+            nrun++;
+         }
+         rot_run<KIND>(p, x, p.imtype, nrun, err);
+         for (int k = 0; k < nrun; k++) {
+            if (++time == p.P) time = 0;
+            for (int type = 0; type < p.ntypes; type++) {
+               if (time == 0) { tmod[type] = 0; toff[type] = 0; }
+               else if (++tmod[type] == tnseg[type]) { tmod[type] = 0; toff[type]++; }
+            }
+         }
+         s += nrun - 1;
+         continue;
+      }
       // does the NEXT step start with a translational sweep?  (decided before this step's rotational sweep runs ahead)
       bool next_trans = false;
       for (int type = 0; type < p.ntypes; type++) next_trans |= (tmod[type] + 1 == tnseg[type]) || (time + 1 == p.P) || p.worm_on;
@@ -1174,7 +1510,10 @@ pimc_steps_kernel(const __grid_constant__ Params p, long t0, long nsteps, int *e
             closed = p.wstate[(size_t)x.c * 8] == 0;
          }
          if (time == 0 && closed) molecular_sweep<KIND>(p, x, type);
-         if (tmod[type] == 0 && closed) bisection_sweep<KIND>(p, x, type, toff[type]);
+         if (tmod[type] == 0 && closed) {
+            if (!(KIND & 4) && p.bis_piped && x.W == 2 && p.numb[type] > 1 && fast_atoms<KIND>(p, type)) bisection_sweep_piped<KIND>(p, x, type, toff[type]);
+            else bisection_sweep<KIND>(p, x, type, toff[type]);
+         }
          if ((KIND & 3) != 0 && type == p.imtype && p.Q > 0) {
             if (piped) {
                rot_sweep_pipe<KIND>(p, x, type, err);
@@ -1192,11 +1531,11 @@ pimc_steps_kernel(const __grid_constant__ Params p, long t0, long nsteps, int *e
    if (piped) {
       __syncthreads();
       for (int i = x.tid; i < nown * 6; i += blockDim.x) {
-         const int q = (i / 6) * p.cpc + x.crank;
+         const int q = owned_slice(p, x, i / 6);
          if (q < p.Q) stream_ptr(p, x.c, p.P + q)[i % 6] = x.rrng[i];
       }
       for (int ls = x.tid; ls < nown; ls += blockDim.x) {
-         const int q = ls * p.cpc + x.crank;
+         const int q = owned_slice(p, x, ls);
          if (q >= p.Q) continue;
          p.vold[((size_t)x.c * p.Q + q) * p.NMpad] = x.slot[ls].vcache;
          p.vepoch[((size_t)x.c * p.Q + q) * p.NMpad] = x.slot[ls].vep;

@@ -413,7 +413,9 @@ int pimcgpu_init(const pimcgpu_system *sys, const pimcgpu_tables *tab)
          for (int i = 0; i < cs; i++) cgi[i] = make_double2(tab->cgrid2d[i], ic[i]);
          // whole-cell copy for the cached rotational sums: the four corners of cell (ir, ic) as ONE aligned 32-byte record
          // {V[ir][ic], V[ir+1][ic], V[ir][ic+1], V[ir+1][ic+1]} -- a single 256-bit gather per evaluation
-         {
+         p.cell4_on = getenv("PIMC_CELL4") ? atoi(getenv("PIMC_CELL4")) : 1;          // measured on C5: 15.6 us per rotational sweep against 16.8 us with the row-pair table
+         p.cell_hint = getenv("PIMC_CELL_HINT") ? atoi(getenv("PIMC_CELL_HINT")) : 0;
+         if (p.cell4_on) {
             std::vector<double> c4((size_t)(rs - 1) * (cs - 1) * 4);
             for (int i = 0; i < rs - 1; i++)
                for (int j = 0; j < cs - 1; j++) {
@@ -556,12 +558,21 @@ int pimcgpu_init(const pimcgpu_system *sys, const pimcgpu_tables *tab)
    if (smem_bytes(p, threads) > 200 * 1024) p.rot_in_smem = 0;
    if (p.segbuf_global && dalloc(&p.segbuf, C * p.nseg_max * p.team_buf_n)) return 1;
    if (dalloc(&p.barrier, C * 32)) return 1;
+   p.bis_piped = (!p.segbuf_global && !getenv("PIMC_NO_BIS_PIPE")) ? 1 : 0;
+   // free-running rotational sweeps (rot_run): one linear rotor listed as the last species, several CTAs per chain, every CTA a
+   // contiguous block of slices with one rot group per slice
+   p.rot_run = 0;
+   if (p.rot_fused && cpc > 1 && p.imtype == p.ntypes - 1 && p.molecule[p.imtype] == 1 && !p.worm_on && p.Q % cpc == 0 && p.Q / cpc <= threads / p.rot_group &&
+       p.Q / cpc >= 2 && !getenv("PIMC_NO_ROT_RUN")) {
+      if (dalloc(&p.rot_flags, C * p.Q)) return 1;
+      p.rot_run = 1;
+   }
    // geometry cache of the rotor-atom terms (rot_potential_cached): one linear rotor among atoms, pipelined sweep, no worm
    p.geo_on = 0;
-   if (p.rot_fused && p.imtype >= 0 && p.molecule[p.imtype] == 1 && !p.worm_on && !p.minimage && p.N > 1 && p.rs2d > 0 && !getenv("PIMC_NO_GEO")) {
+   if (p.rot_fused && p.imtype >= 0 && p.molecule[p.imtype] == 1 && !p.worm_on && !p.minimage && p.N > 1 && p.rs2d > 0 && p.rs2d < 4096 && !getenv("PIMC_NO_GEO")) {
       p.geo_items = p.R * (p.N - 1);
       p.geo_n = (p.geo_items + 31) / 32 * 32;
-      if (dalloc(&p.geo, C * p.Q * 4 * p.geo_n) || dalloc(&p.geo_i, C * p.Q * p.geo_n)) return 1;
+      if (dalloc(&p.geo, C * p.Q * 4 * p.geo_n)) return 1;
       p.geo_on = 1;
    }
    G.smem = smem_bytes(p, threads);
@@ -948,6 +959,7 @@ int pimcgpu_steps(long nsteps)
    cudaLaunchAttribute attr[1];
    launch_config(cfg, attr);
    if (G.p.cpc > 1) CK(cudaMemsetAsync(G.p.barrier, 0, (size_t)G.p.nchains * 32 * sizeof(unsigned), G.stream));
+   if (G.p.rot_run) CK(cudaMemsetAsync(G.p.rot_flags, 0, (size_t)G.p.nchains * G.p.Q * sizeof(int), G.stream));
    void *args[4] = {(void *)&G.p, (void *)&G.step, (void *)&nsteps, (void *)&G.d_err};
    CK(cudaLaunchKernelExC(&cfg, steps_kernel(G.kind, G.p.worm_on), args));
    G.step += nsteps;

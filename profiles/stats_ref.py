@@ -21,7 +21,7 @@ sys.path.insert(0, ROOT)
 CASES = {
     "top_He_C1_P64_Q16_1K": ("C1", dict(P=64, Q=16, temperature=1.0), 64, 25600, 16, 3000),
     "tip4p_C4_P64_Q32": ("C4", dict(P=64, Q=32), 64, 25600, 16, 3000),
-    "lin_C5_P64_Q16_6H2_2K": ("C5", dict(P=64, Q=16, nsolv=6, temperature=2.0), 64, 25600, 16, 3000),
+    "lin_C5_P64_Q16_6H2_2K": ("C5", dict(P=64, Q=16, nsolv=6, temperature=2.0), 128, 25600, 16, 3000),
 }
 
 
