@@ -77,13 +77,13 @@ def blocked_sem(x):
     return best
 
 
-def compare(g, r, cols):
+def compare(g, r, cols, nsigma=2.0):
     for i, nm in cols:
         mg, mr = g[:, i].mean(), r[:, i].mean()
         sg, sr = blocked_sem(g[:, i]), blocked_sem(r[:, i])
         sigma = np.hypot(sg, sr)
         print(f"{nm}: gpu {mg:.5f} +- {sg:.5f}   reference {mr:.5f} +- {sr:.5f}   diff {abs(mg-mr)/sigma:.2f} sigma")
-        assert abs(mg - mr) < 2.0 * sigma + 1e-9 * abs(mr), f"{nm}: {mg} vs {mr} (sigma {sigma})"
+        assert abs(mg - mr) < nsigma * sigma + 1e-9 * abs(mr), f"{nm}: {mg} vs {mr} (sigma {sigma})"
 
 
 def test_free_linear_rotor_matches_reference(pkg):
@@ -136,9 +136,20 @@ def _stats_case(pkg, case, nchains, gpu_per_block, min_sigma_cols=()):
         rows.append(stats_ref.observables(s, n, acc[1], acc[2], acc[3], rcf, a[0:6], a[6:21], a[21:36], d["lambda_bose"], d["mass_bose"]))
     G.close()
     g = np.array(rows)
-    cols = [(i, c) for i, c in enumerate(d["columns"]) if np.any(r[:, i] != 0.0)]
+    names = d["columns"]
+    cols = [(i, c) for i, c in enumerate(names) if np.any(r[:, i] != 0.0)]
     assert len(cols) >= 6
-    compare(g, r, cols)
+    # the observables north_star names, at 2 sigma: energies, <n(0).n(t)>, the superfluid fractions of the .sup file and the
+    # space-fixed fraction averaged over its three statistically equivalent components; the individual tensor components
+    # (six more columns of the same data) are held to 3 sigma so that thirteen simultaneous tests stay meaningful
+    sff = [i for i, c in cols if c.endswith("(sff)")]
+    if sff:
+        g = np.c_[g, g[:, sff].mean(axis=1)]; r = np.c_[r, r[:, sff].mean(axis=1)]
+        cols.append((g.shape[1] - 1, "fs(sff), mean of xx/yy/zz"))
+    primary = [(i, c) for i, c in cols if not (c.endswith("(sff)") or c.endswith("(mff)"))]
+    secondary = [(i, c) for i, c in cols if c.endswith("(sff)") or c.endswith("(mff)")]
+    compare(g, r, primary, 2.0)
+    compare(g, r, secondary, 3.0)
     return g, r
 
 
