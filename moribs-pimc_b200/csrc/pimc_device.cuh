@@ -58,7 +58,8 @@ struct Params {
    const double2 *cell2d;        // [(rs-1)][cs] row pairs {V[ir][ic], V[ir+1][ic]}: a bilinear cell is two adjacent 16-byte
                                  // entries (32 contiguous bytes, 2x the table instead of 4x so the hot region stays in L2)
    const double2 *rgi2d, *cgi2d; // {grid[i], 1/(grid[i+1]-grid[i])} of the two axes
-   int cell4_on, cell_hint;      // whole-cell table in use (else the row-pair table); L2 eviction-priority hints on the gathers
+   int cell4_on, cell_hint;      // whole-cell table in use (else the row-pair table); the random gathers do not allocate in L1 (they never hit
+                                 // there and displace the lines the other loads reuse)
    const double *cell4;          // [(rs-1)][(cs-1)][4] whole cells {V[ir][ic], V[ir+1][ic], V[ir][ic+1], V[ir+1][ic+1]}, 32-byte aligned
    int rg3, thg3, chg3; const double *v3d; double rvmin, rvmax, rvstep;
    int nrot, nlutrot; const double *rgrid, *rdens, *rderv, *resqr, *rdens2, *rderv2, *resqr2; const int *lutrot; double lutrot_scale;
@@ -312,7 +313,7 @@ __device__ __forceinline__ void load_cell4(const double *cell, double &y1, doubl
 }
 __device__ __forceinline__ void load_cell4_keep(const double *cell, double &y1, double &y2, double &y3, double &y4)
 {
-   asm("ld.global.nc.L2::evict_last.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(y1), "=d"(y2), "=d"(y4), "=d"(y3) : "l"(cell));
+   asm("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(y1), "=d"(y2), "=d"(y4), "=d"(y3) : "l"(cell));
 }
 // one geometry record: streamed once per rotational sweep, must not displace the table in L2
 __device__ __forceinline__ void load_geo4(const double *rec, double &ux, double &uy, double &uz, double &w)

@@ -560,18 +560,37 @@ __device__ void bisection_sweep_piped(const Params &p, Ctx &x, int type, int off
             }
             __syncwarp();
          }
-         for (int level = 0; level < L; level++) {
-            const int lss = seg >> level, half = lss >> 1, nmid = 1 << level;
-            double D = 0.0;
-            for (int i = lane; i < nmid * nother; i += 32) {          // partners of the other species (the rotor)
-               const int m = i / nother, jo = i - m * nother;
+         // partners of the other species (the rotor): every (midpoint of any level, partner) term in ONE pass, a lane per term;
+         // midpoint index gm = 2^level - 1 + m enumerates the levels in order
+         double eo = 0.0;
+         int eo_level = -1;
+         if ((seg - 1) * nother <= 32) {
+            if (lane < (seg - 1) * nother) {
+               const int gm = lane / nother, jo = lane - gm * nother;
+               const int level = 31 - __clz(gm + 1), m = gm + 1 - (1 << level);
+               const int lss = seg >> level, half = lss >> 1;
                const int j = (jo < base) ? jo : jo + na;
                const int t1 = half + m * lss, sl = (s0 + t1) % P, g = (s0 + t1 >= P) ? gB : gA;
                double po[3], pn[3];
                #pragma unroll
                for (int d = 0; d < 3; d++) { po[d] = p.pos[pos_index(p, c, sl, d, g)]; pn[d] = nx[t1 * 3 + d]; }
-               D += pair_diff<KIND>(p, x.t, c, g, pn, po, j, sl);
+               eo = pair_diff<KIND>(p, x.t, c, g, pn, po, j, sl);
+               eo_level = level;
             }
+         }
+         for (int level = 0; level < L; level++) {
+            const int lss = seg >> level, half = lss >> 1, nmid = 1 << level;
+            double D = (eo_level == level) ? eo : 0.0;
+            if ((seg - 1) * nother > 32)
+               for (int i = lane; i < nmid * nother; i += 32) {       // many terms: level by level
+                  const int m = i / nother, jo = i - m * nother;
+                  const int j = (jo < base) ? jo : jo + na;
+                  const int t1 = half + m * lss, sl = (s0 + t1) % P, g = (s0 + t1 >= P) ? gB : gA;
+                  double po[3], pn[3];
+                  #pragma unroll
+                  for (int d = 0; d < 3; d++) { po[d] = p.pos[pos_index(p, c, sl, d, g)]; pn[d] = nx[t1 * 3 + d]; }
+                  D += pair_diff<KIND>(p, x.t, c, g, pn, po, j, sl);
+               }
             for (int m = 0; m < nmid; m++) {
                const int t1 = half + m * lss, sl = (s0 + t1) % P;
                const bool wrap = s0 + t1 >= P;
@@ -592,25 +611,30 @@ __device__ void bisection_sweep_piped(const Params &p, Ctx &x, int type, int off
          int used = 0;
          Mrg as;
          if (lane == 0) mrg_load(as, rc);
+         // the term of atom a-1 for every midpoint of every level in one pass (a lane per midpoint), summed per level
+         if (a > 0) {
+            for (int gm = lane; gm < seg - 1; gm += 32) {
+               const int level = 31 - __clz(gm + 1), m = gm + 1 - (1 << level);
+               const int lss = seg >> level, half = lss >> 1;
+               const int t1 = half + m * lss, sl = (s0 + t1) % P;
+               const bool wrap = s0 + t1 >= P;
+               const int g = wrap ? gB : gA, j = wrap ? hB : hA;
+               double d2n = 0.0, d2o = 0.0;
+               #pragma unroll
+               for (int d = 0; d < 3; d++) {
+                  const double pj = __ldcg(p.pos + pos_index(p, c, sl, d, j)), pg = p.pos[pos_index(p, c, sl, d, g)], pn = nx[t1 * 3 + d];
+                  d2n += (pn - pj) * (pn - pj);
+                  d2o += (pg - pj) * (pg - pj);
+               }
+               xi[(gm + 1) * 3] = spot1d_move(p, x.t, sqrt(d2n)) - spot1d_move(p, x.t, sqrt(d2o));     // the normals are spent: reuse their slots
+            }
+            __syncwarp();
+         }
          for (int level = 0; level < L && alive; level++) {
-            const int lss = seg >> level, half = lss >> 1, nmid = 1 << level;
+            const int half = seg >> (level + 1), nmid = 1 << level;
             double e = 0.0;
             if (a > 0)
-               for (int m = lane; m < nmid; m += 32) {
-                  const int t1 = half + m * lss, sl = (s0 + t1) % P;
-                  const bool wrap = s0 + t1 >= P;
-                  const int g = wrap ? gB : gA, j = wrap ? hB : hA;
-                  double d2n = 0.0, d2o = 0.0;
-                  #pragma unroll
-                  for (int d = 0; d < 3; d++) {
-                     const double pj = __ldcg(p.pos + pos_index(p, c, sl, d, j)), pg = p.pos[pos_index(p, c, sl, d, g)], pn = nx[t1 * 3 + d];
-                     d2n += (pn - pj) * (pn - pj);
-                     d2o += (pg - pj) * (pg - pj);
-                  }
-                  e += spot1d_move(p, x.t, sqrt(d2n)) - spot1d_move(p, x.t, sqrt(d2o));
-               }
-            if (a > 0 && nmid > 1) e = team_sum(e, 32);
-            else e = __shfl_sync(0xffffffffu, e, 0);
+               for (int m = 0; m < nmid; m++) e += xi[(nmid + m) * 3];          // gm + 1 = 2^level + m, fixed order
             const double D = dsum[level] + e;
             const double deltav = (D - S) * (p.tau * (double)half);
             S += D;
@@ -763,34 +787,37 @@ __device__ __forceinline__ void geo_fill(const Params &p, Ctx &x, int g, int q)
    }
 }
 
-// four cached items against one orientation n: cos(theta) = n.u, angular cell, the four cell gathers, the bilinear forms
-__device__ __forceinline__ double geo_eval4(const Params &p, const SmallTables &t, double cmin, double n0, double n1, double n2,
+// NB cached items against one orientation n: cos(theta) = n.u, angular cell, the NB cell gathers, the bilinear forms
+#ifndef PIMC_GEO_BATCH
+#define PIMC_GEO_BATCH 7
+#endif
+template <int NB>
+__device__ __forceinline__ double geo_evaln(const Params &p, const SmallTables &t, double cmin, double n0, double n1, double n2,
                                             const double *ux, const double *uy, const double *uz, const double *dr, const int *ib, const bool *ok)
 {
-   double cs[4];
-   int ic[4];
+   double cs[NB];
+   int ic[NB];
    #pragma unroll
-   for (int u = 0; u < 4; u++) {
+   for (int u = 0; u < NB; u++) {
       cs[u] = n0 * ux[u] + n1 * uy[u] + n2 * uz[u];
       ic[u] = lpot_index(cs[u] - cmin, p.inv_dc2d, p.dc2d, p.cs2d);            // LPot2D angular cell, mc_poten.cc:702-704
    }
-   double y1[4], y2[4], y3[4], y4[4];
-   #pragma unroll
+   double y1[NB], y2[NB], y3[NB], y4[NB];
    if (p.cell4_on) {
       if (p.cell_hint) {
          #pragma unroll
-         for (int u = 0; u < 4; u++) load_cell4_keep(p.cell4 + 4 * (size_t)(ib[u] + ic[u]), y1[u], y2[u], y3[u], y4[u]);
+         for (int u = 0; u < NB; u++) load_cell4_keep(p.cell4 + 4 * (size_t)(ib[u] + ic[u]), y1[u], y2[u], y3[u], y4[u]);
       } else {
          #pragma unroll
-         for (int u = 0; u < 4; u++) load_cell4(p.cell4 + 4 * (size_t)(ib[u] + ic[u]), y1[u], y2[u], y3[u], y4[u]);
+         for (int u = 0; u < NB; u++) load_cell4(p.cell4 + 4 * (size_t)(ib[u] + ic[u]), y1[u], y2[u], y3[u], y4[u]);
       }
    } else {
       #pragma unroll
-      for (int u = 0; u < 4; u++) load_cell(p.cell2d + (size_t)(ib[u] + ic[u]), y1[u], y2[u], y3[u], y4[u]);
+      for (int u = 0; u < NB; u++) load_cell(p.cell2d + (size_t)(ib[u] + ic[u]), y1[u], y2[u], y3[u], y4[u]);
    }
    double v = 0.0;
    #pragma unroll
-   for (int u = 0; u < 4; u++) {
+   for (int u = 0; u < NB; u++) {
       const double2 gc = lds_d2(t.s_cgi2d, ic[u]);
       const double dc = (cs[u] - gc.x) * gc.y;
       const double lo = y1[u] + dr[u] * (y2[u] - y1[u]);         // V at cos(theta)_ic, interpolated in r
@@ -802,10 +829,13 @@ __device__ __forceinline__ double geo_eval4(const Params &p, const SmallTables &
 }
 
 // sum over the cached items of rot slice q of LPot2D(r, cos(theta) = n.u) for ONE orientation (NO = 1) or for the
-// proposed and the current orientation (NO = 2: the geometry loads are shared).  Four items per lane in flight.
+// proposed and the current orientation (NO = 2: the geometry loads are shared).  PIMC_GEO_BATCH items per lane in flight:
+// the sums of a slice are two dependent memory round trips per batch, so fewer, larger batches shorten the critical
+// path of the slice (12.5 items per lane on C5: two batches of 7).
 template <int NO>
 __device__ __forceinline__ void rot_potential_cached(const Params &p, Ctx &x, int q, const double *o0, const double *o1, double *vout)
 {
+   constexpr int NB = (NO == 1) ? PIMC_GEO_BATCH : 4;
    const int c = x.c, G = x.G, n = p.geo_items, gn = p.geo_n;
    const double *gb = p.geo + ((size_t)c * p.Q + q) * 4 * gn;
    const int rowlen = p.cell4_on ? p.cs2d - 1 : p.cs2d;
@@ -814,25 +844,25 @@ __device__ __forceinline__ void rot_potential_cached(const Params &p, Ctx &x, in
    double b0 = 0.0, b1 = 0.0, b2 = 0.0;
    if (NO == 2) { b0 = o1[0]; b1 = o1[1]; b2 = o1[2]; }
    double v0 = 0.0, v1 = 0.0;
-   for (int k0 = x.gl; k0 < n; k0 += 4 * G) {
-      double ux[4], uy[4], uz[4], dr[4];
-      int ib[4];
-      bool ok[4];
+   for (int k0 = x.gl; k0 < n; k0 += NB * G) {
+      double ux[NB], uy[NB], uz[NB], dr[NB];
+      int ib[NB];
+      bool ok[NB];
       #pragma unroll
-      for (int u = 0; u < 4; u++) {
+      for (int u = 0; u < NB; u++) {
          const int k = k0 + u * G;
          ok[u] = k < n;
          const int kk = ok[u] ? k : k0;                 // masked slots repeat the first item of the batch (a valid look-up)
          load_geo4(gb + 4 * (size_t)kk, ux[u], uy[u], uz[u], dr[u]);
       }
       #pragma unroll
-      for (int u = 0; u < 4; u++) {
+      for (int u = 0; u < NB; u++) {
          const long long bits = __double_as_longlong(dr[u]);
-         ib[u] = (int)(bits & 0xfffLL) * rowlen;        // row offset of the radial cell in the whole-cell table
+         ib[u] = (int)(bits & 0xfffLL) * rowlen;        // row offset of the radial cell in the table
          dr[u] = __longlong_as_double(bits & ~0xfffLL);
       }
-      v0 += geo_eval4(p, x.t, cmin, a0, a1, a2, ux, uy, uz, dr, ib, ok);
-      if (NO == 2) v1 += geo_eval4(p, x.t, cmin, b0, b1, b2, ux, uy, uz, dr, ib, ok);
+      v0 += geo_evaln<NB>(p, x.t, cmin, a0, a1, a2, ux, uy, uz, dr, ib, ok);
+      if (NO == 2) v1 += geo_evaln<NB>(p, x.t, cmin, b0, b1, b2, ux, uy, uz, dr, ib, ok);
    }
    vout[0] = v0;
    if (NO == 2) vout[1] = v1;
