@@ -94,6 +94,7 @@ struct Params {
    // radial cell row and its radial weight; a rotational proposal only changes cos(theta) = n.u
    int rot_run;                  // linear rotor, several CTAs per chain: free-running rotational sweeps (rot_run), contiguous slice blocks per CTA
    int *rot_flags;               // [c][Q] decisions made by every rot slice in this launch (zeroed before every launch)
+   int mol_piped;                // whole-path sweep with one cross-CTA hand-over per atom (molecular_sweep_piped)
    int bis_piped;                // two-warp teams: bisection sweep software-pipelined over the atoms (bisection_sweep_piped)
    int geo_on, geo_items, geo_n; // enabled; real items per rot slice = R x (N - 1); padded stride
    double *geo;                  // [c][q][geo_n][4]: one aligned 32-byte record {ux, uy, uz, w} per item; w = the radial weight dr with

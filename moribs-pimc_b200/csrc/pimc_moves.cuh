@@ -74,6 +74,7 @@ struct Ctx {
    unsigned bar_target;
    int red_par;
    int rot_iter;       // pipelined rotational sweeps done in this launch
+   unsigned mol_target[2];   // arrivals expected on the two whole-path hand-over counters (molecular_sweep_piped)
 };
 
 // doubles of scratch per bisection team (host and device use the same formula)
@@ -302,6 +303,110 @@ __device__ void molecular_sweep(const Params &p, Ctx &x, int type)
       }
       chain_sync(p, x);
    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The whole-path sweep of an atomic species without exchange cycles, one cross-CTA hand-over per atom instead of two
+// chain barriers.  Every warp of the chain owns a fixed set of slices for the whole sweep: the pair action is diagonal
+// in imaginary time, so a warp only ever reads and shifts beads of its own slices -- positions need no synchronisation
+// at all.  What couples the chain is the scalar dV of an atom: every CTA publishes its partial sum (release) and every
+// CTA waits for all partials (acquire), adds them in CTA order and takes the same decision from the same uniform.
+// The sum of atom a+1 without its partner a is formed BEFORE the wait for atom a; the one missing pair term per slice
+// follows the decision.  Draws (4 per atom from the chain's miscellaneous stream) and acceptance as in molecular_sweep.
+// ---------------------------------------------------------------------------------------------
+template <int KIND>
+__device__ double molecular_partial(const Params &p, Ctx &x, int type, int a0, const double *disp, int jx)
+{
+   const int c = x.c, P = p.P, N = p.N, base = p.first[type], na = p.numb[type], nother = N - na;
+   const int nwc = blockDim.x >> 5, gwarp = x.crank * nwc + (x.tid >> 5), nwarps = p.cpc * nwc, lane = x.tid & 31;
+   double part = 0.0;
+   for (int it = gwarp; it < P; it += nwarps) {
+      double po[3], pn[3];
+      #pragma unroll
+      for (int d = 0; d < 3; d++) { po[d] = p.pos[pos_index(p, c, it, d, a0)]; pn[d] = po[d] + disp[d]; }
+      part += partner_sum_diff<KIND>(p, x.t, c, a0, pn, po, it, lane, 32, jx);
+      for (int jo = lane; jo < nother; jo += 32) {
+         const int j = (jo < base) ? jo : jo + na;
+         part += pair_diff<KIND>(p, x.t, c, a0, pn, po, j, it);
+      }
+   }
+   return part;
+}
+
+template <int KIND>
+__device__ void molecular_sweep_piped(const Params &p, Ctx &x, int type)
+{
+   const int c = x.c, P = p.P, base = p.first[type], na = p.numb[type];
+   const int nwc = blockDim.x >> 5, warp = x.tid >> 5, gwarp = x.crank * nwc + warp, nwarps = p.cpc * nwc, lane = x.tid & 31;
+   uint32_t *ms = stream_ptr(p, c, P + p.Q);
+   double *slots = p.scratch + (size_t)c * 64;                      // [parity of the atom][CTA]
+   unsigned *cnt = p.barrier + (size_t)c * 32 + 24;                 // [parity] arrivals, monotonic within a launch
+   __shared__ int s_acc;
+   bump_pos_epoch(p, x);
+   Mrg rs;
+   mrg_load(rs, ms);
+   const double step = p.mcstep[type];
+   double disp[3], u3, dnext[3], u3next = 0.0;
+   { const double u0 = mrg_u01(rs), u1 = mrg_u01(rs), u2 = mrg_u01(rs); u3 = mrg_u01(rs); disp[0] = step * (u0 - 0.5); disp[1] = step * (u1 - 0.5); disp[2] = step * (u2 - 0.5); }
+   double part = molecular_partial<KIND>(p, x, type, base, disp, -1);
+   for (int a = 0; a < na; a++) {
+      const int par = a & 1;
+      // CTA total of atom a in warp order, published for the other CTAs
+      part = team_sum(part, 32);
+      if (lane == 0) x.red[warp] = part;
+      __syncthreads();
+      if (x.tid == 0) {
+         double sct = 0.0;
+         for (int w = 0; w < nwc; w++) sct += x.red[w];
+         slots[par * 32 + x.crank] = sct;
+         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(cnt + par) : "memory");
+      }
+      // meanwhile: the sum of atom a+1 without its partner a
+      double pre = 0.0;
+      if (a + 1 < na) {
+         const double u0 = mrg_u01(rs), u1 = mrg_u01(rs), u2 = mrg_u01(rs); u3next = mrg_u01(rs);
+         dnext[0] = step * (u0 - 0.5); dnext[1] = step * (u1 - 0.5); dnext[2] = step * (u2 - 0.5);
+         pre = molecular_partial<KIND>(p, x, type, base + a + 1, dnext, base + a);
+      }
+      // every partial of atom a, the decision
+      if (x.tid == 0) {
+         x.mol_target[par] += (unsigned)p.cpc;
+         unsigned v;
+         do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(cnt + par) : "memory"); } while ((int)(v - x.mol_target[par]) < 0);
+         double dv = 0.0;
+         for (int r = 0; r < p.cpc; r++) dv += __ldcg(slots + par * 32 + r);
+         s_acc = ((dv < 0.0) || (exp(-dv * p.tau) > u3)) ? 1 : 0;
+      }
+      __syncthreads();
+      const bool acc = s_acc != 0;
+      if (acc && lane < 3)
+         for (int it = gwarp; it < P; it += nwarps) p.pos[pos_index(p, c, it, lane, base + a)] += disp[lane];
+      if (x.gthread == 0) {
+         double *cn = counter_ptr(p, c, type, 0);
+         cn[0] += 1.0;
+         if (acc) cn[1] += 1.0;
+      }
+      __syncwarp();
+      // the missing partner term of atom a+1, slice by slice (a lane per owned slice)
+      part = pre;
+      if (a + 1 < na) {
+         int k = 0;
+         for (int it = gwarp; it < P; it += nwarps, k++) {
+            if ((k & 31) != lane) continue;
+            double d2n = 0.0, d2o = 0.0;
+            #pragma unroll
+            for (int d = 0; d < 3; d++) {
+               const double pj = p.pos[pos_index(p, c, it, d, base + a)], po = p.pos[pos_index(p, c, it, d, base + a + 1)], pn = po + dnext[d];
+               d2n += (pn - pj) * (pn - pj);
+               d2o += (po - pj) * (po - pj);
+            }
+            part += spot1d_move(p, x.t, sqrt(d2n)) - spot1d_move(p, x.t, sqrt(d2o));
+         }
+         disp[0] = dnext[0]; disp[1] = dnext[1]; disp[2] = dnext[2]; u3 = u3next;
+      }
+   }
+   if (x.gthread == 0) mrg_store(rs, ms);
+   chain_sync(p, x);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1446,6 +1551,7 @@ pimc_steps_kernel(const __grid_constant__ Params p, long t0, long nsteps, int *e
    x.gmask = x.G >= 32 ? 0xffffffffu : (((1u << x.G) - 1u) << ((x.tid & 31) & ~(x.G - 1)));
    x.bar_target = 0;
    x.red_par = 0;
+   x.mol_target[0] = x.mol_target[1] = 0;
    double *cursor = smem;
    x.red = cursor; cursor += 40;
    stage_tables(p, x.t, cursor);
@@ -1503,7 +1609,10 @@ pimc_steps_kernel(const __grid_constant__ Params p, long t0, long nsteps, int *e
          // translational sweeps of this step, then every rotational sweep up to the next translational one in a single
          // free-running stretch (rot_run): the rotor is the last species, so its sweep closes the step
          for (int type = 0; type < p.ntypes; type++) {
-            if (time == 0) molecular_sweep<KIND>(p, x, type);
+            if (time == 0) {
+               if (p.mol_piped && p.numb[type] > 1 && fast_atoms<KIND>(p, type) && p.ncyc[x.c * MAXT + type] == p.numb[type]) molecular_sweep_piped<KIND>(p, x, type);
+               else molecular_sweep<KIND>(p, x, type);
+            }
             if (tmod[type] == 0) {
                if (p.bis_piped && x.W == 2 && p.numb[type] > 1 && fast_atoms<KIND>(p, type)) bisection_sweep_piped<KIND>(p, x, type, toff[type]);
                else bisection_sweep<KIND>(p, x, type, toff[type]);
@@ -1539,7 +1648,10 @@ pimc_steps_kernel(const __grid_constant__ Params p, long t0, long nsteps, int *e
             chain_sync(p, x);
             closed = p.wstate[(size_t)x.c * 8] == 0;
          }
-         if (time == 0 && closed) molecular_sweep<KIND>(p, x, type);
+         if (time == 0 && closed) {
+            if (!(KIND & 4) && p.mol_piped && p.numb[type] > 1 && fast_atoms<KIND>(p, type) && p.ncyc[x.c * MAXT + type] == p.numb[type]) molecular_sweep_piped<KIND>(p, x, type);
+            else molecular_sweep<KIND>(p, x, type);
+         }
          if (tmod[type] == 0 && closed) {
             if (!(KIND & 4) && p.bis_piped && x.W == 2 && p.numb[type] > 1 && fast_atoms<KIND>(p, type)) bisection_sweep_piped<KIND>(p, x, type, toff[type]);
             else bisection_sweep<KIND>(p, x, type, toff[type]);

@@ -559,6 +559,7 @@ int pimcgpu_init(const pimcgpu_system *sys, const pimcgpu_tables *tab)
    if (p.segbuf_global && dalloc(&p.segbuf, C * p.nseg_max * p.team_buf_n)) return 1;
    if (dalloc(&p.barrier, C * 32)) return 1;
    p.bis_piped = (!p.segbuf_global && !getenv("PIMC_NO_BIS_PIPE")) ? 1 : 0;
+   p.mol_piped = getenv("PIMC_NO_MOL_PIPE") ? 0 : 1;
    // free-running rotational sweeps (rot_run): one linear rotor listed as the last species, several CTAs per chain, every CTA a
    // contiguous block of slices with one rot group per slice
    p.rot_run = 0;
@@ -958,7 +959,7 @@ int pimcgpu_steps(long nsteps)
    cudaLaunchConfig_t cfg;
    cudaLaunchAttribute attr[1];
    launch_config(cfg, attr);
-   if (G.p.cpc > 1) CK(cudaMemsetAsync(G.p.barrier, 0, (size_t)G.p.nchains * 32 * sizeof(unsigned), G.stream));
+   CK(cudaMemsetAsync(G.p.barrier, 0, (size_t)G.p.nchains * 32 * sizeof(unsigned), G.stream));
    if (G.p.rot_run) CK(cudaMemsetAsync(G.p.rot_flags, 0, (size_t)G.p.nchains * G.p.Q * sizeof(int), G.stream));
    void *args[4] = {(void *)&G.p, (void *)&G.step, (void *)&nsteps, (void *)&G.d_err};
    CK(cudaLaunchKernelExC(&cfg, steps_kernel(G.kind, G.p.worm_on), args));
