@@ -337,6 +337,10 @@ int pimcgpu_init(const pimcgpu_system *sys, const pimcgpu_tables *tab)
    }
    for (int d = 0; d < 3; d++) p.box[d] = sys->box[d];
    if (p.ispher && p.Q > 0) return fail("pimcgpu_init: ISPHER = 1 is not compatible with ROTATION");
+   // PotRotEnergy aborts on "MIN IMAGE for orient pot" (mc_piqmc.cc:2012): the rotational moves of a linear rotor have no
+   // minimum-image form, so the combination is refused here instead of sampling two different Hamiltonians
+   if (p.minimage && p.Q > 0 && p.imtype >= 0 && p.molecule[p.imtype] == 1 && p.N > 1)
+      return fail("pimcgpu_init: MINIMAGE with ROTATION of a linear rotor is not implemented (MIN IMAGE for orient pot, mc_piqmc.cc:2012)");
    // interaction branch per (type0, type1), the if-chain of mc_piqmc.cc:1847-1958
    for (int t0 = 0; t0 < sys->ntypes; t0++)
       for (int t1 = 0; t1 < sys->ntypes; t1++) {

@@ -250,6 +250,15 @@ int main(int argc, char **argv)
    sys.device = 0;
 #endif
 
+   // mc_main.cc:129-144: never run over the files of an earlier simulation (permutation.tab always; the checkpoint files unless
+   // this is a RESTART).  _io_error prints "<proc>: <message> <file>" through nrerror.
+   auto file_exists = [](const char *f) { struct stat sb; return stat(f, &sb) == 0; };
+   if (rank == 0) {
+      if (file_exists("permutation.tab")) die("QMC ->", "File already exists: permutation.tab");
+      if (!d.restart)
+         for (const char *f : {"yw001.stat", "yw001.conf", "yw001.rand"})
+            if (file_exists(f)) die("QMC ->", string("File already exists: ") + f);
+   }
    // ---- tables: InitPotentials / InitRotDensity, mc_poten.cc:93-164 ----
    pimcgpu_tables tab;
    memset(&tab, 0, sizeof tab);
@@ -294,7 +303,10 @@ int main(int argc, char **argv)
             cout << "generating " << base << ".rot on the device (linden: B=" << d.xrot << " cm-1, " << npt << " points)" << endl;
             vector<double> t4((size_t)npt * 4);
             ck(pimcgpu_gen_linden(d.temperature, Q, d.xrot, npt, d.rot_odevn, t4.data(), nullptr), "pimcgpu_gen_linden");
-            if (rank == 0) ck(pimcgpu_write_rot((base + ".rot").c_str(), t4.data(), npt), "pimcgpu_write_rot");
+            if (rank == 0) {      // temporary name + rename: a rank that starts later sees either no file or the whole file
+               ck(pimcgpu_write_rot((base + ".rot.tmp").c_str(), t4.data(), npt), "pimcgpu_write_rot");
+               if (rename((base + ".rot.tmp").c_str(), (base + ".rot").c_str()) != 0) die("init_rotdens", "cannot rename " + base + ".rot.tmp");
+            }
             trot.assign(4, vector<double>(npt));
             for (int i = 0; i < npt; i++) for (int k = 0; k < 4; k++) trot[k][i] = strtod(fortran_1p(t4[4 * i + k]).c_str(), nullptr);
          } else
@@ -314,10 +326,11 @@ int main(int argc, char **argv)
             ck(pimcgpu_gen_asymrho(d.temperature, Q, d.rot_odevn, 0, 180, d.xrot, d.zrot, d.yrot, maxj, rho.data(), erot.data(), esq.data(), nullptr), "pimcgpu_gen_asymrho");
             // the run uses the values a later run would read back from the files: 8 significant digits (E15.8)
             round_e15_8(rho); round_e15_8(erot); round_e15_8(esq);
-            if (rank == 0) {
-               ck(pimcgpu_write_e15_8((base + ".rho").c_str(), rho.data(), PIMCGPU_SIZE_ROTDEN, 0), "pimcgpu_write_e15_8");
+            if (rank == 0) {      // .rho last and by rename: its presence is what the other ranks (and later runs) test
                ck(pimcgpu_write_e15_8((base + ".eng").c_str(), erot.data(), PIMCGPU_SIZE_ROTDEN, 0), "pimcgpu_write_e15_8");
                ck(pimcgpu_write_e15_8((base + ".esq").c_str(), esq.data(), PIMCGPU_SIZE_ROTDEN, 0), "pimcgpu_write_e15_8");
+               ck(pimcgpu_write_e15_8((base + ".rho.tmp").c_str(), rho.data(), PIMCGPU_SIZE_ROTDEN, 0), "pimcgpu_write_e15_8");
+               if (rename((base + ".rho.tmp").c_str(), (base + ".rho").c_str()) != 0) die("init_rot3D", "cannot rename " + base + ".rho.tmp");
             }
          } else {
          rho = read_numbers(base + ".rho", PIMCGPU_SIZE_ROTDEN);
@@ -340,7 +353,14 @@ int main(int argc, char **argv)
       if (!f.good()) die("initconf", "Can't open input file  [xyz.init]");
       long ntot; f >> ntot;
       int nb = bstype >= 0 ? d.types[bstype].numb : 0;
-      for (int i = 0; i < nb; i++) { f >> pindex[i]; rindex[pindex[i]] = i; }
+      if (nb > N) die("initconf", "more bosons than particles");
+      vector<char> seen_p(max(1, nb), 0);
+      for (int i = 0; i < nb; i++) {
+         f >> pindex[i];
+         if (!f || pindex[i] < 0 || pindex[i] >= nb || seen_p[pindex[i]]) die("initconf", "the permutation on the first line of xyz.init is not a bijection of 0.." + to_string(nb - 1));
+         seen_p[pindex[i]] = 1;
+         rindex[pindex[i]] = i;
+      }
       string line; getline(f, line); getline(f, line);
       for (size_t i = 0; i < n; i++) {
          string label; f >> label;
@@ -388,10 +408,40 @@ int main(int argc, char **argv)
    ncclComm_t comm = nullptr;
    if (ranks > 1) {
       ncclUniqueId id;
-      string idf = d.outdir + ".pimc_nccl_id";
-      if (rank == 0) { ncclGetUniqueId(&id); FILE *f = fopen((idf + ".tmp").c_str(), "wb"); fwrite(&id, sizeof id, 1, f); fclose(f); rename((idf + ".tmp").c_str(), idf.c_str()); }
-      else { FILE *f; while (!(f = fopen(idf.c_str(), "rb"))) this_thread::sleep_for(chrono::milliseconds(50)); if (fread(&id, sizeof id, 1, f) != 1) die("nccl", "bad id file"); fclose(f); }
+      // Rendezvous through the output directory.  A stale id file of an earlier run must never be taken for this run's:
+      // every other rank first drops a hello file, rank 0 waits for all of them, and only then writes a FRESH id file
+      // (temporary name + rename); a rank accepts the id file only if it is newer than its own hello.  MASTER_PORT (set by
+      // torchrun-style launchers) keeps concurrent runs in one directory apart.  Rank 0 removes the files afterwards.
+      const char *nonce = getenv("PIMC_NCCL_NONCE") ? getenv("PIMC_NCCL_NONCE") : (getenv("MASTER_PORT") ? getenv("MASTER_PORT") : "0");
+      const string idf = d.outdir + ".pimc_nccl_id." + nonce;
+      auto mtime_ns = [](const string &f, long long &t) { struct stat sb; if (stat(f.c_str(), &sb) != 0) return false; t = (long long)sb.st_mtim.tv_sec * 1000000000LL + sb.st_mtim.tv_nsec; return true; };
+      if (rank == 0) {
+         remove(idf.c_str());
+         for (int r = 1; r < ranks; r++) {
+            long long t;
+            const string hf = idf + ".hello." + to_string(r);
+            for (int tries = 0; !mtime_ns(hf, t); tries++) { if (tries > 12000) die("nccl", "rank " + to_string(r) + " never arrived"); this_thread::sleep_for(chrono::milliseconds(50)); }
+         }
+         if (ncclGetUniqueId(&id) != ncclSuccess) die("nccl", "ncclGetUniqueId failed");
+         FILE *f = fopen((idf + ".tmp").c_str(), "wb");
+         if (!f || fwrite(&id, sizeof id, 1, f) != 1 || fclose(f) != 0) die("nccl", "cannot write " + idf + ".tmp");
+         if (rename((idf + ".tmp").c_str(), idf.c_str()) != 0) die("nccl", "cannot rename " + idf + ".tmp");
+      } else {
+         const string hf = idf + ".hello." + to_string(rank);
+         { FILE *f = fopen(hf.c_str(), "wb"); if (!f) die("nccl", "cannot write " + hf); fputc('h', f); fclose(f); }
+         long long t_hello = 0, t_id = 0;
+         mtime_ns(hf, t_hello);
+         for (int tries = 0;; tries++) {
+            if (mtime_ns(idf, t_id) && t_id >= t_hello) {
+               FILE *f = fopen(idf.c_str(), "rb");
+               if (f) { const bool ok = fread(&id, sizeof id, 1, f) == 1; fclose(f); if (ok) break; }
+            }
+            if (tries > 12000) die("nccl", "no id file from rank 0");
+            this_thread::sleep_for(chrono::milliseconds(50));
+         }
+      }
       if (ncclCommInitRank(&comm, ranks, id, rank) != ncclSuccess) die("nccl", "ncclCommInitRank failed");
+      if (rank == 0) { remove(idf.c_str()); for (int r = 1; r < ranks; r++) remove((idf + ".hello." + to_string(r)).c_str()); }     // the collective init has consumed them
    }
 #else
    if (ranks > 1) die("main", "built without NCCL: multi-rank runs need -DPIMC_WITH_NCCL");
@@ -421,13 +471,54 @@ int main(int argc, char **argv)
       long done = 0;
       bool print_xyz = true;                                                                 // MCResetBlockAverage, mc_main.cc:543
       long sum_row_at = -1;                                                                  // step of this block's last _sum.eng row
+      // MCSaveAcceptRatio (mc_main.cc:440-441, 879-943): one line every MCSKIP_RATIO steps of the block with the acceptance ratios
+      // accumulated since the block began; worm species get the reference's in-line "open/close [..] .. swap [..] .." columns
+      auto accept_ratio_line = [&](long step) {
+         pimcgpu_scalars sc;
+         pimcgpu_accum_device_ptr();
+         ck(pimcgpu_sync(), "pimcgpu_sync");
+         ck(pimcgpu_block_scalars(&sc), "pimcgpu_block_scalars");
+         if (rank != 0) return;
+         const long pass = (step + P - 1) / P;                                                 // passCount of the step (1-based)
+         cout << "BLOCK:" << setw(8) << block << BLANK << "PASS:" << setw(8) << pass << BLANK << "STEP:" << setw(8) << step << BLANK;
+         for (int t = 0; t < sys.ntypes; t++) {
+            if (d.worm && t == sys.worm_type) {
+               double qt[7], qa[7], cq = 0;
+               ck(pimcgpu_worm_counters(qt, qa, &cq), "pimcgpu_worm_counters");
+               cout << setw(8) << "open/close" << " [ " << qt[0] / cq << "-" << qt[1] / cq << " ] " << BLANK << setw(8) << qa[0] / qt[0] << BLANK << setw(8) << qa[1] / qt[1] << BLANK;
+               cout << setw(8) << "advance/recede" << " [ " << qt[4] / cq << "-" << qt[5] / cq << " ] " << BLANK << setw(8) << qa[4] / qt[4] << BLANK << setw(8) << qa[5] / qt[5] << BLANK;
+               cout << setw(8) << "swap" << " [ " << qt[6] / cq << " ] " << BLANK << setw(8) << qa[6] / qt[6] << BLANK;
+            } else
+               cout << setw(8) << d.types[t].name << BLANK << setw(8) << sc.mcaccep[t][0] / sc.mctotal[t][0] << BLANK << setw(8) << sc.mcaccep[t][1] / sc.mctotal[t][1] << BLANK;
+         }
+         if (Q) cout << BLANK << "Rot: " << setw(8) << sc.mcaccep[imtype][2] / sc.mctotal[imtype][2] << BLANK;
+         cout << endl;
+      };
       while (done < steps_block) {
-         long chunk = min<long>(d.skip_averg, steps_block - done);
+         long chunk = min<long>(d.skip_averg - done % d.skip_averg, steps_block - done);
          if (block <= d.eq_blocks) chunk = min<long>(steps_block - done, 4L * P);            // no estimators while equilibrating
+         if (d.skip_ratio > 0) chunk = min<long>(chunk, d.skip_ratio - done % d.skip_ratio);  // stop where the reference prints its line
          ck(pimcgpu_steps(chunk), "pimcgpu_steps");
          done += chunk;
+         if (d.skip_ratio > 0 && done % d.skip_ratio == 0) accept_ratio_line(done);
          if (block > d.eq_blocks && done % d.skip_averg == 0) {
             ck(pimcgpu_measure(), "pimcgpu_measure");
+            if (bstype >= 0 && rank == 0 && !getenv("PIMC_NO_PERMUTATION_TAB")) {
+               // GetPermutation (mc_estim.cc:2731-2753, called by MCGetAverage when there are bosons): one line "PIndex[0] PIndex[1] ..."
+               // per measurement appended to permutation.tab; chain 0's permutation (closed paths only, like the measurement itself)
+               int st[5] = {0, 0, 0, 0, 0};
+               if (d.worm) ck(pimcgpu_worm_state(0, st), "pimcgpu_worm_state");
+               if (!st[0]) {
+                  ck(pimcgpu_download_state(0, nullptr, nullptr, nullptr, pindex.data()), "pimcgpu_download_state");
+                  static FILE *fperm = nullptr;
+                  if (!fperm) fperm = fopen("permutation.tab", "a");
+                  if (!fperm) die("GetPermutation", "Can't open input file permutation.tab");
+                  ostringstream row;
+                  for (int i = 0; i < d.types[bstype].numb; i++) row << pindex[i] << " ";
+                  fprintf(fperm, "%s\n", row.str().c_str());
+                  if (done >= steps_block) fflush(fperm);
+               }
+            }
             if (print_xyz && rank == 0) {
                // instantaneous configuration of the block's first measured (closed) path: IOxyzAng into <prefix>NNN.xyz
                // (PrintXYZprl, mc_main.cc:395-427,543); chain 0
@@ -499,8 +590,8 @@ int main(int argc, char **argv)
          rename((ckname + ".tmp").c_str(), ckname.c_str());
       }
       if (rank != 0) continue;
-      // MCSaveAcceptRatio, mc_main.cc:879-943
-      cout << "BLOCK:" << setw(8) << block << BLANK << "PASS:" << setw(8) << d.passes << BLANK << "STEP:" << setw(8) << steps_block << BLANK;
+      // end-of-block summary of the same ratios (not in the reference, whose lines come every MCSKIP_RATIO steps above)
+      cout << "BLOCK-END:" << setw(8) << block << BLANK << "PASS:" << setw(8) << d.passes << BLANK << "STEP:" << setw(8) << steps_block << BLANK;
       for (int t = 0; t < sys.ntypes; t++)
          cout << setw(8) << d.types[t].name << BLANK << setw(8) << sc.mcaccep[t][0] / sc.mctotal[t][0] << BLANK << setw(8) << sc.mcaccep[t][1] / sc.mctotal[t][1] << BLANK;
       if (Q) cout << BLANK << "Rot: " << setw(8) << sc.mcaccep[imtype][2] / sc.mctotal[imtype][2] << BLANK;
@@ -567,6 +658,12 @@ int main(int argc, char **argv)
       }
       // checkpoint, mc_main.cc:471-483: yw001.stat / .conf / .tabl in the reference's byte layout, chain 0
       ck(pimcgpu_download_state(0, coords.data(), angles.data(), cosine.data(), bstype >= 0 ? pindex.data() : nullptr), "pimcgpu_download_state");
+      auto backup = [&](const char *f) {      // IOFileBackUp, mc_input.cc:796-815: cp <file> <file>.old
+         ifstream in(f, ios::binary);
+         if (in.good()) { ofstream out(string(f) + ".old", ios::binary); out << in.rdbuf(); }
+      };
+      backup("yw001.stat"); backup("yw001.conf"); backup("yw001.tabl");
+      if (d.worm) backup("yw001.worm");
       { ofstream f("yw001.stat"); f << "STARTBLOCK " << block << endl; }
       {
          ofstream f("yw001.conf", ios::binary);

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _deck(pkg, tmp, blocks="6  2", passes="200"):
+def _deck(pkg, tmp, blocks="6  2", passes="2000"):
     d = os.path.join(pkg.configs.DECKS, "CO2_100K_4_4")
     for f in ("CO2_T100t4.rot", "CO2_fake.pot"):
         shutil.copy(os.path.join(d, f), tmp)
@@ -27,9 +27,10 @@ def _deck(pkg, tmp, blocks="6  2", passes="200"):
     rng = np.random.default_rng(4)
     with open(os.path.join(tmp, "xyz.init"), "w") as f:            # initconf.f:10-23: count (+ permutation), comment, label x phi y cos(theta) z chi
         f.write("4\n# start configuration of the boundary test\n")
+        phi0, ct0 = rng.uniform(0, 6.28), rng.uniform(-0.8, 0.8)         # one orientation, slightly different on the four slices
         for it in range(4):
             x, y, z = 0.05 * rng.standard_normal(3)
-            f.write(f"C {x:.6e} {rng.uniform(0, 6.28):.6e} {y:.6e} {rng.uniform(-0.9, 0.9):.6e} {z:.6e} 0.000000e+00\n")
+            f.write(f"C {x:.6e} {phi0 + 0.05 * rng.standard_normal():.6e} {y:.6e} {ct0 + 0.02 * rng.standard_normal():.6e} {z:.6e} 0.000000e+00\n")
 
 
 def test_reference_main_through_the_c_abi_matches_pimc_b200(pkg, tmp_path):
@@ -53,7 +54,7 @@ def test_reference_main_through_the_c_abi_matches_pimc_b200(pkg, tmp_path):
     assert ea.shape == eb.shape == (4, 10) and list(ea[:, 0]) == [3, 4, 5, 6]
     # columns written by the reference's own SaveEnergy from the accumulators fetched over the ABI (mc_main.cc:780-792)
     assert np.allclose(ea[:, 1:8], eb[:, 1:8], rtol=2e-6, atol=1e-9), np.abs(ea - eb).max()
-    assert abs(ea[:, 1].mean() - 150.0) < 30.0 and abs(ea[:, 4].mean() - 97.0) < 30.0            # free particle at 100 K; CO2 rotor, 4 slices (800 steps per block)
+    assert abs(ea[:, 1].mean() - 150.0) < 30.0 and abs(ea[:, 4].mean() - 97.0) < 30.0            # free particle at 100 K; CO2 rotor, 4 slices (8000 steps per block)
     # the reference's checkpoint and configuration writers ran on the state downloaded through the ABI
     for f in ("yw001.stat", "yw001.conf", "yw001.tabl", "CO2_monomer.xyz", "CO2_monomer003.rcf"):
         assert os.path.exists(a / f), f

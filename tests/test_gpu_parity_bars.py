@@ -217,7 +217,8 @@ def test_rotden_composed_through_device_intermediates(pkg, c1):
     for name, g, r in (("rho", rho, orho), ("erot", erot, oerot), ("esq", esq, oesq)):
         err = np.abs(g - r) / np.maximum(np.abs(r), 1e-290)
         print(f"   {name}: max relative difference {err[well].max():.2e} (well conditioned), {err[same].max():.2e} (all)")
-        assert err[well].max() < RTOL
+        # the synthetic E^2 table is the square of the E table: twice its relative slope, hence twice the bar for the same angle drift
+        assert err[well].max() < (2 * RTOL if name == "esq" else RTOL)
     # everywhere: the difference is the table gradient times the measured angle drift (degrees), nothing else
     dd = np.abs(deg - odeg)
     dd[:, 0] = np.minimum(dd[:, 0], np.abs(360.0 - dd[:, 0])); dd[:, 2] = np.minimum(dd[:, 2], np.abs(360.0 - dd[:, 2]))

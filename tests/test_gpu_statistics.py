@@ -103,11 +103,14 @@ def test_rotor_in_solvent_cluster_matches_reference(pkg):
     compare(g, r, [(0, "K"), (1, "V"), (2, "E_rot")])
 
 
-def _stats_case(pkg, case, nchains, gpu_per_block, min_sigma_cols=()):
+def _stats_case(pkg, case, nchains, gpu_per_block, ngroups=8):
     """Converged observables of north_star -- <K>, <V>, <E_rot>, the orientational correlation <n(0).n(t)> (GetRCF) and the
     superfluid fractions of the .sup / .sffs3d / .mffs3d files -- sampled by the CUDA path against a committed fixture of the
     REFERENCE's own sampling (tests/golden/stats/<case>_ref.json, made here by profiles/stats_ref.py from oracle/_ref:
-    the reference's unmodified move and estimator objects).  2 sigma of the combined block errors, column by column."""
+    the reference's unmodified move and estimator objects).  2 sigma of the combined errors, column by column.
+    Errors: the reference is ONE Markov chain, its error comes from the blocking method; the device runs `ngroups`
+    INDEPENDENT groups of chains (disjoint MRG32k3a streams), so its error is the spread of the group means -- rigorous
+    whatever the autocorrelation time of the slow cluster modes (the area estimators decorrelate over hundreds of passes)."""
     import json
     sys.path.insert(0, os.path.join(ROOT, "profiles"))
     import stats_ref
@@ -119,23 +122,27 @@ def _stats_case(pkg, case, nchains, gpu_per_block, min_sigma_cols=()):
     cfg = pkg.configs.make_config(d["config"], **d["kw"])
     s = cfg.system
     skip = d["skip"]
-    G = pkg.gpu.PimcGpu(cfg, nchains=nchains)
-    G.seed((12345,) * 6)
-    G.steps(2000 * s.P)          # equilibration: the lattice start relaxes over ~1000 passes (slow cluster modes)
-    rows = []
-    for b in range(len(r)):
-        G.accum_reset()
-        for k in range(gpu_per_block // skip):
-            G.steps(skip, sync=False)
-            G.measure()
-        G.sync()
-        acc, lay = G.accum_download()
-        n = acc[0]
-        a = acc[lay["area"]:lay["area"] + 36]
-        rcf = acc[lay["rcf"]:lay["rcf"] + max(1, s.Q)]
-        rows.append(stats_ref.observables(s, n, acc[1], acc[2], acc[3], rcf, a[0:6], a[6:21], a[21:36], d["lambda_bose"], d["mass_bose"]))
-    G.close()
-    g = np.array(rows)
+    per_group = max(1, nchains // ngroups)
+    nblocks = 32
+    groups = []
+    for gi in range(ngroups):
+        G = pkg.gpu.PimcGpu(cfg, nchains=per_group, chain_offset=gi * per_group)
+        G.seed((12345,) * 6)
+        G.steps(2000 * s.P)          # equilibration: the lattice start relaxes over ~1000 passes (slow cluster modes)
+        rows = []
+        for b in range(nblocks):
+            G.accum_reset()
+            for k in range(2 * gpu_per_block // skip):
+                G.steps(skip, sync=False)
+                G.measure()
+            G.sync()
+            acc, lay = G.accum_download()
+            n = acc[0]
+            a = acc[lay["area"]:lay["area"] + 36]
+            rcf = acc[lay["rcf"]:lay["rcf"] + max(1, s.Q)]
+            rows.append(stats_ref.observables(s, n, acc[1], acc[2], acc[3], rcf, a[0:6], a[6:21], a[21:36], d["lambda_bose"], d["mass_bose"]))
+        G.close()
+        groups.append(np.array(rows))
     names = d["columns"]
     cols = [(i, c) for i, c in enumerate(names) if np.any(r[:, i] != 0.0)]
     assert len(cols) >= 6
@@ -144,13 +151,23 @@ def _stats_case(pkg, case, nchains, gpu_per_block, min_sigma_cols=()):
     # (six more columns of the same data) are held to 3 sigma so that thirteen simultaneous tests stay meaningful
     sff = [i for i, c in cols if c.endswith("(sff)")]
     if sff:
-        g = np.c_[g, g[:, sff].mean(axis=1)]; r = np.c_[r, r[:, sff].mean(axis=1)]
-        cols.append((g.shape[1] - 1, "fs(sff), mean of xx/yy/zz"))
-    primary = [(i, c) for i, c in cols if not (c.endswith("(sff)") or c.endswith("(mff)"))]
-    secondary = [(i, c) for i, c in cols if c.endswith("(sff)") or c.endswith("(mff)")]
-    compare(g, r, primary, 2.0)
-    compare(g, r, secondary, 3.0)
-    return g, r
+        groups = [np.c_[g, g[:, sff].mean(axis=1)] for g in groups]
+        r = np.c_[r, r[:, sff].mean(axis=1)]
+        cols.append((r.shape[1] - 1, "fs(sff), mean of xx/yy/zz"))
+    gm = np.array([g.mean(axis=0) for g in groups])            # [group][column]
+    fails = []
+    for i, nm in cols:
+        mg, mr = gm[:, i].mean(), r[:, i].mean()
+        sg = max(gm[:, i].std(ddof=1) / np.sqrt(ngroups), blocked_sem(np.concatenate([g[:, i] for g in groups])))
+        sr = blocked_sem(r[:, i])
+        sigma = np.hypot(sg, sr)
+        primary = not (nm.endswith("(sff)") or nm.endswith("(mff)"))
+        bar = 2.0 if primary else 3.0
+        print(f"{nm}: gpu {mg:.5f} +- {sg:.5f} ({ngroups} independent groups)   reference {mr:.5f} +- {sr:.5f}   diff {abs(mg - mr) / sigma:.2f} sigma (bar {bar})")
+        if not abs(mg - mr) < bar * sigma + 1e-9 * abs(mr):
+            fails.append(f"{nm}: {mg} vs {mr} (sigma {sigma})")
+    assert not fails, fails
+    return gm, r
 
 
 def test_top_in_helium_without_worm_matches_reference(pkg):
@@ -322,7 +339,15 @@ def test_cxx_driver_worm_deck_and_restart(pkg, tmp_path):
     assert xyz[2].startswith("H21") and len(xyz[2].split()) == 7 and xyz[-2].startswith("N2O1")
     rcf = open(tmp_path / "gr004.rcf").read().split("\n")
     assert len(rcf) == 2 * 129 + 4 and rcf[129:132] == ["", "", "#"] and len(rcf[132].split()) == 10
-    # restart: two more blocks, numbered 5 and 6, appended to the same files
+    # restart: two more blocks, numbered 5 and 6, appended to the same files.  permutation.tab of the first run must go first:
+    # the reference refuses to start over it (mc_main.cc:129-131, README.md:50-53) and so does pimc_b200
+    perm = np.loadtxt(tmp_path / "permutation.tab", dtype=int, ndmin=2)
+    assert perm.shape[1] == 5 and all(sorted(r) == [0, 1, 2, 3, 4] for r in perm)
+    again = subprocess.run([drv, "--chains", "8"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert again.returncode == 1 and "File already exists: permutation.tab" in again.stdout
+    os.remove(tmp_path / "permutation.tab")
+    for f in ("yw001.stat.old", "yw001.conf.old", "yw001.tabl.old"):
+        assert os.path.exists(tmp_path / f), f                       # IOFileBackUp copies (mc_main.cc:471-483)
     open(tmp_path / "qmc.input", "w").write(deck.replace("NUMBEROFBLOCKS     4 1 ", "NUMBEROFBLOCKS     2 0 ") + "RESTART\n")
     out = subprocess.run([drv, "--chains", "8"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
