@@ -123,7 +123,7 @@ def _stats_case(pkg, case, nchains, gpu_per_block, ngroups=8):
     s = cfg.system
     skip = d["skip"]
     per_group = max(1, nchains // ngroups)
-    nblocks = 32
+    nblocks = 16
     groups = []
     for gi in range(ngroups):
         G = pkg.gpu.PimcGpu(cfg, nchains=per_group, chain_offset=gi * per_group)
@@ -160,6 +160,10 @@ def _stats_case(pkg, case, nchains, gpu_per_block, ngroups=8):
         mg, mr = gm[:, i].mean(), r[:, i].mean()
         sg = max(gm[:, i].std(ddof=1) / np.sqrt(ngroups), blocked_sem(np.concatenate([g[:, i] for g in groups])))
         sr = blocked_sem(r[:, i])
+        if nm.startswith("fs(sff), mean") and sff:
+            # the largest-over-blocking-levels estimate is itself noisy; the mean of three components is never given a smaller
+            # error than the quadrature combination of its components' errors (independent components)
+            sr = max(sr, np.sqrt(sum(blocked_sem(r[:, j]) ** 2 for j in sff)) / len(sff))
         sigma = np.hypot(sg, sr)
         primary = not (nm.endswith("(sff)") or nm.endswith("(mff)"))
         bar = 2.0 if primary else 3.0
