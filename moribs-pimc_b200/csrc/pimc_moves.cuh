@@ -222,6 +222,77 @@ __device__ __forceinline__ double partner_sum_diff(const Params &p, const SmallT
    return D;
 }
 
+// NU full sub-batches of 32 atom partners starting at atom j0 (every lane has a partner in every sub-batch): the body of the
+// fast path above without the range test.  g: the moved atom, jx: a partner left out (or -1).
+template <int NU>
+__device__ __forceinline__ double spline_batch(const Params &p, const SmallTables &t, const double *px, const double *py, const double *pz,
+                                               int j0, int g, int jx, int jalt, const double *pn, const double *po)
+{
+   double rn[NU], ro[NU];
+   bool ok[NU];
+   #pragma unroll
+   for (int u = 0; u < NU; u++) {
+      const int j = j0 + 32 * u;
+      ok[u] = j != g && j != jx;
+      const int jj = ok[u] ? j : jalt;
+      const double qx = px[jj], qy = py[jj], qz = pz[jj];
+      double inv_;
+      fast_r_invr((pn[0] - qx) * (pn[0] - qx) + (pn[1] - qy) * (pn[1] - qy) + (pn[2] - qz) * (pn[2] - qz), rn[u], inv_);
+      fast_r_invr((po[0] - qx) * (po[0] - qx) + (po[1] - qy) * (po[1] - qy) + (po[2] - qz) * (po[2] - qz), ro[u], inv_);
+   }
+   double e[NU];
+   bool bad = false;
+   #pragma unroll
+   for (int u = 0; u < NU; u++) e[u] = spot1d_poly(p, t, rn[u], bad) - spot1d_poly(p, t, ro[u], bad);
+   if (__builtin_expect(bad, 0)) {
+      #pragma unroll
+      for (int u = 0; u < NU; u++) e[u] = spot1d_move(p, t, rn[u]) - spot1d_move(p, t, ro[u]);
+   }
+   double D = 0.0;
+   #pragma unroll
+   for (int u = 0; u < NU; u++) D += ok[u] ? e[u] : 0.0;
+   return D;
+}
+// the first 32 * nfull atom partners of the species of atom g at slice `it` (lane = partner within a sub-batch); the
+// remaining numb - 32 nfull partners of ALL the beads a warp works on go through one extra pass of the caller (tail_pair),
+// so no sub-batch runs with most of its lanes masked (100 partners: 3 full sub-batches + 4 tail partners instead of 4 sub-batches)
+template <int KIND>
+__device__ __forceinline__ double partner_sum_main(const Params &p, const SmallTables &t, int c, int g, const double *pn, const double *po,
+                                                   int it, int lane, int nfull, int jx)
+{
+   const int tg = type_of(p, g), ja = p.first[tg];
+   const double *px = p.pos + pos_index(p, c, it, 0, 0), *py = px + p.Npad, *pz = py + p.Npad;
+   const int jalt = (g == ja || jx == ja) ? ((g == ja + 1 || jx == ja + 1) ? ja + 2 : ja + 1) : ja;       // any atom other than g and jx
+   double D = 0.0;
+   int u0 = 0;
+   for (; nfull - u0 >= 4; u0 += 4) D += spline_batch<4>(p, t, px, py, pz, ja + lane + 32 * u0, g, jx, jalt, pn, po);
+   switch (nfull - u0) {
+      case 3: D += spline_batch<3>(p, t, px, py, pz, ja + lane + 32 * u0, g, jx, jalt, pn, po); break;
+      case 2: D += spline_batch<2>(p, t, px, py, pz, ja + lane + 32 * u0, g, jx, jalt, pn, po); break;
+      case 1: D += spline_batch<1>(p, t, px, py, pz, ja + lane + 32 * u0, g, jx, jalt, pn, po); break;
+      default: break;
+   }
+   return D;
+}
+// one (bead, partner) term of the tail pass: exact spline path
+__device__ __forceinline__ double tail_pair(const Params &p, const SmallTables &t, int c, int it, int j, const double *pn, const double *po)
+{
+   double d2n = 0.0, d2o = 0.0;
+   #pragma unroll
+   for (int d = 0; d < 3; d++) {
+      const double pj = p.pos[pos_index(p, c, it, d, j)];
+      d2n += (pn[d] - pj) * (pn[d] - pj);
+      d2o += (po[d] - pj) * (po[d] - pj);
+   }
+   double rn, ro, inv_;
+   fast_r_invr(d2n, rn, inv_);
+   fast_r_invr(d2o, ro, inv_);
+   bool bad = false;
+   double e = spot1d_poly(p, t, rn, bad) - spot1d_poly(p, t, ro, bad);
+   if (__builtin_expect(bad, 0)) e = spot1d_move(p, t, rn) - spot1d_move(p, t, ro);
+   return e;
+}
+
 __device__ __forceinline__ void bump_pos_epoch(const Params &p, Ctx &x)
 {
    if (x.gthread == 0) p.pos_epoch[x.c] += 1;      // read by the rot leaders after the next chain barrier
@@ -320,11 +391,24 @@ __device__ double molecular_partial(const Params &p, Ctx &x, int type, int a0, c
    const int c = x.c, P = p.P, N = p.N, base = p.first[type], na = p.numb[type], nother = N - na;
    const int nwc = blockDim.x >> 5, gwarp = x.crank * nwc + (x.tid >> 5), nwarps = p.cpc * nwc, lane = x.tid & 31;
    double part = 0.0;
+   const int nfull = na / 32, ntail = na - 32 * nfull;
+   const int nmine = (P - gwarp + nwarps - 1) / nwarps;               // slices of this warp
+   const bool split = p.poly1d && nfull >= 1 && nmine * ntail <= 32;
+   if (split && lane < nmine * ntail) {                                // tail partners of all my slices in one pass
+      const int k = lane / ntail, j = base + 32 * nfull + (lane - k * ntail), it = gwarp + k * nwarps;
+      if (j != a0 && j != jx) {
+         double po[3], pn[3];
+         #pragma unroll
+         for (int d = 0; d < 3; d++) { po[d] = p.pos[pos_index(p, c, it, d, a0)]; pn[d] = po[d] + disp[d]; }
+         part += tail_pair(p, x.t, c, it, j, pn, po);
+      }
+   }
    for (int it = gwarp; it < P; it += nwarps) {
       double po[3], pn[3];
       #pragma unroll
       for (int d = 0; d < 3; d++) { po[d] = p.pos[pos_index(p, c, it, d, a0)]; pn[d] = po[d] + disp[d]; }
-      part += partner_sum_diff<KIND>(p, x.t, c, a0, pn, po, it, lane, 32, jx);
+      if (split) part += partner_sum_main<KIND>(p, x.t, c, a0, pn, po, it, lane, nfull, jx);
+      else part += partner_sum_diff<KIND>(p, x.t, c, a0, pn, po, it, lane, 32, jx);
       for (int jo = lane; jo < nother; jo += 32) {
          const int j = (jo < base) ? jo : jo + na;
          part += pair_diff<KIND>(p, x.t, c, a0, pn, po, j, it);
@@ -683,9 +767,29 @@ __device__ void bisection_sweep_piped(const Params &p, Ctx &x, int type, int off
                eo_level = level;
             }
          }
+         // atom partners beyond the last full sub-batch of 32: every (midpoint, tail partner) term in one pass
+         const int nfull = na / 32, ntail = na - 32 * nfull;
+         const bool split = p.poly1d && nfull >= 1 && (seg - 1) * ntail <= 32;
+         double et = 0.0;
+         int et_level = -1;
+         if (split && lane < (seg - 1) * ntail) {
+            const int gm = lane / ntail, j = base + 32 * nfull + (lane - gm * ntail);
+            const int level = 31 - __clz(gm + 1), m = gm + 1 - (1 << level);
+            const int lss = seg >> level, half = lss >> 1;
+            const int t1 = half + m * lss, sl = (s0 + t1) % P;
+            const bool wrap = s0 + t1 >= P;
+            const int g = wrap ? gB : gA;
+            if (j != g && j != (wrap ? hB : hA)) {
+               double po[3], pn[3];
+               #pragma unroll
+               for (int d = 0; d < 3; d++) { po[d] = p.pos[pos_index(p, c, sl, d, g)]; pn[d] = nx[t1 * 3 + d]; }
+               et = tail_pair(p, x.t, c, sl, j, pn, po);
+            }
+            et_level = level;
+         }
          for (int level = 0; level < L; level++) {
             const int lss = seg >> level, half = lss >> 1, nmid = 1 << level;
-            double D = (eo_level == level) ? eo : 0.0;
+            double D = ((eo_level == level) ? eo : 0.0) + ((et_level == level) ? et : 0.0);
             if ((seg - 1) * nother > 32)
                for (int i = lane; i < nmid * nother; i += 32) {       // many terms: level by level
                   const int m = i / nother, jo = i - m * nother;
@@ -703,7 +807,8 @@ __device__ void bisection_sweep_piped(const Params &p, Ctx &x, int type, int off
                double po[3], pn[3];
                #pragma unroll
                for (int d = 0; d < 3; d++) { po[d] = p.pos[pos_index(p, c, sl, d, g)]; pn[d] = nx[t1 * 3 + d]; }
-               D += partner_sum_diff<KIND>(p, x.t, c, g, pn, po, sl, lane, 32, wrap ? hB : hA);
+               if (split) D += partner_sum_main<KIND>(p, x.t, c, g, pn, po, sl, lane, nfull, wrap ? hB : hA);
+               else D += partner_sum_diff<KIND>(p, x.t, c, g, pn, po, sl, lane, 32, wrap ? hB : hA);
             }
             D = team_sum(D, 32);
             if (lane == 0) dsum[level] = D;
@@ -1445,18 +1550,21 @@ __device__ void rot_run(const Params &p, Ctx &x, int type, int nrun, int *err)
          bool acc = rot_accept<KIND>(p, sl->rho, vnew, vold, sl->u4, &bad);
          if (bad) { acc = false; atomicOr(err, bad); }
          double *cn = counter_ptr(p, c, type, 2);
-         atomicAdd(cn, 1.0);
          sl->vcache = acc ? vnew : vold;
          sl->vep = sl->epoch;
          sl->gep = sl->epoch;
          if (acc) {
-            atomicAdd(cn + 1, 1.0);
-            rot_commit<KIND>(p, c, q, m, sl->cost, sl->phi, sl->chi);
-            sl->cur[0] = sl->cost; sl->cur[1] = sl->phi; sl->cur[2] = sl->chi;
+            // rot_commit for a linear rotor: the new axis is the proposal's (same expressions, same inputs: sl->a), so the
+            // hand-over to the neighbours does not wait for another sincos / sqrt
+            p.ang[ang_index(p, c, q, 1, m)] = sl->cost;
+            p.ang[ang_index(p, c, q, 0, m)] = sl->phi;
             #pragma unroll
-            for (int i = 0; i < 3; i++) sl->b[i] = sl->a[i];
+            for (int d = 0; d < 3; d++) { const double nd = sl->a[d]; p.cosn[ang_index(p, c, q, d, m)] = nd; sl->b[d] = nd; }
+            sl->cur[0] = sl->cost; sl->cur[1] = sl->phi; sl->cur[2] = sl->chi;
          }
          asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(fl + q), "r"(n + 1) : "memory");
+         atomicAdd(cn, 1.0);
+         if (acc) atomicAdd(cn + 1, 1.0);
       }
       MARK(x, 9);
    }
