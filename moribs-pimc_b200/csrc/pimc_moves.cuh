@@ -1140,12 +1140,22 @@ __device__ __forceinline__ bool rot_accept(const Params &p, const double *rho, d
 
 // density factor i of a step at slice q: i = 0 rho(q0 -> cur), 1 rho(cur -> q2), 2 rho(q0 -> new), 3 rho(new -> q2);
 // cur / nw are the orientations of the slice (matrix or unit vector)
+// nb0 / nb2 (optional): the neighbours' current rotation matrices when the caller holds them (all slices of a one-CTA chain
+// live in the CTA's slots) -- otherwise they are rebuilt from the stored Euler angles (three sincos and an acos each)
 template <int KIND>
-__device__ __forceinline__ double rot_density(const Params &p, const SmallTables &t, int c, int q0, int q2, int m, int i, const double *cur, const double *nw, int *bad)
+__device__ __forceinline__ double rot_density(const Params &p, const SmallTables &t, int c, int q0, int q2, int m, int i, const double *cur, const double *nw, int *bad,
+                                              const double *nb0 = nullptr, const double *nb2 = nullptr)
 {
    const double *mid = (i < 2) ? cur : nw;
    if ((KIND & 3) == 2) {
       Mat3 A, B;
+      if ((i == 0 || i == 2) && nb0) {
+         #pragma unroll
+         for (int k = 0; k < 9; k++) { A.m[k / 3][k % 3] = nb0[k]; B.m[k / 3][k % 3] = mid[k]; }
+      } else if (!(i == 0 || i == 2) && nb2) {
+         #pragma unroll
+         for (int k = 0; k < 9; k++) { A.m[k / 3][k % 3] = mid[k]; B.m[k / 3][k % 3] = nb2[k]; }
+      } else
       if (i == 0 || i == 2) {
          load_rotmat(p, c, q0, m, A);
          #pragma unroll
@@ -1345,10 +1355,12 @@ __device__ __forceinline__ void rot_decide_owned(const Params &p, Ctx &x, int ty
       int q0 = q - 1, q2 = q + 1;
       if (q0 < 0) q0 += Q;
       if (q2 >= Q) q2 -= Q;
+      // a chain that lives in one CTA holds every slice's current matrix in its slots: the neighbours' are read, not rebuilt
+      const double *nb0 = (p.cpc == 1 && (KIND & 3) == 2) ? x.slot[q0].b : nullptr, *nb2 = (p.cpc == 1 && (KIND & 3) == 2) ? x.slot[q2].b : nullptr;
       if (active)
          for (int i = x.gl; i < 4; i += G) {
             int bad = 0;
-            sl->rho[i] = rot_density<KIND>(p, x.t, c, q0, q2, m, i, sl->b, sl->a, &bad);
+            sl->rho[i] = rot_density<KIND>(p, x.t, c, q0, q2, m, i, sl->b, sl->a, &bad, nb0, nb2);
             if (bad) { if (G == 1) sl->bad |= bad; else atomicOr(&sl->bad, bad); }
          }
       group_sync(x);

@@ -15,7 +15,7 @@ n = s.N * s.P
 pin_c = torch.empty((chains, 3, n), dtype=torch.float64, pin_memory=True)
 pin_a = torch.empty((chains, 3, n), dtype=torch.float64, pin_memory=True)
 host_c, host_a = pin_c.numpy(), pin_a.numpy()
-G.download_all_into(host_c, host_a)
+G.download_rows_into(host_c, host_a)
 G.steps(s.P)
 t = {k: 0.0 for k in ("upload", "steps", "measure", "accum", "download")}
 reps = 5
@@ -26,7 +26,7 @@ for _ in range(reps):
     G.accum_reset(); G.steps(s.P, sync=False); G.sync(); t2 = time.perf_counter()
     G.measure(); G.sync(); t3 = time.perf_counter()
     acc, _ = G.accum_download(); t4 = time.perf_counter()
-    G.download_all_into(host_c, host_a)
+    G.download_rows_into(host_c, host_a)
     t5 = time.perf_counter()
     for k, v in zip(t, (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4)):
         t[k] += v
