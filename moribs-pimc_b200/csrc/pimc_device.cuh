@@ -58,6 +58,7 @@ struct Params {
    const double2 *cell2d;        // [(rs-1)][cs] row pairs {V[ir][ic], V[ir+1][ic]}: a bilinear cell is two adjacent 16-byte
                                  // entries (32 contiguous bytes, 2x the table instead of 4x so the hot region stays in L2)
    const double2 *rgi2d, *cgi2d; // {grid[i], 1/(grid[i+1]-grid[i])} of the two axes
+   int geo_hint;                 // L2 policy of the geometry records: 0 evict_first, 1 evict_last, 2 default
    int cell4_on, cell_hint;      // whole-cell table in use (else the row-pair table); the random gathers do not allocate in L1 (they never hit
                                  // there and displace the lines the other loads reuse)
    const double *cell4;          // [(rs-1)][(cs-1)][4] whole cells {V[ir][ic], V[ir+1][ic], V[ir][ic+1], V[ir+1][ic+1]}, 32-byte aligned
@@ -315,6 +316,18 @@ __device__ __forceinline__ void load_cell4(const double *cell, double &y1, doubl
 __device__ __forceinline__ void load_cell4_keep(const double *cell, double &y1, double &y2, double &y3, double &y4)
 {
    asm("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(y1), "=d"(y2), "=d"(y4), "=d"(y3) : "l"(cell));
+}
+__device__ __forceinline__ void load_geo4_keep(const double *rec, double &ux, double &uy, double &uz, double &w)
+{
+   asm volatile("ld.global.L1::no_allocate.L2::evict_last.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(ux), "=d"(uy), "=d"(uz), "=d"(w) : "l"(rec) : "memory");
+}
+__device__ __forceinline__ void load_geo4_plain(const double *rec, double &ux, double &uy, double &uz, double &w)
+{
+   asm volatile("ld.global.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(ux), "=d"(uy), "=d"(uz), "=d"(w) : "l"(rec) : "memory");
+}
+__device__ __forceinline__ void load_cell4_stream(const double *cell, double &y1, double &y2, double &y3, double &y4)
+{
+   asm("ld.global.nc.L1::no_allocate.L2::evict_first.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(y1), "=d"(y2), "=d"(y4), "=d"(y3) : "l"(cell));
 }
 // one geometry record: streamed once per rotational sweep, must not displace the table in L2
 __device__ __forceinline__ void load_geo4(const double *rec, double &ux, double &uy, double &uz, double &w)

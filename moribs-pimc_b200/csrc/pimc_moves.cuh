@@ -1014,7 +1014,10 @@ __device__ __forceinline__ double geo_evaln(const Params &p, const SmallTables &
    }
    double y1[NB], y2[NB], y3[NB], y4[NB];
    if (p.cell4_on) {
-      if (p.cell_hint) {
+      if (p.cell_hint == 2) {
+         #pragma unroll
+         for (int u = 0; u < NB; u++) load_cell4_stream(p.cell4 + 4 * (size_t)(ib[u] + ic[u]), y1[u], y2[u], y3[u], y4[u]);
+      } else if (p.cell_hint) {
          #pragma unroll
          for (int u = 0; u < NB; u++) load_cell4_keep(p.cell4 + 4 * (size_t)(ib[u] + ic[u]), y1[u], y2[u], y3[u], y4[u]);
       } else {
@@ -1063,7 +1066,9 @@ __device__ __forceinline__ void rot_potential_cached(const Params &p, Ctx &x, in
          const int k = k0 + u * G;
          ok[u] = k < n;
          const int kk = ok[u] ? k : k0;                 // masked slots repeat the first item of the batch (a valid look-up)
-         load_geo4(gb + 4 * (size_t)kk, ux[u], uy[u], uz[u], dr[u]);
+         if (p.geo_hint == 1) load_geo4_keep(gb + 4 * (size_t)kk, ux[u], uy[u], uz[u], dr[u]);
+         else if (p.geo_hint == 2) load_geo4_plain(gb + 4 * (size_t)kk, ux[u], uy[u], uz[u], dr[u]);
+         else load_geo4(gb + 4 * (size_t)kk, ux[u], uy[u], uz[u], dr[u]);
       }
       #pragma unroll
       for (int u = 0; u < NB; u++) {

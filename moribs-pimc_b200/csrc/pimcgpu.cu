@@ -574,6 +574,7 @@ int pimcgpu_init(const pimcgpu_system *sys, const pimcgpu_tables *tab)
    }
    // geometry cache of the rotor-atom terms (rot_potential_cached): one linear rotor among atoms, pipelined sweep, no worm
    p.geo_on = 0;
+   p.geo_hint = getenv("PIMC_GEO_HINT") ? atoi(getenv("PIMC_GEO_HINT")) : 0;
    if (p.rot_fused && p.imtype >= 0 && p.molecule[p.imtype] == 1 && !p.worm_on && !p.minimage && p.N > 1 && p.rs2d > 0 && p.rs2d < 4096 && !getenv("PIMC_NO_GEO")) {
       p.geo_items = p.R * (p.N - 1);
       p.geo_n = (p.geo_items + 31) / 32 * 32;
