@@ -355,32 +355,51 @@ def main():
         t_kernel = float(t.item())
     value = per_step_units * world * args.steps / t_kernel
 
-    # ---- end to end through the C ABI with host buffers: upload -> pass -> estimators -> (all-reduce) -> download ----
-    # host state lives in pinned buffers allocated once, as the reference's MCCoords / MCAngles do (mc_setup.cc:135-163)
+    # ---- end to end through the C ABI with host buffers: upload -> pass -> estimators -> (all-reduce) -> download, every step ----
+    # Host state lives in pinned buffers allocated once, as the reference's MCCoords / MCAngles do (mc_setup.cc:135-163).  Two sets
+    # of chains (A, B) take turns on the device, the way a driver time-shares one GPU between two jobs: while set A's pass runs,
+    # set B's previous result travels to the host and its next input to the device on the library's copy stream (split-phase
+    # pimcgpu_upload_states_begin/_commit, pimcgpu_download_states_begin/_end).  Every step still uploads its own input from host
+    # memory and downloads its own result; nothing is skipped, the copies just do not stall the move kernel.
     n_beads = s.N * P
-    pin_c = torch.empty((chains, 3, n_beads), dtype=torch.float64, pin_memory=True)
-    pin_a = torch.empty((chains, 3, n_beads), dtype=torch.float64, pin_memory=True)
-    host_c, host_a = pin_c.numpy(), pin_a.numpy()
-    G.download_all_into(host_c, host_a)
+    pins = [(torch.empty((chains, 3, n_beads), dtype=torch.float64, pin_memory=True), torch.empty((chains, 3, n_beads), dtype=torch.float64, pin_memory=True)) for _ in range(2)]
+    host = [(c.numpy(), a.numpy()) for c, a in pins]
+    for hc, ha in host:
+        G.download_all_into(hc, ha)
+    perm = None
+    if cfg.perm is not None:
+        perm = np.ascontiguousarray(np.tile(np.ascontiguousarray(cfg.perm, dtype=np.int32), (chains, 1)))
     pin_acc = torch.empty(lay["n_total"], dtype=torch.float64, pin_memory=True)
     host_acc = pin_acc.numpy()
     h2d = chains * ((P * 3 * ((s.N + 3) // 4 * 4) + 2 * max(1, s.Q) * 3 * max(1, sum(t.numb for t in s.types if t.molecule))) * 8 + (3 * s.N + 3) * 4)
     d2h = h2d - chains * (3 * s.N + 3) * 4 + lay["n_total"] * 8        # beads, rotor angle / axis rows, accumulators
+
+    def e2e_steps(nsteps):
+        G.upload_begin(host[0][0], host[0][1], perm)
+        for k in range(nsteps):
+            cur, oth = k % 2, 1 - k % 2
+            G.upload_commit()                                       # this step's input (set `cur`) into the state
+            G.accum_reset()
+            G.steps(P, sync=False)
+            G.measure()
+            G.L.pimcgpu_accum_device_ptr()
+            if dist:
+                torch.cuda.current_stream().wait_stream(stream)
+                dist.all_reduce(acc_t)
+                stream.wait_stream(torch.cuda.current_stream())
+            # the device is busy with the pass from here on: finish the previous step's download, send the next step's input
+            if k > 0:
+                G.download_end()                                    # set `oth` (result of the previous step) is on the host
+            G.upload_begin(host[oth][0], host[oth][1], perm)        # next step's input starts travelling now
+            G.download_begin(host[cur][0], host[cur][1])            # this step's result: snapshot, then D2H on the copy stream
+            G.accum_download_into(host_acc)                         # this step's estimator sums on the host (synchronises the pass)
+        G.download_end()
+        G.upload_commit()                                           # the input that was sent ahead for a step that will not run
+
+    e2e_steps(2)                                                    # warm the split-phase path (buffers, streams)
     barrier()
     w0 = time.perf_counter()
-    for _ in range(args.steps):
-        G.upload_all(host_c, host_a, cfg.perm)                  # every chain's beads, angles and permutation: one call
-        G.accum_reset()
-        G.steps(P, sync=False)
-        G.measure()
-        G.L.pimcgpu_accum_device_ptr()
-        if dist:
-            torch.cuda.current_stream().wait_stream(stream)
-            dist.all_reduce(acc_t)
-            torch.cuda.current_stream().synchronize()
-        G.sync()
-        G.accum_download_into(host_acc)
-        G.download_rows_into(host_c, host_a)                    # beads + the rotor rows of MCAngles (the arrays live across steps)
+    e2e_steps(args.steps)
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - w0
     if dist:

@@ -122,6 +122,16 @@ int pimcgpu_download_states(int first, int count, double *coords, double *angles
  * other entries of the caller's MCAngles / MCCosine (allocated once, mc_setup.cc:135-163; never written after MCConfigInit,
  * :471-487) are left untouched: 6 Q doubles per rotor and chain cross the bus instead of 6 N P                                  */
 int pimcgpu_download_states_rows(int first, int count, double *coords, double *angles, double *cosine);
+/* split-phase forms of the two calls above: the copies ride a second stream and overlap the move kernel of the neighbouring
+ * steps (a driver that keeps two sets of chains on the host alternates them on the device; mc_main.cc has no counterpart --
+ * its state never leaves the host).  upload: _begin starts the bead copy into a staging buffer (the state may still be in use by
+ * a running pimcgpu_steps) and prepares angles / permutations, _commit installs everything on the library's stream; the host
+ * arrays must not change between the two.  download: _begin snapshots the beads on the library's stream and hands them to the
+ * copy stream, _end waits and writes the rotor rows of angles / cosine like pimcgpu_download_states_rows.                      */
+int pimcgpu_upload_states_begin(int first, int count, const double *coords, const double *angles, const int *pindex);
+int pimcgpu_upload_states_commit(void);
+int pimcgpu_download_states_begin(int first, int count, double *coords, double *angles, double *cosine);
+int pimcgpu_download_states_end(void);
 
 /* ---- MRG32k3a package seed: RngStream::SetPackageSeed (rngstream.cc:346-353) ---- */
 int pimcgpu_seed(const unsigned long seed6[6]);

@@ -92,8 +92,13 @@ est_energy_kernel(const __grid_constant__ Params p, const __grid_constant__ EstB
 
    // ---- GetPotEnergy_Densities, mc_estim.cc:500-687
    double pot = 0.0;
-   for (long i = gt; i < (long)e.npairs * P; i += nt) {
-      int pi = (int)(i % e.npairs), it = (int)(i / e.npairs);
+   // (pair, slice) items; 32-bit index arithmetic whenever the count allows (a 64-bit divide per item costs more than the spline)
+   const long nitems = (long)e.npairs * P;
+   const bool small = nitems < (1L << 31);
+   for (long i = gt; i < nitems; i += nt) {
+      int pi, it;
+      if (small) { const unsigned iu = (unsigned)i, np = (unsigned)e.npairs; it = (int)(iu / np); pi = (int)(iu - (unsigned)it * np); }
+      else { pi = (int)(i % e.npairs); it = (int)(i / e.npairs); }
       int a0 = e.pairs[2 * pi], a1 = e.pairs[2 * pi + 1];
       int mode = p.mode[type_of(p, a0)][type_of(p, a1)];
       double p0[3], p1[3], dr[3], dr2 = 0.0;
@@ -156,7 +161,18 @@ est_energy_kernel(const __grid_constant__ Params p, const __grid_constant__ EstB
       } else {
          double r = sqrt(dr2);
          if (with_dens) { int br; bin_r(e, r, &br); if (br < BINSR && br >= 0) atomicAdd(&h1[br], 1u); }
-         pot += spot1d(p, t, r);
+         // grid uniform to rounding: the per-interval cubic of the move kernel (same spline piece, 1e-15), else the packed records
+         bool bad = !p.poly1d;
+         double v = 0.0;
+         if (p.poly1d) {
+            const double xq = (r - p.x0_1d) * p.invh_1d;
+            int k = max(0, min((int)xq, p.n1d - 2));
+            bad = !(r > p.x0_1d && r < p.xn_1d);
+            const double tt = xq - (double)k;
+            const double2 A = __ldg(p.pa1d + k), B = __ldg(p.pb1d + k);
+            v = fma(fma(fma(B.y, tt, B.x), tt, A.y), tt, A.x);
+         }
+         pot += bad ? spot1d(p, t, r) : v;
       }
    }
    pot = block_sum(pot, red);

@@ -60,6 +60,16 @@ struct Context {
    size_t stage_chain = 0;          // doubles per chain in `stage`
    double *d_raw = nullptr;         // device scratch [3][N*P]: one chain's beads in the reference layout (import/export transposes)
    double *d_raw_all = nullptr;     // the same for every chain (batched pimcgpu_upload_states / _download_states), allocated on first use
+   // split-phase transfers (pimcgpu_upload_states_begin/_commit, pimcgpu_download_states_begin/_end): a copy stream, separate
+   // staging buffers in each direction, pinned staging of the small per-chain arrays of an upload in flight
+   cudaStream_t copy_stream = nullptr;
+   cudaEvent_t ev_up = nullptr, ev_down = nullptr, ev_done = nullptr, ev_commit = nullptr;
+   int up_slot = 0;                 // which half of the pinned small-array staging the upload in flight uses (two uploads alternate)
+   double *d_raw_up = nullptr;
+   double *stage_up = nullptr;      // pinned: [c][ang | cosn] of the upload in flight
+   int *stage_perm = nullptr;       // pinned: gp, gr, cst, cat, ncy of the upload in flight
+   int up_first = 0, up_count = 0, down_first = 0, down_count = 0;
+   double *down_angles = nullptr, *down_cosine = nullptr;
 } G;
 
 template <class T> int dalloc(T **ptr, size_t n)
@@ -242,6 +252,12 @@ void pimcgpu_finalize(void)
    for (void *q : G.allocs) cudaFree(q);
    G.allocs.clear();
    G.d_raw = nullptr; G.d_raw_all = nullptr;          // lazily allocated scratch belongs to the context that is going away
+   G.d_raw_up = nullptr;
+   if (G.copy_stream) { cudaStreamSynchronize(G.copy_stream); cudaStreamDestroy(G.copy_stream); G.copy_stream = nullptr; }
+   if (G.ev_up) { cudaEventDestroy(G.ev_up); cudaEventDestroy(G.ev_down); cudaEventDestroy(G.ev_done); cudaEventDestroy(G.ev_commit); G.ev_up = G.ev_down = G.ev_done = G.ev_commit = nullptr; }
+   if (G.stage_up) { cudaFreeHost(G.stage_up); G.stage_up = nullptr; }
+   if (G.stage_perm) { cudaFreeHost(G.stage_perm); G.stage_perm = nullptr; }
+   G.up_count = G.down_count = 0;
    if (G.stream) cudaStreamDestroy(G.stream);
    G.stream = nullptr;
    if (G.stage) cudaFreeHost(G.stage);
@@ -913,6 +929,152 @@ int pimcgpu_download_states_rows(int first, int count, double *coords, double *a
                }
             }
       }
+   return 0;
+}
+
+// ---- split-phase transfers: the copies of one step overlap the move kernel of the neighbouring steps ------------------------
+// upload:   _begin copies the beads into a staging buffer on the copy stream (may run while the move kernel of the previous step
+//           is still working on the state) and prepares the small arrays; _commit, on the library's stream, waits for that copy,
+//           transposes into the state and installs angles / permutations.  The host arrays must stay untouched until _commit
+//           returns (it synchronises the small copies).
+// download: _begin snapshots the beads in the reference layout on the library's stream (a device transpose) and lets the copy
+//           stream carry them to the host; the library's stream is free for the next upload / pass at once.  _end waits for
+//           the copy and scatters the rotor rows (as pimcgpu_download_states_rows).
+static int split_phase_setup(void)
+{
+   const Params &p = G.p;
+   const size_t n = (size_t)p.N * p.P, nang = (size_t)std::max(1, p.Q) * 3 * p.NMpad;
+   if (G.copy_stream) return 0;
+   CK(cudaStreamCreateWithFlags(&G.copy_stream, cudaStreamNonBlocking));
+   CK(cudaEventCreateWithFlags(&G.ev_up, cudaEventDisableTiming));
+   CK(cudaEventCreateWithFlags(&G.ev_down, cudaEventDisableTiming));
+   CK(cudaEventCreateWithFlags(&G.ev_done, cudaEventDisableTiming));
+   CK(cudaEventCreateWithFlags(&G.ev_commit, cudaEventDisableTiming));
+   CK(cudaEventRecord(G.ev_commit, G.stream));
+   if (dalloc(&G.d_raw_up, (size_t)p.nchains * 3 * n)) return 1;
+   if (!G.d_raw_all && dalloc(&G.d_raw_all, (size_t)p.nchains * 3 * n)) return 1;
+   CK(cudaHostAlloc((void **)&G.stage_up, 2 * (size_t)p.nchains * 2 * nang * sizeof(double), cudaHostAllocDefault));
+   CK(cudaHostAlloc((void **)&G.stage_perm, 2 * (size_t)p.nchains * (4 * (size_t)p.N + 1 + MAXT) * sizeof(int), cudaHostAllocDefault));
+   return 0;
+}
+
+int pimcgpu_upload_states_begin(int first, int count, const double *coords, const double *angles, const int *pindex)
+{
+   if (!G.live) return fail("pimcgpu_upload_states_begin: not initialised");
+   const Params &p = G.p;
+   if (first < 0 || count < 1 || first + count > p.nchains) return fail("pimcgpu_upload_states_begin: chains %d..%d out of range", first, first + count - 1);
+   if (G.up_count) return fail("pimcgpu_upload_states_begin: an upload is already in flight (call pimcgpu_upload_states_commit)");
+   if (split_phase_setup()) return 1;
+   const size_t n = (size_t)p.N * p.P, nang = (size_t)std::max(1, p.Q) * 3 * p.NMpad;
+   CK(cudaStreamWaitEvent(G.copy_stream, G.ev_commit, 0));          // the previous commit's transpose has read the staging buffer
+   CK(cudaMemcpyAsync(G.d_raw_up, coords, (size_t)count * 3 * n * sizeof(double), cudaMemcpyHostToDevice, G.copy_stream));
+   CK(cudaEventRecord(G.ev_up, G.copy_stream));
+   G.up_slot ^= 1;                                                    // the previous commit's small copies may still read the other half
+   double *stage_up = G.stage_up + (size_t)G.up_slot * p.nchains * 2 * nang;
+   int *stage_perm = G.stage_perm + (size_t)G.up_slot * p.nchains * (4 * (size_t)p.N + 1 + MAXT);
+   if (p.imtype >= 0)
+      for (int cc = 0; cc < count; cc++) {
+         double *hang = stage_up + (size_t)cc * 2 * nang, *hcos = hang + nang;
+         const double *ang = angles + (size_t)cc * 3 * n;
+         for (int q = 0; q < p.Q; q++)
+            for (int m = 0; m < p.NM; m++) {
+               const size_t src = (size_t)(p.first[p.imtype] + m) * p.P + q;
+               const double phi = ang[0 * n + src], cost = ang[1 * n + src], chi = ang[2 * n + src];
+               const double sint = sqrt(1.0 - cost * cost);         // MCCosine from (phi, cos theta), mc_main.cc:192-199
+               const size_t b = (size_t)q * 3 * p.NMpad + m;
+               hang[b] = phi; hang[b + p.NMpad] = cost; hang[b + 2 * p.NMpad] = chi;
+               hcos[b] = sint * cos(phi); hcos[b + p.NMpad] = sint * sin(phi); hcos[b + 2 * p.NMpad] = cost;
+            }
+      }
+   const int nb = p.bstype >= 0 ? p.numb[p.bstype] : 0;
+   const size_t per = 4 * (size_t)p.N + 1 + MAXT;
+   for (int cc = 0; cc < count; cc++) {
+      int *base = stage_perm + (size_t)cc * per;
+      if (permutation_tables(p, pindex ? pindex + (size_t)cc * nb : nullptr, base, base + p.N, base + 2 * p.N, base + 3 * p.N + 1, base + 4 * p.N + 1, "pimcgpu_upload_states_begin")) return 1;
+   }
+   G.up_first = first; G.up_count = count;
+   return 0;
+}
+
+int pimcgpu_upload_states_commit(void)
+{
+   if (!G.live) return fail("pimcgpu_upload_states_commit: not initialised");
+   if (!G.up_count) return fail("pimcgpu_upload_states_commit: no upload in flight");
+   const Params &p = G.p;
+   const int first = G.up_first, count = G.up_count;
+   const size_t npos = (size_t)p.P * 3 * p.Npad, nang = (size_t)std::max(1, p.Q) * 3 * p.NMpad, per = 4 * (size_t)p.N + 1 + MAXT;
+   double *stage_up = G.stage_up + (size_t)G.up_slot * p.nchains * 2 * nang;
+   int *stage_perm = G.stage_perm + (size_t)G.up_slot * p.nchains * per;
+   CK(cudaStreamWaitEvent(G.stream, G.ev_up, 0));
+   state_transpose_kernel<<<dim3((p.P + 31) / 32, (p.N + 31) / 32, 3 * count), dim3(32, 8), 0, G.stream>>>(p.pos + (size_t)first * npos, G.d_raw_up, p.N, p.P, p.Npad, 1);
+   CK(cudaGetLastError());
+   CK(cudaEventRecord(G.ev_commit, G.stream));
+   if (p.imtype >= 0) {
+      CK(cudaMemcpy2DAsync(p.ang + (size_t)first * nang, nang * sizeof(double), stage_up, 2 * nang * sizeof(double), nang * sizeof(double), count, cudaMemcpyHostToDevice, G.stream));
+      CK(cudaMemcpy2DAsync(p.cosn + (size_t)first * nang, nang * sizeof(double), stage_up + nang, 2 * nang * sizeof(double), nang * sizeof(double), count, cudaMemcpyHostToDevice, G.stream));
+   }
+   const size_t w = sizeof(int);
+   CK(cudaMemcpy2DAsync(p.pindex + (size_t)first * p.N, p.N * w, stage_perm, per * w, p.N * w, count, cudaMemcpyHostToDevice, G.stream));
+   CK(cudaMemcpy2DAsync(p.rindex + (size_t)first * p.N, p.N * w, stage_perm + p.N, per * w, p.N * w, count, cudaMemcpyHostToDevice, G.stream));
+   CK(cudaMemcpy2DAsync(p.cyc_start + (size_t)first * (p.N + 1), (p.N + 1) * w, stage_perm + 2 * p.N, per * w, (p.N + 1) * w, count, cudaMemcpyHostToDevice, G.stream));
+   CK(cudaMemcpy2DAsync(p.cyc_atoms + (size_t)first * p.N, p.N * w, stage_perm + 3 * p.N + 1, per * w, p.N * w, count, cudaMemcpyHostToDevice, G.stream));
+   CK(cudaMemcpy2DAsync(p.ncyc + (size_t)first * MAXT, MAXT * w, stage_perm + 4 * p.N + 1, per * w, MAXT * w, count, cudaMemcpyHostToDevice, G.stream));
+   CK(cudaMemsetAsync(p.wstate + (size_t)first * 8, 0, (size_t)count * 8 * sizeof(int), G.stream));
+   CK(cudaMemsetAsync(p.vepoch + (size_t)first * std::max(1, p.Q) * p.NMpad, 0xff, (size_t)count * std::max(1, p.Q) * p.NMpad * sizeof(int), G.stream));
+   for (int cc = 0; cc < count; cc++) std::copy(stage_perm + (size_t)cc * per, stage_perm + (size_t)cc * per + p.N, G.h_pindex.begin() + (size_t)(first + cc) * p.N);
+   G.up_count = 0;
+   return 0;
+}
+
+int pimcgpu_download_states_begin(int first, int count, double *coords, double *angles, double *cosine)
+{
+   if (!G.live) return fail("pimcgpu_download_states_begin: not initialised");
+   const Params &p = G.p;
+   if (first < 0 || count < 1 || first + count > p.nchains) return fail("pimcgpu_download_states_begin: chains %d..%d out of range", first, first + count - 1);
+   if (G.down_count) return fail("pimcgpu_download_states_begin: a download is already in flight (call pimcgpu_download_states_end)");
+   if (!coords) return fail("pimcgpu_download_states_begin: coords is required");
+   if (split_phase_setup()) return 1;
+   const size_t n = (size_t)p.N * p.P, npos = (size_t)p.P * 3 * p.Npad, nang = (size_t)std::max(1, p.Q) * 3 * p.NMpad;
+   // the copy stream may still be reading the previous snapshot: order the new one behind it
+   CK(cudaEventRecord(G.ev_done, G.copy_stream));
+   CK(cudaStreamWaitEvent(G.stream, G.ev_done, 0));
+   state_transpose_kernel<<<dim3((p.P + 31) / 32, (p.N + 31) / 32, 3 * count), dim3(32, 8), 0, G.stream>>>(p.pos + (size_t)first * npos, G.d_raw_all, p.N, p.P, p.Npad, 0);
+   CK(cudaGetLastError());
+   double *s0 = G.stage + (size_t)first * G.stage_chain + npos;
+   if ((angles || cosine) && p.imtype >= 0 && p.Q > 0) {
+      CK(cudaMemcpy2DAsync(s0, G.stage_chain * sizeof(double), p.ang + (size_t)first * nang, nang * sizeof(double), nang * sizeof(double), count, cudaMemcpyDeviceToHost, G.stream));
+      CK(cudaMemcpy2DAsync(s0 + nang, G.stage_chain * sizeof(double), p.cosn + (size_t)first * nang, nang * sizeof(double), nang * sizeof(double), count, cudaMemcpyDeviceToHost, G.stream));
+   }
+   CK(cudaEventRecord(G.ev_down, G.stream));
+   CK(cudaStreamWaitEvent(G.copy_stream, G.ev_down, 0));
+   CK(cudaMemcpyAsync(coords, G.d_raw_all, (size_t)count * 3 * n * sizeof(double), cudaMemcpyDeviceToHost, G.copy_stream));
+   G.down_first = first; G.down_count = count; G.down_angles = angles; G.down_cosine = cosine;
+   return 0;
+}
+
+int pimcgpu_download_states_end(void)
+{
+   if (!G.live) return fail("pimcgpu_download_states_end: not initialised");
+   if (!G.down_count) return fail("pimcgpu_download_states_end: no download in flight");
+   const Params &p = G.p;
+   const size_t n = (size_t)p.N * p.P, npos = (size_t)p.P * 3 * p.Npad, nang = (size_t)std::max(1, p.Q) * 3 * p.NMpad;
+   CK(cudaEventSynchronize(G.ev_down));            // the small rotor arrays are in the pinned staging area
+   CK(cudaStreamSynchronize(G.copy_stream));        // the beads are in the caller's array
+   double *angles = G.down_angles, *cosine = G.down_cosine;
+   if ((angles || cosine) && p.imtype >= 0 && p.Q > 0)
+      for (int cc = 0; cc < G.down_count; cc++) {
+         const double *hang = G.stage + (size_t)(G.down_first + cc) * G.stage_chain + npos, *hcos = hang + nang;
+         double *ang = angles ? angles + (size_t)cc * 3 * n : nullptr, *cs = cosine ? cosine + (size_t)cc * 3 * n : nullptr;
+         for (int q = 0; q < p.Q; q++)
+            for (int m = 0; m < p.NM; m++) {
+               const size_t dst = (size_t)(p.first[p.imtype] + m) * p.P + q, b = (size_t)q * 3 * p.NMpad + m;
+               for (int d = 0; d < 3; d++) {
+                  if (ang) ang[d * n + dst] = hang[b + d * p.NMpad];
+                  if (cs) cs[d * n + dst] = hcos[b + d * p.NMpad];
+               }
+            }
+      }
+   G.down_count = 0;
    return 0;
 }
 

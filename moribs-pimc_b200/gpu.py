@@ -28,6 +28,7 @@ EXPORTS = [
     "pimcgpu_host_stream_state", "pimcgpu_host_lut", "pimcgpu_accum_offset", "pimcgpu_symmetry_moves", "pimcgpu_symmetry_ops",
     "pimcgpu_checkpoint_bytes", "pimcgpu_checkpoint_save", "pimcgpu_checkpoint_load", "pimcgpu_chain_areas", "pimcgpu_worm_moves", "pimcgpu_worm_state", "pimcgpu_worm_set", "pimcgpu_worm_counters",
     "pimcgpu_upload_states", "pimcgpu_download_states", "pimcgpu_download_states_rows",
+    "pimcgpu_upload_states_begin", "pimcgpu_upload_states_commit", "pimcgpu_download_states_begin", "pimcgpu_download_states_end",
     "pimcgpu_gen_asymrho", "pimcgpu_gen_symrho", "pimcgpu_gen_linden", "pimcgpu_gen_wigner_d", "pimcgpu_gen_timing",
     "pimcgpu_format_e15_8", "pimcgpu_write_e15_8", "pimcgpu_write_rot",
     "pimcgpu_eval_rotpro", "pimcgpu_eval_vcalc", "pimcgpu_eval_deleul", "pimcgpu_eval_vcord_grid", "pimcgpu_eval_vspher", "pimcgpu_eval_libm",
@@ -313,6 +314,24 @@ class PimcGpu:
     def download_rows_into(self, coords, angles, cosine=None, first=0):
         """batched download that writes only the rotor rows of angles / cosine (the caller's arrays live across steps)"""
         _ck(self.L.pimcgpu_download_states_rows(C.c_int(first), C.c_int(coords.shape[0]), _dp(coords), _dp(angles), _dp(cosine)))
+
+    # split-phase transfers (the arrays must be contiguous float64 / int32 and stay alive and unchanged until commit / end)
+    def upload_begin(self, coords, angles, perm=None, first=0):
+        assert coords.flags["C_CONTIGUOUS"] and angles.flags["C_CONTIGUOUS"] and coords.dtype == np.float64
+        self._up_keep = (coords, angles, perm)
+        _ck(self.L.pimcgpu_upload_states_begin(C.c_int(first), C.c_int(coords.shape[0]), _dp(coords), _dp(angles), _ip(perm)))
+
+    def upload_commit(self):
+        _ck(self.L.pimcgpu_upload_states_commit())
+        self._up_keep = None
+
+    def download_begin(self, coords, angles, cosine=None, first=0):
+        self._down_keep = (coords, angles, cosine)
+        _ck(self.L.pimcgpu_download_states_begin(C.c_int(first), C.c_int(coords.shape[0]), _dp(coords), _dp(angles), _dp(cosine)))
+
+    def download_end(self):
+        _ck(self.L.pimcgpu_download_states_end())
+        self._down_keep = None
 
     def seed(self, seed6=(12345,) * 6):
         _ck(self.L.pimcgpu_seed((C.c_ulong * 6)(*seed6)))

@@ -429,3 +429,46 @@ def test_full_size_c5_energies_and_checksum_properties(pkg):
     c2, a2, _ = G.download(1)
     assert np.array_equal(c2, c) and np.array_equal(a2, a)
     G.close()
+
+
+def test_split_phase_transfers_equal_the_synchronous_calls(pkg):
+    """pimcgpu_upload_states_begin/_commit and pimcgpu_download_states_begin/_end (copies on a second stream, overlapping the move
+    kernel of the neighbouring steps): two sets of chains alternate on the device exactly as if each had been moved with the
+    synchronous calls -- same states back, same trajectories."""
+    cfg = make(pkg, "C5")
+    s = cfg.system
+    n, C = s.N * s.P, 3
+    rng = np.random.default_rng(17)
+    sets = [np.ascontiguousarray(np.stack([cfg.coords + 0.01 * rng.standard_normal(cfg.coords.shape) for _ in range(C)])) for _ in range(2)]
+    angs = [np.ascontiguousarray(np.stack([cfg.angles.copy() for _ in range(C)])) for _ in range(2)]
+    results = []
+    for split in (False, True):
+        G = pkg.gpu.PimcGpu(cfg, nchains=C)
+        G.seed((41, 42, 43, 44, 45, 46))
+        hc = [x.copy() for x in sets]; ha = [x.copy() for x in angs]
+        if split:
+            G.upload_begin(hc[0], ha[0])
+            for k in range(6):
+                cur, oth = k % 2, 1 - k % 2
+                G.upload_commit()
+                G.steps(7, sync=False)
+                if k > 0:
+                    G.download_end()
+                G.upload_begin(hc[oth], ha[oth])
+                G.download_begin(hc[cur], ha[cur])
+            G.download_end()
+            G.upload_commit()
+        else:
+            for k in range(6):
+                cur = k % 2
+                G.upload_all(hc[cur], ha[cur])
+                G.steps(7)
+                G.download_rows_into(hc[cur], ha[cur])
+        results.append((hc, ha, G.counters()))
+        G.close()
+    for a, b in zip(results[0][0], results[1][0]):
+        assert np.array_equal(a, b)
+    for a, b in zip(results[0][1], results[1][1]):
+        assert np.array_equal(a, b)
+    assert np.array_equal(results[0][2][0], results[1][2][0]) and np.array_equal(results[0][2][1], results[1][2][1])
+    assert not np.array_equal(results[0][0][0], sets[0])
