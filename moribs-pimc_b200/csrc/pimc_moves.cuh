@@ -53,6 +53,7 @@ struct RotSlot {
    double vnew, vold;         // potential sums of the proposed / current orientation (pipelined sweep)
    double cur[3];             // pipelined sweep: current (cost, phi, chi) of the owned slice, kept across time steps
    double vcache;             // pipelined sweep: cached potential sum of the current orientation ...
+   unsigned nbw[12];          // rot_run: the two neighbours' axes as received (2 x 3 doubles in 32-bit halves)
    int vep, epoch;            // ... the position epoch it belongs to, and the epoch seen by the current sweep
    int need_old, bad;
    int gep;                   // position epoch the geometry cache of this slice was filled at (-1: never)
@@ -1076,7 +1077,15 @@ __device__ __forceinline__ void rot_potential_cached(const Params &p, Ctx &x, in
          ib[u] = (int)(bits & 0xfffLL) * rowlen;        // row offset of the radial cell in the table
          dr[u] = __longlong_as_double(bits & ~0xfffLL);
       }
+#ifdef PIMC_TIMELINE
+      asm volatile("" ::"d"(dr[NB - 1]), "d"(ux[0]));
+      MARK(x, 30);
+#endif
       v0 += geo_evaln<NB>(p, x.t, cmin, a0, a1, a2, ux, uy, uz, dr, ib, ok);
+#ifdef PIMC_TIMELINE
+      asm volatile("" ::"d"(v0));
+      MARK(x, 31);
+#endif
       if (NO == 2) v1 += geo_evaln<NB>(p, x.t, cmin, b0, b1, b2, ux, uy, uz, dr, ib, ok);
    }
    vout[0] = v0;
@@ -1488,6 +1497,20 @@ __device__ __forceinline__ int owned_slice(const Params &p, const Ctx &x, int ls
 // count with release semantics; a waiting group polls its two neighbours with acquire loads and reads their axes from L2.
 // Draws, proposals and acceptance are those of rot_step / rot_sweep_pipe.
 // ---------------------------------------------------------------------------------------------
+// publishes the axis of a slice after `done` sweeps of this launch: six 64-bit words {done + 1 : 32 bits of the axis}.
+// Every word certifies its own payload (a 64-bit store is single-copy atomic), so neither side needs a fence; a reader
+// cannot see words of two versions because the publisher's next decision waits for that reader's.
+__device__ __forceinline__ void rot_ll_publish(unsigned long long *dst, const double *axis, int done)
+{
+   const unsigned long long tag = (unsigned long long)(unsigned)(done + 1) << 32;
+   #pragma unroll
+   for (int d = 0; d < 3; d++) {
+      const unsigned long long bits = (unsigned long long)__double_as_longlong(axis[d]);
+      asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(dst + 2 * d), "l"(tag | (bits & 0xffffffffULL)) : "memory");
+      asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(dst + 2 * d + 1), "l"(tag | (bits >> 32)) : "memory");
+   }
+}
+
 template <int KIND>
 __device__ void rot_run(const Params &p, Ctx &x, int type, int nrun, int *err)
 {
@@ -1500,7 +1523,10 @@ __device__ void rot_run(const Params &p, Ctx &x, int type, int nrun, int *err)
    int q0 = q - 1, q2 = q + 1;
    if (q0 < 0) q0 += Q;
    if (q2 >= Q) q2 -= Q;
-   int *fl = p.rot_flags + (size_t)c * Q;
+   unsigned long long *ll = p.rot_ll + (size_t)c * Q * 8;
+   // the geometry cache follows the positions: stale after a translational sweep (the slot's gep is set by the leader's
+   // first decision; the chain barrier between sweeps orders it with this read)
+   if (active && p.geo_on && sl->gep != p.pos_epoch[c]) geo_fill(p, x, g, q);
    if (active)
    for (int it = 0; it < nrun; it++) {
       const int n = x.rot_iter + it;                     // sweeps this slice has completed in this launch
@@ -1522,7 +1548,6 @@ __device__ void rot_run(const Params &p, Ctx &x, int type, int nrun, int *err)
       group_sync(x);
       double vnew = 0.0, vold = 0.0;
       if (p.geo_on) {
-         if (sl->gep != sl->epoch) geo_fill(p, x, g, q);
          double vv[2];
          if (sl->need_old) { rot_potential_cached<2>(p, x, q, sl->a, sl->b, vv); vnew = vv[0]; vold = vv[1]; }
          else { rot_potential_cached<1>(p, x, q, sl->a, nullptr, vv); vnew = vv[0]; }
@@ -1534,23 +1559,29 @@ __device__ void rot_run(const Params &p, Ctx &x, int type, int nrun, int *err)
       for (int o = gw >> 1; o > 0; o >>= 1) { vnew += __shfl_xor_sync(x.gmask, vnew, o); vold += __shfl_xor_sync(x.gmask, vold, o); }
       if (G > 32 && (x.tid & 31) == 0) { x.part[2 * (x.gl >> 5)] = vnew; x.part[2 * (x.gl >> 5) + 1] = vold; }
       MARK(x, 4);
-      // the two neighbours: odd slices wait for this sweep's even decisions, even slices for the previous sweep's odd ones
-      if (x.gl < 2) {
-         const int target = (q & 1) ? n + 1 : n;
-         const int *f = fl + (x.gl == 0 ? q0 : q2);
-         int v;
-         do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory"); } while (v < target);
+      // the two neighbours' axes: odd slices need this sweep's even decisions, even slices the previous sweep's odd ones.
+      // Twelve lanes poll one 64-bit word each (32 bits of payload under the publisher's sweep count): the payload is valid
+      // the moment its own tag is, one L2 round trip, no fence on either side.
+      {
+         const unsigned need = (unsigned)((q & 1) ? n + 1 : n) + 1u;
+         for (int w = x.gl; w < 12; w += G) {
+            const unsigned long long *src = ll + (size_t)(w < 6 ? q0 : q2) * 8 + (w < 6 ? w : w - 6);
+            unsigned long long v;
+            do { asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory"); } while ((unsigned)(v >> 32) < need);
+            sl->nbw[w] = (unsigned)v;
+         }
       }
       group_sync(x);
       MARK(x, 6);
-      // density factors rho(q0 -> cur), rho(cur -> q2), rho(q0 -> new), rho(new -> q2): neighbour axes from L2
+      // density factors rho(q0 -> cur), rho(cur -> q2), rho(q0 -> new), rho(new -> q2)
       if (x.gl < 4) {
-         const int i = x.gl, qq = (i == 0 || i == 2) ? q0 : q2;
+         const int i = x.gl;
          const double *mid = (i < 2) ? sl->b : sl->a;
+         const double *nbv = reinterpret_cast<const double *>(sl->nbw) + ((i == 0 || i == 2) ? 0 : 3);
          double dot = 0.0;
          #pragma unroll
          for (int d = 0; d < 3; d++) {
-            const double nb = __ldcg(p.cosn + ang_index(p, c, qq, d, m));
+            const double nb = nbv[d];
             dot += (i == 0 || i == 2) ? nb * mid[d] : mid[d] * nb;
          }
          sl->rho[i] = (p.rotden_type == 1) ? rsline(p, dot, nullptr) : srotdens(p, x.t, dot);
@@ -1570,16 +1601,16 @@ __device__ void rot_run(const Params &p, Ctx &x, int type, int nrun, int *err)
          sl->vcache = acc ? vnew : vold;
          sl->vep = sl->epoch;
          sl->gep = sl->epoch;
+         // hand the slice's axis to its neighbours first (rot_ll_publish): for a linear rotor the committed axis is the
+         // proposal's (same expressions, same inputs: sl->a), no second sincos / sqrt
+         rot_ll_publish(ll + (size_t)q * 8, acc ? sl->a : sl->b, n + 1);
          if (acc) {
-            // rot_commit for a linear rotor: the new axis is the proposal's (same expressions, same inputs: sl->a), so the
-            // hand-over to the neighbours does not wait for another sincos / sqrt
             p.ang[ang_index(p, c, q, 1, m)] = sl->cost;
             p.ang[ang_index(p, c, q, 0, m)] = sl->phi;
             #pragma unroll
             for (int d = 0; d < 3; d++) { const double nd = sl->a[d]; p.cosn[ang_index(p, c, q, d, m)] = nd; sl->b[d] = nd; }
             sl->cur[0] = sl->cost; sl->cur[1] = sl->phi; sl->cur[2] = sl->chi;
          }
-         asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(fl + q), "r"(n + 1) : "memory");
          atomicAdd(cn, 1.0);
          if (acc) atomicAdd(cn + 1, 1.0);
       }
@@ -1711,6 +1742,7 @@ pimc_steps_kernel(const __grid_constant__ Params p, long t0, long nsteps, int *e
          sl->vcache = p.vold[((size_t)x.c * p.Q + q) * p.NMpad];
          sl->vep = p.vepoch[((size_t)x.c * p.Q + q) * p.NMpad];
          sl->gep = -1;
+         if (((KIND & 7) == 1) && p.rot_run) rot_ll_publish(p.rot_ll + ((size_t)x.c * p.Q + q) * 8, sl->b, 0);
       }
       __syncthreads();
    } else x.slot = reinterpret_cast<RotSlot *>(cursor) + x.grp;      // one slot per rot group

@@ -585,7 +585,7 @@ int pimcgpu_init(const pimcgpu_system *sys, const pimcgpu_tables *tab)
    p.rot_run = 0;
    if (p.rot_fused && cpc > 1 && p.imtype == p.ntypes - 1 && p.molecule[p.imtype] == 1 && !p.worm_on && p.Q % cpc == 0 && p.Q / cpc <= threads / p.rot_group &&
        p.Q / cpc >= 2 && !getenv("PIMC_NO_ROT_RUN")) {
-      if (dalloc(&p.rot_flags, C * p.Q)) return 1;
+      if (dalloc(&p.rot_ll, C * p.Q * 8)) return 1;
       p.rot_run = 1;
    }
    // geometry cache of the rotor-atom terms (rot_potential_cached): one linear rotor among atoms, pipelined sweep, no worm
@@ -1127,7 +1127,7 @@ int pimcgpu_steps(long nsteps)
    cudaLaunchAttribute attr[1];
    launch_config(cfg, attr);
    CK(cudaMemsetAsync(G.p.barrier, 0, (size_t)G.p.nchains * 32 * sizeof(unsigned), G.stream));
-   if (G.p.rot_run) CK(cudaMemsetAsync(G.p.rot_flags, 0, (size_t)G.p.nchains * G.p.Q * sizeof(int), G.stream));
+   if (G.p.rot_run) CK(cudaMemsetAsync(G.p.rot_ll, 0, (size_t)G.p.nchains * G.p.Q * 8 * sizeof(unsigned long long), G.stream));
    void *args[4] = {(void *)&G.p, (void *)&G.step, (void *)&nsteps, (void *)&G.d_err};
    CK(cudaLaunchKernelExC(&cfg, steps_kernel(G.kind, G.p.worm_on), args));
    G.step += nsteps;

@@ -17,7 +17,7 @@ G.steps(int(sys.argv[5]) if len(sys.argv) > 5 else 6)
 n = G.L.pimcgpu_timeline(buf, 4096)
 m = np.array(buf[:n], dtype=np.int64)
 ids, t = m >> 48, m & 0xffffffffffff
-names = {1: "rot sweep start", 2: "leader proposal done", 3: "after group sync", 4: "pair sums done (thread 0)", 5: "stage A done", 6: "after chain barrier",
+names = {30: "batch geometry arrived", 31: "batch gathers consumed", 1: "rot sweep start", 2: "leader proposal done", 3: "after group sync", 4: "pair sums done (thread 0)", 5: "stage A done", 6: "after chain barrier",
          7: "leader decision done", 8: "after sync#3", 9: "decisions done (CTA 0)", 10: "after chain barrier",
          20: "bisect: segment start", 21: "normals drawn", 22: "level pair sums done", 23: "level accept done", 24: "segment end", 25: "after chain barrier"}
 prev = t[0]
