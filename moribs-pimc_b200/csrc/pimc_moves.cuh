@@ -34,8 +34,6 @@ namespace pimc {
 namespace cg = cooperative_groups;
 
 #ifdef PIMC_TIMELINE
-__device__ long long g_marks[4096];
-__device__ int g_nmarks;
 #define MARK(x, id) do { if ((x).gthread == 0 && (x).c == 0 && g_nmarks < 4000) { g_marks[g_nmarks++] = ((long long)(id) << 48) | (clock64() & 0xffffffffffffLL); } } while (0)
 #else
 #define MARK(x, id) do { } while (0)
@@ -1801,7 +1799,8 @@ pimc_steps_kernel(const __grid_constant__ Params p, long t0, long nsteps, int *e
          bool closed = true;
          if ((KIND & 4) && p.worm_on && type == p.worm_type) {
             // mc_main.cc:355-379: MCWormMove, then the path moves of this type in the Z sector only
-            if (x.crank == 0) worm_sweep_cta<KIND>(p, x.t, x.c, x.red, worm_scr);
+            // one CTA per chain holds the current rotation matrix of every slice in its rot slots
+            if (x.crank == 0) worm_sweep_cta<KIND>(p, x.t, x.c, x.red, worm_scr, (piped && p.cpc == 1 && (KIND & 3) == 2) ? x.slot[0].b : nullptr, sizeof(RotSlot));
             chain_sync(p, x);
             closed = p.wstate[(size_t)x.c * 8] == 0;
          }

@@ -10,6 +10,17 @@
 #pragma once
 #include "pimc_device.cuh"
 
+// clock64 timeline of chain 0 / thread 0 (profiles/timeline.py; builds with -DPIMC_TIMELINE only)
+#ifdef PIMC_TIMELINE
+namespace pimc {
+__device__ long long g_marks[4096];
+__device__ int g_nmarks;
+}
+#define WMARK(c, id) do { if (threadIdx.x == 0 && (c) == 0 && g_nmarks < 4000) { g_marks[g_nmarks++] = ((long long)(id) << 48) | (clock64() & 0xffffffffffffLL); } } while (0)
+#else
+#define WMARK(c, id) do { } while (0)
+#endif
+
 namespace pimc {
 
 constexpr int QW_OPEN = 0, QW_CLOSE = 1, QW_ADVANCE = 4, QW_RECEDE = 5, QW_SWAP = 6;     // mc_qworm.h:58-64
@@ -54,6 +65,7 @@ struct WormShared {
    // the recursion of sample_middle as a node list in its own pre-order (worm_bridge_plan): points relative to the left end
    short nd_it0[WORM_MAXM + 1], nd_it1[WORM_MAXM + 1], nd_it2[WORM_MAXM + 1], nd_depth[WORM_MAXM + 1];
    int nnodes, ndepth, gi0;
+   int pl_it0, pl_it2;                   // the bridge to lay out (worm_bridge_fill): end points, pl_it2 - pl_it0 < 2: none
    double gs[3 * (WORM_MAXM + 1)];       // sqrt(-log u1) cos(2 pi u2), still to be divided by sqrt(alpha)
 };
 
@@ -61,14 +73,18 @@ struct WormShared {
 // the moving atom's beads from the state (use_path = 0) or from the proposed path; diff = 1 subtracts the same sum for the
 // beads of the state (qworm_swap, mc_qworm.cc:479-489).  All threads of the CTA; returns the total to every thread.
 template <int KIND>
-__device__ double worm_pot_sum(const Params &p, const SmallTables &t, int c, const WormShared &w, double *red)
+__device__ double worm_pot_sum(const Params &p, const SmallTables &t, int c, const WormShared &w, double *red, int &flip,
+                               const double *slot_b, size_t slot_stride)
 {
    const int P = p.P, N = p.N, base = p.first[p.worm_type];
    const int it0 = w.it0, it1 = w.it1, nint = it1 - it0 - 1;
    const int pit0 = it0 % P;
+   const int nv = w.diff ? 2 : 1;                         // swap: the proposed path (v = 0) minus the state (v = 1), one thread each
    double s = 0.0;
-   for (int i = threadIdx.x; i < nint * N; i += blockDim.x) {
-      const int k = i / N, j = i - k * N;
+   for (int i = threadIdx.x; i < nv * nint * N; i += blockDim.x) {
+      // the slice runs fastest: the lanes of a warp share the partner, hence the branch of the pair term
+      const int vj = i / nint, k = i - vj * nint;
+      const int v = vj / N, j = vj - v * N;
       const int it = it0 + 1 + k, pit = it % P;
       int atom = w.atom0;
       if (w.diff) { if (pit != it) atom = w.atom1; }                       // qworm_swap switches on the wrap alone
@@ -77,24 +93,34 @@ __device__ double worm_pot_sum(const Params &p, const SmallTables &t, int c, con
       if (j == g) continue;
       // the mask uses the worm as it stands in shared memory (the open move evaluates with exists = 0)
       if (w.st[0] && type_of(p, j) == p.worm_type && !worm_world_line(w.st, j - base, pit)) continue;
-      double pn[3], po[3];
+      double px[3];
       #pragma unroll
-      for (int d = 0; d < 3; d++) {
-         po[d] = p.pos[pos_index(p, c, pit, d, g)];
-         pn[d] = w.use_path ? w.path[(it - it0) * 3 + d] : po[d];
-      }
-      s += pair_energy<(KIND & 3)>(p, t, c, g, pn, j, pit, nullptr, nullptr);
-      if (w.diff) s -= pair_energy<(KIND & 3)>(p, t, c, g, po, j, pit, nullptr, nullptr);
+      for (int d = 0; d < 3; d++) px[d] = (w.use_path && v == 0) ? w.path[(it - it0) * 3 + d] : p.pos[pos_index(p, c, pit, d, g)];
+      double e;
+      if ((KIND & 3) == 2 && slot_b && p.mode[type_of(p, g)][type_of(p, j)] == M_TOP_1MOL) {
+         // the top's rotation matrix of this slice from the CTA's rot slot (what load_rotmat would rebuild with an acos and
+         // three sincos from the stored angles: the slot holds matpre of exactly those)
+         const double *rb = reinterpret_cast<const double *>(reinterpret_cast<const char *>(slot_b) + (size_t)(pit / p.R) * slot_stride);
+         Mat3 rm;
+         #pragma unroll
+         for (int q = 0; q < 9; q++) rm.m[q / 3][q % 3] = rb[q];
+         double p1[3];
+         #pragma unroll
+         for (int d = 0; d < 3; d++) p1[d] = p.pos[pos_index(p, c, pit, d, j)];
+         e = vcord(p, rm, p1, px, nullptr, nullptr);
+      } else e = pair_energy<(KIND & 3)>(p, t, c, g, px, j, pit, nullptr, nullptr);
+      s += v ? -e : e;
    }
-   // fixed-order block reduction
+   // fixed-order block reduction; the two halves of red[] alternate between calls, so one barrier per call is enough (a
+   // half is rewritten two calls later, behind the barrier of the call in between)
    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
    const int warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-   __syncthreads();
-   if ((threadIdx.x & 31) == 0) red[warp] = s;
+   double *r = red + 16 * (flip & 1);
+   flip ^= 1;
+   if ((threadIdx.x & 31) == 0) r[warp] = s;
    __syncthreads();
    double tot = 0.0;
-   for (int k = 0; k < nwarp; k++) tot += red[k];
-   __syncthreads();
+   for (int k = 0; k < nwarp; k++) tot += r[k];
    return tot;
 }
 
@@ -105,6 +131,19 @@ __device__ __forceinline__ int w_nrnd(Mrg &g, int n) { return (int)floor(n * mrg
 // arithmetic), draws its two uniforms and evaluates the transcendental part of gauss (mc_randg.cc:138-150); thread 0 then
 // continues with the state behind the last draw and consumes gs[] in program order -- same draws, same operations, same bits
 // as the sequential form, without its ~600 cycles of dependent latency per number on the thread that carries the control flow.
+// the parallel part: w.ng and w.gstate[0] published by a barrier before, gs[] and gstate[1] by one after
+__device__ __forceinline__ void worm_gauss_fill(const Params &p, WormShared &w)
+{
+   const int ng = w.ng;
+   for (int k = threadIdx.x; k < ng; k += blockDim.x) {
+      Mrg h;
+      mrg_load(h, w.gstate[0]);
+      mrg_jump(h, p.worm_jump + (size_t)k * 18);
+      const double u1 = mrg_u01(h), u2 = mrg_u01(h);
+      w.gs[k] = sqrt(-log(u1)) * cos(2.0 * PI * u2);
+      if (k == ng - 1) mrg_store(h, w.gstate[1]);
+   }
+}
 __device__ __forceinline__ void worm_gauss_batch(const Params &p, WormShared &w, Mrg &g)
 {
    if (threadIdx.x == 0) mrg_store(g, w.gstate[0]);
@@ -123,59 +162,84 @@ __device__ __forceinline__ void worm_gauss_batch(const Params &p, WormShared &w,
    if (threadIdx.x == 0) mrg_load(g, w.gstate[1]);
 }
 
-// sample_middle, mc_qworm.cc:240-287: the recursion (midpoint it1 = rint((it0 + it2)/2), left half first) is laid out by
-// thread 0 as a node list in its own pre-order -- node k consumes the gaussians gi0 + 3k .. gi0 + 3k + 2 exactly as the
-// recursive form does -- and then filled level by level by all threads: nodes of one depth only depend on shallower ones.
-// The bridge lives in path[] (point index = it - it0r), both end points already in place.
-__device__ void worm_bridge_plan(WormShared &w, int it0r, int it2r, int gi0)
+// sample_middle, mc_qworm.cc:240-287: the recursion (midpoint it1 = rint((it0 + it2)/2), left half first) samples every
+// interior point of the bridge exactly once, so a segment of length L holds L - 1 nodes and, in the recursion's own
+// pre-order, the left child of node k is node k + 1 and the right child node k + (it1 - it0).  Node k consumes the
+// gaussians gi0 + 3k .. gi0 + 3k + 2 exactly as the recursive form does.  Thread 0 only names the end points
+// (worm_bridge_request); every interior point then finds its own node by walking down from the root (all threads), and
+// the first warp fills the bridge level by level -- nodes of one depth only depend on shallower ones.
+// The bridge lives in path[] (point index = it - pl_it0), both end points already in place.
+__device__ __forceinline__ void worm_bridge_request(WormShared &w, int it0r, int it2r, int gi0)
 {
-   int stk[16][3], sp = 0, n = 0, maxd = -1;
-   stk[sp][0] = it0r; stk[sp][1] = it2r; stk[sp][2] = 0; sp++;
-   while (sp > 0) {
-      sp--;
-      const int it0 = stk[sp][0], it2 = stk[sp][1], dep = stk[sp][2];
-      if ((it2 - it0) < 2) continue;
-      const int it1 = (int)rint(0.5 * (double)(it0 + it2));
-      w.nd_it0[n] = (short)(it0 - it0r); w.nd_it1[n] = (short)(it1 - it0r); w.nd_it2[n] = (short)(it2 - it0r); w.nd_depth[n] = (short)dep;
-      n++;
-      if (dep > maxd) maxd = dep;
-      // left half first, then the right half: push right, then left
-      stk[sp][0] = it1; stk[sp][1] = it2; stk[sp][2] = dep + 1; sp++;
-      stk[sp][0] = it0; stk[sp][1] = it1; stk[sp][2] = dep + 1; sp++;
-   }
-   w.nnodes = n; w.ndepth = maxd + 1; w.gi0 = gi0;
+   w.pl_it0 = it0r; w.pl_it2 = it2r; w.gi0 = gi0;
 }
-// all threads, after a barrier that published the plan, the end points and gs[]
+// all threads, after a barrier that published the request, the end points and gs[]
 __device__ __forceinline__ void worm_bridge_fill(const Params &p, WormShared &w)
 {
-   const int nn = w.nnodes, nd = w.ndepth, gi0 = w.gi0;
-   for (int dep = 0; dep < nd; dep++) {
-      for (int t = threadIdx.x; t < 3 * nn; t += blockDim.x) {
-         const int k = t / 3, d = t - 3 * k;
-         if (w.nd_depth[k] != dep) continue;
-         const int i0 = w.nd_it0[k], i1 = w.nd_it1[k], i2 = w.nd_it2[k];
-         const double s0 = (double)(i1 - i0), s2 = (double)(i2 - i1);
-         const double gkin = (s0 + s2) / (p.worm_twave2 * s0 * s2);
-         const double x0 = w.path[i0 * 3 + d], x2 = w.path[i2 * 3 + d];
-         double x1 = (s2 * x0 + s0 * x2) / (s0 + s2);
-         x1 += (w.gs[gi0 + 3 * k + d] / sqrt(gkin));
-         w.path[i1 * 3 + d] = x1;
+   const int it0r = w.pl_it0, L = w.pl_it2 - w.pl_it0, gi0 = w.gi0;
+   if (L < 2) return;
+   const int nn = L - 1;
+   for (int j = 1 + threadIdx.x; j < L; j += blockDim.x) {
+      int a = it0r, b = w.pl_it2, k = 0, dep = 0;
+      const int target = it0r + j;
+      for (;;) {
+         const int mid = (int)rint(0.5 * (double)(a + b));
+         if (mid == target) {
+            w.nd_it0[k] = (short)(a - it0r); w.nd_it1[k] = (short)j; w.nd_it2[k] = (short)(b - it0r); w.nd_depth[k] = (short)dep;
+            const double s0 = (double)(mid - a), s2 = (double)(b - mid);
+            const double gkin = (s0 + s2) / (p.worm_twave2 * s0 * s2);
+            const double sq = sqrt(gkin);
+            #pragma unroll
+            for (int d = 0; d < 3; d++) w.gs[gi0 + 3 * k + d] = w.gs[gi0 + 3 * k + d] / sq;      // the node's displacement
+            break;
+         }
+         if (target < mid) { b = mid; k += 1; }
+         else { k += mid - a; a = mid; }
+         dep++;
       }
-      __syncthreads();
    }
+   __syncthreads();
+   if (threadIdx.x < 32) {
+      int nd = 0;
+      for (int k = threadIdx.x; k < nn; k += 32) nd = max(nd, (int)w.nd_depth[k] + 1);
+      for (int o = 16; o > 0; o >>= 1) nd = max(nd, __shfl_xor_sync(0xffffffffu, nd, o));
+      for (int dep = 0; dep < nd; dep++) {
+         for (int k = threadIdx.x; k < nn; k += 32) {      // one lane per node, its three coordinates side by side
+            if (w.nd_depth[k] != dep) continue;
+            const int i0 = w.nd_it0[k], i1 = w.nd_it1[k], i2 = w.nd_it2[k];
+            const double s0 = (double)(i1 - i0), s2 = (double)(i2 - i1);
+            // a division by 2^n is the multiplication by 2^-n, bit for bit (no subnormals among coordinates): the levels of a
+            // bridge form a dependent chain, and a double-precision division is most of a level
+            const int len = i2 - i0;
+            const bool pow2 = (len & (len - 1)) == 0;
+            const double inv = __hiloint2double((1023 - (31 - __clz(len))) << 20, 0);
+            #pragma unroll
+            for (int d = 0; d < 3; d++) {
+               const double x0 = w.path[i0 * 3 + d], x2 = w.path[i2 * 3 + d];
+               const double num = s2 * x0 + s0 * x2;
+               double x1 = pow2 ? num * inv : num / (s0 + s2);
+               x1 += w.gs[gi0 + 3 * k + d];
+               w.path[i1 * 3 + d] = x1;
+            }
+         }
+         __syncwarp();
+      }
+   }
+   __syncthreads();
 }
 
 // get_ptable, mc_qworm.cc:577-643: neighbours of world line atomw at slice pt0 among the beads at slice pt1, sorted by
 // distance (mmsort, mc_utils.cc:206-231), weights exp(-dr^2 / (segm * 4 lambda tau)); entries 1..count.  All threads of the
 // CTA: one thread per candidate world line for the distances, thread 0 for the (order-preserving) compaction and the
 // insertion sort, one thread per entry for the weights.  `flag` is an int scratch of numb entries.
-__device__ int worm_get_ptable(const Params &p, int c, WormShared &w, int atomw, int pt0, int pt1, int segm, int t1,
-                               double *dr2_list, int *atm_list, double *ptable, int *flag)
+// worm_ptable_dist: the distances (no barrier; the LAST threads of the CTA take the candidates, so the phase can share a
+// stretch with work that is laid out from thread 0 upwards); worm_ptable_finish: the rest, behind a barrier.
+__device__ __forceinline__ void worm_ptable_dist(const Params &p, int c, const WormShared &w, int atomw, int pt0, int pt1, int t1, double *ptable, int *flag)
 {
    const int base = p.first[p.worm_type], numb = p.numb[p.worm_type];
    const int *rindex = p.rindex + (size_t)c * p.N;
    const int *st = w.st;
-   for (int atom1 = threadIdx.x; atom1 < numb; atom1 += blockDim.x) {
+   for (int atom1 = blockDim.x - 1 - threadIdx.x; atom1 < numb; atom1 += blockDim.x) {
       int ok = 0;
       double dr2 = 0.0;
       if (worm_world_line(st, atom1, pt1)) {
@@ -194,6 +258,10 @@ __device__ int worm_get_ptable(const Params &p, int c, WormShared &w, int atomw,
       flag[atom1] = ok;
       ptable[1 + atom1] = dr2;                          // candidate scratch until the weights are written
    }
+}
+__device__ int worm_ptable_finish(const Params &p, WormShared &w, int segm, double *dr2_list, int *atm_list, double *ptable, const int *flag)
+{
+   const int numb = p.numb[p.worm_type];
    __syncthreads();
    if (threadIdx.x == 0) {
       int count = 0;
@@ -215,6 +283,13 @@ __device__ int worm_get_ptable(const Params &p, int c, WormShared &w, int atomw,
    for (int ic = 1 + threadIdx.x; ic <= count; ic += blockDim.x) ptable[ic] = exp(-norm * dr2_list[ic]);
    __syncthreads();
    return count;
+}
+
+__device__ int worm_get_ptable(const Params &p, int c, WormShared &w, int atomw, int pt0, int pt1, int segm, int t1,
+                               double *dr2_list, int *atm_list, double *ptable, int *flag)
+{
+   worm_ptable_dist(p, c, w, atomw, pt0, pt1, t1, ptable, flag);
+   return worm_ptable_finish(p, w, segm, dr2_list, atm_list, ptable, flag);
 }
 
 // permutation cycles of every type from pindex (what pimcgpu_upload_state prepares on the host); thread 0 only
@@ -253,8 +328,10 @@ __device__ __forceinline__ void worm_write_back(const Params &p, int c, const Wo
 
 // MCWormMove, mc_qworm.cc:93-125, for chain c by the calling CTA.  `scratch` holds WormShared and the neighbour lists.
 template <int KIND>
-__device__ void worm_sweep_cta(const Params &p, const SmallTables &t, int c, double *red, unsigned char *scratch)
+__device__ void worm_sweep_cta(const Params &p, const SmallTables &t, int c, double *red, unsigned char *scratch,
+                               const double *slot_b = nullptr, size_t slot_stride = 0)
 {
+   int flip = 0;
    WormShared &w = *reinterpret_cast<WormShared *>(scratch);
    double *dr2_list = reinterpret_cast<double *>(scratch + ((sizeof(WormShared) + 15) & ~15));
    double *ptable = dr2_list + (p.N + 2);
@@ -275,6 +352,7 @@ __device__ void worm_sweep_cta(const Params &p, const SmallTables &t, int c, dou
    const bool bose_worm = p.bstype >= 0 && p.worm_type == p.bstype;
    for (int atom = 0; atom < numb; atom++) {
       // ---------------- open / close ----------------
+      WMARK(c, 40);
       int segm = 0, gi = 0;
       if (tid == 0) {
          w.ng = 0;
@@ -285,11 +363,12 @@ __device__ void worm_sweep_cta(const Params &p, const SmallTables &t, int c, dou
          }
       }
       worm_gauss_batch(p, w, g);
+      WMARK(c, 41);
       if (tid == 0) {
          qw[14] += 1.0;
          w.go = 0;
          w.wb = 0;
-         w.nnodes = 0; w.ndepth = 0;
+         w.pl_it0 = 0; w.pl_it2 = 0;
          if (w.st[0]) {                                     // qworm_close, mc_qworm.cc:184-238
             qw[QW_CLOSE] += 1.0;
             if (segm <= p.worm_m) {
@@ -300,7 +379,7 @@ __device__ void worm_sweep_cta(const Params &p, const SmallTables &t, int c, dou
                   w.path[d] = p.pos[pos_index(p, c, w.st[1], d, base + w.st[3])];
                   w.path[segm * 3 + d] = p.pos[pos_index(p, c, w.st[2], d, base + w.st[4])];
                }
-               worm_bridge_plan(w, w.st[1], w.st[1] + segm, 0);
+               worm_bridge_request(w, w.st[1], w.st[1] + segm, 0);
                w.wb = 1;
                w.go = 1;
             }
@@ -317,13 +396,16 @@ __device__ void worm_sweep_cta(const Params &p, const SmallTables &t, int c, dou
          w.it0 = w.st[1]; w.it1 = w.st[1] + segm; w.atom0 = w.st[3]; w.atom1 = w.st[4]; w.use_path = 0; w.diff = 0;
       }
       __syncthreads();
+      WMARK(c, 42);
       if (w.go) {
          worm_bridge_fill(p, w);
+         WMARK(c, 43);
          worm_write_back(p, c, w);
-         // qw_open_prob, mc_qworm.cc:127-153
-         const double pot = worm_pot_sum<KIND>(p, t, c, w, red);
+         WMARK(c, 44);
+         // qw_open_prob, mc_qworm.cc:127-153; the end-to-end distance does not depend on the sum (the beads between moved,
+         // the two ends did not): its loads go out first
+         double kin = 0.0;
          if (tid == 0) {
-            double kin = 0.0;
             #pragma unroll
             for (int d = 0; d < 3; d++) {
                double dr = p.pos[pos_index(p, c, w.st[1], d, base + w.st[3])] - p.pos[pos_index(p, c, w.st[2], d, base + w.st[4])];
@@ -331,6 +413,10 @@ __device__ void worm_sweep_cta(const Params &p, const SmallTables &t, int c, dou
                kin += (dr * dr);
             }
             kin /= (p.worm_twave2 * (double)segm);
+         }
+         const double pot = worm_pot_sum<KIND>(p, t, c, w, red, flip, slot_b, slot_stride);
+         WMARK(c, 45);
+         if (tid == 0) {
             const double popen = p.worm_norm * pow((double)segm, 0.5 * 3.0) * exp(kin + pot * p.tau);
             const double prob = w.st[0] ? 1.0 / popen : popen;
             bool acc = false;
@@ -344,6 +430,7 @@ __device__ void worm_sweep_cta(const Params &p, const SmallTables &t, int c, dou
          }
       }
       __syncthreads();
+      WMARK(c, 46);
       // ---------------- advance / recede ----------------
       if (w.st[0]) {                                        // block-uniform: w.st is shared and only thread 0 writes it between barriers
          double r = 0.0;
@@ -360,11 +447,12 @@ __device__ void worm_sweep_cta(const Params &p, const SmallTables &t, int c, dou
             }
          }
          worm_gauss_batch(p, w, g);
+         WMARK(c, 47);
          if (tid == 0) {
             qw[14] += 1.0;
             w.go = 0;
             w.wb = 0;
-            w.nnodes = 0; w.ndepth = 0;
+            w.pl_it0 = 0; w.pl_it2 = 0;
             if (r > 0.5) {                                  // qworm_advance, mc_qworm.cc:299-357
                qw[QW_ADVANCE] += 1.0;
                const int advance = steps;
@@ -380,7 +468,7 @@ __device__ void worm_sweep_cta(const Params &p, const SmallTables &t, int c, dou
                      w.path[d] = p.pos[pos_index(p, c, it0 % P, d, base + w.st[3])];
                      w.path[advance * 3 + d] = w.path[d] + (w.gs[gi++] / sqrt(gvar));          // the new head
                   }
-                  worm_bridge_plan(w, it0, it2, gi);
+                  worm_bridge_request(w, it0, it2, gi);
                   w.it0 = it0; w.it1 = it2 + 1; w.atom0 = w.st[3]; w.atom1 = atom_i_new; w.use_path = 0; w.diff = 0;
                   w.wb = 1;
                   w.go = 1;
@@ -401,10 +489,14 @@ __device__ void worm_sweep_cta(const Params &p, const SmallTables &t, int c, dou
             }
          }
          __syncthreads();
+         WMARK(c, 48);
          if (w.go) {
             worm_bridge_fill(p, w);
+            WMARK(c, 49);
             worm_write_back(p, c, w);
-            const double pot = worm_pot_sum<KIND>(p, t, c, w, red);
+            WMARK(c, 50);
+            const double pot = worm_pot_sum<KIND>(p, t, c, w, red, flip, slot_b, slot_stride);
+            WMARK(c, 51);
             if (tid == 0) {
                bool acc = false;
                if (w.go == 1) {
@@ -419,27 +511,40 @@ __device__ void worm_sweep_cta(const Params &p, const SmallTables &t, int c, dou
             }
          }
          __syncthreads();
+         WMARK(c, 52);
       }
       // ---------------- swap (qworm_swap, mc_qworm.cc:424-551) ----------------
       if (bose_worm) {
          if (tid == 0) qw[14] += 1.0;
          if (w.st[0]) {
-            double pnorm_old = 0.0;
+            double pnorm_old = 0.0, u_swap = 0.0;
             int sw_atom0 = -1, sw_atom1 = -1;
             int count;
+            // A non-empty table draws ONE uniform (atom2swap), and a chosen partner then the gaussians of a bridge of fixed
+            // length: both are drawn ahead, next to the table's distance loads, and handed back if the move stops earlier.
+            Mrg g_before;
+            if (tid == 0) {
+               g_before = g;
+               u_swap = mrg_u01(g);
+               w.ng = (p.worm_m >= 2) ? 3 * (p.worm_m - 1) : 0;
+               mrg_store(g, w.gstate[0]);
+            }
+            __syncthreads();
+            worm_gauss_fill(p, w);
             {
                const int sg = p.worm_m, it0 = w.st[1], it1 = it0 + sg;
                count = worm_get_ptable(p, c, w, w.st[3], it0, it1 % P, sg, it1, dr2_list, atm_list, ptable, seen);
             }
+            WMARK(c, 53);
             if (tid == 0) {
                qw[QW_SWAP] += 1.0;
                w.go = 0;
-               w.ng = 0;
                const int sg = p.worm_m, it0 = w.st[1], it1 = it0 + sg, pit0 = it0, pit1 = it1 % P, atomw = w.st[3];
+               if (count == 0) g = g_before;              // nothing was drawn
                if (count > 0) {
                   // atom2swap, mc_qworm.cc:645-667
                   for (int ic = 1; ic <= count; ic++) pnorm_old += ptable[ic];
-                  const double prand = pnorm_old * mrg_u01(g);
+                  const double prand = pnorm_old * u_swap;
                   double sum = 0.0;
                   int ic = 1;
                   while ((ic <= count) && (sum < prand)) { sum += ptable[ic]; ic++; }
@@ -454,22 +559,26 @@ __device__ void worm_sweep_cta(const Params &p, const SmallTables &t, int c, dou
                         w.path[sg * 3 + d] = p.pos[pos_index(p, c, pit1, d, base + atom1)];
                      }
                      sw_atom0 = atom0; sw_atom1 = atom1;
-                     if (sg >= 2) w.ng = 3 * (sg - 1);
+                     if (sg >= 2) mrg_load(g, w.gstate[1]);      // the bridge's gaussians are consumed
                   }
                }
             }
-            worm_gauss_batch(p, w, g);
+            WMARK(c, 55);
             if (tid == 0 && sw_atom1 >= 0) {
                const int sg = p.worm_m, it0 = w.st[1], it1 = it0 + sg;
-               worm_bridge_plan(w, it0, it1, 0);
+               worm_bridge_request(w, it0, it1, 0);
                w.it0 = it0; w.it1 = it1; w.atom0 = sw_atom0; w.atom1 = sw_atom1; w.use_path = 1; w.diff = 1;
                w.go = 1;
             }
             __syncthreads();
+            WMARK(c, 56);
             if (w.go) {
                worm_bridge_fill(p, w);
-               const double pot = worm_pot_sum<KIND>(p, t, c, w, red);
-               const int count2 = worm_get_ptable(p, c, w, w.atom0, w.it0, w.it1 % P, p.worm_m, w.it1, dr2_list, atm_list, ptable, seen);
+               WMARK(c, 57);
+               worm_ptable_dist(p, c, w, w.atom0, w.it0, w.it1 % P, w.it1, ptable, seen);      // the reverse move's table: its loads fly during the sum
+               const double pot = worm_pot_sum<KIND>(p, t, c, w, red, flip, slot_b, slot_stride);
+               WMARK(c, 58);
+               const int count2 = worm_ptable_finish(p, w, p.worm_m, dr2_list, atm_list, ptable, seen);
                if (tid == 0) {
                   double prob = exp(-pot * p.tau);
                   const int count = count2;
@@ -482,6 +591,7 @@ __device__ void worm_sweep_cta(const Params &p, const SmallTables &t, int c, dou
                   w.go = acc ? 1 : 0;
                }
                __syncthreads();
+               WMARK(c, 59);
                if (w.go) {
                   const int it0 = w.it0, it1 = w.it1, atom0 = w.atom0, atom1 = w.atom1, atomw = w.st[3];
                   // the proposed beads replace the state's between it0 and it1 ...
@@ -511,6 +621,7 @@ __device__ void worm_sweep_cta(const Params &p, const SmallTables &t, int c, dou
                }
             }
             __syncthreads();
+            WMARK(c, 61);
          }
       }
    }

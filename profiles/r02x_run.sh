@@ -1,3 +1,5 @@
 #!/bin/bash
-for gh in 0 1 2; do for ch in 1 2; do echo "GEO_HINT=$gh CELL_HINT=$ch"; PIMC_GEO_HINT=$gh PIMC_CELL_HINT=$ch timeout 300 python profiles/stage_times.py C5 8 2>&1 | tail -2 | head -1; done; done
-timeout 300 python -m pytest tests/test_gpu_parity.py -q -m gpu -x -k "trajectory or geometry or full_size" 2>&1 | tail -3
+timeout 600 python -m pytest tests/test_gpu_worm.py -q -m gpu -x 2>&1 | tail -3
+PROF_WORM=1 TL_WORKLOAD=C2 TL_CHAINS=148 PIMCGPU_LIB=moribs-pimc_b200/csrc/libpimcgpu_tl.so timeout 200 python profiles/timeline.py 0 0 0 1029 2 400 > gpurun_out/r02x_worm_timeline.txt 2>&1
+PROF_WORM=1 timeout 200 python profiles/prof_run.py C2 148 512 512 2>&1 | tail -1
+PROF_WORM=1 timeout 200 python profiles/prof_run.py C3 148 1024 1024 2>&1 | tail -1
