@@ -374,34 +374,51 @@ def main():
     h2d = chains * ((P * 3 * ((s.N + 3) // 4 * 4) + 2 * max(1, s.Q) * 3 * max(1, sum(t.numb for t in s.types if t.molecule))) * 8 + (3 * s.N + 3) * 4)
     d2h = h2d - chains * (3 * s.N + 3) * 4 + lay["n_total"] * 8        # beads, rotor angle / axis rows, accumulators
 
+    trace = {} if os.environ.get("PIMC_E2E_TRACE") else None       # host wall time per call of the loop (rank 0, stderr)
+
+    def timed(name, fn, *a):
+        if trace is None:
+            return fn(*a)
+        t0 = time.perf_counter()
+        r = fn(*a)
+        trace[name] = trace.get(name, 0.0) + time.perf_counter() - t0
+        return r
+
     def e2e_steps(nsteps):
         G.upload_begin(host[0][0], host[0][1], perm)
         for k in range(nsteps):
             cur, oth = k % 2, 1 - k % 2
-            G.upload_commit()                                       # this step's input (set `cur`) into the state
-            G.accum_reset()
-            G.steps(P, sync=False)
-            G.measure()
+            timed("upload_commit", G.upload_commit)                 # this step's input (set `cur`) into the state
+            timed("accum_reset", G.accum_reset)
+            timed("steps", G.steps, P, False)
+            timed("measure", G.measure)
             G.L.pimcgpu_accum_device_ptr()
             if dist:
-                torch.cuda.current_stream().wait_stream(stream)
-                dist.all_reduce(acc_t)
-                stream.wait_stream(torch.cuda.current_stream())
+                def reduce_acc():
+                    torch.cuda.current_stream().wait_stream(stream)
+                    dist.all_reduce(acc_t)
+                    stream.wait_stream(torch.cuda.current_stream())
+                timed("all_reduce", reduce_acc)
+            timed("accum_begin", G.accum_download_begin, host_acc)  # the step's sums travel first, ahead of its configuration
             # the device is busy with the pass from here on: finish the previous step's download, send the next step's input
             if k > 0:
-                G.download_end()                                    # set `oth` (result of the previous step) is on the host
-            G.upload_begin(host[oth][0], host[oth][1], perm)        # next step's input starts travelling now
-            G.download_begin(host[cur][0], host[cur][1])            # this step's result: snapshot, then D2H on the copy stream
-            G.accum_download_into(host_acc)                         # this step's estimator sums on the host (synchronises the pass)
+                timed("download_end", G.download_end)               # set `oth` (result of the previous step) is on the host
+            timed("upload_begin", G.upload_begin, host[oth][0], host[oth][1], perm)     # next step's input starts travelling now
+            timed("download_begin", G.download_begin, host[cur][0], host[cur][1])       # this step's result: snapshot, then D2H on the copy stream
+            timed("accum_end", G.accum_download_end)                                    # this step's estimator sums are on the host (synchronises the pass)
         G.download_end()
         G.upload_commit()                                           # the input that was sent ahead for a step that will not run
 
     e2e_steps(2)                                                    # warm the split-phase path (buffers, streams)
+    if trace is not None:
+        trace.clear()
     barrier()
     w0 = time.perf_counter()
     e2e_steps(args.steps)
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - w0
+    if trace is not None:
+        print(f"[e2e trace rank {rank}] ms per step: " + json.dumps({k: round(1e3 * v / args.steps, 3) for k, v in trace.items()}) + f" total {1e3 * t_e2e / args.steps:.3f}", file=sys.stderr)
     if dist:
         t = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -154,6 +154,11 @@ int    pimcgpu_accum_layout(long *n_total, long *off_scalars, long *off_gr1d, lo
                             long *off_rcf, long *off_relbins);
 void  *pimcgpu_accum_device_ptr(void);
 int    pimcgpu_accum_download(double *host, long n);
+/* the same in two halves: _begin queues the copy on the library's stream (host should be pinned), _end waits for it.
+ * Queued before pimcgpu_download_states_begin, the block's sums (what SaveEnergy etc. need, mc_main.cc:700-760) reach
+ * the host ahead of the much larger configuration.                                             */
+int    pimcgpu_accum_download_begin(double *host, long n);
+int    pimcgpu_accum_download_end(void);
 int    pimcgpu_accum_reset(void);                  /* MCResetBlockAverage, mc_main.cc:524-549  */
 int    pimcgpu_block_scalars(pimcgpu_scalars *out);/* reads the (possibly all-reduced) buffer  */
 int    pimcgpu_counters(double *mctotal, double *mcaccep);   /* [types][3], MCTotal/MCAccep    */

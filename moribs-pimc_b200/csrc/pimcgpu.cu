@@ -63,9 +63,11 @@ struct Context {
    // split-phase transfers (pimcgpu_upload_states_begin/_commit, pimcgpu_download_states_begin/_end): a copy stream, separate
    // staging buffers in each direction, pinned staging of the small per-chain arrays of an upload in flight
    cudaStream_t copy_stream = nullptr;
-   cudaEvent_t ev_up = nullptr, ev_down = nullptr, ev_done = nullptr, ev_commit = nullptr;
+   cudaEvent_t ev_up = nullptr, ev_down = nullptr, ev_done = nullptr, ev_commit = nullptr, ev_acc = nullptr;
    int up_slot = 0;                 // which half of the pinned small-array staging the upload in flight uses (two uploads alternate)
    double *d_raw_up = nullptr;
+   double *d_small_up = nullptr, *d_small_down = nullptr;      // device staging of the rotor rows (split-phase upload / download)
+   int *d_perm_up = nullptr;                                   // ... and of the permutation tables
    double *stage_up = nullptr;      // pinned: [c][ang | cosn] of the upload in flight
    int *stage_perm = nullptr;       // pinned: gp, gr, cst, cat, ncy of the upload in flight
    int up_first = 0, up_count = 0, down_first = 0, down_count = 0;
@@ -252,8 +254,9 @@ void pimcgpu_finalize(void)
    for (void *q : G.allocs) cudaFree(q);
    G.allocs.clear();
    G.d_raw = nullptr; G.d_raw_all = nullptr;          // lazily allocated scratch belongs to the context that is going away
-   G.d_raw_up = nullptr;
+   G.d_raw_up = nullptr; G.d_small_up = nullptr; G.d_small_down = nullptr; G.d_perm_up = nullptr;
    if (G.copy_stream) { cudaStreamSynchronize(G.copy_stream); cudaStreamDestroy(G.copy_stream); G.copy_stream = nullptr; }
+   if (G.ev_acc) { cudaEventDestroy(G.ev_acc); G.ev_acc = nullptr; }
    if (G.ev_up) { cudaEventDestroy(G.ev_up); cudaEventDestroy(G.ev_down); cudaEventDestroy(G.ev_done); cudaEventDestroy(G.ev_commit); G.ev_up = G.ev_down = G.ev_done = G.ev_commit = nullptr; }
    if (G.stage_up) { cudaFreeHost(G.stage_up); G.stage_up = nullptr; }
    if (G.stage_perm) { cudaFreeHost(G.stage_perm); G.stage_perm = nullptr; }
@@ -637,6 +640,43 @@ int pimcgpu_init(const pimcgpu_system *sys, const pimcgpu_tables *tab)
 
 }  // extern "C"
 namespace {
+// The small arrays of a split-phase upload go from their device staging area into the state (angles, axes, permutation
+// tables, closed worm, stale potential cache): device work only, so a commit never queues behind a configuration that is
+// still travelling on a copy engine.
+__global__ void commit_small_kernel(Params p, int first, int count, const double *sd, const int *sp, int has_rot)
+{
+   const size_t nang = (size_t)max(1, p.Q) * 3 * p.NMpad, per = 4 * (size_t)p.N + 1 + MAXT, nve = (size_t)max(1, p.Q) * p.NMpad;
+   const size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+   if (has_rot)
+      for (size_t i = t0; i < (size_t)count * nang; i += stride) {
+         const size_t cc = i / nang, k = i - cc * nang;
+         p.ang[(first + cc) * nang + k] = sd[cc * 2 * nang + k];
+         p.cosn[(first + cc) * nang + k] = sd[cc * 2 * nang + nang + k];
+      }
+   const size_t N = (size_t)p.N;
+   for (size_t i = t0; i < (size_t)count * per; i += stride) {
+      const size_t cc = i / per, k = i - cc * per, c = first + cc;
+      const int v = sp[i];
+      if (k < N) p.pindex[c * N + k] = v;
+      else if (k < 2 * N) p.rindex[c * N + (k - N)] = v;
+      else if (k < 3 * N + 1) p.cyc_start[c * (N + 1) + (k - 2 * N)] = v;
+      else if (k < 4 * N + 1) p.cyc_atoms[c * N + (k - 3 * N - 1)] = v;
+      else p.ncyc[c * MAXT + (k - 4 * N - 1)] = v;
+   }
+   for (size_t i = t0; i < (size_t)count * 8; i += stride) p.wstate[(size_t)first * 8 + i] = 0;
+   for (size_t i = t0; i < (size_t)count * nve; i += stride) p.vepoch[(size_t)first * nve + i] = -1;
+}
+// the rotor rows of a split-phase download into their device staging area ([chain][angles | axes])
+__global__ void snapshot_small_kernel(Params p, int first, int count, double *sd)
+{
+   const size_t nang = (size_t)max(1, p.Q) * 3 * p.NMpad;
+   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)count * nang; i += (size_t)gridDim.x * blockDim.x) {
+      const size_t cc = i / nang, k = i - cc * nang;
+      sd[cc * 2 * nang + k] = p.ang[(first + cc) * nang + k];
+      sd[cc * 2 * nang + nang + k] = p.cosn[(first + cc) * nang + k];
+   }
+}
+
 // Beads between the reference layout raw[d][atom*P + it] (mc_setup.cc:139-148) and the device layout pos[it][d][Npad]:
 // a tiled transpose through shared memory, both sides coalesced.  to_device != 0 imports, else exports.
 __global__ void state_transpose_kernel(double *pos, double *raw, int N, int P, int Npad, int to_device)
@@ -933,13 +973,15 @@ int pimcgpu_download_states_rows(int first, int count, double *coords, double *a
 }
 
 // ---- split-phase transfers: the copies of one step overlap the move kernel of the neighbouring steps ------------------------
-// upload:   _begin copies the beads into a staging buffer on the copy stream (may run while the move kernel of the previous step
-//           is still working on the state) and prepares the small arrays; _commit, on the library's stream, waits for that copy,
-//           transposes into the state and installs angles / permutations.  The host arrays must stay untouched until _commit
-//           returns (it synchronises the small copies).
-// download: _begin snapshots the beads in the reference layout on the library's stream (a device transpose) and lets the copy
-//           stream carry them to the host; the library's stream is free for the next upload / pass at once.  _end waits for
-//           the copy and scatters the rotor rows (as pimcgpu_download_states_rows).
+// upload:   _begin copies the beads, then the prepared small arrays (angles, axes, permutation tables), into device staging
+//           buffers on the copy stream (may run while the move kernel of the previous step is still working on the state);
+//           _commit, on the library's stream, waits for those copies and moves everything into the state with two kernels --
+//           no copy-engine work on the library's stream, so a commit never queues behind a configuration still travelling.
+//           The caller's bead array must stay untouched until the copy stream has read it (pimcgpu_upload_states_commit
+//           followed by any synchronising call, or the next _begin).
+// download: _begin snapshots the beads in the reference layout and the rotor rows on the library's stream (device kernels)
+//           and lets the copy stream carry them to the host; the library's stream is free for the next upload / pass at
+//           once.  _end waits for the copies and scatters the rotor rows (as pimcgpu_download_states_rows).
 static int split_phase_setup(void)
 {
    const Params &p = G.p;
@@ -952,6 +994,8 @@ static int split_phase_setup(void)
    CK(cudaEventCreateWithFlags(&G.ev_commit, cudaEventDisableTiming));
    CK(cudaEventRecord(G.ev_commit, G.stream));
    if (dalloc(&G.d_raw_up, (size_t)p.nchains * 3 * n)) return 1;
+   if (dalloc(&G.d_small_up, (size_t)p.nchains * 2 * nang) || dalloc(&G.d_small_down, (size_t)p.nchains * 2 * nang)) return 1;
+   if (dalloc(&G.d_perm_up, (size_t)p.nchains * (4 * (size_t)p.N + 1 + MAXT))) return 1;
    if (!G.d_raw_all && dalloc(&G.d_raw_all, (size_t)p.nchains * 3 * n)) return 1;
    CK(cudaHostAlloc((void **)&G.stage_up, 2 * (size_t)p.nchains * 2 * nang * sizeof(double), cudaHostAllocDefault));
    CK(cudaHostAlloc((void **)&G.stage_perm, 2 * (size_t)p.nchains * (4 * (size_t)p.N + 1 + MAXT) * sizeof(int), cudaHostAllocDefault));
@@ -966,10 +1010,10 @@ int pimcgpu_upload_states_begin(int first, int count, const double *coords, cons
    if (G.up_count) return fail("pimcgpu_upload_states_begin: an upload is already in flight (call pimcgpu_upload_states_commit)");
    if (split_phase_setup()) return 1;
    const size_t n = (size_t)p.N * p.P, nang = (size_t)std::max(1, p.Q) * 3 * p.NMpad;
-   CK(cudaStreamWaitEvent(G.copy_stream, G.ev_commit, 0));          // the previous commit's transpose has read the staging buffer
+   CK(cudaEventSynchronize(G.ev_up));                                 // the copies of the upload before last have left their pinned staging half
+   CK(cudaStreamWaitEvent(G.copy_stream, G.ev_commit, 0));          // the previous commit has read the device staging buffers
    CK(cudaMemcpyAsync(G.d_raw_up, coords, (size_t)count * 3 * n * sizeof(double), cudaMemcpyHostToDevice, G.copy_stream));
-   CK(cudaEventRecord(G.ev_up, G.copy_stream));
-   G.up_slot ^= 1;                                                    // the previous commit's small copies may still read the other half
+   G.up_slot ^= 1;                                                    // the previous upload's small copies read the other half
    double *stage_up = G.stage_up + (size_t)G.up_slot * p.nchains * 2 * nang;
    int *stage_perm = G.stage_perm + (size_t)G.up_slot * p.nchains * (4 * (size_t)p.N + 1 + MAXT);
    if (p.imtype >= 0)
@@ -992,6 +1036,10 @@ int pimcgpu_upload_states_begin(int first, int count, const double *coords, cons
       int *base = stage_perm + (size_t)cc * per;
       if (permutation_tables(p, pindex ? pindex + (size_t)cc * nb : nullptr, base, base + p.N, base + 2 * p.N, base + 3 * p.N + 1, base + 4 * p.N + 1, "pimcgpu_upload_states_begin")) return 1;
    }
+   // the small arrays follow the beads on the copy stream, into device staging: the commit is device work only
+   if (p.imtype >= 0) CK(cudaMemcpyAsync(G.d_small_up, stage_up, (size_t)count * 2 * nang * sizeof(double), cudaMemcpyHostToDevice, G.copy_stream));
+   CK(cudaMemcpyAsync(G.d_perm_up, stage_perm, (size_t)count * per * sizeof(int), cudaMemcpyHostToDevice, G.copy_stream));
+   CK(cudaEventRecord(G.ev_up, G.copy_stream));
    G.up_first = first; G.up_count = count;
    return 0;
 }
@@ -1003,24 +1051,13 @@ int pimcgpu_upload_states_commit(void)
    const Params &p = G.p;
    const int first = G.up_first, count = G.up_count;
    const size_t npos = (size_t)p.P * 3 * p.Npad, nang = (size_t)std::max(1, p.Q) * 3 * p.NMpad, per = 4 * (size_t)p.N + 1 + MAXT;
-   double *stage_up = G.stage_up + (size_t)G.up_slot * p.nchains * 2 * nang;
    int *stage_perm = G.stage_perm + (size_t)G.up_slot * p.nchains * per;
    CK(cudaStreamWaitEvent(G.stream, G.ev_up, 0));
    state_transpose_kernel<<<dim3((p.P + 31) / 32, (p.N + 31) / 32, 3 * count), dim3(32, 8), 0, G.stream>>>(p.pos + (size_t)first * npos, G.d_raw_up, p.N, p.P, p.Npad, 1);
    CK(cudaGetLastError());
+   commit_small_kernel<<<64, 256, 0, G.stream>>>(p, first, count, G.d_small_up, G.d_perm_up, p.imtype >= 0 ? 1 : 0);
+   CK(cudaGetLastError());
    CK(cudaEventRecord(G.ev_commit, G.stream));
-   if (p.imtype >= 0) {
-      CK(cudaMemcpy2DAsync(p.ang + (size_t)first * nang, nang * sizeof(double), stage_up, 2 * nang * sizeof(double), nang * sizeof(double), count, cudaMemcpyHostToDevice, G.stream));
-      CK(cudaMemcpy2DAsync(p.cosn + (size_t)first * nang, nang * sizeof(double), stage_up + nang, 2 * nang * sizeof(double), nang * sizeof(double), count, cudaMemcpyHostToDevice, G.stream));
-   }
-   const size_t w = sizeof(int);
-   CK(cudaMemcpy2DAsync(p.pindex + (size_t)first * p.N, p.N * w, stage_perm, per * w, p.N * w, count, cudaMemcpyHostToDevice, G.stream));
-   CK(cudaMemcpy2DAsync(p.rindex + (size_t)first * p.N, p.N * w, stage_perm + p.N, per * w, p.N * w, count, cudaMemcpyHostToDevice, G.stream));
-   CK(cudaMemcpy2DAsync(p.cyc_start + (size_t)first * (p.N + 1), (p.N + 1) * w, stage_perm + 2 * p.N, per * w, (p.N + 1) * w, count, cudaMemcpyHostToDevice, G.stream));
-   CK(cudaMemcpy2DAsync(p.cyc_atoms + (size_t)first * p.N, p.N * w, stage_perm + 3 * p.N + 1, per * w, p.N * w, count, cudaMemcpyHostToDevice, G.stream));
-   CK(cudaMemcpy2DAsync(p.ncyc + (size_t)first * MAXT, MAXT * w, stage_perm + 4 * p.N + 1, per * w, MAXT * w, count, cudaMemcpyHostToDevice, G.stream));
-   CK(cudaMemsetAsync(p.wstate + (size_t)first * 8, 0, (size_t)count * 8 * sizeof(int), G.stream));
-   CK(cudaMemsetAsync(p.vepoch + (size_t)first * std::max(1, p.Q) * p.NMpad, 0xff, (size_t)count * std::max(1, p.Q) * p.NMpad * sizeof(int), G.stream));
    for (int cc = 0; cc < count; cc++) std::copy(stage_perm + (size_t)cc * per, stage_perm + (size_t)cc * per + p.N, G.h_pindex.begin() + (size_t)(first + cc) * p.N);
    G.up_count = 0;
    return 0;
@@ -1041,12 +1078,15 @@ int pimcgpu_download_states_begin(int first, int count, double *coords, double *
    state_transpose_kernel<<<dim3((p.P + 31) / 32, (p.N + 31) / 32, 3 * count), dim3(32, 8), 0, G.stream>>>(p.pos + (size_t)first * npos, G.d_raw_all, p.N, p.P, p.Npad, 0);
    CK(cudaGetLastError());
    double *s0 = G.stage + (size_t)first * G.stage_chain + npos;
-   if ((angles || cosine) && p.imtype >= 0 && p.Q > 0) {
-      CK(cudaMemcpy2DAsync(s0, G.stage_chain * sizeof(double), p.ang + (size_t)first * nang, nang * sizeof(double), nang * sizeof(double), count, cudaMemcpyDeviceToHost, G.stream));
-      CK(cudaMemcpy2DAsync(s0 + nang, G.stage_chain * sizeof(double), p.cosn + (size_t)first * nang, nang * sizeof(double), nang * sizeof(double), count, cudaMemcpyDeviceToHost, G.stream));
+   const bool rows = (angles || cosine) && p.imtype >= 0 && p.Q > 0;
+   if (rows) {
+      snapshot_small_kernel<<<64, 256, 0, G.stream>>>(p, first, count, G.d_small_down);
+      CK(cudaGetLastError());
    }
    CK(cudaEventRecord(G.ev_down, G.stream));
    CK(cudaStreamWaitEvent(G.copy_stream, G.ev_down, 0));
+   // the rotor rows first (small), then the beads: both on the copy stream, nothing of it on the library's stream
+   if (rows) CK(cudaMemcpy2DAsync(s0, G.stage_chain * sizeof(double), G.d_small_down, 2 * nang * sizeof(double), 2 * nang * sizeof(double), count, cudaMemcpyDeviceToHost, G.copy_stream));
    CK(cudaMemcpyAsync(coords, G.d_raw_all, (size_t)count * 3 * n * sizeof(double), cudaMemcpyDeviceToHost, G.copy_stream));
    G.down_first = first; G.down_count = count; G.down_angles = angles; G.down_cosine = cosine;
    return 0;
@@ -1058,8 +1098,7 @@ int pimcgpu_download_states_end(void)
    if (!G.down_count) return fail("pimcgpu_download_states_end: no download in flight");
    const Params &p = G.p;
    const size_t n = (size_t)p.N * p.P, npos = (size_t)p.P * 3 * p.Npad, nang = (size_t)std::max(1, p.Q) * 3 * p.NMpad;
-   CK(cudaEventSynchronize(G.ev_down));            // the small rotor arrays are in the pinned staging area
-   CK(cudaStreamSynchronize(G.copy_stream));        // the beads are in the caller's array
+   CK(cudaStreamSynchronize(G.copy_stream));        // the rotor rows are in the pinned staging area, the beads in the caller's array
    double *angles = G.down_angles, *cosine = G.down_cosine;
    if ((angles || cosine) && p.imtype >= 0 && p.Q > 0)
       for (int cc = 0; cc < G.down_count; cc++) {
@@ -1379,6 +1418,24 @@ int pimcgpu_accum_download(double *host, long n)
    if (n > G.nacc) n = G.nacc;
    CK(cudaMemcpyAsync(host, G.e.acc, n * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
    CK(cudaStreamSynchronize(G.stream));
+   return 0;
+}
+// split form: the copy is queued behind what the stream holds now (the estimators, an all-reduce the caller ordered before
+// it), so a large transfer started afterwards -- pimcgpu_download_states_begin -- does not delay the small result
+int pimcgpu_accum_download_begin(double *host, long n)
+{
+   if (!G.live) return fail("pimcgpu_accum_download_begin: not initialised");
+   if (n > G.nacc) n = G.nacc;
+   if (!G.ev_acc) CK(cudaEventCreateWithFlags(&G.ev_acc, cudaEventDisableTiming));
+   CK(cudaMemcpyAsync(host, G.e.acc, n * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
+   CK(cudaEventRecord(G.ev_acc, G.stream));
+   return 0;
+}
+int pimcgpu_accum_download_end(void)
+{
+   if (!G.live) return fail("pimcgpu_accum_download_end: not initialised");
+   if (!G.ev_acc) return fail("pimcgpu_accum_download_end: no download in flight");
+   CK(cudaEventSynchronize(G.ev_acc));
    return 0;
 }
 int pimcgpu_accum_reset(void)

@@ -21,7 +21,7 @@ c_ip = C.POINTER(C.c_int)
 EXPORTS = [
     "pimcgpu_init", "pimcgpu_finalize", "pimcgpu_last_error", "pimcgpu_upload_state", "pimcgpu_download_state",
     "pimcgpu_seed", "pimcgpu_steps", "pimcgpu_sync", "pimcgpu_step_counter", "pimcgpu_geometry", "pimcgpu_measure", "pimcgpu_accum_layout",
-    "pimcgpu_accum_device_ptr", "pimcgpu_accum_download", "pimcgpu_accum_reset", "pimcgpu_block_scalars",
+    "pimcgpu_accum_device_ptr", "pimcgpu_accum_download", "pimcgpu_accum_download_begin", "pimcgpu_accum_download_end", "pimcgpu_accum_reset", "pimcgpu_block_scalars",
     "pimcgpu_counters", "pimcgpu_stream", "pimcgpu_chain_energies", "pimcgpu_chain_rcf", "pimcgpu_eval_spot1d",
     "pimcgpu_eval_lpot2d", "pimcgpu_eval_srotdens", "pimcgpu_eval_rotden", "pimcgpu_eval_vcord", "pimcgpu_eval_caleng",
     "pimcgpu_pot_energy_slice", "pimcgpu_rng_draws", "pimcgpu_fp64_peak", "pimcgpu_host_spline",
@@ -101,6 +101,7 @@ def lib():
         L.pimcgpu_steps.argtypes = [C.c_long]
         L.pimcgpu_rng_draws.argtypes = [C.c_long, C.c_int, c_dp]
         L.pimcgpu_accum_download.argtypes = [c_dp, C.c_long]
+        L.pimcgpu_accum_download_begin.argtypes = [c_dp, C.c_long]
         L.pimcgpu_accum_offset.restype = C.c_long
         L.pimcgpu_checkpoint_bytes.restype = C.c_long
         L.pimcgpu_accum_offset.argtypes = [C.c_char_p]
@@ -435,6 +436,14 @@ class PimcGpu:
         """accumulator buffer into a caller-owned array (e.g. pinned, reused every block)"""
         self.L.pimcgpu_accum_device_ptr()          # folds the move counters into the buffer
         _ck(self.L.pimcgpu_accum_download(_dp(out), C.c_long(len(out))))
+
+    def accum_download_begin(self, out):
+        """queue the copy of the accumulator buffer into a caller-owned (pinned) array; accum_download_end() waits for it.
+        The buffer is taken as it stands (pimcgpu_accum_device_ptr folded the move counters in, an all-reduce may have followed)."""
+        _ck(self.L.pimcgpu_accum_download_begin(_dp(out), C.c_long(len(out))))
+
+    def accum_download_end(self):
+        _ck(self.L.pimcgpu_accum_download_end())
 
     def accum_reset(self):
         _ck(self.L.pimcgpu_accum_reset())

@@ -446,26 +446,39 @@ def test_split_phase_transfers_equal_the_synchronous_calls(pkg):
         G = pkg.gpu.PimcGpu(cfg, nchains=C)
         G.seed((41, 42, 43, 44, 45, 46))
         hc = [x.copy() for x in sets]; ha = [x.copy() for x in angs]
+        accs = []
         if split:
+            acc = np.zeros(G.accum_layout()["n_total"])
             G.upload_begin(hc[0], ha[0])
             for k in range(6):
                 cur, oth = k % 2, 1 - k % 2
                 G.upload_commit()
+                G.accum_reset()
                 G.steps(7, sync=False)
+                G.measure()
+                G.L.pimcgpu_accum_device_ptr()
+                G.accum_download_begin(acc)              # the sums first, the configuration behind them
                 if k > 0:
                     G.download_end()
                 G.upload_begin(hc[oth], ha[oth])
                 G.download_begin(hc[cur], ha[cur])
+                G.accum_download_end()
+                accs.append(acc.copy())
             G.download_end()
             G.upload_commit()
         else:
             for k in range(6):
                 cur = k % 2
                 G.upload_all(hc[cur], ha[cur])
+                G.accum_reset()
                 G.steps(7)
+                G.measure()
+                accs.append(G.accum_download()[0])
                 G.download_rows_into(hc[cur], ha[cur])
-        results.append((hc, ha, G.counters()))
+        results.append((hc, ha, G.counters(), accs))
         G.close()
+    for a, b in zip(results[0][3], results[1][3]):
+        assert np.array_equal(a, b) and np.abs(a).sum() > 0
     for a, b in zip(results[0][0], results[1][0]):
         assert np.array_equal(a, b)
     for a, b in zip(results[0][1], results[1][1]):
