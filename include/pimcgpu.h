@@ -142,7 +142,8 @@ int pimcgpu_steps(long nsteps);
 int pimcgpu_sync(void);
 long pimcgpu_step_counter(void);                   /* passTotal of mc_main.cc:346              */
 /* launch geometry chosen by pimcgpu_init: out8 = {ctas_per_chain, threads_per_cta, team, rot_group, smem bytes,
- * rotor kind, clusters the device can keep resident at once, nchains}                                         */
+ * move-kernel variant (rotor kind 0/1/2; +8: free-running rotational sweeps of a top whose chain lives in one CTA),
+ * clusters the device can keep resident at once, nchains}                                                     */
 int pimcgpu_geometry(int *out8);
 
 /* ---- estimators: the device part of MCGetAverage (mc_main.cc:551-646): GetKinEnergy,

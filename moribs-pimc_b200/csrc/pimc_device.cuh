@@ -94,6 +94,7 @@ struct Params {
    // translational sweeps, so between two of them every (slice, partner) term keeps its unit vector (p_j - p_g)/r, its
    // radial cell row and its radial weight; a rotational proposal only changes cos(theta) = n.u
    int rot_run;                  // linear rotor, several CTAs per chain: free-running rotational sweeps (rot_run), contiguous slice blocks per CTA
+   int rot_run_cta;              // a top whose chain lives in one CTA: free-running sweeps through shared memory (rot_run_cta)
    unsigned long long *rot_ll;   // [c][Q][8] rot_run: axis hand-over records (rot_ll_publish), zeroed at every launch
    int mol_piped;                // whole-path sweep with one cross-CTA hand-over per atom (molecular_sweep_piped)
    int bis_piped;                // two-warp teams: bisection sweep software-pipelined over the atoms (bisection_sweep_piped)

@@ -66,6 +66,7 @@ struct Ctx {
    unsigned gmask;            // lanes of this thread's rot group inside its warp (all lanes when the group fills or spans warps)
    SmallTables t;
    double *team_buf;   // shared: this thread's team scratch (segment positions, unit normals, stream cache, partial sums)
+   volatile int *rot_done;   // shared: rot_run_cta, sweeps completed by every rot slice of the chain in this launch
    double *red;        // shared: 40 doubles
    RotSlot *slot;      // shared: this thread's rot group slot (thread-private storage when the group is one thread)
    double *part;       // shared: per-warp partial sums (new, old) of this thread's rot group, used when it spans warps
@@ -1619,6 +1620,98 @@ __device__ void rot_run(const Params &p, Ctx &x, int type, int nrun, int *err)
 }
 
 // ---------------------------------------------------------------------------------------------
+// The same free-running stretch for a top whose chain lives in ONE CTA (C1-C3): every slice has its rot group, its slot in
+// shared memory holds the current rotation matrix, and the hand-over is a per-slice sweep count next to the slots
+// (volatile shared memory + __threadfence_block).  rot_sweep_pipe runs such a chain in three CTA-wide stages per sweep
+// (sums | even decisions | odd decisions, a barrier after each: every stage as slow as its slowest slice and nothing
+// overlapping); here a slice's proposal and sums run while its neighbours decide.  Draws, sums, the order of the
+// decisions seen by every slice, acceptance and commit are those of rot_sweep_pipe.
+// ---------------------------------------------------------------------------------------------
+template <int KIND>
+__device__ void rot_run_cta(const Params &p, Ctx &x, int type, int nrun, int *err)
+{
+   const int c = x.c, Q = p.Q, G = x.G, m = 0;
+   const int g = p.first[type];
+   // the even slices go to the first half of the rot groups, the odd ones to the second: the groups that share a warp are
+   // in the same phase (a polling group and a working one in one warp take turns at the warp's issue slots)
+   const int ls = x.grp;
+   const bool active = ls < Q;
+   const int q = active ? ((ls < Q / 2) ? 2 * ls : 2 * (ls - Q / 2) + 1) : 0;
+   RotSlot *sl = x.slot + q;
+   int q0 = q - 1, q2 = q + 1;
+   if (q0 < 0) q0 += Q;
+   if (q2 >= Q) q2 -= Q;
+   volatile int *done = x.rot_done;
+   if (active)
+   for (int it = 0; it < nrun; it++) {
+      const int n = x.rot_iter + it;
+      if (x.gl == 0) {
+         Mrg rs;
+         mrg_load(rs, x.rrng + q * 6);
+         double r1 = mrg_u01(rs), r2 = mrg_u01(rs), r3 = mrg_u01(rs), r4 = r3;
+         if ((KIND & 3) == 2) r4 = mrg_u01(rs);
+         mrg_store(rs, x.rrng + q * 6);
+         const int epoch = p.pos_epoch[c];
+         double cost = sl->cur[0], phi = sl->cur[1], chi = sl->cur[2];
+         rot_propose<KIND>(p, type, r1, r2, r3, cost, phi, chi, sl->a);
+         sl->u4 = r4; sl->cost = cost; sl->phi = phi; sl->chi = chi;
+         sl->epoch = epoch;
+         sl->need_old = (sl->vep != epoch) ? 1 : 0;
+         sl->bad = 0;
+      }
+      group_sync(x);
+      double vnew = rot_potential<KIND>(p, x, g, q, sl->a), vold = 0.0;
+      if (sl->need_old) vold = rot_potential<KIND>(p, x, g, q, sl->b);
+      const int gw = (G < 32) ? G : 32;
+      for (int o = gw >> 1; o > 0; o >>= 1) { vnew += __shfl_xor_sync(x.gmask, vnew, o); vold += __shfl_xor_sync(x.gmask, vold, o); }
+      if (G > 32 && (x.tid & 31) == 0) { x.part[2 * (x.gl >> 5)] = vnew; x.part[2 * (x.gl >> 5) + 1] = vold; }
+      // odd slices need this sweep's even decisions, even slices the previous sweep's odd ones
+      if (x.gl < 2) {
+         const int target = (q & 1) ? n + 1 : n;
+         const volatile int *f = done + (x.gl == 0 ? q0 : q2);
+         while (*f < target) { }
+      }
+      // groups that share a warp go on together: lanes that left the poll at different times would otherwise run the rest
+      // of the sweep as separate paths of the warp, one after the other
+      if (G < 32) __syncwarp(); else group_sync(x);
+      __threadfence_block();
+      for (int i = x.gl; i < 4; i += G) {
+         int bad = 0;
+         sl->rho[i] = rot_density<KIND>(p, x.t, c, q0, q2, m, i, sl->b, sl->a, &bad, x.slot[q0].b, x.slot[q2].b);
+         if (bad) { if (G == 1) sl->bad |= bad; else atomicOr(&sl->bad, bad); }
+      }
+      group_sync(x);
+      if (x.gl == 0) {
+         if (G > 32) {
+            vnew = 0.0; vold = 0.0;
+            for (int w = 0; w < (G >> 5); w++) { vnew += x.part[2 * w]; vold += x.part[2 * w + 1]; }
+         }
+         if (!sl->need_old) vold = sl->vcache;
+         int bad = sl->bad;
+         bool acc = rot_accept<KIND>(p, sl->rho, vnew, vold, sl->u4, &bad);
+         if (bad) { acc = false; atomicOr(err, bad); }
+         sl->vcache = acc ? vnew : vold;
+         sl->vep = sl->epoch;
+         if (acc) {
+            #pragma unroll
+            for (int i = 0; i < ((KIND & 3) == 2 ? 9 : 3); i++) sl->b[i] = sl->a[i];
+            sl->cur[0] = sl->cost; sl->cur[1] = sl->phi; sl->cur[2] = sl->chi;
+         }
+         __threadfence_block();
+         done[q] = n + 1;                                 // the neighbours may go on; the global copy of the angles follows
+         double *cn = counter_ptr(p, c, type, 2);
+         atomicAdd(cn, 1.0);
+         if (acc) {
+            atomicAdd(cn + 1, 1.0);
+            rot_commit<KIND>(p, c, q, m, sl->cost, sl->phi, sl->chi);
+         }
+      }
+   }
+   x.rot_iter += nrun;
+   __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
 // the persistent kernel
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void stage_tables(const Params &p, SmallTables &t, double *&cursor)
@@ -1742,6 +1835,10 @@ pimc_steps_kernel(const __grid_constant__ Params p, long t0, long nsteps, int *e
          sl->gep = -1;
          if (((KIND & 7) == 1) && p.rot_run) rot_ll_publish(p.rot_ll + ((size_t)x.c * p.Q + q) * 8, sl->b, 0);
       }
+      if (KIND & 8) {
+         x.rot_done = reinterpret_cast<volatile int *>(x.slot + nown);
+         for (int i = x.tid; i < p.Q; i += blockDim.x) x.rot_done[i] = 0;
+      }
       __syncthreads();
    } else x.slot = reinterpret_cast<RotSlot *>(cursor) + x.grp;      // one slot per rot group
 
@@ -1759,8 +1856,9 @@ pimc_steps_kernel(const __grid_constant__ Params p, long t0, long nsteps, int *e
       toff[type] = time / tnseg[type];
    }
    const bool use_run = ((KIND & 7) == 1) && piped && p.rot_run;
+   const bool use_run_cta = (KIND & 8) != 0;             // the variant is only launched where it applies (pimcgpu_init)
    for (long s = 0; s < nsteps; s++) {
-      if (use_run) {
+      if (use_run || use_run_cta) {
          // translational sweeps of this step, then every rotational sweep up to the next translational one in a single
          // free-running stretch (rot_run): the rotor is the last species, so its sweep closes the step
          for (int type = 0; type < p.ntypes; type++) {
@@ -1781,7 +1879,8 @@ pimc_steps_kernel(const __grid_constant__ Params p, long t0, long nsteps, int *e
             if (tr) break;
             nrun++;
          }
-         rot_run<KIND>(p, x, p.imtype, nrun, err);
+         if (use_run) rot_run<KIND>(p, x, p.imtype, nrun, err);
+         else if (KIND & 8) rot_run_cta<KIND>(p, x, p.imtype, nrun, err);
          for (int k = 0; k < nrun; k++) {
             if (++time == p.P) time = 0;
             for (int type = 0; type < p.ntypes; type++) {
@@ -1813,7 +1912,8 @@ pimc_steps_kernel(const __grid_constant__ Params p, long t0, long nsteps, int *e
             else bisection_sweep<KIND>(p, x, type, toff[type]);
          }
          if ((KIND & 3) != 0 && type == p.imtype && p.Q > 0) {
-            if (piped) {
+            if (KIND & 8) { }                             // free-running variant: every sweep goes through rot_run_cta above
+            else if (piped) {
                rot_sweep_pipe<KIND>(p, x, type, err);
                // a translational sweep (or the end of the launch) needs every decision of this sweep: full barrier
                if ((s == nsteps - 1 || type != p.ntypes - 1 || next_trans) && p.cpc > 1) chain_sync(p, x);

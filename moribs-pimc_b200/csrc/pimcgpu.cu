@@ -197,7 +197,7 @@ size_t smem_bytes(const Params &p, int threads)
    d += 2 * (size_t)(threads / 32);
    if (p.rot_fused) d += 3 * (size_t)((p.Q + p.cpc - 1) / p.cpc);
    size_t bytes = d * sizeof(double);
-   if (p.rot_fused) bytes += (size_t)((p.Q + p.cpc - 1) / p.cpc) * sizeof(RotSlot);
+   if (p.rot_fused) bytes += (size_t)((p.Q + p.cpc - 1) / p.cpc) * sizeof(RotSlot) + (p.rot_run_cta ? (size_t)p.Q * sizeof(int) : 0);
    else if (p.rot_group > 1) bytes += (size_t)(threads / p.rot_group) * sizeof(RotSlot);
    if (p.worm_on) bytes += 16 + worm_scratch_bytes(p.N);
    return bytes;
@@ -209,9 +209,10 @@ void est_shapes(dim3 &g_rcf, dim3 &b_rcf)
    g_rcf = dim3((G.p.Q + 127) / 128, G.p.nchains);
 }
 
-// the step kernel variant: rotor kind in bits 0-1, worm in bit 2
-const void *steps_kernel(int kind, int worm)
+// the step kernel variant: rotor kind in bits 0-1, worm in bit 2, free-running sweeps of a one-CTA top in bit 3
+const void *steps_kernel(int kind, int worm, int run_cta = 0)
 {
+   if (run_cta && kind == 2 && !worm) return (const void *)pimc_steps_kernel<10>;      // bit 3: free-running sweeps of a one-CTA top
    switch (kind + 4 * (worm ? 1 : 0)) {
       case 0: return (const void *)pimc_steps_kernel<0>;
       case 1: return (const void *)pimc_steps_kernel<1>;
@@ -591,6 +592,8 @@ int pimcgpu_init(const pimcgpu_system *sys, const pimcgpu_tables *tab)
       if (dalloc(&p.rot_ll, C * p.Q * 8)) return 1;
       p.rot_run = 1;
    }
+   p.rot_run_cta = (p.rot_fused && cpc == 1 && p.imtype == p.ntypes - 1 && p.molecule[p.imtype] == 2 && !p.worm_on && p.Q >= 2 && p.Q % 2 == 0 &&
+                    p.Q <= threads / p.rot_group && !getenv("PIMC_NO_ROT_RUN")) ? 1 : 0;
    // geometry cache of the rotor-atom terms (rot_potential_cached): one linear rotor among atoms, pipelined sweep, no worm
    p.geo_on = 0;
    p.geo_hint = getenv("PIMC_GEO_HINT") ? atoi(getenv("PIMC_GEO_HINT")) : 0;
@@ -603,7 +606,7 @@ int pimcgpu_init(const pimcgpu_system *sys, const pimcgpu_tables *tab)
    G.smem = smem_bytes(p, threads);
    if (G.smem > 227 * 1024) return fail("pimcgpu_init: %zu bytes of shared memory per CTA exceed the 227 KB limit", G.smem);
    G.kind = p.imtype >= 0 && p.Q > 0 ? p.molecule[p.imtype] : (p.imtype >= 0 ? p.molecule[p.imtype] : 0);
-   const void *kfun = steps_kernel(G.kind, p.worm_on);
+   const void *kfun = steps_kernel(G.kind, p.worm_on, p.rot_run_cta);
    CK(cudaFuncSetAttribute(kfun, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
    if (p.swbar) {
       int per_sm = 0;
@@ -1168,7 +1171,7 @@ int pimcgpu_steps(long nsteps)
    CK(cudaMemsetAsync(G.p.barrier, 0, (size_t)G.p.nchains * 32 * sizeof(unsigned), G.stream));
    if (G.p.rot_run) CK(cudaMemsetAsync(G.p.rot_ll, 0, (size_t)G.p.nchains * G.p.Q * 8 * sizeof(unsigned long long), G.stream));
    void *args[4] = {(void *)&G.p, (void *)&G.step, (void *)&nsteps, (void *)&G.d_err};
-   CK(cudaLaunchKernelExC(&cfg, steps_kernel(G.kind, G.p.worm_on), args));
+   CK(cudaLaunchKernelExC(&cfg, steps_kernel(G.kind, G.p.worm_on, G.p.rot_run_cta), args));
    G.step += nsteps;
    return 0;
 }
@@ -1189,12 +1192,12 @@ long pimcgpu_step_counter(void) { return G.step; }
 int pimcgpu_geometry(int *out8)
 {
    if (!G.live) return fail("pimcgpu_geometry: not initialised");
-   out8[0] = G.p.cpc; out8[1] = G.threads; out8[2] = G.p.team; out8[3] = G.p.rot_group; out8[4] = (int)G.smem; out8[5] = G.kind;
+   out8[0] = G.p.cpc; out8[1] = G.threads; out8[2] = G.p.team; out8[3] = G.p.rot_group; out8[4] = (int)G.smem; out8[5] = G.kind + (G.p.rot_run_cta ? 8 : 0);      // the move kernel's variant (template argument without the worm bit)
    cudaLaunchConfig_t cfg;
    cudaLaunchAttribute attr[1];
    launch_config(cfg, attr);
    int nclusters = -1;
-   const void *kfun = steps_kernel(G.kind, G.p.worm_on);
+   const void *kfun = steps_kernel(G.kind, G.p.worm_on, G.p.rot_run_cta);
    if (G.p.swbar) {
       int per_sm = 0, dev = 0;
       cudaDeviceProp prop;

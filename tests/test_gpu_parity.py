@@ -270,6 +270,34 @@ def test_geometry_independence(pkg):
             assert np.abs(c - ref[0]).max() < 1e-9 and np.abs(a - ref[1]).max() < 1e-9
 
 
+@pytest.mark.parametrize("name", ["C1", "C2", "C3"])
+def test_free_running_top_sweeps_equal_the_staged_ones(pkg, name, monkeypatch):
+    """A top whose chain lives in one CTA sweeps its rot slices free-running (rot_run_cta, kernel variant 10: a slice's
+    proposal and sums overlap its neighbours' decisions) instead of in three CTA-wide stages (rot_sweep_pipe).  Same draws,
+    same sums, same order of decisions seen by every slice: the trajectories are identical bit for bit, so every statistical
+    and oracle comparison made with either path holds for the other."""
+    cfg = make(pkg, name)
+    s = cfg.system
+    out = []
+    for staged in (False, True):
+        if staged:
+            monkeypatch.setenv("PIMC_NO_ROT_RUN", "1")
+        else:
+            monkeypatch.delenv("PIMC_NO_ROT_RUN", raising=False)
+        G = pkg.gpu.PimcGpu(cfg, nchains=3, ctas_per_chain=1)
+        G.seed((11, 12, 13, 14, 15, 16))
+        G.steps(2 * s.P + 3)                       # translational sweeps in between: the stretches restart
+        G.steps(5)                                 # a second launch picks the counters up again
+        st = [G.download(c)[:2] for c in range(3)]
+        out.append((st, G.counters(), G.geometry()))
+        G.close()
+    assert out[0][2]["kind"] == 10 and out[1][2]["kind"] == 2 and out[0][2]["ctas_per_chain"] == 1      # variant 10 = top, free-running
+    for (c0, a0), (c1, a1) in zip(out[0][0], out[1][0]):
+        assert np.array_equal(c0, c1) and np.array_equal(a0, a1)
+    assert np.array_equal(out[0][1][0], out[1][1][0]) and np.array_equal(out[0][1][1], out[1][1][1])
+    assert out[0][1][1][-1][2] > 0                  # rotations were accepted
+
+
 def test_permuted_world_lines_exchange_paths(pkg):
     """BOSE species with a non-identity permutation: bisection segments that cross beta continue on PIndex[atom],
     whole-path moves shift complete cycles, the kinetic estimator closes each path on its successor (a3, a4, a14)."""
