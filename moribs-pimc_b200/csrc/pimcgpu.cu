@@ -543,7 +543,10 @@ int pimcgpu_init(const pimcgpu_system *sys, const pimcgpu_tables *tab)
          threads = (int)std::min<long>(512, std::max<long>(64, ((per + 31) / 32) * 32));
       }
       const int per_cta = (p.Q + cpc - 1) / std::max(1, cpc);
-      if (p.rot_fused && cpc == 1 && top && threads / std::max(1, per_cta) < 4 && !getenv("PIMC_FORCE_FUSED_ROT")) { p.rot_fused = 0; continue; }
+      // ... unless the sweeps run free (rot_run_cta): there a slice's sums overlap its neighbours' decisions and two threads per
+      // slice are enough (C3: 940 vs 783 M bead-updates/s)
+      const bool run_cta = top && cpc == 1 && p.imtype == p.ntypes - 1 && !p.worm_on && p.Q >= 2 && threads >= p.Q && !getenv("PIMC_NO_ROT_RUN");
+      if (p.rot_fused && cpc == 1 && top && threads / std::max(1, per_cta) < 4 && !run_cta && !getenv("PIMC_FORCE_FUSED_ROT")) { p.rot_fused = 0; continue; }
       break;
    }
    if (threads % 32 || threads > PIMC_MAX_THREADS || threads < 32) return fail("pimcgpu_init: threads_per_cta must be a multiple of 32 in [32,%d]", PIMC_MAX_THREADS);
