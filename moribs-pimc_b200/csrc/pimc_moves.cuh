@@ -614,7 +614,22 @@ __device__ void bisection_sweep(const Params &p, Ctx &x, int type, int off)
                   D += pair_diff<KIND>(p, x.t, c, g, pn, po, j, sl);
                }
             }
-            if (alive) {
+            if (alive && !fast_atoms<KIND>(p, type)) {
+               // general pair terms (tops, rotors, minimum image, worm masks): the (midpoint, partner) pairs of the level are
+               // dealt flat over the team -- a system of two particles (C1) has ONE partner per midpoint, and sixteen
+               // midpoints in turn on one lane was most of its sweep
+               for (int i = x.lane_t; i < nmid * N; i += T) {
+                  const int m = i / N, j = i - m * N;
+                  const int t1 = half + m * lss;
+                  const int sl = (s0 + t1) % P;
+                  const int g = (s0 + t1 >= P) ? gB : gA;
+                  if (j == g || !partner_on_line<KIND>(p, c, j, sl)) continue;
+                  double po[3], pn[3];
+                  #pragma unroll
+                  for (int d = 0; d < 3; d++) { po[d] = p.pos[pos_index(p, c, sl, d, g)]; pn[d] = nx[t1 * 3 + d]; }
+                  D += pair_diff<KIND>(p, x.t, c, g, pn, po, j, sl);
+               }
+            } else if (alive) {
                // the warps of the team take the midpoints in turn; with fewer midpoints than warps several warps share one
                const int wpm = (nmid >= W) ? 1 : W / nmid, mstep = W / wpm;
                const int li = (x.tw % wpm) * x.wlanes + x.wl, stride = wpm * x.wlanes;
