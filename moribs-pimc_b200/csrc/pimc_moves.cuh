@@ -614,21 +614,42 @@ __device__ void bisection_sweep(const Params &p, Ctx &x, int type, int off)
                   D += pair_diff<KIND>(p, x.t, c, g, pn, po, j, sl);
                }
             }
-            if (alive && !fast_atoms<KIND>(p, type)) {
-               // general pair terms (tops, rotors, minimum image, worm masks): the (midpoint, partner) pairs of the level are
-               // dealt flat over the team -- a system of two particles (C1) has ONE partner per midpoint, and sixteen
-               // midpoints in turn on one lane was most of its sweep
-               for (int i = x.lane_t; i < nmid * N; i += T) {
-                  const int m = i / N, j = i - m * N;
-                  const int t1 = half + m * lss;
-                  const int sl = (s0 + t1) % P;
-                  const int g = (s0 + t1 >= P) ? gB : gA;
-                  if (j == g || !partner_on_line<KIND>(p, c, j, sl)) continue;
-                  double po[3], pn[3];
-                  #pragma unroll
-                  for (int d = 0; d < 3; d++) { po[d] = p.pos[pos_index(p, c, sl, d, g)]; pn[d] = nx[t1 * 3 + d]; }
-                  D += pair_diff<KIND>(p, x.t, c, g, pn, po, j, sl);
-               }
+            // general pair terms (tops, rotors, minimum image, worm masks) of a one-warp team with few partners: the
+            // (midpoint, partner) pairs of the level are evaluated flat over the team -- a system of two particles (C1) has ONE
+            // partner per midpoint, and sixteen midpoints in turn on one lane was most of its sweep -- into the spare half of
+            // the team's buffer; every lane then adds the terms it used to evaluate itself, in the order it used to (midpoints
+            // in turn, its partners in stride order), so the sum is the same bit for bit
+            double *esc = nx + (p.seg_max + 1) * 6 + p.seg_max * 3 + TEAM_EXTRA;
+            const bool flat = !fast_atoms<KIND>(p, type) && W == 1 && N < 2 * T && nmid * N <= (p.seg_max + 1) * 6;
+            if (flat) {
+               if (alive)
+                  for (int i = x.lane_t; i < nmid * N; i += T) {
+                     const int m = i / N, j = i - m * N;
+                     const int t1 = half + m * lss;
+                     const int sl = (s0 + t1) % P;
+                     const int g = (s0 + t1 >= P) ? gB : gA;
+                     double e = 0.0;
+                     if (j != g && partner_on_line<KIND>(p, c, j, sl)) {
+                        double po[3], pn[3];
+                        #pragma unroll
+                        for (int d = 0; d < 3; d++) { po[d] = p.pos[pos_index(p, c, sl, d, g)]; pn[d] = nx[t1 * 3 + d]; }
+                        e = pair_diff<KIND>(p, x.t, c, g, pn, po, j, sl);
+                     }
+                     esc[i] = e;
+                  }
+               team_sync(x);
+               if (alive)
+                  for (int m = 0; m < nmid; m++) {
+                     const int t1 = half + m * lss;
+                     const int sl = (s0 + t1) % P;
+                     const int g = (s0 + t1 >= P) ? gB : gA;
+                     double sm = 0.0;
+                     for (int j = x.lane_t; j < N; j += T) {
+                        if (j == g || !partner_on_line<KIND>(p, c, j, sl)) continue;
+                        sm += esc[m * N + j];
+                     }
+                     D += sm;
+                  }
             } else if (alive) {
                // the warps of the team take the midpoints in turn; with fewer midpoints than warps several warps share one
                const int wpm = (nmid >= W) ? 1 : W / nmid, mstep = W / wpm;
