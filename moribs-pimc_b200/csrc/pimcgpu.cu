@@ -596,7 +596,8 @@ int pimcgpu_init(const pimcgpu_system *sys, const pimcgpu_tables *tab)
       p.rot_run = 1;
    }
    p.rot_run_cta = (p.rot_fused && cpc == 1 && p.imtype == p.ntypes - 1 && p.molecule[p.imtype] == 2 && !p.worm_on && p.Q >= 2 && p.Q % 2 == 0 &&
-                    p.Q <= threads / p.rot_group && !getenv("PIMC_NO_ROT_RUN")) ? 1 : 0;
+                    p.Q <= threads / p.rot_group && (p.rot_group >= 32 || (p.Q * p.rot_group) % 32 == 0) &&      // whole warps: the groups of a warp re-converge with a full __syncwarp
+                    !getenv("PIMC_NO_ROT_RUN")) ? 1 : 0;
    // geometry cache of the rotor-atom terms (rot_potential_cached): one linear rotor among atoms, pipelined sweep, no worm
    p.geo_on = 0;
    p.geo_hint = getenv("PIMC_GEO_HINT") ? atoi(getenv("PIMC_GEO_HINT")) : 0;
